@@ -1,0 +1,230 @@
+"""The drop-in seam: a binder with the call signature of the reference's ``LoadKeOps`` objects.
+
+``pykeops.common.keops_io.keops_binder["nvrtc"]`` is looked up at call time by the reference's
+``GenredAutograd_base._forward`` (``pykeops/pykeops/torch/generic/generic_red.py:89-129``) and
+``KernelSolveAutograd.forward`` (``pykeops/pykeops/torch/operations.py:45-81``); an object with
+
+* constructor ``B(tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id, formula, aliases, nargs,
+  dtype, lang, optional_flags)`` (argument order of ``LoadKeOps.init``,
+  ``pykeops/pykeops/common/keops_io/LoadKeOps.py:33-46``),
+* ``.import_module() -> self`` and ``.genred_pytorch(device_args, ranges, nx, ny, nbatchdims, out,
+  *args) -> Tensor`` (``LoadKeOps.py:177-186,245-252``),
+* attributes ``.dimout`` and ``.tagIJ`` (``LoadKeOps.py:19-20``),
+
+is all they need.  :class:`LoadKeOpsB200` is that object, backed by the sm_100a code generator and
+``libkb200.so``; ``register_into_pykeops()`` installs it into an importable reference ``pykeops``.
+There is deliberately no CPU path: ``tagCPUGPU == 0`` raises.
+"""
+from __future__ import annotations
+
+import threading
+import types
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .formulas.parser import parse_reduction, parse_alias
+from .formulas.reductions import Reduction
+from .formulas.ir import FormulaError
+from .codegen.emit import generate, KernelSource
+from .runtime import plan, capi
+
+_binder_cache: Dict[tuple, "LoadKeOpsB200"] = {}
+_cache_lock = threading.RLock()
+
+
+def _normalise_aliases(aliases: Sequence[str]) -> List[str]:
+    """``"x = Vi(3)"`` -> ``"x=Var(k,3,0)"`` with k the list position (``LoadKeOps.py:47-64``)."""
+    out = []
+    for k, alias in enumerate(aliases):
+        if alias is None:
+            continue
+        name, var = parse_alias(alias, k)
+        ind, dim, cat = var.params
+        out.append(("%s=" % name if name else "") + "Var(%d,%d,%d)" % (ind, dim, cat))
+    return out
+
+
+class LoadKeOpsB200:
+    """Formula -> compiled sm_100a kernels -> asynchronous launch on the current torch stream."""
+
+    def __new__(cls, tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id_request, formula, aliases,
+                nargs, dtype, lang, optional_flags):
+        key = (tagCPUGPU, tag1D2D, tagHostDevice, bool(use_ranges), device_id_request, formula,
+               tuple(aliases), nargs, dtype, lang, tuple(sorted(optional_flags.items())))
+        with _cache_lock:
+            self = _binder_cache.get(key)
+            if self is None:
+                self = object.__new__(cls)
+                self._init(tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id_request, formula,
+                           aliases, nargs, dtype, lang, optional_flags)
+                _binder_cache[key] = self
+            return self
+
+    def _init(self, tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id_request, formula, aliases,
+              nargs, dtype, lang, optional_flags):
+        if tagCPUGPU == 0:
+            raise ValueError("[KeOps-B200] this engine has no CPU backend (backend='CPU' is not available).")
+        if tagHostDevice == 0:
+            raise ValueError("[KeOps-B200] input arrays must be CUDA tensors (GPU_*_host modes were dropped).")
+        if lang not in ("torch", "pytorch"):
+            raise ValueError("[KeOps-B200] only the torch binding is implemented.")
+        if dtype not in ("float32", "float64"):
+            raise ValueError("not implemented")
+        p = types.SimpleNamespace()
+        p.aliases_old = list(aliases)
+        p.aliases = _normalise_aliases(aliases)
+        p.red_formula_string = formula
+        p.dtype = dtype
+        p.lang = lang
+        p.nargs = nargs
+        p.tag1D2D = tag1D2D
+        p.tagCPUGPU, p.tagHostDevice = tagCPUGPU, tagHostDevice
+        p.use_ranges = bool(use_ranges)
+        p.device_id_request = device_id_request
+        p.sum_scheme = optional_flags.get("sum_scheme", "auto")
+        p.dtype_acc = optional_flags.get("dtype_acc", "auto")
+        p.use_fast_math = bool(optional_flags.get("use_fast_math", 1))
+        p.enable_chunks = optional_flags.get("enable_chunks", 1)
+        p.mult_var_highdim = optional_flags.get("multVar_highdim", 0)
+        if p.dtype_acc not in ("auto", "float32", "float64", "float16"):
+            raise ValueError('[KeOps] invalid value for option dtype_acc : should be one of "auto", "float16", "float32" or "float64".')
+        if dtype == "float64" and p.dtype_acc not in ("auto", "float64"):
+            raise ValueError("[KeOps] invalid parameter dtype_acc : should be 'float64' when dtype is 'float64'")
+
+        red: Reduction = parse_reduction(formula, p.aliases)
+        self.red = red
+        if p.sum_scheme == "auto":
+            p.sum_scheme = "block_sum" if red.kind in ("Sum", "LSE") else "direct_sum"
+        p.tagI = red.tagI
+        p.tagZero = 1 if red.is_zero else 0
+        p.dim, p.dimred = red.dim, red.dimred
+        p.reduction_op = formula.split("(")[0]
+        p.axis = 1 - red.tagI
+        cfg = plan.default_config(red, dtype)
+        self.ks: KernelSource = generate(red, dtype, nargs, cfg, use_fast_math=p.use_fast_math,
+                                         sum_scheme=p.sum_scheme, dtype_acc=p.dtype_acc)
+        if self.ks.is_zero:
+            p.tagZero = 1
+        # metadata in the reference's *post-swap* convention (``LoadKeOps.py:151-153``): indsi are
+        # always the cat-0 variables, whatever tagI is.
+        vs = sorted(red.variables(), key=lambda v: v.params[0])
+        p.indsi = tuple(v.params[0] for v in vs if v.params[2] == 0)
+        p.indsj = tuple(v.params[0] for v in vs if v.params[2] == 1)
+        p.indsp = tuple(v.params[0] for v in vs if v.params[2] == 2)
+        p.dimsx = tuple(v.params[1] for v in vs if v.params[2] == 0)
+        p.dimsy = tuple(v.params[1] for v in vs if v.params[2] == 1)
+        p.dimsp = tuple(v.params[1] for v in vs if v.params[2] == 2)
+        p.dimy = sum(d for _, d in self.ks.col_vars)
+        self.params = p
+        self.dimout = p.dim
+        self.tagIJ = p.tagI
+        self._vars = {v.params[0]: (v.params[1], v.params[2]) for v in vs}
+        self._loaded: Dict[int, plan.LoadedKernel] = {}
+
+    # ---- reference-compatible surface ----------------------------------------------------------
+    def import_module(self):
+        return self
+
+    def reset(self):
+        self._loaded.clear()
+
+    def _kernel(self, device: int) -> plan.LoadedKernel:
+        lk = self._loaded.get(device)
+        if lk is None:
+            lk = plan.load_kernel(self.ks, self.params.use_fast_math and self.params.dtype == "float32", device)
+            self._loaded[device] = lk
+        return lk
+
+    def genred(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
+        p = self.params
+        if ranges:
+            raise NotImplementedError("[KeOps-B200] block-sparse `ranges` are not implemented yet.")
+        if nbatchdims:
+            raise NotImplementedError("[KeOps-B200] batch dimensions are not implemented yet.")
+        if len(args) != p.nargs:
+            raise ValueError("[KeOps-B200] expected %d arguments, got %d" % (p.nargs, len(args)))
+        tdtype = torch.float32 if p.dtype == "float32" else torch.float64
+        dev = None
+        for k, a in enumerate(args):
+            if not isinstance(a, torch.Tensor) or not a.is_cuda:
+                raise ValueError("[KeOps-B200] argument %d must be a CUDA tensor (there is no CPU fallback)." % k)
+            if a.dtype != tdtype:
+                raise ValueError("[KeOps-B200] argument %d has dtype %s, expected %s" % (k, a.dtype, tdtype))
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise ValueError("[KeOps] Input arrays must be all located on the same device.")
+        if dev is None:
+            raise ValueError("[KeOps-B200] at least one argument is required")
+        nx, ny = int(nx), int(ny)
+        # shape checks (subset of Sizes<T>, keopscore/keopscore/include/Sizes.h:262-411)
+        fixed = []
+        for ind, (dim, cat) in self._vars.items():
+            a = args[ind]
+            if cat == 2:
+                if a.numel() != dim:
+                    raise ValueError("[KeOps] Wrong value of the 'vector size' dimension for arg number %d : is %d but should be %d"
+                                     % (ind, a.numel(), dim))
+            else:
+                n_expected = nx if cat == 0 else ny
+                if a.dim() != 2 or a.shape[1] != dim:
+                    raise ValueError("[KeOps] Wrong value of the 'vector size' dimension 1 for arg number %d : is %s but should be %d"
+                                     % (ind, tuple(a.shape), dim))
+                if a.shape[0] != n_expected:
+                    raise ValueError("[KeOps] Wrong value of the '%s' dimension 0 for arg number %d : is %d but should be %d"
+                                     % ("ij"[cat], ind, a.shape[0], n_expected))
+        args = tuple(a if a.is_contiguous() else a.contiguous() for a in args)
+
+        nrow, ncol = (nx, ny) if p.tagI == 0 else (ny, nx)
+        shapeout = (nrow, p.dim)
+        if out is None:
+            out = torch.empty(shapeout, dtype=tdtype, device=dev)
+        else:
+            if tuple(out.shape) != shapeout or out.dtype != tdtype or out.device != dev or not out.is_contiguous():
+                raise ValueError("[KeOps-B200] `out` must be a contiguous %s tensor of shape %s on %s"
+                                 % (tdtype, shapeout, dev))
+        if p.tagZero:
+            out.zero_()
+            return out
+        if nrow == 0:
+            return out
+        lk = self._kernel(dev.index if dev.index is not None else torch.cuda.current_device())
+        ks = self.ks
+        rows_per_block = ks.cfg.T * ks.cfg.R
+        esz = 4 if p.dtype == "float32" else 8
+        if p.tag1D2D == 1 or True:
+            nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ,
+                                                  lk.sm_count * lk.blocks_per_sm, ks.dimpart, esz)
+        ws = None
+        if nsplit > 1:
+            ws = torch.empty(nsplit * nrow * ks.dimpart, dtype=tdtype, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            capi.genred_launch(lk.fn_reduce, lk.fn_combine, stream, nrow, ncol, rows_per_block, ks.cfg.T,
+                               nsplit, max(col_chunk, 1), out.data_ptr(), ws.data_ptr() if ws is not None else 0,
+                               [a.data_ptr() for a in args])
+        if ws is not None:
+            ws.record_stream(torch.cuda.current_stream(dev))
+        self.last_launch = dict(nsplit=nsplit, col_chunk=col_chunk, grid_x=-(-nrow // rows_per_block),
+                                regs=lk.regs, blocks_per_sm=lk.blocks_per_sm)
+        return out
+
+    genred_pytorch = genred
+
+
+def get_binder(formula: str, aliases: Sequence[str], nargs: int, dtype: str, optional_flags: Optional[dict] = None,
+               device_id: int = -1) -> LoadKeOpsB200:
+    flags = dict(dtype_acc="auto", sum_scheme="auto", use_fast_math=1, enable_chunks=1, multVar_highdim=0)
+    if optional_flags:
+        flags.update(optional_flags)
+    return LoadKeOpsB200(1, 0, 1, False, device_id, formula, list(aliases), nargs, dtype, "torch", flags)
+
+
+def register_into_pykeops():
+    """Install this engine as the GPU binder of an importable reference ``pykeops``:
+    ``keops_binder['nvrtc'] = LoadKeOpsB200`` (``pykeops/pykeops/common/keops_io/__init__.py:6-13``)."""
+    from pykeops.common import keops_io  # type: ignore
+
+    keops_io.keops_binder["nvrtc"] = LoadKeOpsB200
+    return keops_io.keops_binder

@@ -1,0 +1,738 @@
+"""CUDA source emitter: reduction descriptor -> one sm_100a translation unit.
+
+Replaces the reference's kernel skeletons ``GpuReduc1D`` / ``GpuReduc2D``
+(``keopscore/keopscore/mapreduce/gpu/GpuReduc1D.py:47-95``, ``GpuReduc2D.py:85-199``).  The design is
+different:
+
+* a thread owns ``R`` output rows held as packed f32x2 register pairs, so one FADD2/FMUL2/FFMA2
+  issue slot serves two (i,j) pairs and one shared-memory read of ``y_j`` serves ``R`` pairs;
+* the streamed operand is staged with ``cp.async`` into a double-buffered tile (one barrier per
+  tile instead of two), in one padded row per ``j`` so it is read back with broadcast ``LDS.128``;
+* everything that does not depend on both indices is hoisted out of the pair loop;
+* the column range can be split over ``gridDim.y`` (bounded temporary, merged by a second tiny
+  kernel) so that the grid can be shaped to the 148 SMs whatever ``M`` is.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from ..formulas.ir import Node, FormulaError
+from ..formulas.reductions import Reduction
+from .lower import Lowerer
+from .scalar import Graph, SNode, SV, C, P, I, J, IJ, topo_order
+
+GENERATOR_VERSION = "kb200-gen-1"
+
+_PRELUDE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "kb200_device.cuh")
+_prelude_cache: Optional[str] = None
+
+
+def prelude() -> str:
+    global _prelude_cache
+    if _prelude_cache is None:
+        with open(_PRELUDE_PATH) as f:
+            _prelude_cache = f.read()
+    return _prelude_cache
+
+
+@dataclass(frozen=True)
+class KernelConfig:
+    T: int = 256        # threads per CTA
+    R: int = 4          # output rows per thread
+    TJ: int = 256       # streamed rows per shared-memory tile
+    unroll: int = 8     # unroll factor of the pair loop
+    min_blocks: int = 1  # __launch_bounds__ second argument
+
+    def key(self) -> str:
+        return "T%d_R%d_TJ%d_U%d_B%d" % (self.T, self.R, self.TJ, self.unroll, self.min_blocks)
+
+
+@dataclass
+class KernelSource:
+    source: str
+    kernel_name: str
+    combine_name: str
+    cfg: KernelConfig
+    dtype: str
+    tagI: int
+    dim: int               # output reals per row
+    dimred: int            # accumulator size reported to callers (reference convention)
+    dimpart: int           # reals per row in a split-j partial
+    nargs: int
+    row_vars: List[Tuple[int, int]]   # (arg index, dim) of output-side variables
+    col_vars: List[Tuple[int, int]]   # streamed variables
+    par_vars: List[Tuple[int, int]]
+    stride: int            # reals per staged row
+    smem_bytes: int
+    is_zero: bool = False
+    hash: str = ""
+
+
+# ------------------------------------------------------------------------------------------
+# fusion / sign-resolution pass on the scalar DAG
+# ------------------------------------------------------------------------------------------
+class _Rewriter:
+    """Contracts add/sub of products into fma and resolves pending negations where they are free."""
+
+    def __init__(self, g: Graph):
+        self.g = g
+        self.memo: Dict[int, SNode] = {}
+
+    def vmode(self, n: SNode) -> bool:
+        return n.cls in (I, IJ)
+
+    def cheap_neg(self, operand: SNode, user_cls: int, user_v: bool) -> bool:
+        if not user_v:
+            return True  # scalar SASS has negate modifiers on every FP operand
+        return operand.op == "const" or operand.cls < user_cls
+
+    def neg_of(self, n: SNode) -> SNode:
+        """Rewritten node for -(n), n being an *original* node."""
+        g = self.g
+        if n.op == "const":
+            return g._mk("const", (), -n.val, C)
+        if n.op == "neg":
+            return self.rw(n.args[0])
+        if n.op == "sub":
+            p, q = n.args
+            return self._sub(q, p, n.cls)
+        v = self.vmode(n)
+        if n.op == "mul":
+            a, b = n.args
+            for x, y in ((a, b), (b, a)):
+                if x.op == "const" or (x.cls < n.cls) or not v:
+                    return g._mk("mul", (self.neg_of(x), self.rw(y)), None, n.cls)
+        return g._mk("neg", (self.rw(n),), None, n.cls)
+
+    def _add(self, x: SNode, y: SNode, cls: int) -> SNode:
+        g = self.g
+        cands = [a for a in (x, y) if a.op == "mul"]
+        if cands:
+            m = max(cands, key=lambda a: a.uid)
+            other = y if m is x else x
+            return g._mk("fma", (self.rw(m.args[0]), self.rw(m.args[1]), self.rw(other)), None, cls)
+        return g._mk("add", (self.rw(x), self.rw(y)), None, cls)
+
+    def _sub(self, p: SNode, q: SNode, cls: int) -> SNode:
+        """p - q with original nodes p, q."""
+        g = self.g
+        v = cls in (I, IJ)
+        if q.op == "mul":
+            c, d = q.args
+            for x, y in ((c, d), (d, c)):
+                if self.cheap_neg(x, cls, v):
+                    return g._mk("fma", (self.neg_of(x), self.rw(y), self.rw(p)), None, cls)
+        if p.op == "mul" and self.cheap_neg(q, cls, v):
+            return g._mk("fma", (self.rw(p.args[0]), self.rw(p.args[1]), self.neg_of(q)), None, cls)
+        return g._mk("sub", (self.rw(p), self.rw(q)), None, cls)
+
+    def rw(self, n: SNode) -> SNode:
+        out = self.memo.get(n.uid)
+        if out is not None:
+            return out
+        g = self.g
+        if n.op in ("const", "load"):
+            out = n
+        elif n.op == "add":
+            out = self._add(n.args[0], n.args[1], n.cls)
+        elif n.op == "sub":
+            out = self._sub(n.args[0], n.args[1], n.cls)
+        elif n.op == "neg":
+            out = self.neg_of(n.args[0])
+        else:
+            out = g._mk(n.op, tuple(self.rw(a) for a in n.args), n.val, n.cls)
+        self.memo[n.uid] = out
+        return out
+
+    def signed(self, sv: SV) -> SNode:
+        return self.neg_of(sv.n) if sv.neg else self.rw(sv.n)
+
+
+# ------------------------------------------------------------------------------------------
+# expression printing
+# ------------------------------------------------------------------------------------------
+def _lit(v: float, f64: bool) -> str:
+    if v != v:
+        return "(real)NAN"
+    if v in (float("inf"), float("-inf")):
+        return ("-" if v < 0 else "") + "KB_INF"
+    if f64:
+        return repr(float(v))
+    s = "%.9g" % v
+    if "." not in s and "e" not in s and "inf" not in s:
+        s += ".0"
+    return s + "f"
+
+
+_FN1 = {"rcp", "exp", "ex2", "log", "lg2", "sqrt", "rsqrt", "sin", "cos", "asin", "acos", "atan", "abs",
+        "sign", "step", "relu", "floor", "round0", "xlogx", "sinxdivx"}
+_FN2 = {"div", "atan2", "powf", "fmax", "fmin", "lt", "le", "eq", "ne"}
+_FN3 = {"sel_ge0", "clamp", "inrange", "mod"}
+
+
+class _Printer:
+    def __init__(self, f64: bool):
+        self.f64 = f64
+        self.names: Dict[int, str] = {}
+
+    def ref(self, n: SNode) -> str:
+        if n.op == "const":
+            return _lit(n.val, self.f64)
+        return self.names[n.uid]
+
+    def expr(self, n: SNode) -> str:
+        v = n.cls in (I, IJ)
+        sfx = "_v" if v else ""
+        a = [self.ref(x) for x in n.args]
+        op = n.op
+        if op in ("add", "sub", "mul"):
+            return "kb_%s%s(%s, %s)" % (op, sfx, a[0], a[1])
+        if op == "fma":
+            return "kb_fma%s(%s, %s, %s)" % (sfx, a[0], a[1], a[2])
+        if op == "neg":
+            return "kb_neg%s(%s)" % (sfx, a[0])
+        if op in _FN1 or op in _FN2 or op in _FN3:
+            return "kb_%s%s(%s)" % (op, sfx, ", ".join(a))
+        raise NotImplementedError("emit: unknown scalar op " + op)
+
+
+# ------------------------------------------------------------------------------------------
+# the generator
+# ------------------------------------------------------------------------------------------
+def _collect_vars(red: Reduction):
+    vs = {}
+    for v in red.variables():
+        ind, dim, cat = v.params
+        if ind in vs and vs[ind] != (dim, cat):
+            raise FormulaError("variable %d is used with inconsistent (dim, cat)" % ind)
+        vs[ind] = (dim, cat)
+    return vs
+
+
+def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast_math: bool = True,
+             sum_scheme: str = "block_sum", dtype_acc: str = "auto") -> KernelSource:
+    if dtype not in ("float32", "float64"):
+        raise ValueError("dtype %s is not implemented (float32 / float64 only)" % dtype)
+    f64 = dtype == "float64"
+    fast = bool(use_fast_math) and not f64
+    tagI = red.tagI
+    lpp = 1 if f64 else 2
+    if cfg.R % lpp != 0:
+        raise ValueError("R must be even for float32 kernels")
+
+    varinfo = _collect_vars(red)
+    for ind in varinfo:
+        if ind >= nargs:
+            raise FormulaError("formula uses Var(%d,...) but only %d arguments are declared" % (ind, nargs))
+    row_vars = sorted((ind, d) for ind, (d, c) in varinfo.items() if c == tagI)
+    col_vars = sorted((ind, d) for ind, (d, c) in varinfo.items() if c == 1 - tagI)
+    par_vars = sorted((ind, d) for ind, (d, c) in varinfo.items() if c == 2)
+
+    kind = red.kind
+    base = dict(cfg=cfg, dtype=dtype, tagI=tagI, dim=red.dim, dimred=red.dimred, nargs=nargs,
+                row_vars=row_vars, col_vars=col_vars, par_vars=par_vars)
+    if kind == "Zero":
+        return KernelSource(source="", kernel_name="", combine_name="", dimpart=0, stride=0, smem_bytes=0,
+                            is_zero=True, **base)
+
+    g = Graph(fast=fast, tagI=tagI)
+    L = Lowerer(g)
+    F = L(red.formula)
+    G = L(red.weight) if red.weight is not None else []
+    if kind == "Sum" and all(sv.const() == 0.0 for sv in F):
+        return KernelSource(source="", kernel_name="", combine_name="", dimpart=0, stride=0, smem_bytes=0,
+                            is_zero=True, **base)
+
+    rwt = _Rewriter(g)
+    # --- roots ------------------------------------------------------------------------------
+    # Sum / LSE weights accumulate |value| and apply the pulled-out sign at the very end.
+    acc_terms: List[Tuple[str, Tuple[SNode, ...], bool]] = []   # (mode, nodes, negative)
+    value_nodes: List[SNode] = []                               # materialised per-pair values
+    if kind == "Sum":
+        for sv in F:
+            acc_terms.append(_acc_term(rwt, sv))
+    elif kind == "LSE":
+        value_nodes = [rwt.signed(F[0])]
+        for sv in G:
+            acc_terms.append(_acc_term(rwt, sv))
+    else:
+        value_nodes = [rwt.signed(sv) for sv in F]
+
+    roots: List[SNode] = list(value_nodes)
+    for mode, nodes, _ in acc_terms:
+        roots.extend(nodes)
+    order = topo_order(roots)
+
+    pr = _Printer(f64)
+    stride = sum(d for _, d in col_vars)
+    stride = max(4, (stride + 3) // 4 * 4) if not f64 else max(2, (stride + 1) // 2 * 2)
+    col_off: Dict[int, int] = {}
+    off = 0
+    for ind, d in col_vars:
+        col_off[ind] = off
+        off += d
+
+    # --- statements per region ----------------------------------------------------------------
+    pre: List[str] = []      # before the loop: P scalars, I vectors
+    body_j: List[str] = []   # per streamed row: J scalars
+    body_ij: List[str] = []  # per pair
+    used_col: Dict[Tuple[int, int], str] = {}
+    for n in order:
+        if n.op == "const":
+            continue
+        if n.op == "load":
+            ind, comp, cat = n.val
+            if n.cls == P:
+                nm = "p%d_%d" % (ind, comp)
+                pre.append("const real %s = a%d[%d];" % (nm, ind, comp))
+            elif n.cls == I:
+                nm = "x%d_%d" % (ind, comp)
+                d = varinfo[ind][0]
+                pre.append("V %s; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) %s.l[q] = a%d[rowc[q] * %d + %d];"
+                           % (nm, nm, ind, d, comp))
+            else:
+                nm = "y%d_%d" % (ind, comp)
+                used_col[(ind, comp)] = nm
+            pr.names[n.uid] = nm
+            continue
+        prefix = {P: "p", I: "h", J: "s", IJ: "t", C: "c"}[n.cls]
+        nm = "%s%d" % (prefix, n.uid)
+        pr.names[n.uid] = nm
+        ty = "V" if n.cls in (I, IJ) else "real"
+        stmt = "const %s %s = %s;" % (ty, nm, pr.expr(n))
+        if n.cls in (C, P, I):
+            pre.append(stmt)
+        elif n.cls == J:
+            body_j.append(stmt)
+        else:
+            body_ij.append(stmt)
+
+    # loads of the staged row: vector loads of the padded row, then named components
+    vec = 2 if f64 else 4
+    vty = "double2" if f64 else "float4"
+    comp_names = ["x", "y", "z", "w"]
+    need_chunks = sorted({(col_off[ind] + comp) // vec for (ind, comp) in used_col})
+    row_loads = ["const %s q%d = yrow[%d];" % (vty, c, c) for c in need_chunks]
+    for (ind, comp), nm in sorted(used_col.items()):
+        pos = col_off[ind] + comp
+        row_loads.append("const real %s = q%d.%s;" % (nm, pos // vec, comp_names[pos % vec]))
+
+    W = _Writer()
+    hdr = _kernel_header(W, red, cfg, f64, fast, stride, nargs, varinfo)
+    kname, cname = "kb200_reduce", "kb200_combine"
+
+    red_code = _ReductionCode(red, pr, acc_terms, value_nodes, sum_scheme, dtype_acc, f64, fast)
+
+    # ---------------- main kernel ----------------
+    W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
+    W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s)"
+      % (kname, "".join(", const real* __restrict__ a%d" % k for k in range(nargs))))
+    W("{")
+    W.indent()
+    W("__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
+    W("const int tid = threadIdx.x;")
+    W("const long long row0 = (long long)blockIdx.x * (KB_T * KB_R) + tid;")
+    W("long long rowc[KB_R];")
+    W("KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) { long long r_ = row0 + (long long)q * KB_T; rowc[q] = r_ < nrow ? r_ : nrow - 1; }")
+    W("const long long jbeg = (long long)blockIdx.y * col_chunk;")
+    W("const long long jend = (jbeg + col_chunk < ncol) ? (jbeg + col_chunk) : ncol;")
+    W("// ---- hoisted: parameters and output-side (row) values")
+    for s in pre:
+        W(s)
+    W("// ---- accumulators")
+    red_code.declare(W)
+    W("// ---- stage the first tile")
+    _stage(W, col_vars, col_off, "jbeg", "0")
+    W("kb_cp_commit(); kb_cp_wait_all(); __syncthreads();")
+    W("int buf = 0;")
+    W("for (long long jt = jbeg; jt < jend; jt += KB_TJ) {")
+    W.indent()
+    W("if (jt + KB_TJ < jend) {")
+    W.indent()
+    _stage(W, col_vars, col_off, "jt + KB_TJ", "buf ^ 1")
+    W.dedent()
+    W("}")
+    W("kb_cp_commit();")
+    W("const int jn = (int)((jend - jt < KB_TJ) ? (jend - jt) : KB_TJ);")
+    red_code.tile_begin(W)
+    W("const %s* yrow = reinterpret_cast<const %s*>(&sm[buf][0]);" % (vty, vty))
+    W("#pragma unroll %d" % cfg.unroll)
+    W("for (int jr = 0; jr < jn; jr++, yrow += KB_STRIDE / %d) {" % vec)
+    W.indent()
+    for s in row_loads:
+        W(s)
+    for s in body_j:
+        W(s)
+    for s in body_ij:
+        W(s)
+    red_code.update(W)
+    W.dedent()
+    W("}")
+    red_code.tile_end(W)
+    W("kb_cp_wait_all(); __syncthreads();")
+    W("buf ^= 1;")
+    W.dedent()
+    W("}")
+    W("// ---- write back")
+    red_code.finalize(W)
+    W.dedent()
+    W("}")
+    W("")
+    # ---------------- combine kernel (merges split-j partials) ----------------
+    red_code.combine_kernel(W, cname)
+
+    src = hdr + W.text()
+    h = hashlib.sha256((GENERATOR_VERSION + src).encode()).hexdigest()[:16]
+    return KernelSource(source=src, kernel_name=kname, combine_name=cname, dimpart=red_code.dimpart,
+                        stride=stride, smem_bytes=2 * cfg.TJ * stride * (8 if f64 else 4), hash=h, **base)
+
+
+def _acc_term(rwt: _Rewriter, sv: SV):
+    """Decompose an accumulated value: ('fma', (a, b), neg) -> acc += a*b ; ('add', (v,), neg)."""
+    n = sv.n
+    if sv.const() == 0.0:
+        return ("zero", (), False)
+    if n.op == "mul":
+        return ("fma", (rwt.rw(n.args[0]), rwt.rw(n.args[1])), sv.neg)
+    return ("add", (rwt.rw(n),), sv.neg)
+
+
+class _Writer:
+    def __init__(self):
+        self.lines: List[str] = []
+        self.lvl = 0
+
+    def __call__(self, s: str = ""):
+        self.lines.append(("  " * self.lvl + s) if s else "")
+
+    def indent(self):
+        self.lvl += 1
+
+    def dedent(self):
+        self.lvl -= 1
+
+    def text(self) -> str:
+        return "\n".join(self.lines) + "\n"
+
+
+def _kernel_header(W, red, cfg, f64, fast, stride, nargs, varinfo) -> str:
+    lines = [
+        "// generated by keops_b200 (%s) -- do not edit" % GENERATOR_VERSION,
+        "// reduction: %s" % red.canonical(),
+        "#define KB_T %d" % cfg.T,
+        "#define KB_R %d" % cfg.R,
+        "#define KB_TJ %d" % cfg.TJ,
+        "#define KB_STRIDE %d" % stride,
+        "#define KB_F64 %d" % (1 if f64 else 0),
+        "#define KB_FAST %d" % (1 if fast else 0),
+        prelude(),
+        "",
+    ]
+    return "\n".join(lines)
+
+
+def _stage(W: _Writer, col_vars, col_off, jbase: str, buf: str):
+    """cp.async one tile of every streamed variable into sm[buf] (row-padded AoS)."""
+    for ind, d in col_vars:
+        W("for (int e = tid; e < KB_TJ * %d; e += KB_T) {" % d)
+        W.indent()
+        if d == 1:
+            W("const int jr_ = e; const int c_ = 0;")
+        else:
+            W("const int jr_ = e / %d; const int c_ = e - jr_ * %d;" % (d, d))
+        W("const long long j_ = (%s) + jr_;" % jbase)
+        W("const bool ok_ = j_ < jend;")
+        W("kb_cp_async(&sm[%s][jr_ * KB_STRIDE + %d + c_], a%d + (ok_ ? (j_ * %d + c_) : 0), ok_);"
+          % (buf, col_off[ind], ind, d))
+        W.dedent()
+        W("}")
+
+
+# ------------------------------------------------------------------------------------------
+# reduction-specific code
+# ------------------------------------------------------------------------------------------
+class _ReductionCode:
+    def __init__(self, red: Reduction, pr: _Printer, acc_terms, value_nodes, sum_scheme, dtype_acc, f64, fast):
+        self.red, self.pr = red, pr
+        self.kind = red.kind
+        self.acc_terms, self.values = acc_terms, value_nodes
+        self.f64, self.fast = f64, fast
+        self.scheme = sum_scheme if self.kind in ("Sum", "LSE") else "direct_sum"
+        if self.scheme not in ("block_sum", "direct_sum", "kahan_scheme"):
+            raise ValueError('invalid value for option sum_scheme : should be one of "auto", "direct_sum", "block_sum" or "kahan_scheme".')
+        self.acc64 = (not f64) and dtype_acc in ("float64", "double") and self.kind == "Sum"
+        self.dimF = red.dimF
+        k = self.kind
+        if k == "Sum":
+            self.dimpart = red.dim
+        elif k == "LSE":
+            self.dimpart = red.dim
+        elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
+            self.dimpart = 2 * self.dimF
+        else:
+            self.dimpart = 2 * red.K * self.dimF
+        self.is_max = k in ("Max", "ArgMax", "Max_ArgMax")
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _term_expr(self, term, acc: str) -> Optional[str]:
+        mode, nodes, _ = term
+        if mode == "zero":
+            return None
+        if mode == "fma":
+            return "kb_fma_v(%s, %s, %s)" % (self.pr.ref(nodes[0]), self.pr.ref(nodes[1]), acc)
+        return "kb_add_v(%s, %s)" % (acc, self.pr.ref(nodes[0]))
+
+    def _term_value(self, term) -> Optional[str]:
+        """Expression of |term| as a V (for Kahan)."""
+        mode, nodes, _ = term
+        if mode == "zero":
+            return None
+        if mode == "fma":
+            return "kb_mul_v(%s, %s)" % (self.pr.ref(nodes[0]), self.pr.ref(nodes[1]))
+        n = nodes[0]
+        if n.cls in (I, IJ):
+            return self.pr.ref(n)
+        return "kb_bcast_v(%s)" % self.pr.ref(n)
+
+    # ---- declarations --------------------------------------------------------------------------
+    def declare(self, W):
+        k, d = self.kind, self.dimF
+        if k == "Sum":
+            n = len(self.acc_terms)
+            if self.acc64:
+                W("double accd[%d][KB_R];" % n)
+                W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) accd[k_][q] = 0.0;" % n)
+            else:
+                W("V acc[%d];" % n)
+                W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) acc[k_] = kb_bcast_v((real)0);" % n)
+            if self.scheme == "kahan_scheme":
+                W("V comp[%d];" % n)
+                W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) comp[k_] = kb_bcast_v((real)0);" % n)
+        elif k == "LSE":
+            n = len(self.acc_terms)
+            W("V mx = kb_bcast_v(-KB_INF);")
+            W("V acc[%d];" % n)
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) acc[k_] = kb_bcast_v((real)0);" % n)
+        elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
+            init = "-KB_INF" if self.is_max else "KB_INF"
+            W("V best[%d]; int bidx[%d][KB_R];" % (d, d))
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { best[k_] = kb_bcast_v(%s); KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) bidx[k_][q] = 0; }" % (d, init))
+        else:
+            K = self.red.K
+            W("real kval[%d][KB_R][%d]; int kidx[%d][KB_R][%d]; V thr[%d];" % (d, K, d, K, d))
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { thr[k_] = kb_bcast_v(KB_INF);" % d)
+            W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { kval[k_][q][l_] = KB_INF; kidx[k_][q][l_] = 0; } }" % K)
+
+    def tile_begin(self, W):
+        if self.kind in ("Sum", "LSE") and self.scheme == "block_sum":
+            n = len(self.acc_terms)
+            W("V tmp[%d];" % n)
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) tmp[k_] = kb_bcast_v((real)0);" % n)
+
+    def _accname(self):
+        return "tmp" if self.scheme == "block_sum" else "acc"
+
+    def update(self, W):
+        k = self.kind
+        if k == "Sum":
+            if self.scheme == "kahan_scheme":
+                for i, term in enumerate(self.acc_terms):
+                    val = self._term_value(term)
+                    if val is None:
+                        continue
+                    W("{ const V a_ = kb_sub_v(%s, comp[%d]); const V b_ = kb_add_v(acc[%d], a_); comp[%d] = kb_sub_v(kb_sub_v(b_, acc[%d]), a_); acc[%d] = b_; }"
+                      % (val, i, i, i, i, i))
+                return
+            if self.acc64 and self.scheme != "block_sum":
+                for i, term in enumerate(self.acc_terms):
+                    val = self._term_value(term)
+                    if val is None:
+                        continue
+                    W("{ const V v_ = %s; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) accd[%d][q] += (double)v_.l[q]; }" % (val, i))
+                return
+            a = self._accname()
+            for i, term in enumerate(self.acc_terms):
+                e = self._term_expr(term, "%s[%d]" % (a, i))
+                if e is not None:
+                    W("%s[%d] = %s;" % (a, i, e))
+        elif k == "LSE":
+            f = self.pr.ref(self.values[0])
+            fv = f if self.values[0].cls in (I, IJ) else "kb_bcast_v(%s)" % f
+            a = self._accname()
+            n = len(self.acc_terms)
+            W("const V f_ = %s;" % fv)
+            # rare path: a new running maximum on at least one lane
+            W("{ bool any_ = false; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (f_.l[q] > mx.l[q]);")
+            W("  if (any_) { KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) if (f_.l[q] > mx.l[q]) {")
+            W("      const real sc_ = kb_exp(mx.l[q] - f_.l[q]); mx.l[q] = f_.l[q];")
+            W("      KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { acc[k_].l[q] *= sc_;%s }" % (n, " tmp[k_].l[q] *= sc_;" if a == "tmp" else ""))
+            W("  } } }")
+            if self.fast:
+                W("const V e_ = kb_ex2_v(kb_mul_v(kb_sub_v(f_, mx), %s));" % _lit(1.4426950408889634, self.f64))
+            else:
+                W("const V e_ = kb_exp_v(kb_sub_v(f_, mx));")
+            for i, term in enumerate(self.acc_terms):
+                mode, nodes, _ = term
+                if mode == "zero":
+                    continue
+                if mode == "fma":
+                    W("%s[%d] = kb_fma_v(kb_mul_v(%s, %s), e_, %s[%d]);" % (a, i, self.pr.ref(nodes[0]), self.pr.ref(nodes[1]), a, i))
+                else:
+                    nd = nodes[0]
+                    if nd.op == "const" and nd.val == 1.0:
+                        W("%s[%d] = kb_add_v(%s[%d], e_);" % (a, i, a, i))
+                    else:
+                        W("%s[%d] = kb_fma_v(%s, e_, %s[%d]);" % (a, i, self.pr.ref(nd), a, i))
+        elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
+            cmp = ">" if self.is_max else "<"
+            for i, nd in enumerate(self.values):
+                f = self.pr.ref(nd)
+                fv = f if nd.cls in (I, IJ) else "kb_bcast_v(%s)" % f
+                W("{ const V f_ = %s; bool any_ = false; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (f_.l[q] %s best[%d].l[q]);" % (fv, cmp, i))
+                W("  if (any_) { KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) if (f_.l[q] %s best[%d].l[q]) { best[%d].l[q] = f_.l[q]; bidx[%d][q] = (int)(jt + jr); } } }"
+                  % (cmp, i, i, i))
+        else:
+            K = self.red.K
+            for i, nd in enumerate(self.values):
+                f = self.pr.ref(nd)
+                fv = f if nd.cls in (I, IJ) else "kb_bcast_v(%s)" % f
+                W("{ const V f_ = %s; bool any_ = false; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (f_.l[q] < thr[%d].l[q]);" % (fv, i))
+                W("  if (any_) { KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) if (f_.l[q] < thr[%d].l[q]) {" % i)
+                W("      kb_kmin_insert<%d, int>(kval[%d][q], kidx[%d][q], f_.l[q], (int)(jt + jr)); thr[%d].l[q] = kval[%d][q][%d]; } } }"
+                  % (K, i, i, i, i, K - 1))
+
+    def tile_end(self, W):
+        if self.kind in ("Sum", "LSE") and self.scheme == "block_sum":
+            n = len(self.acc_terms)
+            if self.acc64:
+                W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) accd[k_][q] += (double)tmp[k_].l[q];" % n)
+            else:
+                W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) acc[k_] = kb_add_v(acc[k_], tmp[k_]);" % n)
+
+    # ---- output ----------------------------------------------------------------------------------
+    def _signs(self):
+        return ["-" if t[2] else "" for t in self.acc_terms]
+
+    def finalize(self, W):
+        """Write either the final output (gridDim.y == 1) or this split's partial accumulator."""
+        k, d = self.kind, self.dimF
+        W("KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) {")
+        W.indent()
+        W("const long long r_ = row0 + (long long)q * KB_T;")
+        W("if (r_ < nrow) {")
+        W.indent()
+        W("real* po = (gridDim.y == 1) ? (out + r_ * %d) : (partial + ((long long)blockIdx.y * nrow + r_) * %d);" % (self.red.dim, self.dimpart))
+        if k == "Sum":
+            for i, s in enumerate(self._signs()):
+                src = "(real)accd[%d][q]" % i if self.acc64 else "acc[%d].l[q]" % i
+                W("po[%d] = %s%s;" % (i, s, src))
+        elif k == "LSE":
+            W("po[0] = mx.l[q];")
+            for i, s in enumerate(self._signs()):
+                W("po[%d] = %sacc[%d].l[q];" % (1 + i, s, i))
+        elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
+            W("if (gridDim.y == 1) {")
+            W.indent()
+            for i in range(d):
+                if k in ("Min", "Max"):
+                    W("po[%d] = best[%d].l[q];" % (i, i))
+                elif k in ("ArgMin", "ArgMax"):
+                    W("po[%d] = (real)bidx[%d][q];" % (i, i))
+                else:
+                    W("po[%d] = best[%d].l[q]; po[%d] = (real)bidx[%d][q];" % (i, i, d + i, i))
+            W.dedent()
+            W("} else {")
+            W.indent()
+            for i in range(d):
+                W("po[%d] = best[%d].l[q]; po[%d] = (real)bidx[%d][q];" % (i, i, d + i, i))
+            W.dedent()
+            W("}")
+        else:
+            K = self.red.K
+            W("if (gridDim.y == 1) {")
+            W.indent()
+            for i in range(d):
+                W("KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) {" % K)
+                if k == "KMin":
+                    W("  po[l_ * %d + %d] = kval[%d][q][l_];" % (d, i, i))
+                elif k == "ArgKMin":
+                    W("  po[l_ * %d + %d] = (real)kidx[%d][q][l_];" % (d, i, i))
+                else:
+                    W("  po[l_ * %d + %d] = kval[%d][q][l_]; po[l_ * %d + %d] = (real)kidx[%d][q][l_];"
+                      % (2 * d, i, i, 2 * d, d + i, i))
+                W("}")
+            W.dedent()
+            W("} else {")
+            W.indent()
+            for i in range(d):
+                W("KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { po[l_ * %d + %d] = kval[%d][q][l_]; po[l_ * %d + %d] = (real)kidx[%d][q][l_]; }"
+                  % (K, 2 * d, i, i, 2 * d, d + i, i))
+            W.dedent()
+            W("}")
+        W.dedent()
+        W("}")
+        W.dedent()
+        W("}")
+
+    def combine_kernel(self, W, cname: str):
+        """One thread per output row merges the ``nsplit`` partial accumulators in split order
+        (so ties still resolve to the smallest index)."""
+        k, d, dp, dim = self.kind, self.dimF, self.dimpart, self.red.dim
+        W("extern \"C\" __global__ void __launch_bounds__(256)")
+        W("%s(const long long nrow, const int nsplit, const real* __restrict__ partial, real* __restrict__ out)" % cname)
+        W("{")
+        W.indent()
+        W("const long long r_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+        W("if (r_ >= nrow) return;")
+        W("const real* pp = partial + r_ * %d;" % dp)
+        W("const long long sstride = nrow * %d;" % dp)
+        W("real* po = out + r_ * %d;" % dim)
+        if k == "Sum":
+            W("real a_[%d];" % dp)
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) a_[k_] = pp[k_];" % dp)
+            W("for (int s_ = 1; s_ < nsplit; s_++) { KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) a_[k_] += pp[s_ * sstride + k_]; }" % dp)
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) po[k_] = a_[k_];" % dp)
+        elif k == "LSE":
+            W("real m_ = pp[0]; real a_[%d];" % (dp - 1))
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) a_[k_] = pp[1 + k_];" % (dp - 1))
+            W("for (int s_ = 1; s_ < nsplit; s_++) {")
+            W("  const real* ps = pp + s_ * sstride; const real m2_ = ps[0];")
+            W("  if (m_ > m2_) { const real e_ = kb_exp(m2_ - m_); KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) a_[k_] += ps[1 + k_] * e_; }" % (dp - 1))
+            W("  else { const real e_ = kb_exp(m_ - m2_); KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) a_[k_] = ps[1 + k_] + e_ * a_[k_]; m_ = m2_; }" % (dp - 1))
+            W("}")
+            W("po[0] = m_; KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) po[1 + k_] = a_[k_];" % (dp - 1))
+        elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
+            cmp = ">" if self.is_max else "<"
+            W("real v_[%d], ix_[%d];" % (d, d))
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { v_[k_] = pp[k_]; ix_[k_] = pp[%d + k_]; }" % (d, d))
+            W("for (int s_ = 1; s_ < nsplit; s_++) { const real* ps = pp + s_ * sstride;")
+            W("  KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) if (ps[k_] %s v_[k_]) { v_[k_] = ps[k_]; ix_[k_] = ps[%d + k_]; } }" % (d, cmp, d))
+            for i in range(d):
+                if k in ("Min", "Max"):
+                    W("po[%d] = v_[%d];" % (i, i))
+                elif k in ("ArgMin", "ArgMax"):
+                    W("po[%d] = ix_[%d];" % (i, i))
+                else:
+                    W("po[%d] = v_[%d]; po[%d] = ix_[%d];" % (i, i, d + i, i))
+        else:
+            K = self.red.K
+            W("for (int k_ = 0; k_ < %d; k_++) {" % d)
+            W("  real v_[%d], ix_[%d];" % (K, K))
+            W("  KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { v_[l_] = pp[l_ * %d + k_]; ix_[l_] = pp[l_ * %d + %d + k_]; }" % (K, 2 * d, 2 * d, d))
+            W("  for (int s_ = 1; s_ < nsplit; s_++) { const real* ps = pp + s_ * sstride;")
+            W("    for (int l_ = 0; l_ < %d; l_++) { const real f_ = ps[l_ * %d + k_]; if (!(f_ < v_[%d])) break;" % (K, 2 * d, K - 1))
+            W("      kb_kmin_insert<%d, real>(v_, ix_, f_, ps[l_ * %d + %d + k_]); } }" % (K, 2 * d, d))
+            W("  KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) {" % K)
+            if k == "KMin":
+                W("    po[l_ * %d + k_] = v_[l_];" % d)
+            elif k == "ArgKMin":
+                W("    po[l_ * %d + k_] = ix_[l_];" % d)
+            else:
+                W("    po[l_ * %d + k_] = v_[l_]; po[l_ * %d + %d + k_] = ix_[l_];" % (2 * d, 2 * d, d))
+            W("  }")
+            W("}")
+        W.dedent()
+        W("}")

@@ -1,0 +1,216 @@
+"""Lowering of the vector formula IR to the scalar DAG (one signed scalar per component).
+
+Summation order follows the reference's generated code so that value orderings (ArgMin / ArgKMin)
+agree: ``Sum`` and ``Scalprod`` accumulate left to right starting from the first term
+(``keopscore/keopscore/formulas/maths/Sum.py:20-24``), and products feeding an
+addition are contracted to FMAs by the emitter exactly as nvcc contracts the reference's code.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+from ..formulas.ir import Node, FormulaError
+from .scalar import Graph, SV
+
+
+class Lowerer:
+    def __init__(self, graph: Graph):
+        self.g = graph
+        self.memo: Dict[int, List[SV]] = {}
+
+    def __call__(self, node: Node) -> List[SV]:
+        key = id(node)
+        out = self.memo.get(key)
+        if out is None:
+            out = self._lower(node)
+            if len(out) != node.dim:
+                raise FormulaError("internal: lowering of %s produced %d components, expected %d"
+                                   % (node.op, len(out), node.dim))
+            self.memo[key] = out
+        return out
+
+    def _bc(self, vals: List[SV], dim: int, k: int) -> SV:
+        return vals[k] if len(vals) > 1 else vals[0]
+
+    def _lower(self, n: Node) -> List[SV]:
+        g, op = self.g, n.op
+        L = self
+
+        if op == "Var":
+            ind, dim, cat = n.params
+            return [g.load(ind, k, cat) for k in range(dim)]
+        if op == "Zero":
+            return [g.const(0.0)] * n.dim
+        if op == "IntCst":
+            return [g.const(float(n.params[0]))]
+        if op == "RatCst":
+            return [g.const(n.params[0] / n.params[1])]
+        if op == "FloatCst":
+            return [g.const(n.params[0])]
+
+        if op in ("Add", "Subtract", "Mult", "Divide", "Powf", "Atan2", "LessThan", "LessOrEqual",
+                  "Equal", "NotEqual"):
+            a, b = L(n.args[0]), L(n.args[1])
+            out = []
+            for k in range(n.dim):
+                x, y = self._bc(a, n.dim, k), self._bc(b, n.dim, k)
+                if op == "Add":
+                    out.append(g.add(x, y))
+                elif op == "Subtract":
+                    out.append(g.sub(x, y))
+                elif op == "Mult":
+                    out.append(g.mul(x, y))
+                elif op == "Divide":
+                    out.append(g.div(x, y))
+                elif op == "Powf":
+                    out.append(g.fn2("powf", x, y))
+                elif op == "Atan2":
+                    out.append(g.fn2("atan2", x, y))
+                elif op == "LessThan":
+                    out.append(g.fn2("lt", x, y))
+                elif op == "LessOrEqual":
+                    out.append(g.fn2("le", x, y))
+                elif op == "Equal":
+                    out.append(g.fn2("eq", x, y))
+                else:
+                    out.append(g.fn2("ne", x, y))
+            return out
+
+        if op in _UNARY:
+            (a,) = [L(x) for x in n.args]
+            return [_UNARY[op](g, x, n) for x in a]
+
+        if op == "IfElse":
+            c, a, b = [L(x) for x in n.args]
+            return [g.select_ge0(self._bc(c, n.dim, k), self._bc(a, n.dim, k), self._bc(b, n.dim, k))
+                    for k in range(n.dim)]
+        if op == "Clamp":
+            x, lo, hi = [L(v) for v in n.args]
+            return [g.fn3("clamp", self._bc(x, n.dim, k), self._bc(lo, n.dim, k), self._bc(hi, n.dim, k))
+                    for k in range(n.dim)]
+        if op == "Mod":
+            x, m, d = [L(v) for v in n.args]
+            return [g.fn3("mod", self._bc(x, n.dim, k), self._bc(m, n.dim, k), self._bc(d, n.dim, k))
+                    for k in range(n.dim)]
+
+        if op == "Sum":
+            a = L(n.args[0])
+            acc = a[0]
+            for x in a[1:]:
+                acc = g.add(acc, x)
+            return [acc]
+        if op == "SumT":
+            a = L(n.args[0])
+            return [a[0]] * n.dim
+        if op == "Scalprod":
+            a, b = L(n.args[0]), L(n.args[1])
+            acc = g.mul(a[0], b[0])
+            for x, y in zip(a[1:], b[1:]):
+                acc = g.add(acc, g.mul(x, y))
+            return [acc]
+        if op in ("Max", "Min"):
+            a = L(n.args[0])
+            acc = a[0]
+            for x in a[1:]:
+                acc = g.fn2("fmax" if op == "Max" else "fmin", acc, x)
+            return [acc]
+        if op in ("ArgMax", "ArgMin"):
+            a = L(n.args[0])
+            best, arg = a[0], g.const(0.0)
+            for k, x in enumerate(a[1:], start=1):
+                # strict comparison: first extremum wins (reference ``maths/ArgMax.py`` / ``ArgMin.py``)
+                better = g.fn2("lt", best, x) if op == "ArgMax" else g.fn2("lt", x, best)
+                # better is 1.0 / 0.0 ; select via (better - 0.5) >= 0
+                sel = g.sub(better, g.const(0.5))
+                arg = g.select_ge0(sel, g.const(float(k)), arg)
+                best = g.select_ge0(sel, x, best)
+            return [arg]
+        if op == "OneHot":
+            a = L(n.args[0])[0]
+            r = g.fn1("round0", a)
+            return [g.fn2("eq", r, g.const(float(k))) for k in range(n.dim)]
+        if op == "Concat":
+            return L(n.args[0]) + L(n.args[1])
+        if op == "Extract":
+            start, dim = n.params
+            return L(n.args[0])[start:start + dim]
+        if op == "ExtractT":
+            start, dim = n.params
+            a = L(n.args[0])
+            z = g.const(0.0)
+            return [z] * start + a + [z] * (dim - start - len(a))
+        if op == "MatVecMult":
+            A, b = L(n.args[0]), L(n.args[1])
+            m = len(b)
+            rows = len(A) // m
+            out = []
+            for r in range(rows):
+                acc = g.mul(A[r * m], b[0])
+                for c in range(1, m):
+                    acc = g.add(acc, g.mul(A[r * m + c], b[c]))
+                out.append(acc)
+            return out
+        if op == "VecMatMult":
+            b, A = L(n.args[0]), L(n.args[1])
+            m = len(b)
+            cols = len(A) // m
+            out = []
+            for c in range(cols):
+                acc = g.mul(b[0], A[c])
+                for r in range(1, m):
+                    acc = g.add(acc, g.mul(b[r], A[r * cols + c]))
+                out.append(acc)
+            return out
+        if op == "TensorProd":
+            a, b = L(n.args[0]), L(n.args[1])
+            return [g.mul(x, y) for x in a for y in b]
+        raise NotImplementedError("operation %s is not supported by the sm_100a code generator" % op)
+
+
+def _pow(g: Graph, x: SV, n: Node) -> SV:
+    return g.powi(x, n.params[0])
+
+
+def _round(g: Graph, x: SV, n: Node) -> SV:
+    d = n.params[0]
+    if d == 0:
+        return g.fn1("round0", x, parity=-1)
+    s = float(10 ** d)
+    return g.mul(g.fn1("round0", g.mul(x, g.const(s)), parity=-1), g.const(1.0 / s))
+
+
+def _clampint(g: Graph, x: SV, n: Node) -> SV:
+    lo, hi = n.params
+    return g.fn3("clamp", x, g.const(float(lo)), g.const(float(hi)))
+
+
+def _diffclampint(g: Graph, x: SV, n: Node) -> SV:
+    lo, hi = n.params
+    return g.fn3("inrange", x, g.const(float(lo)), g.const(float(hi)))
+
+
+_UNARY = {
+    "Minus": lambda g, x, n: -x,
+    "Square": lambda g, x, n: g.square(x),
+    "Inv": lambda g, x, n: g.rcp(x),
+    "Exp": lambda g, x, n: g.exp(x),
+    "Log": lambda g, x, n: g.log(x),
+    "Sqrt": lambda g, x, n: g.sqrt(x),
+    "Rsqrt": lambda g, x, n: g.rsqrt(x),
+    "Sin": lambda g, x, n: g.fn1("sin", x, parity=-1),
+    "Cos": lambda g, x, n: g.fn1("cos", x, parity=1),
+    "Asin": lambda g, x, n: g.fn1("asin", x, parity=-1),
+    "Acos": lambda g, x, n: g.fn1("acos", x),
+    "Atan": lambda g, x, n: g.fn1("atan", x, parity=-1),
+    "Abs": lambda g, x, n: g.fn1("abs", x, parity=1),
+    "Sign": lambda g, x, n: g.fn1("sign", x, parity=-1),
+    "Step": lambda g, x, n: g.fn1("step", x),
+    "ReLU": lambda g, x, n: g.fn1("relu", x),
+    "Floor": lambda g, x, n: g.fn1("floor", x),
+    "XLogX": lambda g, x, n: g.fn1("xlogx", x),
+    "SinXDivX": lambda g, x, n: g.fn1("sinxdivx", x, parity=1),
+    "Pow": _pow,
+    "Round": _round,
+    "ClampInt": _clampint,
+    "DiffClampInt": _diffclampint,
+}

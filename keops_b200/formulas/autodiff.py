@@ -1,0 +1,190 @@
+"""Reverse-mode symbolic differentiation on the vector IR.
+
+``grad(F, v, gradin)`` returns the formula ``[dF/dv]^T . gradin`` with ``dim == v.dim``,
+the same contract as the reference's ``Grad(F, v, gradin) = F.DiffT(v, gradin)``
+(``keopscore/keopscore/formulas/autodiff/Grad.py:14-27``).  The per-op rules are the usual
+calculus identities (cf. each reference op's ``DiffT`` / ``Derivative``, e.g.
+``maths/Mult.py:28-38``, ``maths/Divide.py:28-37``, ``maths/Sum.py:26-30``, ``maths/Exp.py:17-19``);
+zeros are pruned by the IR constructors so the result stays small.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+from . import ir
+from .ir import Node, FormulaError
+
+
+def _depends(f: Node, v: Node) -> bool:
+    return v in f.variables()
+
+
+def grad(f: Node, v: Node, gradin: Node) -> Node:
+    """Adjoint of the differential of ``f`` w.r.t. the variable ``v`` applied to ``gradin``."""
+    if v.op != "Var":
+        raise FormulaError("can only differentiate with respect to a Var")
+    if gradin.dim != f.dim:
+        if gradin.dim == 1:
+            gradin = ir.SumT(gradin, f.dim)
+        else:
+            raise FormulaError(
+                "gradient input has dimension %d, formula has dimension %d" % (gradin.dim, f.dim)
+            )
+    return _grad(f, v, gradin, {})
+
+
+def _grad(f: Node, v: Node, g: Node, memo: Dict[Tuple[int, int], Node]) -> Node:
+    if g.is_zero or not _depends(f, v):
+        return ir.Zero(v.dim)
+    key = (id(f), id(g))
+    hit = memo.get(key)
+    if hit is not None:
+        return hit
+    res = _rule(f, v, g, memo)
+    memo[key] = res
+    return res
+
+
+def _reduce_to(g: Node, dim: int) -> Node:
+    """Adjoint of broadcasting a ``dim``-vector up to ``g.dim``."""
+    if g.dim == dim:
+        return g
+    if dim == 1:
+        return ir.Sum(g)
+    raise FormulaError("internal: cannot reduce gradient of dim %d to %d" % (g.dim, dim))
+
+
+def _rule(f: Node, v: Node, g: Node, memo) -> Node:
+    op = f.op
+    G = lambda child, gi: _grad(child, v, _reduce_to(gi, child.dim), memo)
+
+    if op == "Var":
+        return g if f is v else ir.Zero(v.dim)
+    if op in ("Zero", "IntCst", "RatCst", "FloatCst"):
+        return ir.Zero(v.dim)
+
+    if op == "Add":
+        a, b = f.args
+        return G(a, g) + G(b, g)
+    if op == "Subtract":
+        a, b = f.args
+        return G(a, g) - G(b, g)
+    if op == "Minus":
+        (a,) = f.args
+        return G(a, -g)
+    if op == "Mult":
+        a, b = f.args
+        return G(a, g * b) + G(b, g * a)
+    if op == "Divide":
+        a, b = f.args
+        return G(a, g / b) - G(b, (g * a) / ir.Square(b))
+    if op == "Square":
+        (a,) = f.args
+        return G(a, ir.IntCst(2) * (a * g))
+    if op == "Inv":
+        (a,) = f.args
+        return G(a, -(g / ir.Square(a)))
+    if op == "Exp":
+        (a,) = f.args
+        return G(a, g * f)
+    if op == "Log":
+        (a,) = f.args
+        return G(a, g / a)
+    if op == "Sqrt":
+        (a,) = f.args
+        return G(a, (ir.RatCst(1, 2) * ir.Rsqrt(a)) * g)
+    if op == "Rsqrt":
+        (a,) = f.args
+        return G(a, (ir.RatCst(-1, 2) * ir.Pow(f, 3)) * g)
+    if op == "Pow":
+        (a,) = f.args
+        (m,) = f.params
+        return G(a, (ir.IntCst(m) * ir.Pow(a, m - 1)) * g)
+    if op == "Powf":
+        a, b = f.args
+        return G(a, (b * ir.Powf(a, b - ir.IntCst(1))) * g) + G(b, (ir.Log(a) * f) * g)
+    if op == "Sin":
+        (a,) = f.args
+        return G(a, ir.Cos(a) * g)
+    if op == "Cos":
+        (a,) = f.args
+        return G(a, -(ir.Sin(a) * g))
+    if op == "Acos":
+        (a,) = f.args
+        return G(a, -(ir.Rsqrt(ir.IntCst(1) - ir.Square(a)) * g))
+    if op == "Asin":
+        (a,) = f.args
+        return G(a, ir.Rsqrt(ir.IntCst(1) - ir.Square(a)) * g)
+    if op == "Atan":
+        (a,) = f.args
+        return G(a, g / (ir.IntCst(1) + ir.Square(a)))
+    if op == "Atan2":
+        a, b = f.args  # atan2(a, b)
+        den = ir.Square(a) + ir.Square(b)
+        return G(a, (b / den) * g) + G(b, -((a / den) * g))
+    if op == "Abs":
+        (a,) = f.args
+        return G(a, ir.Sign(a) * g)
+    if op == "ReLU":
+        (a,) = f.args
+        return G(a, ir.Step(a) * g)
+    if op == "XLogX":
+        (a,) = f.args
+        return G(a, (ir.Log(a) + ir.IntCst(1)) * g)
+    if op == "SinXDivX":
+        (a,) = f.args
+        return G(a, (ir.Cos(a) / a - ir.Sin(a) / ir.Square(a)) * g)
+    if op in ("Sign", "Step", "Floor", "Round", "LessThan", "LessOrEqual", "Equal", "NotEqual",
+              "ArgMax", "ArgMin", "OneHot", "DiffClampInt"):
+        return ir.Zero(v.dim)
+    if op == "IfElse":
+        c, a, b = f.args
+        z = ir.Zero(g.dim)
+        return G(a, ir.IfElse(c, g, z)) + G(b, ir.IfElse(c, z, g))
+    if op == "ClampInt":
+        (a,) = f.args
+        lo, hi = f.params
+        return G(a, ir.DiffClampInt(a, lo, hi) * g)
+    if op == "Clamp":
+        x, lo, hi = f.args
+        # same alternative form as the reference (``maths/Clamp.py``)
+        alt = ir.ClampInt((x - lo) / (hi - lo), 0, 1) * (hi - lo) + lo
+        return _grad(alt, v, g, memo)
+    if op == "Mod":
+        x, n, d = f.args
+        return G(x, g)
+
+    if op == "Sum":
+        (a,) = f.args
+        return G(a, ir.SumT(g, a.dim))
+    if op == "SumT":
+        (a,) = f.args
+        return G(a, ir.Sum(g))
+    if op == "Scalprod":
+        a, b = f.args
+        return G(a, g * b) + G(b, g * a)
+    if op == "Max" or op == "Min":
+        (a,) = f.args
+        arg = ir.ArgMax(a) if op == "Max" else ir.ArgMin(a)
+        return G(a, ir.OneHot(arg, a.dim) * g)
+    if op == "Concat":
+        a, b = f.args
+        return G(a, ir.Extract(g, 0, a.dim)) + G(b, ir.Extract(g, a.dim, b.dim))
+    if op == "Extract":
+        (a,) = f.args
+        start, _ = f.params
+        return G(a, ir.ExtractT(g, start, a.dim))
+    if op == "ExtractT":
+        (a,) = f.args
+        start, _ = f.params
+        return G(a, ir.Extract(g, start, a.dim))
+    if op == "MatVecMult":
+        A, b = f.args
+        return G(A, ir.TensorProd(g, b)) + G(b, ir.VecMatMult(g, A))
+    if op == "VecMatMult":
+        b, A = f.args
+        return G(A, ir.TensorProd(b, g)) + G(b, ir.MatVecMult(A, g))
+    if op == "TensorProd":
+        a, b = f.args
+        return G(a, ir.MatVecMult(g, b)) + G(b, ir.VecMatMult(a, g))
+    raise NotImplementedError("no differentiation rule for operation " + op)

@@ -1,0 +1,576 @@
+"""Vector-level formula IR.
+
+A formula ``F(x_i, y_j, p)`` is a DAG of immutable, hash-consed :class:`Node` objects.  Every
+node has a static output dimension ``dim``; element-wise operations broadcast a ``dim == 1``
+operand against a ``dim == n`` operand exactly like the reference's ``VectorizedScalarOp``
+(``keopscore/keopscore/formulas/VectorizedScalarOp.py:7-24``).
+
+Unlike the reference -- where each ``Operation`` prints its own C++ block
+(``keopscore/keopscore/formulas/Operation.py:66-116``) -- nodes here carry no code: the vector DAG
+is lowered to a *scalar* DAG by :mod:`keops_b200.codegen.lower`, which is where simplification,
+CSE, FMA fusion and i/j/parameter hoisting happen.  Only structural simplifications that keep
+autodiff output small (zero / one propagation) are applied at construction time.
+"""
+from __future__ import annotations
+
+from fractions import Fraction
+from typing import Dict, Iterable, List, Optional, Tuple
+
+
+class FormulaError(ValueError):
+    """Raised for malformed formulas (mirrors ``KeOps_Error`` -> ``ValueError``,
+    ``keopscore/keopscore/utils/misc_utils.py:28-35``)."""
+
+
+_INTERN: Dict[tuple, "Node"] = {}
+
+
+class Node:
+    __slots__ = ("op", "args", "params", "dim", "_key", "_vars")
+
+    def __new__(cls, op: str, args: Tuple["Node", ...] = (), params: tuple = (), dim: int = 1):
+        key = (op, tuple(id(a) for a in args), params, dim)
+        hit = _INTERN.get(key)
+        if hit is not None:
+            return hit
+        self = object.__new__(cls)
+        self.op = op
+        self.args = tuple(args)
+        self.params = tuple(params)
+        self.dim = int(dim)
+        self._key = key
+        self._vars = None
+        _INTERN[key] = self
+        return self
+
+    # ---- structural helpers -------------------------------------------------------------
+    def variables(self) -> List["Node"]:
+        """All ``Var`` leaves, sorted by index (cf. ``Operation.Vars_``, ``Operation.py:36-39``)."""
+        if self._vars is None:
+            if self.op == "Var":
+                vs = {self}
+            else:
+                vs = set()
+                for a in self.args:
+                    vs.update(a.variables())
+            self._vars = sorted(vs, key=lambda v: v.params[0])
+        return self._vars
+
+    @property
+    def is_zero(self) -> bool:
+        return self.op == "Zero"
+
+    def const_value(self) -> Optional[Fraction]:
+        if self.op == "IntCst":
+            return Fraction(self.params[0])
+        if self.op == "RatCst":
+            return Fraction(self.params[0], self.params[1])
+        return None
+
+    def __repr__(self):
+        if self.op == "Var":
+            return "Var(%d,%d,%d)" % self.params
+        if self.op == "Zero":
+            return "Zero(%d)" % self.dim
+        if self.op == "IntCst":
+            return "IntCst(%d)" % self.params
+        if self.op == "RatCst":
+            return "RatCst(%d,%d)" % self.params
+        inner = ",".join([repr(a) for a in self.args] + [repr(p) for p in self.params])
+        return "%s(%s)" % (self.op, inner)
+
+    # ---- python operators (used by the parser and by autodiff) ---------------------------
+    def __add__(self, o):
+        return Add(self, as_node(o))
+
+    def __radd__(self, o):
+        return Add(as_node(o), self)
+
+    def __sub__(self, o):
+        return Subtract(self, as_node(o))
+
+    def __rsub__(self, o):
+        return Subtract(as_node(o), self)
+
+    def __mul__(self, o):
+        return Mult(self, as_node(o))
+
+    def __rmul__(self, o):
+        return Mult(as_node(o), self)
+
+    def __truediv__(self, o):
+        return Divide(self, as_node(o))
+
+    def __rtruediv__(self, o):
+        return Divide(as_node(o), self)
+
+    def __neg__(self):
+        return Minus(self)
+
+    def __pow__(self, m):
+        if isinstance(m, Node):
+            return Powf(self, m)
+        if m == 2:
+            return Square(self)
+        if isinstance(m, int):
+            return Pow(self, m)
+        if m == 0.5:
+            return Sqrt(self)
+        if m == -0.5:
+            return Rsqrt(self)
+        return Powf(self, FloatCst(float(m)))
+
+    def __or__(self, o):
+        return Scalprod(self, as_node(o))
+
+    def __lt__(self, o):
+        return LessThan(self, as_node(o))
+
+    def __gt__(self, o):
+        return LessThan(as_node(o), self)
+
+    def __le__(self, o):
+        return LessOrEqual(self, as_node(o))
+
+    def __ge__(self, o):
+        return LessOrEqual(as_node(o), self)
+
+    __hash__ = object.__hash__
+
+    def __eq__(self, o):  # identity (nodes are interned)
+        return self is o
+
+    def __ne__(self, o):
+        return self is not o
+
+
+def as_node(x) -> Node:
+    if isinstance(x, Node):
+        return x
+    if isinstance(x, bool):
+        raise FormulaError("invalid operand type bool")
+    if isinstance(x, int):
+        return IntCst(x)
+    if isinstance(x, float):
+        if x == int(x) and abs(x) < 2 ** 31:
+            return IntCst(int(x))
+        return FloatCst(x)
+    raise FormulaError("invalid operand type : " + str(type(x)))
+
+
+# ------------------------------------------------------------------------------------------
+# leaves
+# ------------------------------------------------------------------------------------------
+def Var(ind: int, dim: int, cat: int) -> Node:
+    """``Var(ind, dim, cat)``: cat 0 = i-indexed, 1 = j-indexed, 2 = parameter
+    (``keopscore/keopscore/formulas/variables/Var.py:10-39``)."""
+    if cat not in (0, 1, 2):
+        raise FormulaError("Var category must be 0, 1 or 2")
+    if dim < 1:
+        raise FormulaError("Var dimension must be positive")
+    return Node("Var", (), (int(ind), int(dim), int(cat)), dim)
+
+
+def Zero(dim: int) -> Node:
+    return Node("Zero", (), (), dim)
+
+
+def IntCst(v: int) -> Node:
+    return Node("IntCst", (), (int(v),), 1)
+
+
+def RatCst(p: int, q: int) -> Node:
+    if q == 0:
+        raise FormulaError("division by zero")
+    f = Fraction(int(p), int(q))
+    if f.denominator == 1:
+        return IntCst(f.numerator)
+    return Node("RatCst", (), (f.numerator, f.denominator), 1)
+
+
+def IntInv(v: int) -> Node:
+    return RatCst(1, v)
+
+
+def FloatCst(v: float) -> Node:
+    return Node("FloatCst", (), (float(v),), 1)
+
+
+def _const(fr: Fraction) -> Node:
+    return RatCst(fr.numerator, fr.denominator)
+
+
+# ------------------------------------------------------------------------------------------
+# broadcasting helpers
+# ------------------------------------------------------------------------------------------
+def _bdim(*args: Node) -> int:
+    dims = {a.dim for a in args}
+    if len(dims) > 2 or (len(dims) == 2 and min(dims) != 1):
+        raise FormulaError(
+            "dimensions are not compatible for element-wise operation: %s" % sorted(dims)
+        )
+    return max(dims)
+
+
+def Broadcast(a: Node, dim: int) -> Node:
+    if a.dim == dim:
+        return a
+    if a.dim == 1:
+        return SumT(a, dim)
+    raise FormulaError("dimensions are not compatible for Broadcast operation")
+
+
+# ------------------------------------------------------------------------------------------
+# arithmetic
+# ------------------------------------------------------------------------------------------
+def Add(a: Node, b: Node) -> Node:
+    d = _bdim(a, b)
+    if a.is_zero:
+        return Broadcast(b, d)
+    if b.is_zero:
+        return Broadcast(a, d)
+    ca, cb = a.const_value(), b.const_value()
+    if ca is not None and cb is not None:
+        return _const(ca + cb)
+    if a is b:
+        return Mult(IntCst(2), a)
+    return Node("Add", (a, b), (), d)
+
+
+def Subtract(a: Node, b: Node) -> Node:
+    d = _bdim(a, b)
+    if a.is_zero:
+        return Minus(Broadcast(b, d))
+    if b.is_zero:
+        return Broadcast(a, d)
+    if a is b:
+        return Zero(d)
+    ca, cb = a.const_value(), b.const_value()
+    if ca is not None and cb is not None:
+        return _const(ca - cb)
+    return Node("Subtract", (a, b), (), d)
+
+
+def Minus(a: Node) -> Node:
+    if a.is_zero:
+        return a
+    c = a.const_value()
+    if c is not None:
+        return _const(-c)
+    if a.op == "Minus":
+        return a.args[0]
+    return Node("Minus", (a,), (), a.dim)
+
+
+def Mult(a: Node, b: Node) -> Node:
+    d = _bdim(a, b)
+    if a.is_zero or b.is_zero:
+        return Zero(d)
+    ca, cb = a.const_value(), b.const_value()
+    if ca is not None and cb is not None:
+        return _const(ca * cb)
+    if ca is not None:
+        if ca == 1:
+            return b
+        if ca == -1:
+            return Minus(b)
+    if cb is not None:
+        if cb == 1:
+            return a
+        if cb == -1:
+            return Minus(a)
+    if a is b:
+        return Square(a)
+    return Node("Mult", (a, b), (), d)
+
+
+def Divide(a: Node, b: Node) -> Node:
+    d = _bdim(a, b)
+    if b.is_zero:
+        raise FormulaError("division by zero")
+    if a.is_zero:
+        return Zero(d)
+    cb = b.const_value()
+    if cb is not None:
+        # f / n -> (1/n) * f   (reference: ``maths/Divide.py:59-62``)
+        return Mult(_const(1 / cb), a)
+    ca = a.const_value()
+    if ca is not None and ca == 1:
+        return Inv(b)
+    return Node("Divide", (a, b), (), d)
+
+
+def _unary(op: str):
+    def make(a: Node) -> Node:
+        return Node(op, (a,), (), a.dim)
+
+    make.__name__ = op
+    return make
+
+
+def Square(a: Node) -> Node:
+    if a.is_zero:
+        return a
+    c = a.const_value()
+    if c is not None:
+        return _const(c * c)
+    return Node("Square", (a,), (), a.dim)
+
+
+def Inv(a: Node) -> Node:
+    c = a.const_value()
+    if c is not None:
+        if c == 0:
+            raise FormulaError("division by zero")
+        return _const(1 / c)
+    return Node("Inv", (a,), (), a.dim)
+
+
+Exp = _unary("Exp")
+Log = _unary("Log")
+Sin = _unary("Sin")
+Cos = _unary("Cos")
+Acos = _unary("Acos")
+Asin = _unary("Asin")
+Atan = _unary("Atan")
+Floor = _unary("Floor")
+XLogX = _unary("XLogX")
+SinXDivX = _unary("SinXDivX")
+
+
+def _unary_zero_fixed(op: str):
+    def make(a: Node) -> Node:
+        if a.is_zero:
+            return a
+        return Node(op, (a,), (), a.dim)
+
+    make.__name__ = op
+    return make
+
+
+Sqrt = _unary_zero_fixed("Sqrt")
+Rsqrt = _unary_zero_fixed("Rsqrt")  # reference guards x == 0 -> 0 (``math_functions.py:104-108``)
+Abs = _unary_zero_fixed("Abs")
+Sign = _unary_zero_fixed("Sign")
+ReLU = _unary_zero_fixed("ReLU")
+Step = _unary("Step")
+
+
+def Pow(a: Node, m: int) -> Node:
+    m = int(m)
+    if m == 1:
+        return a
+    if m == 2:
+        return Square(a)
+    if m == 0:
+        return Broadcast(IntCst(1), a.dim)
+    return Node("Pow", (a,), (m,), a.dim)
+
+
+def Powf(a: Node, b: Node) -> Node:
+    return Node("Powf", (a, as_node(b)), (), _bdim(a, as_node(b)))
+
+
+def Round(a: Node, d: int = 0) -> Node:
+    return Node("Round", (a,), (int(d),), a.dim)
+
+
+def Atan2(a: Node, b: Node) -> Node:
+    return Node("Atan2", (a, b), (), _bdim(a, b))
+
+
+def _cmp(op: str):
+    def make(a: Node, b: Node) -> Node:
+        return Node(op, (a, b), (), _bdim(a, b))
+
+    make.__name__ = op
+    return make
+
+
+LessThan = _cmp("LessThan")
+LessOrEqual = _cmp("LessOrEqual")
+Equal = _cmp("Equal")
+NotEqual = _cmp("NotEqual")
+
+
+def IfElse(c: Node, a: Node, b: Node) -> Node:
+    """``IfElse(f, a, b) = a if f >= 0 else b`` (``maths/IfElse.py``)."""
+    d = _bdim(c, a, b)
+    if a.is_zero and b.is_zero:
+        return Zero(d)
+    return Node("IfElse", (c, a, b), (), d)
+
+
+def Clamp(x: Node, a: Node, b: Node) -> Node:
+    return Node("Clamp", (x, a, b), (), _bdim(x, a, b))
+
+
+def ClampInt(x: Node, a: int, b: int) -> Node:
+    return Node("ClampInt", (x,), (int(a), int(b)), x.dim)
+
+
+def DiffClampInt(x: Node, a: int, b: int) -> Node:
+    return Node("DiffClampInt", (x,), (int(a), int(b)), x.dim)
+
+
+def Mod(x: Node, n: Node, d: Node) -> Node:
+    return Node("Mod", (x, n, d), (), _bdim(x, n, d))
+
+
+# ------------------------------------------------------------------------------------------
+# vector <-> scalar
+# ------------------------------------------------------------------------------------------
+def Sum(a: Node) -> Node:
+    if a.dim == 1:
+        return a
+    if a.is_zero:
+        return Zero(1)
+    if a.op == "SumT":
+        return Mult(IntCst(a.dim), a.args[0])
+    return Node("Sum", (a,), (), 1)
+
+
+def SumT(a: Node, dim: int) -> Node:
+    if a.dim != 1:
+        raise FormulaError("SumT expects a scalar formula")
+    if dim == 1:
+        return a
+    if a.is_zero:
+        return Zero(dim)
+    return Node("SumT", (a,), (int(dim),), dim)
+
+
+def Scalprod(a: Node, b: Node) -> Node:
+    if a.dim != b.dim:
+        raise FormulaError("Scalprod: dimensions must be the same")
+    if a.is_zero or b.is_zero:
+        return Zero(1)
+    if a.dim == 1:
+        return Mult(a, b)
+    return Node("Scalprod", (a, b), (), 1)
+
+
+def Max(a: Node) -> Node:
+    return a if a.dim == 1 else Node("Max", (a,), (), 1)
+
+
+def Min(a: Node) -> Node:
+    return a if a.dim == 1 else Node("Min", (a,), (), 1)
+
+
+def ArgMax(a: Node) -> Node:
+    return Node("ArgMax", (a,), (), 1)
+
+
+def ArgMin(a: Node) -> Node:
+    return Node("ArgMin", (a,), (), 1)
+
+
+def SqNorm2(a: Node) -> Node:
+    return Sum(Square(a))
+
+
+def Norm2(a: Node) -> Node:
+    return Sqrt(Scalprod(a, a))
+
+
+def Normalize(a: Node) -> Node:
+    return Mult(Rsqrt(SqNorm2(a)), a)
+
+
+def SqDist(a: Node, b: Node) -> Node:
+    return SqNorm2(Subtract(a, b))
+
+
+def WeightedSqNorm(A: Node, x: Node) -> Node:
+    """``SqNormIso`` / ``SqNormDiag`` / ``SymSqNorm`` depending on ``A.dim``
+    (``maths/WeightedSqNorm.py``)."""
+    if A.dim == 1:
+        return Mult(A, SqNorm2(x))
+    if A.dim == x.dim:
+        return Sum(Mult(A, Square(x)))
+    if A.dim == x.dim * x.dim:
+        return Scalprod(x, MatVecMult(A, x))
+    raise FormulaError("WeightedSqNorm: incompatible dimensions")
+
+
+def WeightedSqDist(A: Node, x: Node, y: Node) -> Node:
+    return WeightedSqNorm(A, Subtract(x, y))
+
+
+# ------------------------------------------------------------------------------------------
+# shape ops
+# ------------------------------------------------------------------------------------------
+def Concat(a: Node, b: Node) -> Node:
+    if a.is_zero and b.is_zero:
+        return Zero(a.dim + b.dim)
+    return Node("Concat", (a, b), (), a.dim + b.dim)
+
+
+def Extract(a: Node, start: int, dim: int) -> Node:
+    start, dim = int(start), int(dim)
+    if start < 0 or start + dim > a.dim:
+        raise FormulaError("Index out of bound in Extract")
+    if a.is_zero:
+        return Zero(dim)
+    if start == 0 and dim == a.dim:
+        return a
+    return Node("Extract", (a,), (start, dim), dim)
+
+
+def ExtractT(a: Node, start: int, dim: int) -> Node:
+    start, dim = int(start), int(dim)
+    if start < 0 or start + a.dim > dim:
+        raise FormulaError("Index out of bound in ExtractT")
+    if a.is_zero:
+        return Zero(dim)
+    if start == 0 and dim == a.dim:
+        return a
+    return Node("ExtractT", (a,), (start, dim), dim)
+
+
+def Elem(a: Node, m: int) -> Node:
+    m = int(m)
+    if m < 0 or m >= a.dim:
+        raise FormulaError("Index out of bound in Elem")
+    return Extract(a, m, 1)
+
+
+def ElemT(a: Node, n: int, m: int) -> Node:
+    if a.dim != 1:
+        raise FormulaError("Input of ElemT should be a scalar")
+    return ExtractT(a, int(m), int(n))
+
+
+def OneHot(a: Node, dim: int) -> Node:
+    if a.dim != 1:
+        raise FormulaError("OneHot operation is only valid for scalar input")
+    return Node("OneHot", (a,), (int(dim),), int(dim))
+
+
+def MatVecMult(A: Node, b: Node) -> Node:
+    if A.dim % b.dim != 0:
+        raise FormulaError("Dimensions of A and B are not compatible for matrix-vector product")
+    return Node("MatVecMult", (A, b), (), A.dim // b.dim)
+
+
+def VecMatMult(b: Node, A: Node) -> Node:
+    if A.dim % b.dim != 0:
+        raise FormulaError("Dimensions of A and B are not compatible for vector-matrix product")
+    return Node("VecMatMult", (b, A), (), A.dim // b.dim)
+
+
+def TensorProd(a: Node, b: Node) -> Node:
+    if a.is_zero or b.is_zero:
+        return Zero(a.dim * b.dim)
+    return Node("TensorProd", (a, b), (), a.dim * b.dim)
+
+
+# names visible to the formula parser -------------------------------------------------------
+PUBLIC_OPS = {
+    name: obj
+    for name, obj in list(globals().items())
+    if callable(obj) and name[0].isupper() and name not in ("Node", "FormulaError", "Fraction")
+}
+for _hidden in ("Broadcast", "Dict", "Iterable", "List", "Optional", "Tuple"):
+    PUBLIC_OPS.pop(_hidden, None)

@@ -1,0 +1,193 @@
+"""Compilation cache, kernel configuration heuristics and launch-shape tuner.
+
+Replaces ``keopscore/keopscore/binders/LinkCompile.py`` (hash -> artefact on disk),
+``keopscore/keopscore/utils/Cache.py`` (memoisation) and the block-size logic of
+``KeOps_module::launch_kernel`` (``keopscore/keopscore/binders/nvrtc/keops_nvrtc.cpp:441-458``).
+
+Cache key = sha256(generator version + full generated source + NVRTC options): the source text
+already contains the tile configuration, dtype, fast-math flag and the canonical reduction.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+import os
+import threading
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from ..codegen.emit import KernelConfig, KernelSource, generate, GENERATOR_VERSION
+from ..formulas.reductions import Reduction
+from . import capi
+
+_lock = threading.RLock()
+
+
+def cache_dir() -> str:
+    """Cubin cache: ``$KB200_CACHE_DIR``, else an in-tree folder (so that cubins cross-compiled by
+    ``build()`` travel with the repository snapshot), else ``~/.cache/keops_b200``."""
+    d = os.environ.get("KB200_CACHE_DIR")
+    if not d:
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_cache", GENERATOR_VERSION)
+        try:
+            os.makedirs(d, exist_ok=True)
+            if not os.access(d, os.W_OK):
+                raise OSError
+        except OSError:
+            d = os.path.join(os.path.expanduser("~"), ".cache", "keops_b200", GENERATOR_VERSION)
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def clean_cache():
+    """Counterpart of ``pykeops.clean_pykeops()`` (``pykeops/pykeops/__init__.py:47-61``)."""
+    with _lock:
+        d = cache_dir()
+        for f in os.listdir(d):
+            if f.endswith(".cubin") or f.endswith(".cu"):
+                try:
+                    os.remove(os.path.join(d, f))
+                except OSError:
+                    pass
+        for m in _modules.values():
+            m.module.unload()
+        _modules.clear()
+        _cubins.clear()
+
+
+_cubins: Dict[str, bytes] = {}
+
+
+def nvrtc_options(fast: bool) -> List[str]:
+    opts = ["-lineinfo"]
+    if fast:
+        opts.append("--use_fast_math")
+    extra = os.environ.get("KB200_NVRTC_FLAGS")
+    if extra:
+        opts.extend(extra.split())
+    return opts
+
+
+def get_cubin(ks: KernelSource, fast: bool) -> bytes:
+    opts = nvrtc_options(fast)
+    key = hashlib.sha256((ks.hash + "|" + " ".join(opts)).encode()).hexdigest()[:20]
+    with _lock:
+        blob = _cubins.get(key)
+        if blob is not None:
+            return blob
+        path = os.path.join(cache_dir(), "kb200_%s.cubin" % key)
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                blob = f.read()
+        else:
+            blob = capi.compile_to_cubin(ks.source, opts, name="kb200_%s.cu" % key)
+            tmp = path + ".tmp%d" % os.getpid()
+            with open(tmp, "wb") as f:
+                f.write(blob)
+            os.replace(tmp, path)
+            if os.environ.get("KB200_KEEP_SOURCE"):
+                with open(path[:-6] + ".cu", "w") as f:
+                    f.write(ks.source)
+        _cubins[key] = blob
+        return blob
+
+
+# ------------------------------------------------------------------------------------------
+# configuration heuristics
+# ------------------------------------------------------------------------------------------
+def default_config(red: Reduction, dtype: str) -> KernelConfig:
+    """Pick (T, R, TJ, unroll) from the formula's register / shared-memory footprint."""
+    tagI = red.tagI
+    dimx = sum(v.params[1] for v in red.variables() if v.params[2] == tagI)
+    dimy = sum(v.params[1] for v in red.variables() if v.params[2] == 1 - tagI)
+    f64 = dtype == "float64"
+    env = os.environ.get("KB200_CONFIG")  # e.g. "T=128,R=4,TJ=256,U=8,B=2" (debug / tuning)
+    acc_regs = red.dimred if red.kind not in ("Sum", "LSE") else 2 * red.dim
+    work = dimx + acc_regs
+    if f64:
+        R = 2 if work <= 24 else 1
+        T = 128
+        min_blocks = 1
+    else:
+        if work <= 12:
+            R, T, min_blocks = 4, 256, 4
+        elif work <= 40:
+            R, T, min_blocks = 2, 256, 2
+        else:
+            R, T, min_blocks = 2, 128, 1
+    esz = 8 if f64 else 4
+    vec = 2 if f64 else 4
+    stride = max(vec, -(-dimy // vec) * vec)
+    TJ = 16384 // (stride * esz)          # two buffers <= 32 KB
+    TJ = max(8, min(256, 1 << int(math.log2(max(TJ, 1)))))
+    body = max(1, dimx + dimy) * (R // (1 if f64 else 2))
+    unroll = 8 if body <= 16 else (4 if body <= 64 else (2 if body <= 160 else 1))
+    cfg = KernelConfig(T=T, R=R, TJ=TJ, unroll=unroll, min_blocks=min_blocks)
+    if env:
+        kv = dict(item.split("=") for item in env.split(","))
+        cfg = KernelConfig(T=int(kv.get("T", cfg.T)), R=int(kv.get("R", cfg.R)), TJ=int(kv.get("TJ", cfg.TJ)),
+                           unroll=int(kv.get("U", cfg.unroll)), min_blocks=int(kv.get("B", cfg.min_blocks)))
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# loaded kernels + launch shape
+# ------------------------------------------------------------------------------------------
+@dataclass
+class LoadedKernel:
+    ks: KernelSource
+    module: capi.Module
+    fn_reduce: int
+    fn_combine: int
+    regs: int
+    blocks_per_sm: int
+    sm_count: int
+
+
+_modules: Dict[Tuple[str, int], LoadedKernel] = {}
+
+
+def load_kernel(ks: KernelSource, fast: bool, device: int) -> LoadedKernel:
+    key = (ks.hash + ("f" if fast else "p"), device)
+    with _lock:
+        lk = _modules.get(key)
+        if lk is None:
+            cubin = get_cubin(ks, fast)
+            mod = capi.Module(cubin, device)
+            fr = mod.function(ks.kernel_name)
+            fc = mod.function(ks.combine_name)
+            regs, _, _ = capi.function_info(fr)
+            bps = max(1, capi.max_active_blocks(fr, ks.cfg.T, 0))
+            sm = capi.device_info(device)["sm_count"]
+            lk = LoadedKernel(ks, mod, fr, fc, regs, bps, sm)
+            _modules[key] = lk
+        return lk
+
+
+def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int, dimpart: int, esz: int,
+                 max_split: int = 64, ws_limit_bytes: int = 2 << 30) -> Tuple[int, int]:
+    """Choose the number of column splits so that the grid fills an integer number of waves.
+
+    All CTAs do the same amount of work, so wall time ~ waves * work-per-CTA.  Without splitting,
+    ``gx`` CTAs over ``slots`` resident slots waste up to one whole wave (M=1e6 rows -> 1.65 waves
+    -> 2).  Splitting the streamed range into ``ns`` chunks multiplies the CTA count and lets the
+    last wave be (nearly) full; partials are merged by ``kb200_combine``.
+    Returns (nsplit, col_chunk)."""
+    gx = -(-nrow // rows_per_block)
+    ntiles = max(1, -(-ncol // TJ))
+    best = None
+    for ns in range(1, max_split + 1):
+        if ns > ntiles:
+            break
+        tiles_per = -(-ntiles // ns)
+        ns_eff = -(-ntiles // tiles_per)
+        if ns_eff != ns:
+            continue
+        if ns > 1 and ns * nrow * dimpart * esz > ws_limit_bytes:
+            break
+        waves = -(-(gx * ns) // slots)
+        # cost in tile units: per-CTA prologue/epilogue overhead ~ 2 tiles, combine ~ ns/8 tiles
+        cost = waves * (tiles_per + 2.0) + (0.25 * ns if ns > 1 else 0.0)
+        if best is None or cost < best[0] * 0.98:
+            best = (cost, ns, tiles_per * TJ)
+    return best[1], best[2]

@@ -1,0 +1,792 @@
+"""CPU oracle for the KeOps map-reduce hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module; the product (``keops_b200/``) never does and has no CPU fallback.
+
+It is a dense numpy restatement of what the reference computes for
+``out_i = Reduce_j F(x_i, y_j, p)``:
+
+* the formula string is ``eval``'d in a namespace of operation classes, like the reference's
+  ``GetReduction`` (``keopscore/keopscore/formulas/GetReduction.py:19-39``);
+* each operation evaluates itself on broadcastable ``(M, N, dim)`` arrays in the formula dtype with
+  the reference CPU code's operation order -- e.g. ``Sum`` / ``Scalprod`` accumulate left to right,
+  ``out = 0; out += arg[k]`` (``formulas/maths/Sum.py:20-24``), and no FMA contraction (the CPU
+  backend is built without ``-march=native``, ``config/base_config.py:266-291``);
+* each operation knows its adjoint ``difft(v, gradin)`` (the reference's ``DiffT``), so that
+  ``Grad_WithSavedForward`` strings -- what ``GenredAutograd._backward`` hands to the engine
+  (``pykeops/pykeops/torch/generic/generic_red.py:165-189``) -- can be evaluated too;
+* reductions follow ``keopscore/keopscore/formulas/reductions/*.py`` and the scalar loop of
+  ``CpuReduc`` (``keopscore/keopscore/mapreduce/cpu/CpuReduc.py:46-67``): ties in Min / ArgMin /
+  KMin go to the smallest index; arg-type outputs are stored as floats; ``Max_SumShiftExp``
+  returns the unnormalised pair ``(m, s)``.  Sums over ``j`` are accumulated in float64 and rounded
+  once (the reference uses float32 block sums of ~sqrt(N) terms; both agree to ~1e-7 relative).
+
+Parity pinning: ``tests/test_oracle_vs_golden.py`` checks this module against outputs of the real
+reference (CPU backend, run in the build container by ``tests/golden/make_golden.py``) and against
+the reference's one hard-coded known answer (``pykeops/pykeops/torch/test_install.py:5-25``).
+"""
+from __future__ import annotations
+
+import re
+from fractions import Fraction
+
+import numpy as np
+
+# ------------------------------------------------------------------------------------------
+# operations
+# ------------------------------------------------------------------------------------------
+
+
+class Op:
+    dim = 1
+    children = ()
+
+    # python operators, as in ``formulas/Operation.py:118-216``
+    def __add__(s, o): return Add(s, _w(o))
+    def __radd__(s, o): return Add(_w(o), s)
+    def __sub__(s, o): return Subtract(s, _w(o))
+    def __rsub__(s, o): return Subtract(_w(o), s)
+    def __mul__(s, o): return Mult(s, _w(o))
+    def __rmul__(s, o): return Mult(_w(o), s)
+    def __truediv__(s, o): return Divide(s, _w(o))
+    def __rtruediv__(s, o): return Divide(_w(o), s)
+    def __neg__(s): return Minus(s)
+    def __or__(s, o): return Scalprod(s, _w(o))
+    def __lt__(s, o): return LessThan(s, _w(o))
+    def __gt__(s, o): return LessThan(_w(o), s)
+    def __le__(s, o): return LessOrEqual(s, _w(o))
+    def __ge__(s, o): return LessOrEqual(_w(o), s)
+
+    def __pow__(s, m):
+        if isinstance(m, Op):
+            return Powf(s, m)
+        if m == 2:
+            return Square(s)
+        if isinstance(m, int):
+            return Pow(s, m)
+        if m == 0.5:
+            return Sqrt(s)
+        if m == -0.5:
+            return Rsqrt(s)
+        return Powf(s, Cst(float(m)))
+
+    def vars(self):
+        out = {}
+        for c in self.children:
+            out.update(c.vars())
+        return out
+
+    def iszero(self):
+        return False
+
+
+def _w(x):
+    if isinstance(x, Op):
+        return x
+    if isinstance(x, (int, float)):
+        return Cst(x)
+    raise ValueError("invalid operand " + repr(x))
+
+
+class Var(Op):
+    def __init__(self, ind, dim, cat):
+        self.ind, self.dim, self.cat = int(ind), int(dim), int(cat)
+
+    def vars(self):
+        return {self.ind: self}
+
+    def ev(self, env):
+        return env.var(self)
+
+    def difft(self, v, g):
+        same = (self.ind, self.dim, self.cat) == (v.ind, v.dim, v.cat)
+        return g if same else Zero(v.dim)
+
+
+class Zero(Op):
+    def __init__(self, dim):
+        self.dim = int(dim)
+
+    def iszero(self):
+        return True
+
+    def ev(self, env):
+        return np.zeros((1, 1, self.dim), env.dtype)
+
+    def difft(self, v, g):
+        return Zero(v.dim)
+
+
+class Cst(Op):
+    """IntCst / RatCst / float constant."""
+
+    def __init__(self, val):
+        self.val = val
+
+    def ev(self, env):
+        return np.full((1, 1, 1), float(self.val), env.dtype)
+
+    def difft(self, v, g):
+        return Zero(v.dim)
+
+
+def IntCst(v): return Cst(int(v))
+def RatCst(p, q): return Cst(Fraction(int(p), int(q)))
+def IntInv(v): return Cst(Fraction(1, int(v)))
+
+
+def _bd(*ops):
+    return max(o.dim for o in ops)
+
+
+def _red(g, dim):
+    """adjoint of broadcasting dim -> g.dim"""
+    if g.dim == dim:
+        return g
+    if dim == 1:
+        return Sum(g)
+    raise ValueError("cannot reduce gradient")
+
+
+def _z(*xs):
+    return any(x.iszero() for x in xs)
+
+
+class _Elementwise(Op):
+    def __init__(self, *children):
+        self.children = children
+        self.dim = _bd(*children)
+
+    def ev(self, env):
+        return self.f(env, *[c.ev(env) for c in self.children])
+
+
+class _Add(_Elementwise):
+
+    def f(self, env, a, b): return a + b
+    def difft(self, v, g):
+        a, b = self.children
+        return a.difft(v, _red(g, a.dim)) + b.difft(v, _red(g, b.dim))          # maths/Add.py
+
+
+
+def Add(a, b):
+    if a.iszero():
+        return Broadcast(b, _bd(a, b))
+    if b.iszero():
+        return Broadcast(a, _bd(a, b))
+    return _Add(a, b)
+
+class _Subtract(_Elementwise):
+
+    def f(self, env, a, b): return a - b
+    def difft(self, v, g):
+        a, b = self.children
+        return a.difft(v, _red(g, a.dim)) - b.difft(v, _red(g, b.dim))          # maths/Subtract.py:26-33
+
+
+
+def Subtract(a, b):
+    if b.iszero():
+        return Broadcast(a, _bd(a, b))
+    if a.iszero():
+        return Minus(Broadcast(b, _bd(a, b)))
+    return _Subtract(a, b)
+
+class _Minus(_Elementwise):
+
+    def f(self, env, a): return -a
+    def difft(self, v, g):
+        return -(self.children[0].difft(v, g))                                   # maths/Minus.py:25-27
+
+
+
+def Minus(a):
+    return a if a.iszero() else _Minus(a)
+
+class _Mult(_Elementwise):
+
+    def f(self, env, a, b): return a * b
+    def difft(self, v, g):
+        a, b = self.children                                                     # maths/Mult.py:28-38
+        return a.difft(v, _red(g * b, a.dim)) + b.difft(v, _red(g * a, b.dim))
+
+
+
+def Mult(a, b):
+    if _z(a, b):
+        return Zero(_bd(a, b))
+    return _Mult(a, b)
+
+class _Divide(_Elementwise):
+
+    def f(self, env, a, b): return a / b
+    def difft(self, v, g):
+        a, b = self.children                                                     # maths/Divide.py:28-37
+        return a.difft(v, _red(g / b, a.dim)) - b.difft(v, _red(g * a / Square(b), b.dim))
+
+
+
+def Divide(a, b):
+    if a.iszero():
+        return Zero(_bd(a, b))
+    return _Divide(a, b)
+
+def Broadcast(a, dim):
+    if a.dim == dim:
+        return a
+    if a.dim == 1:
+        return SumT(a, dim)
+    raise ValueError("dimensions are not compatible for Broadcast")
+
+
+class _Unary(_Elementwise):
+    """f(a); ``d(a)`` returns f'(a) as a formula (``VectorizedScalarOp.DiffT``,
+    ``formulas/VectorizedScalarOp.py:39-47``)."""
+
+    def difft(self, v, g):
+        (a,) = self.children
+        d = self.d(a)
+        if d is None:
+            return Zero(v.dim)
+        return a.difft(v, g * d)
+
+
+class _Square(_Unary):
+    def f(self, env, a): return a * a
+    def d(self, a): return 2 * a                                                 # maths/Square.py:20-22
+
+
+
+def Square(a):
+    return a if a.iszero() else _Square(a)
+
+class Exp(_Unary):
+    def f(self, env, a): return np.exp(a)
+    def d(self, a): return self                                                  # maths/Exp.py:17-19
+
+
+class Log(_Unary):
+    def f(self, env, a): return np.log(a)
+    def d(self, a): return Inv(a)
+
+
+class Inv(_Unary):
+    def f(self, env, a): return env.dtype.type(1) / a
+    def d(self, a): return -Inv(Square(a))                                       # maths/Inv.py
+
+
+class Sqrt(_Unary):
+    def f(self, env, a): return np.sqrt(a)
+    def d(self, a): return IntInv(2) * Rsqrt(a)                                  # maths/Sqrt.py
+
+
+class Rsqrt(_Unary):
+    def f(self, env, a):                                                         # utils/math_functions.py:104-108
+        with np.errstate(divide="ignore"):
+            return np.where(a == 0, env.dtype.type(0), env.dtype.type(1) / np.sqrt(a))
+    def d(self, a): return IntInv(-2) * Pow(self, 3)                             # maths/Rsqrt.py
+
+
+class Sin(_Unary):
+    def f(self, env, a): return np.sin(a)
+    def d(self, a): return Cos(a)
+
+
+class Cos(_Unary):
+    def f(self, env, a): return np.cos(a)
+    def d(self, a): return -Sin(a)
+
+
+class Abs(_Unary):
+    def f(self, env, a): return np.abs(a)
+    def d(self, a): return Sign(a)
+
+
+class Sign(_Unary):
+    def f(self, env, a): return np.sign(a)
+    def d(self, a): return None
+
+
+class Step(_Unary):
+    def f(self, env, a): return np.where(a < 0, env.dtype.type(0), env.dtype.type(1))
+    def d(self, a): return None
+
+
+class ReLU(_Unary):
+    def f(self, env, a): return np.where(a < 0, env.dtype.type(0), a)
+    def d(self, a): return Step(a)
+
+
+class Floor(_Unary):
+    def f(self, env, a): return np.floor(a)
+    def d(self, a): return None
+
+
+class Atan(_Unary):
+    def f(self, env, a): return np.arctan(a)
+    def d(self, a): return Inv(1 + Square(a))
+
+
+class Asin(_Unary):
+    def f(self, env, a): return np.arcsin(a)
+    def d(self, a): return Rsqrt(1 - Square(a))
+
+
+class Acos(_Unary):
+    def f(self, env, a): return np.arccos(a)
+    def d(self, a): return -Rsqrt(1 - Square(a))
+
+
+class XLogX(_Unary):
+    def f(self, env, a):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(a != 0, a * np.log(a), env.dtype.type(0))
+    def d(self, a): return Log(a) + 1
+
+
+class Pow(_Unary):
+    def __init__(self, a, m):
+        super().__init__(a)
+        self.m = int(m)
+    def f(self, env, a): return np.power(a, self.m).astype(env.dtype)
+    def d(self, a): return self.m * Pow(a, self.m - 1) if self.m != 1 else Cst(1)
+
+
+class Powf(_Elementwise):
+    # reference quirk: ``keops_powf`` is the C *float* function ``powf`` for every dtype
+    # (``utils/math_functions.py:97-99``), so fp64 formulas get a float32-accurate power.
+    def f(self, env, a, b): return np.power(a.astype(np.float32), b.astype(np.float32)).astype(env.dtype)
+    def difft(self, v, g):
+        a, b = self.children                                                     # maths/Powf.py
+        return a.difft(v, _red(g * (b * Powf(a, b - 1)), a.dim)) + b.difft(v, _red(g * (Log(a) * self), b.dim))
+
+
+class LessThan(_Elementwise):
+    def f(self, env, a, b): return (a < b).astype(env.dtype)
+    def difft(self, v, g): return Zero(v.dim)
+
+
+class LessOrEqual(_Elementwise):
+    def f(self, env, a, b): return (a <= b).astype(env.dtype)
+    def difft(self, v, g): return Zero(v.dim)
+
+
+class IfElse(_Elementwise):
+    def f(self, env, c, a, b): return np.where(c >= 0, a, b)                     # math_functions.py keops_ifelse
+    def difft(self, v, g):
+        c, a, b = self.children
+        z = Zero(g.dim)
+        return a.difft(v, _red(IfElse(c, g, z), a.dim)) + b.difft(v, _red(IfElse(c, z, g), b.dim))
+
+
+class _Sum(Op):
+
+    def __init__(self, a):
+        self.children = (a,)
+        self.dim = 1
+
+    def ev(self, env):
+        a = self.children[0].ev(env)
+        acc = a[..., 0:1].copy()                 # out = 0; out += a[k], k = 0..dim-1
+        for k in range(1, a.shape[-1]):
+            acc = acc + a[..., k:k + 1]
+        return acc
+
+    def difft(self, v, g):
+        a = self.children[0]
+        return a.difft(v, SumT(g, a.dim))                                        # maths/Sum.py:26-30
+
+
+
+def Sum(a):
+    if a.dim == 1:
+        return a
+    if a.iszero():
+        return Zero(1)
+    return _Sum(a)
+
+class _SumT(Op):
+
+    def __init__(self, a, dim):
+        self.children = (a,)
+        self.dim = int(dim)
+
+    def ev(self, env):
+        a = self.children[0].ev(env)
+        return np.broadcast_to(a, a.shape[:-1] + (self.dim,))
+
+    def difft(self, v, g):
+        return self.children[0].difft(v, Sum(g))                                 # maths/SumT.py:28-32
+
+
+
+def SumT(a, dim):
+    if dim == 1:
+        return a
+    if a.iszero():
+        return Zero(dim)
+    return _SumT(a, dim)
+
+class _Scalprod(Op):
+
+    def __init__(self, a, b):
+        if a.dim != b.dim:
+            raise ValueError("Scalprod: dimensions must be the same")
+        self.children = (a, b)
+        self.dim = 1
+
+    def ev(self, env):
+        a, b = [c.ev(env) for c in self.children]
+        acc = a[..., 0:1] * b[..., 0:1]
+        for k in range(1, self.children[0].dim):
+            acc = acc + a[..., k:k + 1] * b[..., k:k + 1]
+        return acc
+
+    def difft(self, v, g):
+        a, b = self.children                                                     # maths/Scalprod.py:38-40
+        return a.difft(v, g * b) + b.difft(v, g * a)
+
+
+
+def Scalprod(a, b):
+    if _z(a, b):
+        return Zero(1)
+    return _Scalprod(a, b)
+
+class Concat(Op):
+    def __init__(self, a, b):
+        self.children = (a, b)
+        self.dim = a.dim + b.dim
+
+    def ev(self, env):
+        a, b = [c.ev(env) for c in self.children]
+        shp = np.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+        return np.concatenate([np.broadcast_to(a, shp + a.shape[-1:]), np.broadcast_to(b, shp + b.shape[-1:])], -1)
+
+    def difft(self, v, g):
+        a, b = self.children                                                     # maths/Concat.py:28-33
+        return a.difft(v, Extract(g, 0, a.dim)) + b.difft(v, Extract(g, a.dim, b.dim))
+
+
+class _Extract(Op):
+
+    def __init__(self, a, start, dim):
+        self.children = (a,)
+        self.start, self.dim = int(start), int(dim)
+
+    def ev(self, env):
+        return self.children[0].ev(env)[..., self.start:self.start + self.dim]
+
+    def difft(self, v, g):
+        a = self.children[0]
+        return a.difft(v, ExtractT(g, self.start, a.dim))                        # maths/Extract.py:31-35
+
+
+
+def Extract(a, start, dim):
+    if a.iszero():
+        return Zero(dim)
+    return _Extract(a, start, dim)
+
+class _ExtractT(Op):
+
+    def __init__(self, a, start, dim):
+        self.children = (a,)
+        self.start, self.dim = int(start), int(dim)
+
+    def ev(self, env):
+        a = self.children[0].ev(env)
+        out = np.zeros(a.shape[:-1] + (self.dim,), env.dtype)
+        out[..., self.start:self.start + a.shape[-1]] = a
+        return out
+
+    def difft(self, v, g):
+        a = self.children[0]
+        return a.difft(v, Extract(g, self.start, a.dim))
+
+
+
+def ExtractT(a, start, dim):
+    if a.iszero():
+        return Zero(dim)
+    return _ExtractT(a, start, dim)
+
+class Round(_Unary):
+    def __init__(self, a, d=0):
+        super().__init__(a)
+        self.d = int(d)
+    def f(self, env, a):                                                         # math_functions.py keops_round
+        r = lambda t: np.where(t >= 0, np.floor(t + 0.5), np.ceil(t - 0.5))     # C round(): half away from zero
+        if self.d == 0:
+            return r(a).astype(env.dtype)
+        s = env.dtype.type(10 ** self.d)
+        return (r(a * s) / s).astype(env.dtype)
+    def d_(self, a): return None
+    def difft(self, v, g): return Zero(v.dim)
+
+
+class Clamp(_Elementwise):
+    def f(self, env, x, a, b): return np.where(x < a, a, np.where(x > b, b, x))  # math_functions.py keops_clamp
+    def difft(self, v, g):
+        x, a, b = self.children                                                  # maths/Clamp.py (ClampInt form)
+        alt = ClampInt((x - a) / (b - a), 0, 1) * (b - a) + a
+        return alt.difft(v, g)
+
+
+class ClampInt(_Unary):
+    def __init__(self, a, lo, hi):
+        super().__init__(a)
+        self.lo, self.hi = int(lo), int(hi)
+    def f(self, env, a): return np.clip(a, env.dtype.type(self.lo), env.dtype.type(self.hi))
+    def d(self, a): return DiffClampInt(a, self.lo, self.hi)
+
+
+class DiffClampInt(_Unary):
+    def __init__(self, a, lo, hi):
+        super().__init__(a)
+        self.lo, self.hi = int(lo), int(hi)
+    def f(self, env, a): return np.where(a < self.lo, 0, np.where(a > self.hi, 0, 1)).astype(env.dtype)
+    def d(self, a): return None
+
+
+class TensorProd(Op):
+    def __init__(self, a, b):
+        self.children = (a, b)
+        self.dim = a.dim * b.dim
+    def ev(self, env):
+        a, b = [c.ev(env) for c in self.children]
+        return (a[..., :, None] * b[..., None, :]).reshape(np.broadcast_shapes(a.shape[:-1], b.shape[:-1]) + (self.dim,))
+    def difft(self, v, g):
+        a, b = self.children                                                     # maths/TensorProd.py
+        return a.difft(v, MatVecMult(g, b)) + b.difft(v, VecMatMult(a, g))
+
+
+class MatVecMult(Op):
+    def __init__(self, A, b):
+        self.children = (A, b)
+        self.dim = A.dim // b.dim
+    def ev(self, env):
+        A, b = [c.ev(env) for c in self.children]
+        m = self.children[1].dim
+        A = A.reshape(A.shape[:-1] + (self.dim, m))
+        acc = A[..., 0] * b[..., 0:1]
+        for k in range(1, m):
+            acc = acc + A[..., k] * b[..., k:k + 1]
+        return acc
+    def difft(self, v, g):
+        A, b = self.children                                                     # maths/MatVecMult.py
+        return A.difft(v, TensorProd(g, b)) + b.difft(v, VecMatMult(g, A))
+
+
+class VecMatMult(Op):
+    def __init__(self, b, A):
+        self.children = (b, A)
+        self.dim = A.dim // b.dim
+    def ev(self, env):
+        b, A = [c.ev(env) for c in self.children]
+        m = self.children[0].dim
+        A = A.reshape(A.shape[:-1] + (m, self.dim))
+        acc = b[..., 0:1] * A[..., 0, :]
+        for k in range(1, m):
+            acc = acc + b[..., k:k + 1] * A[..., k, :]
+        return acc
+    def difft(self, v, g):
+        b, A = self.children
+        return A.difft(v, TensorProd(b, g)) + b.difft(v, MatVecMult(A, g))
+
+
+def Elem(a, m): return Extract(a, m, 1)
+def ElemT(a, n, m): return ExtractT(a, m, n)
+def SqNorm2(a): return Sum(Square(a))                                            # maths/SqNorm2.py
+def Norm2(a): return Sqrt(Scalprod(a, a))                                        # maths/Norm2.py
+def Normalize(a): return Rsqrt(SqNorm2(a)) * a                                   # maths/Normalize.py
+def SqDist(a, b): return SqNorm2(a - b)                                          # maths/SqDist.py
+
+
+def WeightedSqNorm(A, x):
+    if A.dim == 1:
+        return A * SqNorm2(x)
+    if A.dim == x.dim:
+        return Sum(A * Square(x))
+    raise NotImplementedError("SymSqNorm is not restated in the oracle")
+
+
+def WeightedSqDist(A, x, y): return WeightedSqNorm(A, x - y)
+
+
+# ------------------------------------------------------------------------------------------
+# reductions
+# ------------------------------------------------------------------------------------------
+class Reduction:
+    def __init__(self, kind, F, tagI, K=1, G=None):
+        self.kind, self.F, self.tagI, self.K, self.G = kind, F, int(tagI), int(K), G
+
+    def vars(self):
+        out = dict(self.F.vars())
+        if self.G is not None:
+            out.update(self.G.vars())
+        return out
+
+
+def Sum_Reduction(F, tagI): return Reduction("Sum", F, tagI)
+def Zero_Reduction(dim, tagI): return Reduction("Zero", Zero(dim), tagI)
+def Max_SumShiftExpWeight_Reduction(F, tagI, G=None): return Reduction("LSE", F, tagI, G=_w(1 if G is None else G))
+Max_SumShiftExp_Reduction = Max_SumShiftExpWeight_Reduction
+def Min_Reduction(F, tagI): return Reduction("Min", F, tagI)
+def Max_Reduction(F, tagI): return Reduction("Max", F, tagI)
+def ArgMin_Reduction(F, tagI): return Reduction("ArgMin", F, tagI)
+def ArgMax_Reduction(F, tagI): return Reduction("ArgMax", F, tagI)
+def Min_ArgMin_Reduction(F, tagI): return Reduction("Min_ArgMin", F, tagI)
+def Max_ArgMax_Reduction(F, tagI): return Reduction("Max_ArgMax", F, tagI)
+def KMin_Reduction(F, K, tagI): return Reduction("KMin", F, tagI, K)
+def ArgKMin_Reduction(F, K, tagI): return Reduction("ArgKMin", F, tagI, K)
+def KMin_ArgKMin_Reduction(F, K, tagI): return Reduction("KMin_ArgKMin", F, tagI, K)
+
+
+def Grad_WithSavedForward(red, v, gradin, f0):
+    """``reductions/Sum_Reduction.py:42-45``, ``Max_SumShiftExpWeight_Reduction.py:89-103``,
+    ``ArgKMin_Reduction.py:33-37``."""
+    newtag = v.cat % 2
+    if red.kind == "Sum":
+        return Sum_Reduction(red.F.difft(v, gradin), newtag)
+    if red.kind == "LSE":
+        M = Extract(f0, 0, 1)
+        gS = Extract(gradin, 1, red.G.dim)
+        H = Exp(red.F - M) * red.G
+        return Sum_Reduction(H.difft(v, _red(gS, H.dim) if gS.dim != H.dim else gS), newtag)
+    if red.kind in ("ArgMin", "ArgMax", "ArgKMin", "Zero"):
+        return Zero_Reduction(v.dim, newtag)
+    raise NotImplementedError("no autodiff through " + red.kind)
+
+
+_NAMESPACE = {k: v for k, v in list(globals().items()) if k[0].isupper() and k not in ("Op", "Reduction", "Fraction")}
+_NAMESPACE.update({"Vi": lambda p, d: Var(p, d, 0), "Vj": lambda p, d: Var(p, d, 1), "Pm": lambda p, d: Var(p, d, 2)})
+
+
+def parse(formula, aliases=()):
+    local = {}
+    for k, alias in enumerate(aliases):
+        if alias is None or "=" not in alias:
+            continue
+        name, rhs = alias.replace(" ", "").split("=")
+        m = re.fullmatch(r"(Vi|Vj|Pm)\((\d+)(?:,(\d+))?\)", rhs)
+        if m:
+            cat = {"Vi": 0, "Vj": 1, "Pm": 2}[m.group(1)]
+            pos, dim = (k, int(m.group(2))) if m.group(3) is None else (int(m.group(2)), int(m.group(3)))
+            local[name] = Var(pos, dim, cat)
+        else:
+            local[name] = eval(rhs, dict(_NAMESPACE), {})
+    return eval(formula, dict(_NAMESPACE), local)
+
+
+# ------------------------------------------------------------------------------------------
+# evaluation
+# ------------------------------------------------------------------------------------------
+class _Env:
+    def __init__(self, args, dtype, tagI, rows):
+        self.args, self.dtype, self.tagI, self.rows = args, np.dtype(dtype), tagI, rows
+
+    def var(self, v):
+        a = np.asarray(self.args[v.ind], dtype=self.dtype)
+        if v.cat == 2:
+            return a.reshape(1, 1, v.dim)
+        a = a.reshape(-1, v.dim)
+        if v.cat == self.tagI:      # output-side variable: current chunk of rows
+            return a[self.rows][:, None, :]
+        return a[None, :, :]
+
+
+def genred(formula, aliases, args, dtype="float32", chunk_elems=1 << 24):
+    """Raw kernel output ``(nrow, dim)`` of the reduction string, before any Python post-processing
+    (what ``LoadKeOps.genred`` returns, ``pykeops/pykeops/common/keops_io/LoadKeOps.py:177-243``)."""
+    red = parse(formula, aliases)
+    dtype = np.dtype(dtype)
+    vs = red.vars()
+    tagI = red.tagI
+    nrow = ncol = None
+    for v in vs.values():
+        if v.cat == 2:
+            continue
+        n = np.asarray(args[v.ind]).reshape(-1, v.dim).shape[0]
+        if v.cat == tagI:
+            nrow = n
+        else:
+            ncol = n
+    if nrow is None or ncol is None:
+        raise ValueError("oracle.genred needs at least one i- and one j-variable (or explicit sizes)")
+    F, G, K = red.F, red.G, red.K
+    d = F.dim
+    kind = red.kind
+    dimout = {"Sum": d, "Zero": d, "Min": d, "Max": d, "ArgMin": d, "ArgMax": d, "Min_ArgMin": 2 * d, "Max_ArgMax": 2 * d,
+              "KMin": K * d, "ArgKMin": K * d, "KMin_ArgKMin": 2 * K * d}.get(kind)
+    if kind == "LSE":
+        dimout = 1 + G.dim
+    out = np.zeros((nrow, dimout), dtype)
+    if kind == "Zero" or nrow == 0:
+        return out
+    step = max(1, chunk_elems // max(1, ncol * max(d, 1)))
+    for r0 in range(0, nrow, step):
+        rows = slice(r0, min(nrow, r0 + step))
+        nr = rows.stop - rows.start
+        env = _Env(args, dtype, tagI, rows)
+        Fv = np.broadcast_to(F.ev(env), (nr, ncol, d))
+        if kind == "Sum":
+            out[rows] = Fv.sum(axis=1, dtype=np.float64).astype(dtype)
+        elif kind == "LSE":
+            Gv = np.broadcast_to(G.ev(env), (nr, ncol, G.dim))
+            if ncol == 0:
+                out[rows, 0] = -np.inf
+                continue
+            m = Fv.max(axis=1)                                    # (nr, 1)
+            e = np.exp(Fv - m[:, None, :])
+            s = (e * Gv).sum(axis=1, dtype=np.float64)
+            out[rows, 0:1] = m
+            out[rows, 1:] = s.astype(dtype)
+        elif kind in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
+            if ncol == 0:
+                val = np.full((nr, d), np.inf if "Min" in kind else -np.inf, dtype)
+                idx = np.zeros((nr, d), np.int64)
+            else:
+                idx = Fv.argmin(axis=1) if "Min" in kind else Fv.argmax(axis=1)     # first extremum wins
+                val = np.take_along_axis(Fv, idx[:, None, :], axis=1)[:, 0, :]
+            if kind in ("Min", "Max"):
+                out[rows] = val
+            elif kind in ("ArgMin", "ArgMax"):
+                out[rows] = idx.astype(dtype)
+            else:
+                out[rows, :d] = val
+                out[rows, d:] = idx.astype(dtype)
+        else:
+            order = np.argsort(Fv, axis=1, kind="stable")[:, :K, :]                 # ties -> smallest index
+            vals = np.take_along_axis(Fv, order, axis=1)
+            kk = order.shape[1]
+            v_full = np.full((nr, K, d), np.inf, dtype)
+            i_full = np.zeros((nr, K, d), dtype)
+            v_full[:, :kk] = vals
+            i_full[:, :kk] = order.astype(dtype)
+            if kind == "KMin":
+                out[rows] = v_full.reshape(nr, K * d)
+            elif kind == "ArgKMin":
+                out[rows] = i_full.reshape(nr, K * d)
+            else:
+                out[rows] = np.stack([v_full, i_full], axis=2).reshape(nr, 2 * K * d)
+    return out
+
+
+def dense(formula, aliases, args, dtype="float64"):
+    """Dense ``(nrow, ncol, dimF)`` values of the reduction's formula (small cases only); used by the
+    tests to decide whether an index mismatch is a genuine near-tie."""
+    red = parse(formula, aliases)
+    tagI = red.tagI
+    nrow = ncol = None
+    for v in red.vars().values():
+        if v.cat == 2:
+            continue
+        n = np.asarray(args[v.ind]).reshape(-1, v.dim).shape[0]
+        if v.cat == tagI:
+            nrow = n
+        else:
+            ncol = n
+    env = _Env(args, np.dtype(dtype), tagI, slice(0, nrow))
+    return np.broadcast_to(red.F.ev(env), (nrow, ncol, red.F.dim)).copy()

@@ -1,0 +1,197 @@
+"""Generate golden input/output vectors by running the REAL reference (getkeops/keops v2.3, CPU
+backend ``CpuReduc``) in the build container.  The reference cannot travel to the GPU box, so the
+vectors are committed under ``tests/golden/cases/`` together with this script.
+
+Run (from the repo root, in the container where /root/reference is mounted)::
+
+    CXX=/usr/bin/g++ KEOPS_CACHE_FOLDER=/tmp/keops_cache \
+    PYTHONPATH=/root/reference/keopscore:/root/reference/pykeops python tests/golden/make_golden.py
+
+Each case stores: the reduction string exactly as ``pykeops`` hands it to its binder
+(``keops_binder[...](..., formula, aliases, nargs, dtype, 'torch', optional_flags)``,
+``pykeops/pykeops/torch/generic/generic_red.py:91-103``), the input arrays, and the *raw* binder output
+(before ``postprocess``).  Inputs are drawn from a fixed-seed numpy generator.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "cases")
+
+G = "Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,1,1)),0)"
+C4 = "Max_SumShiftExp_Reduction((Var(0,1,1) - ((Sum(Square((Var(1,3,0) - Var(2,3,1)))) / IntCst(2)) / Var(3,1,2))),0)"
+
+
+def V(k, d, c):
+    return "Var(%d,%d,%d)" % (k, d, c)
+
+
+# name, formula, [(dim, cat, kind)], dtype, (nx, ny)
+#   kind: 'u' uniform[0,1), 'n' normal, 'p' positive uniform[0.5,2), 'eps' small positive scalar
+CASES = []
+
+
+def case(name, formula, args, dtypes=("float32", "float64"), sizes=(57, 83), aliases=None):
+    for dt in dtypes:
+        CASES.append(dict(name="%s_%s" % (name, dt), formula=formula, args=args, dtype=dt, sizes=sizes,
+                          aliases=aliases))
+
+
+XYB = [(3, 0, "u"), (3, 1, "u"), (1, 1, "u")]
+case("gauss_sum", G, XYB)
+case("gauss_grad_x", "Grad_WithSavedForward(%s,%s,%s,%s)" % (G, V(0, 3, 0), V(3, 1, 0), V(4, 1, 0)),
+     XYB + [(1, 0, "n"), (1, 0, "n")])
+case("gauss_grad_y", "Grad_WithSavedForward(%s,%s,%s,%s)" % (G, V(1, 3, 1), V(3, 1, 0), V(4, 1, 0)),
+     XYB + [(1, 0, "n"), (1, 0, "n")])
+case("gauss_grad_b", "Grad_WithSavedForward(%s,%s,%s,%s)" % (G, V(2, 1, 1), V(3, 1, 0), V(4, 1, 0)),
+     XYB + [(1, 0, "n"), (1, 0, "n")])
+case("gauss_sum_axis0", G[:-3] + ",1)", XYB)
+case("gauss_randn_200x300", G, [(3, 0, "n"), (3, 1, "n"), (1, 1, "n")], sizes=(200, 300))
+case("gauss_vec_b", "Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,5,1)),0)",
+     [(3, 0, "u"), (3, 1, "u"), (5, 1, "n")])
+for K, D in ((3, 3), (10, 3), (10, 64), (1, 2)):
+    case("argkmin_K%d_D%d" % (K, D),
+         "ArgKMin_Reduction(Sum(Square((Var(0,%d,0) - Var(1,%d,1)))),%d,0)" % (D, D, K),
+         [(D, 0, "n"), (D, 1, "n")], sizes=(64, 301))
+case("argkmin_axis0", "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),4,1)", [(3, 0, "n"), (3, 1, "n")],
+     sizes=(151, 40))
+case("kmin", "KMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),5,0)", [(3, 0, "n"), (3, 1, "n")])
+case("kmin_argkmin", "KMin_ArgKMin_Reduction(Sqrt(Sum(Square((Var(0,3,0) - Var(1,3,1))))),5,0)",
+     [(3, 0, "n"), (3, 1, "n")])
+case("kmin_argkmin_vec", "KMin_ArgKMin_Reduction(Square((Var(0,2,0) - Var(1,2,1))),3,0)", [(2, 0, "n"), (2, 1, "n")])
+case("min", "Min_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),0)", [(3, 0, "n"), (3, 1, "n")])
+case("argmin", "ArgMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),0)", [(3, 0, "n"), (3, 1, "n")])
+case("min_argmin", "Min_ArgMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),0)", [(3, 0, "n"), (3, 1, "n")])
+case("min_argmin_vec_axis0", "Min_ArgMin_Reduction((Var(0,3,0) - Var(1,3,1)),1)", [(3, 0, "n"), (3, 1, "n")])
+case("max", "Max_Reduction((Var(0,3,0) * Var(1,3,1)),0)", [(3, 0, "n"), (3, 1, "n")])
+case("argmax", "ArgMax_Reduction((Var(0,3,0) | Var(1,3,1)),0)", [(3, 0, "n"), (3, 1, "n")])
+case("max_argmax", "Max_ArgMax_Reduction((Var(0,3,0) | Var(1,3,1)),1)", [(3, 0, "n"), (3, 1, "n")])
+LSE_ARGS = [(1, 1, "u"), (3, 0, "u"), (3, 1, "u"), (1, 2, "eps")]
+case("lse_softmin", C4, LSE_ARGS)
+case("lse_grad_x", "Grad_WithSavedForward(%s,%s,%s,%s)" % (C4, V(1, 3, 0), V(4, 2, 0), V(5, 2, 0)),
+     LSE_ARGS + [(2, 0, "n"), ("lse_fwd", 0, C4)])
+case("lse_grad_f", "Grad_WithSavedForward(%s,%s,%s,%s)" % (C4, V(0, 1, 1), V(4, 2, 0), V(5, 2, 0)),
+     LSE_ARGS + [(2, 0, "n"), ("lse_fwd", 0, C4)])
+case("lse_grad_eps", "Grad_WithSavedForward(%s,%s,%s,%s)" % (C4, V(3, 1, 2), V(4, 2, 0), V(5, 2, 0)),
+     LSE_ARGS + [(2, 0, "n"), ("lse_fwd", 0, C4)])
+case("lse_weighted", "Max_SumShiftExpWeight_Reduction((Var(0,3,0) | Var(1,3,1)),0,Var(2,2,1))",
+     [(3, 0, "n"), (3, 1, "n"), (2, 1, "n")])
+case("sumsoftmaxweight", "Max_SumShiftExpWeight_Reduction((Var(0,3,0) | Var(1,3,1)),0,Concat(IntCst(1),Var(2,2,1)))",
+     [(3, 0, "n"), (3, 1, "n"), (2, 1, "n")])
+case("lse_axis0", "Max_SumShiftExp_Reduction(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1))))),1)", [(3, 0, "n"), (3, 1, "n")])
+case("kernelsolve_matvec", "Sum_Reduction(Exp(-g*SqDist(x,y))*b,0)",
+     [(16, 0, "u"), (16, 1, "u"), (1, 1, "n"), (1, 2, "p")], aliases=["x=Vi(16)", "y=Vj(16)", "b=Vj(1)", "g=Pm(1)"])
+case("matern", "Sum_Reduction(Exp(-Sqrt(Sum(Square(x-y))))*(IntCst(1)+Sqrt(Sum(Square(x-y))))*b,0)",
+     [(3, 0, "u"), (3, 1, "u"), (2, 1, "n")], aliases=["x=Vi(3)", "y=Vj(3)", "b=Vj(2)"])
+OPS = {
+    "inv_log": "Sum_Reduction(Log(IntCst(1)+Sum(Square(x-y)))*Inv(IntCst(2)+(x|y))*b,0)",
+    "rsqrt_abs": "Sum_Reduction(Rsqrt(IntCst(1)+Sum(Abs(x-y)))*b,0)",
+    "sign_relu_step": "Sum_Reduction(Sum(Sign(x-y)*ReLU(x-y)+Step(y-x))*b,0)",
+    "ifelse": "Sum_Reduction(IfElse(x-y,x*y,x+y)*b,0)",
+    "pow_powf": "Sum_Reduction(Sum(Pow(x-y,3))*b+Powf(IntCst(1)+Sum(Square(x-y)),Elem(y,0)),0)",
+    "sincos": "Sum_Reduction(Sin(x|y)*Cos(Sum(x-y))*b,0)",
+    "normalize_norm2": "Sum_Reduction((Normalize(x)|y)*Norm2(x-y)*b,0)",
+    "concat_extract": "Sum_Reduction(Concat(Extract(x,1,2)*Elem(y,0),Sum(y)*b),0)",
+    "sumT_elemT": "Sum_Reduction(SumT(b,3)*x+ElemT(Elem(y,2),3,1),0)",
+    "matvec": "Sum_Reduction(MatVecMult(TensorProd(x,y),x)*b,0)",
+    "clamp": "Sum_Reduction(Clamp(x-y,IntCst(0),b+IntCst(1)),0)",
+    "div_scalar": "Sum_Reduction((x-y)/(IntCst(1)+Sum(Square(y)))*b,0)",
+    "weightedsqdist": "Sum_Reduction(Exp(-WeightedSqDist(b+IntCst(1),x,y)),0)",
+    "xlogx_sqrt": "Sum_Reduction(Sum(XLogX(IntCst(1)+Square(x-y)))*Sqrt(b*b),0)",
+    "atan_round": "Sum_Reduction(Atan(x|y)*Round(IntCst(3)*b,0)+Floor(Sum(x)*b),0)",
+}
+for nm, f in OPS.items():
+    ali = ["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"]
+    case("op_" + nm, f, [(3, 0, "u"), (3, 1, "u"), (1, 1, "p")], dtypes=("float32",), aliases=ali)
+GRAD_OPS = ["inv_log", "rsqrt_abs", "ifelse", "pow_powf", "sincos", "normalize_norm2", "concat_extract", "matvec",
+            "div_scalar", "weightedsqdist", "xlogx_sqrt", "clamp"]
+for nm in GRAD_OPS:
+    f = OPS[nm]
+    ali = ["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"]
+    for vname, vstr in (("x", V(0, 3, 0)), ("y", V(1, 3, 1)), ("b", V(2, 1, 1))):
+        if (nm, vname) == ("ifelse", "b"):
+            # reference quirk: IfElse.DiffT (formulas/maths/IfElse.py) broadcasts the gradient to the
+            # dimension of the condition, so d/db comes back with dim 3 instead of 1 -- not a parity target
+            continue
+        case("grad_%s_%s" % (nm, vname), "Grad_WithSavedForward(%s,%s,%s,%s)" % (f, vstr, "Var(3,DIMOUT,0)", "Var(4,DIMOUT,0)"),
+             [(3, 0, "u"), (3, 1, "u"), (1, 1, "p"), ("eta", 0, f), ("fwd", 0, f)], dtypes=("float64",),
+             aliases=ali + ["Var(3,DIMOUT,0)", "Var(4,DIMOUT,0)"])
+
+
+def flags(formula):
+    head = formula.split("(")[0]
+    sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
+                       "Grad_WithSavedForward")
+    return dict(dtype_acc="auto", sum_scheme="block_sum" if sumlike else "direct_sum", use_fast_math=1,
+                enable_chunks=1, multVar_highdim=0)
+
+
+def run_reference(formula, aliases, args, dtype, nx, ny):
+    import torch
+    from pykeops.common.keops_io import keops_binder
+
+    targs = [torch.from_numpy(np.ascontiguousarray(a)) for a in args]
+    b = keops_binder["cpp"](0, 0, 0, False, -1, formula, list(aliases), len(targs), dtype, "torch", flags(formula))
+    out = b.import_module().genred_pytorch(targs[0].device, None, nx, ny, 0, None, *targs)
+    return out.numpy().copy(), int(b.dimout), int(b.tagIJ)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20260101)
+    index = []
+    only = sys.argv[1:]
+    for c in CASES:
+        if only and not any(o in c["name"] for o in only):
+            continue
+        dt = np.dtype(c["dtype"])
+        nx, ny = c["sizes"]
+        args = []
+        formula, aliases = c["formula"], c["aliases"]
+        for spec in c["args"]:
+            dim, cat, kind = spec
+            n = {0: nx, 1: ny}.get(cat)
+            if dim in ("lse_fwd", "fwd", "eta"):
+                # saved forward output (or a random upstream gradient of the same shape)
+                fwd, dimout, _ = run_reference(kind, aliases[:3] if aliases else [], args[:4 if dim == "lse_fwd" else 3],
+                                               c["dtype"], nx, ny)
+                if dim == "eta":
+                    a = rng.standard_normal(fwd.shape).astype(dt)
+                else:
+                    a = fwd.astype(dt)
+                args.append(a)
+                continue
+            shape = (dim,) if cat == 2 else (n, dim)
+            if kind == "u":
+                a = rng.random(shape)
+            elif kind == "n":
+                a = rng.standard_normal(shape)
+            elif kind == "p":
+                a = 0.5 + 1.5 * rng.random(shape)
+            elif kind == "eps":
+                a = np.full(shape, 0.05)
+            args.append(a.astype(dt))
+        if "DIMOUT" in formula:
+            dimout = args[-1].shape[1]
+            formula = formula.replace("DIMOUT", str(dimout))
+            aliases = [a.replace("DIMOUT", str(dimout)) for a in aliases]
+        if aliases is None:
+            aliases = []
+        out, dimout, tagIJ = run_reference(formula, aliases, args, c["dtype"], nx, ny)
+        path = os.path.join(OUT, c["name"] + ".npz")
+        meta = dict(name=c["name"], formula=formula, aliases=aliases, dtype=c["dtype"], nx=nx, ny=ny,
+                    nargs=len(args), dimout=dimout, tagIJ=tagIJ)
+        np.savez_compressed(path, out=out, meta=json.dumps(meta), **{"arg%d" % k: a for k, a in enumerate(args)})
+        index.append(meta)
+        print("%-40s out %s  tagIJ=%d" % (c["name"], out.shape, tagIJ))
+    if not only:
+        with open(os.path.join(HERE, "index.json"), "w") as f:
+            json.dump(index, f, indent=1)
+    print("wrote %d cases" % len(index))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

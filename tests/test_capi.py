@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/kb200.h declares;
+NVRTC cross-compiles generated kernels to sm_100a cubins here (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "kb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(kb200_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from keops_b200.runtime import capi
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), "libkb200.so does not export %s" % s
+    assert set(syms) == set(capi.EXPORTED_SYMBOLS)
+    assert lib.kb200_abi_version() == 1
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from keops_b200.runtime import capi
+    with pytest.raises(capi.KB200Error) as e:
+        capi.device_info(0)
+    assert e.value.status == capi.KB200_ENOCUDA
+
+
+def test_nvrtc_reports_the_compiler_log():
+    from keops_b200.runtime import capi
+    with pytest.raises(capi.KB200CompileError) as e:
+        capi.compile_to_cubin("__global__ void k() { this is not cuda; }")
+    assert "error" in str(e.value)
+
+
+def test_generated_kernel_compiles_to_sm100a_with_packed_fp32():
+    from keops_b200.formulas.parser import parse_reduction
+    from keops_b200.codegen.emit import generate
+    from keops_b200.runtime import capi, plan
+    red = parse_reduction("Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,1,1)),0)")
+    ks = generate(red, "float32", 3, plan.default_config(red, "float32"))
+    cubin = capi.compile_to_cubin(ks.source, plan.nvrtc_options(True))
+    assert cubin[:4] == b"\x7fELF"
+    path = "/tmp/kb200_test_%d.cubin" % os.getpid()
+    open(path, "wb").write(cubin)
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    except FileNotFoundError:
+        pytest.skip("cuobjdump not available")
+    finally:
+        pass
+    os.remove(path)
+    assert "sm_100a" in sass or "SM100a" in sass or "EF_CUDA_SM100" in sass
+    for mnemonic in ("FFMA2", "FADD2", "FMUL2", "MUFU.EX2", "LDGSTS", "LDS.128"):
+        assert mnemonic in sass, mnemonic
+    assert "LDL" not in sass and "STL" not in sass  # no local-memory spills
+
+
+def test_binder_refuses_cpu_backend():
+    from keops_b200.binder import LoadKeOpsB200
+    flags = dict(dtype_acc="auto", sum_scheme="auto", use_fast_math=1, enable_chunks=1, multVar_highdim=0)
+    with pytest.raises(ValueError):
+        LoadKeOpsB200(0, 0, 0, False, -1, "Sum_Reduction(Var(0,1,0)*Var(1,1,1),0)", [], 2, "float32", "torch", flags)

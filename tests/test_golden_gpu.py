@@ -1,0 +1,81 @@
+"""GPU: the CUDA path, called through the C-ABI (libkb200.so) behind the reference's binder
+interface, against golden outputs of the real reference (tests/golden/make_golden.py).
+
+Tolerances (BASELINE.json north_star): fp32 within 1e-5 relative, fp64 within 1e-12 relative,
+indices bit-exact except genuine near-ties (checked explicitly against dense fp64 values)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def run_binder(meta, args, device, flags=None):
+    from keops_b200.binder import LoadKeOpsB200
+    f = util.default_flags(meta["formula"])
+    if flags:
+        f.update(flags)
+    b = LoadKeOpsB200(1, 0, 1, False, -1, meta["formula"], meta["aliases"], meta["nargs"], meta["dtype"], "torch", f)
+    targs = [torch.from_numpy(np.ascontiguousarray(a)).to(device) for a in args]
+    out = b.import_module().genred_pytorch(device, None, meta["nx"], meta["ny"], 0, None, *targs)
+    torch.cuda.synchronize()
+    return b, out.cpu().numpy()
+
+
+def check_indices(meta, args, got_idx, ref_idx, slot_to_comp, what):
+    """Indices must match bit-exactly unless the two candidates are a near-tie in value."""
+    if np.array_equal(got_idx, ref_idx):
+        return
+    from oracle import keops_oracle as ko
+    F = ko.dense(meta["formula"], meta["aliases"], args, "float64")
+    bad = np.argwhere(got_idx != ref_idx)
+    assert len(bad) <= max(1, got_idx.size // 200), "%s: %d index mismatches" % (what, len(bad))
+    eps = 2.0 ** -22 if meta["dtype"] == "float32" else 2.0 ** -50
+    for r, s in bad:
+        c = slot_to_comp(s)
+        j1, j2 = int(got_idx[r, s]), int(ref_idx[r, s])
+        v1, v2 = F[r, j1, c], F[r, j2, c]
+        assert abs(v1 - v2) <= eps * max(abs(v1), abs(v2), 1e-30), \
+            "%s: row %d slot %d: got j=%d (%.9g) ref j=%d (%.9g) is not a tie" % (what, r, s, j1, v1, j2, v2)
+
+
+@pytest.mark.parametrize("name", util.golden_names())
+def test_cuda_matches_reference(name, cuda_device):
+    meta, args, ref = util.load_case(name)
+    b, got = run_binder(meta, args, cuda_device)
+    assert b.dimout == meta["dimout"] and b.tagIJ == meta["tagIJ"]
+    assert got.shape == ref.shape
+    head = meta["formula"].split("(")[0]
+    d = b.red.dimF
+    if head in ("ArgMin_Reduction", "ArgMax_Reduction"):
+        check_indices(meta, args, got, ref, lambda s: s, name)
+    elif head == "ArgKMin_Reduction":
+        check_indices(meta, args, got, ref, lambda s: s % d, name)
+    elif head in ("Min_ArgMin_Reduction", "Max_ArgMax_Reduction"):
+        util.assert_close(got[:, :d], ref[:, :d], meta["dtype"], name)
+        check_indices(meta, args, got[:, d:], ref[:, d:], lambda s: s, name)
+    elif head == "KMin_ArgKMin_Reduction":
+        g3, r3 = got.reshape(len(got), -1, 2, d), ref.reshape(len(ref), -1, 2, d)
+        util.assert_close(g3[:, :, 0], r3[:, :, 0], meta["dtype"], name)
+        check_indices(meta, args, g3[:, :, 1].reshape(len(got), -1), r3[:, :, 1].reshape(len(ref), -1),
+                      lambda s: s % d, name)
+    else:
+        util.assert_close(got, ref, meta["dtype"], name, rtol=util.rtol_for(meta))
+
+
+@pytest.mark.parametrize("name", [n for n in util.golden_names() if n.startswith(("gauss_sum_float", "lse_softmin", "argkmin_K10_D3"))])
+@pytest.mark.parametrize("flags", [dict(use_fast_math=0), dict(sum_scheme="direct_sum"), dict(sum_scheme="kahan_scheme")])
+def test_option_variants(name, flags, cuda_device):
+    meta, args, ref = util.load_case(name)
+    head = meta["formula"].split("(")[0]
+    if "sum_scheme" in flags and head not in ("Sum_Reduction", "Max_SumShiftExp_Reduction"):
+        pytest.skip("sum schemes only apply to sum-type reductions")
+    if flags.get("sum_scheme") == "kahan_scheme" and head != "Sum_Reduction":
+        pytest.skip("kahan implemented for Sum only")
+    b, got = run_binder(meta, args, cuda_device, flags)
+    if head == "ArgKMin_Reduction":
+        check_indices(meta, args, got, ref, lambda s: s % b.red.dimF, name)
+    else:
+        util.assert_close(got, ref, meta["dtype"], name)
