@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB200_ABI_VERSION 1
+#define KB200_ABI_VERSION 2
 
 #define KB200_OK 0
 #define KB200_ENOCUDA 20001  /* libcuda.so.1 could not be loaded / cuInit failed        */
@@ -105,11 +105,16 @@ int kb200_launch(kb200_function fn, void* stream, unsigned grid_x, unsigned grid
  *                           scheme needs `workspace` of nsplit*nrow*dimpart elements when nsplit > 1
  *   out                     device pointer, nrow * dim elements
  *   args / nargs            device pointers of the formula's variables, in Var index order
+ *   nbatch, batch_strides   number of independent problems (gridDim.z, 1..65535) and, per argument,
+ *                           the element stride between two problems (0 = argument shared by all;
+ *                           NULL = all zero).  `out` / `workspace` are batch-major.  This replaces
+ *                           the reference's emulation of batch dimensions through block-diagonal
+ *                           ranges (keopscore/keopscore/include/Ranges.h:40-86).
  * All pointers are device pointers of the formula dtype (float or double).                       */
 int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, void* stream,
                         int64_t nrow, int64_t ncol, int rows_per_block, int block, int nsplit,
                         int64_t col_chunk, void* out, void* workspace, int nargs,
-                        const void* const* args);
+                        const void* const* args, int nbatch, const int64_t* batch_strides);
 
 #ifdef __cplusplus
 }

@@ -9,3 +9,35 @@ __version__ = "0.1.0"
 from .runtime import capi as _capi  # noqa: F401  (fails loudly if the native runtime is missing)
 from .binder import LoadKeOpsB200, get_binder, register_into_pykeops  # noqa: F401
 from .runtime.plan import clean_cache  # noqa: F401
+
+
+def install_as_pykeops():
+    """Make ``import pykeops`` / ``from pykeops.torch import LazyTensor, Genred, KernelSolve`` resolve to
+    this package, so existing user code runs unchanged on the B200 engine."""
+    import sys
+    import types
+    from . import torch as _t
+
+    if "pykeops" in sys.modules and not getattr(sys.modules["pykeops"], "__kb200_shim__", False):
+        raise RuntimeError("a real pykeops is already imported; use keops_b200.register_into_pykeops() instead")
+    root = types.ModuleType("pykeops")
+    root.__kb200_shim__ = True
+    root.__version__ = "2.3+kb200." + __version__
+    root.torch = _t
+    root.clean_pykeops = clean_cache
+    root.test_torch_bindings = lambda: _smoke_install()
+    sys.modules["pykeops"] = root
+    sys.modules["pykeops.torch"] = _t
+    return root
+
+
+def _smoke_install():
+    """Same known answer as ``pykeops/pykeops/torch/test_install.py:5-25``."""
+    import torch as th
+    from .torch import Genred
+    x = th.arange(1, 10, dtype=th.float32).view(-1, 3).cuda()
+    y = th.arange(3, 9, dtype=th.float32).view(-1, 3).cuda()
+    out = Genred("SqNorm2(x-y)", ["x=Vi(3)", "y=Vj(3)"], reduction_op="Sum", axis=0)(x, y)
+    ok = th.allclose(out.view(-1).cpu(), th.tensor([63.0, 90.0]))
+    print("pyKeOps-B200 bindings are working!" if ok else "pyKeOps-B200: outputs wrong values...")
+    return ok

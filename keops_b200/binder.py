@@ -140,8 +140,6 @@ class LoadKeOpsB200:
         p = self.params
         if ranges:
             raise NotImplementedError("[KeOps-B200] block-sparse `ranges` are not implemented yet.")
-        if nbatchdims:
-            raise NotImplementedError("[KeOps-B200] batch dimensions are not implemented yet.")
         if len(args) != p.nargs:
             raise ValueError("[KeOps-B200] expected %d arguments, got %d" % (p.nargs, len(args)))
         tdtype = torch.float32 if p.dtype == "float32" else torch.float64
@@ -158,26 +156,55 @@ class LoadKeOpsB200:
         if dev is None:
             raise ValueError("[KeOps-B200] at least one argument is required")
         nx, ny = int(nx), int(ny)
-        # shape checks (subset of Sizes<T>, keopscore/keopscore/include/Sizes.h:262-411)
-        fixed = []
+        nb = int(nbatchdims or 0)
+        # ---- shapes: [batch..., n, dim] for variables, [batch..., dim] for parameters
+        #      (subset of Sizes<T>, keopscore/keopscore/include/Sizes.h:262-411)
+        batch_shape = ()
+        if nb:
+            shapes = []
+            for ind, (dim, cat) in self._vars.items():
+                a = args[ind]
+                lead = a.shape[:-1] if cat == 2 else a.shape[:-2]
+                lead = (1,) * (nb - len(lead)) + tuple(lead)
+                shapes.append(lead)
+            batch_shape = tuple(torch.broadcast_shapes(*shapes)) if shapes else (1,) * nb
+        nbatch = 1
+        for b_ in batch_shape:
+            nbatch *= int(b_)
+        args = list(args)
+        strides = [0] * p.nargs
         for ind, (dim, cat) in self._vars.items():
             a = args[ind]
-            if cat == 2:
+            tail = (dim,) if cat == 2 else ((nx if cat == 0 else ny), dim)
+            if cat == 2 and nb == 0:
                 if a.numel() != dim:
                     raise ValueError("[KeOps] Wrong value of the 'vector size' dimension for arg number %d : is %d but should be %d"
                                      % (ind, a.numel(), dim))
+                args[ind] = a.reshape(dim).contiguous()
+                continue
+            if a.dim() < len(tail) or tuple(a.shape[-len(tail):]) != tail:
+                raise ValueError("[KeOps] Wrong shape for arg number %d : is %s but should end with %s"
+                                 % (ind, tuple(a.shape), tail))
+            lead = tuple(a.shape[:-len(tail)])
+            lead = (1,) * (nb - len(lead)) + lead
+            if len(lead) != nb:
+                raise ValueError("[KeOps] Wrong number of batch dimensions for arg number %d" % ind)
+            per = 1
+            for t_ in tail:
+                per *= t_
+            if all(l == 1 for l in lead):
+                args[ind] = a.reshape(tail).contiguous()           # shared by every batch
             else:
-                n_expected = nx if cat == 0 else ny
-                if a.dim() != 2 or a.shape[1] != dim:
-                    raise ValueError("[KeOps] Wrong value of the 'vector size' dimension 1 for arg number %d : is %s but should be %d"
-                                     % (ind, tuple(a.shape), dim))
-                if a.shape[0] != n_expected:
-                    raise ValueError("[KeOps] Wrong value of the '%s' dimension 0 for arg number %d : is %d but should be %d"
-                                     % ("ij"[cat], ind, a.shape[0], n_expected))
-        args = tuple(a if a.is_contiguous() else a.contiguous() for a in args)
+                if lead != batch_shape:                           # partial broadcast: materialise it
+                    a = a.reshape(lead + tail).expand(batch_shape + tail)
+                args[ind] = a.contiguous()
+                strides[ind] = per
+        for k in range(p.nargs):
+            if k not in self._vars:
+                args[k] = args[k].contiguous()
 
         nrow, ncol = (nx, ny) if p.tagI == 0 else (ny, nx)
-        shapeout = (nrow, p.dim)
+        shapeout = batch_shape + (nrow, p.dim)
         if out is None:
             out = torch.empty(shapeout, dtype=tdtype, device=dev)
         else:
@@ -187,27 +214,39 @@ class LoadKeOpsB200:
         if p.tagZero:
             out.zero_()
             return out
-        if nrow == 0:
+        if nrow == 0 or nbatch == 0:
             return out
         lk = self._kernel(dev.index if dev.index is not None else torch.cuda.current_device())
         ks = self.ks
         rows_per_block = ks.cfg.T * ks.cfg.R
         esz = 4 if p.dtype == "float32" else 8
-        if p.tag1D2D == 1 or True:
-            nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ,
-                                                  lk.sm_count * lk.blocks_per_sm, ks.dimpart, esz)
-        ws = None
-        if nsplit > 1:
-            ws = torch.empty(nsplit * nrow * ks.dimpart, dtype=tdtype, device=dev)
+        slots = max(1, (lk.sm_count * lk.blocks_per_sm) // min(nbatch, lk.sm_count * lk.blocks_per_sm))
+        nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
+                                              ws_limit_bytes=max(1, (2 << 30) // nbatch))
+        if p.tag1D2D == 1 and nsplit == 1 and ncol > 4 * ks.cfg.TJ:
+            # backend="GPU_2D": the caller asked for the split-column scheme explicitly
+            ntiles = -(-ncol // ks.cfg.TJ)
+            nsplit = min(8, ntiles)
+            col_chunk = -(-ntiles // nsplit) * ks.cfg.TJ
+            nsplit = -(-ncol // col_chunk)
+        BMAX = 65535
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            capi.genred_launch(lk.fn_reduce, lk.fn_combine, stream, nrow, ncol, rows_per_block, ks.cfg.T,
-                               nsplit, max(col_chunk, 1), out.data_ptr(), ws.data_ptr() if ws is not None else 0,
-                               [a.data_ptr() for a in args])
-        if ws is not None:
-            ws.record_stream(torch.cuda.current_stream(dev))
+            out_flat = out.view(nbatch, nrow * p.dim)
+            for b0 in range(0, nbatch, BMAX):
+                bn = min(BMAX, nbatch - b0)
+                ws = None
+                if nsplit > 1:
+                    ws = torch.empty(bn * nsplit * nrow * ks.dimpart, dtype=tdtype, device=dev)
+                ptrs = [a.data_ptr() + b0 * strides[k] * esz for k, a in enumerate(args)]
+                capi.genred_launch(lk.fn_reduce, lk.fn_combine, stream, nrow, ncol, rows_per_block, ks.cfg.T,
+                                   nsplit, max(col_chunk, 1), out_flat[b0].data_ptr(),
+                                   ws.data_ptr() if ws is not None else 0, ptrs, bn, strides)
+                if ws is not None:
+                    ws.record_stream(torch.cuda.current_stream(dev))
         self.last_launch = dict(nsplit=nsplit, col_chunk=col_chunk, grid_x=-(-nrow // rows_per_block),
-                                regs=lk.regs, blocks_per_sm=lk.blocks_per_sm)
+                                nbatch=nbatch, regs=lk.regs, blocks_per_sm=lk.blocks_per_sm,
+                                launches=(2 if nsplit > 1 else 1) * -(-nbatch // BMAX))
         return out
 
     genred_pytorch = genred

@@ -24,7 +24,7 @@ from ..formulas.reductions import Reduction
 from .lower import Lowerer
 from .scalar import Graph, SNode, SV, C, P, I, J, IJ, topo_order
 
-GENERATOR_VERSION = "kb200-gen-1"
+GENERATOR_VERSION = "kb200-gen-2"
 
 _PRELUDE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "kb200_device.cuh")
 _prelude_cache: Optional[str] = None
@@ -328,12 +328,18 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
 
     # ---------------- main kernel ----------------
     W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
-    W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s)"
-      % (kname, "".join(", const real* __restrict__ a%d" % k for k in range(nargs))))
+    W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s)"
+      % (kname, "".join(", const real* __restrict__ a%d_" % k for k in range(nargs)),
+         "".join(", const long long bs%d" % k for k in range(nargs))))
     W("{")
     W.indent()
     W("__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
     W("const int tid = threadIdx.x;")
+    W("// batch index = blockIdx.z; bs<k> is the element stride of argument k between batches (0 = shared)")
+    for k in range(nargs):
+        W("const real* __restrict__ a%d = a%d_ + (long long)blockIdx.z * bs%d;" % (k, k, k))
+    W("out += (long long)blockIdx.z * nrow * %d;" % red.dim)
+    W("partial += (long long)blockIdx.z * gridDim.y * nrow * %d;" % red_code.dimpart)
     W("const long long row0 = (long long)blockIdx.x * (KB_T * KB_R) + tid;")
     W("long long rowc[KB_R];")
     W("KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) { long long r_ = row0 + (long long)q * KB_T; rowc[q] = r_ < nrow ? r_ : nrow - 1; }")
@@ -687,6 +693,8 @@ class _ReductionCode:
         W.indent()
         W("const long long r_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
         W("if (r_ >= nrow) return;")
+        W("partial += (long long)blockIdx.z * nsplit * nrow * %d;" % dp)
+        W("out += (long long)blockIdx.z * nrow * %d;" % dim)
         W("const real* pp = partial + r_ * %d;" % dp)
         W("const long long sstride = nrow * %d;" % dp)
         W("real* po = out + r_ * %d;" % dim)

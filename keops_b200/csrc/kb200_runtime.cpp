@@ -381,10 +381,12 @@ int kb200_launch(kb200_function fn, void* stream, unsigned gx, unsigned gy, unsi
 
 int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, void* stream, int64_t nrow,
                         int64_t ncol, int rows_per_block, int block, int nsplit, int64_t col_chunk, void* out,
-                        void* workspace, int nargs, const void* const* args) {
+                        void* workspace, int nargs, const void* const* args, int nbatch,
+                        const int64_t* batch_strides) {
   int st = driver();
   if (st) return st;
-  if (!reduce_fn || !out || rows_per_block <= 0 || block <= 0 || nsplit <= 0 || nargs < 0 || nargs > 60)
+  if (!reduce_fn || !out || rows_per_block <= 0 || block <= 0 || nsplit <= 0 || nargs < 0 || nargs > 60 ||
+      nbatch < 1 || nbatch > 65535)
     return fail(KB200_EINVAL, "kb200_genred_launch: invalid argument");
   if (nsplit > 1 && (!workspace || !combine_fn))
     return fail(KB200_EINVAL, "kb200_genred_launch: split reduction needs a workspace and a combine kernel");
@@ -393,7 +395,8 @@ int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, voi
   void* out_ = out;
   void* ws_ = workspace;
   const void* argv[64];
-  void* params[5 + 64];
+  long long strides[64];
+  void* params[5 + 128];
   params[0] = &nrow_;
   params[1] = &ncol_;
   params[2] = &chunk_;
@@ -402,17 +405,19 @@ int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, voi
   for (int i = 0; i < nargs; ++i) {
     argv[i] = args[i];
     params[5 + i] = &argv[i];
+    strides[i] = batch_strides ? (long long)batch_strides[i] : 0LL;
+    params[5 + nargs + i] = &strides[i];
   }
   unsigned gx = (unsigned)((nrow + rows_per_block - 1) / rows_per_block);
-  CU_TRY(g_drv.LaunchKernel(reinterpret_cast<CUfunction>(reduce_fn), gx, (unsigned)nsplit, 1, (unsigned)block, 1, 1,
-                            0, reinterpret_cast<CUstream>(stream), params, nullptr),
+  CU_TRY(g_drv.LaunchKernel(reinterpret_cast<CUfunction>(reduce_fn), gx, (unsigned)nsplit, (unsigned)nbatch, (unsigned)block,
+                            1, 1, 0, reinterpret_cast<CUstream>(stream), params, nullptr),
          "cuLaunchKernel(kb200_reduce)");
   if (nsplit > 1) {
     int ns = nsplit;
     const void* ws_c = workspace;
     void* cparams[4] = {&nrow_, &ns, &ws_c, &out_};
     unsigned cg = (unsigned)((nrow + 255) / 256);
-    CU_TRY(g_drv.LaunchKernel(reinterpret_cast<CUfunction>(combine_fn), cg, 1, 1, 256, 1, 1, 0,
+    CU_TRY(g_drv.LaunchKernel(reinterpret_cast<CUfunction>(combine_fn), cg, 1, (unsigned)nbatch, 256, 1, 1, 0,
                               reinterpret_cast<CUstream>(stream), cparams, nullptr),
            "cuLaunchKernel(kb200_combine)");
   }

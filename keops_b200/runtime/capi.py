@@ -54,7 +54,7 @@ def _load() -> C.CDLL:
         "kb200_max_active_blocks": (i, [vp, i, sz, C.POINTER(i)]),
         "kb200_device_info": (i, [i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i64), C.POINTER(i64)]),
         "kb200_launch": (i, [vp, vp, u, u, u, u, u, u, u, C.POINTER(vp)]),
-        "kb200_genred_launch": (i, [vp, vp, vp, i64, i64, i, i, i, i64, vp, vp, i, C.POINTER(vp)]),
+        "kb200_genred_launch": (i, [vp, vp, vp, i64, i64, i, i, i, i64, vp, vp, i, C.POINTER(vp), i, C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -141,11 +141,13 @@ def device_info(device: int):
 
 def genred_launch(reduce_fn: int, combine_fn: Optional[int], stream: int, nrow: int, ncol: int,
                   rows_per_block: int, block: int, nsplit: int, col_chunk: int, out_ptr: int,
-                  workspace_ptr: int, arg_ptrs: Sequence[int]):
+                  workspace_ptr: int, arg_ptrs: Sequence[int], nbatch: int = 1,
+                  batch_strides: Optional[Sequence[int]] = None):
     n = len(arg_ptrs)
     arr = (C.c_void_p * max(n, 1))(*arg_ptrs)
+    bs = None if batch_strides is None else (C.c_int64 * max(n, 1))(*batch_strides)
     check(lib.kb200_genred_launch(reduce_fn, combine_fn or None, stream or None, nrow, ncol, rows_per_block,
-                                  block, nsplit, col_chunk, out_ptr, workspace_ptr or None, n, arr))
+                                  block, nsplit, col_chunk, out_ptr, workspace_ptr or None, n, arr, nbatch, bs))
 
 
 def launch(fn: int, stream: int, grid, block, smem: int, params: Sequence):

@@ -1,0 +1,227 @@
+"""GPU: the pykeops.torch-compatible front-end (Genred / LazyTensor / KernelSolve) on the sm_100a engine.
+
+Shapes, seeds and tolerances mirror the reference's own tests (all "KeOps vs dense torch"):
+pykeops/pykeops/torch/test_install.py:5-25, test/test_lazytensor_gaussian_cpu.py:5-57,
+test/test_torch.py:104-160,241-323,373-415,478-530,585-630, test/test_numpy.py:260-285."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(cuda_device):
+    import keops_b200.torch as kt
+    return kt
+
+
+def test_install_known_answer(api, cuda_device):
+    x = torch.arange(1, 10, dtype=torch.float32).view(-1, 3).to(cuda_device)
+    y = torch.arange(3, 9, dtype=torch.float32).view(-1, 3).to(cuda_device)
+    out = api.Genred("SqNorm2(x-y)", ["x=Vi(3)", "y=Vj(3)"], reduction_op="Sum", axis=0)(x, y)
+    assert out.view(-1).tolist() == [63.0, 90.0]
+
+
+def test_pykeops_shim_runs_reference_style_user_code(cuda_device):
+    import keops_b200
+    keops_b200.install_as_pykeops()
+    from pykeops.torch import LazyTensor  # noqa: the user's unchanged import line
+    torch.manual_seed(0)
+    x, y = torch.rand(50, 3, device=cuda_device), torch.rand(60, 3, device=cuda_device)
+    D = ((LazyTensor(x[:, None, :]) - LazyTensor(y[None, :, :])) ** 2).sum(-1)
+    idx = D.argKmin(3, dim=1)
+    ref = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1).argsort(dim=1)[:, :3]
+    assert torch.equal(idx, ref)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-5), (torch.float64, 1e-12)])
+def test_lazytensor_gaussian_conv_and_gradients(api, cuda_device, dtype, rtol):
+    # test_lazytensor_gaussian_cpu.py: M=N=1000, D=3, seed 0, scaled inputs, forward + 1st + 2nd order grads
+    torch.manual_seed(0)
+    M, N, D, DV = 1000, 1000, 3, 1
+    x = (torch.randn(M, D, dtype=dtype) / math.sqrt(D)).to(cuda_device)
+    y = (torch.randn(N, D, dtype=dtype) / math.sqrt(D)).to(cuda_device)
+    b = torch.randn(N, DV, dtype=dtype).to(cuda_device).requires_grad_(True)
+    x.requires_grad_(True)
+
+    def fun(x, y, b, lazy):
+        if lazy:
+            Dxy = ((api.LazyTensor(x[:, None, :]) - api.LazyTensor(y[None, :, :])) ** 2).sum(dim=2)
+            return (-Dxy).exp() @ b
+        Dxy = ((x[:, None, :] - y[None, :, :]) ** 2).sum(dim=2)
+        return (-Dxy).exp() @ b
+
+    outs = []
+    for lazy in (True, False):
+        out = fun(x, y, b, lazy)
+        g_b, g_x = torch.autograd.grad((out ** 2).sum(), [b, x], create_graph=True)
+        gg_b, = torch.autograd.grad((g_b ** 2).sum() + (g_x ** 2).sum(), [b], retain_graph=True)
+        outs.append((out, g_b, g_x, gg_b))
+    for got, ref in zip(*outs):
+        scale = ref.abs().max()
+        assert (got - ref).abs().max() <= 20 * rtol * scale, (got - ref).abs().max() / scale
+
+
+@pytest.mark.parametrize("backend", ["auto", "GPU", "GPU_1D", "GPU_2D"])
+def test_genred_sum_backends(api, cuda_device, backend):
+    torch.manual_seed(1)
+    M, N, D = 700, 1900, 3
+    x, y, b = torch.rand(M, D, device=cuda_device), torch.rand(N, D, device=cuda_device), torch.rand(N, 2, device=cuda_device)
+    p = torch.tensor([0.7], device=cuda_device)
+    conv = api.Genred("Exp(-p*SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(2)", "p=Pm(1)"], reduction_op="Sum", axis=1)
+    got = conv(x, y, b, p, backend=backend)
+    ref = torch.exp(-0.7 * ((x[:, None] - y[None]) ** 2).sum(-1)) @ b
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5 * ref.abs().max().item())
+    with pytest.raises(ValueError):
+        conv(x, y, b, p, backend="CPU")
+
+
+def test_heterogeneous_aliases_and_out_inplace(api, cuda_device):
+    torch.manual_seed(2)
+    M, N = 300, 500
+    x, y, b = torch.rand(M, 3, device=cuda_device), torch.rand(N, 3, device=cuda_device), torch.rand(N, 1, device=cuda_device)
+    conv = api.Genred("Exp(-SqDist(x,y))*b", ["x=Vi(0,3)", "b=Vj(2,1)", "y=Vj(1,3)"], reduction_op="Sum", axis=1)
+    out = torch.empty(M, 1, device=cuda_device)
+    ret = conv(x, y, b, out=out)
+    assert ret.data_ptr() == out.data_ptr()
+    ref = torch.exp(-((x[:, None] - y[None]) ** 2).sum(-1)) @ b
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float64, 1e-11)])
+def test_logsumexp_and_gradients(api, cuda_device, dtype, tol):
+    torch.manual_seed(3)
+    M, N = 400, 600
+    x = torch.rand(M, 3, dtype=dtype, device=cuda_device, requires_grad=True)
+    y = torch.rand(N, 3, dtype=dtype, device=cuda_device)
+    f = torch.rand(N, 1, dtype=dtype, device=cuda_device, requires_grad=True)
+    eps = 0.05
+
+    def softmin(lazy):
+        if lazy:
+            C = ((api.Vi(x) - api.Vj(y)) ** 2).sum(-1) / 2
+            return (api.Vj(f) - C / eps).logsumexp(dim=1)
+        C = ((x[:, None] - y[None]) ** 2).sum(-1) / 2
+        return (f.view(1, -1) - C / eps).logsumexp(dim=1, keepdim=True)
+
+    res = []
+    for lazy in (True, False):
+        s = softmin(lazy)
+        gx, gf = torch.autograd.grad((s ** 2).sum(), [x, f])
+        res.append((s, gx, gf))
+    for got, ref in zip(*res):
+        assert (got - ref).abs().max() <= tol * ref.abs().max(), (got - ref).abs().max() / ref.abs().max()
+
+
+def test_sumsoftmaxweight_and_weighted_lse(api, cuda_device):
+    torch.manual_seed(4)
+    M, N = 200, 350
+    x, y = torch.randn(M, 3, device=cuda_device), torch.randn(N, 3, device=cuda_device)
+    w = torch.rand(N, 2, device=cuda_device) + 0.5
+    S = (api.Vi(x) | api.Vj(y))
+    got = S.sumsoftmaxweight(api.Vj(w), dim=1)
+    ref = torch.softmax(x @ y.T, dim=1) @ w
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+    got2 = S.logsumexp(dim=1, weight=api.Vj(w))
+    ref2 = torch.log(torch.exp(x @ y.T) @ w)
+    assert torch.allclose(got2, ref2, rtol=1e-4, atol=1e-4)
+
+
+def test_argkmin_exact_indices(api, cuda_device):
+    # test_numpy.py:260-285 (ArgKMin K=3 vs argsort, exact)
+    torch.manual_seed(5)
+    M, N, D, K = 1500, 4000, 3, 10
+    x, y = torch.randn(M, D, device=cuda_device), torch.randn(N, D, device=cuda_device)
+    D_ij = ((api.Vi(x) - api.Vj(y)) ** 2).sum(-1)
+    idx = D_ij.argKmin(K, dim=1)
+    assert idx.dtype == torch.int64 and idx.shape == (M, K)
+    d = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+    ref = d.topk(K, dim=1, largest=False).indices
+    mism = idx != ref
+    if mism.any():  # only genuine near-ties may differ
+        dv = d.gather(1, idx)[mism] - d.gather(1, ref)[mism]
+        assert dv.abs().max() <= 1e-6 and mism.float().mean() < 1e-3
+    vals, idx2 = D_ij.Kmin_argKmin(K, dim=1)
+    assert torch.equal(idx2, idx)
+    assert torch.allclose(vals, d.gather(1, idx), rtol=1e-5, atol=1e-6)
+
+
+def test_min_argmin_high_dim(api, cuda_device):
+    # test_torch.py:585-630 uses D=990 to force the reference's chunked mode; here D=200 keeps the
+    # fully unrolled kernel small
+    torch.manual_seed(6)
+    M, N, D = 100, 250, 200
+    x, y = torch.rand(M, D, device=cuda_device), torch.rand(N, D, device=cuda_device)
+    Dij = ((api.Vi(x) - api.Vj(y)) ** 2).sum(-1)
+    vals, idx = Dij.min_argmin(dim=1)
+    d = torch.cdist(x.double(), y.double()) ** 2
+    rv, ri = d.min(dim=1)
+    assert torch.equal(idx.view(-1), ri)
+    assert torch.allclose(vals.view(-1).double(), rv, rtol=1e-5)
+    with pytest.raises(NotImplementedError):
+        xr = x.clone().requires_grad_(True)
+        v = ((api.Vi(xr) - api.Vj(y)) ** 2).sum(-1).min(dim=1)
+        v.sum().backward()
+
+
+def test_kernel_solve_matches_dense_solve_and_grad(api, cuda_device):
+    # test_torch.py:373-415
+    torch.manual_seed(7)
+    N, D, Dv = 300, 3, 2
+    x = torch.rand(N, D, device=cuda_device, requires_grad=True)
+    b = torch.rand(N, Dv, device=cuda_device)
+    sigma = torch.tensor([0.5], device=cuda_device)
+    alpha = 0.1
+    Kinv = api.KernelSolve("Exp(-oos2*SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(2)", "oos2=Pm(1)"], "b", axis=1)
+    oos2 = 1 / sigma ** 2
+    c = Kinv(x, x, b, oos2, alpha=alpha, eps=1e-7)
+    Kxx = torch.exp(-oos2 * ((x[:, None] - x[None]) ** 2).sum(-1)) + alpha * torch.eye(N, device=cuda_device)
+    cref = torch.linalg.solve(Kxx, b)
+    assert torch.allclose(c, cref, atol=1e-4)
+    u = torch.rand_like(c)
+    g, = torch.autograd.grad(c, x, u)
+    gref, = torch.autograd.grad(cref, x, u)
+    assert torch.allclose(g, gref, atol=1e-3, rtol=1e-3)
+    # LazyTensor.solve
+    K_xx = (-(api.Vi(x.detach()) - api.Vj(x.detach())).sqnorm2() * oos2.item()).exp()
+    c2 = K_xx.solve(api.Vi(b), alpha=alpha, eps=1e-7)
+    assert torch.allclose(c2, cref, atol=1e-4)
+
+
+def test_batch_dimensions_with_broadcast_and_grads(api, cuda_device):
+    # test_torch.py:478-530 / test_lazytensor_gaussian_batch.py
+    torch.manual_seed(8)
+    B1, B2, M, N, D = 3, 2, 40, 70, 3
+    x = torch.randn(B1, B2, M, 1, D, device=cuda_device, requires_grad=True)
+    y = torch.randn(B1, 1, 1, N, D, device=cuda_device)
+    b = torch.randn(1, B2, 1, N, 2, device=cuda_device, requires_grad=True)
+
+    def fun(lazy):
+        if lazy:
+            K = (-((api.LazyTensor(x) - api.LazyTensor(y)) ** 2).sum(-1)).exp()
+            return (K * api.LazyTensor(b)).sum(dim=3)
+        K = (-((x - y) ** 2).sum(-1)).exp()
+        return (K[..., None] * b).sum(dim=3)
+
+    res = []
+    for lazy in (True, False):
+        o = fun(lazy)
+        gx, gb = torch.autograd.grad((o ** 2).sum(), [x, b])
+        res.append((o, gx, gb))
+    for got, ref in zip(*res):
+        assert got.shape == ref.shape
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4 * ref.abs().max().item())
+
+
+def test_error_behaviour(api, cuda_device):
+    x = torch.rand(10, 3, device=cuda_device)
+    with pytest.raises(ValueError):
+        api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], axis=1)(x)            # wrong number of args
+    with pytest.raises(ValueError):
+        api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], axis=1)(x, x.cpu())   # mixed devices / no CPU path
+    with pytest.raises(ValueError):
+        api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(4)"], axis=1)(x, x)         # wrong vector size
+    with pytest.raises(ValueError):
+        api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], axis=1, sum_scheme="nope")
