@@ -238,33 +238,11 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
         return KernelSource(source="", kernel_name="", combine_name="", dimpart=0, stride=0, smem_bytes=0,
                             is_zero=True, **base)
 
-    g = Graph(fast=fast, tagI=tagI)
-    L = Lowerer(g)
-    F = L(red.formula)
-    G = L(red.weight) if red.weight is not None else []
-    if kind == "Sum" and all(sv.const() == 0.0 for sv in F):
+    low = lower_reduction(red, fast)
+    if low is None:
         return KernelSource(source="", kernel_name="", combine_name="", dimpart=0, stride=0, smem_bytes=0,
                             is_zero=True, **base)
-
-    rwt = _Rewriter(g)
-    # --- roots ------------------------------------------------------------------------------
-    # Sum / LSE weights accumulate |value| and apply the pulled-out sign at the very end.
-    acc_terms: List[Tuple[str, Tuple[SNode, ...], bool]] = []   # (mode, nodes, negative)
-    value_nodes: List[SNode] = []                               # materialised per-pair values
-    if kind == "Sum":
-        for sv in F:
-            acc_terms.append(_acc_term(rwt, sv))
-    elif kind == "LSE":
-        value_nodes = [rwt.signed(F[0])]
-        for sv in G:
-            acc_terms.append(_acc_term(rwt, sv))
-    else:
-        value_nodes = [rwt.signed(sv) for sv in F]
-
-    roots: List[SNode] = list(value_nodes)
-    for mode, nodes, _ in acc_terms:
-        roots.extend(nodes)
-    order = topo_order(roots)
+    g, acc_terms, value_nodes, order = low.graph, low.acc_terms, low.value_nodes, low.order
 
     pr = _Printer(f64)
     stride = sum(d for _, d in col_vars)
@@ -394,6 +372,45 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
     h = hashlib.sha256((GENERATOR_VERSION + src).encode()).hexdigest()[:16]
     return KernelSource(source=src, kernel_name=kname, combine_name=cname, dimpart=red_code.dimpart,
                         stride=stride, smem_bytes=2 * cfg.TJ * stride * (8 if f64 else 4), hash=h, **base)
+
+
+@dataclass
+class LoweredReduction:
+    """Scalar-level program of a reduction: what is evaluated per pair and how it is accumulated."""
+    graph: Graph
+    acc_terms: List[Tuple[str, Tuple[SNode, ...], bool]]   # Sum / LSE weights: (mode, nodes, negative)
+    value_nodes: List[SNode]                                # LSE exponent / Min / KMin values
+    order: List[SNode]                                      # topological order of everything needed
+
+
+def lower_reduction(red: Reduction, fast: bool) -> Optional[LoweredReduction]:
+    """Vector IR -> optimised scalar DAG.  Returns None when the reduction is structurally zero.
+
+    Sum terms and LSE weights accumulate the *unsigned* product / value and the pulled-out sign is
+    applied once at write-back (negation is free there, not in the packed FFMA2 loop)."""
+    g = Graph(fast=fast, tagI=red.tagI)
+    L = Lowerer(g)
+    F = L(red.formula)
+    G = L(red.weight) if red.weight is not None else []
+    kind = red.kind
+    if kind == "Sum" and all(sv.const() == 0.0 for sv in F):
+        return None
+    rwt = _Rewriter(g)
+    acc_terms: List[Tuple[str, Tuple[SNode, ...], bool]] = []
+    value_nodes: List[SNode] = []
+    if kind == "Sum":
+        for sv in F:
+            acc_terms.append(_acc_term(rwt, sv))
+    elif kind == "LSE":
+        value_nodes = [rwt.signed(F[0])]
+        for sv in G:
+            acc_terms.append(_acc_term(rwt, sv))
+    else:
+        value_nodes = [rwt.signed(sv) for sv in F]
+    roots: List[SNode] = list(value_nodes)
+    for mode, nodes, _ in acc_terms:
+        roots.extend(nodes)
+    return LoweredReduction(g, acc_terms, value_nodes, topo_order(roots))
 
 
 def _acc_term(rwt: _Rewriter, sv: SV):

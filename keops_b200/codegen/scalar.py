@@ -165,21 +165,35 @@ class Graph:
         return self._mul_regroup(a.n, b.n, sign)
 
     def _mul_regroup(self, x: SNode, y: SNode, sign: bool) -> SV:
-        """x*y, moving hoistable factors together: (p*q)*w -> (p*w)*q when that lowers the class
-        of the inner product (only with fast math, as it re-associates)."""
-        if self.fast or x.op == "const" or y.op == "const":
-            for u, w in ((x, y), (y, x)):
-                if u.op == "mul" and w.cls < u.cls:
-                    p, q = u.args
-                    if p.cls > q.cls:
-                        p, q = q, p
-                    # p is the more hoistable factor of u
-                    if max(p.cls, w.cls) < u.cls and (self.fast or (p.op == "const" and w.op == "const")):
-                        inner = self.mul(SV(p), SV(w))
-                        return self.mul(SV(inner.n, inner.neg != sign), SV(q))
+        """x*y, re-associated so that hoistable factors meet: ((p*q)*r)*w -> ((p*w)*q)*r whenever ``p*w``
+        has a lower dependency class than the product it came from (constants fold, parameter-only
+        and row-only factors leave the pair loop).  Re-association is a ``use_fast_math`` licence;
+        without it only constants are merged."""
+        for u, w in ((x, y), (y, x)):
+            if w.cls < u.cls and (self.fast or w.op == "const"):
+                r = self._absorb(u, w, 0)
+                if r is not None:
+                    return SV(r.n, r.neg != sign)
         if x.uid > y.uid:
             x, y = y, x
         return SV(self._mk("mul", (x, y)), sign)
+
+    def _absorb(self, n: SNode, w: SNode, depth: int) -> Optional[SV]:
+        """Product ``n*w`` with ``w`` pushed down onto a factor of ``n`` where the partial product has a
+        strictly lower class than the factor chain it leaves; None if there is no such place."""
+        if n.op != "mul" or depth > 6:
+            return None
+        p, q = n.args
+        for a, other in ((p, q), (q, p)):
+            if max(a.cls, w.cls) < n.cls and (self.fast or (a.op == "const" and w.op == "const")):
+                return self.mul(self.mul(SV(a), SV(w)), SV(other))
+        if not self.fast:
+            return None
+        for a, other in ((p, q), (q, p)):
+            r = self._absorb(a, w, depth + 1)
+            if r is not None:
+                return self.mul(r, SV(other))
+        return None
 
     def square(self, a: SV) -> SV:
         return self.mul(SV(a.n), SV(a.n))

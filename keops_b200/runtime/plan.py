@@ -109,7 +109,11 @@ def default_config(red: Reduction, dtype: str) -> KernelConfig:
         T = 128
         min_blocks = 1
     else:
-        if work <= 12:
+        kfam = red.kind in ("KMin", "ArgKMin", "KMin_ArgKMin")
+        if kfam and dimx <= 8 and red.K * red.dimF <= 16:
+            # measured on B200 (ArgKMin K=10, D=3, M=N=1e6): 253 ms vs 296 ms for (T=256, R=2)
+            R, T, min_blocks = 4, 128, 2
+        elif work <= 12:
             R, T, min_blocks = 4, 256, 4
         elif work <= 40:
             R, T, min_blocks = 2, 256, 2
@@ -122,6 +126,8 @@ def default_config(red: Reduction, dtype: str) -> KernelConfig:
     TJ = max(8, min(256, 1 << int(math.log2(max(TJ, 1)))))
     body = max(1, dimx + dimy) * (R // (1 if f64 else 2))
     unroll = 8 if body <= 16 else (4 if body <= 64 else (2 if body <= 160 else 1))
+    if red.kind in ("KMin", "ArgKMin", "KMin_ArgKMin"):
+        unroll = min(unroll, 4)
     cfg = KernelConfig(T=T, R=R, TJ=TJ, unroll=unroll, min_blocks=min_blocks)
     if env:
         kv = dict(item.split("=") for item in env.split(","))

@@ -130,15 +130,22 @@ class LazyTensor:
         return self._dtype
 
     @property
-    def shape(self):
+    def _shape(self):
         bd = () if self.batchdims is None else tuple(self.batchdims)
         ni = 1 if self.ni is None else self.ni
         nj = 1 if self.nj is None else self.nj
         nd = 1 if self.ndim is None else self.ndim
-        return bd + (ni, nj) if nd == 1 else bd + (ni, nj, nd)
+        return bd + (ni, nj, nd)
+
+    @property
+    def shape(self):
+        """(batch..., M, N, D), the trailing D being dropped when it is 1 (``lazy_tensor.py:1003-1009``)."""
+        s = self._shape
+        return s[:-1] if s[-1] == 1 else s
 
     def dim(self):
-        return len(self.shape)
+        """Number of dimensions *including* the trailing vector dimension (``lazy_tensor.py:1011-1015``)."""
+        return len(self._shape)
 
     def new_variable_index(self):
         sv = self.symbolic_variables
@@ -365,7 +372,7 @@ class LazyTensor:
     def norm2(self): return self.unary("Norm2", dimres=1)
 
     def norm(self, dim):
-        if dim not in (-1, len(self.shape) - 1):
+        if dim not in (-1, len(self._shape) - 1):
             raise ValueError("KeOps only supports norms over the last dimension.")
         return self.norm2()
 
@@ -394,7 +401,7 @@ class LazyTensor:
 
     def __getitem__(self, key):
         if isinstance(key, tuple):
-            if len(key) == len(self.shape) and all(k == slice(None) for k in key[:-1]):
+            if len(key) == len(self._shape) and all(k == slice(None) for k in key[:-1]):
                 key = key[-1]
             else:
                 raise ValueError("LazyTensors only support indexing with respect to their last dimension.")
@@ -635,6 +642,9 @@ class LazyTensor:
 
     def __matmul__(self, v, **kwargs):
         """``K @ v`` = ``(K * Vj(v)).sum(axis of j)`` (``lazy_tensor.py:2490-2527``)."""
+        if self._shape[-1] != 1:
+            raise ValueError("The 'K @ v' syntax is only supported for LazyTensors 'K' whose trailing dimension "
+                             "is equal to 1. Here, K.shape = {}.".format(self.shape))
         if _is_lt(v):
             Kv = self * v
         else:
@@ -645,7 +655,7 @@ class LazyTensor:
             Kv = self * LazyTensor(v.view(newdims))
         out = Kv.sum(Kv.dim() - 2, **kwargs)
         if not _is_lt(v) and v.dim() == 1:
-            out = out.squeeze(-1)
+            out = out.view(-1)
         return out
 
     @property

@@ -1,0 +1,93 @@
+"""CPU, world_size = 2, gloo: the output-index sharding and replication logic of
+keops_b200.distributed (the compute step is injected: the CPU oracle stands in for the CUDA Genred,
+which is exercised on GPUs by tests/test_distributed_gpu.py and bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from keops_b200.distributed import ShardedGenred, all_gather_rows, shard_bounds
+
+FORMULA, ALIASES = "Exp(-SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(2)"]
+RED = "Sum_Reduction(Exp(-SqDist(x,y))*b,0)"
+KNN_F, KNN_A = "SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"]
+
+
+def oracle_compute(red_string, aliases):
+    from oracle import keops_oracle as ko
+
+    def run(*args):
+        out = ko.genred(red_string, aliases, [a.numpy() for a in args], "float32")
+        return torch.from_numpy(out)
+    return run
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, M, N, mode, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    x, y, b = torch.rand(M, 3, generator=g), torch.rand(N, 3, generator=g), torch.rand(N, 2, generator=g)
+    i0, i1 = shard_bounds(M, world, rank)
+    j0, j1 = shard_bounds(N, world, rank)
+    sg = ShardedGenred(FORMULA, ALIASES, "Sum", axis=1, compute=oracle_compute(RED, ALIASES))
+    if mode == "all_gather":
+        out = sg(x[i0:i1], y[j0:j1], b[j0:j1], n_streamed=N, mode="all_gather")
+    elif mode == "broadcast":
+        yy, bb = (y, b) if rank == 0 else (None, None)
+        out = sg(x[i0:i1], yy, bb, n_streamed=N, mode="broadcast", src=0)
+    else:
+        out = sg(x[i0:i1], y, b, mode="replicated")
+    # arg-type reduction: indices must be global without any fix-up
+    sk = ShardedGenred(KNN_F, KNN_A, "ArgKMin", axis=1, opt_arg=3,
+                       compute=oracle_compute("ArgKMin_Reduction(SqDist(x,y),3,0)", KNN_A))
+    idx = sk(x[i0:i1], y[j0:j1], n_streamed=N, mode="all_gather")
+    gathered = all_gather_rows(out, M)
+    q.put((rank, i0, i1, out.numpy(), idx.numpy(), gathered.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["all_gather", "broadcast", "replicated"])
+@pytest.mark.parametrize("M,N", [(37, 53), (40, 64)])
+def test_sharded_reduction_matches_single_process(mode, M, N):
+    from oracle import keops_oracle as ko
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, M, N, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    x, y, b = torch.rand(M, 3, generator=g), torch.rand(N, 3, generator=g), torch.rand(N, 2, generator=g)
+    full = ko.genred(RED, ALIASES, [x.numpy(), y.numpy(), b.numpy()], "float32")
+    knn = ko.genred("ArgKMin_Reduction(SqDist(x,y),3,0)", KNN_A, [x.numpy(), y.numpy()], "float32")
+    for rank, i0, i1, out, idx, gathered in res:
+        assert np.array_equal(out, full[i0:i1])          # same oracle arithmetic on the same rows: bit-exact
+        assert np.array_equal(idx, knn[i0:i1])
+        assert np.array_equal(gathered, full)
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[r][1] == b[r + 1][0] for r in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1

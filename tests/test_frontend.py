@@ -1,0 +1,88 @@
+"""CPU: host-side logic of the engine -- parser, symbolic autodiff, lowering to the scalar DAG, sign /
+FMA rewriting -- evaluated with a numpy interpreter of the DAG (tests/dag_eval.py) against golden
+outputs of the real reference, plus metadata (dimout, tagIJ) checks and NVRTC cross-compilation of every
+generated kernel for sm_100a."""
+import numpy as np
+import pytest
+
+from tests import util, dag_eval
+
+
+@pytest.mark.parametrize("name", util.golden_names())
+def test_lowered_formula_matches_reference(name):
+    meta, args, ref = util.load_case(name)
+    got = dag_eval.evaluate(meta["formula"], meta["aliases"], args, "float64", fast=False)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    head = meta["formula"].split("(")[0]
+    if "Arg" in head or "KMin" in head:
+        # orderings are checked bit-exactly on the GPU and in the oracle; here values / indices in fp64
+        same = np.isclose(got, ref, rtol=1e-5, atol=1e-6)
+        assert same.mean() > 0.999
+    else:
+        rtol = 2e-5 if meta["dtype"] == "float32" else util.rtol_for(meta) * 50
+        util.assert_close(got, ref, "float64", name, rtol=rtol)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("name", ["gauss_grad_x_float32", "lse_grad_x_float32", "kernelsolve_matvec_float32",
+                                  "op_div_scalar_float32", "grad_inv_log_x_float64"])
+def test_fast_math_regrouping_preserves_values(name, fast):
+    meta, args, ref = util.load_case(name)
+    got = dag_eval.evaluate(meta["formula"], meta["aliases"], args, "float64", fast=fast)
+    util.assert_close(got, ref, "float64", name, rtol=2e-5)
+
+
+def test_metadata_matches_reference():
+    from keops_b200.formulas.parser import parse_reduction
+    for name in util.golden_names():
+        meta, _, _ = util.load_case(name)
+        red = parse_reduction(meta["formula"], meta["aliases"])
+        assert red.dim == meta["dimout"], name
+        assert red.tagI == meta["tagIJ"], name
+
+
+def test_second_order_gradient_strings():
+    """Backward of a backward: the reduction string nests two Grad_WithSavedForward calls
+    (pykeops/pykeops/torch/generic/generic_red.py:189); check it against dense numpy calculus."""
+    rng = np.random.default_rng(3)
+    M, N = 23, 31
+    x, y, b = rng.random((M, 3)), rng.random((N, 3)), rng.random((N, 1))
+    e1, e2 = rng.standard_normal((M, 1)), rng.standard_normal((N, 1))
+    G = "Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,1,1)),0)"
+    g1 = "Grad_WithSavedForward(%s,Var(2,1,1),Var(3,1,0),Var(4,1,0))" % G            # d/db -> indexed by j
+    g2 = "Grad_WithSavedForward(%s,Var(3,1,0),Var(5,1,1),Var(6,1,1))" % g1           # d/d(eta) of that -> indexed by i
+    K = np.exp(-((x[:, None] - y[None]) ** 2).sum(-1))
+    fwd = K @ b
+    gb = K.T @ e1                       # (N,1)
+    got1 = dag_eval.evaluate(g1, [], [x, y, b, e1, fwd])
+    np.testing.assert_allclose(got1, gb, rtol=1e-10)
+    got2 = dag_eval.evaluate(g2, [], [x, y, b, e1, fwd, e2, gb])
+    np.testing.assert_allclose(got2, K @ e2, rtol=1e-10)
+
+
+def test_every_golden_kernel_cross_compiles_for_sm100a():
+    from keops_b200.formulas.parser import parse_reduction
+    from keops_b200.codegen.emit import generate
+    from keops_b200.runtime import plan
+    seen = set()
+    for name in util.golden_names():
+        meta, _, _ = util.load_case(name)
+        key = (meta["formula"], meta["dtype"])
+        if key in seen or not name.startswith(("gauss", "argkmin_K10", "lse_softmin", "min_argmin", "kmin_argkmin_f", "kernelsolve")):
+            continue
+        seen.add(key)
+        red = parse_reduction(meta["formula"], meta["aliases"])
+        ks = generate(red, meta["dtype"], meta["nargs"], plan.default_config(red, meta["dtype"]))
+        if ks.is_zero:
+            continue
+        cubin = plan.get_cubin(ks, fast=(meta["dtype"] == "float32"))
+        assert cubin[:4] == b"\x7fELF", name
+
+
+def test_parser_errors():
+    from keops_b200.formulas.parser import parse_reduction
+    from keops_b200.formulas.ir import FormulaError
+    for bad in ("Sum_Reduction(Foo(Var(0,3,0)),0)", "Var(0,3,0)+Var(1,3,1)", "Sum_Reduction(Var(0,3,0)+Var(1,2,1),0)",
+                "Sum_Reduction(__import__('os').system('true'),0)", "Sum_Reduction(Var(0,3,0),2)"):
+        with pytest.raises((FormulaError, ValueError)):
+            parse_reduction(bad)
