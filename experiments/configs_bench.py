@@ -1,0 +1,93 @@
+"""Times every BASELINE.json config at full size on one B200 and prints one JSON line per kernel.
+
+  python experiments/configs_bench.py [--only NAME] [--once] [--size M]
+
+``--once`` launches each selected kernel exactly twice (warm-up + one) -- the form used under ncu.
+Rooflines are the FP32-pipe / MUFU issue bounds of SURVEY.md 8(d) at the max SM clock.
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from keops_b200.binder import get_binder
+
+G = "Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,1,1)),0)"
+GX = "Grad_WithSavedForward(%s,Var(0,3,0),Var(3,1,0),Var(4,1,0))" % G
+GY = "Grad_WithSavedForward(%s,Var(1,3,1),Var(3,1,0),Var(4,1,0))" % G
+GB = "Grad_WithSavedForward(%s,Var(2,1,1),Var(3,1,0),Var(4,1,0))" % G
+KNN3 = "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)"
+KNN64 = "ArgKMin_Reduction(Sum(Square((Var(0,64,0) - Var(1,64,1)))),10,0)"
+LSE = "Max_SumShiftExp_Reduction((Var(0,1,1) - ((Sum(Square((Var(1,3,0) - Var(2,3,1)))) / IntCst(2)) / Var(3,1,2))),0)"
+KS16 = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)"
+SM, HZ = 148, 1.965e9
+# pairs / clk / SM bounds
+BOUND = {"gauss_fwd": 16.0, "gauss_dx": 128 / 11.0, "gauss_dy": 128 / 11.0, "gauss_db": 16.0, "knn_d3": 128 / 7.0,
+         "knn_d64": 128 / 129.0, "lse_f32": 128 / 12.0, "lse_f64": 64 / 36.0, "ksolve_d16": 128 / 34.0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--once", action="store_true")
+    ap.add_argument("--size", type=int, default=1000000)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    M = N = args.size
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def gauss_inputs():
+        x, y, b = torch.randn(M, 3, device=dev), torch.randn(N, 3, device=dev), torch.randn(N, 1, device=dev)
+        eta = torch.randn(M, 1, device=dev)
+        fwd = get_binder(G, [], 3, "float32").genred_pytorch(dev, None, M, N, 0, None, x, y, b)
+        return x, y, b, eta, fwd
+
+    cases = {
+        "gauss_fwd": lambda: (G, 3, "float32", gauss_inputs()[:3]),
+        "gauss_dx": lambda: (GX, 5, "float32", gauss_inputs()),
+        "gauss_dy": lambda: (GY, 5, "float32", gauss_inputs()),
+        "gauss_db": lambda: (GB, 5, "float32", gauss_inputs()),
+        "knn_d3": lambda: (KNN3, 2, "float32", (torch.randn(M, 3, device=dev), torch.randn(N, 3, device=dev))),
+        "knn_d64": lambda: (KNN64, 2, "float32", (torch.randn(M, 64, device=dev), torch.randn(N, 64, device=dev))),
+        "lse_f32": lambda: (LSE, 4, "float32", (torch.rand(N, 1, device=dev), torch.rand(M, 3, device=dev),
+                                                torch.rand(N, 3, device=dev), torch.tensor([0.05], device=dev))),
+        "lse_f64": lambda: (LSE, 4, "float64", (torch.rand(N, 1, device=dev, dtype=torch.float64),
+                                                torch.rand(M, 3, device=dev, dtype=torch.float64),
+                                                torch.rand(N, 3, device=dev, dtype=torch.float64),
+                                                torch.tensor([0.05], device=dev, dtype=torch.float64))),
+        "ksolve_d16": lambda: (KS16, 4, "float32", (torch.rand(M, 16, device=dev), torch.rand(N, 16, device=dev),
+                                                    torch.randn(N, 1, device=dev), torch.tensor([2.0], device=dev))),
+    }
+    names = [args.only] if args.only else list(cases)
+    for name in names:
+        formula, nargs, dtype, targs = cases[name]()
+        bd = get_binder(formula, [], nargs, dtype)
+        out = bd.genred_pytorch(dev, None, M, N, 0, None, *targs)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(1 if args.once else args.reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            bd.genred_pytorch(dev, None, M, N, 0, out, *targs)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        rate = float(M) * N / (best * 1e-3)
+        peak = BOUND[name] * SM * HZ
+        print(json.dumps({"case": name, "M": M, "N": N, "dtype": dtype, "ms": best, "pair_evals_per_s": rate,
+                          "roofline_pairs_per_s": peak, "frac": rate / peak, "cfg": bd.ks.cfg.key(),
+                          "nsplit": bd.last_launch["nsplit"], "regs": bd.last_launch["regs"],
+                          "blocks_per_sm": bd.last_launch["blocks_per_sm"]}), flush=True)
+        del targs, out
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
