@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB200_ABI_VERSION 2
+#define KB200_ABI_VERSION 3
 
 #define KB200_OK 0
 #define KB200_ENOCUDA 20001  /* libcuda.so.1 could not be loaded / cuInit failed        */
@@ -115,6 +115,24 @@ int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, voi
                         int64_t nrow, int64_t ncol, int rows_per_block, int block, int nsplit,
                         int64_t col_chunk, void* out, void* workspace, int nargs,
                         const void* const* args, int nbatch, const int64_t* batch_strides);
+
+/* Block-sparse map-reduce launch: row-range k = rows [ranges_x[2k], ranges_x[2k+1]) is reduced over the
+ * union of the column ranges ranges_y[2l .. 2l+1], l in [slices_x[k-1], slices_x[k]) (slices_x[-1] = 0).
+ * replaces: the `ranges` branch of KeOps_module<TYPE>::launch_kernel
+ *           (keopscore/keopscore/binders/nvrtc/keops_nvrtc.cpp:571-595), its host-side lookup-table
+ *           construction range_preprocess_from_device (:152-237) and kernel GpuConv1DOnDevice_ranges
+ *           (keopscore/keopscore/mapreduce/gpu/GpuReduc1D_ranges.py:77-172).
+ * Differences: no host copy of the ranges and no per-block lookup table -- every CTA locates its
+ * (range, chunk) by bisection in `block_ends` (device, int64[nranges]: inclusive prefix sum of
+ * ceil(range length / rows_per_block)); `grid_x` >= block_ends[nranges-1] (surplus CTAs exit).
+ *
+ *   reduce_fn   the "kb200_reduce_ranges" kernel of a module generated in ranges mode
+ *   ranges_x, slices_x, ranges_y, block_ends   device pointers, int64, contiguous
+ * Rows covered by no range are not written (as in the reference).                                     */
+int kb200_genred_launch_ranges(kb200_function reduce_fn, void* stream, int64_t nrow, int64_t ncol,
+                               int block, int64_t grid_x, void* out, int nargs, const void* const* args,
+                               const int64_t* ranges_x, const int64_t* slices_x, const int64_t* ranges_y,
+                               const int64_t* block_ends, int nranges);
 
 #ifdef __cplusplus
 }

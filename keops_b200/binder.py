@@ -120,7 +120,9 @@ class LoadKeOpsB200:
         self.dimout = p.dim
         self.tagIJ = p.tagI
         self._vars = {v.params[0]: (v.params[1], v.params[2]) for v in vs}
-        self._loaded: Dict[int, plan.LoadedKernel] = {}
+        self._loaded: Dict[object, plan.LoadedKernel] = {}
+        self.ks_ranges: Optional[KernelSource] = None
+        self._range_tables: Dict[tuple, tuple] = {}
 
     # ---- reference-compatible surface ----------------------------------------------------------
     def import_module(self):
@@ -138,8 +140,12 @@ class LoadKeOpsB200:
 
     def genred(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
         p = self.params
-        if ranges:
-            raise NotImplementedError("[KeOps-B200] block-sparse `ranges` are not implemented yet.")
+        if ranges is not None and len(ranges) == 0:
+            ranges = None
+        if ranges is not None and int(nbatchdims or 0) > 0:
+            # reference: Ranges.h:88-96 ("not supported with batch processing")
+            raise ValueError("[KeOps] The 'ranges' argument (block-sparse mode) is not supported with batch processing, "
+                             "but we detected %d > 0 batch dimensions." % int(nbatchdims))
         if len(args) != p.nargs:
             raise ValueError("[KeOps-B200] expected %d arguments, got %d" % (p.nargs, len(args)))
         tdtype = torch.float32 if p.dtype == "float32" else torch.float64
@@ -206,7 +212,8 @@ class LoadKeOpsB200:
         nrow, ncol = (nx, ny) if p.tagI == 0 else (ny, nx)
         shapeout = batch_shape + (nrow, p.dim)
         if out is None:
-            out = torch.empty(shapeout, dtype=tdtype, device=dev)
+            # block-sparse mode: rows covered by no range are never written (garbage in the reference) -> zeros
+            out = (torch.zeros if ranges is not None else torch.empty)(shapeout, dtype=tdtype, device=dev)
         else:
             if tuple(out.shape) != shapeout or out.dtype != tdtype or out.device != dev or not out.is_contiguous():
                 raise ValueError("[KeOps-B200] `out` must be a contiguous %s tensor of shape %s on %s"
@@ -216,37 +223,107 @@ class LoadKeOpsB200:
             return out
         if nrow == 0 or nbatch == 0:
             return out
+        if ranges is not None:
+            return self._genred_ranges(dev, ranges, nrow, ncol, out, args, tdtype)
         lk = self._kernel(dev.index if dev.index is not None else torch.cuda.current_device())
         ks = self.ks
         rows_per_block = ks.cfg.T * ks.cfg.R
         esz = 4 if p.dtype == "float32" else 8
         slots = max(1, (lk.sm_count * lk.blocks_per_sm) // min(nbatch, lk.sm_count * lk.blocks_per_sm))
-        nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
-                                              ws_limit_bytes=max(1, (2 << 30) // nbatch))
-        if p.tag1D2D == 1 and nsplit == 1 and ncol > 4 * ks.cfg.TJ:
-            # backend="GPU_2D": the caller asked for the split-column scheme explicitly
-            ntiles = -(-ncol // ks.cfg.TJ)
-            nsplit = min(8, ntiles)
-            col_chunk = -(-ntiles // nsplit) * ks.cfg.TJ
-            nsplit = -(-ncol // col_chunk)
+        ws_limit = max(1, (2 << 30) // nbatch)
+        kfam = self.red.kind in ("KMin", "ArgKMin", "KMin_ArgKMin")
+        if nbatch == 1 and p.tag1D2D == 0:
+            # restart cost of a K-min list, in tile units: ~ K * log(N/K) insertions per row, each stalling its warp
+            penalty = (0.02 * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0
+            segments = plan.launch_segments(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
+                                            split_penalty_tiles=penalty, ws_limit_bytes=ws_limit)
+        else:
+            nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
+                                                  ws_limit_bytes=ws_limit,
+                                                  split_penalty_tiles=(0.02 * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0)
+            if p.tag1D2D == 1 and nsplit == 1 and ncol > 4 * ks.cfg.TJ:
+                # backend="GPU_2D": the caller asked for the split-column scheme explicitly
+                ntiles = -(-ncol // ks.cfg.TJ)
+                nsplit = min(8, ntiles)
+                col_chunk = -(-ntiles // nsplit) * ks.cfg.TJ
+                nsplit = -(-ncol // col_chunk)
+            segments = [(0, nrow, nsplit, col_chunk)]
+        row_dims = {ind: dim for ind, (dim, cat) in self._vars.items() if cat == p.tagI}
         BMAX = 65535
+        launches = 0
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             out_flat = out.view(nbatch, nrow * p.dim)
-            for b0 in range(0, nbatch, BMAX):
-                bn = min(BMAX, nbatch - b0)
-                ws = None
-                if nsplit > 1:
-                    ws = torch.empty(bn * nsplit * nrow * ks.dimpart, dtype=tdtype, device=dev)
-                ptrs = [a.data_ptr() + b0 * strides[k] * esz for k, a in enumerate(args)]
-                capi.genred_launch(lk.fn_reduce, lk.fn_combine, stream, nrow, ncol, rows_per_block, ks.cfg.T,
-                                   nsplit, max(col_chunk, 1), out_flat[b0].data_ptr(),
-                                   ws.data_ptr() if ws is not None else 0, ptrs, bn, strides)
-                if ws is not None:
-                    ws.record_stream(torch.cuda.current_stream(dev))
+            for (r0, r1, nsplit, col_chunk) in segments:
+                nseg = r1 - r0
+                for b0 in range(0, nbatch, BMAX):
+                    bn = min(BMAX, nbatch - b0)
+                    ws = None
+                    if nsplit > 1:
+                        ws = torch.empty(bn * nsplit * nseg * ks.dimpart, dtype=tdtype, device=dev)
+                    ptrs = [a.data_ptr() + (b0 * strides[k] + r0 * row_dims.get(k, 0)) * esz for k, a in enumerate(args)]
+                    capi.genred_launch(lk.fn_reduce, lk.fn_combine, stream, nseg, ncol, rows_per_block, ks.cfg.T,
+                                       nsplit, max(col_chunk, 1), out_flat[b0].data_ptr() + r0 * p.dim * esz,
+                                       ws.data_ptr() if ws is not None else 0, ptrs, bn, strides)
+                    launches += 2 if nsplit > 1 else 1
+                    if ws is not None:
+                        ws.record_stream(torch.cuda.current_stream(dev))
+        nsplit, col_chunk = segments[-1][2], segments[-1][3]
         self.last_launch = dict(nsplit=nsplit, col_chunk=col_chunk, grid_x=-(-nrow // rows_per_block),
-                                nbatch=nbatch, regs=lk.regs, blocks_per_sm=lk.blocks_per_sm,
-                                launches=(2 if nsplit > 1 else 1) * -(-nbatch // BMAX))
+                                nbatch=nbatch, regs=lk.regs, blocks_per_sm=lk.blocks_per_sm, launches=launches,
+                                segments=[(a, b, c) for a, b, c, _ in segments])
+        return out
+
+    # ---- block-sparse mode -----------------------------------------------------------------------
+    def _kernel_ranges(self, device: int) -> plan.LoadedKernel:
+        lk = self._loaded.get(("ranges", device))
+        if lk is None:
+            p = self.params
+            if self.ks_ranges is None:
+                self.ks_ranges = generate(self.red, p.dtype, p.nargs, self.ks.cfg, use_fast_math=p.use_fast_math,
+                                          sum_scheme=p.sum_scheme, dtype_acc=p.dtype_acc, ranges=True)
+            lk = plan.load_kernel(self.ks_ranges, p.use_fast_math and p.dtype == "float32", device)
+            self._loaded[("ranges", device)] = lk
+        return lk
+
+    def _genred_ranges(self, dev, ranges, nrow, ncol, out, args, tdtype):
+        """``ranges = (ranges_i, slices_i, redranges_j, ranges_j, slices_j, redranges_i)``: the first three
+        drive a reduction over j (tagI == 0), the last three a reduction over i
+        (``pykeops/pykeops/torch/generic/generic_red.py:581-639``, ``keops_nvrtc.cpp:166-170``)."""
+        p = self.params
+        if len(ranges) != 6:
+            raise ValueError("[KeOps] the 'ranges' argument should be a tuple of 6 integer arrays.")
+        rx, sx, ry = ranges[0:3] if p.tagI == 0 else ranges[3:6]
+        rx_user = rx
+        rx, sx, ry = (r.to(device=dev, dtype=torch.int64).contiguous() for r in (rx, sx, ry))
+        nranges = int(rx.shape[0])
+        if rx.dim() != 2 or rx.shape[1] != 2 or ry.dim() != 2 or ry.shape[1] != 2 or sx.numel() != nranges:
+            raise ValueError("[KeOps] wrong shapes for the 'ranges' arrays: expected (Nc,2), (Nc,), (Ncc,2).")
+        if nranges == 0:
+            return out
+        lk = self._kernel_ranges(dev.index if dev.index is not None else torch.cuda.current_device())
+        cfg = self.ks_ranges.cfg
+        rpb = cfg.T * cfg.R
+        key = (rx_user.data_ptr(), rx_user._version, nranges, rpb)
+        hit = self._range_tables.get(key)
+        if hit is None:
+            # chunks per row-range, prefix-summed on the device; the grid size is the one value the host needs
+            block_ends = torch.cumsum((rx[:, 1] - rx[:, 0] + (rpb - 1)).clamp_(min=0) // rpb, 0)
+            grid_x = int(block_ends[-1].item())
+            if len(self._range_tables) > 64:
+                self._range_tables.clear()
+            hit = (block_ends, grid_x, rx_user)     # keep the tensor alive so that its data_ptr stays unique
+            self._range_tables[key] = hit
+        block_ends, grid_x, _ = hit
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            capi.genred_launch_ranges(lk.fn_reduce, stream, nrow, ncol, cfg.T, grid_x, out.data_ptr(),
+                                      [a.data_ptr() for a in args], rx.data_ptr(), sx.data_ptr(), ry.data_ptr(),
+                                      block_ends.data_ptr(), nranges)
+            for t in (rx, sx, ry, block_ends):
+                t.record_stream(torch.cuda.current_stream(dev))
+        self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=grid_x, nbatch=1, regs=lk.regs,
+                                blocks_per_sm=lk.blocks_per_sm, launches=1, ranges=nranges)
         return out
 
     genred_pytorch = genred

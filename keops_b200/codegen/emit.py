@@ -24,7 +24,7 @@ from ..formulas.reductions import Reduction
 from .lower import Lowerer
 from .scalar import Graph, SNode, SV, C, P, I, J, IJ, topo_order
 
-GENERATOR_VERSION = "kb200-gen-2"
+GENERATOR_VERSION = "kb200-gen-3"
 
 _PRELUDE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "kb200_device.cuh")
 _prelude_cache: Optional[str] = None
@@ -45,9 +45,11 @@ class KernelConfig:
     TJ: int = 256       # streamed rows per shared-memory tile
     unroll: int = 8     # unroll factor of the pair loop
     min_blocks: int = 1  # __launch_bounds__ second argument
+    group: int = 1      # Min / KMin families: streamed rows evaluated branch-free before one threshold test
 
     def key(self) -> str:
-        return "T%d_R%d_TJ%d_U%d_B%d" % (self.T, self.R, self.TJ, self.unroll, self.min_blocks)
+        k = "T%d_R%d_TJ%d_U%d_B%d" % (self.T, self.R, self.TJ, self.unroll, self.min_blocks)
+        return k if self.group == 1 else k + "_G%d" % self.group
 
 
 @dataclass
@@ -213,7 +215,10 @@ def _collect_vars(red: Reduction):
 
 
 def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast_math: bool = True,
-             sum_scheme: str = "block_sum", dtype_acc: str = "auto") -> KernelSource:
+             sum_scheme: str = "block_sum", dtype_acc: str = "auto", ranges: bool = False) -> KernelSource:
+    """``ranges=True`` emits the block-sparse variant ``kb200_reduce_ranges`` (reference:
+    ``keopscore/keopscore/mapreduce/gpu/GpuReduc1D_ranges.py:77-172``) instead of the dense pair
+    ``kb200_reduce`` / ``kb200_combine``."""
     if dtype not in ("float32", "float64"):
         raise ValueError("dtype %s is not implemented (float32 / float64 only)" % dtype)
     f64 = dtype == "float64"
@@ -293,10 +298,14 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
     vty = "double2" if f64 else "float4"
     comp_names = ["x", "y", "z", "w"]
     need_chunks = sorted({(col_off[ind] + comp) // vec for (ind, comp) in used_col})
-    row_loads = ["const %s q%d = yrow[%d];" % (vty, c, c) for c in need_chunks]
-    for (ind, comp), nm in sorted(used_col.items()):
-        pos = col_off[ind] + comp
-        row_loads.append("const real %s = q%d.%s;" % (nm, pos // vec, comp_names[pos % vec]))
+    def row_loads_from(ptr: str) -> List[str]:
+        out = ["const %s q%d = %s[%d];" % (vty, c, ptr, c) for c in need_chunks]
+        for (ind, comp), nm in sorted(used_col.items()):
+            pos = col_off[ind] + comp
+            out.append("const real %s = q%d.%s;" % (nm, pos // vec, comp_names[pos % vec]))
+        return out
+
+    row_loads = row_loads_from("yrow")
 
     W = _Writer()
     hdr = _kernel_header(W, red, cfg, f64, fast, stride, nargs, varinfo)
@@ -304,69 +313,143 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
 
     red_code = _ReductionCode(red, pr, acc_terms, value_nodes, sum_scheme, dtype_acc, f64, fast)
 
-    # ---------------- main kernel ----------------
-    W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
-    W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s)"
-      % (kname, "".join(", const real* __restrict__ a%d_" % k for k in range(nargs)),
-         "".join(", const long long bs%d" % k for k in range(nargs))))
-    W("{")
-    W.indent()
-    W("__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
-    W("const int tid = threadIdx.x;")
-    W("// batch index = blockIdx.z; bs<k> is the element stride of argument k between batches (0 = shared)")
-    for k in range(nargs):
-        W("const real* __restrict__ a%d = a%d_ + (long long)blockIdx.z * bs%d;" % (k, k, k))
-    W("out += (long long)blockIdx.z * nrow * %d;" % red.dim)
-    W("partial += (long long)blockIdx.z * gridDim.y * nrow * %d;" % red_code.dimpart)
-    W("const long long row0 = (long long)blockIdx.x * (KB_T * KB_R) + tid;")
-    W("long long rowc[KB_R];")
-    W("KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) { long long r_ = row0 + (long long)q * KB_T; rowc[q] = r_ < nrow ? r_ : nrow - 1; }")
-    W("const long long jbeg = (long long)blockIdx.y * col_chunk;")
-    W("const long long jend = (jbeg + col_chunk < ncol) ? (jbeg + col_chunk) : ncol;")
-    W("// ---- hoisted: parameters and output-side (row) values")
-    for s in pre:
-        W(s)
-    W("// ---- accumulators")
-    red_code.declare(W)
-    W("// ---- stage the first tile")
-    _stage(W, col_vars, col_off, "jbeg", "0")
-    W("kb_cp_commit(); kb_cp_wait_all(); __syncthreads();")
-    W("int buf = 0;")
-    W("for (long long jt = jbeg; jt < jend; jt += KB_TJ) {")
-    W.indent()
-    W("if (jt + KB_TJ < jend) {")
-    W.indent()
-    _stage(W, col_vars, col_off, "jt + KB_TJ", "buf ^ 1")
-    W.dedent()
-    W("}")
-    W("kb_cp_commit();")
-    W("const int jn = (int)((jend - jt < KB_TJ) ? (jend - jt) : KB_TJ);")
-    red_code.tile_begin(W)
-    W("const %s* yrow = reinterpret_cast<const %s*>(&sm[buf][0]);" % (vty, vty))
-    W("#pragma unroll %d" % cfg.unroll)
-    W("for (int jr = 0; jr < jn; jr++, yrow += KB_STRIDE / %d) {" % vec)
-    W.indent()
-    for s in row_loads:
-        W(s)
-    for s in body_j:
-        W(s)
-    for s in body_ij:
-        W(s)
-    red_code.update(W)
-    W.dedent()
-    W("}")
-    red_code.tile_end(W)
-    W("kb_cp_wait_all(); __syncthreads();")
-    W("buf ^= 1;")
-    W.dedent()
-    W("}")
-    W("// ---- write back")
-    red_code.finalize(W)
-    W.dedent()
-    W("}")
-    W("")
-    # ---------------- combine kernel (merges split-j partials) ----------------
-    red_code.combine_kernel(W, cname)
+    def tile_loop():
+        """Stage + stream the column range [jbeg, jend) through the double-buffered tile."""
+        W("// ---- stage the first tile")
+        _stage(W, col_vars, col_off, "jbeg", "0")
+        W("kb_cp_commit(); kb_cp_wait_all(); __syncthreads();")
+        W("int buf = 0;")
+        W("for (long long jt = jbeg; jt < jend; jt += KB_TJ) {")
+        W.indent()
+        W("if (jt + KB_TJ < jend) {")
+        W.indent()
+        _stage(W, col_vars, col_off, "jt + KB_TJ", "buf ^ 1")
+        W.dedent()
+        W("}")
+        W("kb_cp_commit();")
+        W("const int jn = (int)((jend - jt < KB_TJ) ? (jend - jt) : KB_TJ);")
+        red_code.tile_begin(W)
+        W("const %s* yrow = reinterpret_cast<const %s*>(&sm[buf][0]);" % (vty, vty))
+        G = cfg.group if red_code.supports_groups() else 1
+        W("int jr = 0;")
+        if G > 1:
+            # branch-free evaluation of G streamed rows, then ONE combined threshold test; the rare
+            # path replays the group in column order so that ties still go to the smallest index
+            W("#pragma unroll 1")
+            W("for (; jr + %d <= jn; jr += %d, yrow += %d * (KB_STRIDE / %d)) {" % (G, G, G, vec))
+            W.indent()
+            W("V fg_[%d][%d];" % (G, len(value_nodes)))
+            W("KB_UNROLL_ALL for (int g_ = 0; g_ < %d; g_++) {" % G)
+            W.indent()
+            W("const %s* yr_ = yrow + g_ * (KB_STRIDE / %d);" % (vty, vec))
+            for s_ in row_loads_from("yr_"):
+                W(s_)
+            for s_ in body_j:
+                W(s_)
+            for s_ in body_ij:
+                W(s_)
+            red_code.group_store(W)
+            W.dedent()
+            W("}")
+            red_code.group_update(W, G)
+            W.dedent()
+            W("}")
+        W("#pragma unroll %d" % (cfg.unroll if G == 1 else 1))
+        W("for (; jr < jn; jr++, yrow += KB_STRIDE / %d) {" % vec)
+        W.indent()
+        for s_ in row_loads:
+            W(s_)
+        for s_ in body_j:
+            W(s_)
+        for s_ in body_ij:
+            W(s_)
+        red_code.update(W)
+        W.dedent()
+        W("}")
+        red_code.tile_end(W)
+        W("kb_cp_wait_all(); __syncthreads();")
+        W("buf ^= 1;")
+        W.dedent()
+        W("}")
+
+    arg_decl = "".join(", const real* __restrict__ a%d_" % k for k in range(nargs))
+    if not ranges:
+        # ---------------- dense kernel ----------------
+        W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
+        W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s)"
+          % (kname, arg_decl, "".join(", const long long bs%d" % k for k in range(nargs))))
+        W("{")
+        W.indent()
+        W("__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
+        W("const int tid = threadIdx.x;")
+        W("// batch index = blockIdx.z; bs<k> is the element stride of argument k between batches (0 = shared)")
+        for k in range(nargs):
+            W("const real* __restrict__ a%d = a%d_ + (long long)blockIdx.z * bs%d;" % (k, k, k))
+        W("out += (long long)blockIdx.z * nrow * %d;" % red.dim)
+        W("partial += (long long)blockIdx.z * gridDim.y * nrow * %d;" % red_code.dimpart)
+        W("const long long row0 = (long long)blockIdx.x * (KB_T * KB_R) + tid;")
+        W("long long rowc[KB_R];")
+        W("KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) { long long r_ = row0 + (long long)q * KB_T; rowc[q] = r_ < nrow ? r_ : nrow - 1; }")
+        W("const long long jbeg = (long long)blockIdx.y * col_chunk;")
+        W("const long long jend = (jbeg + col_chunk < ncol) ? (jbeg + col_chunk) : ncol;")
+        W("// ---- hoisted: parameters and output-side (row) values")
+        for s_ in pre:
+            W(s_)
+        W("// ---- accumulators")
+        red_code.declare(W)
+        tile_loop()
+        W("// ---- write back")
+        red_code.finalize(W)
+        W.dedent()
+        W("}")
+        W("")
+        # ---------------- combine kernel (merges split-j partials) ----------------
+        red_code.combine_kernel(W, cname)
+    else:
+        # ---------------- block-sparse kernel ----------------
+        kname, cname = "kb200_reduce_ranges", ""
+        W("// One CTA = one chunk of KB_T*KB_R rows of one row-range; blk_end[k] is the inclusive prefix sum of")
+        W("// the number of chunks of ranges 0..k (the reference builds a (range, start, end) lookup table per")
+        W("// block on the host, keops_nvrtc.cpp:210-237; here each CTA finds its range by bisection).")
+        W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
+        W("%s(const long long nrow, const long long ncol, real* __restrict__ out%s, const long long* __restrict__ rng_x, const long long* __restrict__ slc_x, const long long* __restrict__ rng_y, const long long* __restrict__ blk_end, const int nranges)"
+          % (kname, arg_decl))
+        W("{")
+        W.indent()
+        W("__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
+        W("const int tid = threadIdx.x;")
+        for k in range(nargs):
+            W("const real* __restrict__ a%d = a%d_;" % (k, k))
+        W("int lo_ = 0, hi_ = nranges;")
+        W("while (lo_ < hi_) { const int mid_ = (lo_ + hi_) >> 1; if (blk_end[mid_] > (long long)blockIdx.x) hi_ = mid_; else lo_ = mid_ + 1; }")
+        W("if (lo_ >= nranges) return;")
+        W("const long long first_ = lo_ ? blk_end[lo_ - 1] : 0;")
+        W("const long long start_x = rng_x[2 * lo_] + ((long long)blockIdx.x - first_) * (KB_T * KB_R);")
+        W("const long long end_x = (start_x + KB_T * KB_R < rng_x[2 * lo_ + 1]) ? (start_x + KB_T * KB_R) : rng_x[2 * lo_ + 1];")
+        W("const long long row0 = start_x + tid;")
+        W("long long rowc[KB_R];")
+        W("KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) { long long r_ = row0 + (long long)q * KB_T; rowc[q] = r_ < end_x ? r_ : end_x - 1; }")
+        W("// ---- hoisted: parameters and output-side (row) values")
+        for s_ in pre:
+            W(s_)
+        W("// ---- accumulators")
+        red_code.declare(W)
+        W("// ---- the column ranges of this row-range; contiguous ones are merged (GpuReduc1D_ranges.py:129-131)")
+        W("long long sl_ = lo_ ? slc_x[lo_ - 1] : 0;")
+        W("const long long sl_end_ = slc_x[lo_];")
+        W("while (sl_ < sl_end_) {")
+        W.indent()
+        W("const long long jbeg = rng_y[2 * sl_];")
+        W("long long jend = rng_y[2 * sl_ + 1];")
+        W("sl_++;")
+        W("while (sl_ < sl_end_ && rng_y[2 * sl_] == jend) { jend = rng_y[2 * sl_ + 1]; sl_++; }")
+        tile_loop()
+        W.dedent()
+        W("}")
+        W("// ---- write back")
+        red_code.finalize(W, row_limit="end_x", allow_partial=False)
+        W.dedent()
+        W("}")
 
     src = hdr + W.text()
     h = hashlib.sha256((GENERATOR_VERSION + src).encode()).hexdigest()[:16]
@@ -627,6 +710,43 @@ class _ReductionCode:
                 W("      kb_kmin_insert<%d, int>(kval[%d][q], kidx[%d][q], f_.l[q], (int)(jt + jr)); thr[%d].l[q] = kval[%d][q][%d]; } } }"
                   % (K, i, i, i, i, K - 1))
 
+    # ---- grouped evaluation (Min / KMin families) ----------------------------------------------
+    def supports_groups(self) -> bool:
+        return self.kind not in ("Sum", "LSE")
+
+    def _value_v(self, nd) -> str:
+        f = self.pr.ref(nd)
+        return f if nd.cls in (I, IJ) else "kb_bcast_v(%s)" % f
+
+    def group_store(self, W):
+        for i, nd in enumerate(self.values):
+            W("fg_[g_][%d] = %s;" % (i, self._value_v(nd)))
+
+    def group_update(self, W, G: int):
+        k = self.kind
+        nv = len(self.values)
+        minlike = k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax")
+        cmp = ">" if self.is_max else "<"
+        ref = "best" if minlike else "thr"
+        W("bool any_ = false;")
+        W("KB_UNROLL_ALL for (int g_ = 0; g_ < %d; g_++) KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (fg_[g_][k_].l[q] %s %s[k_].l[q]);"
+          % (G, nv, cmp, ref))
+        W("if (any_) {")
+        W.indent()
+        W("KB_UNROLL_ALL for (int g_ = 0; g_ < %d; g_++) KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) {" % (G, nv))
+        W.indent()
+        W("const real f1_ = fg_[g_][k_].l[q];")
+        if minlike:
+            W("if (f1_ %s best[k_].l[q]) { best[k_].l[q] = f1_; bidx[k_][q] = (int)(jt + jr + g_); }" % cmp)
+        else:
+            K = self.red.K
+            W("if (f1_ < thr[k_].l[q]) { kb_kmin_insert<%d, int>(kval[k_][q], kidx[k_][q], f1_, (int)(jt + jr + g_)); thr[k_].l[q] = kval[k_][q][%d]; }"
+              % (K, K - 1))
+        W.dedent()
+        W("}")
+        W.dedent()
+        W("}")
+
     def tile_end(self, W):
         if self.kind in ("Sum", "LSE") and self.scheme == "block_sum":
             n = len(self.acc_terms)
@@ -639,15 +759,18 @@ class _ReductionCode:
     def _signs(self):
         return ["-" if t[2] else "" for t in self.acc_terms]
 
-    def finalize(self, W):
+    def finalize(self, W, row_limit: str = "nrow", allow_partial: bool = True):
         """Write either the final output (gridDim.y == 1) or this split's partial accumulator."""
         k, d = self.kind, self.dimF
         W("KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) {")
         W.indent()
         W("const long long r_ = row0 + (long long)q * KB_T;")
-        W("if (r_ < nrow) {")
+        W("if (r_ < %s) {" % row_limit)
         W.indent()
-        W("real* po = (gridDim.y == 1) ? (out + r_ * %d) : (partial + ((long long)blockIdx.y * nrow + r_) * %d);" % (self.red.dim, self.dimpart))
+        if allow_partial:
+            W("real* po = (gridDim.y == 1) ? (out + r_ * %d) : (partial + ((long long)blockIdx.y * nrow + r_) * %d);" % (self.red.dim, self.dimpart))
+        else:
+            W("real* po = out + r_ * %d;" % self.red.dim)
         if k == "Sum":
             for i, s in enumerate(self._signs()):
                 src = "(real)accd[%d][q]" % i if self.acc64 else "acc[%d].l[q]" % i

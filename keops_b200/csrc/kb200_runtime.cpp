@@ -424,4 +424,38 @@ int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, voi
   return 0;
 }
 
+int kb200_genred_launch_ranges(kb200_function reduce_fn, void* stream, int64_t nrow, int64_t ncol, int block,
+                               int64_t grid_x, void* out, int nargs, const void* const* args,
+                               const int64_t* ranges_x, const int64_t* slices_x, const int64_t* ranges_y,
+                               const int64_t* block_ends, int nranges) {
+  int st = driver();
+  if (st) return st;
+  if (!reduce_fn || !out || block <= 0 || nargs < 0 || nargs > 60 || nranges < 0 || grid_x < 0 ||
+      grid_x > 2147483647LL || (nranges > 0 && (!ranges_x || !slices_x || !ranges_y || !block_ends)))
+    return fail(KB200_EINVAL, "kb200_genred_launch_ranges: invalid argument");
+  if (nrow <= 0 || nranges == 0 || grid_x == 0) return 0;
+  long long nrow_ = nrow, ncol_ = ncol;
+  void* out_ = out;
+  const void* argv[64];
+  const void *rx = ranges_x, *sx = slices_x, *ry = ranges_y, *be = block_ends;
+  int nr = nranges;
+  void* params[3 + 64 + 5];
+  params[0] = &nrow_;
+  params[1] = &ncol_;
+  params[2] = &out_;
+  for (int i = 0; i < nargs; ++i) {
+    argv[i] = args[i];
+    params[3 + i] = &argv[i];
+  }
+  params[3 + nargs] = &rx;
+  params[4 + nargs] = &sx;
+  params[5 + nargs] = &ry;
+  params[6 + nargs] = &be;
+  params[7 + nargs] = &nr;
+  CU_TRY(g_drv.LaunchKernel(reinterpret_cast<CUfunction>(reduce_fn), (unsigned)grid_x, 1, 1, (unsigned)block, 1, 1, 0,
+                            reinterpret_cast<CUstream>(stream), params, nullptr),
+         "cuLaunchKernel(kb200_reduce_ranges)");
+  return 0;
+}
+
 }  // extern "C"

@@ -55,6 +55,7 @@ def _load() -> C.CDLL:
         "kb200_device_info": (i, [i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i64), C.POINTER(i64)]),
         "kb200_launch": (i, [vp, vp, u, u, u, u, u, u, u, C.POINTER(vp)]),
         "kb200_genred_launch": (i, [vp, vp, vp, i64, i64, i, i, i, i64, vp, vp, i, C.POINTER(vp), i, C.POINTER(i64)]),
+        "kb200_genred_launch_ranges": (i, [vp, vp, i64, i64, i, i64, vp, i, C.POINTER(vp), vp, vp, vp, vp, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -68,7 +69,7 @@ EXPORTED_SYMBOLS = (
     "kb200_abi_version", "kb200_last_error", "kb200_compile", "kb200_compile_to_memory", "kb200_free",
     "kb200_module_load", "kb200_module_load_file", "kb200_module_unload", "kb200_module_get_function",
     "kb200_function_info", "kb200_max_active_blocks", "kb200_device_info", "kb200_launch",
-    "kb200_genred_launch",
+    "kb200_genred_launch", "kb200_genred_launch_ranges",
 )
 
 
@@ -148,6 +149,15 @@ def genred_launch(reduce_fn: int, combine_fn: Optional[int], stream: int, nrow: 
     bs = None if batch_strides is None else (C.c_int64 * max(n, 1))(*batch_strides)
     check(lib.kb200_genred_launch(reduce_fn, combine_fn or None, stream or None, nrow, ncol, rows_per_block,
                                   block, nsplit, col_chunk, out_ptr, workspace_ptr or None, n, arr, nbatch, bs))
+
+
+def genred_launch_ranges(reduce_fn: int, stream: int, nrow: int, ncol: int, block: int, grid_x: int, out_ptr: int,
+                         arg_ptrs: Sequence[int], ranges_x_ptr: int, slices_x_ptr: int, ranges_y_ptr: int,
+                         block_ends_ptr: int, nranges: int):
+    n = len(arg_ptrs)
+    arr = (C.c_void_p * max(n, 1))(*arg_ptrs)
+    check(lib.kb200_genred_launch_ranges(reduce_fn, stream or None, nrow, ncol, block, grid_x, out_ptr, n, arr,
+                                         ranges_x_ptr, slices_x_ptr, ranges_y_ptr, block_ends_ptr, nranges))
 
 
 def launch(fn: int, stream: int, grid, block, smem: int, params: Sequence):

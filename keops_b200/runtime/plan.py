@@ -128,11 +128,18 @@ def default_config(red: Reduction, dtype: str) -> KernelConfig:
     unroll = 8 if body <= 16 else (4 if body <= 64 else (2 if body <= 160 else 1))
     if red.kind in ("KMin", "ArgKMin", "KMin_ArgKMin"):
         unroll = min(unroll, 4)
-    cfg = KernelConfig(T=T, R=R, TJ=TJ, unroll=unroll, min_blocks=min_blocks)
+    group = 1
+    if red.kind not in ("Sum", "LSE") and not f64:
+        # values held per group: group * dimF * R registers; keep the branch-free window small
+        nval = max(1, red.dimF) * R
+        if dimx + dimy <= 16:
+            group = max(1, min(4, 16 // nval))
+    cfg = KernelConfig(T=T, R=R, TJ=TJ, unroll=unroll, min_blocks=min_blocks, group=group)
     if env:
         kv = dict(item.split("=") for item in env.split(","))
         cfg = KernelConfig(T=int(kv.get("T", cfg.T)), R=int(kv.get("R", cfg.R)), TJ=int(kv.get("TJ", cfg.TJ)),
-                           unroll=int(kv.get("U", cfg.unroll)), min_blocks=int(kv.get("B", cfg.min_blocks)))
+                           unroll=int(kv.get("U", cfg.unroll)), min_blocks=int(kv.get("B", cfg.min_blocks)),
+                           group=int(kv.get("G", cfg.group)))
     return cfg
 
 
@@ -161,7 +168,7 @@ def load_kernel(ks: KernelSource, fast: bool, device: int) -> LoadedKernel:
             cubin = get_cubin(ks, fast)
             mod = capi.Module(cubin, device)
             fr = mod.function(ks.kernel_name)
-            fc = mod.function(ks.combine_name)
+            fc = mod.function(ks.combine_name) if ks.combine_name else 0
             regs, _, _ = capi.function_info(fr)
             bps = max(1, capi.max_active_blocks(fr, ks.cfg.T, 0))
             sm = capi.device_info(device)["sm_count"]
@@ -171,7 +178,7 @@ def load_kernel(ks: KernelSource, fast: bool, device: int) -> LoadedKernel:
 
 
 def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int, dimpart: int, esz: int,
-                 max_split: int = 64, ws_limit_bytes: int = 2 << 30) -> Tuple[int, int]:
+                 max_split: int = 64, ws_limit_bytes: int = 2 << 30, split_penalty_tiles: float = 0.0) -> Tuple[int, int]:
     """Choose the number of column splits so that the grid fills an integer number of waves.
 
     All CTAs do the same amount of work, so wall time ~ waves * work-per-CTA.  Without splitting,
@@ -193,7 +200,38 @@ def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int,
             break
         waves = -(-(gx * ns) // slots)
         # cost in tile units: per-CTA prologue/epilogue overhead ~ 2 tiles, combine ~ ns/8 tiles
-        cost = waves * (tiles_per + 2.0) + (0.25 * ns if ns > 1 else 0.0)
+        cost = waves * (tiles_per + 2.0 + (split_penalty_tiles if ns > 1 else 0.0)) + (0.25 * ns if ns > 1 else 0.0)
         if best is None or cost < best[0] * 0.98:
             best = (cost, ns, tiles_per * TJ)
     return best[1], best[2]
+
+
+def launch_segments(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int, dimpart: int, esz: int,
+                    split_penalty_tiles: float = 0.0, ws_limit_bytes: int = 2 << 30):
+    """Row segments ``[(row_begin, row_end, nsplit, col_chunk), ...]`` covering ``[0, nrow)``.
+
+    Splitting the column range of *every* CTA fixes wave quantisation but makes each split restart its
+    accumulator (for K-min lists every restart replays the ~K log(N/K) insertions of the transient).
+    When the grid holds at least one full wave it is cheaper to launch the whole waves unsplit and to
+    split only the rows of the last, partial wave so that they also fill the machine:
+    time ~ full_waves * T + (T / ns) instead of (full_waves + 1) * T or full-split with restart costs.
+    ``split_penalty_tiles``: extra cost of one restart, in tile units (0 for sums)."""
+    gx = -(-nrow // rows_per_block)
+    ntiles = max(1, -(-ncol // TJ))
+    ns_all, chunk_all = launch_shape(nrow, ncol, rows_per_block, TJ, slots, dimpart, esz, ws_limit_bytes=ws_limit_bytes,
+                                     split_penalty_tiles=split_penalty_tiles)
+    tiles_all = -(-ntiles // ns_all)
+    cost_all = -(-(gx * ns_all) // slots) * (tiles_all + 2.0 + (split_penalty_tiles if ns_all > 1 else 0.0)) + (0.25 * ns_all if ns_all > 1 else 0.0)
+    full_waves, rem = divmod(gx, slots)
+    if full_waves == 0 or rem == 0:
+        return [(0, nrow, ns_all, chunk_all)]
+    rows_a = full_waves * slots * rows_per_block
+    nrow_b = nrow - rows_a
+    ns_b, chunk_b = launch_shape(nrow_b, ncol, rows_per_block, TJ, slots, dimpart, esz, ws_limit_bytes=ws_limit_bytes,
+                                 split_penalty_tiles=split_penalty_tiles)
+    tiles_b = -(-ntiles // ns_b)
+    cost_tail = full_waves * (ntiles + 2.0) + -(-(rem * ns_b) // slots) * (tiles_b + 2.0 + (split_penalty_tiles if ns_b > 1 else 0.0)) \
+        + (0.25 * ns_b if ns_b > 1 else 0.0) + 1.0
+    if cost_tail < cost_all:
+        return [(0, rows_a, 1, ntiles * TJ), (rows_a, nrow, ns_b, chunk_b)]
+    return [(0, nrow, ns_all, chunk_all)]

@@ -11,8 +11,8 @@ Supported surface: constructors from tensors / floats / ints / lists / ``(ind, d
 ``Vi / Vj / Pm``, element-wise arithmetic and math functions, ``sum(-1)``, ``|``, ``@``,
 concatenation / extraction, all reductions of the engine (sum, logsumexp, sumsoftmaxweight, min,
 argmin, min_argmin, max, argmax, max_argmax, Kmin, argKmin, Kmin_argKmin), ``solve`` and batch
-dimensions.  Not carried over: complex numbers, float16, ``ranges`` (block-sparse reductions),
-TensorDot / Kron / BSpline / SoftDTW.
+dimensions, block-sparse ``ranges`` (helpers in :mod:`keops_b200.torch.cluster`).  Not carried over: complex
+numbers, float16, TensorDot / Kron / BSpline / SoftDTW.
 """
 from __future__ import annotations
 

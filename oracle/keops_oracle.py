@@ -774,6 +774,59 @@ def genred(formula, aliases, args, dtype="float32", chunk_elems=1 << 24):
     return out
 
 
+def genred_ranges(formula, aliases, args, ranges, dtype="float32"):
+    """Block-sparse reduction (``ranges`` 6-tuple, ``pykeops/pykeops/torch/generic/generic_red.py:581-639``):
+    row-range ``k`` is reduced over the union of its column ranges, in increasing column order, exactly
+    like the scalar loops of ``CpuReduc_ranges`` (``keopscore/keopscore/mapreduce/cpu/CpuReduc_ranges.py:173-228``);
+    arg-type outputs are *global* column indices.  Rows covered by no range are left at 0."""
+    red = parse(formula, aliases)
+    tagI = red.tagI
+    vs = red.vars()
+    rx, sx, ry = (np.asarray(r, np.int64) for r in (ranges[0:3] if tagI == 0 else ranges[3:6]))
+    nrow = None
+    for v in vs.values():
+        if v.cat == tagI:
+            nrow = np.asarray(args[v.ind]).reshape(-1, v.dim).shape[0]
+    out = None
+    d, K, kind = red.F.dim, red.K, red.kind
+    for k in range(rx.shape[0]):
+        r0, r1 = int(rx[k, 0]), int(rx[k, 1])
+        if r1 <= r0:
+            continue
+        s0 = 0 if k == 0 else int(sx[k - 1])
+        cols = [np.arange(int(ry[l, 0]), int(ry[l, 1])) for l in range(s0, int(sx[k]))]
+        J = np.concatenate(cols) if cols else np.zeros(0, np.int64)
+        sub = list(args)
+        for v in vs.values():
+            a = np.asarray(args[v.ind])
+            if v.cat == tagI:
+                sub[v.ind] = a.reshape(-1, v.dim)[r0:r1]
+            elif v.cat == 1 - tagI:
+                sub[v.ind] = a.reshape(-1, v.dim)[J]
+        if len(J) == 0:
+            continue    # the reference writes the accumulator's initial value here; not exercised by the fixtures
+        res = genred(formula, aliases, sub, dtype)
+        if out is None:
+            out = np.zeros((nrow, res.shape[1]), res.dtype)
+
+        def remap(block):                                   # local column positions -> global column indices
+            return J[block.astype(np.int64)].astype(res.dtype)
+        if kind in ("ArgMin", "ArgMax"):
+            res = remap(res)
+        elif kind == "ArgKMin":
+            r3 = remap(res).reshape(-1, K, d)
+            r3[:, len(J):, :] = 0                           # fewer than K columns: padding entries stay (inf, 0)
+            res = r3.reshape(res.shape)
+        elif kind in ("Min_ArgMin", "Max_ArgMax"):
+            res[:, d:] = remap(res[:, d:])
+        elif kind == "KMin_ArgKMin":
+            r3 = res.reshape(-1, K, 2, d)
+            r3[:, :, 1, :] = np.where(np.isfinite(r3[:, :, 0, :]), remap(r3[:, :, 1, :]), 0)
+            res = r3.reshape(res.shape)
+        out[r0:r1] = res
+    return out
+
+
 def dense(formula, aliases, args, dtype="float64"):
     """Dense ``(nrow, ncol, dimF)`` values of the reduction's formula (small cases only); used by the
     tests to decide whether an index mismatch is a genuine near-tie."""
