@@ -81,6 +81,20 @@ int kb200_max_active_blocks(kb200_function fn, int block_size, size_t dynamic_sm
 int kb200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
                       int64_t* l2_bytes, int64_t* total_mem_bytes);
 
+/* Opt a kernel in to more than 48 KB of dynamic shared memory (cuFuncSetAttribute); the tensor-core
+ * K-nearest-neighbour kernel stages its operand tiles in ~140 KB.  The reference assumes 48 KB
+ * (keopscore/keopscore/include/CudaSizes.h:11-31).                                                     */
+int kb200_function_set_max_dynamic_smem(kb200_function fn, int bytes);
+
+/* Encode a TMA descriptor (CUtensorMap, 128 bytes, 64-byte aligned host buffer) for a row-major 2-D
+ * array `base[outer][inner]` of 2-byte (bf16) or 4-byte (f32) elements with a row pitch of
+ * `row_stride_bytes`; the kernel receives it as a __grid_constant__ parameter and issues
+ * cp.async.bulk.tensor loads of (box_outer x box_inner) tiles, optionally 32/64/128-byte swizzled
+ * (the layout tcgen05.mma shared-memory descriptors expect).  No reference counterpart: the
+ * reference's kernels only use plain global loads.                                     */
+int kb200_tensor_map_2d(void* tensor_map, int elem_bytes, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
 /* ---- launch -----------------------------------------------------------------------------
  * Generic asynchronous launch (cuLaunchKernel) on `stream` (a CUstream / cudaStream_t; NULL =
  * legacy default stream).  `params[i]` points to the i-th kernel argument.                      */

@@ -17,6 +17,7 @@ There is deliberately no CPU path: ``tagCPUGPU == 0`` raises.
 """
 from __future__ import annotations
 
+import os
 import threading
 import types
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -27,6 +28,7 @@ from .formulas.parser import parse_reduction, parse_alias
 from .formulas.reductions import Reduction
 from .formulas.ir import FormulaError
 from .codegen.emit import generate, KernelSource
+from .codegen import knn_tc
 from .runtime import plan, capi
 
 _binder_cache: Dict[tuple, "LoadKeOpsB200"] = {}
@@ -225,6 +227,34 @@ class LoadKeOpsB200:
             return out
         if ranges is not None:
             return self._genred_ranges(dev, ranges, nrow, ncol, out, args, tdtype)
+        tc = knn_tc.eligible(self.red, p.dtype, nrow, ncol, nbatch)
+        if tc is not None:
+            return self._genred_knn_tc(dev, tc, nrow, ncol, out, args, strides, tdtype)
+        return self._launch_dense(dev, nrow, ncol, nbatch, out, args, strides, tdtype)
+
+    def _genred_knn_tc(self, dev, tc, nrow, ncol, out, args, strides, tdtype):
+        """K-min of a squared distance in large dimension: tcgen05 filter + exact re-evaluation
+        (``codegen/knn_tc.py``); rows whose candidate list overflowed go through the CUDA-core kernel."""
+        p = self.params
+        row_ind, col_ind, D = tc
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        eng = knn_tc.get(D, self.red.K, self.red.kind, p.use_fast_math, index)
+        with torch.cuda.device(dev):
+            over = eng.run(args[row_ind], args[col_ind], out.view(nrow, p.dim), torch.cuda.current_stream(dev))
+        self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0, blocks_per_sm=1,
+                                launches=4, engine="tcgen05", overflow_rows=eng.last["overflow"])
+        if over.numel():
+            sub = list(args)
+            sub[row_ind] = args[row_ind][over].contiguous()
+            res = torch.empty((over.numel(), p.dim), dtype=tdtype, device=dev)
+            self._launch_dense(dev, over.numel(), ncol, 1, res, sub, strides, tdtype)
+            out.view(nrow, p.dim)[over] = res
+            self.last_launch["engine"] = "tcgen05"
+            self.last_launch["overflow_rows"] = int(over.numel())
+        return out
+
+    def _launch_dense(self, dev, nrow, ncol, nbatch, out, args, strides, tdtype):
+        p = self.params
         lk = self._kernel(dev.index if dev.index is not None else torch.cuda.current_device())
         ks = self.ks
         rows_per_block = ks.cfg.T * ks.cfg.R
@@ -232,7 +262,11 @@ class LoadKeOpsB200:
         slots = max(1, (lk.sm_count * lk.blocks_per_sm) // min(nbatch, lk.sm_count * lk.blocks_per_sm))
         ws_limit = max(1, (2 << 30) // nbatch)
         kfam = self.red.kind in ("KMin", "ArgKMin", "KMin_ArgKMin")
-        if nbatch == 1 and p.tag1D2D == 0:
+        # Tail-split pays only when a restart is expensive (K-min lists).  For sums, measured on B200
+        # (Gaussian conv, M=N=1e6): one long unsplit wave + a split tail = 272 ms vs 262 ms for the uniform
+        # 3-way split, whose short CTAs backfill and average out per-SM speed differences.
+        tail_split = kfam if os.environ.get("KB200_TAILSPLIT") is None else os.environ["KB200_TAILSPLIT"] == "1"
+        if nbatch == 1 and p.tag1D2D == 0 and tail_split:
             # restart cost of a K-min list, in tile units: ~ K * log(N/K) insertions per row, each stalling its warp
             penalty = (0.02 * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0
             segments = plan.launch_segments(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,

@@ -1,0 +1,191 @@
+"""Tensor-core path for K-min reductions of a squared Euclidean distance in large dimension.
+
+``KMin / ArgKMin / KMin_ArgKMin_Reduction(Sum(Square(x_i - y_j)), K, tagI)`` with ``D >= 16`` is what the
+reference runs through the generic ``GpuReduc1D`` kernel at 2 D + 1 FP32 instructions per pair
+(``keopscore/keopscore/mapreduce/gpu/GpuReduc1D.py:70-90``, reduction
+``keopscore/keopscore/formulas/reductions/KMin_ArgKMin_Reduction.py:16-100``).  Here the contraction
+``x_i . y_j`` is a tcgen05 GEMM used as a conservative *filter*; survivors are re-evaluated exactly, so
+the output is bit-identical to the CUDA-core kernel (``keops_b200/csrc/kb200_knn_tc.cu`` has the bound).
+
+This module recognises the pattern, JIT-compiles the three kernels for (D, K, output kind) and drives
+them: ``prep`` (bf16 copies + penalties) -> ``filter`` (TMA + tcgen05 + TMEM) -> ``select`` (exact top-K);
+rows whose candidate list overflowed are recomputed by the caller with the CUDA-core kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import threading
+from typing import Dict, Optional, Tuple
+
+from ..formulas.reductions import Reduction
+from ..runtime import capi, plan
+
+_SRC_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "kb200_knn_tc.cu")
+VERSION = "knn-tc-4"
+BM, BN, STAGES, HS = 256, 128, 4, 16
+ROW_BATCH = 1 << 20          # rows per filter launch: bounds the candidate workspace (CAP * 4 bytes per row)
+_lock = threading.RLock()
+
+
+def match(red: Reduction) -> Optional[Tuple[int, int, int]]:
+    """``(row_var_index, col_var_index, D)`` if the reduction is a K-min of ``Sum(Square(Var - Var))`` between
+    one output-side and one streamed variable of equal dimension; ``None`` otherwise."""
+    if red.kind not in ("KMin", "ArgKMin", "KMin_ArgKMin") or red.dimF != 1:
+        return None
+    f = red.formula
+    if f.op != "Sum" or len(f.args) != 1 or f.args[0].op != "Square":
+        return None
+    sub = f.args[0].args[0]
+    if sub.op != "Subtract" or len(sub.args) != 2 or any(a.op != "Var" for a in sub.args):
+        return None
+    (ia, da, ca), (ib, db, cb) = sub.args[0].params, sub.args[1].params
+    if da != db or {ca, cb} != {0, 1}:
+        return None
+    row, col = (ia, ib) if ca == red.tagI else (ib, ia)
+    return row, col, da
+
+
+def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int) -> Optional[Tuple[int, int, int]]:
+    """The tensor-core path pays off once the GEMM dominates: D >= 16 and a full machine of 256-row CTAs."""
+    if os.environ.get("KB200_KNN_TC", "1") == "0" or dtype != "float32" or nbatch != 1:
+        return None
+    m = match(red)
+    if m is None:
+        return None
+    D = m[2]
+    if D < 16 or D > 141 or red.K > 16 or nrow < 8192 or ncol < 4096 or ncol >= (1 << 31) - BN:
+        return None                      # D <= 141: operand tiles of 2 + 4 stages must fit 227 KB of shared memory
+    return m
+
+
+class KnnTensorCore:
+    """Compiled kernels for one (D, K, output kind, fast-math) combination on one device."""
+
+    def __init__(self, D: int, K: int, kind: str, fast: bool, device: int, cap: int = 320):
+        self.D, self.K, self.kind, self.fast, self.cap = D, K, kind, fast, cap
+        # operand rows: D data columns + 3 penalty columns, as KBM 64-column blocks + one remainder block
+        total = D + 3
+        full, r = divmod(total, 64)
+        if r == 0:
+            self.KBM, self.REM = full - 1, 64
+        else:
+            self.KBM, self.REM = full, (16 if r <= 16 else (32 if r <= 32 else 64))
+        self.DPG = 64 * self.KBM + self.REM
+        self.outw = 2 * K if kind == "KMin_ArgKMin" else K
+        out_code = {"ArgKMin": 0, "KMin": 1, "KMin_ArgKMin": 2}[kind]
+        with open(_SRC_PATH) as f:
+            body = f.read()
+        defs = ("#define KT_D %d\n#define KT_KBM %d\n#define KT_REM %d\n#define KT_K %d\n#define KT_CAP %d\n"
+                "#define KT_OUT %d\n#define KT_FAST %d\n" % (D, self.KBM, self.REM, K, cap, out_code, 1 if fast else 0))
+        self.BN = int(os.environ.get("KT_BN", BN))
+        self.STAGES = int(os.environ.get("KT_STAGES", STAGES if self.BN == 128 else 6))
+        defs += "#define KT_BN %d\n#define KT_STAGES %d\n#define KT_DBG %d\n" % (self.BN, self.STAGES, int(os.environ.get("KT_DBG", 0)))
+        defs += "#define KT_SPIN %d\n" % int(os.environ.get("KT_SPIN", 0))
+        src = defs + body
+        opts = plan.nvrtc_options(fast)
+        key = hashlib.sha256((VERSION + src + " ".join(opts)).encode()).hexdigest()[:20]
+        path = os.path.join(plan.cache_dir(), "kb200_knntc_%s.cubin" % key)
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                cubin = f.read()
+        else:
+            cubin = capi.compile_to_cubin(src, opts, name="kb200_knntc_%s.cu" % key)
+            tmp = path + ".tmp%d" % os.getpid()
+            with open(tmp, "wb") as f:
+                f.write(cubin)
+            os.replace(tmp, path)
+        self.cubin = cubin
+        blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K
+        self.smem = 1024 + 2 * blk(128) + self.STAGES * blk(self.BN) + HS * self.BN * 4 + 640
+        self.smem = max(self.smem, 120 * 1024)     # one CTA per SM: each CTA allocates all 512 TMEM columns
+        self.module = None
+        if device >= 0:
+            self.module = capi.Module(cubin, device)
+            self.fn_prep = self.module.function("kb200_knn_prep")
+            self.fn_filter = self.module.function("kb200_knn_filter")
+            self.fn_select = self.module.function("kb200_knn_select")
+            capi.set_max_dynamic_smem(self.fn_filter, self.smem)
+
+    def _maps(self, abf, n, box_rows):
+        """TMA descriptors of a bf16 operand array (n, DPG): the 64-column main blocks (128-byte swizzle) and the
+        remainder block (swizzled at its own width), with boxes of ``box_rows`` rows."""
+        pitch = self.DPG * 2
+        rem = capi.tensor_map_2d(abf.data_ptr() + 128 * self.KBM, 2, self.REM, n, pitch, self.REM, box_rows, self.REM * 2)
+        if self.KBM == 0:
+            return rem, rem            # the main map is never dereferenced
+        return capi.tensor_map_2d(abf.data_ptr(), 2, 64 * self.KBM, n, pitch, 64, box_rows, 128), rem
+
+    def run(self, x, y, out, stream_obj):
+        """x (M, D), y (N, D) fp32 contiguous CUDA tensors; out (M, outw) fp32.  Returns the tensor of row
+        indices whose candidate list overflowed (usually empty) -- the caller recomputes those rows."""
+        import torch
+        M, N = x.shape[0], y.shape[0]
+        dev = x.device
+        stream = stream_obj.cuda_stream
+        i64, ptr, i32 = C.c_longlong, C.c_void_p, C.c_int
+        BN = self.BN
+        ntiles = -(-N // BN)
+        ybf = torch.empty((N, self.DPG), dtype=torch.int16, device=dev)
+        ypen = torch.empty(ntiles * BN, dtype=torch.float32, device=dev)    # padded: the last tile is bulk-copied whole
+        capi.launch(self.fn_prep, stream, (-(-N // 256),), (256,), 0,
+                    [i64(N), ptr(y.data_ptr()), ptr(ybf.data_ptr()), ptr(ypen.data_ptr()), i32(0)])
+        map_y, map_yr = self._maps(ybf, N, BN)
+        overflow_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        overflow_rows = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        for r0 in range(0, M, ROW_BATCH):
+            m = min(ROW_BATCH, M - r0)
+            xs = x[r0:r0 + m]
+            xbf = torch.empty((m, self.DPG), dtype=torch.int16, device=dev)
+            xpen = torch.empty(m, dtype=torch.float32, device=dev)
+            capi.launch(self.fn_prep, stream, (-(-m // 256),), (256,), 0,
+                        [i64(m), ptr(xs.data_ptr()), ptr(xbf.data_ptr()), ptr(xpen.data_ptr()), i32(1)])
+            map_x, map_xr = self._maps(xbf, m, 128)
+            cand = torch.empty(m * self.cap, dtype=torch.int32, device=dev)
+            count = torch.empty(m, dtype=torch.int32, device=dev)
+            if os.environ.get("KT_TIME"):
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(stream_obj)
+            capi.launch(self.fn_filter, stream, (-(-m // BM),), (320,), self.smem,
+                        [map_x, map_xr, map_y, map_yr, i64(m), i64(N), ptr(ypen.data_ptr()), ptr(xpen.data_ptr()),
+                         ptr(cand.data_ptr()), ptr(count.data_ptr())])
+            if os.environ.get("KT_TIME"):
+                ev1.record(stream_obj)
+                torch.cuda.synchronize()
+                print("KT_TIME filter %.3f ms (BN=%d STAGES=%d DBG=%s)" % (ev0.elapsed_time(ev1), BN, self.STAGES, os.environ.get("KT_DBG", "0")))
+            # select writes rows r0.. of `out`; overflow rows are reported relative to the batch
+            ov_before = overflow_count.clone() if r0 else None
+            capi.launch(self.fn_select, stream, (-(-m // 8),), (256,), 0,
+                        [i64(m), i64(N), ptr(xs.data_ptr()), ptr(y.data_ptr()), ptr(cand.data_ptr()), ptr(count.data_ptr()),
+                         ptr(out.data_ptr() + r0 * self.outw * 4), ptr(overflow_count.data_ptr()),
+                         ptr(overflow_rows.data_ptr())])
+            if r0:
+                # make the batch-relative indices appended by this launch global
+                a, b = int(ov_before.item()), int(overflow_count.item())
+                if b > a:
+                    overflow_rows[a:b] += r0
+            if os.environ.get("KT_STATS"):
+                cf = count.float()
+                self.stats = dict(mean_candidates=float(cf.mean()), max_candidates=float(cf.max()),
+                                  p99=float(cf.kthvalue(max(1, int(0.99 * m))).values))
+            for t in (xbf, xpen, cand, count):
+                t.record_stream(stream_obj)
+        for t in (ybf, ypen):
+            t.record_stream(stream_obj)
+        n_over = int(overflow_count.item())          # one host sync per call (the reference syncs on every call)
+        self.last = dict(overflow=n_over, ntiles=ntiles, ctas=-(-min(M, ROW_BATCH) // BM))
+        return overflow_rows[:n_over].to(torch.int64)
+
+
+_cache: Dict[tuple, KnnTensorCore] = {}
+
+
+def get(D: int, K: int, kind: str, fast: bool, device: int) -> KnnTensorCore:
+    key = (D, K, kind, bool(fast), device)
+    with _lock:
+        k = _cache.get(key)
+        if k is None:
+            k = KnnTensorCore(D, K, kind, fast, device)
+            _cache[key] = k
+        return k

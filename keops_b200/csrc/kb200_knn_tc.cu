@@ -1,0 +1,520 @@
+// kb200_knn_tc.cu -- K-nearest-neighbour reductions (KMin / ArgKMin / KMin_ArgKMin of a squared
+// Euclidean distance, large D) on the 5th-generation tensor cores of sm_100a.
+//
+// Reference semantics: KMin_ArgKMin_Reduction (keopscore/keopscore/formulas/reductions/
+// KMin_ArgKMin_Reduction.py:16-100) applied to Sum(Square(x_i - y_j)); the reference evaluates every
+// pair on CUDA cores (GpuReduc1D.py:70-90; 129 FP32 instructions per pair at D = 64).
+//
+// Design ("tensor-core K-min"): the contraction x_i . y_j runs on tcgen05.mma (bf16
+// operands, fp32 accumulation in TMEM) purely as a *filter*; every surviving pair is re-evaluated exactly
+// (fp32, the reference's operation order) by kb200_knn_select, so the result is bit-identical to the
+// CUDA-core kernel whatever the filter's rounding:
+//
+//   acc_ij ~ x_i.y_j   with |acc_ij - x_i.y_j| <= (c/2)(|x_i|^2 + |y_j|^2)     (c covers bf16 rounding of both
+//                                                                               operands, fp32 accumulation and
+//                                                                               the fp32 rounding of the exact path)
+//   (acc_ij is produced *including* the column penalty: three extra K columns hold 1 on the x side and
+//    the bf16 hi/mid/lo split of -(1-c)|y_j|^2/2 on the y side, so the epilogue is a pure max-reduction)
+//   U_ij = acc_ij - (1-c)|y_j|^2/2   (upper bound of  x.y - |y|^2/2  minus (c/2)|x|^2)
+//   L_ij = acc_ij - (1+c)|y_j|^2/2   (lower bound of  x.y - |y|^2/2  plus  (c/2)|x|^2)
+//   Theta_i = K-th largest L_ij seen so far  ==>  at least K columns are at least that close, hence column j
+//   can belong to the final K nearest only if  U_ij >= Theta_i - c|x_i|^2 =: tau_i  (non-strict: ties kept).
+//
+// kb200_knn_filter : one CTA = 256 rows (two 128-row accumulators) x all columns, streamed in 128-column
+//   tiles.  Warp 0 = TMA producer (y tiles, 128B-swizzled, + the per-column penalty), warp 1 = MMA issuer,
+//   warps 2..9 = epilogue: one thread per row, tcgen05.ld of its 128 accumulators, FMNMX3 max-reduction against
+//   tau_i; survivors are appended to the row's candidate list and update Theta_i (register-resident list).
+//   4-stage smem ring, double-buffered TMEM accumulators (2 row blocks x 2 buffers x 128 columns = 512).
+// kb200_knn_prep   : fp32 -> bf16 operand rows (data, penalty columns, zero padding) + per-row penalty terms.
+// kb200_knn_select : one warp per row, exact distances of the candidates + ordered top-K (ties -> smallest j).
+//
+// Compile-time parameters (defined by keops_b200/codegen/knn_tc.py): KT_D (true dimension); the bf16 operand
+// rows hold D + 3 columns padded to KT_DPG = 64 * KT_KBM + KT_REM (KT_KBM 128-byte-swizzled 64-column blocks
+// plus one remainder block of KT_REM = 16 / 32 / 64 columns swizzled at its own width); KT_K, KT_CAP (candidate
+// slots per row, multiple of 32), KT_OUT (0 ArgKMin, 1 KMin, 2 KMin_ArgKMin), KT_FAST (1: FTZ arithmetic of
+// --use_fast_math, like the CUDA-core kernel).
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#ifndef KT_D
+#define KT_D 64
+#define KT_KBM 1
+#define KT_REM 16
+#define KT_K 10
+#define KT_CAP 320
+#define KT_OUT 0
+#define KT_FAST 1
+#endif
+
+#define KT_BM 256                             /* rows per CTA: two 128-row accumulators                         */
+#ifndef KT_BN
+#define KT_BN 128                             /* columns per tile (= N of one tcgen05.mma): 64 or 128           */
+#endif
+#ifndef KT_SPIN
+#define KT_SPIN 0                             /* 1: poll barriers with test_wait instead of try_wait             */
+#endif
+#ifndef KT_DBG
+#define KT_DBG 0                              /* 1: no rare path, 2: TMEM loads only, 3: no TMEM loads (timing experiments) */
+#endif
+#define KT_NBUF (512 / (2 * KT_BN))           /* TMEM accumulator buffers per row block (all 512 columns used)   */
+#define KT_DPG (64 * KT_KBM + KT_REM)
+#ifndef KT_STAGES
+#define KT_STAGES 4
+#endif
+#define KT_HS 16                              /* slots of the column-penalty ring                               */
+#define KT_C 0.008f
+#define KT_TILE_BYTES(rows) ((rows) * 128)                    /* rows x 64 bf16                                 */
+#define KT_RTILE_BYTES(rows) ((rows) * KT_REM * 2)            /* rows x KT_REM bf16                             */
+#define KT_BLK_BYTES(rows) (KT_KBM * KT_TILE_BYTES(rows) + KT_RTILE_BYTES(rows))   /* one operand block, all of K */
+#define KT_A_BYTES (2 * KT_BLK_BYTES(128))
+#define KT_B_BYTES KT_BLK_BYTES(KT_BN)
+#define KT_SMEM_BYTES (1024 + KT_A_BYTES + KT_STAGES * KT_B_BYTES + KT_HS * KT_BN * 4 + 640) /* mirrored in knn_tc.py */
+#define KT_INF (__int_as_float(0x7f800000))
+
+struct __align__(64) KtTensorMap { u64 opaque[16]; };
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 kt_smem(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void kt_mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void kt_mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void kt_mbar_arrive(u32 bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void kt_mbar_wait(u32 bar, u32 parity) {
+  // bounded spin: a protocol bug traps (the launch fails loudly) instead of hanging the GPU
+  for (u32 spins = 0;; ++spins) {
+    u32 done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+#if KT_SPIN
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void kt_tma_2d(u32 dst, const KtTensorMap* map, int c0, int c1, u32 bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"((u64)map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void kt_bulk_1d(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"((u64)src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void kt_mma_bf16(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void kt_mma_commit(u32 bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// one lane of a *converged* warp; keeping the warp converged lets the compiler hold descriptors and
+// barrier addresses in uniform registers (a divergent `if (lane == 0)` wraps every UTCHMMA in an ELECT loop)
+__device__ __forceinline__ bool kt_elect() {
+  u32 pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void kt_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void kt_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 64 consecutive 32-bit columns: thread `lane` of the warp receives columns [col, col+64) of its TMEM lane
+#define KT_R8(b) "%" #b
+__device__ __forceinline__ void kt_tmem_ld64_nowait(u32 taddr, float* v) {
+  u32 r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+        "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int e = 0; e < 64; e++) v[e] = __uint_as_float(r[e]);
+}
+__device__ __forceinline__ void kt_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile whose rows are `row_bytes` (32 / 64 / 128) wide and swizzled at that width: rows are
+// row_bytes apart, 8-row groups 8 * row_bytes apart (SBO); layout type 6 / 4 / 2 = SWIZZLE_32B / 64B / 128B
+__device__ __forceinline__ u64 kt_smem_desc(u32 saddr, u32 row_bytes) {
+  const u64 layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  return (u64)((saddr & 0x3FFFF) >> 4) | ((u64)1 << 16) | ((u64)((8 * row_bytes) >> 4) << 32) | ((u64)1 << 46) | (layout << 61);
+}
+// bf16 x bf16 -> f32, A and B K-major, M = 128, N = KT_BN
+#define KT_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | (((u32)KT_BN >> 3) << 17) | ((128u >> 4) << 24))
+
+// ------------------------------------------------------------------------------------------------
+// prep: fp32 rows -> bf16 operand rows of KT_DPG columns + fp32 penalty
+//   mode 0 (streamed side y): [ y_0 .. y_{D-1}, -h_hi, -h_mid, -h_lo, 0 .. ],  h = (1-c)|y|^2/2 split into three
+//                             bf16 terms (24 significant bits);  pen = h
+//   mode 1 (output side x)  : [ x_0 .. x_{D-1}, 1, 1, 1, 0 .. ];               pen = c|x|^2
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned short kt_bf16_rn(float v) {
+  u32 b = __float_as_uint(v);
+  b += 0x7FFFu + ((b >> 16) & 1u);            // round to nearest even (finite inputs)
+  return (unsigned short)(b >> 16);
+}
+__device__ __forceinline__ float kt_bf16_to_f(unsigned short h) { return __uint_as_float(((u32)h) << 16); }
+
+extern "C" __global__ void __launch_bounds__(256)
+kb200_knn_prep(const long long n, const float* __restrict__ a, unsigned short* __restrict__ abf,
+               float* __restrict__ pen, const int mode) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* row = a + r * KT_D;
+  unsigned short* orow = abf + r * KT_DPG;
+  float s = 0.0f;
+#pragma unroll 8
+  for (int k = 0; k < KT_D; k++) {
+    const float v = row[k];
+    s = fmaf(v, v, s);
+    orow[k] = kt_bf16_rn(v);
+  }
+  if (mode == 0) {
+    const float h = (1.0f - KT_C) * 0.5f * s;
+    const unsigned short hi = kt_bf16_rn(h);
+    const float r1 = h - kt_bf16_to_f(hi);
+    const unsigned short mid = kt_bf16_rn(r1);
+    const unsigned short lo = kt_bf16_rn(r1 - kt_bf16_to_f(mid));
+    orow[KT_D] = hi ^ 0x8000u; orow[KT_D + 1] = mid ^ 0x8000u; orow[KT_D + 2] = lo ^ 0x8000u;   // negated
+    pen[r] = h;
+  } else {
+    orow[KT_D] = 0x3F80u; orow[KT_D + 1] = 0x3F80u; orow[KT_D + 2] = 0x3F80u;                   // 1.0
+    pen[r] = KT_C * s;
+  }
+  for (int k = KT_D + 3; k < KT_DPG; k++) orow[k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(320, 1)
+kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_xr,
+                 const __grid_constant__ KtTensorMap map_y, const __grid_constant__ KtTensorMap map_yr,
+                 const long long nrow, const long long ncol, const float* __restrict__ ypen,
+                 const float* __restrict__ xpen, int* __restrict__ cand, int* __restrict__ cand_count) {
+  extern __shared__ unsigned char kt_raw[];
+  const u32 raw = kt_smem(kt_raw);
+  const u32 base = (raw + 1023u) & ~1023u;                       // swizzle atoms need (up to) 1024-byte alignment
+  unsigned char* gbase = kt_raw + (base - raw);
+  const u32 sA = base;                                           // 2 row blocks x [KBM main tiles | remainder tile]
+  const u32 sB = sA + KT_A_BYTES;                                // STAGES x [KBM main tiles | remainder tile]
+  const u32 sH = sB + KT_STAGES * KT_B_BYTES;                    // ring of column penalties (KT_HS x KT_BN floats)
+  const float* hy = reinterpret_cast<const float*>(gbase + KT_A_BYTES + KT_STAGES * KT_B_BYTES);
+  const u32 sBar = sH + KT_HS * KT_BN * 4;
+  // barriers (8 bytes each): full[8] @0, empty[8] @64, tfull[buf][rb] (<= 8) @128, tempty[buf][rb] @192,
+  //                          hfull[16] @256, hempty[16] @384, afull @512, tmem pointer @520
+  const u32 bFull = sBar, bEmpty = sBar + 64, bTFull = sBar + 128, bTEmpty = sBar + 192, bAFull = sBar + 512;
+  const u32 bHFull = sBar + 256, bHEmpty = sBar + 384;
+  volatile u32* tmem_slot =
+      reinterpret_cast<volatile u32*>(gbase + KT_A_BYTES + KT_STAGES * KT_B_BYTES + KT_HS * KT_BN * 4 + 520);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row_base = (long long)blockIdx.x * KT_BM;
+  const int ntiles = (int)((ncol + KT_BN - 1) / KT_BN);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < KT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
+    for (int b = 0; b < 2 * KT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, 4); }
+    for (int h = 0; h < KT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, 8); }
+    kt_mbar_init(bAFull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sBar + 520), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  kt_fence_before();
+  __syncthreads();
+  kt_fence_after();
+  const u32 tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    if (kt_elect()) {
+      kt_mbar_expect_tx(bAFull, KT_A_BYTES);
+      for (int rb = 0; rb < 2; rb++) {
+        for (int kb = 0; kb < KT_KBM; kb++)
+          kt_tma_2d(sA + rb * KT_BLK_BYTES(128) + kb * KT_TILE_BYTES(128), &map_x, kb * 64, (int)(row_base + rb * 128), bAFull);
+        kt_tma_2d(sA + rb * KT_BLK_BYTES(128) + KT_KBM * KT_TILE_BYTES(128), &map_xr, 0, (int)(row_base + rb * 128), bAFull);
+      }
+    }
+    __syncwarp();
+    for (int t = 0; t < ntiles; t++) {
+      const int s = t % KT_STAGES, h = t % KT_HS;
+      kt_mbar_wait(bEmpty + 8 * s, ((t / KT_STAGES) & 1) ^ 1);
+      kt_mbar_wait(bHEmpty + 8 * h, ((t / KT_HS) & 1) ^ 1);
+      if (kt_elect()) {
+        kt_mbar_expect_tx(bFull + 8 * s, KT_B_BYTES);
+        for (int kb = 0; kb < KT_KBM; kb++)
+          kt_tma_2d(sB + s * KT_B_BYTES + kb * KT_TILE_BYTES(KT_BN), &map_y, kb * 64, t * KT_BN, bFull + 8 * s);
+        kt_tma_2d(sB + s * KT_B_BYTES + KT_KBM * KT_TILE_BYTES(KT_BN), &map_yr, 0, t * KT_BN, bFull + 8 * s);
+        // column penalties of this tile (only the rare path of the epilogue reads them)
+        kt_mbar_expect_tx(bHFull + 8 * h, KT_BN * 4);
+        kt_bulk_1d(sH + h * KT_BN * 4, ypen + (long long)t * KT_BN, KT_BN * 4, bHFull + 8 * h);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+    kt_mbar_wait(bAFull, 0);
+    for (int t = 0; t < ntiles; t++) {
+      const int s = t % KT_STAGES, buf = t % KT_NBUF;
+      kt_mbar_wait(bFull + 8 * s, (t / KT_STAGES) & 1);
+#pragma unroll
+      for (int rb = 0; rb < 2; rb++) {
+        // each (buffer, row block) accumulator has its own full / empty pair: the other row block's MMAs
+        // cover the commit -> epilogue -> release round trip of this one
+        kt_mbar_wait(bTEmpty + 8 * (buf * 2 + rb), ((t / KT_NBUF) & 1) ^ 1);
+        kt_fence_after();
+        if (kt_elect()) {
+          const u32 d = tmem + (u32)((buf * 2 + rb) * KT_BN);
+#pragma unroll
+          for (int kb = 0; kb < KT_KBM; kb++) {
+            const u64 ad = kt_smem_desc(sA + rb * KT_BLK_BYTES(128) + kb * KT_TILE_BYTES(128), 128);
+            const u64 bd = kt_smem_desc(sB + s * KT_B_BYTES + kb * KT_TILE_BYTES(KT_BN), 128);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {            // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
+              if (KT_DBG != 6) kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), KT_IDESC, (u32)((kb | k) != 0));
+              if (KT_DBG == 7) kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), KT_IDESC, 1u);
+            }
+          }
+          {
+            const u64 ad = kt_smem_desc(sA + rb * KT_BLK_BYTES(128) + KT_KBM * KT_TILE_BYTES(128), KT_REM * 2);
+            const u64 bd = kt_smem_desc(sB + s * KT_B_BYTES + KT_KBM * KT_TILE_BYTES(KT_BN), KT_REM * 2);
+#pragma unroll
+            for (int k = 0; k < KT_REM / 16; k++)
+              kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), KT_IDESC, (u32)((KT_KBM | k) != 0));
+          }
+          kt_mma_commit(bTFull + 8 * (buf * 2 + rb));  // this accumulator is complete
+          if (rb == 1) kt_mma_commit(bEmpty + 8 * s);  // smem stage may be refilled once these MMAs have read it
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: one thread per row =====================
+    const int q = warp & 3, rb = (warp - 2) >> 2;
+    const long long i = row_base + rb * 128 + q * 32 + lane;
+    const bool live = i < nrow;
+    const float cx = live ? xpen[i] : 0.0f;
+    float tau = live ? -KT_INF : KT_INF;
+    float lst[KT_K];                                  // K largest lower bounds, descending
+#pragma unroll
+    for (int l = 0; l < KT_K; l++) lst[l] = -KT_INF;
+    int cnt = 0;
+    int* my_cand = cand + (live ? i : 0) * (long long)KT_CAP;
+    const float cy_scale = 2.0f * KT_C / (1.0f - KT_C);   // c|y|^2 = cy_scale * (1-c)|y|^2/2
+    for (int t = 0; t < ntiles; t++) {
+      const int buf = t % KT_NBUF, hslot = t % KT_HS;
+      kt_mbar_wait(bTFull + 8 * (buf * 2 + rb), (t / KT_NBUF) & 1);
+      kt_fence_after();
+      const float* hyt = hy + hslot * KT_BN;
+      bool hy_ready = false;                          // the penalty tile is waited for on first use only
+      const u32 tbase = tmem + ((u32)(q * 32) << 16) + (u32)((buf * 2 + rb) * KT_BN);
+      // the whole row of this tile goes to registers first, so that the accumulator buffer is handed back to
+      // the MMA warp before any (data-dependent) candidate processing
+      float uu[KT_BN];
+#if KT_DBG >= 3
+#pragma unroll
+      for (int e = 0; e < KT_BN; e++) uu[e] = -1.0f;
+#else
+#pragma unroll
+      for (int c = 0; c < KT_BN / 64; c++) kt_tmem_ld64_nowait(tbase + (u32)(c * 64), uu + c * 64);
+      kt_tmem_wait_ld();
+#endif
+      kt_fence_before();
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));
+#pragma unroll
+      for (int c = 0; c < KT_BN / 64; c++) {
+        float* u = uu + c * 64;                       // U_ij of 64 columns (the penalty is already inside)
+        float mg[8];                                  // maxima of the eight 8-column sub-groups
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+          float m = fmaxf(fmaxf(u[8 * g + 0], u[8 * g + 1]), u[8 * g + 2]);
+          m = fmaxf(fmaxf(m, u[8 * g + 3]), u[8 * g + 4]);
+          m = fmaxf(fmaxf(m, u[8 * g + 5]), u[8 * g + 6]);
+          mg[g] = fmaxf(m, u[8 * g + 7]);
+        }
+        const float m01 = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
+        const float m23 = fmaxf(fmaxf(mg[4], mg[5]), fmaxf(mg[6], mg[7]));
+#if KT_DBG >= 2
+        if (fmaxf(m01, m23) == 12345.678f) cnt++;
+#endif
+        if (KT_DBG == 0 && fmaxf(m01, m23) >= tau) {
+          // rare path (a few hundred times per row over the whole stream): everything statically indexed
+#pragma unroll
+          for (int g = 0; g < 8; g++) {
+            if (mg[g] >= tau) {
+              u32 hits = 0;
+#pragma unroll
+              for (int e = 0; e < 8; e++) hits |= (u[8 * g + e] >= tau) ? (1u << e) : 0u;
+              const long long j0 = (long long)t * KT_BN + c * 64 + g * 8;
+              while (hits) {
+                const int e = __ffs(hits) - 1;
+                hits &= hits - 1;
+                // 8 -> 1 select tree instead of a dynamically indexed (local-memory) array
+                const float a0 = (e & 1) ? u[8 * g + 1] : u[8 * g + 0], a1 = (e & 1) ? u[8 * g + 3] : u[8 * g + 2];
+                const float a2 = (e & 1) ? u[8 * g + 5] : u[8 * g + 4], a3 = (e & 1) ? u[8 * g + 7] : u[8 * g + 6];
+                const float b0 = (e & 2) ? a1 : a0, b1 = (e & 2) ? a3 : a2;
+                const float ue = (e & 4) ? b1 : b0;
+                if (ue >= tau && j0 + e < ncol) {
+                  if (cnt < KT_CAP) my_cand[cnt] = (int)(j0 + e);
+                  cnt++;
+                  if (!hy_ready) { kt_mbar_wait(bHFull + 8 * hslot, (t / KT_HS) & 1); hy_ready = true; }
+                  const float lo = ue - cy_scale * hyt[c * 64 + g * 8 + e];
+                  if (lo > lst[KT_K - 1]) {
+#pragma unroll
+                    for (int l = KT_K - 1; l > 0; --l) {
+                      if (lo > lst[l - 1]) lst[l] = lst[l - 1];
+                      else if (lo > lst[l]) lst[l] = lo;
+                    }
+                    if (lo > lst[0]) lst[0] = lo;
+                    tau = lst[KT_K - 1] - cx;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
+    }
+    if (live) cand_count[i] = cnt;
+  }
+  kt_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// select: exact fp32 distances of the candidates (the CUDA-core kernel's operation order: d0*d0, then
+// fma(d_k, d_k, acc) for k = 1..D-1) and the K smallest in (distance, index) order
+// ------------------------------------------------------------------------------------------------
+// x row in registers (loaded once per warp row), y row streamed with 16-byte loads when D allows it
+__device__ __forceinline__ float kt_sqdist(const float (&xr)[KT_D], const float* __restrict__ yr) {
+  float acc = 0.0f;
+#if KT_D % 4 == 0
+  const float4* y4 = reinterpret_cast<const float4*>(yr);
+#pragma unroll
+  for (int k4 = 0; k4 < KT_D / 4; k4++) {
+    const float4 v = __ldg(y4 + k4);
+    const float d0 = xr[4 * k4 + 0] - v.x, d1 = xr[4 * k4 + 1] - v.y, d2 = xr[4 * k4 + 2] - v.z, d3 = xr[4 * k4 + 3] - v.w;
+    acc = (k4 == 0) ? d0 * d0 : fmaf(d0, d0, acc);
+    acc = fmaf(d1, d1, acc);
+    acc = fmaf(d2, d2, acc);
+    acc = fmaf(d3, d3, acc);
+  }
+#else
+#pragma unroll
+  for (int k = 0; k < KT_D; k++) {
+    const float d = xr[k] - __ldg(yr + k);
+    acc = (k == 0) ? d * d : fmaf(d, d, acc);
+  }
+#endif
+  return acc;
+}
+
+extern "C" __global__ void __launch_bounds__(256)
+kb200_knn_select(const long long nrow, const long long ncol, const float* __restrict__ x, const float* __restrict__ y,
+                 const int* __restrict__ cand, const int* __restrict__ cand_count, float* __restrict__ out,
+                 int* __restrict__ overflow_count, int* __restrict__ overflow_rows) {
+  const int lane = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= nrow) return;
+  const int n = cand_count[i];
+  constexpr int OUTW = (KT_OUT == 2) ? 2 * KT_K : KT_K;
+  if (n > KT_CAP) {                                   // candidate list overflowed: the caller recomputes this row
+    if (lane == 0) { const int s = atomicAdd(overflow_count, 1); overflow_rows[s] = (int)i; }
+    return;
+  }
+  constexpr int PER = KT_CAP / 32;
+  float dv[PER];
+  int dj[PER];
+  float xr[KT_D];
+#pragma unroll
+  for (int k = 0; k < KT_D; k++) xr[k] = __ldg(x + i * KT_D + k);
+#pragma unroll
+  for (int p = 0; p < PER; p++) {
+    const int e = p * 32 + lane;
+    dv[p] = KT_INF;
+    dj[p] = 0x7fffffff;
+    if (e < n) {
+      const int j = cand[i * (long long)KT_CAP + e];
+      dj[p] = j;
+      dv[p] = kt_sqdist(xr, y + (long long)j * KT_D);
+    }
+  }
+  for (int l = 0; l < KT_K; l++) {
+    float bv = dv[0];
+    int bj = dj[0], bp = 0;
+#pragma unroll
+    for (int p = 1; p < PER; p++)
+      if (dv[p] < bv || (dv[p] == bv && dj[p] < bj)) { bv = dv[p]; bj = dj[p]; bp = p; }
+    float wv = bv;
+    int wj = bj;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, wj, o);
+      if (ov < wv || (ov == wv && oj < wj)) { wv = ov; wj = oj; }
+    }
+    if (wj == bj && bj != 0x7fffffff) {               // this lane owned the winner: retire it
+#pragma unroll
+      for (int p = 0; p < PER; p++)
+        if (p == bp) { dv[p] = KT_INF; dj[p] = 0x7fffffff; }
+    }
+    if (lane == 0) {
+      const bool none = (wj == 0x7fffffff);           // fewer than K columns: (inf, 0) like the reference's init
+      const float val = none ? KT_INF : wv;
+      const float idx = none ? 0.0f : (float)wj;
+      float* po = out + i * OUTW;
+      if (KT_OUT == 0) po[l] = idx;
+      else if (KT_OUT == 1) po[l] = val;
+      else { po[2 * l] = val; po[2 * l + 1] = idx; }
+    }
+  }
+}

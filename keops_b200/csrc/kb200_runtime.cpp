@@ -57,6 +57,10 @@ struct Driver {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                            unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
   int status = -1;  // -1 not tried, 0 ok, >0 error code
 };
 
@@ -108,7 +112,9 @@ int driver() {
             bind(lib, "cuFuncGetAttribute", d.FuncGetAttribute) &&
             bind(lib, "cuOccupancyMaxActiveBlocksPerMultiprocessor", d.OccupancyMaxActiveBlocks) &&
             bind(lib, "cuLaunchKernel", d.LaunchKernel) &&
-            bind(lib, "cuGetErrorString", d.GetErrorString);
+            bind(lib, "cuGetErrorString", d.GetErrorString) &&
+            bind(lib, "cuFuncSetAttribute", d.FuncSetAttribute) &&
+            bind(lib, "cuTensorMapEncodeTiled", d.TensorMapEncodeTiled);
   if (!ok) {
     g_drv.status = KB200_ENOCUDA;
     return fail(KB200_ENOCUDA, "libcuda.so.1 lacks a required symbol");
@@ -421,6 +427,47 @@ int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, voi
                               reinterpret_cast<CUstream>(stream), cparams, nullptr),
            "cuLaunchKernel(kb200_combine)");
   }
+  return 0;
+}
+
+int kb200_function_set_max_dynamic_smem(kb200_function fn, int bytes) {
+  int st = driver();
+  if (st) return st;
+  if (!fn || bytes < 0) return fail(KB200_EINVAL, "kb200_function_set_max_dynamic_smem: invalid argument");
+  CU_TRY(g_drv.FuncSetAttribute(reinterpret_cast<CUfunction>(fn), CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, bytes),
+         "cuFuncSetAttribute(MAX_DYNAMIC_SHARED_SIZE_BYTES)");
+  return 0;
+}
+
+int kb200_tensor_map_2d(void* tensor_map, int elem_bytes, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  int st = driver();
+  if (st) return st;
+  if (!tensor_map || !base || (reinterpret_cast<uintptr_t>(tensor_map) & 63) || (reinterpret_cast<uintptr_t>(base) & 15) ||
+      (row_stride_bytes & 15) || box_inner == 0 || box_outer == 0 || box_inner > 256 || box_outer > 256)
+    return fail(KB200_EINVAL, "kb200_tensor_map_2d: invalid argument / alignment");
+  CUtensorMapDataType dt;
+  switch (elem_bytes) {
+    case 2: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; break;
+    case 4: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+    default: return fail(KB200_EINVAL, "kb200_tensor_map_2d: elem_bytes must be 2 (bf16) or 4 (f32)");
+  }
+  CUtensorMapSwizzle sw;
+  switch (swizzle_bytes) {
+    case 0: sw = CU_TENSOR_MAP_SWIZZLE_NONE; break;
+    case 32: sw = CU_TENSOR_MAP_SWIZZLE_32B; break;
+    case 64: sw = CU_TENSOR_MAP_SWIZZLE_64B; break;
+    case 128: sw = CU_TENSOR_MAP_SWIZZLE_128B; break;
+    default: return fail(KB200_EINVAL, "kb200_tensor_map_2d: swizzle_bytes must be 0, 32, 64 or 128");
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CU_TRY(g_drv.TensorMapEncodeTiled(reinterpret_cast<CUtensorMap*>(tensor_map), dt, 2, const_cast<void*>(base), dims,
+                                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+         "cuTensorMapEncodeTiled");
   return 0;
 }
 

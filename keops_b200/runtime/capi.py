@@ -54,6 +54,8 @@ def _load() -> C.CDLL:
         "kb200_max_active_blocks": (i, [vp, i, sz, C.POINTER(i)]),
         "kb200_device_info": (i, [i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i64), C.POINTER(i64)]),
         "kb200_launch": (i, [vp, vp, u, u, u, u, u, u, u, C.POINTER(vp)]),
+        "kb200_function_set_max_dynamic_smem": (i, [vp, i]),
+        "kb200_tensor_map_2d": (i, [vp, i, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, i]),
         "kb200_genred_launch": (i, [vp, vp, vp, i64, i64, i, i, i, i64, vp, vp, i, C.POINTER(vp), i, C.POINTER(i64)]),
         "kb200_genred_launch_ranges": (i, [vp, vp, i64, i64, i, i64, vp, i, C.POINTER(vp), vp, vp, vp, vp, i]),
     }
@@ -69,7 +71,7 @@ EXPORTED_SYMBOLS = (
     "kb200_abi_version", "kb200_last_error", "kb200_compile", "kb200_compile_to_memory", "kb200_free",
     "kb200_module_load", "kb200_module_load_file", "kb200_module_unload", "kb200_module_get_function",
     "kb200_function_info", "kb200_max_active_blocks", "kb200_device_info", "kb200_launch",
-    "kb200_genred_launch", "kb200_genred_launch_ranges",
+    "kb200_genred_launch", "kb200_genred_launch_ranges", "kb200_function_set_max_dynamic_smem", "kb200_tensor_map_2d",
 )
 
 
@@ -158,6 +160,27 @@ def genred_launch_ranges(reduce_fn: int, stream: int, nrow: int, ncol: int, bloc
     arr = (C.c_void_p * max(n, 1))(*arg_ptrs)
     check(lib.kb200_genred_launch_ranges(reduce_fn, stream or None, nrow, ncol, block, grid_x, out_ptr, n, arr,
                                          ranges_x_ptr, slices_x_ptr, ranges_y_ptr, block_ends_ptr, nranges))
+
+
+def set_max_dynamic_smem(fn: int, nbytes: int):
+    check(lib.kb200_function_set_max_dynamic_smem(fn, int(nbytes)))
+
+
+class TensorMap(C.Structure):
+    """Opaque 128-byte CUtensorMap, 64-byte aligned (pass by value as a __grid_constant__ kernel parameter)."""
+    _fields_ = [("opaque", C.c_uint64 * 16)]
+    _align_ = 64
+
+
+def tensor_map_2d(base_ptr: int, elem_bytes: int, inner: int, outer: int, row_stride_bytes: int, box_inner: int,
+                  box_outer: int, swizzle_bytes: int) -> "TensorMap":
+    buf = C.create_string_buffer(128 + 64)
+    addr = (C.addressof(buf) + 63) & ~63
+    check(lib.kb200_tensor_map_2d(addr, elem_bytes, base_ptr, inner, outer, row_stride_bytes, box_inner, box_outer,
+                                  swizzle_bytes))
+    tm = TensorMap()
+    C.memmove(C.addressof(tm), addr, 128)
+    return tm
 
 
 def launch(fn: int, stream: int, grid, block, smem: int, params: Sequence):

@@ -111,8 +111,9 @@ def default_config(red: Reduction, dtype: str) -> KernelConfig:
     else:
         kfam = red.kind in ("KMin", "ArgKMin", "KMin_ArgKMin")
         if kfam and dimx <= 8 and red.K * red.dimF <= 16:
-            # measured on B200 (ArgKMin K=10, D=3, M=N=1e6): 253 ms vs 296 ms for (T=256, R=2)
-            R, T, min_blocks = 4, 128, 2
+            # measured on B200 (ArgKMin K=10, D=3, M=N=1e6, group=4): (T=256, R=4, 2 CTAs/SM, 128 regs) 232.9 ms;
+            # (T=128, R=4, 4 CTAs/SM) 239.2 ms; without the register cap (148 regs, 3 CTAs/SM) 252.5 ms
+            R, T, min_blocks = 4, 256, 2
         elif work <= 12:
             R, T, min_blocks = 4, 256, 4
         elif work <= 40:

@@ -1,0 +1,88 @@
+"""Tensor-core K-min path (tcgen05 filter + exact re-evaluation, ``keops_b200/csrc/kb200_knn_tc.cu``):
+its output must be *bit-identical* to the CUDA-core kernel's, whose parity with the reference is pinned
+by the golden fixtures (``tests/test_golden_gpu.py``: argkmin_K10_D64, kmin_argkmin, ...)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import keops_oracle as ko
+
+
+def _run(formula, nargs, args, M, N, dev, tc):
+    import torch
+    from keops_b200.binder import get_binder
+    old = os.environ.get("KB200_KNN_TC")
+    os.environ["KB200_KNN_TC"] = "1" if tc else "0"
+    try:
+        bd = get_binder(formula, [], nargs, "float32")
+        out = bd.genred_pytorch(dev, None, M, N, 0, None, *args)
+        torch.cuda.synchronize()
+        return out, dict(bd.last_launch)
+    finally:
+        if old is None:
+            os.environ.pop("KB200_KNN_TC", None)
+        else:
+            os.environ["KB200_KNN_TC"] = old
+
+
+CASES = [
+    # kind, D, K, M, N, tagI   (remainder block 16 / 64 / 32 / 64 columns; two main blocks for D = 128)
+    ("ArgKMin", 64, 10, 9000, 7001, 0),
+    ("KMin_ArgKMin", 100, 5, 8192, 6000, 0),
+    ("KMin", 16, 3, 8500, 5000, 0),
+    ("ArgKMin", 32, 1, 8200, 4100, 0),
+    ("ArgKMin", 128, 10, 8192, 4500, 0),
+    ("ArgKMin", 61, 4, 5000, 9000, 1),      # reduction over i: the output (and the tensor-core rows) follow j
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,D,K,M,N,tagI", CASES)
+def test_tensor_core_kmin_identical_to_cuda_core(kind, D, K, M, N, tagI, cuda_device):
+    import torch
+    torch.manual_seed(D * 1000 + K)
+    x, y = torch.randn(M, D, device=cuda_device), torch.randn(N, D, device=cuda_device)
+    f = "%s_Reduction(Sum(Square((Var(0,%d,0) - Var(1,%d,1)))),%d,%d)" % (kind, D, D, K, tagI)
+    o_tc, ll = _run(f, 2, (x, y), M, N, cuda_device, True)
+    assert ll.get("engine") == "tcgen05", ll          # the tensor-core kernels really ran
+    o_cc, ll2 = _run(f, 2, (x, y), M, N, cuda_device, False)
+    assert ll2.get("engine") is None
+    assert torch.equal(o_tc, o_cc)
+    # and a sample of rows against the CPU oracle (reference semantics: ties -> smallest index)
+    rows = slice(0, 64)
+    xa, ya = x.cpu().numpy(), y.cpu().numpy()
+    if tagI == 0:
+        ref = ko.genred(f, [], [xa[rows], ya], "float32")
+    else:
+        ref = ko.genred(f, [], [xa, ya[rows]], "float32")
+    got = o_tc[rows].cpu().numpy()
+    if kind == "ArgKMin":
+        agree = (got == ref).all(axis=1).mean()
+        assert agree > 0.9          # the numpy oracle does not contract FMAs: near-ties may swap
+    else:
+        np.testing.assert_allclose(got[:, ::2] if kind == "KMin_ArgKMin" else got,
+                                   ref[:, ::2] if kind == "KMin_ArgKMin" else ref, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_tensor_core_kmin_duplicates_and_outliers(cuda_device):
+    """Adversarial inputs for the filter: exact duplicate columns (ties must go to the smallest index), a huge
+    outlier column and rows, and clustered data whose neighbours are much closer than the norms."""
+    import torch
+    torch.manual_seed(5)
+    M, N, D, K = 8192, 6000, 64, 10
+    base = torch.randn(50, D, device=cuda_device) * 3
+    y = base[torch.randint(0, 50, (N,), device=cuda_device)] + 0.01 * torch.randn(N, D, device=cuda_device)
+    y[100:140] = y[60:100]                      # 40 exact duplicates of earlier columns
+    y[7] = 1e3                                   # outlier column
+    x = base[torch.randint(0, 50, (M,), device=cuda_device)] + 0.01 * torch.randn(M, D, device=cuda_device)
+    x[3] = -5e2                                  # outlier row
+    x[4] = y[60]                                 # a query that coincides with duplicated columns
+    f = "ArgKMin_Reduction(Sum(Square((Var(0,%d,0) - Var(1,%d,1)))),%d,0)" % (D, D, K)
+    o_tc, ll = _run(f, 2, (x, y), M, N, cuda_device, True)
+    o_cc, _ = _run(f, 2, (x, y), M, N, cuda_device, False)
+    assert ll.get("engine") == "tcgen05"
+    assert torch.equal(o_tc, o_cc), "overflow rows: %s" % ll.get("overflow_rows")
+    row = o_tc[4].long().tolist()
+    assert row[0] == 60 and row[1] == 100       # distance 0 twice: the smaller index first
