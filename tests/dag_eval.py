@@ -67,11 +67,14 @@ def evaluate(formula, aliases, args, dtype="float64", fast=False):
     d = red.dimF
     if red.kind in ("Sum", "LSE"):
         terms = []
-        for mode, nodes, neg in low.acc_terms:
+        scales = low.row_scales or [None] * len(low.acc_terms)
+        for (mode, nodes, neg), h in zip(low.acc_terms, scales):
             if mode == "zero":
                 terms.append(np.zeros((nrow, ncol), dt))
                 continue
             t = full(val[nodes[0].uid] * val[nodes[1].uid]) if mode == "fma" else full(val[nodes[0].uid])
+            if h is not None:       # row-side factor applied at write-back
+                t = t * full(val[h.uid])
             terms.append(-t if neg else t)
         if red.kind == "Sum":
             return np.stack([t.sum(axis=1, dtype=np.float64) for t in terms], axis=1).astype(dt)
