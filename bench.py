@@ -42,6 +42,9 @@ GRAD_X = "Grad_WithSavedForward(%s,Var(0,3,0),Var(3,1,0),Var(4,1,0))" % GAUSS
 GRAD_Y = "Grad_WithSavedForward(%s,Var(1,3,1),Var(3,1,0),Var(4,1,0))" % GAUSS
 KNN = "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)"
 SM_COUNT, SM_MAX_HZ = 148, 1.965e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one kb200_reduce launch of the full-size forward conv, from the
+# committed `ncu --set full` capture profiles/r01_ncu_gauss_fwd.txt (28.110 MB + 14 KB; algorithmic bytes 32 MB)
+NCU_DRAM_BYTES_FWD = 28110336 + 14080
 ROOFLINE_PAIRS_PER_CLK_SM = {"gauss_fwd": 16.0, "gauss_grad": 128.0 / 11.0, "knn_d3": 128.0 / 7.0}
 
 
@@ -100,6 +103,18 @@ class ClockSampler:
                 "reasons": reasons}
 
 
+_JSON_FD = None
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -146,7 +161,7 @@ def run_reference_arm(args):
     import numpy as np
     from oracle import ref_runner
     if not ref_runner.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (run oracle/build_ref.py where /root/reference is mounted)"}))
+        emit_json({"impl": "reference", "unavailable": "oracle/_ref was not built (run oracle/build_ref.py where /root/reference is mounted)"})
         return 0
     rng = np.random.default_rng(0)
     N = N_FULL
@@ -176,7 +191,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_json(line)
     return 0
 
 
@@ -193,6 +208,12 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / ref_cuda / knn / fwd_bwd legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kb200" else args.warmup
+    # the driver parses ONE JSON line from stdout: libraries that print to fd 1 (NCCL's version banner)
+    # are sent to stderr, and the JSON line is written to the original stdout
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -299,6 +320,33 @@ def main():
     h2d = hx_slab.numel() * 4 + (hy_p.numel() + hb_p.numel()) * 4 * (1 if (world == 1 or rank == 0) else 0)
     d2h = hout.numel() * 4
 
+    # ---- KNN K=10 (BASELINE configs[2], D=3) on the same sharding: each rank answers its slab of
+    # queries against the full (replicated) database; max over ranks; aggregate queries/s
+    knn_line = None
+    if not args.no_extras:
+        knn_b = get_binder(KNN, [], 2, "float32")
+        ko = knn_b.genred_pytorch(dev, None, Ms, N, 0, None, x, y)
+        sync_all()
+        knn_ms = []
+        for _ in range(3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if world > 1:
+                dist.broadcast(y, 0)
+            knn_b.genred_pytorch(dev, None, Ms, N, 0, ko, x, y)
+            e1.record()
+            sync_all()
+            knn_ms.append(e0.elapsed_time(e1))
+        kt = torch.tensor([min(knn_ms)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+        knn_t = float(kt.item())
+        knn_line = {"metric": "knn_k10_queries_per_s", "value": M / (knn_t * 1e-3), "unit": "queries/s", "D": 3, "K": 10,
+                    "ms": knn_t, "pair_evals_per_s": float(M) * N / (knn_t * 1e-3), "n_gpus": world,
+                    "frac_of_roofline": float(M) * N / (knn_t * 1e-3) / (ROOFLINE_PAIRS_PER_CLK_SM["knn_d3"] * SM_COUNT * SM_MAX_HZ * world)}
+        del ko
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -327,7 +375,8 @@ def main():
         "gpu_launches": int(kernel_launches),
         "clocks": clocks,
         "roofline": {"bound": "sfu", "achieved": achieved, "peak": peak_pairs, "unit": "pair-evals/s",
-                     "frac": achieved / peak_pairs, "traffic": None,
+                     "frac": achieved / peak_pairs,
+                     "traffic": NCU_DRAM_BYTES_FWD if (world == 1 and M == M_FULL) else None,
                      "note": "FP32/SFU roofline (SURVEY 8d): 1 MUFU.EX2 per pair at 16/clk/SM x 148 SM x %.0f MHz (max SM clock, %s)"
                              % (sm_hz / 1e6, peaks_src),
                      "kernel": "kb200_reduce", "ms_per_launch": k_ms},
@@ -338,6 +387,8 @@ def main():
     if clocks and clocks.get("sm_mhz"):
         line["roofline"]["frac_at_sustained_clock"] = achieved / (ROOFLINE_PAIRS_PER_CLK_SM["gauss_fwd"] * SM_COUNT * clocks["sm_mhz"] * 1e6)
 
+    if knn_line is not None:
+        line["knn"] = knn_line
     if not args.no_extras and world == 1:
         # ---- backward reductions + KNN (device-resident, CUDA events) -----------------------------
         def time_binder(bd, nrow, ncol, targs, reps=3):
@@ -363,11 +414,6 @@ def main():
                            "fwd_ms": fwd_ms, "grad_x_ms": gx_ms, "grad_y_ms": gy_ms,
                            "grad_x_frac_of_roofline": M * N / (gx_ms * 1e-3) / pk,
                            "grad_y_frac_of_roofline": M * N / (gy_ms * 1e-3) / pk}
-        knn_b = get_binder(KNN, [], 2, "float32")
-        knn_ms, _ = time_binder(knn_b, M, N, (x, y))
-        pk = ROOFLINE_PAIRS_PER_CLK_SM["knn_d3"] * SM_COUNT * sm_hz
-        line["knn"] = {"metric": "knn_k10_queries_per_s", "value": M / (knn_ms * 1e-3), "unit": "queries/s", "D": 3, "K": 10,
-                       "ms": knn_ms, "pair_evals_per_s": M * N / (knn_ms * 1e-3), "frac_of_roofline": M * N / (knn_ms * 1e-3) / pk}
         # ---- the reference's own CUDA kernel on the same GPU ---------------------------------------
         try:
             from oracle import ref_runner
@@ -397,7 +443,7 @@ def main():
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:
             line["cpu_baseline"] = {"unavailable": str(e)[:200]}
-    print(json.dumps(line))
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
