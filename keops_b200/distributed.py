@@ -108,3 +108,81 @@ class ShardedGenred:
                                group=self.group)
                 args.append(buf)
         return self.compute(*args, **call_kwargs)
+
+
+class ShardedKernelSolve:
+    """Row-sharded conjugate gradient for ``(alpha Id + K) a = b`` (single-process solver:
+    ``keops_b200.torch.KernelSolve``, reference ``pykeops/pykeops/torch/operations.py:29-87`` and
+    ``pykeops/pykeops/common/operations.py:90-114``).
+
+    ``K_ij = formula(x_i, y_j, ...)`` is square (M = N = ``n_total``).  Every rank owns one contiguous row
+    slab of the CG vectors (``b``, ``a``, ``r``, ``p``) and of the output-side variables.  The fixed streamed
+    variables are replicated ONCE per solve; each iteration then costs one ``all_gather`` of the search
+    direction ``p`` (4 MB at N = 10^6), one local map-reduce launch (this rank's rows against the full
+    ``p``) and two all-reduced scalars (``p.Kp`` and ``|r|^2``).  The recurrence and the stopping rule
+    are the reference's, so every rank takes the same number of iterations.
+
+    ``local_args`` follow the aliases: output-side variables and the right-hand side (at ``varinvalias``'s
+    position) = this rank's slab; other streamed variables = this rank's slab (``mode="all_gather"``) or
+    the full array (``mode="replicated"``); parameters = full.  Returns this rank's slab of ``a``.
+    ``compute(*full_args) -> local rows of K v`` is injectable (CPU ``gloo`` tests)."""
+
+    def __init__(self, formula: str, aliases: Sequence[str], varinvalias: str, axis: int = 0, group=None,
+                 compute: Optional[Callable] = None, **genred_kwargs):
+        self.group = group
+        probe = "Sum_Reduction(%s,%d)" % (formula, axis2cat(axis))
+        self.aliases = complete_aliases(probe, list(aliases))
+        self.cats, self.dims = [], []
+        for k, sig in enumerate(self.aliases):
+            _, cat, dim, pos = get_type(sig, position_in_list=k)
+            if pos != k:
+                raise ValueError("ShardedKernelSolve expects aliases in positional order")
+            self.cats.append(cat)
+            self.dims.append(dim)
+        if varinvalias[:4] == "Var(":
+            self.varinvpos = int(varinvalias[4:varinvalias.find(",")])
+        else:
+            self.varinvpos = [s[:s.find("=")].strip() for s in self.aliases].index(varinvalias)
+        self.out_cat = axis2cat(axis)
+        if self.cats[self.varinvpos] != 1 - self.out_cat:
+            raise ValueError("the unknown of KernelSolve must be indexed by the reduced index")
+        if compute is None:
+            from .torch import Genred
+            compute = Genred(formula, list(aliases), reduction_op="Sum", axis=axis, **genred_kwargs)
+        self.compute = compute
+        self.last_iterations = 0
+
+    def __call__(self, *local_args, n_total: int, alpha: float = 1e-10, eps: float = 1e-6, mode: str = "all_gather",
+                 max_iter: Optional[int] = None):
+        from .torch.kernel_solve import conjugate_gradient
+        if mode not in ("all_gather", "replicated"):
+            raise ValueError("mode must be 'all_gather' or 'replicated'")
+        on = dist.is_initialized()
+        world = dist.get_world_size(self.group) if on else 1
+        fixed: List[Optional[torch.Tensor]] = []
+        for k, (a, cat) in enumerate(zip(local_args, self.cats)):
+            if k == self.varinvpos:
+                fixed.append(None)
+            elif cat == self.out_cat or cat == 2 or world == 1 or mode == "replicated":
+                fixed.append(a)
+            else:
+                fixed.append(all_gather_rows(a, n_total, self.group))     # once per solve
+        b = local_args[self.varinvpos]
+
+        def linop(p_local):
+            p_full = all_gather_rows(p_local.contiguous(), n_total, self.group) if world > 1 else p_local
+            args = [p_full if k == self.varinvpos else a for k, a in enumerate(fixed)]
+            res = self.compute(*args)
+            if alpha:
+                res = res + alpha * p_local
+            return res
+
+        def dot(u, v):
+            s = (u * v).sum()
+            if world > 1:
+                dist.all_reduce(s, group=self.group)
+            return s
+
+        a = conjugate_gradient(linop, b, eps=eps, max_iter=max_iter, dot=dot, numel=int(n_total) * b[0].numel())
+        self.last_iterations = conjugate_gradient.last_iterations
+        return a

@@ -19,22 +19,30 @@ from ..common import axis2cat, complete_aliases, get_optional_flags, get_sizes, 
 from .genred import GenredAutograd, GenredParameters, _resolve_backend, _set_device
 
 
-def conjugate_gradient(linop, b, eps=1e-6, max_iter=None):
-    """Same recurrence and stopping rule as ``ConjugateGradientSolver`` (``common/operations.py:90-114``)."""
-    delta = b.numel() * eps ** 2
+def conjugate_gradient(linop, b, eps=1e-6, max_iter=None, dot=None, numel=None):
+    """Same recurrence and stopping rule as ``ConjugateGradientSolver`` (``common/operations.py:90-114``).
+
+    ``dot(u, v)`` (default: the local sum of products) and ``numel`` (default ``b.numel()``) are
+    injectable so that the row-sharded solver (``keops_b200.distributed.ShardedKernelSolve``) can run the
+    very same recurrence with all-reduced scalars."""
+    if dot is None:
+        def dot(u, v):
+            return (u * v).sum()
+    delta = (b.numel() if numel is None else numel) * eps ** 2
     a = torch.zeros_like(b)
     r = b.clone()
-    nr2 = (r * r).sum()
+    nr2 = dot(r, r)
+    conjugate_gradient.last_iterations = 0
     if nr2 < delta:
         return a
     p = r.clone()
     k = 0
     while True:
         Mp = linop(p)
-        alp = nr2 / (p * Mp).sum()
+        alp = nr2 / dot(p, Mp)
         a.add_(alp * p)
         r.sub_(alp * Mp)
-        nr2new = (r * r).sum()
+        nr2new = dot(r, r)
         k += 1
         if nr2new < delta or (max_iter is not None and k >= max_iter):
             break

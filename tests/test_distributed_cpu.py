@@ -91,3 +91,53 @@ def test_shard_bounds_cover_and_balance():
             assert all(b[r][1] == b[r + 1][0] for r in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# row-sharded conjugate gradient (KernelSolve over 2 ranks)
+# ---------------------------------------------------------------------------------------------
+KS_F, KS_A = "Exp(-g*SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(2)", "g=Pm(1)"]
+KS_RED = "Sum_Reduction(Exp(-g*SqDist(x,y))*b,0)"
+
+
+def _ks_worker(rank, world, port, n, q):
+    from keops_b200.distributed import ShardedKernelSolve
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(n, 3, generator=g, dtype=torch.float64)
+    rhs = torch.randn(n, 2, generator=g, dtype=torch.float64)
+    gam = torch.tensor([4.0], dtype=torch.float64)
+    i0, i1 = shard_bounds(n, world, rank)
+
+    def compute(*args):
+        from oracle import keops_oracle as ko
+        return torch.from_numpy(ko.genred(KS_RED, KS_A, [a.numpy() for a in args], "float64"))
+
+    ks = ShardedKernelSolve(KS_F, KS_A, "b", axis=1, compute=compute)
+    a = ks(x[i0:i1], x[i0:i1], rhs[i0:i1], gam, n_total=n, alpha=0.5, eps=1e-10)
+    q.put((rank, i0, i1, a.numpy(), ks.last_iterations))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_kernel_solve_matches_dense_solve():
+    world, port, n = 2, _free_port(), 61
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ks_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(n, 3, generator=g, dtype=torch.float64)
+    rhs = torch.randn(n, 2, generator=g, dtype=torch.float64)
+    K = torch.exp(-4.0 * ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)) + 0.5 * torch.eye(n, dtype=torch.float64)
+    sol = torch.linalg.solve(K, rhs).numpy()
+    iters = {r[4] for r in res}
+    assert len(iters) == 1 and 0 < iters.pop() <= 2 * n          # every rank stops at the same iteration
+    for rank, i0, i1, a, _ in res:
+        assert np.abs(a - sol[i0:i1]).max() < 1e-7 * np.abs(sol).max()
