@@ -28,7 +28,7 @@ from .formulas.parser import parse_reduction, parse_alias
 from .formulas.reductions import Reduction
 from .formulas.ir import FormulaError
 from .codegen.emit import generate, KernelSource
-from .codegen import knn_tc
+from .codegen import conv_tc, knn_tc
 from .runtime import plan, capi
 
 _binder_cache: Dict[tuple, "LoadKeOpsB200"] = {}
@@ -230,6 +230,9 @@ class LoadKeOpsB200:
         tc = knn_tc.eligible(self.red, p.dtype, nrow, ncol, nbatch)
         if tc is not None:
             return self._genred_knn_tc(dev, tc, nrow, ncol, out, args, strides, tdtype)
+        ct = conv_tc.eligible(self.red, p.dtype, nrow, ncol, nbatch, p.use_fast_math, p.sum_scheme, p.dtype_acc)
+        if ct is not None:
+            return self._genred_conv_tc(dev, ct, nrow, ncol, out, args)
         return self._launch_dense(dev, nrow, ncol, nbatch, out, args, strides, tdtype)
 
     def _genred_knn_tc(self, dev, tc, nrow, ncol, out, args, strides, tdtype):
@@ -251,6 +254,21 @@ class LoadKeOpsB200:
             out.view(nrow, p.dim)[over] = res
             self.last_launch["engine"] = "tcgen05"
             self.last_launch["overflow_rows"] = int(over.numel())
+        return out
+
+    def _genred_conv_tc(self, dev, ct, nrow, ncol, out, args):
+        """Gaussian-kernel Sum reduction with the squared distance on the tensor cores (``codegen/conv_tc.py``):
+        tcgen05 GEMM on three-term bf16 splits + ex2 / weighted accumulation epilogue, under the stated tolerance."""
+        p = self.params
+        row_ind, col_ind, D, b_ind, DB, terms = ct
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        eng = conv_tc.get(D, DB, index)
+        with torch.cuda.device(dev):
+            coef = conv_tc.coefficient(terms, args, dev)
+            eng.run(args[row_ind], args[col_ind], args[b_ind], coef, out.view(nrow, p.dim),
+                    torch.cuda.current_stream(dev))
+        self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0, blocks_per_sm=1,
+                                launches=3, engine="tcgen05-conv")
         return out
 
     def _launch_dense(self, dev, nrow, ncol, nbatch, out, args, strides, tdtype):

@@ -1,0 +1,278 @@
+"""Tensor-core path for Gaussian-kernel Sum reductions in medium / large dimension.
+
+``Sum_Reduction(Exp(c * |x_i - y_j|^2) * b_j, tagI)`` -- the Gaussian convolution / kernel matrix-vector product
+behind ``KernelSolve`` (``pykeops/pykeops/torch/operations.py:29-87``) -- costs the reference's generic
+``GpuReduc1D`` kernel 2 D + 2 FP32 instructions and one ``ex2`` per pair
+(``keopscore/keopscore/mapreduce/gpu/GpuReduc1D.py:70-90``).  For ``D >= 8`` the squared distance *is* a dense
+contraction, so here it runs as a tcgen05 GEMM on three-term bf16 splits of the fp32 coordinates (six
+products: fp32-grade accuracy, see ``keops_b200/csrc/kb200_conv_tc.cu`` for the bound) and the CUDA cores only
+do ``ex2`` + the weighted accumulation: the kernel moves from the FP32-pipe roofline to the MUFU one.
+
+This module recognises the pattern, JIT-compiles the two kernels for ``(D, dim b)`` and drives them:
+``prep`` (bf16 operand rows, squared norms, padded b) x 2 -> ``conv_tc`` (TMA + tcgen05 + TMEM + epilogue).
+The scalar coefficient ``c`` (constants and ``Pm`` parameters) is evaluated on the device with a few
+one-element torch ops, so there is no host synchronisation.
+
+Stated tolerance: relative error of each exponent ``<= ~2^-21 |c| log2(e) (|x - m|^2 + |y - m|^2)`` with ``m`` the
+mean of the streamed cloud; measured against the reference at the BASELINE KernelSolve shape (D = 16) the result
+agrees to ~1e-6 relative.  ``KB200_CONV_TC=0`` disables the path (CUDA-core kernel, reference operation order).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import threading
+from typing import Callable, Dict, Optional, Tuple
+
+from ..formulas.ir import Node
+from ..formulas.reductions import Reduction
+from ..runtime import capi, plan
+
+_CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
+_SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
+_COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
+VERSION = "conv-tc-1"
+BM, BN, STAGES, HS = 256, 128, 4, 8
+MAX_DB = 8
+_lock = threading.RLock()
+
+
+# ---------------------------------------------------------------------------------------------
+# pattern matching
+# ---------------------------------------------------------------------------------------------
+def _sqdist(node: Node) -> Optional[Tuple[Node, Node]]:
+    """``(a, b)`` if node is ``Sum(Square(Subtract(Var a, Var b)))`` (what SqDist / SqNorm2(x-y) lower to)."""
+    if node.op != "Sum" or len(node.args) != 1 or node.args[0].op != "Square":
+        return None
+    sub = node.args[0].args[0]
+    if sub.op != "Subtract" or len(sub.args) != 2 or any(a.op != "Var" for a in sub.args):
+        return None
+    return sub.args[0], sub.args[1]
+
+
+def _is_scalar_param_expr(node: Node) -> bool:
+    """dimension-1 expression of constants and parameters (category 2 variables) only"""
+    if node.dim != 1:
+        return False
+    if node.op == "Var":
+        return node.params[2] == 2
+    if node.op in ("IntCst", "RatCst", "FloatCst"):
+        return True
+    if node.op in ("Minus", "Mult", "Divide", "Inv", "Square", "Add", "Subtract"):
+        return all(_is_scalar_param_expr(a) for a in node.args)
+    return False
+
+
+def _scaled_sqdist(node: Node):
+    """``(coef_terms, (a, b))`` when node = (product of scalar parameter expressions, possibly negated / divided)
+    times a squared distance between two variables.  ``coef_terms`` is a list of ``(node, power)`` with power +-1
+    and a leading sign as ``("sign", s)``."""
+    sd = _sqdist(node)
+    if sd is not None:
+        return [], sd
+    if node.op == "Minus":
+        r = _scaled_sqdist(node.args[0])
+        return None if r is None else (r[0] + [(None, -1)], r[1])
+    if node.op == "Mult":
+        a, b = node.args
+        for s, o in ((a, b), (b, a)):
+            if _is_scalar_param_expr(s):
+                r = _scaled_sqdist(o)
+                if r is not None:
+                    return r[0] + [(s, 1)], r[1]
+        return None
+    if node.op == "Divide":
+        a, b = node.args
+        if _is_scalar_param_expr(b):
+            r = _scaled_sqdist(a)
+            if r is not None:
+                return r[0] + [(b, -1)], r[1]
+        return None
+    return None
+
+
+def match(red: Reduction):
+    """``(row_var, col_var, D, b_var, DB, coef_terms)`` for ``Sum_Reduction(Exp(c |x - y|^2) * b, tagI)`` with x the
+    output-side variable, y and b streamed variables; ``None`` otherwise."""
+    if red.kind != "Sum":
+        return None
+    f = red.formula
+    if f.op != "Mult" or len(f.args) != 2:
+        return None
+    for e, b in ((f.args[0], f.args[1]), (f.args[1], f.args[0])):
+        if e.op != "Exp" or b.op != "Var":
+            continue
+        r = _scaled_sqdist(e.args[0])
+        if r is None:
+            continue
+        terms, (va, vb) = r
+        (ia, da, ca), (ib, db, cb) = va.params, vb.params
+        if da != db or {ca, cb} != {0, 1}:
+            continue
+        row, col = (ia, ib) if ca == red.tagI else (ib, ia)
+        bi, bdim, bcat = b.params
+        if bcat != 1 - red.tagI or bdim > MAX_DB or e.dim != 1:
+            continue
+        return row, col, da, bi, bdim, terms
+    return None
+
+
+def _eval_scalar(node: Node, args):
+    """one-element fp32 tensor (or python float) value of a scalar parameter expression -- device ops only"""
+    if node.op == "Var":
+        return args[node.params[0]].reshape(-1)[:1]
+    if node.op == "IntCst":
+        return float(node.params[0])
+    if node.op == "RatCst":
+        return float(node.params[0]) / float(node.params[1])
+    if node.op == "FloatCst":
+        return float(node.params[0])
+    v = [_eval_scalar(a, args) for a in node.args]
+    if node.op == "Minus":
+        return -v[0]
+    if node.op == "Mult":
+        return v[0] * v[1]
+    if node.op == "Divide":
+        return v[0] / v[1]
+    if node.op == "Inv":
+        return 1.0 / v[0]
+    if node.op == "Square":
+        return v[0] * v[0]
+    if node.op == "Add":
+        return v[0] + v[1]
+    if node.op == "Subtract":
+        return v[0] - v[1]
+    raise ValueError(node.op)
+
+
+def coefficient(terms, args, device):
+    """the scalar c of ``exp(c |x - y|^2)`` as a one-element fp32 CUDA tensor"""
+    import torch
+    c = 1.0
+    for node, power in terms:
+        if node is None:
+            c = -c
+        elif power == 1:
+            c = c * _eval_scalar(node, args)
+        else:
+            c = c / _eval_scalar(node, args)
+    if not isinstance(c, torch.Tensor):
+        c = torch.full((1,), float(c), dtype=torch.float32, device=device)
+    return c.to(torch.float32).contiguous()
+
+
+def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, use_fast_math: bool,
+             sum_scheme: str = "block_sum", dtype_acc: str = "float32"):
+    """The tensor-core path pays off once 2 D + 2 FP32 instructions per pair exceed the MUFU bound (D >= 8) and the
+    grid fills the machine with 256-row CTAs; it reproduces the default (block_sum, fp32 accumulation) scheme."""
+    if os.environ.get("KB200_CONV_TC", "1") == "0" or dtype != "float32" or nbatch != 1 or not use_fast_math:
+        return None
+    if sum_scheme not in ("block_sum", "auto") or dtype_acc not in ("float32", "auto"):
+        return None
+    m = match(red)
+    if m is None:
+        return None
+    D = m[2]
+    dmin = int(os.environ.get("KB200_CONV_TC_DMIN", 8))
+    if D < dmin or 6 * D + 3 > 128 or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
+        return None                      # 6 D + 3 <= 128: resident x tiles + 4 stages of y tiles in 227 KB of smem
+    return m
+
+
+class ConvTensorCore:
+    """Compiled kernels for one (D, dim b) combination on one device."""
+
+    def __init__(self, D: int, DB: int, device: int):
+        self.D, self.DB = D, DB
+        total = 6 * D + 3
+        full, r = divmod(total, 64)
+        if r == 0:
+            self.KBM, self.REM = full - 1, 64
+        else:
+            self.KBM, self.REM = full, (16 if r <= 16 else (32 if r <= 32 else 64))
+        self.DPG = 64 * self.KBM + self.REM
+        with open(_COMMON_PATH) as f:
+            body = f.read()
+        with open(_SRC_PATH) as f:
+            body += f.read()
+        self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
+        defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
+                "#define CT_HS %d\n#define CT_DBG %d\n" % (D, DB, self.KBM, self.REM, self.STAGES, HS,
+                                                        int(os.environ.get("CT_DBG", 0))))
+        src = defs + body
+        opts = plan.nvrtc_options(True)
+        key = hashlib.sha256((VERSION + src + " ".join(opts)).encode()).hexdigest()[:20]
+        path = os.path.join(plan.cache_dir(), "kb200_convtc_%s.cubin" % key)
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                cubin = f.read()
+        else:
+            cubin = capi.compile_to_cubin(src, opts, name="kb200_convtc_%s.cu" % key)
+            tmp = path + ".tmp%d" % os.getpid()
+            with open(tmp, "wb") as f:
+                f.write(cubin)
+            os.replace(tmp, path)
+        self.cubin = cubin
+        blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K
+        self.smem = 1024 + 2 * blk(128) + self.STAGES * blk(BN) + HS * BN * DB * 4 + 640
+        if self.smem > 227 * 1024:
+            raise ValueError("conv_tc: D = %d, dim b = %d needs %d bytes of shared memory" % (D, DB, self.smem))
+        self.smem = max(self.smem, 120 * 1024)     # one CTA per SM: each CTA allocates all 512 TMEM columns
+        self.module = None
+        if device >= 0:
+            self.module = capi.Module(cubin, device)
+            self.fn_prep = self.module.function("kb200_conv_prep")
+            self.fn_conv = self.module.function("kb200_conv_tc")
+            capi.set_max_dynamic_smem(self.fn_conv, self.smem)
+
+    def _maps(self, abf, n, box_rows):
+        pitch = self.DPG * 2
+        rem = capi.tensor_map_2d(abf.data_ptr() + 128 * self.KBM, 2, self.REM, n, pitch, self.REM, box_rows, self.REM * 2)
+        if self.KBM == 0:
+            return rem, rem            # the main map is never dereferenced
+        return capi.tensor_map_2d(abf.data_ptr(), 2, 64 * self.KBM, n, pitch, 64, box_rows, 128), rem
+
+    def run(self, x, y, b, coef, out, stream_obj):
+        """x (M, D), y (N, D), b (N, DB) fp32 contiguous CUDA tensors, coef a one-element fp32 tensor;
+        out (M, DB) fp32.  Everything is enqueued on ``stream_obj``; no host synchronisation."""
+        import torch
+        M, N = x.shape[0], y.shape[0]
+        dev = x.device
+        stream = stream_obj.cuda_stream
+        i64, ptr, i32 = C.c_longlong, C.c_void_p, C.c_int
+        ntiles = -(-N // BN)
+        npad = ntiles * BN
+        shift = y.mean(dim=0, dtype=torch.float32).contiguous()            # common shift: x - y is unchanged
+        ybf = torch.empty((N, self.DPG), dtype=torch.int16, device=dev)
+        xbf = torch.empty((M, self.DPG), dtype=torch.int16, device=dev)
+        ysq = torch.empty(N, dtype=torch.float32, device=dev)
+        xsq = torch.empty(M, dtype=torch.float32, device=dev)
+        bpad = torch.empty(npad * self.DB, dtype=torch.float32, device=dev)
+        capi.launch(self.fn_prep, stream, (-(-npad // 256),), (256,), 0,
+                    [i64(N), i64(npad), ptr(y.data_ptr()), ptr(shift.data_ptr()), ptr(ybf.data_ptr()), ptr(ysq.data_ptr()),
+                     ptr(b.data_ptr()), ptr(bpad.data_ptr()), i32(0)])
+        capi.launch(self.fn_prep, stream, (-(-M // 256),), (256,), 0,
+                    [i64(M), i64(M), ptr(x.data_ptr()), ptr(shift.data_ptr()), ptr(xbf.data_ptr()), ptr(xsq.data_ptr()),
+                     ptr(0), ptr(0), i32(1)])
+        map_y, map_yr = self._maps(ybf, N, BN)
+        map_x, map_xr = self._maps(xbf, M, 128)
+        capi.launch(self.fn_conv, stream, (-(-M // BM),), (320,), self.smem,
+                    [map_x, map_xr, map_y, map_yr, i64(M), i64(N), ptr(bpad.data_ptr()), ptr(xsq.data_ptr()),
+                     ptr(coef.data_ptr()), ptr(out.data_ptr())])
+        for t in (shift, ybf, xbf, ysq, xsq, bpad, coef):
+            t.record_stream(stream_obj)
+        self.last = dict(ntiles=ntiles, ctas=-(-M // BM))
+
+
+_cache: Dict[tuple, ConvTensorCore] = {}
+
+
+def get(D: int, DB: int, device: int) -> ConvTensorCore:
+    key = (D, DB, device)
+    with _lock:
+        k = _cache.get(key)
+        if k is None:
+            k = ConvTensorCore(D, DB, device)
+            _cache[key] = k
+        return k

@@ -22,8 +22,10 @@ from typing import Dict, Optional, Tuple
 from ..formulas.reductions import Reduction
 from ..runtime import capi, plan
 
-_SRC_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "kb200_knn_tc.cu")
-VERSION = "knn-tc-4"
+_CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
+_SRC_PATH = os.path.join(_CSRC, "kb200_knn_tc.cu")
+_COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")      # PTX wrappers, prepended (NVRTC has no include path)
+VERSION = "knn-tc-5"
 BM, BN, STAGES, HS = 256, 128, 4, 16
 ROW_BATCH = 1 << 20          # rows per filter launch: bounds the candidate workspace (CAP * 4 bytes per row)
 _lock = threading.RLock()
@@ -75,8 +77,10 @@ class KnnTensorCore:
         self.DPG = 64 * self.KBM + self.REM
         self.outw = 2 * K if kind == "KMin_ArgKMin" else K
         out_code = {"ArgKMin": 0, "KMin": 1, "KMin_ArgKMin": 2}[kind]
-        with open(_SRC_PATH) as f:
+        with open(_COMMON_PATH) as f:
             body = f.read()
+        with open(_SRC_PATH) as f:
+            body += f.read()
         defs = ("#define KT_D %d\n#define KT_KBM %d\n#define KT_REM %d\n#define KT_K %d\n#define KT_CAP %d\n"
                 "#define KT_OUT %d\n#define KT_FAST %d\n" % (D, self.KBM, self.REM, K, cap, out_code, 1 if fast else 0))
         self.BN = int(os.environ.get("KT_BN", BN))

@@ -1,0 +1,308 @@
+// kb200_conv_tc.cu -- Gaussian-kernel Sum reductions  out_i = sum_j exp(c |x_i - y_j|^2) b_j  in medium / large
+// dimension on the 5th-generation tensor cores of sm_100a (tcgen05.mma, TMEM accumulators, TMA operand tiles).
+//
+// Reference semantics: Sum_Reduction (keopscore/keopscore/formulas/reductions/Sum_Reduction.py:10-50) of
+// Exp(c * Sum(Square(x - y))) * b evaluated pair by pair on CUDA cores by GpuReduc1D
+// (keopscore/keopscore/mapreduce/gpu/GpuReduc1D.py:70-90): 2 D + 2 FP32 instructions + 1 MUFU.EX2 per pair
+// (34 + 1 at D = 16, the KernelSolve configuration).  Here the squared distance is a dense contraction
+//
+//     |x - y|^2 = |x|^2 + |y|^2 - 2 x.y ,      acc_ij = x_i . y_j - |y_j|^2 / 2      (one tcgen05 GEMM)
+//
+// so a pair costs 1 FFMA (exponent) + 1 MUFU.EX2 + DB FFMA (accumulation) on the CUDA cores: the kernel is bound by
+// the MUFU pipe (16 ex2 / clk / SM) instead of the FP32 pipe.
+//
+// Precision (the "stated tolerance" of the tensor-core path): every fp32 coordinate is split
+// into three bf16 terms v = v1 + v2 + v3 (8 + 8 + 8 significant bits: exact), and the GEMM accumulates the six
+// products  x1 y1, x1 y2, x2 y1, x1 y3, x2 y2, x3 y1  in fp32 -- everything down to 2^-24 |x_k y_k|; the dropped
+// products (x2 y3, x3 y2, x3 y3) are <= 2^-23 |x_k y_k|.  -|y|^2/2 enters the same accumulation through three
+// more K columns (a three-term bf16 split against 1, 1, 1 on the x side).  Both clouds are shifted by a common
+// vector (the caller passes the mean of the streamed cloud), which leaves x - y unchanged and keeps |x|^2 + |y|^2
+// -- hence the cancellation error  ~2^-22 (|x|^2 + |y|^2) |c| log2(e)  of the exponent -- small.
+//
+// kb200_conv_prep : fp32 rows -> the 6 D + 3 bf16 operand columns (zero padded to CT_DPG) + |x - shift|^2;
+//                   on the streamed side also a zero-padded copy of b (whole 128-column tiles).
+// kb200_conv_tc   : one CTA = 256 output rows (two 128-row accumulators) x all streamed columns in 128-column
+//                   tiles.  Warp 0 = TMA producer (operand tiles + the b tile), warp 1 = MMA issuer, warps 2..9 =
+//                   epilogue, one thread per output row: tcgen05.ld of its 128 accumulators, ex2, FFMA with b_j
+//                   (broadcast LDS.128), per-tile partial sums added to the running sum (the reference's
+//                   block_sum scheme, sum_schemes.py:55-71).  4-stage smem ring, double-buffered TMEM.
+//
+// Compile-time parameters (keops_b200/codegen/conv_tc.py): CT_D, CT_DB (dimension of b), CT_KBM / CT_REM (operand
+// rows = CT_KBM 128-byte-swizzled 64-column blocks + one remainder block of CT_REM columns), CT_STAGES, CT_HS.
+// The PTX wrappers (kt_*) come from kb200_tc_common.cuh, prepended by the host code.
+
+#ifndef CT_D
+#define CT_D 16
+#define CT_DB 1
+#define CT_KBM 1
+#define CT_REM 64
+#endif
+#ifndef CT_STAGES
+#define CT_STAGES 4
+#endif
+#ifndef CT_HS
+#define CT_HS 8                               /* slots of the b-tile ring                                        */
+#endif
+#ifndef CT_DBG
+#define CT_DBG 0                              /* timing experiments: 1 no ex2, 2 no TMEM loads                   */
+#endif
+#define CT_BM 256                             /* rows per CTA: two 128-row accumulators                          */
+#define CT_BN 128                             /* columns per tile (= N of one tcgen05.mma)                       */
+#define CT_NBUF 2                             /* TMEM accumulator buffers per row block: 2 x 2 x 128 = 512 cols  */
+#define CT_NCOL (6 * CT_D + 3)                /* used K columns                                                  */
+#define CT_DPG (64 * CT_KBM + CT_REM)
+#define CT_TILE_BYTES(rows) ((rows) * 128)
+#define CT_RTILE_BYTES(rows) ((rows) * CT_REM * 2)
+#define CT_BLK_BYTES(rows) (CT_KBM * CT_TILE_BYTES(rows) + CT_RTILE_BYTES(rows))
+#define CT_A_BYTES (2 * CT_BLK_BYTES(128))
+#define CT_B_BYTES CT_BLK_BYTES(CT_BN)
+#define CT_H_BYTES (CT_BN * CT_DB * 4)        /* one b tile                                                      */
+#define CT_SMEM_BYTES (1024 + CT_A_BYTES + CT_STAGES * CT_B_BYTES + CT_HS * CT_H_BYTES + 640) /* mirrored in conv_tc.py */
+#define CT_LOG2E 1.4426950408889634f
+// bf16 x bf16 -> f32, A and B K-major, M = 128, N = CT_BN
+#define CT_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | (((u32)CT_BN >> 3) << 17) | ((128u >> 4) << 24))
+
+// ------------------------------------------------------------------------------------------------
+// prep
+//   side 0 (streamed, y): [ y1 | y2 | y1 | y3 | y2 | y1 | -h1 -h2 -h3 | 0 .. ],  h = |y - shift|^2 / 2
+//                         + bpad (npad x CT_DB): b for rows < n, 0 for the padding of the last tile
+//   side 1 (output,   x): [ x1 | x1 | x2 | x1 | x2 | x3 |  1   1   1  | 0 .. ],  sq[r] = |x - shift|^2
+//   (v1, v2, v3 = successive bf16 round-to-nearest remainders of the shifted coordinate)
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256)
+kb200_conv_prep(const long long n, const long long npad, const float* __restrict__ a, const float* __restrict__ shift,
+                unsigned short* __restrict__ abf, float* __restrict__ sq, const float* __restrict__ b,
+                float* __restrict__ bpad, const int side) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (side == 0 && r < npad) {
+#pragma unroll
+    for (int d = 0; d < CT_DB; d++) bpad[r * CT_DB + d] = (r < n) ? b[r * CT_DB + d] : 0.0f;
+  }
+  if (r >= n) return;
+  const float* row = a + r * CT_D;
+  unsigned short* orow = abf + r * CT_DPG;
+  float s = 0.0f;
+#pragma unroll 4
+  for (int k = 0; k < CT_D; k++) {
+    const float v = row[k] - (shift ? shift[k] : 0.0f);
+    s = fmaf(v, v, s);
+    const unsigned short p1 = kt_bf16_rn(v);
+    const float r1 = v - kt_bf16_to_f(p1);
+    const unsigned short p2 = kt_bf16_rn(r1);
+    const unsigned short p3 = kt_bf16_rn(r1 - kt_bf16_to_f(p2));
+    if (side == 0) {
+      orow[k] = p1; orow[CT_D + k] = p2; orow[2 * CT_D + k] = p1;
+      orow[3 * CT_D + k] = p3; orow[4 * CT_D + k] = p2; orow[5 * CT_D + k] = p1;
+    } else {
+      orow[k] = p1; orow[CT_D + k] = p1; orow[2 * CT_D + k] = p2;
+      orow[3 * CT_D + k] = p1; orow[4 * CT_D + k] = p2; orow[5 * CT_D + k] = p3;
+    }
+  }
+  if (side == 0) {
+    const float h = 0.5f * s;
+    const unsigned short hi = kt_bf16_rn(h);
+    const float r1 = h - kt_bf16_to_f(hi);
+    const unsigned short mid = kt_bf16_rn(r1);
+    const unsigned short lo = kt_bf16_rn(r1 - kt_bf16_to_f(mid));
+    orow[6 * CT_D] = hi ^ 0x8000u; orow[6 * CT_D + 1] = mid ^ 0x8000u; orow[6 * CT_D + 2] = lo ^ 0x8000u;   // negated
+  } else {
+    orow[6 * CT_D] = 0x3F80u; orow[6 * CT_D + 1] = 0x3F80u; orow[6 * CT_D + 2] = 0x3F80u;                   // 1.0
+  }
+  sq[r] = s;
+  for (int k = CT_NCOL; k < CT_DPG; k++) orow[k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue of one tile for one output row: tmp_d = sum_e exp2(fma(u_e, c2, rowc)) * b[e][d]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ct_ex2(float s) {
+  float p;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(s));
+  return p;
+}
+
+template <bool TAIL>
+__device__ __forceinline__ void ct_tile(const float (&u)[CT_BN], const float* __restrict__ bt, const float c2,
+                                        const float rowc, const long long j0, const long long ncol,
+                                        float (&acc)[CT_DB]) {
+  float tmp[2][CT_DB];                                // two interleaved partial sums per component
+#pragma unroll
+  for (int d = 0; d < CT_DB; d++) tmp[0][d] = tmp[1][d] = 0.0f;
+#pragma unroll
+  for (int e4 = 0; e4 < CT_BN / 4; e4++) {
+    float p[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+#if CT_DBG == 1
+      p[e] = fmaf(u[4 * e4 + e], c2, rowc);
+#else
+      p[e] = ct_ex2(fmaf(u[4 * e4 + e], c2, rowc));
+#endif
+      if (TAIL && j0 + 4 * e4 + e >= ncol) p[e] = 0.0f;
+    }
+    // the four b rows of these columns: 4 * CT_DB consecutive floats, read with broadcast LDS.128
+    float bv[4 * CT_DB];
+    const float4* b4 = reinterpret_cast<const float4*>(bt + 4 * e4 * CT_DB);
+#pragma unroll
+    for (int v = 0; v < CT_DB; v++) {
+      const float4 q = b4[v];
+      bv[4 * v + 0] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int d = 0; d < CT_DB; d++) tmp[e & 1][d] = fmaf(p[e], bv[e * CT_DB + d], tmp[e & 1][d]);
+  }
+#pragma unroll
+  for (int d = 0; d < CT_DB; d++) acc[d] += tmp[0][d] + tmp[1][d];
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(320, 1)
+kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_xr,
+              const __grid_constant__ KtTensorMap map_y, const __grid_constant__ KtTensorMap map_yr,
+              const long long nrow, const long long ncol, const float* __restrict__ bpad,
+              const float* __restrict__ xsq, const float* __restrict__ coef, float* __restrict__ out) {
+  extern __shared__ unsigned char ct_raw[];
+  const u32 raw = kt_smem(ct_raw);
+  const u32 base = (raw + 1023u) & ~1023u;                       // swizzle atoms need (up to) 1024-byte alignment
+  unsigned char* gbase = ct_raw + (base - raw);
+  const u32 sA = base;                                           // 2 row blocks x [KBM main tiles | remainder tile]
+  const u32 sB = sA + CT_A_BYTES;                                // STAGES x [KBM main tiles | remainder tile]
+  const u32 sH = sB + CT_STAGES * CT_B_BYTES;                    // ring of b tiles (CT_HS x CT_BN x CT_DB floats)
+  const float* hb = reinterpret_cast<const float*>(gbase + CT_A_BYTES + CT_STAGES * CT_B_BYTES);
+  const u32 sBar = sH + CT_HS * CT_H_BYTES;
+  // barriers (8 bytes each): full[8] @0, empty[8] @64, tfull[buf][rb] @128, tempty[buf][rb] @192,
+  //                          hfull[16] @256, hempty[16] @384, afull @512, tmem pointer @520
+  const u32 bFull = sBar, bEmpty = sBar + 64, bTFull = sBar + 128, bTEmpty = sBar + 192, bAFull = sBar + 512;
+  const u32 bHFull = sBar + 256, bHEmpty = sBar + 384;
+  volatile u32* tmem_slot =
+      reinterpret_cast<volatile u32*>(gbase + CT_A_BYTES + CT_STAGES * CT_B_BYTES + CT_HS * CT_H_BYTES + 520);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row_base = (long long)blockIdx.x * CT_BM;
+  const int ntiles = (int)((ncol + CT_BN - 1) / CT_BN);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
+    for (int b = 0; b < 2 * CT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, 4); }
+    for (int h = 0; h < CT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, 8); }
+    kt_mbar_init(bAFull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sBar + 520), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  kt_fence_before();
+  __syncthreads();
+  kt_fence_after();
+  const u32 tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    if (kt_elect()) {
+      kt_mbar_expect_tx(bAFull, CT_A_BYTES);
+      for (int rb = 0; rb < 2; rb++) {
+        for (int kb = 0; kb < CT_KBM; kb++)
+          kt_tma_2d(sA + rb * CT_BLK_BYTES(128) + kb * CT_TILE_BYTES(128), &map_x, kb * 64, (int)(row_base + rb * 128), bAFull);
+        kt_tma_2d(sA + rb * CT_BLK_BYTES(128) + CT_KBM * CT_TILE_BYTES(128), &map_xr, 0, (int)(row_base + rb * 128), bAFull);
+      }
+    }
+    __syncwarp();
+    for (int t = 0; t < ntiles; t++) {
+      const int s = t % CT_STAGES, h = t % CT_HS;
+      kt_mbar_wait(bEmpty + 8 * s, ((t / CT_STAGES) & 1) ^ 1);
+      kt_mbar_wait(bHEmpty + 8 * h, ((t / CT_HS) & 1) ^ 1);
+      if (kt_elect()) {
+        kt_mbar_expect_tx(bFull + 8 * s, CT_B_BYTES);
+        for (int kb = 0; kb < CT_KBM; kb++)
+          kt_tma_2d(sB + s * CT_B_BYTES + kb * CT_TILE_BYTES(CT_BN), &map_y, kb * 64, t * CT_BN, bFull + 8 * s);
+        kt_tma_2d(sB + s * CT_B_BYTES + CT_KBM * CT_TILE_BYTES(CT_BN), &map_yr, 0, t * CT_BN, bFull + 8 * s);
+        kt_mbar_expect_tx(bHFull + 8 * h, CT_H_BYTES);
+        kt_bulk_1d(sH + h * CT_H_BYTES, bpad + (long long)t * CT_BN * CT_DB, CT_H_BYTES, bHFull + 8 * h);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+    kt_mbar_wait(bAFull, 0);
+    for (int t = 0; t < ntiles; t++) {
+      const int s = t % CT_STAGES, buf = t % CT_NBUF;
+      kt_mbar_wait(bFull + 8 * s, (t / CT_STAGES) & 1);
+#pragma unroll
+      for (int rb = 0; rb < 2; rb++) {
+        kt_mbar_wait(bTEmpty + 8 * (buf * 2 + rb), ((t / CT_NBUF) & 1) ^ 1);
+        kt_fence_after();
+        if (kt_elect()) {
+          const u32 d = tmem + (u32)((buf * 2 + rb) * CT_BN);
+#pragma unroll
+          for (int kb = 0; kb < CT_KBM; kb++) {
+            const u64 ad = kt_smem_desc(sA + rb * CT_BLK_BYTES(128) + kb * CT_TILE_BYTES(128), 128);
+            const u64 bd = kt_smem_desc(sB + s * CT_B_BYTES + kb * CT_TILE_BYTES(CT_BN), 128);
+#pragma unroll
+            for (int k = 0; k < 4; k++)              // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
+              kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), CT_IDESC, (u32)((kb | k) != 0));
+          }
+          {
+            const u64 ad = kt_smem_desc(sA + rb * CT_BLK_BYTES(128) + CT_KBM * CT_TILE_BYTES(128), CT_REM * 2);
+            const u64 bd = kt_smem_desc(sB + s * CT_B_BYTES + CT_KBM * CT_TILE_BYTES(CT_BN), CT_REM * 2);
+#pragma unroll
+            for (int k = 0; k < CT_REM / 16; k++)
+              kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), CT_IDESC, (u32)((CT_KBM | k) != 0));
+          }
+          kt_mma_commit(bTFull + 8 * (buf * 2 + rb));  // this accumulator is complete
+          if (rb == 1) kt_mma_commit(bEmpty + 8 * s);  // smem stage may be refilled once these MMAs have read it
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: one thread per output row =====================
+    const int q = warp & 3, rb = (warp - 2) >> 2;
+    const long long i = row_base + rb * 128 + q * 32 + lane;
+    const bool live = i < nrow;
+    const float cl = coef[0] * CT_LOG2E;              // exponent = cl * |x - y|^2  (base 2)
+    const float c2 = -2.0f * cl;
+    const float rowc = live ? cl * xsq[i] : 0.0f;
+    float acc[CT_DB];
+#pragma unroll
+    for (int d = 0; d < CT_DB; d++) acc[d] = 0.0f;
+    for (int t = 0; t < ntiles; t++) {
+      const int buf = t % CT_NBUF, hslot = t % CT_HS;
+      kt_mbar_wait(bTFull + 8 * (buf * 2 + rb), (t / CT_NBUF) & 1);
+      kt_fence_after();
+      const u32 tbase = tmem + ((u32)(q * 32) << 16) + (u32)((buf * 2 + rb) * CT_BN);
+      float uu[CT_BN];
+#if CT_DBG == 2
+#pragma unroll
+      for (int e = 0; e < CT_BN; e++) uu[e] = -1.0f;
+#else
+#pragma unroll
+      for (int c = 0; c < CT_BN / 64; c++) kt_tmem_ld64_nowait(tbase + (u32)(c * 64), uu + c * 64);
+      kt_tmem_wait_ld();
+#endif
+      kt_fence_before();
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));   // accumulator back to the MMA warp
+      kt_mbar_wait(bHFull + 8 * hslot, (t / CT_HS) & 1);
+      const float* bt = hb + hslot * (CT_BN * CT_DB);
+      if (t == ntiles - 1) ct_tile<true>(uu, bt, c2, rowc, (long long)t * CT_BN, ncol, acc);
+      else ct_tile<false>(uu, bt, c2, rowc, (long long)t * CT_BN, ncol, acc);
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
+    }
+    if (live) {
+#pragma unroll
+      for (int d = 0; d < CT_DB; d++) out[i * CT_DB + d] = acc[d];
+    }
+  }
+  kt_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
