@@ -232,7 +232,8 @@ class LoadKeOpsB200:
             return self._genred_knn_tc(dev, tc, nrow, ncol, out, args, strides, tdtype)
         ct = conv_tc.eligible(self.red, p.dtype, nrow, ncol, nbatch, p.use_fast_math, p.sum_scheme, p.dtype_acc)
         if ct is not None:
-            return self._genred_conv_tc(dev, ct, nrow, ncol, out, args)
+            if self._genred_conv_tc(dev, ct, nrow, ncol, out, args):
+                return out
         return self._launch_dense(dev, nrow, ncol, nbatch, out, args, strides, tdtype)
 
     def _genred_knn_tc(self, dev, tc, nrow, ncol, out, args, strides, tdtype):
@@ -265,11 +266,14 @@ class LoadKeOpsB200:
         eng = conv_tc.get(D, DB, index)
         with torch.cuda.device(dev):
             coef = conv_tc.coefficient(terms, args, dev)
-            eng.run(args[row_ind], args[col_ind], args[b_ind], coef, out.view(nrow, p.dim),
-                    torch.cuda.current_stream(dev))
+            ok = eng.run(args[row_ind], args[col_ind], args[b_ind], coef, out.view(nrow, p.dim),
+                         torch.cuda.current_stream(dev))
+        if not ok:
+            return False            # accuracy guard: the caller runs the CUDA-core kernel
         self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0, blocks_per_sm=1,
-                                launches=3, engine="tcgen05-conv")
-        return out
+                                launches=3 + (eng.last["nchunks"] > 1), engine="tcgen05-conv",
+                                error_bound=eng.last_bound, nchunks=eng.last["nchunks"])
+        return True
 
     def _launch_dense(self, dev, nrow, ncol, nbatch, out, args, strides, tdtype):
         p = self.params

@@ -11,11 +11,14 @@ do ``ex2`` + the weighted accumulation: the kernel moves from the FP32-pipe roof
 This module recognises the pattern, JIT-compiles the two kernels for ``(D, dim b)`` and drives them:
 ``prep`` (bf16 operand rows, squared norms, padded b) x 2 -> ``conv_tc`` (TMA + tcgen05 + TMEM + epilogue).
 The scalar coefficient ``c`` (constants and ``Pm`` parameters) is evaluated on the device with a few
-one-element torch ops, so there is no host synchronisation.
+one-element torch ops.
 
-Stated tolerance: relative error of each exponent ``<= ~2^-21 |c| log2(e) (|x - m|^2 + |y - m|^2)`` with ``m`` the
-mean of the streamed cloud; measured against the reference at the BASELINE KernelSolve shape (D = 16) the result
-agrees to ~1e-6 relative.  ``KB200_CONV_TC=0`` disables the path (CUDA-core kernel, reference operation order).
+Stated tolerance: the relative error of one term ``exp(c |x_i - y_j|^2)`` is about
+``2^-22 |c| (max_i |x_i - m|^2 + max_j |y_j - m|^2)`` with ``m`` the mean of the streamed cloud (cancellation in
+``|x|^2 + |y|^2 - 2 x.y``).  ``run`` evaluates that bound on the device and refuses the launch when it exceeds
+``TOL`` (5e-6, half of the fp32 parity bar of 1e-5); the binder then runs the CUDA-core kernel, which forms
+``x - y`` directly.  Measured at the BASELINE KernelSolve shape (D = 16, M = N = 1e6) the result agrees with the
+CUDA-core kernel to 4e-6 of the largest output.  ``KB200_CONV_TC=0`` disables the path.
 """
 from __future__ import annotations
 
@@ -32,9 +35,13 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-1"
+VERSION = "conv-tc-4"
 BM, BN, STAGES, HS = 256, 128, 4, 8
+THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
+CHUNK_MB = 48              # bf16 operand rows of one column chunk (must stay L2-resident)
+# stated tolerance of the path: bound on the relative error of one term exp(c |x_i - y_j|^2) (0 disables the guard)
+TOL = 5e-6                 # default; the environment variable KB200_CONV_TC_TOL overrides it per call
 _lock = threading.RLock()
 
 
@@ -175,9 +182,43 @@ def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, use_
         return None
     D = m[2]
     dmin = int(os.environ.get("KB200_CONV_TC_DMIN", 8))
-    if D < dmin or 6 * D + 3 > 128 or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
-        return None                      # 6 D + 3 <= 128: resident x tiles + 4 stages of y tiles in 227 KB of smem
+    kbm, rem, _ = layout(D)
+    if D < dmin or 64 * kbm + rem > 128 or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
+        return None                      # K <= 128: resident x tiles + 4 stages of y tiles in 227 KB of smem
+    if smem_bytes(D, m[4]) > 227 * 1024:
+        return None
     return m
+
+
+def _blocks(total: int) -> Tuple[int, int]:
+    """operand rows of ``total`` bf16 columns as KBM 64-column blocks (128-byte swizzle) + one remainder block of
+    16 / 32 / 64 columns (swizzled at its own width)"""
+    full, r = divmod(total, 64)
+    if r == 0:
+        return full - 1, 64
+    return full, (16 if r <= 16 else (32 if r <= 32 else 64))
+
+
+def layout(D: int) -> Tuple[int, int, int]:
+    """``(KBM, REM, PEN)``: the six product blocks (6 D columns) plus the three -|y|^2/2 columns (PEN = 1) whenever
+    they fit K <= 128; otherwise (PEN = 0, D = 21) |y|^2 is added in the epilogue.  Measured on B200 at D = 16,
+    M = N = 1e6: K = 128 with the penalty columns 277 ms, K = 96 with the epilogue FFMA + wider b tile 294 ms -- the
+    epilogue's issue slots and LDS bandwidth are scarcer than tensor-core time."""
+    with_pen, without = _blocks(6 * D + 3), _blocks(6 * D)
+    width = lambda kb: 64 * kb[0] + kb[1]
+    if os.environ.get("KB200_CONV_TC_PEN") in ("0", "1"):
+        pen = int(os.environ["KB200_CONV_TC_PEN"])
+        return (with_pen if pen else without) + (pen,)
+    if width(with_pen) > 128 and width(without) <= 128:
+        return without + (0,)
+    return with_pen + (1,)
+
+
+def smem_bytes(D: int, DB: int, stages: int = STAGES) -> int:
+    """dynamic shared memory of kb200_conv_tc (CT_SMEM_BYTES in the kernel)"""
+    kbm, rem, pen = layout(D)
+    blk = lambda rows: kbm * rows * 128 + rows * rem * 2       # one operand block, all of K
+    return 1024 + 2 * blk(128) + stages * blk(BN) + HS * BN * (DB + 1 - pen) * 4 + BM * DB * 4 + 640
 
 
 class ConvTensorCore:
@@ -185,21 +226,17 @@ class ConvTensorCore:
 
     def __init__(self, D: int, DB: int, device: int):
         self.D, self.DB = D, DB
-        total = 6 * D + 3
-        full, r = divmod(total, 64)
-        if r == 0:
-            self.KBM, self.REM = full - 1, 64
-        else:
-            self.KBM, self.REM = full, (16 if r <= 16 else (32 if r <= 32 else 64))
+        self.KBM, self.REM, self.PEN = layout(D)
         self.DPG = 64 * self.KBM + self.REM
+        self.W = DB + 1 - self.PEN                   # floats per column of the b tile
         with open(_COMMON_PATH) as f:
             body = f.read()
         with open(_SRC_PATH) as f:
             body += f.read()
         self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
         defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
-                "#define CT_HS %d\n#define CT_DBG %d\n" % (D, DB, self.KBM, self.REM, self.STAGES, HS,
-                                                        int(os.environ.get("CT_DBG", 0))))
+                "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n" % (D, DB, self.KBM, self.REM, self.STAGES, HS,
+                                                                       int(os.environ.get("CT_DBG", 0)), self.PEN))
         src = defs + body
         opts = plan.nvrtc_options(True)
         key = hashlib.sha256((VERSION + src + " ".join(opts)).encode()).hexdigest()[:20]
@@ -214,16 +251,17 @@ class ConvTensorCore:
                 f.write(cubin)
             os.replace(tmp, path)
         self.cubin = cubin
-        blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K
-        self.smem = 1024 + 2 * blk(128) + self.STAGES * blk(BN) + HS * BN * DB * 4 + 640
+        self.smem = smem_bytes(D, DB, self.STAGES)
         if self.smem > 227 * 1024:
             raise ValueError("conv_tc: D = %d, dim b = %d needs %d bytes of shared memory" % (D, DB, self.smem))
         self.smem = max(self.smem, 120 * 1024)     # one CTA per SM: each CTA allocates all 512 TMEM columns
         self.module = None
+        self.last_bound = None
         if device >= 0:
             self.module = capi.Module(cubin, device)
             self.fn_prep = self.module.function("kb200_conv_prep")
             self.fn_conv = self.module.function("kb200_conv_tc")
+            self.fn_combine = self.module.function("kb200_conv_combine")
             capi.set_max_dynamic_smem(self.fn_conv, self.smem)
 
     def _maps(self, abf, n, box_rows):
@@ -235,7 +273,7 @@ class ConvTensorCore:
 
     def run(self, x, y, b, coef, out, stream_obj):
         """x (M, D), y (N, D), b (N, DB) fp32 contiguous CUDA tensors, coef a one-element fp32 tensor;
-        out (M, DB) fp32.  Everything is enqueued on ``stream_obj``; no host synchronisation."""
+        out (M, DB) fp32.  Returns False (nothing written) when the accuracy guard rejects the inputs."""
         import torch
         M, N = x.shape[0], y.shape[0]
         dev = x.device
@@ -248,21 +286,43 @@ class ConvTensorCore:
         xbf = torch.empty((M, self.DPG), dtype=torch.int16, device=dev)
         ysq = torch.empty(N, dtype=torch.float32, device=dev)
         xsq = torch.empty(M, dtype=torch.float32, device=dev)
-        bpad = torch.empty(npad * self.DB, dtype=torch.float32, device=dev)
+        bpad = torch.empty(npad * self.W, dtype=torch.float32, device=dev)
         capi.launch(self.fn_prep, stream, (-(-npad // 256),), (256,), 0,
                     [i64(N), i64(npad), ptr(y.data_ptr()), ptr(shift.data_ptr()), ptr(ybf.data_ptr()), ptr(ysq.data_ptr()),
                      ptr(b.data_ptr()), ptr(bpad.data_ptr()), i32(0)])
         capi.launch(self.fn_prep, stream, (-(-M // 256),), (256,), 0,
                     [i64(M), i64(M), ptr(x.data_ptr()), ptr(shift.data_ptr()), ptr(xbf.data_ptr()), ptr(xsq.data_ptr()),
                      ptr(0), ptr(0), i32(1)])
+        tol = float(os.environ.get("KB200_CONV_TC_TOL", TOL))
+        self.last_bound = None
+        if tol > 0.0:
+            # accuracy guard: the exponent carries an absolute error ~ 2^-22 |c| log2(e) (max |x-m|^2 + max |y-m|^2); when
+            # that exceeds the stated tolerance (clouds much wider than the kernel bandwidth) the caller falls back to
+            # the CUDA-core kernel, which forms x - y directly.  One host read, like the reference's per-call sync.
+            bound = coef.abs() * (xsq.max() + ysq.max()) * (2.0 ** -22)
+            self.last_bound = float(bound.item())
+            if not self.last_bound <= tol:          # also catches NaN / inf inputs
+                return False
         map_y, map_yr = self._maps(ybf, N, BN)
         map_x, map_xr = self._maps(xbf, M, 128)
-        capi.launch(self.fn_conv, stream, (-(-M // BM),), (320,), self.smem,
-                    [map_x, map_xr, map_y, map_yr, i64(M), i64(N), ptr(bpad.data_ptr()), ptr(xsq.data_ptr()),
-                     ptr(coef.data_ptr()), ptr(out.data_ptr())])
-        for t in (shift, ybf, xbf, ysq, xsq, bpad, coef):
+        # column chunks: every CTA streams all operand rows of its chunk, so a chunk must stay L2-resident
+        # (126 MB L2; measured at M = N = 1e6, D = 16: one 256 MB chunk 288 ms, L2-sized chunks %s)
+        chunk_bytes = int(os.environ.get("KB200_CONV_TC_CHUNK_MB", CHUNK_MB)) << 20
+        tiles_per_chunk = max(1, chunk_bytes // (BN * self.DPG * 2))
+        nchunks = -(-ntiles // tiles_per_chunk)
+        tiles_per_chunk = -(-ntiles // nchunks)                   # balanced
+        nchunks = -(-ntiles // tiles_per_chunk)
+        dst = out if nchunks == 1 else torch.empty((nchunks, M, self.DB), dtype=torch.float32, device=dev)
+        capi.launch(self.fn_conv, stream, (-(-M // BM), nchunks), (THREADS,), self.smem,
+                    [map_x, map_xr, map_y, map_yr, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
+                     ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr())])
+        if nchunks > 1:
+            capi.launch(self.fn_combine, stream, (-(-(M * self.DB) // 256),), (256,), 0,
+                        [i64(M * self.DB), i32(nchunks), ptr(dst.data_ptr()), ptr(out.data_ptr())])
+        for t in (shift, ybf, xbf, ysq, xsq, bpad, coef, dst):
             t.record_stream(stream_obj)
-        self.last = dict(ntiles=ntiles, ctas=-(-M // BM))
+        self.last = dict(ntiles=ntiles, ctas=-(-M // BM) * nchunks, nchunks=nchunks)
+        return True
 
 
 _cache: Dict[tuple, ConvTensorCore] = {}

@@ -22,10 +22,13 @@
 // kb200_conv_prep : fp32 rows -> the 6 D + 3 bf16 operand columns (zero padded to CT_DPG) + |x - shift|^2;
 //                   on the streamed side also a zero-padded copy of b (whole 128-column tiles).
 // kb200_conv_tc   : one CTA = 256 output rows (two 128-row accumulators) x all streamed columns in 128-column
-//                   tiles.  Warp 0 = TMA producer (operand tiles + the b tile), warp 1 = MMA issuer, warps 2..9 =
-//                   epilogue, one thread per output row: tcgen05.ld of its 128 accumulators, ex2, FFMA with b_j
-//                   (broadcast LDS.128), per-tile partial sums added to the running sum (the reference's
-//                   block_sum scheme, sum_schemes.py:55-71).  4-stage smem ring, double-buffered TMEM.
+//                   tiles.  Warp 0 = TMA producer (operand tiles + the b tile), warp 1 = MMA issuer, warps 2..17 =
+//                   epilogue: a thread owns one output row and one 64-column half of every tile (two threads per
+//                   row; 4 epilogue warps per scheduler hide the TMEM-load and barrier latencies behind the other
+//                   warps' ex2 stream): tcgen05.ld of its 64 accumulators, ex2, FFMA with b_j (broadcast LDS.128),
+//                   per-tile partial sums added to the running sum (the reference's block_sum scheme,
+//                   sum_schemes.py:55-71); the two halves of a row are added through shared memory at the end.
+//                   4-stage smem ring, double-buffered TMEM accumulators.
 //
 // Compile-time parameters (keops_b200/codegen/conv_tc.py): CT_D, CT_DB (dimension of b), CT_KBM / CT_REM (operand
 // rows = CT_KBM 128-byte-swizzled 64-column blocks + one remainder block of CT_REM columns), CT_STAGES, CT_HS.
@@ -49,15 +52,24 @@
 #define CT_BM 256                             /* rows per CTA: two 128-row accumulators                          */
 #define CT_BN 128                             /* columns per tile (= N of one tcgen05.mma)                       */
 #define CT_NBUF 2                             /* TMEM accumulator buffers per row block: 2 x 2 x 128 = 512 cols  */
-#define CT_NCOL (6 * CT_D + 3)                /* used K columns                                                  */
+#ifndef CT_PEN
+#define CT_PEN 1                              /* 1: -|y|^2/2 rides in three extra K columns; 0: |y|^2 is added in the
+                                                 epilogue (one more FFMA per pair) when that saves a K block       */
+#endif
+#define CT_NCOL (6 * CT_D + 3 * CT_PEN)       /* used K columns                                                  */
+#define CT_W (CT_DB + 1 - CT_PEN)             /* floats per column of the b tile: [ |y|^2 (CT_PEN == 0) , b ]      */
 #define CT_DPG (64 * CT_KBM + CT_REM)
 #define CT_TILE_BYTES(rows) ((rows) * 128)
 #define CT_RTILE_BYTES(rows) ((rows) * CT_REM * 2)
 #define CT_BLK_BYTES(rows) (CT_KBM * CT_TILE_BYTES(rows) + CT_RTILE_BYTES(rows))
 #define CT_A_BYTES (2 * CT_BLK_BYTES(128))
 #define CT_B_BYTES CT_BLK_BYTES(CT_BN)
-#define CT_H_BYTES (CT_BN * CT_DB * 4)        /* one b tile                                                      */
-#define CT_SMEM_BYTES (1024 + CT_A_BYTES + CT_STAGES * CT_B_BYTES + CT_HS * CT_H_BYTES + 640) /* mirrored in conv_tc.py */
+#define CT_H_BYTES (CT_BN * CT_W * 4)         /* one b tile                                                      */
+#define CT_X_BYTES (CT_BM * CT_DB * 4)        /* exchange of the second column half's sums at the end            */
+#define CT_EPI_WARPS 16
+#define CT_THREADS (64 + 32 * CT_EPI_WARPS)
+#define CT_HALF (CT_BN / 2)                   /* columns per epilogue thread and tile                            */
+#define CT_SMEM_BYTES (1024 + CT_A_BYTES + CT_STAGES * CT_B_BYTES + CT_HS * CT_H_BYTES + CT_X_BYTES + 640) /* mirrored in conv_tc.py */
 #define CT_LOG2E 1.4426950408889634f
 // bf16 x bf16 -> f32, A and B K-major, M = 128, N = CT_BN
 #define CT_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | (((u32)CT_BN >> 3) << 17) | ((128u >> 4) << 24))
@@ -65,7 +77,8 @@
 // ------------------------------------------------------------------------------------------------
 // prep
 //   side 0 (streamed, y): [ y1 | y2 | y1 | y3 | y2 | y1 | -h1 -h2 -h3 | 0 .. ],  h = |y - shift|^2 / 2
-//                         + bpad (npad x CT_DB): b for rows < n, 0 for the padding of the last tile
+//                         + bpad (npad x CT_W): [ |y - shift|^2 if CT_PEN == 0 , b ] for rows < n, 0 for the padding
+//                           of the last tile
 //   side 1 (output,   x): [ x1 | x1 | x2 | x1 | x2 | x3 |  1   1   1  | 0 .. ],  sq[r] = |x - shift|^2
 //   (v1, v2, v3 = successive bf16 round-to-nearest remainders of the shifted coordinate)
 // ------------------------------------------------------------------------------------------------
@@ -76,7 +89,8 @@ kb200_conv_prep(const long long n, const long long npad, const float* __restrict
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (side == 0 && r < npad) {
 #pragma unroll
-    for (int d = 0; d < CT_DB; d++) bpad[r * CT_DB + d] = (r < n) ? b[r * CT_DB + d] : 0.0f;
+    for (int d = 0; d < CT_DB; d++) bpad[r * CT_W + (1 - CT_PEN) + d] = (r < n) ? b[r * CT_DB + d] : 0.0f;
+    if (CT_PEN == 0 && r >= n) bpad[r * CT_W] = 0.0f;
   }
   if (r >= n) return;
   const float* row = a + r * CT_D;
@@ -98,7 +112,9 @@ kb200_conv_prep(const long long n, const long long npad, const float* __restrict
       orow[3 * CT_D + k] = p1; orow[4 * CT_D + k] = p2; orow[5 * CT_D + k] = p3;
     }
   }
-  if (side == 0) {
+  if (CT_PEN == 0) {
+    if (side == 0) bpad[r * CT_W] = s;
+  } else if (side == 0) {
     const float h = 0.5f * s;
     const unsigned short hi = kt_bf16_rn(h);
     const float r1 = h - kt_bf16_to_f(hi);
@@ -113,7 +129,7 @@ kb200_conv_prep(const long long n, const long long npad, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// epilogue of one tile for one output row: tmp_d = sum_e exp2(fma(u_e, c2, rowc)) * b[e][d]
+// epilogue of one tile for one output row: tmp_d = sum_e exp2(fma(u_e, c2, rowc) [+ cl |y_e|^2]) * b[e][d]
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ct_ex2(float s) {
   float p;
@@ -122,36 +138,39 @@ __device__ __forceinline__ float ct_ex2(float s) {
 }
 
 template <bool TAIL>
-__device__ __forceinline__ void ct_tile(const float (&u)[CT_BN], const float* __restrict__ bt, const float c2,
-                                        const float rowc, const long long j0, const long long ncol,
+__device__ __forceinline__ void ct_tile(const float (&u)[CT_HALF], const float* __restrict__ bt, const float c2,
+                                        const float cl, const float rowc, const long long j0, const long long ncol,
                                         float (&acc)[CT_DB]) {
   float tmp[2][CT_DB];                                // two interleaved partial sums per component
 #pragma unroll
   for (int d = 0; d < CT_DB; d++) tmp[0][d] = tmp[1][d] = 0.0f;
 #pragma unroll
-  for (int e4 = 0; e4 < CT_BN / 4; e4++) {
+  for (int e4 = 0; e4 < CT_HALF / 4; e4++) {
+    // the four b-tile rows of these columns: 4 * CT_W consecutive floats, read with broadcast LDS.128
+    float bv[4 * CT_W];
+    const float4* b4 = reinterpret_cast<const float4*>(bt + 4 * e4 * CT_W);
+#pragma unroll
+    for (int v = 0; v < CT_W; v++) {
+      const float4 q = b4[v];
+      bv[4 * v + 0] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
+    }
     float p[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
+      float sarg = fmaf(u[4 * e4 + e], c2, rowc);
+      if (CT_PEN == 0) sarg = fmaf(bv[e * CT_W], cl, sarg);          // + cl |y_j|^2
 #if CT_DBG == 1
-      p[e] = fmaf(u[4 * e4 + e], c2, rowc);
+      p[e] = sarg;
 #else
-      p[e] = ct_ex2(fmaf(u[4 * e4 + e], c2, rowc));
+      p[e] = ct_ex2(sarg);
 #endif
       if (TAIL && j0 + 4 * e4 + e >= ncol) p[e] = 0.0f;
-    }
-    // the four b rows of these columns: 4 * CT_DB consecutive floats, read with broadcast LDS.128
-    float bv[4 * CT_DB];
-    const float4* b4 = reinterpret_cast<const float4*>(bt + 4 * e4 * CT_DB);
-#pragma unroll
-    for (int v = 0; v < CT_DB; v++) {
-      const float4 q = b4[v];
-      bv[4 * v + 0] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
     }
 #pragma unroll
     for (int e = 0; e < 4; e++)
 #pragma unroll
-      for (int d = 0; d < CT_DB; d++) tmp[e & 1][d] = fmaf(p[e], bv[e * CT_DB + d], tmp[e & 1][d]);
+      for (int d = 0; d < CT_DB; d++)
+        tmp[e & 1][d] = fmaf(p[e], bv[e * CT_W + (1 - CT_PEN) + d], tmp[e & 1][d]);
   }
 #pragma unroll
   for (int d = 0; d < CT_DB; d++) acc[d] += tmp[0][d] + tmp[1][d];
@@ -160,11 +179,12 @@ __device__ __forceinline__ void ct_tile(const float (&u)[CT_BN], const float* __
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(320, 1)
+extern "C" __global__ void __launch_bounds__(CT_THREADS, 1)
 kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_xr,
               const __grid_constant__ KtTensorMap map_y, const __grid_constant__ KtTensorMap map_yr,
-              const long long nrow, const long long ncol, const float* __restrict__ bpad,
-              const float* __restrict__ xsq, const float* __restrict__ coef, float* __restrict__ out) {
+              const long long nrow, const long long ncol, const long long chunk_cols,
+              const float* __restrict__ bpad, const float* __restrict__ xsq, const float* __restrict__ coef,
+              float* __restrict__ out) {
   extern __shared__ unsigned char ct_raw[];
   const u32 raw = kt_smem(ct_raw);
   const u32 base = (raw + 1023u) & ~1023u;                       // swizzle atoms need (up to) 1024-byte alignment
@@ -173,22 +193,30 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
   const u32 sB = sA + CT_A_BYTES;                                // STAGES x [KBM main tiles | remainder tile]
   const u32 sH = sB + CT_STAGES * CT_B_BYTES;                    // ring of b tiles (CT_HS x CT_BN x CT_DB floats)
   const float* hb = reinterpret_cast<const float*>(gbase + CT_A_BYTES + CT_STAGES * CT_B_BYTES);
-  const u32 sBar = sH + CT_HS * CT_H_BYTES;
+  const u32 sX = sH + CT_HS * CT_H_BYTES;                         // CT_BM x CT_DB floats
+  float* xch = reinterpret_cast<float*>(gbase + CT_A_BYTES + CT_STAGES * CT_B_BYTES + CT_HS * CT_H_BYTES);
+  const u32 sBar = sX + CT_X_BYTES;
   // barriers (8 bytes each): full[8] @0, empty[8] @64, tfull[buf][rb] @128, tempty[buf][rb] @192,
   //                          hfull[16] @256, hempty[16] @384, afull @512, tmem pointer @520
   const u32 bFull = sBar, bEmpty = sBar + 64, bTFull = sBar + 128, bTEmpty = sBar + 192, bAFull = sBar + 512;
   const u32 bHFull = sBar + 256, bHEmpty = sBar + 384;
   volatile u32* tmem_slot =
-      reinterpret_cast<volatile u32*>(gbase + CT_A_BYTES + CT_STAGES * CT_B_BYTES + CT_HS * CT_H_BYTES + 520);
+      reinterpret_cast<volatile u32*>(gbase + CT_A_BYTES + CT_STAGES * CT_B_BYTES + CT_HS * CT_H_BYTES + CT_X_BYTES + 520);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row_base = (long long)blockIdx.x * CT_BM;
-  const int ntiles = (int)((ncol + CT_BN - 1) / CT_BN);
+  // blockIdx.y = column chunk (chunk_cols is a multiple of CT_BN).  CTAs are dispatched x-fastest, so all row blocks
+  // of one chunk run together and the chunk's operand rows stay L2-resident while every CTA streams them.
+  const long long col0 = (long long)blockIdx.y * chunk_cols;
+  const long long col1 = (col0 + chunk_cols < ncol) ? col0 + chunk_cols : ncol;
+  const int t0 = (int)(col0 / CT_BN);
+  const int ntiles = (int)((col1 - col0 + CT_BN - 1) / CT_BN);
+  out += (long long)blockIdx.y * nrow * CT_DB;                   // chunk partial sums (gridDim.y > 1) or the output
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
-    for (int b = 0; b < 2 * CT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, 4); }
-    for (int h = 0; h < CT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, 8); }
+    for (int b = 0; b < 2 * CT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, CT_EPI_WARPS / 2); }
+    for (int h = 0; h < CT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, CT_EPI_WARPS); }
     kt_mbar_init(bAFull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,10 +247,10 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
       if (kt_elect()) {
         kt_mbar_expect_tx(bFull + 8 * s, CT_B_BYTES);
         for (int kb = 0; kb < CT_KBM; kb++)
-          kt_tma_2d(sB + s * CT_B_BYTES + kb * CT_TILE_BYTES(CT_BN), &map_y, kb * 64, t * CT_BN, bFull + 8 * s);
-        kt_tma_2d(sB + s * CT_B_BYTES + CT_KBM * CT_TILE_BYTES(CT_BN), &map_yr, 0, t * CT_BN, bFull + 8 * s);
+          kt_tma_2d(sB + s * CT_B_BYTES + kb * CT_TILE_BYTES(CT_BN), &map_y, kb * 64, (t0 + t) * CT_BN, bFull + 8 * s);
+        kt_tma_2d(sB + s * CT_B_BYTES + CT_KBM * CT_TILE_BYTES(CT_BN), &map_yr, 0, (t0 + t) * CT_BN, bFull + 8 * s);
         kt_mbar_expect_tx(bHFull + 8 * h, CT_H_BYTES);
-        kt_bulk_1d(sH + h * CT_H_BYTES, bpad + (long long)t * CT_BN * CT_DB, CT_H_BYTES, bHFull + 8 * h);
+        kt_bulk_1d(sH + h * CT_H_BYTES, bpad + (long long)(t0 + t) * CT_BN * CT_W, CT_H_BYTES, bHFull + 8 * h);
       }
       __syncwarp();
     }
@@ -260,9 +288,12 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue: one thread per output row =====================
-    const int q = warp & 3, rb = (warp - 2) >> 2;
-    const long long i = row_base + rb * 128 + q * 32 + lane;
+    // ===================== epilogue: one thread per (output row, 64-column half) =====================
+    // warps 2-5: row block 0, half 0 | 6-9: row block 1, half 0 | 10-13: row block 0, half 1 | 14-17: row block 1,
+    // half 1; inside each group the four warps cover the four TMEM lane quarters (a warp may only read quarter warp % 4)
+    const int ew = warp - 2, q = warp & 3, rb = (ew >> 2) & 1, half = ew >> 3;
+    const int rloc = rb * 128 + q * 32 + lane;        // row inside the CTA
+    const long long i = row_base + rloc;
     const bool live = i < nrow;
     const float cl = coef[0] * CT_LOG2E;              // exponent = cl * |x - y|^2  (base 2)
     const float c2 = -2.0f * cl;
@@ -274,29 +305,35 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
       const int buf = t % CT_NBUF, hslot = t % CT_HS;
       kt_mbar_wait(bTFull + 8 * (buf * 2 + rb), (t / CT_NBUF) & 1);
       kt_fence_after();
-      const u32 tbase = tmem + ((u32)(q * 32) << 16) + (u32)((buf * 2 + rb) * CT_BN);
-      float uu[CT_BN];
+      const u32 tbase = tmem + ((u32)(q * 32) << 16) + (u32)((buf * 2 + rb) * CT_BN + half * CT_HALF);
+      float uu[CT_HALF];
 #if CT_DBG == 2
 #pragma unroll
-      for (int e = 0; e < CT_BN; e++) uu[e] = -1.0f;
+      for (int e = 0; e < CT_HALF; e++) uu[e] = -1.0f;
 #else
-#pragma unroll
-      for (int c = 0; c < CT_BN / 64; c++) kt_tmem_ld64_nowait(tbase + (u32)(c * 64), uu + c * 64);
+      kt_tmem_ld64_nowait(tbase, uu);
       kt_tmem_wait_ld();
 #endif
       kt_fence_before();
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));   // accumulator back to the MMA warp
       kt_mbar_wait(bHFull + 8 * hslot, (t / CT_HS) & 1);
-      const float* bt = hb + hslot * (CT_BN * CT_DB);
-      if (t == ntiles - 1) ct_tile<true>(uu, bt, c2, rowc, (long long)t * CT_BN, ncol, acc);
-      else ct_tile<false>(uu, bt, c2, rowc, (long long)t * CT_BN, ncol, acc);
+      const float* bt = hb + hslot * (CT_BN * CT_W) + half * (CT_HALF * CT_W);
+      const long long j0 = (long long)(t0 + t) * CT_BN + half * CT_HALF;
+      if (j0 + CT_HALF > ncol) ct_tile<true>(uu, bt, c2, cl, rowc, j0, ncol, acc);
+      else ct_tile<false>(uu, bt, c2, cl, rowc, j0, ncol, acc);
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
     }
-    if (live) {
+    // row sum = first half + second half (fixed order: deterministic)
+    if (half == 1) {
 #pragma unroll
-      for (int d = 0; d < CT_DB; d++) out[i * CT_DB + d] = acc[d];
+      for (int d = 0; d < CT_DB; d++) xch[rloc * CT_DB + d] = acc[d];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * CT_EPI_WARPS) : "memory");
+    if (half == 0 && live) {
+#pragma unroll
+      for (int d = 0; d < CT_DB; d++) out[i * CT_DB + d] = acc[d] + xch[rloc * CT_DB + d];
     }
   }
   kt_fence_before();
@@ -305,4 +342,16 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// combine: out = sum over column chunks of the partial sums, in chunk order (deterministic)
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256)
+kb200_conv_combine(const long long n, const int nchunks, const float* __restrict__ partial, float* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float s = partial[e];
+  for (int c = 1; c < nchunks; c++) s += partial[(long long)c * n + e];
+  out[e] = s;
 }

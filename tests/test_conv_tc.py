@@ -1,0 +1,205 @@
+"""Tensor-core Gaussian Sum reduction (``keops_b200/csrc/kb200_conv_tc.cu``, ``codegen/conv_tc.py``).
+
+CPU part: pattern recognition, operand layout, eligibility.  GPU part: the tcgen05 path against the CUDA-core kernel
+(whose parity with the reference is pinned by the golden fixtures), against the reference's own generated CUDA and CPU
+code for the KernelSolve formula (``oracle/_ref``: gauss16_pm_f32) and against the numpy oracle; the accuracy guard
+and its fallback.  Tolerance: the north-star fp32 bar, 1e-5 relative (``tests/util.py``)."""
+import os
+
+import numpy as np
+import pytest
+
+from keops_b200.codegen import conv_tc
+from keops_b200.formulas.parser import parse_reduction
+from tests import util
+
+KS = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)"
+
+
+# ---------------------------------------------------------------------------------------------
+# host logic (no GPU)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("formula,expect", [
+    (KS, (0, 1, 16, 2, 1)),
+    ("Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,1,1)),0)", (0, 1, 3, 2, 1)),
+    ("Sum_Reduction(Var(2,3,1)*Exp(-SqDist(Var(0,8,0),Var(1,8,1))/Var(3,1,2)),0)", (0, 1, 8, 2, 3)),
+    ("Sum_Reduction(Exp(-IntCst(2)*SqNorm2(Var(0,8,0)-Var(1,8,1)))*Var(2,1,1),0)", (0, 1, 8, 2, 1)),
+    # reduction over i: the output follows j, x_i and b_i are streamed
+    ("Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,2,0),1)", (1, 0, 16, 2, 2)),
+    ("Sum_Reduction(Exp(-(Var(3,1,2)*Var(3,1,2))*SqDist(Var(1,16,1),Var(0,16,0)))*Var(2,1,1),0)", (0, 1, 16, 2, 1)),
+])
+def test_match_recognises_gaussian_convolutions(formula, expect):
+    m = conv_tc.match(parse_reduction(formula))
+    assert m is not None and m[:5] == expect
+
+
+@pytest.mark.parametrize("formula", [
+    "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,0),0)",      # b is output-indexed
+    "Sum_Reduction(Exp(-Var(3,1,0)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)",      # per-row bandwidth
+    "Sum_Reduction(Exp(-Sqrt(SqDist(Var(0,16,0),Var(1,16,1))))*Var(2,1,1),0)",           # Laplacian kernel
+    "Sum_Reduction(Exp(-SqDist(Var(0,16,0),Var(1,16,0)))*Var(2,1,1),0)",                 # both operands on one side
+    "Max_SumShiftExp_Reduction(-SqDist(Var(0,16,0),Var(1,16,1)),0)",
+    "Sum_Reduction(Exp(-SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,9,1),0)",                 # dim b > MAX_DB
+])
+def test_match_rejects_other_formulas(formula):
+    assert conv_tc.match(parse_reduction(formula)) is None
+
+
+def test_layout_and_eligibility():
+    assert conv_tc.layout(16) == (1, 64, 1)        # 96 product + 3 penalty columns, padded to 128
+    assert conv_tc.layout(21) == (1, 64, 0)        # 126 product columns; |y|^2 goes to the epilogue
+    assert conv_tc.layout(8) == (0, 64, 1)         # 48 + 3 columns in one 64-column block
+    assert conv_tc.layout(20) == (1, 64, 1)
+    red = parse_reduction(KS)
+    assert conv_tc.eligible(red, "float32", 100000, 100000, 1, True) is not None
+    assert conv_tc.eligible(red, "float64", 100000, 100000, 1, True) is None       # fp64: exact path only
+    assert conv_tc.eligible(red, "float32", 100000, 100000, 1, False) is None      # no fast math: exact expf
+    assert conv_tc.eligible(red, "float32", 100000, 100000, 2, True) is None       # batch dimensions
+    assert conv_tc.eligible(red, "float32", 1000, 100000, 1, True) is None         # too few rows to fill the machine
+    assert conv_tc.eligible(red, "float32", 100000, 100000, 1, True, "kahan_scheme") is None
+    g3 = parse_reduction("Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,1,1)),0)")
+    assert conv_tc.eligible(g3, "float32", 100000, 100000, 1, True) is None        # D = 3 stays on the CUDA cores
+    g22 = parse_reduction(KS.replace("16", "22"))
+    assert conv_tc.eligible(g22, "float32", 100000, 100000, 1, True) is None       # K > 128 does not fit
+    assert conv_tc.eligible(parse_reduction(KS.replace("Var(2,1,1)", "Var(2,8,1)")), "float32", 100000, 100000, 1, True) is None  # b ring too wide for smem
+    for D, DB in ((8, 1), (16, 1), (16, 4), (21, 4)):
+        assert conv_tc.smem_bytes(D, DB) <= 227 * 1024
+
+
+def test_kernels_compile_for_sm100a():
+    eng = conv_tc.ConvTensorCore(16, 1, device=-1)            # NVRTC, --gpu-architecture=sm_100a, no GPU needed
+    assert eng.cubin[:4] == b"\x7fELF"
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU parity
+# ---------------------------------------------------------------------------------------------
+class _env:
+    def __init__(self, **kw):
+        self.kw = {k: str(v) for k, v in kw.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update(self.kw)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _run(formula, nargs, args, nx, ny, dev, tc, **env):
+    import torch
+    from keops_b200.binder import get_binder
+    with _env(KB200_CONV_TC="1" if tc else "0", **env):
+        bd = get_binder(formula, [], nargs, "float32")
+        out = bd.genred_pytorch(dev, None, nx, ny, 0, None, *args)
+        torch.cuda.synchronize()
+        return out, dict(bd.last_launch)
+
+
+CASES = [
+    # D, DB, nx, ny, tagI, coefficient spelling
+    (16, 1, 9000, 7001, 0, "-Var(3,1,2)*"),           # KernelSolve formula, ragged last tile
+    (8, 3, 8192, 4096, 0, "-Var(3,1,2)*"),            # penalty columns inside K, vector b
+    (13, 2, 8300, 5000, 0, "-IntCst(2)*"),            # constant coefficient, K = 64 + 16
+    (20, 1, 8192, 3000, 0, "-Var(3,1,2)*Var(3,1,2)*"),
+    (16, 2, 5000, 9000, 1, "-Var(3,1,2)*"),           # reduction over i
+    (21, 4, 8192, 2000, 0, "-Var(3,1,2)*"),           # widest supported operand rows
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,DB,nx,ny,tagI,coef", CASES)
+def test_tensor_core_conv_matches_cuda_core(D, DB, nx, ny, tagI, coef, cuda_device):
+    import torch
+    torch.manual_seed(D * 100 + DB)
+    dev = cuda_device
+    x, y = torch.rand(nx, D, device=dev), torch.rand(ny, D, device=dev)
+    b = torch.randn((ny if tagI == 0 else nx), DB, device=dev)
+    g = torch.tensor([0.7], device=dev)
+    f = "Sum_Reduction(Exp(%sSqDist(Var(0,%d,0),Var(1,%d,1)))*Var(2,%d,%d),%d)" % (coef, D, D, DB, 1 - tagI, tagI)
+    o_tc, ll = _run(f, 4, (x, y, b, g), nx, ny, dev, True)
+    assert ll.get("engine") == "tcgen05-conv", ll         # the tensor-core kernels really ran
+    assert ll["error_bound"] <= 5e-6
+    o_cc, ll2 = _run(f, 4, (x, y, b, g), nx, ny, dev, False)
+    assert ll2.get("engine") is None
+    util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 conv vs CUDA cores")
+    # several column chunks (forced) give the same sums up to fp32 re-association
+    o_ch, ll3 = _run(f, 4, (x, y, b, g), nx, ny, dev, True, KB200_CONV_TC_CHUNK_MB=1)
+    if (ny if tagI == 0 else nx) * 2 * (64 * conv_tc.layout(D)[0] + conv_tc.layout(D)[1]) > (1 << 20):
+        assert ll3["nchunks"] > 1
+    util.assert_close(o_ch.cpu().numpy(), o_cc.cpu().numpy(), "float32", "chunked tcgen05 conv vs CUDA cores")
+    # sampled rows against the numpy oracle (reference operation order, exact exp)
+    from oracle import keops_oracle as ko
+    rows = slice(0, 48)
+    xa, ya, ba, ga = (t.cpu().numpy() for t in (x, y, b, g))
+    if tagI == 0:
+        ref = ko.genred(f, [], [xa[rows], ya, ba, ga], "float32")
+    else:
+        ref = ko.genred(f, [], [xa, ya[rows], ba, ga], "float32")
+    util.assert_close(o_tc[rows].cpu().numpy(), ref, "float32", "tcgen05 conv vs oracle")
+
+
+@pytest.mark.gpu
+def test_tensor_core_conv_vs_reference_code(cuda_device):
+    """KernelSolve matvec formula against the reference's own generated CUDA kernel (all rows) and CPU code (sample)."""
+    import torch
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref not built")
+    dev = cuda_device
+    torch.manual_seed(3)
+    nx, ny = 40000, 30011
+    x, y, b = torch.rand(nx, 16, device=dev), torch.rand(ny, 16, device=dev), torch.randn(ny, 1, device=dev)
+    g = torch.tensor([1.0], device=dev)
+    o_tc, ll = _run(KS, 4, (x, y, b, g), nx, ny, dev, True)
+    assert ll.get("engine") == "tcgen05-conv"
+    ref = ref_runner.RefCuda("gauss16_pm_f32", 0)([x, y, b, g], nx, ny)
+    torch.cuda.synchronize()
+    util.assert_close(o_tc.cpu().numpy(), ref.cpu().numpy(), "float32", "tcgen05 conv vs reference CUDA")
+    rows = np.arange(0, nx, 157)
+    cpu = ref_runner.run_cpu("gauss16_pm_f32", [x.cpu().numpy()[rows], y.cpu().numpy(), b.cpu().numpy(), g.cpu().numpy()],
+                             len(rows), ny)
+    util.assert_close(o_tc.cpu().numpy()[rows], cpu, "float32", "tcgen05 conv vs reference CPU")
+
+
+@pytest.mark.gpu
+def test_accuracy_guard_falls_back_to_cuda_cores(cuda_device):
+    """A cloud much wider than the kernel bandwidth would lose digits in |x|^2 + |y|^2 - 2 x.y: the guard must send it
+    to the CUDA-core kernel (which forms x - y directly), and the result must be that kernel's, bit for bit."""
+    import torch
+    dev = cuda_device
+    torch.manual_seed(4)
+    nx, ny = 8192, 4096
+    x, y = 50.0 * torch.rand(nx, 16, device=dev), 50.0 * torch.rand(ny, 16, device=dev)
+    y[:nx // 2] = x[:ny][:nx // 2] + 0.05 * torch.randn(nx // 2, 16, device=dev)     # close pairs carry the sums
+    b, g = torch.randn(ny, 1, device=dev), torch.tensor([2.0], device=dev)
+    o, ll = _run(KS, 4, (x, y, b, g), nx, ny, dev, True)
+    assert ll.get("engine") is None, ll
+    o_cc, _ = _run(KS, 4, (x, y, b, g), nx, ny, dev, False)
+    assert torch.equal(o, o_cc)
+    # a shifted (not wider) cloud is fine: the common shift removes the offset
+    x2, y2 = torch.rand(nx, 16, device=dev) + 1000.0, torch.rand(ny, 16, device=dev) + 1000.0
+    o2, ll2 = _run(KS, 4, (x2, y2, b, g), nx, ny, dev, True)
+    assert ll2.get("engine") == "tcgen05-conv" and ll2["error_bound"] <= 5e-6
+    o2_cc, _ = _run(KS, 4, (x2, y2, b, g), nx, ny, dev, False)
+    util.assert_close(o2.cpu().numpy(), o2_cc.cpu().numpy(), "float32", "shifted cloud")
+
+
+@pytest.mark.gpu
+def test_tensor_core_conv_is_deterministic_and_linear(cuda_device):
+    import torch
+    dev = cuda_device
+    torch.manual_seed(5)
+    nx, ny = 10000, 12000
+    x, y = torch.rand(nx, 16, device=dev), torch.rand(ny, 16, device=dev)
+    b1, b2, g = torch.randn(ny, 1, device=dev), torch.randn(ny, 1, device=dev), torch.tensor([1.3], device=dev)
+    o1, _ = _run(KS, 4, (x, y, b1, g), nx, ny, dev, True)
+    o1b, _ = _run(KS, 4, (x, y, b1, g), nx, ny, dev, True)
+    assert torch.equal(o1, o1b)
+    o2, _ = _run(KS, 4, (x, y, b2, g), nx, ny, dev, True)
+    o12, _ = _run(KS, 4, (x, y, b1 + 2.0 * b2, g), nx, ny, dev, True)
+    util.assert_close(o12.cpu().numpy(), (o1 + 2.0 * o2).cpu().numpy(), "float32", "linearity in b")
