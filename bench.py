@@ -41,6 +41,7 @@ GAUSS = "Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var
 GRAD_X = "Grad_WithSavedForward(%s,Var(0,3,0),Var(3,1,0),Var(4,1,0))" % GAUSS
 GRAD_Y = "Grad_WithSavedForward(%s,Var(1,3,1),Var(3,1,0),Var(4,1,0))" % GAUSS
 KNN = "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)"
+KSOLVE = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)"    # BASELINE configs[4] matvec
 SM_COUNT, SM_MAX_HZ = 148, 1.965e9
 # dram__bytes_read.sum + dram__bytes_write.sum of one kb200_reduce launch of the full-size forward conv, from the
 # committed `ncu --set full` capture profiles/r01_ncu_gauss_fwd.txt (28.110 MB + 14 KB; algorithmic bytes 32 MB)
@@ -414,6 +415,38 @@ def main():
                            "fwd_ms": fwd_ms, "grad_x_ms": gx_ms, "grad_y_ms": gy_ms,
                            "grad_x_frac_of_roofline": M * N / (gx_ms * 1e-3) / pk,
                            "grad_y_frac_of_roofline": M * N / (gy_ms * 1e-3) / pk}
+        # ---- KernelSolve matvec (BASELINE configs[4]): Gaussian kernel, D = 16, one CG iteration = M*N pairs.
+        # Tensor-core path (tcgen05 GEMM for |x-y|^2, MUFU-bound) vs the CUDA-core kernel (FP32-pipe-bound, 34 ops/pair)
+        try:
+            kx, ky = torch.rand(M, 16, device=dev), torch.rand(N, 16, device=dev)
+            kb_, kg = torch.randn(N, 1, device=dev), torch.tensor([1.0], device=dev)
+            ks_b = get_binder(KSOLVE, [], 4, "float32")
+            probe = torch.zeros(2, dtype=torch.int64, device=dev)
+            ks_b.clock_probe = probe
+            tc_ms, o_tc = time_binder(ks_b, M, N, (kx, ky, kb_, kg))
+            engine = ks_b.last_launch.get("engine")
+            cyc, ns = (int(v) for v in probe.tolist())
+            real_hz = cyc / (ns * 1e-9) if ns > 0 else None
+            os.environ["KB200_CONV_TC"] = "0"
+            try:
+                cc_ms, o_cc = time_binder(ks_b, M, N, (kx, ky, kb_, kg), reps=1)
+            finally:
+                os.environ.pop("KB200_CONV_TC", None)
+            mufu_peak = 16.0 * SM_COUNT
+            line["ksolve_matvec"] = {
+                "workload": "Gaussian kernel matvec D=16 M=N=%d fp32 (one KernelSolve CG iteration)" % M,
+                "value": M * N / (tc_ms * 1e-3), "unit": "pair-evals/s", "ms": tc_ms, "engine": engine,
+                "cuda_core_ms": cc_ms, "speedup_vs_cuda_core": cc_ms / tc_ms,
+                "max_rel_diff_vs_cuda_core": float((o_tc - o_cc).abs().max() / o_cc.abs().max()),
+                "error_bound": ks_b.last_launch.get("error_bound"),
+                "roofline": {"bound": "sfu", "note": "1 MUFU.EX2 per pair at 16/clk/SM (measured 15.9, experiments/mufu_peak.py)",
+                             "frac_at_max_clock": M * N / (tc_ms * 1e-3) / (mufu_peak * sm_hz),
+                             "sm_clock_hz_measured_in_kernel": real_hz,
+                             "frac_at_measured_clock": (M * N / (tc_ms * 1e-3) / (mufu_peak * real_hz)) if real_hz else None},
+                "cuda_core_frac_of_fp32_roofline": M * N / (cc_ms * 1e-3) / (128.0 / 34.0 * SM_COUNT * sm_hz)}
+            del kx, ky, kb_, o_tc, o_cc
+        except Exception as e:
+            line["ksolve_matvec"] = {"unavailable": str(e)[:300]}
         # ---- the reference's own CUDA kernel on the same GPU ---------------------------------------
         try:
             from oracle import ref_runner

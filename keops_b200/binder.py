@@ -266,8 +266,9 @@ class LoadKeOpsB200:
         eng = conv_tc.get(D, DB, index)
         with torch.cuda.device(dev):
             coef = conv_tc.coefficient(terms, args, dev)
+            # `clock_probe` (bench.py sets it): int64[2] tensor receiving (SM cycles, ns) of one CTA of the kernel
             ok = eng.run(args[row_ind], args[col_ind], args[b_ind], coef, out.view(nrow, p.dim),
-                         torch.cuda.current_stream(dev))
+                         torch.cuda.current_stream(dev), clock_probe=getattr(self, "clock_probe", None))
         if not ok:
             return False            # accuracy guard: the caller runs the CUDA-core kernel
         self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0, blocks_per_sm=1,

@@ -35,10 +35,11 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-4"
+VERSION = "conv-tc-6"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
+POLY = 0                   # experiment (see kb200_conv_tc.cu): of every 8 pairs, exp2 of this many on the FMA pipe
 CHUNK_MB = 48              # bf16 operand rows of one column chunk (must stay L2-resident)
 # stated tolerance of the path: bound on the relative error of one term exp(c |x_i - y_j|^2) (0 disables the guard)
 TOL = 5e-6                 # default; the environment variable KB200_CONV_TC_TOL overrides it per call
@@ -235,8 +236,9 @@ class ConvTensorCore:
             body += f.read()
         self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
         defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
-                "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n" % (D, DB, self.KBM, self.REM, self.STAGES, HS,
-                                                                       int(os.environ.get("CT_DBG", 0)), self.PEN))
+                "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n#define CT_POLY %d\n"
+                % (D, DB, self.KBM, self.REM, self.STAGES, HS, int(os.environ.get("CT_DBG", 0)), self.PEN,
+                   int(os.environ.get("CT_POLY", POLY))))
         src = defs + body
         opts = plan.nvrtc_options(True)
         key = hashlib.sha256((VERSION + src + " ".join(opts)).encode()).hexdigest()[:20]
@@ -271,9 +273,10 @@ class ConvTensorCore:
             return rem, rem            # the main map is never dereferenced
         return capi.tensor_map_2d(abf.data_ptr(), 2, 64 * self.KBM, n, pitch, 64, box_rows, 128), rem
 
-    def run(self, x, y, b, coef, out, stream_obj):
+    def run(self, x, y, b, coef, out, stream_obj, clock_probe=None):
         """x (M, D), y (N, D), b (N, DB) fp32 contiguous CUDA tensors, coef a one-element fp32 tensor;
-        out (M, DB) fp32.  Returns False (nothing written) when the accuracy guard rejects the inputs."""
+        out (M, DB) fp32.  Returns False (nothing written) when the accuracy guard rejects the inputs.
+        ``clock_probe``: optional int64 CUDA tensor of 2 elements receiving (SM cycles, nanoseconds) of CTA 0."""
         import torch
         M, N = x.shape[0], y.shape[0]
         dev = x.device
@@ -315,7 +318,8 @@ class ConvTensorCore:
         dst = out if nchunks == 1 else torch.empty((nchunks, M, self.DB), dtype=torch.float32, device=dev)
         capi.launch(self.fn_conv, stream, (-(-M // BM), nchunks), (THREADS,), self.smem,
                     [map_x, map_xr, map_y, map_yr, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
-                     ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr())])
+                     ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr()),
+                     ptr(clock_probe.data_ptr() if clock_probe is not None else 0)])
         if nchunks > 1:
             capi.launch(self.fn_combine, stream, (-(-(M * self.DB) // 256),), (256,), 0,
                         [i64(M * self.DB), i32(nchunks), ptr(dst.data_ptr()), ptr(out.data_ptr())])

@@ -137,6 +137,98 @@ __device__ __forceinline__ float ct_ex2(float s) {
   return p;
 }
 
+// Experiment kept behind CT_POLY (default 0 = off): of every 8 pairs, CT_POLY get exp2 from a polynomial on the FMA
+// pipe instead of MUFU.EX2, all arithmetic packed (f32x2).  Measured on B200 (M = N = 1e6, D = 8 / 16): off 258 / 277 ms,
+// CT_POLY = 2: 261 / 283 ms with the XU pipe down from 91 % to 67 % busy (ncu) -- with 4 epilogue warps per scheduler
+// and 96 registers per thread the longer dependency chains are not hidden, so the freed MUFU time is not converted.
+#ifndef CT_POLY
+#define CT_POLY 0
+#endif
+#define CT_FASTPATH (CT_W == 1 && CT_POLY > 0)     /* dim b = 1, penalty inside K: packed f32x2 epilogue           */
+
+// ---- packed (f32x2) helpers: one issue slot feeds two pairs ----
+__device__ __forceinline__ u64 ct_pack(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void ct_unpack(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 ct_fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 ct_add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// exp2 of two arguments on the FMA pipe (the MUFU pipe is the bottleneck of this kernel; the FMA pipe is 3/4 idle):
+// round-to-nearest split s = n + f with the 1.5 * 2^23 trick, degree-5 minimax polynomial of 2^f on [-1/2, 1/2]
+// (max relative error 2.1e-7 in fp32 Horner form, the same as ex2.approx's 2 ulp), exponent patched in with an integer
+// multiply-add.  Arguments are clamped to [-125, 126]: below, ex2.approx.ftz would return 0 and this returns < 2.4e-38.
+__device__ __forceinline__ u64 ct_exp2_poly2(u64 s2) {
+  float s0, s1;
+  ct_unpack(s2, s0, s1);
+  s0 = fminf(fmaxf(s0, -125.0f), 126.0f);
+  s1 = fminf(fmaxf(s1, -125.0f), 126.0f);
+  const u64 s = ct_pack(s0, s1);
+  const u64 magic = ct_pack(12582912.0f, 12582912.0f), nmagic = ct_pack(-12582912.0f, -12582912.0f);
+  const u64 t = ct_add2(s, magic);                         // low mantissa bits of t = round(s)
+  const u64 n = ct_add2(t, nmagic);
+  const u64 f = ct_fma2(n, ct_pack(-1.0f, -1.0f), s);      // exact
+  u64 p = ct_pack(1.327647129e-03f, 1.327647129e-03f);
+  p = ct_fma2(p, f, ct_pack(9.675540961e-03f, 9.675540961e-03f));
+  p = ct_fma2(p, f, ct_pack(5.550713092e-02f, 5.550713092e-02f));
+  p = ct_fma2(p, f, ct_pack(2.402212024e-01f, 2.402212024e-01f));
+  p = ct_fma2(p, f, ct_pack(6.931469440e-01f, 6.931469440e-01f));
+  p = ct_fma2(p, f, ct_pack(1.000000119e+00f, 1.000000119e+00f));
+  float p0, p1, t0, t1;
+  ct_unpack(p, p0, p1);
+  ct_unpack(t, t0, t1);
+  const int r0 = __float_as_int(t0) * 0x800000 + __float_as_int(p0);     // IMAD: (n << 23) + bits(p)
+  const int r1 = __float_as_int(t1) * 0x800000 + __float_as_int(p1);
+  return ct_pack(__int_as_float(r0), __int_as_float(r1));
+}
+
+#if CT_FASTPATH
+// dim b = 1: eight columns per step -- 4 FFMA2 (exponents), 8 - CT_POLY MUFU.EX2 + CT_POLY / 2 packed polynomials,
+// 4 FFMA2 (accumulation, two interleaved packed partial sums), 2 broadcast LDS.128
+__device__ __forceinline__ void ct_tile_fast(const float (&u)[CT_HALF], const float* __restrict__ bt, const float c2,
+                                             const float rowc, float (&acc)[CT_DB]) {
+  const u64 c2p = ct_pack(c2, c2), rcp = ct_pack(rowc, rowc);
+  u64 tmp0 = 0ull, tmp1 = 0ull;
+#pragma unroll
+  for (int e8 = 0; e8 < CT_HALF / 8; e8++) {
+    const ulonglong2 ba = *reinterpret_cast<const ulonglong2*>(bt + 8 * e8);         // b of columns 0..3 as two packs
+    const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(bt + 8 * e8 + 4);     // columns 4..7
+    u64 sp[4], pp[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) sp[k] = ct_fma2(ct_pack(u[8 * e8 + 2 * k], u[8 * e8 + 2 * k + 1]), c2p, rcp);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k >= 4 - CT_POLY / 2) {
+        pp[k] = ct_exp2_poly2(sp[k]);
+      } else {
+        float a, b;
+        ct_unpack(sp[k], a, b);
+        pp[k] = ct_pack(ct_ex2(a), ct_ex2(b));
+      }
+    }
+    tmp0 = ct_fma2(pp[0], ba.x, tmp0);
+    tmp1 = ct_fma2(pp[1], ba.y, tmp1);
+    tmp0 = ct_fma2(pp[2], bb.x, tmp0);
+    tmp1 = ct_fma2(pp[3], bb.y, tmp1);
+  }
+  float a0, a1, b0, b1;
+  ct_unpack(tmp0, a0, a1);
+  ct_unpack(tmp1, b0, b1);
+  acc[0] += (a0 + a1) + (b0 + b1);
+}
+#endif
+
 template <bool TAIL>
 __device__ __forceinline__ void ct_tile(const float (&u)[CT_HALF], const float* __restrict__ bt, const float c2,
                                         const float cl, const float rowc, const long long j0, const long long ncol,
@@ -184,7 +276,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
               const __grid_constant__ KtTensorMap map_y, const __grid_constant__ KtTensorMap map_yr,
               const long long nrow, const long long ncol, const long long chunk_cols,
               const float* __restrict__ bpad, const float* __restrict__ xsq, const float* __restrict__ coef,
-              float* __restrict__ out) {
+              float* __restrict__ out, unsigned long long* __restrict__ clk) {
   extern __shared__ unsigned char ct_raw[];
   const u32 raw = kt_smem(ct_raw);
   const u32 base = (raw + 1023u) & ~1023u;                       // swizzle atoms need (up to) 1024-byte alignment
@@ -204,6 +296,13 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
       reinterpret_cast<volatile u32*>(gbase + CT_A_BYTES + CT_STAGES * CT_B_BYTES + CT_HS * CT_H_BYTES + CT_X_BYTES + 520);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // optional clock probe (CTA 0): SM cycles and nanoseconds spent by this CTA -> the SM clock this kernel really ran at
+  // (nvidia-smi reports 1965 MHz while the tensor pipe is busy; cycles / time says ~1.83 GHz)
+  unsigned long long clk_c0 = 0, clk_t0 = 0;
+  if (clk != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(clk_c0));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(clk_t0));
+  }
   const long long row_base = (long long)blockIdx.x * CT_BM;
   // blockIdx.y = column chunk (chunk_cols is a multiple of CT_BN).  CTAs are dispatched x-fastest, so all row blocks
   // of one chunk run together and the chunk's operand rows stay L2-resident while every CTA streams them.
@@ -321,7 +420,11 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
       const float* bt = hb + hslot * (CT_BN * CT_W) + half * (CT_HALF * CT_W);
       const long long j0 = (long long)(t0 + t) * CT_BN + half * CT_HALF;
       if (j0 + CT_HALF > ncol) ct_tile<true>(uu, bt, c2, cl, rowc, j0, ncol, acc);
+#if CT_FASTPATH && CT_DBG == 0
+      else ct_tile_fast(uu, bt, c2, rowc, acc);
+#else
       else ct_tile<false>(uu, bt, c2, cl, rowc, j0, ncol, acc);
+#endif
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
     }
@@ -341,6 +444,13 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
   if (warp == 0) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+  if (clk != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    unsigned long long c1, t1;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c1));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    clk[0] = c1 - clk_c0;
+    clk[1] = t1 - clk_t0;
   }
 }
 
