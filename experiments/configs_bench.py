@@ -81,7 +81,14 @@ def main():
             best = ms if best is None else min(best, ms)
         rate = float(M) * N / (best * 1e-3)
         peak = BOUND[name] * SM * HZ
+        engine = bd.last_launch.get("engine") or "cuda-core"
+        extra = {}
+        if engine == "tcgen05-conv":
+            # the squared distance runs on the tensor cores: the CUDA-core bound becomes 1 MUFU.EX2 per pair (16 / clk / SM)
+            extra = {"cuda_core_roofline_pairs_per_s": peak, "frac_of_cuda_core_roofline": rate / peak}
+            peak = 16.0 * SM * HZ
         print(json.dumps({"case": name, "M": M, "N": N, "dtype": dtype, "ms": best, "pair_evals_per_s": rate,
+                          "engine": engine, **extra,
                           "roofline_pairs_per_s": peak, "frac": rate / peak, "cfg": bd.ks.cfg.key(),
                           "nsplit": bd.last_launch["nsplit"], "regs": bd.last_launch["regs"],
                           "blocks_per_sm": bd.last_launch["blocks_per_sm"]}), flush=True)
