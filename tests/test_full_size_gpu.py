@@ -190,3 +190,34 @@ def test_lse_softmin_full_size(dtype, key, cuda_device):
     ms2 = run(binder(LSE, 4, dtype), dev, M, N, targs[0] + c, *targs[1:])
     got2 = (ms2[:, 0] + ms2[:, 1].log()).cpu().numpy()
     util.assert_close(got2, got + c, dtype, "softmin shift property", rtol=util.RTOL[dtype] * 4)
+
+
+def test_kernel_solve_full_size(cuda_device):
+    """BASELINE configs[4]: KernelSolve (CG) with a Gaussian kernel, N = 10^6, D = 16, fp32.  The matvec runs on the
+    tensor-core path (tcgen05 GEMM + MUFU epilogue, stated tolerance 5e-6); the solution must satisfy the system to the
+    solver's own stopping rule when the residual is re-evaluated with the CUDA-core (reference-order) kernel."""
+    import os
+    from keops_b200.torch import Genred, KernelSolve
+    from keops_b200.torch import kernel_solve as ks_mod
+    dev = cuda_device
+    n, D, alpha, eps = 1000000, 16, 1000.0, 1e-6
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.rand(n, D, generator=g).to(dev)
+    b = torch.randn(n, 1, generator=g).to(dev)
+    gam = torch.tensor([2.0], device=dev)
+    aliases = ["x=Vi(%d)" % D, "y=Vj(%d)" % D, "b=Vj(1)", "g=Pm(1)"]
+    a = KernelSolve("Exp(-g*SqDist(x,y))*b", aliases, "b", axis=1)(x, x, b, gam, alpha=alpha, eps=eps)
+    iters = ks_mod.conjugate_gradient.last_iterations
+    assert 1 <= iters <= 60, iters
+    K = Genred("Exp(-g*SqDist(x,y))*b", aliases, reduction_op="Sum", axis=1)
+    from keops_b200.binder import get_binder
+    bd = get_binder("Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)", [], 4, "float32")
+    bd.genred_pytorch(dev, None, n, n, 0, None, x, x, a, gam)
+    assert bd.last_launch.get("engine") == "tcgen05-conv", bd.last_launch      # these inputs pass the accuracy guard
+    os.environ["KB200_CONV_TC"] = "0"
+    try:
+        res = K(x, x, a, gam) + alpha * a - b
+    finally:
+        os.environ.pop("KB200_CONV_TC", None)
+    rel = float(res.norm() / b.norm())
+    assert rel < 1e-5, rel             # stopping rule: |r| < eps * sqrt(N) = 1e-6 |b|; matvec tolerance adds a few 1e-6
