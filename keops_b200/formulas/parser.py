@@ -124,6 +124,13 @@ class _Interp(ast.NodeVisitor):
             if len(args) != 2:
                 raise FormulaError("%s inside a formula needs (pos, dim)" % name)
             return ir.Var(args[0], args[1], _CATS[name])
+        if name == "Grad" and args and isinstance(args[0], Node):
+            # formula-level symbolic gradient  Grad(f, v, e)  (what LazyTensor.grad prints,
+            # pykeops/pykeops/common/lazy_tensor.py:1918-1936; keopscore/keopscore/formulas/autodiff/Grad.py:4-12)
+            if len(args) != 3:
+                raise FormulaError("Grad(f, v, gradin) expects three arguments")
+            from .autodiff import grad as _grad_formula
+            return _grad_formula(args[0], ir.as_node(args[1]), ir.as_node(args[2]))
         if name in _REDUCTIONS:
             return self._call_reduction(name, args)
         fn = ir.PUBLIC_OPS.get(name)

@@ -16,6 +16,7 @@ numbers, float16, TensorDot / Kron / BSpline / SoftDTW.
 """
 from __future__ import annotations
 
+import copy
 import math
 import re
 from typing import Optional
@@ -214,8 +215,8 @@ class LazyTensor:
         elif opt_arg is not None:
             if opt_pos == "last":
                 r.formula = "%s(%s, %s, %s)" % (operation, self.formula, other.formula, opt_arg)
-            else:
-                r.formula = "%s(%s, %s, %s)" % (operation, opt_arg, self.formula, other.formula)
+            else:                       # "middle" (lazy_tensor.py:557-560)
+                r.formula = "%s(%s, %s, %s)" % (operation, self.formula, opt_arg, other.formula)
         else:
             r.formula = "%s(%s, %s)" % (operation, self.formula, other.formula)
         return r
@@ -658,9 +659,63 @@ class LazyTensor:
             out = out.view(-1)
         return out
 
+    def t(self):
+        """Matrix transposition: the i- and j-variables trade places, ``K.t().shape == (..., N, M, D)``
+        (``pykeops/pykeops/common/lazy_tensor.py:2529-2601``)."""
+        from .cluster import swap_axes
+        r = copy.copy(self)
+        r.ni, r.nj = self.nj, self.ni
+        r.ranges = swap_axes(self.ranges)
+        if getattr(r, "axis", None) in (0, 1):
+            r.axis = 1 - r.axis
+
+        def swap(f):
+            if f is None:
+                return None
+            f = re.sub(r"(Var|VarSymb)\((\d+),(\d+),0\)", r"\1(\2,\3,i)", f)
+            f = re.sub(r"(Var|VarSymb)\((\d+),(\d+),1\)", r"\1(\2,\3,0)", f)
+            return re.sub(r"(Var|VarSymb)\((\d+),(\d+),i\)", r"\1(\2,\3,1)", f)
+
+        r.formula, r.formula2 = swap(self.formula), swap(self.formula2)
+        r.symbolic_variables = tuple((ind, dim, (1 - cat) if cat in (0, 1) else cat)
+                                     for ind, dim, cat in self.symbolic_variables)
+        # variables are labelled by id(): the transposed copy needs ids of its own, otherwise K and K.t() could
+        # not appear in the same formula (the same tensor would be an i- and a j-variable at once)
+        newvars = []
+        for v in self.variables:
+            if isinstance(v, list):
+                newvars.append(v)
+                continue
+            w = v.view(v.shape)
+            newvars.append(w)
+            for attr in ("formula", "formula2"):
+                f = getattr(r, attr)
+                if f is not None:
+                    setattr(r, attr, f.replace("Var(%d," % id(v), "Var(%d," % id(w)))
+        r.variables = tuple(newvars)
+        return r
+
     @property
     def T(self):
-        raise NotImplementedError("[KeOps-B200] LazyTensor.T is not implemented.")
+        """Numpy-friendly alias of :meth:`t` (``lazy_tensor.py:2603-2608``)."""
+        return self.t()
+
+    def matvec(self, v):
+        """``K @ v`` under the name :mod:`scipy.sparse.linalg` expects (``lazy_tensor.py:2610-2631``)."""
+        return self @ v
+
+    def rmatvec(self, v):
+        """``K.T @ v`` (``lazy_tensor.py:2633-2639``)."""
+        return self.T @ v
+
+    def grad(self, other, gradin):
+        """Symbolic gradient: ``x.grad(v, e)`` encodes the adjoint of the differential of ``x`` with respect to the
+        variable ``v``, applied to ``e`` (``lazy_tensor.py:1918-1936``; formula-level ``Grad``)."""
+        return self.binary(gradin, "Grad", dimres=other.ndim, dimcheck="same", opt_arg=other.formula, opt_pos="middle")
+
+    def sinc(self):
+        """``sin(pi x) / (pi x)`` (``lazy_tensor.py:1267-1274``)."""
+        return (math.pi * self).sinxdivx()
 
 
 def Vi(x_or_ind, dim=None):

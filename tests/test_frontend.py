@@ -86,3 +86,33 @@ def test_parser_errors():
                 "Sum_Reduction(__import__('os').system('true'),0)", "Sum_Reduction(Var(0,3,0),2)"):
         with pytest.raises((FormulaError, ValueError)):
             parse_reduction(bad)
+
+
+def test_formula_level_grad_equals_reduction_level_grad():
+    """``Grad(f, v, e)`` inside a formula (what ``LazyTensor.grad`` prints, lazy_tensor.py:1918-1936) is the same symbolic
+    gradient as ``Grad(Sum_Reduction(f), v, e)`` (keopscore/keopscore/formulas/autodiff/Grad.py:4-12)."""
+    from keops_b200.formulas.parser import parse_reduction
+    f = "Exp(-SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,1,1)"
+    a = parse_reduction("Sum_Reduction(Grad(%s, Var(0,3,0), Var(3,1,0)),0)" % f)
+    b = parse_reduction("Grad(Sum_Reduction(%s,0), Var(0,3,0), Var(3,1,0))" % f)
+    assert a.formula is b.formula and a.tagI == b.tagI == 0
+
+
+def test_lazytensor_transposition_bookkeeping():
+    """``K.t()`` swaps the i / j roles, sizes and ranges, and relabels its variables (lazy_tensor.py:2529-2601)."""
+    import re
+    import torch
+    from keops_b200.torch import LazyTensor
+    x, y = torch.randn(5, 3), torch.randn(7, 3)
+    K = (-((LazyTensor(x[:, None, :]) - LazyTensor(y[None, :, :])) ** 2).sum(2)).exp()
+    Kt = K.t()
+    assert K.shape == (5, 7) and Kt.shape == (7, 5) and K.T.shape == (7, 5)
+    cats = lambda f: re.findall(r"Var\((\d+),3,([01])\)", f)
+    (xi, ci), (yj, cj) = cats(K.formula)
+    (xt, cti), (yt, ctj) = cats(Kt.formula)
+    assert (ci, cj, cti, ctj) == ("0", "1", "1", "0")
+    assert {xi, yj}.isdisjoint({xt, yt})                       # fresh ids: K and K.t() can share a formula
+    assert Kt.t().shape == K.shape
+    r = tuple(torch.zeros(1, 2, dtype=torch.int32) + k for k in range(6))
+    K.ranges = r
+    assert [int(t[0, 0]) for t in K.t().ranges] == [3, 4, 5, 0, 1, 2]

@@ -225,3 +225,43 @@ def test_error_behaviour(api, cuda_device):
         api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(4)"], axis=1)(x, x)         # wrong vector size
     with pytest.raises(ValueError):
         api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], axis=1, sum_scheme="nope")
+
+
+def test_lazytensor_transpose_matvec_rmatvec_sinc(api, cuda_device):
+    """``K.t()``, ``K.T``, ``matvec`` / ``rmatvec`` (scipy LinearOperator protocol) and ``sinc``
+    (pykeops/pykeops/common/lazy_tensor.py:2529-2639, 1267-1274; docstring example of ``t``)."""
+    torch.manual_seed(3)
+    dev = cuda_device
+    x, y = torch.randn(300, 3, device=dev), torch.randn(200, 3, device=dev)
+    x_i, y_j = api.LazyTensor(x[:, None, :]), api.LazyTensor(y[None, :, :])
+    K = (-((x_i - y_j) ** 2).sum(2)).exp()
+    Kd = (-((x[:, None, :] - y[None, :, :]) ** 2).sum(2)).exp()
+    assert K.shape == (300, 200) and K.t().shape == (200, 300) and K.T.shape == (200, 300)
+    w, v = torch.rand(300, 2, device=dev), torch.rand(200, 2, device=dev)
+    torch.testing.assert_close(K.t() @ w, Kd.t() @ w, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(K.rmatvec(w), Kd.t() @ w, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(K.matvec(v), Kd @ v, rtol=1e-5, atol=1e-5)
+    # K and K.t() in one formula: the same tensors appear as i- and j-variables
+    xx_i, xx_j = api.LazyTensor(x[:, None, :]), api.LazyTensor(x[None, :, :])
+    S = (-((xx_i - xx_j) ** 2).sum(2)).exp() * (xx_i | xx_j)
+    Sd = (-((x[:, None, :] - x[None, :, :]) ** 2).sum(2)).exp() * (x @ x.t())
+    torch.testing.assert_close((S + S.t()).sum(1).view(-1), (Sd + Sd.t()).sum(1), rtol=1e-4, atol=1e-4)
+    s = ((x_i - y_j) ** 2).sum(2).sinc().sum(1)
+    d2 = ((x[:, None, :] - y[None, :, :]) ** 2).sum(2)
+    torch.testing.assert_close(s.view(-1), torch.sinc(d2).sum(1), rtol=1e-4, atol=1e-4)
+
+
+def test_lazytensor_symbolic_grad(api, cuda_device):
+    """``F.grad(v, e)``: formula-level ``Grad`` (lazy_tensor.py:1918-1936) against torch autograd."""
+    torch.manual_seed(4)
+    dev = cuda_device
+    x = torch.randn(120, 3, device=dev, requires_grad=True)
+    y, b = torch.randn(90, 3, device=dev), torch.randn(90, 1, device=dev)
+    e = torch.randn(120, 1, device=dev)
+    x_i, y_j, b_j, e_i = api.LazyTensor(x.detach()[:, None, :]), api.LazyTensor(y[None, :, :]), \
+        api.LazyTensor(b[None, :, :]), api.LazyTensor(e[:, None, :])
+    F = (-((x_i - y_j) ** 2).sum(2)).exp() * b_j
+    g = F.grad(x_i, e_i).sum(1)                     # sum_j dF_ij/dx_i^T e_i
+    dense = ((-((x[:, None, :] - y[None, :, :]) ** 2).sum(2)).exp() * b.view(1, -1)).sum(1, keepdim=True)
+    (ref,) = torch.autograd.grad(dense, x, e)
+    torch.testing.assert_close(g, ref, rtol=1e-4, atol=1e-4)
