@@ -35,10 +35,12 @@ def main():
     ap.add_argument("--once", action="store_true")
     ap.add_argument("--size", type=int, default=1000000)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--rows", type=int, default=None, help="output rows M (default: --size); the shard of one GPU out of 8 is 125000")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    M = N = args.size
+    N = args.size
+    M = args.rows or N
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def gauss_inputs():

@@ -308,10 +308,22 @@ class LoadKeOpsB200:
         row_dims = {ind: dim for ind, (dim, cat) in self._vars.items() if cat == p.tagI}
         BMAX = 65535
         launches = 0
+        # K-min lists of a split launch are seeded with the K-th smallest value over a column sample (an upper
+        # bound of the final K-th value), so that each split skips the transient of ~K log(n/K) insertions
+        n_seed = 0
+        if (kfam and nbatch == 1 and lk.fn_seeded and any(sg[2] > 1 for sg in segments)
+                and os.environ.get("KB200_KMIN_SEED", "1") != "0"):
+            n_seed = plan.kmin_seed_columns(ncol, ks.cfg.TJ)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             out_flat = out.view(nbatch, nrow * p.dim)
-            for (r0, r1, nsplit, col_chunk) in segments:
+            if n_seed:
+                launches += self._launch_kmin_seeded(lk, stream, dev, tdtype, esz, nrow, ncol, n_seed, segments, out_flat,
+                                                     args, strides, row_dims, rows_per_block)
+                segments_to_run = []
+            else:
+                segments_to_run = segments
+            for (r0, r1, nsplit, col_chunk) in segments_to_run:
                 nseg = r1 - r0
                 for b0 in range(0, nbatch, BMAX):
                     bn = min(BMAX, nbatch - b0)
@@ -328,8 +340,46 @@ class LoadKeOpsB200:
         nsplit, col_chunk = segments[-1][2], segments[-1][3]
         self.last_launch = dict(nsplit=nsplit, col_chunk=col_chunk, grid_x=-(-nrow // rows_per_block),
                                 nbatch=nbatch, regs=lk.regs, blocks_per_sm=lk.blocks_per_sm, launches=launches,
-                                segments=[(a, b, c) for a, b, c, _ in segments])
+                                segments=[(a, b, c) for a, b, c, _ in segments], kmin_seed_columns=n_seed)
         return out
+
+    def _launch_kmin_seeded(self, lk, stream, dev, tdtype, esz, nrow, ncol, n_seed, segments, out_flat, args, strides,
+                            row_dims, rows_per_block):
+        """Sample pass (K-min over the first ``n_seed`` columns, partial-list output) + the row segments through
+        ``kb200_reduce_seeded`` / ``kb200_combine``.  Same arithmetic in both passes, so the sample's own columns
+        re-qualify in the main pass and the result is identical to the unseeded kernel's."""
+        import ctypes as C
+        p, ks = self.params, self.ks
+        i64, ptr, i32 = C.c_longlong, C.c_void_p, C.c_int
+        d, K = self.red.dimF, self.red.K
+        T = ks.cfg.T
+        seedws = torch.empty(nrow * ks.dimpart, dtype=tdtype, device=dev)
+
+        def launch(r0, nseg, ncols, nsplit, col_chunk, out_ptr, ws_ptr, seed_ptr, force_partial):
+            ptrs = [a.data_ptr() + r0 * row_dims.get(k, 0) * esz for k, a in enumerate(args)]
+            params = [i64(nseg), i64(ncols), i64(max(col_chunk, 1)), ptr(out_ptr), ptr(ws_ptr)]
+            params += [ptr(q) for q in ptrs] + [i64(int(st)) for st in strides]
+            params += [ptr(seed_ptr), i64(ks.dimpart), i32(force_partial)]
+            capi.launch(lk.fn_seeded, stream, (-(-nseg // rows_per_block), nsplit, 1), (T,), 0, params)
+
+        # 1. sample pass: one unsplit launch over columns [0, n_seed), lists written in the partial layout
+        launch(0, nrow, n_seed, 1, n_seed, out_flat[0].data_ptr(), seedws.data_ptr(), 0, 1)
+        count = 1
+        # 2. main pass; seed value of (row r, component k) = K-th value of its sample list = seedws[r][(K-1) * 2d + k]
+        for (r0, r1, nsplit, col_chunk) in segments:
+            nseg = r1 - r0
+            ws = torch.empty(nsplit * nseg * ks.dimpart, dtype=tdtype, device=dev) if nsplit > 1 else None
+            seed_ptr = seedws.data_ptr() + (r0 * ks.dimpart + (K - 1) * 2 * d) * esz
+            out_ptr = out_flat[0].data_ptr() + r0 * p.dim * esz
+            launch(r0, nseg, ncol, nsplit, col_chunk, out_ptr, ws.data_ptr() if ws is not None else 0, seed_ptr, 0)
+            count += 1
+            if nsplit > 1:
+                capi.launch(lk.fn_combine, stream, (-(-nseg // 256), 1, 1), (256,), 0,
+                            [i64(nseg), i32(nsplit), ptr(ws.data_ptr()), ptr(out_ptr)])
+                count += 1
+                ws.record_stream(torch.cuda.current_stream(dev))
+        seedws.record_stream(torch.cuda.current_stream(dev))
+        return count
 
     # ---- block-sparse mode -----------------------------------------------------------------------
     def _kernel_ranges(self, device: int) -> plan.LoadedKernel:

@@ -24,7 +24,7 @@ from ..formulas.reductions import Reduction
 from .lower import Lowerer
 from .scalar import Graph, SNode, SV, C, P, I, J, IJ, topo_order
 
-GENERATOR_VERSION = "kb200-gen-3"
+GENERATOR_VERSION = "kb200-gen-4"
 
 _PRELUDE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "kb200_device.cuh")
 _prelude_cache: Optional[str] = None
@@ -376,9 +376,18 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
     arg_decl = "".join(", const real* __restrict__ a%d_" % k for k in range(nargs))
     if not ranges:
         # ---------------- dense kernel ----------------
-        W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
-        W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s)"
-          % (kname, arg_decl, "".join(", const long long bs%d" % k for k in range(nargs))))
+        stride_decl = "".join(", const long long bs%d" % k for k in range(nargs))
+        kfam = kind in ("KMin", "ArgKMin", "KMin_ArgKMin")
+        red_code.seeded = kfam
+        if kfam:
+            # K-min kernels: one device body, two entry points -- kb200_reduce (the C-ABI signature of
+            # kb200_genred_launch) and kb200_reduce_seeded (+ per-row seed thresholds / forced partial output)
+            W("__device__ __forceinline__ void kb200_reduce_body(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s, const real* __restrict__ seed, const long long seed_stride, const int force_partial)"
+              % (arg_decl, stride_decl))
+        else:
+            W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
+            W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s)"
+              % (kname, arg_decl, stride_decl))
         W("{")
         W.indent()
         W("__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
@@ -404,6 +413,18 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
         W.dedent()
         W("}")
         W("")
+        if kfam:
+            call_args = "nrow, ncol, col_chunk, out, partial" + "".join(", a%d_" % k for k in range(nargs)) \
+                + "".join(", bs%d" % k for k in range(nargs))
+            W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
+            W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s)"
+              % (kname, arg_decl, stride_decl))
+            W("{ kb200_reduce_body(%s, nullptr, 0, 0); }" % call_args)
+            W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
+            W("%s_seeded(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s, const real* __restrict__ seed, const long long seed_stride, const int force_partial)"
+              % (kname, arg_decl, stride_decl))
+            W("{ kb200_reduce_body(%s, seed, seed_stride, force_partial); }" % call_args)
+            W("")
         # ---------------- combine kernel (merges split-j partials) ----------------
         red_code.combine_kernel(W, cname)
     else:
@@ -651,6 +672,7 @@ class _ReductionCode:
         else:
             self.dimpart = 2 * red.K * self.dimF
         self.is_max = k in ("Max", "ArgMax", "Max_ArgMax")
+        self.seeded = False        # set by generate(): dense K-min kernels take a per-row seed threshold
 
     # ---- helpers -----------------------------------------------------------------------------
     def _term_expr(self, term, acc: str) -> Optional[str]:
@@ -700,7 +722,13 @@ class _ReductionCode:
             K = self.red.K
             W("real kval[%d][KB_R][%d]; int kidx[%d][KB_R][%d]; V thr[%d];" % (d, K, d, K, d))
             W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { thr[k_] = kb_bcast_v(KB_INF);" % d)
-            W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { kval[k_][q][l_] = KB_INF; kidx[k_][q][l_] = 0; } }" % K)
+            if self.seeded:
+                # seed[r][k_] = an upper bound of the row's final K-th smallest value (K-th smallest over a column
+                # sample, same arithmetic).  The list starts full of placeholders just above it: candidates beyond
+                # the bound are never inserted (no transient of ~K log(n/K) insertions per column split), and every
+                # real candidate (<= bound) orders before every placeholder, here and in kb200_combine.
+                W("  if (seed != nullptr) { KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) thr[k_].l[q] = kb_next_up(seed[rowc[q] * seed_stride + k_]); }")
+            W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { kval[k_][q][l_] = thr[k_].l[q]; kidx[k_][q][l_] = 0; } }" % K)
 
     def tile_begin(self, W):
         if self.kind in ("Sum", "LSE") and self.scheme == "block_sum":
@@ -837,8 +865,10 @@ class _ReductionCode:
         W("const long long r_ = row0 + (long long)q * KB_T;")
         W("if (r_ < %s) {" % row_limit)
         W.indent()
+        final = "(gridDim.y == 1 && !force_partial)" if (self.seeded and allow_partial) else "(gridDim.y == 1)"
+        self._final_cond = final
         if allow_partial:
-            W("real* po = (gridDim.y == 1) ? (out + r_ * %d) : (partial + ((long long)blockIdx.y * nrow + r_) * %d);" % (self.red.dim, self.dimpart))
+            W("real* po = %s ? (out + r_ * %d) : (partial + ((long long)blockIdx.y * nrow + r_) * %d);" % (final, self.red.dim, self.dimpart))
         else:
             W("real* po = out + r_ * %d;" % self.red.dim)
         if k == "Sum":
@@ -871,7 +901,7 @@ class _ReductionCode:
             W("}")
         else:
             K = self.red.K
-            W("if (gridDim.y == 1) {")
+            W("if %s {" % final)
             W.indent()
             for i in range(d):
                 W("KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) {" % K)

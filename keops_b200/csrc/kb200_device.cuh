@@ -146,6 +146,13 @@ KB_DEV real kb_fmin(real a, real b) { return fminf(a, b); }
 #define KB_INF (__int_as_float(0x7f800000))
 #endif
 
+// smallest representable value above s (s itself when it is +inf or NaN): seeds of the K-min lists
+#if KB_F64
+KB_DEV real kb_next_up(real s) { return (s < KB_INF) ? nextafter(s, KB_INF) : s; }
+#else
+KB_DEV real kb_next_up(real s) { return (s < KB_INF) ? nextafterf(s, KB_INF) : s; }
+#endif
+
 // semantics of the comparison / selection family follow keopscore/utils/math_functions.py:112-150
 KB_DEV real kb_sign(real x) { return (x > (real)0) ? (real)1 : ((x < (real)0) ? (real)-1 : (real)0); }
 KB_DEV real kb_step(real x) { return (x < (real)0) ? (real)0 : (real)1; }

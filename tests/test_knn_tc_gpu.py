@@ -86,3 +86,51 @@ def test_tensor_core_kmin_duplicates_and_outliers(cuda_device):
     assert torch.equal(o_tc, o_cc), "overflow rows: %s" % ll.get("overflow_rows")
     row = o_tc[4].long().tolist()
     assert row[0] == 60 and row[1] == 100       # distance 0 twice: the smaller index first
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded split launches of the CUDA-core K-min kernel (binder._launch_kmin_seeded)
+# ---------------------------------------------------------------------------------------------
+def _run_seed(formula, dtype, args, M, N, dev, seed):
+    import torch
+    from keops_b200.binder import get_binder
+    old = {k: os.environ.get(k) for k in ("KB200_KMIN_SEED", "KB200_KNN_TC")}
+    os.environ["KB200_KMIN_SEED"] = "1" if seed else "0"
+    os.environ["KB200_KNN_TC"] = "0"
+    try:
+        bd = get_binder(formula, [], len(args), dtype)
+        out = bd.genred_pytorch(dev, None, M, N, 0, None, *args)
+        torch.cuda.synchronize()
+        return out, dict(bd.last_launch)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("formula,dtype,M,N,D", [
+    ("ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)", "float32", 20000, 300000, 3),
+    ("KMin_ArgKMin_Reduction(Square((Var(0,2,0) - Var(1,2,1))),3,0)", "float32", 9000, 140001, 2),   # dimF = 2
+    ("KMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),5,1)", "float64", 100000, 7000, 3),       # reduction over i
+    ("ArgKMin_Reduction((Var(0,3,0) | Var(1,3,1)),4,0)", "float32", 5000, 70000, 3),                  # negative values
+])
+def test_seeded_kmin_identical_to_unseeded(formula, dtype, M, N, D, cuda_device):
+    """Column splits whose lists start from the K-th smallest value of a column sample must return exactly what
+    the unseeded kernel returns (values and indices, ties included)."""
+    import torch
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    torch.manual_seed(M + N)
+    x, y = torch.randn(M, D, device=cuda_device, dtype=tdt), torch.randn(N, D, device=cuda_device, dtype=tdt)
+    tagI = int(formula.rstrip(")").split(",")[-1])
+    streamed = y if tagI == 0 else x
+    # exact duplicates, inside and outside the sample, so that ties at the seed value occur
+    streamed[5000:5400] = streamed[100:500]
+    streamed[-300:] = streamed[200:500]
+    o_s, ll = _run_seed(formula, dtype, (x, y), M, N, cuda_device, True)
+    assert ll.get("kmin_seed_columns", 0) > 0, ll        # the seeded path really ran
+    o_u, ll2 = _run_seed(formula, dtype, (x, y), M, N, cuda_device, False)
+    assert ll2.get("kmin_seed_columns", 0) == 0 and max(s[2] for s in ll2["segments"]) > 1
+    assert torch.equal(o_s, o_u)
