@@ -289,15 +289,19 @@ class LoadKeOpsB200:
         # (Gaussian conv, M=N=1e6): one long unsplit wave + a split tail = 272 ms vs 262 ms for the uniform
         # 3-way split, whose short CTAs backfill and average out per-SM speed differences.
         tail_split = kfam if os.environ.get("KB200_TAILSPLIT") is None else os.environ["KB200_TAILSPLIT"] == "1"
+        # restart cost of a K-min list, in units of the whole column range: independent splits each replay the
+        # transient of an empty list; splits that share thresholds (kb200_reduce_seeded) pay much less
+        shared = kfam and nbatch == 1 and os.environ.get("KB200_KMIN_SEED", "1") != "0"
+        kpen = float(os.environ.get("KB200_SPLIT_PENALTY", 0.002 if shared else 0.02))   # measured sweep: experiments/knn_seed_sweep.sh
         if nbatch == 1 and p.tag1D2D == 0 and tail_split:
             # restart cost of a K-min list, in tile units: ~ K * log(N/K) insertions per row, each stalling its warp
-            penalty = (0.02 * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0
+            penalty = (kpen * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0
             segments = plan.launch_segments(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
                                             split_penalty_tiles=penalty, ws_limit_bytes=ws_limit)
         else:
             nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
                                                   ws_limit_bytes=ws_limit,
-                                                  split_penalty_tiles=(0.02 * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0)
+                                                  split_penalty_tiles=(kpen * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0)
             if p.tag1D2D == 1 and nsplit == 1 and ncol > 4 * ks.cfg.TJ:
                 # backend="GPU_2D": the caller asked for the split-column scheme explicitly
                 ntiles = -(-ncol // ks.cfg.TJ)
@@ -308,12 +312,11 @@ class LoadKeOpsB200:
         row_dims = {ind: dim for ind, (dim, cat) in self._vars.items() if cat == p.tagI}
         BMAX = 65535
         launches = 0
-        # K-min lists of a split launch are seeded with the K-th smallest value over a column sample (an upper
-        # bound of the final K-th value), so that each split skips the transient of ~K log(n/K) insertions
+        # column splits of a K-min reduction share per-row thresholds through global memory (kb200_reduce_seeded)
         n_seed = 0
         if (kfam and nbatch == 1 and lk.fn_seeded and any(sg[2] > 1 for sg in segments)
                 and os.environ.get("KB200_KMIN_SEED", "1") != "0"):
-            n_seed = plan.kmin_seed_columns(ncol, ks.cfg.TJ)
+            n_seed = 1
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             out_flat = out.view(nbatch, nrow * p.dim)
@@ -345,40 +348,38 @@ class LoadKeOpsB200:
 
     def _launch_kmin_seeded(self, lk, stream, dev, tdtype, esz, nrow, ncol, n_seed, segments, out_flat, args, strides,
                             row_dims, rows_per_block):
-        """Sample pass (K-min over the first ``n_seed`` columns, partial-list output) + the row segments through
-        ``kb200_reduce_seeded`` / ``kb200_combine``.  Same arithmetic in both passes, so the sample's own columns
-        re-qualify in the main pass and the result is identical to the unseeded kernel's."""
+        """Row segments through ``kb200_reduce_seeded`` / ``kb200_combine``: the column splits of a row publish their
+        K-th smallest value to ``shthr[row][component]`` (atomic min, starts at +inf) and skip candidates above the
+        smallest value published so far -- an upper bound of the final K-th value, so the result is exactly the
+        unsplit kernel's while each split is spared the transient of a list that starts empty."""
         import ctypes as C
         p, ks = self.params, self.ks
         i64, ptr, i32 = C.c_longlong, C.c_void_p, C.c_int
-        d, K = self.red.dimF, self.red.K
+        d = self.red.dimF
         T = ks.cfg.T
-        seedws = torch.empty(nrow * ks.dimpart, dtype=tdtype, device=dev)
-
-        def launch(r0, nseg, ncols, nsplit, col_chunk, out_ptr, ws_ptr, seed_ptr, force_partial):
-            ptrs = [a.data_ptr() + r0 * row_dims.get(k, 0) * esz for k, a in enumerate(args)]
-            params = [i64(nseg), i64(ncols), i64(max(col_chunk, 1)), ptr(out_ptr), ptr(ws_ptr)]
-            params += [ptr(q) for q in ptrs] + [i64(int(st)) for st in strides]
-            params += [ptr(seed_ptr), i64(ks.dimpart), i32(force_partial)]
-            capi.launch(lk.fn_seeded, stream, (-(-nseg // rows_per_block), nsplit, 1), (T,), 0, params)
-
-        # 1. sample pass: one unsplit launch over columns [0, n_seed), lists written in the partial layout
-        launch(0, nrow, n_seed, 1, n_seed, out_flat[0].data_ptr(), seedws.data_ptr(), 0, 1)
-        count = 1
-        # 2. main pass; seed value of (row r, component k) = K-th value of its sample list = seedws[r][(K-1) * 2d + k]
+        shthr = torch.full((nrow * d,), float("inf"), dtype=tdtype, device=dev)
+        count = 0
         for (r0, r1, nsplit, col_chunk) in segments:
             nseg = r1 - r0
             ws = torch.empty(nsplit * nseg * ks.dimpart, dtype=tdtype, device=dev) if nsplit > 1 else None
-            seed_ptr = seedws.data_ptr() + (r0 * ks.dimpart + (K - 1) * 2 * d) * esz
             out_ptr = out_flat[0].data_ptr() + r0 * p.dim * esz
-            launch(r0, nseg, ncol, nsplit, col_chunk, out_ptr, ws.data_ptr() if ws is not None else 0, seed_ptr, 0)
+            ptrs = [a.data_ptr() + r0 * row_dims.get(k, 0) * esz for k, a in enumerate(args)]
+            if nsplit == 1:          # nothing to share: the plain entry point (fewer registers)
+                capi.genred_launch(lk.fn_reduce, lk.fn_combine, stream, nseg, ncol, rows_per_block, T, 1,
+                                   max(col_chunk, 1), out_ptr, 0, ptrs, 1, strides)
+                count += 1
+                continue
+            params = [i64(nseg), i64(ncol), i64(max(col_chunk, 1)), ptr(out_ptr), ptr(ws.data_ptr() if ws is not None else 0)]
+            params += [ptr(q) for q in ptrs] + [i64(int(st)) for st in strides]
+            params += [ptr(shthr.data_ptr() + r0 * d * esz), i32(0)]
+            capi.launch(lk.fn_seeded, stream, (-(-nseg // rows_per_block), nsplit, 1), (T,), 0, params)
             count += 1
             if nsplit > 1:
                 capi.launch(lk.fn_combine, stream, (-(-nseg // 256), 1, 1), (256,), 0,
                             [i64(nseg), i32(nsplit), ptr(ws.data_ptr()), ptr(out_ptr)])
                 count += 1
                 ws.record_stream(torch.cuda.current_stream(dev))
-        seedws.record_stream(torch.cuda.current_stream(dev))
+        shthr.record_stream(torch.cuda.current_stream(dev))
         return count
 
     # ---- block-sparse mode -----------------------------------------------------------------------

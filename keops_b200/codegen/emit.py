@@ -24,7 +24,7 @@ from ..formulas.reductions import Reduction
 from .lower import Lowerer
 from .scalar import Graph, SNode, SV, C, P, I, J, IJ, topo_order
 
-GENERATOR_VERSION = "kb200-gen-4"
+GENERATOR_VERSION = "kb200-gen-5"
 
 _PRELUDE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "kb200_device.cuh")
 _prelude_cache: Optional[str] = None
@@ -381,8 +381,8 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
         red_code.seeded = kfam
         if kfam:
             # K-min kernels: one device body, two entry points -- kb200_reduce (the C-ABI signature of
-            # kb200_genred_launch) and kb200_reduce_seeded (+ per-row seed thresholds / forced partial output)
-            W("__device__ __forceinline__ void kb200_reduce_body(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s, const real* __restrict__ seed, const long long seed_stride, const int force_partial)"
+            # kb200_genred_launch) and kb200_reduce_seeded (+ per-row thresholds shared by the column splits)
+            W("__device__ __forceinline__ void kb200_reduce_body(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s, real* __restrict__ shthr, const int force_partial)"
               % (arg_decl, stride_decl))
         else:
             W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
@@ -419,11 +419,11 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
             W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
             W("%s(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s)"
               % (kname, arg_decl, stride_decl))
-            W("{ kb200_reduce_body(%s, nullptr, 0, 0); }" % call_args)
+            W("{ kb200_reduce_body(%s, nullptr, 0); }" % call_args)
             W("extern \"C\" __global__ void __launch_bounds__(KB_T, %d)" % cfg.min_blocks)
-            W("%s_seeded(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s, const real* __restrict__ seed, const long long seed_stride, const int force_partial)"
+            W("%s_seeded(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, real* __restrict__ partial%s%s, real* __restrict__ shthr, const int force_partial)"
               % (kname, arg_decl, stride_decl))
-            W("{ kb200_reduce_body(%s, seed, seed_stride, force_partial); }" % call_args)
+            W("{ kb200_reduce_body(%s, shthr, force_partial); }" % call_args)
             W("")
         # ---------------- combine kernel (merges split-j partials) ----------------
         red_code.combine_kernel(W, cname)
@@ -672,7 +672,7 @@ class _ReductionCode:
         else:
             self.dimpart = 2 * red.K * self.dimF
         self.is_max = k in ("Max", "ArgMax", "Max_ArgMax")
-        self.seeded = False        # set by generate(): dense K-min kernels take a per-row seed threshold
+        self.seeded = False        # set by generate(): dense K-min kernels share per-row thresholds between splits
 
     # ---- helpers -----------------------------------------------------------------------------
     def _term_expr(self, term, acc: str) -> Optional[str]:
@@ -722,13 +722,17 @@ class _ReductionCode:
             K = self.red.K
             W("real kval[%d][KB_R][%d]; int kidx[%d][KB_R][%d]; V thr[%d];" % (d, K, d, K, d))
             W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { thr[k_] = kb_bcast_v(KB_INF);" % d)
+            W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { kval[k_][q][l_] = KB_INF; kidx[k_][q][l_] = 0; } }" % K)
             if self.seeded:
-                # seed[r][k_] = an upper bound of the row's final K-th smallest value (K-th smallest over a column
-                # sample, same arithmetic).  The list starts full of placeholders just above it: candidates beyond
-                # the bound are never inserted (no transient of ~K log(n/K) insertions per column split), and every
-                # real candidate (<= bound) orders before every placeholder, here and in kb200_combine.
-                W("  if (seed != nullptr) { KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) thr[k_].l[q] = kb_next_up(seed[rowc[q] * seed_stride + k_]); }")
-            W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { kval[k_][q][l_] = thr[k_].l[q]; kidx[k_][q][l_] = 0; } }" % K)
+                # Column splits of one row cooperate through shthr[row][k_] (global memory, starts at +inf): the smallest
+                # K-th value any split has published so far -- an upper bound of the row's final K-th smallest value.
+                # Candidates above it are not inserted, so a split does not replay the whole transient of a list that
+                # starts empty (measured: 15 % of the 4-column groups took the insertion path with 7 splits, 3 % unsplit).
+                # Non-strict at the bound (kb_next_up), so ties still reach the merge, which orders them by split.
+                W("real* const shp = (shthr != nullptr) ? (shthr + row0 * %d) : nullptr;" % d)
+                W("if (shp != nullptr) {")
+                W("  KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++)" % d)
+                W("    if (row0 + (long long)q * KB_T < nrow) thr[k_].l[q] = kb_next_up(__ldcg(shp + q * (KB_T * %d) + k_)); }" % d)
 
     def tile_begin(self, W):
         if self.kind in ("Sum", "LSE") and self.scheme == "block_sum":
@@ -805,8 +809,10 @@ class _ReductionCode:
                 fv = f if nd.cls in (I, IJ) else "kb_bcast_v(%s)" % f
                 W("{ const V f_ = %s; bool any_ = false; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (f_.l[q] < thr[%d].l[q]);" % (fv, i))
                 W("  if (any_) { KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) if (f_.l[q] < thr[%d].l[q]) {" % i)
-                W("      kb_kmin_insert<%d, int>(kval[%d][q], kidx[%d][q], f_.l[q], (int)(jt + jr)); thr[%d].l[q] = kval[%d][q][%d]; } } }"
-                  % (K, i, i, i, i, K - 1))
+                # seeded: thr = min(local K-th, shared bound); the local K-th only decreases, so min with the old thr keeps it
+                newthr = ("kb_fmin(kval[%d][q][%d], thr[%d].l[q])" % (i, K - 1, i)) if self.seeded else ("kval[%d][q][%d]" % (i, K - 1))
+                W("      kb_kmin_insert<%d, int>(kval[%d][q], kidx[%d][q], f_.l[q], (int)(jt + jr)); thr[%d].l[q] = %s; } } }"
+                  % (K, i, i, i, newthr))
 
     # ---- grouped evaluation (Min / KMin families) ----------------------------------------------
     def supports_groups(self) -> bool:
@@ -838,14 +844,25 @@ class _ReductionCode:
             W("if (f1_ %s best[k_].l[q]) { best[k_].l[q] = f1_; bidx[k_][q] = (int)(jt + jr + g_); }" % cmp)
         else:
             K = self.red.K
-            W("if (f1_ < thr[k_].l[q]) { kb_kmin_insert<%d, int>(kval[k_][q], kidx[k_][q], f1_, (int)(jt + jr + g_)); thr[k_].l[q] = kval[k_][q][%d]; }"
-              % (K, K - 1))
+            newthr = ("kb_fmin(kval[k_][q][%d], thr[k_].l[q])" % (K - 1)) if self.seeded else ("kval[k_][q][%d]" % (K - 1))
+            W("if (f1_ < thr[k_].l[q]) { kb_kmin_insert<%d, int>(kval[k_][q], kidx[k_][q], f1_, (int)(jt + jr + g_)); thr[k_].l[q] = %s; }"
+              % (K, newthr))
         W.dedent()
         W("}")
         W.dedent()
         W("}")
 
     def tile_end(self, W):
+        if self.seeded:
+            # once per tile: publish this split's K-th value if it beats the shared bound, and tighten the local
+            # threshold with the bound (invariant: thr = min(local K-th value, next_up(bound seen so far)))
+            K, d = self.red.K, self.dimF
+            W("if (shp != nullptr) {")
+            W("  KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++)" % d)
+            W("    if (row0 + (long long)q * KB_T < nrow) {")
+            W("      real* a_ = shp + q * (KB_T * %d) + k_; real s_ = __ldcg(a_);" % d)
+            W("      if (kval[k_][q][%d] < s_) { kb_atomic_min(a_, kval[k_][q][%d]); s_ = kval[k_][q][%d]; }" % (K - 1, K - 1, K - 1))
+            W("      thr[k_].l[q] = kb_fmin(thr[k_].l[q], kb_next_up(s_)); } }")
         if self.kind in ("Sum", "LSE") and self.scheme == "block_sum":
             n = len(self.acc_terms)
             if self.acc64:

@@ -146,11 +146,21 @@ KB_DEV real kb_fmin(real a, real b) { return fminf(a, b); }
 #define KB_INF (__int_as_float(0x7f800000))
 #endif
 
-// smallest representable value above s (s itself when it is +inf or NaN): seeds of the K-min lists
+// smallest representable value above s (s itself when it is +inf or NaN), and an atomic minimum on reals (ordered-integer
+// trick: non-negative floats order like signed ints, negative ones like reversed unsigned ints): the thresholds that the
+// column splits of a K-min reduction share through global memory
 #if KB_F64
 KB_DEV real kb_next_up(real s) { return (s < KB_INF) ? nextafter(s, KB_INF) : s; }
+KB_DEV void kb_atomic_min(real* addr, real v) {
+  if (v >= 0.0) atomicMin(reinterpret_cast<long long*>(addr), __double_as_longlong(v));
+  else atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
 #else
 KB_DEV real kb_next_up(real s) { return (s < KB_INF) ? nextafterf(s, KB_INF) : s; }
+KB_DEV void kb_atomic_min(real* addr, real v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
 #endif
 
 // semantics of the comparison / selection family follow keopscore/utils/math_functions.py:112-150

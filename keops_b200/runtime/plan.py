@@ -156,7 +156,7 @@ class LoadedKernel:
     regs: int
     blocks_per_sm: int
     sm_count: int
-    fn_seeded: int = 0        # K-min kernels: entry point with per-row seed thresholds (kb200_reduce_seeded)
+    fn_seeded: int = 0        # K-min kernels: entry point whose column splits share per-row thresholds (kb200_reduce_seeded)
 
 
 _modules: Dict[Tuple[str, int], LoadedKernel] = {}
@@ -180,18 +180,6 @@ def load_kernel(ks: KernelSource, fast: bool, device: int) -> LoadedKernel:
             lk = LoadedKernel(ks, mod, fr, fc, regs, bps, sm, fs)
             _modules[key] = lk
         return lk
-
-
-def kmin_seed_columns(ncol: int, TJ: int) -> int:
-    """Size of the column sample whose K-th smallest value seeds the K-min lists of a split launch (0 = no seeding).
-
-    A split of n columns that starts from an empty list replays ~K (1 + ln(n / K)) insertions per row; started from
-    the K-th smallest of a sample of n0 columns it needs ~K ln(1 + n / n0).  The sample pass costs n0 / ncol of the
-    work (1 / 64 here) on a grid that does not fill the machine, hence the cap."""
-    if ncol < 65536:
-        return 0
-    n0 = -(-(ncol // 64) // TJ) * TJ
-    return max(4096, min(n0, 32768))
 
 
 def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int, dimpart: int, esz: int,

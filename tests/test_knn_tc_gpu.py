@@ -118,8 +118,8 @@ def _run_seed(formula, dtype, args, M, N, dev, seed):
     ("ArgKMin_Reduction((Var(0,3,0) | Var(1,3,1)),4,0)", "float32", 5000, 70000, 3),                  # negative values
 ])
 def test_seeded_kmin_identical_to_unseeded(formula, dtype, M, N, D, cuda_device):
-    """Column splits whose lists start from the K-th smallest value of a column sample must return exactly what
-    the unseeded kernel returns (values and indices, ties included)."""
+    """Column splits that share per-row thresholds through global memory must return exactly what
+    independent splits return (values and indices, ties included)."""
     import torch
     tdt = torch.float32 if dtype == "float32" else torch.float64
     torch.manual_seed(M + N)
