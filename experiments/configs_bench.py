@@ -23,6 +23,9 @@ KNN3 = "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)"
 KNN64 = "ArgKMin_Reduction(Sum(Square((Var(0,64,0) - Var(1,64,1)))),10,0)"
 LSE = "Max_SumShiftExp_Reduction((Var(0,1,1) - ((Sum(Square((Var(1,3,0) - Var(2,3,1)))) / IntCst(2)) / Var(3,1,2))),0)"
 KS16 = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)"
+REF_KEY = {"gauss_fwd": "gauss_fwd_f32", "gauss_dx": "gauss_dx_f32", "gauss_dy": "gauss_dy_f32", "gauss_db": "gauss_db_f32",
+           "knn_d3": "argkmin10_d3_f32", "knn_d64": "argkmin10_d64_f32", "lse_f32": "lse_f32", "lse_f64": "lse_f64",
+           "ksolve_d16": "gauss16_pm_f32"}
 SM, HZ = 148, 1.965e9
 # pairs / clk / SM bounds
 BOUND = {"gauss_fwd": 16.0, "gauss_dx": 128 / 11.0, "gauss_dy": 128 / 11.0, "gauss_db": 16.0, "knn_d3": 128 / 7.0,
@@ -35,6 +38,7 @@ def main():
     ap.add_argument("--once", action="store_true")
     ap.add_argument("--size", type=int, default=1000000)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--ref", action="store_true", help="also time the reference's own CUDA kernel (oracle/_ref) on a row sample")
     ap.add_argument("--rows", type=int, default=None, help="output rows M (default: --size); the shard of one GPU out of 8 is 125000")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -89,6 +93,29 @@ def main():
             # the squared distance runs on the tensor cores: the CUDA-core bound becomes 1 MUFU.EX2 per pair (16 / clk / SM)
             extra = {"cuda_core_roofline_pairs_per_s": peak, "frac_of_cuda_core_roofline": rate / peak}
             peak = 16.0 * SM * HZ
+        if args.ref:
+            # the reference's generated GpuConv1DOnDevice for the same formula, same GPU, same (full) size
+            from oracle import ref_runner
+            key = REF_KEY.get(name)
+            if key and ref_runner.available():
+                tagI = ref_runner.manifest()[key]["tagI"]
+                rows = M if tagI == 0 else N
+                rc = ref_runner.RefCuda(key, 0)
+                var_cat = {v.params[0]: v.params[2] for v in bd.red.formula.variables()} if hasattr(bd, "red") else {}
+                rargs = [a[:rows].contiguous() if var_cat.get(k) == tagI else a for k, a in enumerate(targs)]
+                nx, ny = (rows, N) if tagI == 0 else (M, rows)
+                ro = rc(rargs, nx, ny)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                flush.zero_()
+                e0.record()
+                rc(rargs, nx, ny, out=ro)
+                e1.record()
+                torch.cuda.synchronize()
+                rms = e0.elapsed_time(e1)
+                rrate = float(nx) * ny / (rms * 1e-3)
+                extra.update({"ref_cuda_pair_evals_per_s": rrate, "ref_cuda_rows": rows, "ref_cuda_ms": rms,
+                              "speedup_vs_ref_cuda": rate / rrate})
         print(json.dumps({"case": name, "M": M, "N": N, "dtype": dtype, "ms": best, "pair_evals_per_s": rate,
                           "engine": engine, **extra,
                           "roofline_pairs_per_s": peak, "frac": rate / peak, "cfg": bd.ks.cfg.key(),
