@@ -15,6 +15,7 @@ different:
 from __future__ import annotations
 
 import hashlib
+import sys
 import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -221,6 +222,12 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
     ``kb200_reduce`` / ``kb200_combine``."""
     if dtype not in ("float32", "float64"):
         raise ValueError("dtype %s is not implemented (float32 / float64 only)" % dtype)
+    # the scalar DAG of a D-dimensional left-to-right sum is D levels deep and the rewriters below are recursive:
+    # make room for the high-dimensional formulas the reference handles in chunk mode (GpuReduc1D_chunks.py)
+    maxdim = max([v.params[1] for v in red.variables()] + [1])
+    need = 2000 + 40 * maxdim
+    if sys.getrecursionlimit() < need:
+        sys.setrecursionlimit(need)
     f64 = dtype == "float64"
     fast = bool(use_fast_math) and not f64
     tagI = red.tagI

@@ -116,3 +116,14 @@ def test_lazytensor_transposition_bookkeeping():
     r = tuple(torch.zeros(1, 2, dtype=torch.int32) + k for k in range(6))
     K.ranges = r
     assert [int(t[0, 0]) for t in K.t().ranges] == [3, 4, 5, 0, 1, 2]
+
+
+def test_high_dimensional_formula_generates():
+    """D = 600: the scalar DAG of a D-term left-to-right sum is D levels deep; the recursive rewriters must cope
+    (the reference handles such formulas in chunk mode, keopscore/keopscore/mapreduce/gpu/GpuReduc1D_chunks.py)."""
+    from keops_b200.formulas.parser import parse_reduction
+    from keops_b200.codegen.emit import generate
+    from keops_b200.runtime import plan
+    red = parse_reduction("Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,600,0),Var(1,600,1)))*Var(2,1,1),0)")
+    ks = generate(red, "float32", 4, plan.default_config(red, "float32"))
+    assert "kb200_reduce" in ks.source and ks.stride >= 600

@@ -79,3 +79,23 @@ def test_option_variants(name, flags, cuda_device):
         check_indices(meta, args, got, ref, lambda s: s % b.red.dimF, name)
     else:
         util.assert_close(got, ref, meta["dtype"], name)
+
+
+@pytest.mark.gpu
+def test_high_dimensional_gaussian_vs_oracle(cuda_device):
+    """D = 300 (beyond the tensor-core path's K <= 128 and the reference's chunk-mode threshold of 100): the generic
+    CUDA-core kernel must still be correct."""
+    import torch
+    from keops_b200.binder import get_binder
+    from oracle import keops_oracle as ko
+    rng = np.random.default_rng(11)
+    D, M, N = 300, 70, 90
+    x = (rng.random((M, D)) / np.sqrt(D)).astype(np.float32)
+    y = (rng.random((N, D)) / np.sqrt(D)).astype(np.float32)
+    b = rng.standard_normal((N, 2)).astype(np.float32)
+    g = np.array([3.0], np.float32)
+    f = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,%d,0),Var(1,%d,1)))*Var(2,2,1),0)" % (D, D)
+    targs = [torch.from_numpy(a).to(cuda_device) for a in (x, y, b, g)]
+    out = get_binder(f, [], 4, "float32").genred_pytorch(cuda_device, None, M, N, 0, None, *targs)
+    torch.cuda.synchronize()
+    util.assert_close(out.cpu().numpy(), ko.genred(f, [], [x, y, b, g], "float32"), "float32", "gaussian D=300")
