@@ -37,9 +37,15 @@ def main():
         binder = get_binder(f, [], 4, "float32")
         for n in sizes:
             x, y, b = torch.rand(n, D, device=dev), torch.rand(n, D, device=dev), torch.randn(n, 1, device=dev)
-            _, t, ll = run(binder, x, y, b, torch.tensor([1.0], device=dev), True, nrep=3)
-            print("CT_ONLY D=%d n=%d DBG=%s STAGES=%s: %.3f ms  %.3e pair/s" % (
-                D, n, os.environ.get("CT_DBG", "0"), os.environ.get("CT_STAGES", "4"), t, n * n / t * 1e3), flush=True)
+            gv = torch.tensor([1.0 if D <= 21 else 16.0 / D], device=dev)
+            o, t, ll = run(binder, x, y, b, gv, True, nrep=3)
+            line = "CT_ONLY D=%d n=%d DBG=%s STAGES=%s: %.3f ms  %.3e pair/s (%s, bound %s)" % (
+                D, n, os.environ.get("CT_DBG", "0"), os.environ.get("CT_STAGES", "4"), t, n * n / t * 1e3,
+                ll.get("engine"), ll.get("error_bound"))
+            if os.environ.get("CT_COMPARE"):
+                o2, t2, _ = run(binder, x, y, b, gv, False, nrep=1)
+                line += "  cuda-core %.1f ms, max diff / max %.2e" % (t2, float((o - o2).abs().max() / o2.abs().max()))
+            print(line, flush=True)
         return
     for D, gval, scale in cases:
         os.environ["KB200_CONV_TC_DMIN"] = "3"

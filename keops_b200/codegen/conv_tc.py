@@ -35,7 +35,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-6"
+VERSION = "conv-tc-7"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
@@ -184,8 +184,8 @@ def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, use_
     D = m[2]
     dmin = int(os.environ.get("KB200_CONV_TC_DMIN", 8))
     kbm, rem, _ = layout(D)
-    if D < dmin or 64 * kbm + rem > 128 or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
-        return None                      # K <= 128: resident x tiles + 4 stages of y tiles in 227 KB of smem
+    if D < dmin or kbm + 1 > HD_MAX_KB or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
+        return None                      # K <= 576 (D <= 95): resident operand rows + the streamed ring in 227 KB of smem
     if smem_bytes(D, m[4]) > 227 * 1024:
         return None
     return m
@@ -200,6 +200,15 @@ def _blocks(total: int) -> Tuple[int, int]:
     return full, (16 if r <= 16 else (32 if r <= 32 else 64))
 
 
+HD_MAX_KB = 9              # resident operand rows of the high-dimensional kernel: 9 x 16 KB
+
+
+def is_hd(D: int) -> bool:
+    """K = 6 D + 3 > 128 bf16 columns (D >= 21 with the penalty columns, D >= 22 always): ``kb200_conv_tc_hd`` -- one
+    128-row block per CTA resident for all of K, the streamed side in 64-column k-blocks accumulated in TMEM."""
+    return 6 * D > 128
+
+
 def layout(D: int) -> Tuple[int, int, int]:
     """``(KBM, REM, PEN)``: the six product blocks (6 D columns) plus the three -|y|^2/2 columns (PEN = 1) whenever
     they fit K <= 128; otherwise (PEN = 0, D = 21) |y|^2 is added in the epilogue.  Measured on B200 at D = 16,
@@ -207,6 +216,8 @@ def layout(D: int) -> Tuple[int, int, int]:
     epilogue's issue slots and LDS bandwidth are scarcer than tensor-core time."""
     with_pen, without = _blocks(6 * D + 3), _blocks(6 * D)
     width = lambda kb: 64 * kb[0] + kb[1]
+    if is_hd(D):                          # high-dimensional kernel: uniform 64-column k-blocks, penalty inside K
+        return -(-(6 * D + 3) // 64) - 1, 64, 1
     if os.environ.get("KB200_CONV_TC_PEN") in ("0", "1"):
         pen = int(os.environ["KB200_CONV_TC_PEN"])
         return (with_pen if pen else without) + (pen,)
@@ -218,6 +229,8 @@ def layout(D: int) -> Tuple[int, int, int]:
 def smem_bytes(D: int, DB: int, stages: int = STAGES) -> int:
     """dynamic shared memory of kb200_conv_tc (CT_SMEM_BYTES in the kernel)"""
     kbm, rem, pen = layout(D)
+    if is_hd(D):                         # HD_SMEM_BYTES
+        return 1024 + (kbm + 1) * 16384 + stages * 16384 + HS * BN * DB * 4 + 3 * 128 * DB * 4 + 640
     blk = lambda rows: kbm * rows * 128 + rows * rem * 2       # one operand block, all of K
     return 1024 + 2 * blk(128) + stages * blk(BN) + HS * BN * (DB + 1 - pen) * 4 + BM * DB * 4 + 640
 
@@ -228,6 +241,7 @@ class ConvTensorCore:
     def __init__(self, D: int, DB: int, device: int):
         self.D, self.DB = D, DB
         self.KBM, self.REM, self.PEN = layout(D)
+        self.hd = is_hd(D)
         self.DPG = 64 * self.KBM + self.REM
         self.W = DB + 1 - self.PEN                   # floats per column of the b tile
         with open(_COMMON_PATH) as f:
@@ -262,7 +276,7 @@ class ConvTensorCore:
         if device >= 0:
             self.module = capi.Module(cubin, device)
             self.fn_prep = self.module.function("kb200_conv_prep")
-            self.fn_conv = self.module.function("kb200_conv_tc")
+            self.fn_conv = self.module.function("kb200_conv_tc_hd" if self.hd else "kb200_conv_tc")
             self.fn_combine = self.module.function("kb200_conv_combine")
             capi.set_max_dynamic_smem(self.fn_conv, self.smem)
 
@@ -306,8 +320,13 @@ class ConvTensorCore:
             self.last_bound = float(bound.item())
             if not self.last_bound <= tol:          # also catches NaN / inf inputs
                 return False
-        map_y, map_yr = self._maps(ybf, N, BN)
-        map_x, map_xr = self._maps(xbf, M, 128)
+        if self.hd:
+            pitch = self.DPG * 2
+            map_y = capi.tensor_map_2d(ybf.data_ptr(), 2, self.DPG, N, pitch, 64, BN, 128)
+            map_x = capi.tensor_map_2d(xbf.data_ptr(), 2, self.DPG, M, pitch, 64, 128, 128)
+        else:
+            map_y, map_yr = self._maps(ybf, N, BN)
+            map_x, map_xr = self._maps(xbf, M, 128)
         # column chunks: every CTA streams all operand rows of its chunk, so a chunk must stay L2-resident
         # (126 MB L2; measured at M = N = 1e6, D = 16: one 256 MB chunk 288 ms, L2-sized chunks %s)
         chunk_bytes = int(os.environ.get("KB200_CONV_TC_CHUNK_MB", CHUNK_MB)) << 20
@@ -316,16 +335,21 @@ class ConvTensorCore:
         tiles_per_chunk = -(-ntiles // nchunks)                   # balanced
         nchunks = -(-ntiles // tiles_per_chunk)
         dst = out if nchunks == 1 else torch.empty((nchunks, M, self.DB), dtype=torch.float32, device=dev)
-        capi.launch(self.fn_conv, stream, (-(-M // BM), nchunks), (THREADS,), self.smem,
-                    [map_x, map_xr, map_y, map_yr, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
-                     ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr()),
-                     ptr(clock_probe.data_ptr() if clock_probe is not None else 0)])
+        if self.hd:
+            capi.launch(self.fn_conv, stream, (-(-M // 128), nchunks), (THREADS,), self.smem,
+                        [map_x, map_y, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
+                         ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr())])
+        else:
+            capi.launch(self.fn_conv, stream, (-(-M // BM), nchunks), (THREADS,), self.smem,
+                        [map_x, map_xr, map_y, map_yr, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
+                         ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr()),
+                         ptr(clock_probe.data_ptr() if clock_probe is not None else 0)])
         if nchunks > 1:
             capi.launch(self.fn_combine, stream, (-(-(M * self.DB) // 256),), (256,), 0,
                         [i64(M * self.DB), i32(nchunks), ptr(dst.data_ptr()), ptr(out.data_ptr())])
         for t in (shift, ybf, xbf, ysq, xsq, bpad, coef, dst):
             t.record_stream(stream_obj)
-        self.last = dict(ntiles=ntiles, ctas=-(-M // BM) * nchunks, nchunks=nchunks)
+        self.last = dict(ntiles=ntiles, ctas=-(-M // (128 if self.hd else BM)) * nchunks, nchunks=nchunks)
         return True
 
 

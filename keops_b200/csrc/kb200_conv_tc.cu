@@ -229,15 +229,15 @@ __device__ __forceinline__ void ct_tile_fast(const float (&u)[CT_HALF], const fl
 }
 #endif
 
-template <bool TAIL>
-__device__ __forceinline__ void ct_tile(const float (&u)[CT_HALF], const float* __restrict__ bt, const float c2,
+template <bool TAIL, int NC>
+__device__ __forceinline__ void ct_tile(const float (&u)[NC], const float* __restrict__ bt, const float c2,
                                         const float cl, const float rowc, const long long j0, const long long ncol,
                                         float (&acc)[CT_DB]) {
   float tmp[2][CT_DB];                                // two interleaved partial sums per component
 #pragma unroll
   for (int d = 0; d < CT_DB; d++) tmp[0][d] = tmp[1][d] = 0.0f;
 #pragma unroll
-  for (int e4 = 0; e4 < CT_HALF / 4; e4++) {
+  for (int e4 = 0; e4 < NC / 4; e4++) {
     // the four b-tile rows of these columns: 4 * CT_W consecutive floats, read with broadcast LDS.128
     float bv[4 * CT_W];
     const float4* b4 = reinterpret_cast<const float4*>(bt + 4 * e4 * CT_W);
@@ -419,11 +419,11 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
       kt_mbar_wait(bHFull + 8 * hslot, (t / CT_HS) & 1);
       const float* bt = hb + hslot * (CT_BN * CT_W) + half * (CT_HALF * CT_W);
       const long long j0 = (long long)(t0 + t) * CT_BN + half * CT_HALF;
-      if (j0 + CT_HALF > ncol) ct_tile<true>(uu, bt, c2, cl, rowc, j0, ncol, acc);
+      if (j0 + CT_HALF > ncol) ct_tile<true, CT_HALF>(uu, bt, c2, cl, rowc, j0, ncol, acc);
 #if CT_FASTPATH && CT_DBG == 0
       else ct_tile_fast(uu, bt, c2, rowc, acc);
 #else
-      else ct_tile<false>(uu, bt, c2, cl, rowc, j0, ncol, acc);
+      else ct_tile<false, CT_HALF>(uu, bt, c2, cl, rowc, j0, ncol, acc);
 #endif
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
@@ -451,6 +451,169 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     clk[0] = c1 - clk_c0;
     clk[1] = t1 - clk_t0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// high-dimensional variant (K = 6 D + 3 > 128, up to 576 bf16 columns: D <= 95)
+//   One CTA = ONE 128-row block whose operand rows stay resident for all of K (CT_KB 64-column blocks, 16 KB each);
+//   the streamed side goes through the smem ring one 128-column x 64-K block at a time, and the MMA warp accumulates
+//   a tile over the K blocks in TMEM before committing it to the epilogue.  Per pair this moves 2 * CT_KB * 64 / 128
+//   bytes from L2 (the 256-row kernel above would have to re-stream its operand rows as well: 1.5 x more).
+//   Epilogue: 16 warps, a thread = one row x one 32-column quarter of every tile.
+// ------------------------------------------------------------------------------------------------
+#ifndef CT_KB
+#define CT_KB (CT_KBM + 1)                    /* only meaningful when CT_REM == 64                               */
+#endif
+#define HD_BLK 16384                          /* 128 rows x 64 bf16                                              */
+#define HD_A_BYTES (CT_KB * HD_BLK)
+#define HD_QUART (CT_BN / 4)
+#define HD_X_BYTES (3 * 128 * CT_DB * 4)      /* sums of column quarters 1..3, added to quarter 0 at the end      */
+#define HD_SMEM_BYTES (1024 + HD_A_BYTES + CT_STAGES * HD_BLK + CT_HS * CT_H_BYTES + HD_X_BYTES + 640) /* mirrored in conv_tc.py */
+
+extern "C" __global__ void __launch_bounds__(CT_THREADS, 1)
+kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_y,
+                 const long long nrow, const long long ncol, const long long chunk_cols,
+                 const float* __restrict__ bpad, const float* __restrict__ xsq, const float* __restrict__ coef,
+                 float* __restrict__ out) {
+  extern __shared__ unsigned char ct_raw[];
+  const u32 raw = kt_smem(ct_raw);
+  const u32 base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = ct_raw + (base - raw);
+  const u32 sA = base;                                           // CT_KB resident k-blocks of this CTA's 128 rows
+  const u32 sB = sA + HD_A_BYTES;                                // ring of streamed k-blocks
+  const u32 sH = sB + CT_STAGES * HD_BLK;                        // ring of b tiles
+  const float* hb = reinterpret_cast<const float*>(gbase + HD_A_BYTES + CT_STAGES * HD_BLK);
+  const u32 sX = sH + CT_HS * CT_H_BYTES;
+  float* xch = reinterpret_cast<float*>(gbase + HD_A_BYTES + CT_STAGES * HD_BLK + CT_HS * CT_H_BYTES);
+  const u32 sBar = sX + HD_X_BYTES;
+  // barriers: full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @192, hfull[16] @256, hempty[16] @384, afull @512, tmem @520
+  const u32 bFull = sBar, bEmpty = sBar + 64, bTFull = sBar + 128, bTEmpty = sBar + 192, bAFull = sBar + 512;
+  const u32 bHFull = sBar + 256, bHEmpty = sBar + 384;
+  volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(
+      gbase + HD_A_BYTES + CT_STAGES * HD_BLK + CT_HS * CT_H_BYTES + HD_X_BYTES + 520);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row_base = (long long)blockIdx.x * 128;
+  const long long col0 = (long long)blockIdx.y * chunk_cols;
+  const long long col1 = (col0 + chunk_cols < ncol) ? col0 + chunk_cols : ncol;
+  const int t0 = (int)(col0 / CT_BN);
+  const int ntiles = (int)((col1 - col0 + CT_BN - 1) / CT_BN);
+  out += (long long)blockIdx.y * nrow * CT_DB;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
+    for (int b = 0; b < CT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, CT_EPI_WARPS); }
+    for (int h = 0; h < CT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, CT_EPI_WARPS); }
+    kt_mbar_init(bAFull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sBar + 520), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  kt_fence_before();
+  __syncthreads();
+  kt_fence_after();
+  const u32 tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (kt_elect()) {
+      kt_mbar_expect_tx(bAFull, HD_A_BYTES);
+      for (int kb = 0; kb < CT_KB; kb++) kt_tma_2d(sA + kb * HD_BLK, &map_x, kb * 64, (int)row_base, bAFull);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int t = 0; t < ntiles; t++) {
+      const int h = t % CT_HS;
+      kt_mbar_wait(bHEmpty + 8 * h, ((t / CT_HS) & 1) ^ 1);
+      if (kt_elect()) {
+        kt_mbar_expect_tx(bHFull + 8 * h, CT_H_BYTES);
+        kt_bulk_1d(sH + h * CT_H_BYTES, bpad + (long long)(t0 + t) * CT_BN * CT_W, CT_H_BYTES, bHFull + 8 * h);
+      }
+      __syncwarp();
+      for (int kb = 0; kb < CT_KB; kb++, it++) {
+        const int s = it % CT_STAGES;
+        kt_mbar_wait(bEmpty + 8 * s, ((it / CT_STAGES) & 1) ^ 1);
+        if (kt_elect()) {
+          kt_mbar_expect_tx(bFull + 8 * s, HD_BLK);
+          kt_tma_2d(sB + s * HD_BLK, &map_y, kb * 64, (t0 + t) * CT_BN, bFull + 8 * s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: a tile accumulates over the CT_KB k-blocks =====================
+    kt_mbar_wait(bAFull, 0);
+    int it = 0;
+    for (int t = 0; t < ntiles; t++) {
+      const int buf = t % CT_NBUF;
+      kt_mbar_wait(bTEmpty + 8 * buf, ((t / CT_NBUF) & 1) ^ 1);
+      kt_fence_after();
+      for (int kb = 0; kb < CT_KB; kb++, it++) {
+        const int s = it % CT_STAGES;
+        kt_mbar_wait(bFull + 8 * s, (it / CT_STAGES) & 1);
+        kt_fence_after();
+        if (kt_elect()) {
+          const u32 d = tmem + (u32)(buf * CT_BN);
+          const u64 ad = kt_smem_desc(sA + kb * HD_BLK, 128);
+          const u64 bd = kt_smem_desc(sB + s * HD_BLK, 128);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), CT_IDESC, (u32)((kb | k) != 0));
+          kt_mma_commit(bEmpty + 8 * s);                   // the ring slot may be refilled once these MMAs have read it
+          if (kb == CT_KB - 1) kt_mma_commit(bTFull + 8 * buf);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: one thread per (row, 32-column quarter) =====================
+    const int ew = warp - 2, q = warp & 3, part = ew >> 2;
+    const int rloc = q * 32 + lane;
+    const long long i = row_base + rloc;
+    const bool live = i < nrow;
+    const float cl = coef[0] * CT_LOG2E;
+    const float c2 = -2.0f * cl;
+    const float rowc = live ? cl * xsq[i] : 0.0f;
+    float acc[CT_DB];
+#pragma unroll
+    for (int d = 0; d < CT_DB; d++) acc[d] = 0.0f;
+    for (int t = 0; t < ntiles; t++) {
+      const int buf = t % CT_NBUF, hslot = t % CT_HS;
+      kt_mbar_wait(bTFull + 8 * buf, (t / CT_NBUF) & 1);
+      kt_fence_after();
+      float uu[HD_QUART];
+      kt_tmem_ld32_nowait(tmem + ((u32)(q * 32) << 16) + (u32)(buf * CT_BN + part * HD_QUART), uu);
+      kt_tmem_wait_ld();
+      kt_fence_before();
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * buf);
+      kt_mbar_wait(bHFull + 8 * hslot, (t / CT_HS) & 1);
+      const float* bt = hb + hslot * (CT_BN * CT_W) + part * (HD_QUART * CT_W);
+      const long long j0 = (long long)(t0 + t) * CT_BN + part * HD_QUART;
+      if (j0 + HD_QUART > ncol) ct_tile<true, HD_QUART>(uu, bt, c2, cl, rowc, j0, ncol, acc);
+      else ct_tile<false, HD_QUART>(uu, bt, c2, cl, rowc, j0, ncol, acc);
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
+    }
+    if (part > 0) {
+#pragma unroll
+      for (int d = 0; d < CT_DB; d++) xch[((part - 1) * 128 + rloc) * CT_DB + d] = acc[d];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * CT_EPI_WARPS) : "memory");
+    if (part == 0 && live) {
+#pragma unroll
+      for (int d = 0; d < CT_DB; d++)
+        out[i * CT_DB + d] = ((acc[d] + xch[rloc * CT_DB + d]) + xch[(128 + rloc) * CT_DB + d]) + xch[(256 + rloc) * CT_DB + d];
+    }
+  }
+  kt_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 

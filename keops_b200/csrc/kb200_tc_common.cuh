@@ -112,6 +112,22 @@ __device__ __forceinline__ void kt_tmem_ld64_nowait(u32 taddr, float* v) {
 #pragma unroll
   for (int e = 0; e < 64; e++) v[e] = __uint_as_float(r[e]);
 }
+// 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void kt_tmem_ld32_nowait(u32 taddr, float* v) {
+  u32 r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int e = 0; e < 32; e++) v[e] = __uint_as_float(r[e]);
+}
 __device__ __forceinline__ void kt_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile whose rows are `row_bytes` (32 / 64 / 128) wide and swizzled at that width: rows are

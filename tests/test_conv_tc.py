@@ -59,8 +59,11 @@ def test_layout_and_eligibility():
     assert conv_tc.eligible(red, "float32", 100000, 100000, 1, True, "kahan_scheme") is None
     g3 = parse_reduction("Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,1,1)),0)")
     assert conv_tc.eligible(g3, "float32", 100000, 100000, 1, True) is None        # D = 3 stays on the CUDA cores
-    g22 = parse_reduction(KS.replace("16", "22"))
-    assert conv_tc.eligible(g22, "float32", 100000, 100000, 1, True) is None       # K > 128 does not fit
+    g64 = parse_reduction(KS.replace("16", "64"))
+    assert conv_tc.is_hd(64) and conv_tc.layout(64) == (6, 64, 1)                  # 387 columns -> 7 k-blocks of 64
+    assert conv_tc.eligible(g64, "float32", 100000, 100000, 1, True) is not None   # high-dimensional kernel
+    g96 = parse_reduction(KS.replace("16", "96"))
+    assert conv_tc.eligible(g96, "float32", 100000, 100000, 1, True) is None       # K > 576: rows no longer resident
     assert conv_tc.eligible(parse_reduction(KS.replace("Var(2,1,1)", "Var(2,8,1)")), "float32", 100000, 100000, 1, True) is None  # b ring too wide for smem
     for D, DB in ((8, 1), (16, 1), (16, 4), (21, 4)):
         assert conv_tc.smem_bytes(D, DB) <= 227 * 1024
@@ -107,7 +110,10 @@ CASES = [
     (13, 2, 8300, 5000, 0, "-IntCst(2)*"),            # constant coefficient, K = 64 + 16
     (20, 1, 8192, 3000, 0, "-Var(3,1,2)*Var(3,1,2)*"),
     (16, 2, 5000, 9000, 1, "-Var(3,1,2)*"),           # reduction over i
-    (21, 4, 8192, 2000, 0, "-Var(3,1,2)*"),           # widest supported operand rows
+    (21, 4, 8192, 2000, 0, "-Var(3,1,2)*"),           # widest operand rows of the 256-row kernel
+    (22, 1, 8200, 3001, 0, "-Var(3,1,2)*"),           # high-dimensional kernel (kb200_conv_tc_hd): 3 k-blocks
+    (64, 2, 8192, 2500, 0, "-Var(3,1,2)*"),           # 7 k-blocks, vector b
+    (95, 1, 4000, 8300, 1, "-Var(3,1,2)*"),           # 9 k-blocks (the maximum), reduction over i
 ]
 
 
@@ -119,7 +125,7 @@ def test_tensor_core_conv_matches_cuda_core(D, DB, nx, ny, tagI, coef, cuda_devi
     dev = cuda_device
     x, y = torch.rand(nx, D, device=dev), torch.rand(ny, D, device=dev)
     b = torch.randn((ny if tagI == 0 else nx), DB, device=dev)
-    g = torch.tensor([0.7], device=dev)
+    g = torch.tensor([0.7 if D <= 21 else 8.0 / D], device=dev)      # keep exp(-g |x-y|^2) away from underflow
     f = "Sum_Reduction(Exp(%sSqDist(Var(0,%d,0),Var(1,%d,1)))*Var(2,%d,%d),%d)" % (coef, D, D, DB, 1 - tagI, tagI)
     o_tc, ll = _run(f, 4, (x, y, b, g), nx, ny, dev, True)
     assert ll.get("engine") == "tcgen05-conv", ll         # the tensor-core kernels really ran
