@@ -23,7 +23,6 @@ CUDA-core kernel to 4e-6 of the largest output.  ``KB200_CONV_TC=0`` disables th
 from __future__ import annotations
 
 import ctypes as C
-import hashlib
 import os
 import threading
 from typing import Callable, Dict, Optional, Tuple
@@ -254,19 +253,7 @@ class ConvTensorCore:
                 % (D, DB, self.KBM, self.REM, self.STAGES, HS, int(os.environ.get("CT_DBG", 0)), self.PEN,
                    int(os.environ.get("CT_POLY", POLY))))
         src = defs + body
-        opts = plan.nvrtc_options(True)
-        key = hashlib.sha256((VERSION + src + " ".join(opts)).encode()).hexdigest()[:20]
-        path = os.path.join(plan.cache_dir(), "kb200_convtc_%s.cubin" % key)
-        if os.path.exists(path):
-            with open(path, "rb") as f:
-                cubin = f.read()
-        else:
-            cubin = capi.compile_to_cubin(src, opts, name="kb200_convtc_%s.cu" % key)
-            tmp = path + ".tmp%d" % os.getpid()
-            with open(tmp, "wb") as f:
-                f.write(cubin)
-            os.replace(tmp, path)
-        self.cubin = cubin
+        self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(True), "kb200_convtc", VERSION)
         self.smem = smem_bytes(D, DB, self.STAGES)
         if self.smem > 227 * 1024:
             raise ValueError("conv_tc: D = %d, dim b = %d needs %d bytes of shared memory" % (D, DB, self.smem))

@@ -14,7 +14,6 @@ rows whose candidate list overflowed are recomputed by the caller with the CUDA-
 from __future__ import annotations
 
 import ctypes as C
-import hashlib
 import os
 import threading
 from typing import Dict, Optional, Tuple
@@ -88,19 +87,7 @@ class KnnTensorCore:
         defs += "#define KT_BN %d\n#define KT_STAGES %d\n#define KT_DBG %d\n" % (self.BN, self.STAGES, int(os.environ.get("KT_DBG", 0)))
         defs += "#define KT_SPIN %d\n" % int(os.environ.get("KT_SPIN", 0))
         src = defs + body
-        opts = plan.nvrtc_options(fast)
-        key = hashlib.sha256((VERSION + src + " ".join(opts)).encode()).hexdigest()[:20]
-        path = os.path.join(plan.cache_dir(), "kb200_knntc_%s.cubin" % key)
-        if os.path.exists(path):
-            with open(path, "rb") as f:
-                cubin = f.read()
-        else:
-            cubin = capi.compile_to_cubin(src, opts, name="kb200_knntc_%s.cu" % key)
-            tmp = path + ".tmp%d" % os.getpid()
-            with open(tmp, "wb") as f:
-                f.write(cubin)
-            os.replace(tmp, path)
-        self.cubin = cubin
+        self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(fast), "kb200_knntc", VERSION)
         blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K
         self.smem = 1024 + 2 * blk(128) + self.STAGES * blk(self.BN) + HS * self.BN * 4 + 640
         self.smem = max(self.smem, 120 * 1024)     # one CTA per SM: each CTA allocates all 512 TMEM columns

@@ -68,6 +68,23 @@ def nvrtc_options(fast: bool) -> List[str]:
     return opts
 
 
+def compile_cached(source: str, options: Sequence[str], prefix: str, version: str) -> bytes:
+    """NVRTC -> sm_100a cubin for a hand-written kernel source, cached on disk by content hash (same in-tree cache
+    as the generated kernels, so that cubins cross-compiled by ``build()`` travel with the repository snapshot)."""
+    key = hashlib.sha256((version + source + " ".join(options)).encode()).hexdigest()[:20]
+    path = os.path.join(cache_dir(), "%s_%s.cubin" % (prefix, key))
+    with _lock:
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                return f.read()
+        cubin = capi.compile_to_cubin(source, list(options), name="%s_%s.cu" % (prefix, key))
+        tmp = path + ".tmp%d" % os.getpid()
+        with open(tmp, "wb") as f:
+            f.write(cubin)
+        os.replace(tmp, path)
+        return cubin
+
+
 def get_cubin(ks: KernelSource, fast: bool) -> bytes:
     opts = nvrtc_options(fast)
     key = hashlib.sha256((ks.hash + "|" + " ".join(opts)).encode()).hexdigest()[:20]
