@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--size", type=int, default=1000000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--ref", action="store_true", help="also time the reference's own CUDA kernel (oracle/_ref) on a row sample")
+    ap.add_argument("--cpu", action="store_true", help="also time the reference's own CPU code (oracle/_ref, OpenMP, all host cores) on a bounded row sample")
     ap.add_argument("--rows", type=int, default=None, help="output rows M (default: --size); the shard of one GPU out of 8 is 125000")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -116,6 +117,30 @@ def main():
                 rrate = float(nx) * ny / (rms * 1e-3)
                 extra.update({"ref_cuda_pair_evals_per_s": rrate, "ref_cuda_rows": rows, "ref_cuda_ms": rms,
                               "speedup_vs_ref_cuda": rate / rrate})
+        if args.cpu:
+            # the reference's generated CpuReduc code (g++ -O3 -fopenmp) on the host cores of this box, on a bounded sample
+            # of output rows against all columns (~2 s of CPU work per case; 1e12 pairs would take minutes to hours)
+            import time
+            from oracle import ref_runner
+            key = REF_KEY.get(name)
+            if key and ref_runner.available():
+                tagI = ref_runner.manifest()[key]["tagI"]
+                var_cat = {v.params[0]: v.params[2] for v in bd.red.formula.variables()}
+                host = [a.cpu().numpy() for a in targs]
+
+                def cpu_run(rows):
+                    cargs = [a[:rows] if var_cat.get(k) == tagI else a for k, a in enumerate(host)]
+                    nx, ny = (rows, N) if tagI == 0 else (M, rows)
+                    t0 = time.perf_counter()
+                    ref_runner.run_cpu(key, cargs, nx, ny)
+                    return time.perf_counter() - t0, float(nx) * ny
+                cores = os.cpu_count() or 1
+                cpu_run(cores)                                  # warm-up (thread pool)
+                dt, pairs = cpu_run(8 * cores)
+                rows = int(max(8 * cores, min(M if tagI == 0 else N, 2.0 * (8 * cores) / max(dt, 1e-6)) // cores * cores))
+                dt, pairs = cpu_run(rows)
+                extra.update({"ref_cpu_pair_evals_per_s": pairs / dt, "ref_cpu_rows": rows, "ref_cpu_cores": cores,
+                              "speedup_vs_ref_cpu": rate / (pairs / dt)})
         print(json.dumps({"case": name, "M": M, "N": N, "dtype": dtype, "ms": best, "pair_evals_per_s": rate,
                           "engine": engine, **extra,
                           "roofline_pairs_per_s": peak, "frac": rate / peak, "cfg": bd.ks.cfg.key(),
