@@ -34,7 +34,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-7"
+VERSION = "conv-tc-8"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
@@ -183,8 +183,8 @@ def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, use_
     D = m[2]
     dmin = int(os.environ.get("KB200_CONV_TC_DMIN", 8))
     kbm, rem, _ = layout(D)
-    if D < dmin or kbm + 1 > HD_MAX_KB or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
-        return None                      # K <= 576 (D <= 95): resident operand rows + the streamed ring in 227 KB of smem
+    if D < dmin or D > HD_MAX_D or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
+        return None
     if smem_bytes(D, m[4]) > 227 * 1024:
         return None
     return m
@@ -199,7 +199,8 @@ def _blocks(total: int) -> Tuple[int, int]:
     return full, (16 if r <= 16 else (32 if r <= 32 else 64))
 
 
-HD_MAX_KB = 9              # resident operand rows of the high-dimensional kernel: 9 x 16 KB
+HD_MAX_KB = 9              # resident operand rows of the high-dimensional kernel: 9 x 16 KB (D <= 95); beyond, both sides stream
+HD_MAX_D = 2048            # operand rows of 6 D + 3 bf16 columns: 24 KB per point at D = 2048
 
 
 def is_hd(D: int) -> bool:
@@ -229,6 +230,8 @@ def smem_bytes(D: int, DB: int, stages: int = STAGES) -> int:
     """dynamic shared memory of kb200_conv_tc (CT_SMEM_BYTES in the kernel)"""
     kbm, rem, pen = layout(D)
     if is_hd(D):                         # HD_SMEM_BYTES
+        if kbm + 1 > HD_MAX_KB:          # CT_ASTREAM: both operands go through the ring
+            return 1024 + stages * 32768 + HS * BN * DB * 4 + 3 * 128 * DB * 4 + 640
         return 1024 + (kbm + 1) * 16384 + stages * 16384 + HS * BN * DB * 4 + 3 * 128 * DB * 4 + 640
     blk = lambda rows: kbm * rows * 128 + rows * rem * 2       # one operand block, all of K
     return 1024 + 2 * blk(128) + stages * blk(BN) + HS * BN * (DB + 1 - pen) * 4 + BM * DB * 4 + 640
@@ -249,9 +252,9 @@ class ConvTensorCore:
             body += f.read()
         self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
         defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
-                "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n#define CT_POLY %d\n"
+                "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n#define CT_POLY %d\n#define CT_ASTREAM %d\n"
                 % (D, DB, self.KBM, self.REM, self.STAGES, HS, int(os.environ.get("CT_DBG", 0)), self.PEN,
-                   int(os.environ.get("CT_POLY", POLY))))
+                   int(os.environ.get("CT_POLY", POLY)), 1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(True), "kb200_convtc", VERSION)
         self.smem = smem_bytes(D, DB, self.STAGES)

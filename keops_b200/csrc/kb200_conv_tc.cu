@@ -465,11 +465,17 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
 #ifndef CT_KB
 #define CT_KB (CT_KBM + 1)                    /* only meaningful when CT_REM == 64                               */
 #endif
+#ifndef CT_ASTREAM
+#define CT_ASTREAM 0                          /* 1 (K > 576): the row block's k-blocks are streamed through the ring
+                                                 next to the streamed side's instead of staying resident: any D, at
+                                                 twice the L2 -> smem traffic per pair                              */
+#endif
 #define HD_BLK 16384                          /* 128 rows x 64 bf16                                              */
-#define HD_A_BYTES (CT_KB * HD_BLK)
+#define HD_STAGE_BYTES ((1 + CT_ASTREAM) * HD_BLK)
+#define HD_A_BYTES (CT_ASTREAM ? 0 : CT_KB * HD_BLK)
 #define HD_QUART (CT_BN / 4)
 #define HD_X_BYTES (3 * 128 * CT_DB * 4)      /* sums of column quarters 1..3, added to quarter 0 at the end      */
-#define HD_SMEM_BYTES (1024 + HD_A_BYTES + CT_STAGES * HD_BLK + CT_HS * CT_H_BYTES + HD_X_BYTES + 640) /* mirrored in conv_tc.py */
+#define HD_SMEM_BYTES (1024 + HD_A_BYTES + CT_STAGES * HD_STAGE_BYTES + CT_HS * CT_H_BYTES + HD_X_BYTES + 640) /* mirrored in conv_tc.py */
 
 extern "C" __global__ void __launch_bounds__(CT_THREADS, 1)
 kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_y,
@@ -482,16 +488,16 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
   unsigned char* gbase = ct_raw + (base - raw);
   const u32 sA = base;                                           // CT_KB resident k-blocks of this CTA's 128 rows
   const u32 sB = sA + HD_A_BYTES;                                // ring of streamed k-blocks
-  const u32 sH = sB + CT_STAGES * HD_BLK;                        // ring of b tiles
-  const float* hb = reinterpret_cast<const float*>(gbase + HD_A_BYTES + CT_STAGES * HD_BLK);
+  const u32 sH = sB + CT_STAGES * HD_STAGE_BYTES;                        // ring of b tiles
+  const float* hb = reinterpret_cast<const float*>(gbase + HD_A_BYTES + CT_STAGES * HD_STAGE_BYTES);
   const u32 sX = sH + CT_HS * CT_H_BYTES;
-  float* xch = reinterpret_cast<float*>(gbase + HD_A_BYTES + CT_STAGES * HD_BLK + CT_HS * CT_H_BYTES);
+  float* xch = reinterpret_cast<float*>(gbase + HD_A_BYTES + CT_STAGES * HD_STAGE_BYTES + CT_HS * CT_H_BYTES);
   const u32 sBar = sX + HD_X_BYTES;
   // barriers: full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @192, hfull[16] @256, hempty[16] @384, afull @512, tmem @520
   const u32 bFull = sBar, bEmpty = sBar + 64, bTFull = sBar + 128, bTEmpty = sBar + 192, bAFull = sBar + 512;
   const u32 bHFull = sBar + 256, bHEmpty = sBar + 384;
   volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(
-      gbase + HD_A_BYTES + CT_STAGES * HD_BLK + CT_HS * CT_H_BYTES + HD_X_BYTES + 520);
+      gbase + HD_A_BYTES + CT_STAGES * HD_STAGE_BYTES + CT_HS * CT_H_BYTES + HD_X_BYTES + 520);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row_base = (long long)blockIdx.x * 128;
@@ -519,11 +525,13 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+#if !CT_ASTREAM
     if (kt_elect()) {
       kt_mbar_expect_tx(bAFull, HD_A_BYTES);
       for (int kb = 0; kb < CT_KB; kb++) kt_tma_2d(sA + kb * HD_BLK, &map_x, kb * 64, (int)row_base, bAFull);
     }
     __syncwarp();
+#endif
     int it = 0;
     for (int t = 0; t < ntiles; t++) {
       const int h = t % CT_HS;
@@ -537,15 +545,20 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
         const int s = it % CT_STAGES;
         kt_mbar_wait(bEmpty + 8 * s, ((it / CT_STAGES) & 1) ^ 1);
         if (kt_elect()) {
-          kt_mbar_expect_tx(bFull + 8 * s, HD_BLK);
-          kt_tma_2d(sB + s * HD_BLK, &map_y, kb * 64, (t0 + t) * CT_BN, bFull + 8 * s);
+          kt_mbar_expect_tx(bFull + 8 * s, HD_STAGE_BYTES);
+          kt_tma_2d(sB + s * HD_STAGE_BYTES, &map_y, kb * 64, (t0 + t) * CT_BN, bFull + 8 * s);
+#if CT_ASTREAM
+          kt_tma_2d(sB + s * HD_STAGE_BYTES + HD_BLK, &map_x, kb * 64, (int)row_base, bFull + 8 * s);
+#endif
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: a tile accumulates over the CT_KB k-blocks =====================
+#if !CT_ASTREAM
     kt_mbar_wait(bAFull, 0);
+#endif
     int it = 0;
     for (int t = 0; t < ntiles; t++) {
       const int buf = t % CT_NBUF;
@@ -557,8 +570,8 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
         kt_fence_after();
         if (kt_elect()) {
           const u32 d = tmem + (u32)(buf * CT_BN);
-          const u64 ad = kt_smem_desc(sA + kb * HD_BLK, 128);
-          const u64 bd = kt_smem_desc(sB + s * HD_BLK, 128);
+          const u64 ad = kt_smem_desc(CT_ASTREAM ? (sB + s * HD_STAGE_BYTES + HD_BLK) : (sA + kb * HD_BLK), 128);
+          const u64 bd = kt_smem_desc(sB + s * HD_STAGE_BYTES, 128);
 #pragma unroll
           for (int k = 0; k < 4; k++)
             kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), CT_IDESC, (u32)((kb | k) != 0));

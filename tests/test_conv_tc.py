@@ -63,7 +63,10 @@ def test_layout_and_eligibility():
     assert conv_tc.is_hd(64) and conv_tc.layout(64) == (6, 64, 1)                  # 387 columns -> 7 k-blocks of 64
     assert conv_tc.eligible(g64, "float32", 100000, 100000, 1, True) is not None   # high-dimensional kernel
     g96 = parse_reduction(KS.replace("16", "96"))
-    assert conv_tc.eligible(g96, "float32", 100000, 100000, 1, True) is None       # K > 576: rows no longer resident
+    assert conv_tc.eligible(g96, "float32", 100000, 100000, 1, True) is not None   # K > 576: both operands stream
+    assert conv_tc.smem_bytes(96, 1) < conv_tc.smem_bytes(95, 1)
+    g4k = parse_reduction(KS.replace("16", "4096"))
+    assert conv_tc.eligible(g4k, "float32", 100000, 100000, 1, True) is None
     assert conv_tc.eligible(parse_reduction(KS.replace("Var(2,1,1)", "Var(2,8,1)")), "float32", 100000, 100000, 1, True) is None  # b ring too wide for smem
     for D, DB in ((8, 1), (16, 1), (16, 4), (21, 4)):
         assert conv_tc.smem_bytes(D, DB) <= 227 * 1024
@@ -113,7 +116,9 @@ CASES = [
     (21, 4, 8192, 2000, 0, "-Var(3,1,2)*"),           # widest operand rows of the 256-row kernel
     (22, 1, 8200, 3001, 0, "-Var(3,1,2)*"),           # high-dimensional kernel (kb200_conv_tc_hd): 3 k-blocks
     (64, 2, 8192, 2500, 0, "-Var(3,1,2)*"),           # 7 k-blocks, vector b
-    (95, 1, 4000, 8300, 1, "-Var(3,1,2)*"),           # 9 k-blocks (the maximum), reduction over i
+    (95, 1, 4000, 8300, 1, "-Var(3,1,2)*"),           # 9 k-blocks (the resident maximum), reduction over i
+    (128, 2, 8192, 1300, 0, "-Var(3,1,2)*"),          # 13 k-blocks: both operands stream through the ring
+    (300, 1, 8192, 1100, 0, "-Var(3,1,2)*"),          # 29 k-blocks
 ]
 
 
