@@ -234,6 +234,10 @@ class LoadKeOpsB200:
         if ct is not None:
             if self._genred_conv_tc(dev, ct, nrow, ncol, out, args):
                 return out
+        if self.red.kind == "LSE":
+            cl = conv_tc.eligible_lse(self.red, p.dtype, nrow, ncol, nbatch, p.use_fast_math, p.sum_scheme, p.dtype_acc)
+            if cl is not None and self._genred_lse_tc(dev, cl, nrow, ncol, out, args):
+                return out
         return self._launch_dense(dev, nrow, ncol, nbatch, out, args, strides, tdtype)
 
     def _genred_knn_tc(self, dev, tc, nrow, ncol, out, args, strides, tdtype):
@@ -274,6 +278,25 @@ class LoadKeOpsB200:
         self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0, blocks_per_sm=1,
                                 launches=3 + (eng.last["nchunks"] > 1), engine="tcgen05-conv",
                                 error_bound=eng.last_bound, nchunks=eng.last["nchunks"])
+        return True
+
+    def _genred_lse_tc(self, dev, cl, nrow, ncol, out, args):
+        """``Max_SumShiftExp[Weight]`` of ``a_j + c |x_i - y_j|^2`` (soft-min of a Sinkhorn iteration) in dimension
+        D >= 8: the same tensor-core kernels in LSE mode (``codegen/conv_tc.py``), same tolerance guard."""
+        p = self.params
+        row_ind, col_ind, D, a_ind, w_ind, DB, terms = cl
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        eng = conv_tc.get(D, DB, index, lse=True)
+        with torch.cuda.device(dev):
+            coef = conv_tc.coefficient(terms, args, dev)
+            w = args[w_ind] if w_ind is not None else torch.ones((ncol, 1), dtype=torch.float32, device=dev)
+            acol = args[a_ind].reshape(-1) if a_ind is not None else None
+            ok = eng.run(args[row_ind], args[col_ind], w, coef, out.view(nrow, p.dim), torch.cuda.current_stream(dev),
+                         acol=acol)
+        if not ok:
+            return False
+        self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0, blocks_per_sm=1,
+                                launches=3, engine="tcgen05-lse", error_bound=eng.last_bound, nchunks=1)
         return True
 
     def _launch_dense(self, dev, nrow, ncol, nbatch, out, args, strides, tdtype):

@@ -34,7 +34,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-8"
+VERSION = "conv-tc-9"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
@@ -122,6 +122,43 @@ def match(red: Reduction):
         if bcat != 1 - red.tagI or bdim > MAX_DB or e.dim != 1:
             continue
         return row, col, da, bi, bdim, terms
+    return None
+
+
+def match_lse(red: Reduction):
+    """``(row_var, col_var, D, a_var or None, weight_var or None, DB, coef_terms)`` for
+    ``Max_SumShiftExp[Weight]_Reduction(a_j + c |x_i - y_j|^2, tagI[, b_j])`` -- the soft-min of a Sinkhorn iteration
+    (BASELINE configs[3] in dimension D >= 8): ``a`` an optional streamed scalar variable (added or the minuend of a
+    subtraction), ``b`` absent (weight 1) or a streamed variable; ``None`` otherwise."""
+    if red.kind != "LSE" or red.formula.dim != 1:
+        return None
+    f = red.formula
+    cands = [(None, f, False)]
+    if f.op == "Add" and len(f.args) == 2:
+        cands += [(f.args[0], f.args[1], False), (f.args[1], f.args[0], False)]
+    if f.op == "Subtract" and len(f.args) == 2:
+        cands += [(f.args[0], f.args[1], True)]                    # a - E: the coefficient of E changes sign
+    for a, e, negate in cands:
+        if a is not None and (a.op != "Var" or a.params[1] != 1 or a.params[2] != 1 - red.tagI):
+            continue
+        r = _scaled_sqdist(e)
+        if r is None:
+            continue
+        terms, (va, vb) = r
+        if negate:
+            terms = terms + [(None, -1)]
+        (ia, da, ca), (ib, db, cb) = va.params, vb.params
+        if da != db or {ca, cb} != {0, 1}:
+            continue
+        row, col = (ia, ib) if ca == red.tagI else (ib, ia)
+        w = red.weight
+        if w is None or (w.op == "IntCst" and w.params[0] == 1):
+            wvar, DB = None, 1
+        elif w.op == "Var" and w.params[2] == 1 - red.tagI and w.params[1] <= MAX_DB:
+            wvar, DB = w.params[0], w.params[1]
+        else:
+            continue
+        return row, col, da, (a.params[0] if a is not None else None), wvar, DB, terms
     return None
 
 
@@ -226,22 +263,44 @@ def layout(D: int) -> Tuple[int, int, int]:
     return with_pen + (1,)
 
 
-def smem_bytes(D: int, DB: int, stages: int = STAGES) -> int:
-    """dynamic shared memory of kb200_conv_tc (CT_SMEM_BYTES in the kernel)"""
+def smem_bytes(D: int, DB: int, stages: int = STAGES, lse: bool = False) -> int:
+    """dynamic shared memory of kb200_conv_tc / kb200_conv_tc_hd (CT_SMEM_BYTES / HD_SMEM_BYTES in the kernel)"""
     kbm, rem, pen = layout(D)
+    OW = DB + (1 if lse else 0)
     if is_hd(D):                         # HD_SMEM_BYTES
         if kbm + 1 > HD_MAX_KB:          # CT_ASTREAM: both operands go through the ring
-            return 1024 + stages * 32768 + HS * BN * DB * 4 + 3 * 128 * DB * 4 + 640
-        return 1024 + (kbm + 1) * 16384 + stages * 16384 + HS * BN * DB * 4 + 3 * 128 * DB * 4 + 640
+            return 1024 + stages * 32768 + HS * BN * DB * 4 + 3 * 128 * OW * 4 + 640
+        return 1024 + (kbm + 1) * 16384 + stages * 16384 + HS * BN * DB * 4 + 3 * 128 * OW * 4 + 640
     blk = lambda rows: kbm * rows * 128 + rows * rem * 2       # one operand block, all of K
-    return 1024 + 2 * blk(128) + stages * blk(BN) + HS * BN * (DB + 1 - pen) * 4 + BM * DB * 4 + 640
+    return 1024 + 2 * blk(128) + stages * blk(BN) + HS * BN * (DB + 1 - pen) * 4 + BM * OW * 4 + 640
+
+
+def eligible_lse(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, use_fast_math: bool,
+                 sum_scheme: str = "block_sum", dtype_acc: str = "float32"):
+    """Same conditions as :func:`eligible` for the LogSumExp family; the column term rides in the penalty columns,
+    which the D = 21 layout does not have."""
+    if os.environ.get("KB200_CONV_TC", "1") == "0" or dtype != "float32" or nbatch != 1 or not use_fast_math:
+        return None
+    if sum_scheme not in ("block_sum", "auto") or dtype_acc not in ("float32", "auto"):
+        return None
+    m = match_lse(red)
+    if m is None:
+        return None
+    D, DB = m[2], m[5]
+    dmin = int(os.environ.get("KB200_CONV_TC_DMIN", 8))
+    if D < dmin or D > HD_MAX_D or layout(D)[2] != 1 or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
+        return None
+    if smem_bytes(D, DB, lse=True) > 227 * 1024:
+        return None
+    return m
 
 
 class ConvTensorCore:
-    """Compiled kernels for one (D, dim b) combination on one device."""
+    """Compiled kernels for one (D, dim b, Sum | LSE) combination on one device."""
 
-    def __init__(self, D: int, DB: int, device: int):
-        self.D, self.DB = D, DB
+    def __init__(self, D: int, DB: int, device: int, lse: bool = False):
+        self.D, self.DB, self.lse = D, DB, bool(lse)
+        self.OUTW = DB + (1 if lse else 0)
         self.KBM, self.REM, self.PEN = layout(D)
         self.hd = is_hd(D)
         self.DPG = 64 * self.KBM + self.REM
@@ -253,11 +312,13 @@ class ConvTensorCore:
         self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
         defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
                 "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n#define CT_POLY %d\n#define CT_ASTREAM %d\n"
+                "#define CT_LSE %d\n"
                 % (D, DB, self.KBM, self.REM, self.STAGES, HS, int(os.environ.get("CT_DBG", 0)), self.PEN,
-                   int(os.environ.get("CT_POLY", POLY)), 1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0))
+                   0 if lse else int(os.environ.get("CT_POLY", POLY)),
+                   1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0, 1 if lse else 0))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(True), "kb200_convtc", VERSION)
-        self.smem = smem_bytes(D, DB, self.STAGES)
+        self.smem = smem_bytes(D, DB, self.STAGES, lse)
         if self.smem > 227 * 1024:
             raise ValueError("conv_tc: D = %d, dim b = %d needs %d bytes of shared memory" % (D, DB, self.smem))
         self.smem = max(self.smem, 120 * 1024)     # one CTA per SM: each CTA allocates all 512 TMEM columns
@@ -277,10 +338,12 @@ class ConvTensorCore:
             return rem, rem            # the main map is never dereferenced
         return capi.tensor_map_2d(abf.data_ptr(), 2, 64 * self.KBM, n, pitch, 64, box_rows, 128), rem
 
-    def run(self, x, y, b, coef, out, stream_obj, clock_probe=None):
+    def run(self, x, y, b, coef, out, stream_obj, clock_probe=None, acol=None):
         """x (M, D), y (N, D), b (N, DB) fp32 contiguous CUDA tensors, coef a one-element fp32 tensor;
         out (M, DB) fp32.  Returns False (nothing written) when the accuracy guard rejects the inputs.
-        ``clock_probe``: optional int64 CUDA tensor of 2 elements receiving (SM cycles, nanoseconds) of CTA 0."""
+        ``clock_probe``: optional int64 CUDA tensor of 2 elements receiving (SM cycles, nanoseconds) of CTA 0.
+        LSE engines: ``b`` = weights (ones for the plain LogSumExp), ``acol`` = the column term a_j (N,) or None,
+        ``out`` (M, 1 + DB) receives (m_i, s_i)."""
         import torch
         M, N = x.shape[0], y.shape[0]
         dev = x.device
@@ -296,10 +359,11 @@ class ConvTensorCore:
         bpad = torch.empty(npad * self.W, dtype=torch.float32, device=dev)
         capi.launch(self.fn_prep, stream, (-(-npad // 256),), (256,), 0,
                     [i64(N), i64(npad), ptr(y.data_ptr()), ptr(shift.data_ptr()), ptr(ybf.data_ptr()), ptr(ysq.data_ptr()),
-                     ptr(b.data_ptr()), ptr(bpad.data_ptr()), i32(0)])
+                     ptr(b.data_ptr()), ptr(bpad.data_ptr()), i32(0), ptr(acol.data_ptr() if acol is not None else 0),
+                     ptr(coef.data_ptr())])
         capi.launch(self.fn_prep, stream, (-(-M // 256),), (256,), 0,
                     [i64(M), i64(M), ptr(x.data_ptr()), ptr(shift.data_ptr()), ptr(xbf.data_ptr()), ptr(xsq.data_ptr()),
-                     ptr(0), ptr(0), i32(1)])
+                     ptr(0), ptr(0), i32(1), ptr(0), ptr(coef.data_ptr())])
         tol = float(os.environ.get("KB200_CONV_TC_TOL", TOL))
         self.last_bound = None
         if tol > 0.0:
@@ -307,6 +371,8 @@ class ConvTensorCore:
             # that exceeds the stated tolerance (clouds much wider than the kernel bandwidth) the caller falls back to
             # the CUDA-core kernel, which forms x - y directly.  One host read, like the reference's per-call sync.
             bound = coef.abs() * (xsq.max() + ysq.max()) * (2.0 ** -22)
+            if acol is not None:                   # the column term shares the accumulation: + 2^-22 * 2 max |a_j|
+                bound = bound + acol.abs().max() * (2.0 ** -21)
             self.last_bound = float(bound.item())
             if not self.last_bound <= tol:          # also catches NaN / inf inputs
                 return False
@@ -321,7 +387,7 @@ class ConvTensorCore:
         # (126 MB L2; measured at M = N = 1e6, D = 16: one 256 MB chunk 288 ms, L2-sized chunks %s)
         chunk_bytes = int(os.environ.get("KB200_CONV_TC_CHUNK_MB", CHUNK_MB)) << 20
         tiles_per_chunk = max(1, chunk_bytes // (BN * self.DPG * 2))
-        nchunks = -(-ntiles // tiles_per_chunk)
+        nchunks = 1 if self.lse else -(-ntiles // tiles_per_chunk)   # (m, s) partials have no combine kernel
         tiles_per_chunk = -(-ntiles // nchunks)                   # balanced
         nchunks = -(-ntiles // tiles_per_chunk)
         dst = out if nchunks == 1 else torch.empty((nchunks, M, self.DB), dtype=torch.float32, device=dev)
@@ -346,11 +412,11 @@ class ConvTensorCore:
 _cache: Dict[tuple, ConvTensorCore] = {}
 
 
-def get(D: int, DB: int, device: int) -> ConvTensorCore:
-    key = (D, DB, device)
+def get(D: int, DB: int, device: int, lse: bool = False) -> ConvTensorCore:
+    key = (D, DB, device, bool(lse))
     with _lock:
         k = _cache.get(key)
         if k is None:
-            k = ConvTensorCore(D, DB, device)
+            k = ConvTensorCore(D, DB, device, lse)
             _cache[key] = k
         return k

@@ -43,6 +43,12 @@
 #ifndef CT_STAGES
 #define CT_STAGES 4
 #endif
+#ifndef CT_LSE
+#define CT_LSE 0                              /* 1: Max_SumShiftExpWeight reduction  (m_i, s_i) = (max_j F_ij, sum_j exp(F_ij - m_i) b_j)
+                                                 of F_ij = a_j + c |x_i - y_j|^2  (reference: Max_SumShiftExpWeight_Reduction.py:16-123);
+                                                 a_j rides in the penalty columns, the running max lives in base-2 units   */
+#endif
+#define CT_OUTW (CT_DB + CT_LSE)              /* output floats per row: [m ,] s                                   */
 #ifndef CT_HS
 #define CT_HS 8                               /* slots of the b-tile ring                                        */
 #endif
@@ -65,7 +71,7 @@
 #define CT_A_BYTES (2 * CT_BLK_BYTES(128))
 #define CT_B_BYTES CT_BLK_BYTES(CT_BN)
 #define CT_H_BYTES (CT_BN * CT_W * 4)         /* one b tile                                                      */
-#define CT_X_BYTES (CT_BM * CT_DB * 4)        /* exchange of the second column half's sums at the end            */
+#define CT_X_BYTES (CT_BM * CT_OUTW * 4)      /* exchange of the second column half's sums at the end            */
 #define CT_EPI_WARPS 16
 #define CT_THREADS (64 + 32 * CT_EPI_WARPS)
 #define CT_HALF (CT_BN / 2)                   /* columns per epilogue thread and tile                            */
@@ -85,7 +91,8 @@
 extern "C" __global__ void __launch_bounds__(256)
 kb200_conv_prep(const long long n, const long long npad, const float* __restrict__ a, const float* __restrict__ shift,
                 unsigned short* __restrict__ abf, float* __restrict__ sq, const float* __restrict__ b,
-                float* __restrict__ bpad, const int side) {
+                float* __restrict__ bpad, const int side, const float* __restrict__ acol,
+                const float* __restrict__ coef) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (side == 0 && r < npad) {
 #pragma unroll
@@ -115,7 +122,8 @@ kb200_conv_prep(const long long n, const long long npad, const float* __restrict
   if (CT_PEN == 0) {
     if (side == 0) bpad[r * CT_W] = s;
   } else if (side == 0) {
-    const float h = 0.5f * s;
+    // LSE: F_ij = a_j + c |x - y|^2 = -2c (x.y - |y|^2/2 - a_j / (2c)) + c |x|^2 : the column term joins the penalty
+    const float h = 0.5f * s + ((CT_LSE && acol != nullptr) ? acol[r] / (2.0f * coef[0]) : 0.0f);
     const unsigned short hi = kt_bf16_rn(h);
     const float r1 = h - kt_bf16_to_f(hi);
     const unsigned short mid = kt_bf16_rn(r1);
@@ -268,6 +276,61 @@ __device__ __forceinline__ void ct_tile(const float (&u)[NC], const float* __res
   for (int d = 0; d < CT_DB; d++) acc[d] += tmp[0][d] + tmp[1][d];
 }
 
+#if CT_LSE
+// one tile of a Max_SumShiftExpWeight reduction for one output row, base-2 units: v_e = log2(e) F_e;
+// pass 1: exponents + tile maximum; rescale the running sums if the maximum moved; pass 2: sums of 2^(v_e - M2) b_e
+template <bool TAIL, int NC>
+__device__ __forceinline__ void ct_tile_lse(float (&u)[NC], const float* __restrict__ bt, const float c2,
+                                            const float rowc, const long long j0, const long long ncol, float& M2,
+                                            float (&acc)[CT_DB]) {
+  float vmax = -KT_INF;
+#pragma unroll
+  for (int e = 0; e < NC; e++) {
+    float v = fmaf(u[e], c2, rowc);
+    if (TAIL && j0 + e >= ncol) v = -KT_INF;
+    u[e] = v;
+    vmax = fmaxf(vmax, v);
+  }
+  if (vmax > M2) {                                    // (also the first tile: M2 = -inf, the sums are still 0)
+    const float sc = ct_ex2(M2 - vmax);
+#pragma unroll
+    for (int d = 0; d < CT_DB; d++) acc[d] *= sc;
+    M2 = vmax;
+  }
+  if (M2 == -KT_INF) return;                          // nothing but masked / -inf entries so far
+  float tmp[2][CT_DB];
+#pragma unroll
+  for (int d = 0; d < CT_DB; d++) tmp[0][d] = tmp[1][d] = 0.0f;
+#pragma unroll
+  for (int e4 = 0; e4 < NC / 4; e4++) {
+    float bv[4 * CT_DB];
+    const float4* b4 = reinterpret_cast<const float4*>(bt + 4 * e4 * CT_DB);
+#pragma unroll
+    for (int v = 0; v < CT_DB; v++) {
+      const float4 q = b4[v];
+      bv[4 * v + 0] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float p = ct_ex2(u[4 * e4 + e] - M2);
+#pragma unroll
+      for (int d = 0; d < CT_DB; d++) tmp[e & 1][d] = fmaf(p, bv[e * CT_DB + d], tmp[e & 1][d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < CT_DB; d++) acc[d] += tmp[0][d] + tmp[1][d];
+}
+
+// merge (M2b, Sb) into (M2a, Sa): the pair algebra of the reference's ReducePair, in base-2 units
+__device__ __forceinline__ void ct_lse_merge(float& Ma, float (&Sa)[CT_DB], const float Mb, const float* Sb) {
+  const float M = fmaxf(Ma, Mb);
+  const float fa = (Ma == -KT_INF) ? 0.0f : ct_ex2(Ma - M), fb = (Mb == -KT_INF) ? 0.0f : ct_ex2(Mb - M);
+#pragma unroll
+  for (int d = 0; d < CT_DB; d++) Sa[d] = Sa[d] * fa + Sb[d] * fb;
+  Ma = M;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
@@ -310,7 +373,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
   const long long col1 = (col0 + chunk_cols < ncol) ? col0 + chunk_cols : ncol;
   const int t0 = (int)(col0 / CT_BN);
   const int ntiles = (int)((col1 - col0 + CT_BN - 1) / CT_BN);
-  out += (long long)blockIdx.y * nrow * CT_DB;                   // chunk partial sums (gridDim.y > 1) or the output
+  out += (long long)blockIdx.y * nrow * CT_OUTW;                 // chunk partial sums (gridDim.y > 1) or the output
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
@@ -400,6 +463,9 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
     float acc[CT_DB];
 #pragma unroll
     for (int d = 0; d < CT_DB; d++) acc[d] = 0.0f;
+#if CT_LSE
+    float M2 = -KT_INF;                               // running maximum of log2(e) F_ij
+#endif
     for (int t = 0; t < ntiles; t++) {
       const int buf = t % CT_NBUF, hslot = t % CT_HS;
       kt_mbar_wait(bTFull + 8 * (buf * 2 + rb), (t / CT_NBUF) & 1);
@@ -419,24 +485,39 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
       kt_mbar_wait(bHFull + 8 * hslot, (t / CT_HS) & 1);
       const float* bt = hb + hslot * (CT_BN * CT_W) + half * (CT_HALF * CT_W);
       const long long j0 = (long long)(t0 + t) * CT_BN + half * CT_HALF;
+#if CT_LSE
+      if (j0 + CT_HALF > ncol) ct_tile_lse<true, CT_HALF>(uu, bt, c2, rowc, j0, ncol, M2, acc);
+      else ct_tile_lse<false, CT_HALF>(uu, bt, c2, rowc, j0, ncol, M2, acc);
+#else
       if (j0 + CT_HALF > ncol) ct_tile<true, CT_HALF>(uu, bt, c2, cl, rowc, j0, ncol, acc);
 #if CT_FASTPATH && CT_DBG == 0
       else ct_tile_fast(uu, bt, c2, rowc, acc);
 #else
       else ct_tile<false, CT_HALF>(uu, bt, c2, cl, rowc, j0, ncol, acc);
 #endif
+#endif
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
     }
-    // row sum = first half + second half (fixed order: deterministic)
+    // row result = first half (+) second half (fixed order: deterministic)
     if (half == 1) {
+#if CT_LSE
+      xch[rloc * CT_OUTW] = M2;
+#endif
 #pragma unroll
-      for (int d = 0; d < CT_DB; d++) xch[rloc * CT_DB + d] = acc[d];
+      for (int d = 0; d < CT_DB; d++) xch[rloc * CT_OUTW + CT_LSE + d] = acc[d];
     }
     asm volatile("bar.sync 1, %0;" ::"r"(32 * CT_EPI_WARPS) : "memory");
     if (half == 0 && live) {
+#if CT_LSE
+      ct_lse_merge(M2, acc, xch[rloc * CT_OUTW], xch + rloc * CT_OUTW + 1);
+      out[i * CT_OUTW] = M2 * 0.6931471805599453f;                  // back to natural units: m_i = max_j F_ij
+#pragma unroll
+      for (int d = 0; d < CT_DB; d++) out[i * CT_OUTW + 1 + d] = acc[d];
+#else
 #pragma unroll
       for (int d = 0; d < CT_DB; d++) out[i * CT_DB + d] = acc[d] + xch[rloc * CT_DB + d];
+#endif
     }
   }
   kt_fence_before();
@@ -474,7 +555,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
 #define HD_STAGE_BYTES ((1 + CT_ASTREAM) * HD_BLK)
 #define HD_A_BYTES (CT_ASTREAM ? 0 : CT_KB * HD_BLK)
 #define HD_QUART (CT_BN / 4)
-#define HD_X_BYTES (3 * 128 * CT_DB * 4)      /* sums of column quarters 1..3, added to quarter 0 at the end      */
+#define HD_X_BYTES (3 * 128 * CT_OUTW * 4)    /* sums of column quarters 1..3, added to quarter 0 at the end      */
 #define HD_SMEM_BYTES (1024 + HD_A_BYTES + CT_STAGES * HD_STAGE_BYTES + CT_HS * CT_H_BYTES + HD_X_BYTES + 640) /* mirrored in conv_tc.py */
 
 extern "C" __global__ void __launch_bounds__(CT_THREADS, 1)
@@ -505,7 +586,7 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
   const long long col1 = (col0 + chunk_cols < ncol) ? col0 + chunk_cols : ncol;
   const int t0 = (int)(col0 / CT_BN);
   const int ntiles = (int)((col1 - col0 + CT_BN - 1) / CT_BN);
-  out += (long long)blockIdx.y * nrow * CT_DB;
+  out += (long long)blockIdx.y * nrow * CT_OUTW;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
@@ -593,6 +674,9 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
     float acc[CT_DB];
 #pragma unroll
     for (int d = 0; d < CT_DB; d++) acc[d] = 0.0f;
+#if CT_LSE
+    float M2 = -KT_INF;
+#endif
     for (int t = 0; t < ntiles; t++) {
       const int buf = t % CT_NBUF, hslot = t % CT_HS;
       kt_mbar_wait(bTFull + 8 * buf, (t / CT_NBUF) & 1);
@@ -606,20 +690,37 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
       kt_mbar_wait(bHFull + 8 * hslot, (t / CT_HS) & 1);
       const float* bt = hb + hslot * (CT_BN * CT_W) + part * (HD_QUART * CT_W);
       const long long j0 = (long long)(t0 + t) * CT_BN + part * HD_QUART;
+#if CT_LSE
+      if (j0 + HD_QUART > ncol) ct_tile_lse<true, HD_QUART>(uu, bt, c2, rowc, j0, ncol, M2, acc);
+      else ct_tile_lse<false, HD_QUART>(uu, bt, c2, rowc, j0, ncol, M2, acc);
+#else
       if (j0 + HD_QUART > ncol) ct_tile<true, HD_QUART>(uu, bt, c2, cl, rowc, j0, ncol, acc);
       else ct_tile<false, HD_QUART>(uu, bt, c2, cl, rowc, j0, ncol, acc);
+#endif
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
     }
     if (part > 0) {
+#if CT_LSE
+      xch[((part - 1) * 128 + rloc) * CT_OUTW] = M2;
+#endif
 #pragma unroll
-      for (int d = 0; d < CT_DB; d++) xch[((part - 1) * 128 + rloc) * CT_DB + d] = acc[d];
+      for (int d = 0; d < CT_DB; d++) xch[((part - 1) * 128 + rloc) * CT_OUTW + CT_LSE + d] = acc[d];
     }
     asm volatile("bar.sync 1, %0;" ::"r"(32 * CT_EPI_WARPS) : "memory");
     if (part == 0 && live) {
+#if CT_LSE
+#pragma unroll
+      for (int p_ = 0; p_ < 3; p_++)
+        ct_lse_merge(M2, acc, xch[(p_ * 128 + rloc) * CT_OUTW], xch + (p_ * 128 + rloc) * CT_OUTW + 1);
+      out[i * CT_OUTW] = M2 * 0.6931471805599453f;
+#pragma unroll
+      for (int d = 0; d < CT_DB; d++) out[i * CT_OUTW + 1 + d] = acc[d];
+#else
 #pragma unroll
       for (int d = 0; d < CT_DB; d++)
         out[i * CT_DB + d] = ((acc[d] + xch[rloc * CT_DB + d]) + xch[(128 + rloc) * CT_DB + d]) + xch[(256 + rloc) * CT_DB + d];
+#endif
     }
   }
   kt_fence_before();

@@ -214,3 +214,71 @@ def test_tensor_core_conv_is_deterministic_and_linear(cuda_device):
     o2, _ = _run(KS, 4, (x, y, b2, g), nx, ny, dev, True)
     o12, _ = _run(KS, 4, (x, y, b1 + 2.0 * b2, g), nx, ny, dev, True)
     util.assert_close(o12.cpu().numpy(), (o1 + 2.0 * o2).cpu().numpy(), "float32", "linearity in b")
+
+
+# ---------------------------------------------------------------------------------------------
+# LogSumExp on the tensor cores (kb200_conv_tc / kb200_conv_tc_hd in LSE mode)
+# ---------------------------------------------------------------------------------------------
+def test_match_lse_patterns():
+    soft = "Max_SumShiftExp_Reduction((Var(0,1,1) - ((Sum(Square((Var(1,16,0) - Var(2,16,1)))) / IntCst(2)) / Var(3,1,2))),0)"
+    m = conv_tc.match_lse(parse_reduction(soft))
+    assert m is not None and m[:6] == (1, 2, 16, 0, None, 1)
+    w = "Max_SumShiftExpWeight_Reduction(-SqDist(Var(0,16,0),Var(1,16,1))*Var(3,1,2),0,Var(2,2,1))"
+    assert conv_tc.match_lse(parse_reduction(w))[:6] == (0, 1, 16, None, 2, 2)
+    assert conv_tc.eligible_lse(parse_reduction(soft), "float32", 100000, 100000, 1, True) is not None
+    assert conv_tc.eligible_lse(parse_reduction(soft.replace("16", "3")), "float32", 100000, 100000, 1, True) is None
+    assert conv_tc.eligible_lse(parse_reduction(soft.replace("16", "21")), "float32", 100000, 100000, 1, True) is None
+    # a row-indexed offset or a non-distance exponent is not this pattern
+    assert conv_tc.match_lse(parse_reduction(soft.replace("Var(0,1,1)", "Var(0,1,0)"))) is None
+    assert conv_tc.match_lse(parse_reduction("Max_SumShiftExp_Reduction((Var(0,16,0) | Var(1,16,1)),0)")) is None
+    assert conv_tc.match_lse(parse_reduction(KS)) is None
+
+
+LSE_CASES = [
+    # D, weight dim (0 = plain LogSumExp), nx, ny, tagI
+    (16, 0, 9000, 7001, 0),
+    (8, 2, 8192, 4096, 0),
+    (16, 0, 5000, 9000, 1),
+    (64, 0, 8192, 2500, 0),       # high-dimensional kernel
+    (128, 3, 8192, 1300, 0),      # both operands streamed
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,DW,nx,ny,tagI", LSE_CASES)
+def test_tensor_core_lse_matches_cuda_core(D, DW, nx, ny, tagI, cuda_device):
+    import torch
+    torch.manual_seed(D * 10 + DW)
+    dev = cuda_device
+    x, y = torch.rand(nx, D, device=dev), torch.rand(ny, D, device=dev)
+    ns = ny if tagI == 0 else nx                      # streamed side
+    a = torch.rand(ns, 1, device=dev)
+    eps = torch.tensor([D / 24.0], device=dev)        # temperature ~ typical squared distance / 8
+    cs = 1 - tagI
+    if DW:
+        w = torch.rand(ns, DW, device=dev) + 0.1
+        f = ("Max_SumShiftExpWeight_Reduction((Var(2,1,%d) - ((Sum(Square((Var(0,%d,0) - Var(1,%d,1)))) / IntCst(2)) / Var(3,1,2))),%d,Var(4,%d,%d))"
+             % (cs, D, D, tagI, DW, cs))
+        args = (x, y, a, eps, w)
+    else:
+        f = ("Max_SumShiftExp_Reduction((Var(2,1,%d) - ((Sum(Square((Var(0,%d,0) - Var(1,%d,1)))) / IntCst(2)) / Var(3,1,2))),%d)"
+             % (cs, D, D, tagI))
+        args = (x, y, a, eps)
+    o_tc, ll = _run(f, len(args), args, nx, ny, dev, True)
+    assert ll.get("engine") == "tcgen05-lse", ll
+    o_cc, ll2 = _run(f, len(args), args, nx, ny, dev, False)
+    assert ll2.get("engine") is None
+    # raw (m, s) output: m = max_j F_ij, s = sum_j exp(F_ij - m) b_j
+    util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 LSE (m, s) vs CUDA cores")
+    lse_tc = o_tc[:, 0] + torch.log(o_tc[:, 1])
+    lse_cc = o_cc[:, 0] + torch.log(o_cc[:, 1])
+    util.assert_close(lse_tc.cpu().numpy(), lse_cc.cpu().numpy(), "float32", "log-sum-exp")
+    from oracle import keops_oracle as ko
+    rows = slice(0, 40)
+    host = [t.cpu().numpy() for t in args]
+    if tagI == 0:
+        host[0] = host[0][rows]
+    else:
+        host[1] = host[1][rows]
+    ref = ko.genred(f, [], host, "float32")
+    util.assert_close(o_tc[rows].cpu().numpy(), ref, "float32", "tcgen05 LSE vs oracle")
