@@ -141,7 +141,10 @@ def default_config(red: Reduction, dtype: str) -> KernelConfig:
     vec = 2 if f64 else 4
     stride = max(vec, -(-dimy // vec) * vec)
     TJ = 16384 // (stride * esz)          # two buffers <= 32 KB
-    TJ = max(8, min(256, 1 << int(math.log2(max(TJ, 1)))))
+    # longer tiles amortise the per-tile barrier / bookkeeping; measured on B200 at M = N = 1e6 (experiments/tj_sweep.sh),
+    # TJ = 256 / 512 / 1024: ArgKMin D=3 232.1 / 228.5 / 222.7 ms, LSE 350.1 / 349.3 / 342.8 ms, Gaussian conv 262.6 / 259.0 / 261.4 ms
+    tj_cap = 256 if f64 else (512 if red.kind == "Sum" else 1024)     # fp64 LSE: 1604 ms at 256, 1615 ms at 512
+    TJ = max(8, min(tj_cap, 1 << int(math.log2(max(TJ, 1)))))
     body = max(1, dimx + dimy) * (R // (1 if f64 else 2))
     unroll = 8 if body <= 16 else (4 if body <= 64 else (2 if body <= 160 else 1))
     if red.kind in ("KMin", "ArgKMin", "KMin_ArgKMin"):
