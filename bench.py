@@ -44,8 +44,8 @@ KNN = "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)"
 KSOLVE = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)"    # BASELINE configs[4] matvec
 SM_COUNT, SM_MAX_HZ = 148, 1.965e9
 # dram__bytes_read.sum + dram__bytes_write.sum of one kb200_reduce launch of the full-size forward conv, from the
-# committed `ncu --set full` capture profiles/r01_ncu_gauss_fwd.txt (28.110 MB + 14 KB; algorithmic bytes 32 MB)
-NCU_DRAM_BYTES_FWD = 28110336 + 14080
+# committed `ncu --set full` capture profiles/r01_ncu_gauss_fwd_v2.txt (28.148 MB + 42 KB; algorithmic bytes 32 MB)
+NCU_DRAM_BYTES_FWD = 28147968 + 42496
 ROOFLINE_PAIRS_PER_CLK_SM = {"gauss_fwd": 16.0, "gauss_grad": 128.0 / 11.0, "knn_d3": 128.0 / 7.0}
 
 
