@@ -415,6 +415,26 @@ def main():
                            "fwd_ms": fwd_ms, "grad_x_ms": gx_ms, "grad_y_ms": gy_ms,
                            "grad_x_frac_of_roofline": M * N / (gx_ms * 1e-3) / pk,
                            "grad_y_frac_of_roofline": M * N / (gy_ms * 1e-3) / pk}
+        # ---- the other BASELINE configs at full size: KNN K=10 in D=64 (configs[2]) and the LogSumExp soft-min (configs[3])
+        try:
+            KNN64 = "ArgKMin_Reduction(Sum(Square((Var(0,64,0) - Var(1,64,1)))),10,0)"
+            qx, qy = torch.randn(M, 64, device=dev), torch.randn(N, 64, device=dev)
+            kb64 = get_binder(KNN64, [], 2, "float32")
+            k64_ms, _ = time_binder(kb64, M, N, (qx, qy))
+            line["knn_d64"] = {"metric": "knn_k10_queries_per_s", "value": M / (k64_ms * 1e-3), "unit": "queries/s", "D": 64,
+                               "K": 10, "ms": k64_ms, "pair_evals_per_s": float(M) * N / (k64_ms * 1e-3),
+                               "engine": kb64.last_launch.get("engine") or "cuda-core",
+                               "x_cuda_core_fp32_roofline": float(M) * N / (k64_ms * 1e-3) / (128.0 / 129.0 * SM_COUNT * sm_hz)}
+            del qx, qy
+            LSE = "Max_SumShiftExp_Reduction((Var(0,1,1) - ((Sum(Square((Var(1,3,0) - Var(2,3,1)))) / IntCst(2)) / Var(3,1,2))),0)"
+            lf, lx, ly = torch.rand(N, 1, device=dev), torch.rand(M, 3, device=dev), torch.rand(N, 3, device=dev)
+            lse_ms, _ = time_binder(get_binder(LSE, [], 4, "float32"), M, N, (lf, lx, ly, torch.tensor([0.05], device=dev)))
+            line["lse_softmin"] = {"workload": "LogSumExp soft-min M=N=%d D=3 fp32 (BASELINE configs[3])" % M, "ms": lse_ms,
+                                   "value": float(M) * N / (lse_ms * 1e-3), "unit": "pair-evals/s",
+                                   "frac_of_roofline": float(M) * N / (lse_ms * 1e-3) / (128.0 / 12.0 * SM_COUNT * sm_hz)}
+            del lf, lx, ly
+        except Exception as e:
+            line["knn_d64"] = {"unavailable": str(e)[:300]}
         # ---- KernelSolve matvec (BASELINE configs[4]): Gaussian kernel, D = 16, one CG iteration = M*N pairs.
         # Tensor-core path (tcgen05 GEMM for |x-y|^2, MUFU-bound) vs the CUDA-core kernel (FP32-pipe-bound, 34 ops/pair)
         try:
