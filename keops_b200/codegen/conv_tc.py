@@ -34,10 +34,13 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-9"
+VERSION = "conv-tc-10"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
+MULTICAST = 0              # kb200_conv_tc_hd: 2-CTA clusters multicasting the streamed k-blocks (KB200_CONV_TC_MC=1 enables).
+                           # Correct (tests pass with it on) but no faster: D=64, M=N=1e6 717 ms without, 726 ms with -- the
+                           # bound is the shared-memory port (operand reads of M=128 x N=128 MMAs + TMA fills), not L2
 POLY = 0                   # experiment (see kb200_conv_tc.cu): of every 8 pairs, exp2 of this many on the FMA pipe
 CHUNK_MB = 48              # bf16 operand rows of one column chunk (must stay L2-resident)
 # stated tolerance of the path: bound on the relative error of one term exp(c |x_i - y_j|^2) (0 disables the guard)
@@ -303,6 +306,8 @@ class ConvTensorCore:
         self.OUTW = DB + (1 if lse else 0)
         self.KBM, self.REM, self.PEN = layout(D)
         self.hd = is_hd(D)
+        # CTA pairs sharing the streamed k-blocks by TMA multicast (high-dimensional kernel only)
+        self.mc = 1 if (self.hd and os.environ.get("KB200_CONV_TC_MC", str(MULTICAST)) != "0") else 0
         self.DPG = 64 * self.KBM + self.REM
         self.W = DB + 1 - self.PEN                   # floats per column of the b tile
         with open(_COMMON_PATH) as f:
@@ -312,10 +317,10 @@ class ConvTensorCore:
         self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
         defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
                 "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n#define CT_POLY %d\n#define CT_ASTREAM %d\n"
-                "#define CT_LSE %d\n"
+                "#define CT_LSE %d\n#define CT_MC %d\n"
                 % (D, DB, self.KBM, self.REM, self.STAGES, HS, int(os.environ.get("CT_DBG", 0)), self.PEN,
                    0 if lse else int(os.environ.get("CT_POLY", POLY)),
-                   1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0, 1 if lse else 0))
+                   1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0, 1 if lse else 0, self.mc))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(True), "kb200_convtc", VERSION)
         self.smem = smem_bytes(D, DB, self.STAGES, lse)
@@ -378,7 +383,7 @@ class ConvTensorCore:
                 return False
         if self.hd:
             pitch = self.DPG * 2
-            map_y = capi.tensor_map_2d(ybf.data_ptr(), 2, self.DPG, N, pitch, 64, BN, 128)
+            map_y = capi.tensor_map_2d(ybf.data_ptr(), 2, self.DPG, N, pitch, 64, BN // 2 if self.mc else BN, 128)
             map_x = capi.tensor_map_2d(xbf.data_ptr(), 2, self.DPG, M, pitch, 64, 128, 128)
         else:
             map_y, map_yr = self._maps(ybf, N, BN)
@@ -392,7 +397,10 @@ class ConvTensorCore:
         nchunks = -(-ntiles // tiles_per_chunk)
         dst = out if nchunks == 1 else torch.empty((nchunks, M, self.DB), dtype=torch.float32, device=dev)
         if self.hd:
-            capi.launch(self.fn_conv, stream, (-(-M // 128), nchunks), (THREADS,), self.smem,
+            gx = -(-M // 128)
+            if self.mc:
+                gx += gx & 1               # whole CTA pairs; the odd block out computes rows >= M and stores nothing
+            capi.launch(self.fn_conv, stream, (gx, nchunks), (THREADS,), self.smem,
                         [map_x, map_y, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
                          ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr())])
         else:

@@ -551,6 +551,12 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
                                                  next to the streamed side's instead of staying resident: any D, at
                                                  twice the L2 -> smem traffic per pair                              */
 #endif
+#ifndef CT_MC
+#define CT_MC 0                               /* 1: CTA pairs (cluster 2x1x1) share the streamed k-blocks: each CTA loads
+                                                 one 64-column half and TMA-multicasts it to both, halving the L2 -> smem
+                                                 traffic of the streamed side.  Measured: no gain (717 vs 726 ms at D = 64,
+                                                 M = N = 1e6) -- the kernel is bound by the shared-memory port, not by L2  */
+#endif
 #define HD_BLK 16384                          /* 128 rows x 64 bf16                                              */
 #define HD_STAGE_BYTES ((1 + CT_ASTREAM) * HD_BLK)
 #define HD_A_BYTES (CT_ASTREAM ? 0 : CT_KB * HD_BLK)
@@ -558,7 +564,11 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
 #define HD_X_BYTES (3 * 128 * CT_OUTW * 4)    /* sums of column quarters 1..3, added to quarter 0 at the end      */
 #define HD_SMEM_BYTES (1024 + HD_A_BYTES + CT_STAGES * HD_STAGE_BYTES + CT_HS * CT_H_BYTES + HD_X_BYTES + 640) /* mirrored in conv_tc.py */
 
-extern "C" __global__ void __launch_bounds__(CT_THREADS, 1)
+extern "C" __global__ void
+#if CT_MC
+__cluster_dims__(2, 1, 1)
+#endif
+__launch_bounds__(CT_THREADS, 1)
 kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_y,
                  const long long nrow, const long long ncol, const long long chunk_cols,
                  const float* __restrict__ bpad, const float* __restrict__ xsq, const float* __restrict__ coef,
@@ -589,7 +599,8 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
   out += (long long)blockIdx.y * nrow * CT_OUTW;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
+    // CT_MC: a ring slot is written by both CTAs of the pair, so it is free only when both MMA warps have read it
+    for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1 + CT_MC); }
     for (int b = 0; b < CT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, CT_EPI_WARPS); }
     for (int h = 0; h < CT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, CT_EPI_WARPS); }
     kt_mbar_init(bAFull, 1);
@@ -603,6 +614,10 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
   __syncthreads();
   kt_fence_after();
   const u32 tmem = *tmem_slot;
+#if CT_MC
+  kt_cluster_sync();                                             // the peer's barriers exist before anything targets them
+  const u32 crank = kt_cluster_ctarank();
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -627,7 +642,13 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
         kt_mbar_wait(bEmpty + 8 * s, ((it / CT_STAGES) & 1) ^ 1);
         if (kt_elect()) {
           kt_mbar_expect_tx(bFull + 8 * s, HD_STAGE_BYTES);
+#if CT_MC
+          // this CTA's half (64 of the 128 columns of the tile) goes to both CTAs of the pair
+          kt_tma_2d_mc(sB + s * HD_STAGE_BYTES + crank * (HD_BLK / 2), &map_y, kb * 64,
+                       (t0 + t) * CT_BN + (int)crank * (CT_BN / 2), bFull + 8 * s, (unsigned short)3);
+#else
           kt_tma_2d(sB + s * HD_STAGE_BYTES, &map_y, kb * 64, (t0 + t) * CT_BN, bFull + 8 * s);
+#endif
 #if CT_ASTREAM
           kt_tma_2d(sB + s * HD_STAGE_BYTES + HD_BLK, &map_x, kb * 64, (int)row_base, bFull + 8 * s);
 #endif
@@ -656,7 +677,11 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 4; k++)
             kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), CT_IDESC, (u32)((kb | k) != 0));
+#if CT_MC
+          kt_mma_commit_mc(bEmpty + 8 * s, (unsigned short)3);   // releases the slot in both CTAs of the pair
+#else
           kt_mma_commit(bEmpty + 8 * s);                   // the ring slot may be refilled once these MMAs have read it
+#endif
           if (kb == CT_KB - 1) kt_mma_commit(bTFull + 8 * buf);
         }
         __syncwarp();
@@ -725,6 +750,9 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
   }
   kt_fence_before();
   __syncthreads();
+#if CT_MC
+  kt_cluster_sync();                                             // no CTA leaves while its peer may still target it
+#endif
   if (warp == 0) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");

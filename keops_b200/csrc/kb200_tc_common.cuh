@@ -55,6 +55,28 @@ __device__ __forceinline__ void kt_tma_2d(u32 dst, const KtTensorMap* map, int c
       "l"((u64)map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// TMA tile load multicast to the CTAs of `mask` in the cluster: the tile lands at the same shared-memory offset in every
+// destination CTA and completes bytes on the mbarrier at the same offset there
+__device__ __forceinline__ void kt_tma_2d_mc(u32 dst, const KtTensorMap* map, int c0, int c1, u32 bar, unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"((u64)map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void kt_mma_commit_mc(u32 bar, unsigned short mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ u32 kt_cluster_ctarank() {
+  u32 r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void kt_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void kt_bulk_1d(u32 dst, const void* src, u32 bytes, u32 bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"((u64)src), "r"(bytes), "r"(bar)
