@@ -421,7 +421,7 @@ _cache: Dict[tuple, ConvTensorCore] = {}
 
 
 def get(D: int, DB: int, device: int, lse: bool = False) -> ConvTensorCore:
-    key = (D, DB, device, bool(lse))
+    key = (D, DB, device, bool(lse), os.environ.get("KB200_CONV_TC_MC", str(MULTICAST)), os.environ.get("CT_POLY", str(POLY)))
     with _lock:
         k = _cache.get(key)
         if k is None:

@@ -282,3 +282,20 @@ def test_tensor_core_lse_matches_cuda_core(D, DW, nx, ny, tagI, cuda_device):
         host[1] = host[1][rows]
     ref = ko.genred(f, [], host, "float32")
     util.assert_close(o_tc[rows].cpu().numpy(), ref, "float32", "tcgen05 LSE vs oracle")
+
+
+@pytest.mark.gpu
+def test_cluster_multicast_variant_is_identical(cuda_device):
+    """Opt-in 2-CTA clusters that TMA-multicast the streamed k-blocks (``KB200_CONV_TC_MC=1``): same MMAs, same
+    epilogue, so the output must be bit-identical to the single-CTA kernel -- also with an odd number of row blocks."""
+    import torch
+    dev = cuda_device
+    torch.manual_seed(9)
+    nx, ny, D = 128 * 65 + 17, 3001, 64                 # 66 row blocks + a ragged one -> 67, padded to 68 CTAs
+    x, y, b = torch.rand(nx, D, device=dev), torch.rand(ny, D, device=dev), torch.randn(ny, 1, device=dev)
+    g = torch.tensor([0.1], device=dev)
+    f = KS.replace("16", "64")
+    o1, ll1 = _run(f, 4, (x, y, b, g), nx, ny, dev, True, KB200_CONV_TC_MC=1)
+    o0, ll0 = _run(f, 4, (x, y, b, g), nx, ny, dev, True, KB200_CONV_TC_MC=0)
+    assert ll1.get("engine") == ll0.get("engine") == "tcgen05-conv"
+    assert torch.equal(o1, o0)
