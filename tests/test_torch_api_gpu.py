@@ -265,3 +265,18 @@ def test_lazytensor_symbolic_grad(api, cuda_device):
     dense = ((-((x[:, None, :] - y[None, :, :]) ** 2).sum(2)).exp() * b.view(1, -1)).sum(1, keepdim=True)
     (ref,) = torch.autograd.grad(dense, x, e)
     torch.testing.assert_close(g, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("D,DV", [(300, 1), (3, 300)])
+def test_high_dimensional_x_or_b_like_reference_chunk_tests(api, cuda_device, D, DV):
+    """Mirrors pykeops/pykeops/test/test_chunks.py (D = 300: the reference's chunked mode) and test_finalchunks.py
+    (dim b = 300: its final-chunk mode): same shapes, seed, scaling and tolerance."""
+    M, N = 200, 300
+    torch.manual_seed(0)
+    x = torch.rand(M, 1, D, device=cuda_device) / math.sqrt(D)
+    y = torch.rand(1, N, D, device=cuda_device) / math.sqrt(D)
+    b = torch.randn(N, DV, device=cuda_device)
+    Kxy = (-((api.LazyTensor(x) - api.LazyTensor(y)).square()).sum(dim=2)).exp()
+    out = Kxy.__matmul__(b, sum_scheme="block_sum")
+    ref = (-((x - y) ** 2).sum(dim=2)).exp() @ b
+    assert torch.allclose(out, ref, atol=1e-4)
