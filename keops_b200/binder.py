@@ -125,6 +125,66 @@ class LoadKeOpsB200:
         self._loaded: Dict[object, plan.LoadedKernel] = {}
         self.ks_ranges: Optional[KernelSource] = None
         self._range_tables: Dict[tuple, tuple] = {}
+        self._optional_flags = dict(optional_flags)
+        self._init_args = (tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id_request, lang)
+        self._wide = self._detect_wide(red)
+        self._wide_binders: Dict[int, "LoadKeOpsB200"] = {}
+
+    # ---- wide streamed factor (the reference's "final chunks" mode, GpuReduc1D_finalchunks.py) ----------------
+    WIDE_MIN, WIDE_CHUNK = 100, 32          # same threshold as the reference (dim > 100); chunk of the wide variable
+
+    @staticmethod
+    def _detect_wide(red: Reduction):
+        """``Sum_Reduction(E_ij * b, tagI)`` with ``E`` scalar and ``b`` a *streamed* variable of dimension >= 100 (attention-
+        like sums): the accumulator (dim b values per output row) does not fit the register file.  Returns
+        ``(b index, dim b, b category, text of E)`` when the reduction can be evaluated chunk by chunk of ``b``."""
+        if red.kind != "Sum":
+            return None
+        f = red.formula
+        if f.op != "Mult" or len(f.args) != 2:
+            return None
+        for e, b in ((f.args[0], f.args[1]), (f.args[1], f.args[0])):
+            if b.op == "Var" and e.dim == 1 and b.params[1] >= LoadKeOpsB200.WIDE_MIN and b.params[2] == 1 - red.tagI \
+                    and all(v.params[0] != b.params[0] for v in e.variables()):
+                text = repr(e)
+                try:                         # the chunk kernels are built from the printed sub-formula: it must round-trip
+                    from .formulas.parser import parse_formula
+                    if parse_formula(text) is not e:
+                        return None
+                except Exception:
+                    return None
+                return b.params[0], b.params[1], b.params[2], text
+        return None
+
+    def _genred_wide(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
+        """Chunks of ``WIDE_CHUNK`` components of the wide variable, one launch of the narrow kernel each (``E_ij`` is
+        recomputed per chunk: a few operations against ``WIDE_CHUNK`` FMAs); the chunk results fill ``out[..., c0:c1]``."""
+        ind, DV, cat, etext = self._wide
+        p = self.params
+        C = self.WIDE_CHUNK
+        b = args[ind]
+        if not isinstance(b, torch.Tensor) or b.shape[-1] != DV:
+            raise ValueError("[KeOps] Wrong value of the 'vector size' dimension for arg number %d" % ind)
+        res, launches = out, 0
+        for c0 in range(0, DV, C):
+            w = min(C, DV - c0)
+            sub = self._wide_binders.get(w)
+            if sub is None:
+                formula = "Sum_Reduction(Mult(%s,Var(%d,%d,%d)),%d)" % (etext, ind, w, cat, p.tagI)
+                t = self._init_args
+                sub = LoadKeOpsB200(t[0], t[1], t[2], t[3], t[4], formula, [], p.nargs, p.dtype, t[5], self._optional_flags)
+                self._wide_binders[w] = sub
+            a2 = list(args)
+            a2[ind] = b[..., c0:c0 + w].contiguous()
+            so = sub.genred(device_args, ranges, nx, ny, nbatchdims, None, *a2)
+            launches += sub.last_launch.get("launches", 1)
+            if res is None:
+                res = torch.empty(tuple(so.shape[:-1]) + (DV,), dtype=so.dtype, device=so.device)
+            elif tuple(res.shape) != tuple(so.shape[:-1]) + (DV,):
+                raise ValueError("[KeOps-B200] `out` must have shape %s" % (tuple(so.shape[:-1]) + (DV,),))
+            res[..., c0:c0 + w] = so
+        self.last_launch = dict(sub.last_launch, launches=launches, engine="cuda-core/wide-chunks", wide_chunks=-(-DV // C))
+        return res
 
     # ---- reference-compatible surface ----------------------------------------------------------
     def import_module(self):
@@ -142,6 +202,8 @@ class LoadKeOpsB200:
 
     def genred(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
         p = self.params
+        if self._wide is not None and len(args) == p.nargs and os.environ.get("KB200_WIDE_CHUNKS", "1") != "0":
+            return self._genred_wide(device_args, ranges, nx, ny, nbatchdims, out, *args)
         if ranges is not None and len(ranges) == 0:
             ranges = None
         if ranges is not None and int(nbatchdims or 0) > 0:

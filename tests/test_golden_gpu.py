@@ -99,3 +99,36 @@ def test_high_dimensional_gaussian_vs_oracle(cuda_device):
     out = get_binder(f, [], 4, "float32").genred_pytorch(cuda_device, None, M, N, 0, None, *targs)
     torch.cuda.synchronize()
     util.assert_close(out.cpu().numpy(), ko.genred(f, [], [x, y, b, g], "float32"), "float32", "gaussian D=300")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tagI", [0, 1])
+def test_wide_streamed_factor_is_chunked(tagI, cuda_device):
+    """dim b = 300 (the reference's final-chunk mode, GpuReduc1D_finalchunks.py): evaluated in chunks of 32 components,
+    must agree with the unchunked kernel and with the oracle; also with a user-provided ``out``."""
+    import os
+    import torch
+    from keops_b200.binder import get_binder
+    from oracle import keops_oracle as ko
+    rng = np.random.default_rng(5)
+    M, N, DV = 333, 257, 300
+    x = rng.random((M, 3)).astype(np.float32)
+    y = rng.random((N, 3)).astype(np.float32)
+    b = rng.standard_normal((N if tagI == 0 else M, DV)).astype(np.float32)
+    f = "Sum_Reduction(Exp(-SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,%d,%d),%d)" % (DV, 1 - tagI, tagI)
+    targs = [torch.from_numpy(a).to(cuda_device) for a in (x, y, b)]
+    bd = get_binder(f, [], 3, "float32")
+    out = bd.genred_pytorch(cuda_device, None, M, N, 0, None, *targs)
+    assert bd.last_launch.get("wide_chunks") == 10, bd.last_launch
+    ref = ko.genred(f, [], [x, y, b], "float32")
+    util.assert_close(out.cpu().numpy(), ref, "float32", "wide b, chunked")
+    os.environ["KB200_WIDE_CHUNKS"] = "0"
+    try:
+        plain = bd.genred_pytorch(cuda_device, None, M, N, 0, None, *targs)
+        assert bd.last_launch.get("wide_chunks") is None
+    finally:
+        os.environ.pop("KB200_WIDE_CHUNKS", None)
+    util.assert_close(out.cpu().numpy(), plain.cpu().numpy(), "float32", "wide b, chunked vs unchunked")
+    dst = torch.empty_like(out)
+    res = bd.genred_pytorch(cuda_device, None, M, N, 0, dst, *targs)
+    assert res.data_ptr() == dst.data_ptr() and torch.equal(dst, out)
