@@ -131,11 +131,13 @@ class LoadKeOpsB200:
         self._wide_binders: Dict[int, "LoadKeOpsB200"] = {}
 
     # ---- wide streamed factor (the reference's "final chunks" mode, GpuReduc1D_finalchunks.py) ----------------
-    WIDE_MIN, WIDE_CHUNK = 100, 32          # same threshold as the reference (dim > 100); chunk of the wide variable
+    # measured on B200 (D = 3 Gaussian, M = N = 5e4; experiments/wide_b_sweep.py), single kernel vs chunks of 32:
+    # dim b = 40: 4.7 / 5.0 ms, 64: 12.0 / 7.3 ms, 96: 18.8 / 11.0 ms, 300: 470 / 34 ms (chunks of 16: 51 ms, of 64: 53 ms)
+    WIDE_MIN, WIDE_CHUNK = 64, 32
 
     @staticmethod
     def _detect_wide(red: Reduction):
-        """``Sum_Reduction(E_ij * b, tagI)`` with ``E`` scalar and ``b`` a *streamed* variable of dimension >= 100 (attention-
+        """``Sum_Reduction(E_ij * b, tagI)`` with ``E`` scalar and ``b`` a *streamed* variable of dimension >= 64 (attention-
         like sums): the accumulator (dim b values per output row) does not fit the register file.  Returns
         ``(b index, dim b, b category, text of E)`` when the reduction can be evaluated chunk by chunk of ``b``."""
         if red.kind != "Sum":
@@ -173,6 +175,7 @@ class LoadKeOpsB200:
                 formula = "Sum_Reduction(Mult(%s,Var(%d,%d,%d)),%d)" % (etext, ind, w, cat, p.tagI)
                 t = self._init_args
                 sub = LoadKeOpsB200(t[0], t[1], t[2], t[3], t[4], formula, [], p.nargs, p.dtype, t[5], self._optional_flags)
+                sub._wide = None               # a chunk kernel is never chunked again
                 self._wide_binders[w] = sub
             a2 = list(args)
             a2[ind] = b[..., c0:c0 + w].contiguous()
