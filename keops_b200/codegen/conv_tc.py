@@ -34,10 +34,11 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-10"
+VERSION = "conv-tc-11"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
+ATMEM = 1                  # kb200_conv_tc_hd: resident operand in TMEM (KB200_CONV_TC_ATMEM=0: in shared memory)
 MULTICAST = 0              # kb200_conv_tc_hd: 2-CTA clusters multicasting the streamed k-blocks (KB200_CONV_TC_MC=1 enables).
                            # Correct (tests pass with it on) but no faster: D=64, M=N=1e6 717 ms without, 726 ms with -- the
                            # bound is the shared-memory port (operand reads of M=128 x N=128 MMAs + TMA fills), not L2
@@ -308,6 +309,8 @@ class ConvTensorCore:
         self.hd = is_hd(D)
         # CTA pairs sharing the streamed k-blocks by TMA multicast (high-dimensional kernel only)
         self.mc = 1 if (self.hd and os.environ.get("KB200_CONV_TC_MC", str(MULTICAST)) != "0") else 0
+        # resident operand in tensor memory: 32 columns per k-block next to the 2 x 128 accumulator columns (K <= 512)
+        self.atmem = 1 if (self.hd and self.KBM + 1 <= 8 and os.environ.get("KB200_CONV_TC_ATMEM", str(ATMEM)) != "0") else 0
         self.DPG = 64 * self.KBM + self.REM
         self.W = DB + 1 - self.PEN                   # floats per column of the b tile
         with open(_COMMON_PATH) as f:
@@ -317,10 +320,10 @@ class ConvTensorCore:
         self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
         defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
                 "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n#define CT_POLY %d\n#define CT_ASTREAM %d\n"
-                "#define CT_LSE %d\n#define CT_MC %d\n"
+                "#define CT_LSE %d\n#define CT_MC %d\n#define CT_ATMEM %d\n"
                 % (D, DB, self.KBM, self.REM, self.STAGES, HS, int(os.environ.get("CT_DBG", 0)), self.PEN,
                    0 if lse else int(os.environ.get("CT_POLY", POLY)),
-                   1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0, 1 if lse else 0, self.mc))
+                   1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0, 1 if lse else 0, self.mc, self.atmem))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(True), "kb200_convtc", VERSION)
         self.smem = smem_bytes(D, DB, self.STAGES, lse)
@@ -402,7 +405,7 @@ class ConvTensorCore:
                 gx += gx & 1               # whole CTA pairs; the odd block out computes rows >= M and stores nothing
             capi.launch(self.fn_conv, stream, (gx, nchunks), (THREADS,), self.smem,
                         [map_x, map_y, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
-                         ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr())])
+                         ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr()), ptr(xbf.data_ptr())])
         else:
             capi.launch(self.fn_conv, stream, (-(-M // BM), nchunks), (THREADS,), self.smem,
                         [map_x, map_xr, map_y, map_yr, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
@@ -421,7 +424,8 @@ _cache: Dict[tuple, ConvTensorCore] = {}
 
 
 def get(D: int, DB: int, device: int, lse: bool = False) -> ConvTensorCore:
-    key = (D, DB, device, bool(lse), os.environ.get("KB200_CONV_TC_MC", str(MULTICAST)), os.environ.get("CT_POLY", str(POLY)))
+    key = (D, DB, device, bool(lse), os.environ.get("KB200_CONV_TC_MC", str(MULTICAST)), os.environ.get("CT_POLY", str(POLY)),
+           os.environ.get("KB200_CONV_TC_ATMEM", str(ATMEM)))
     with _lock:
         k = _cache.get(key)
         if k is None:

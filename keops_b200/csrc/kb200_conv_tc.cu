@@ -557,9 +557,16 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
                                                  traffic of the streamed side.  Measured: no gain (717 vs 726 ms at D = 64,
                                                  M = N = 1e6) -- the kernel is bound by the shared-memory port, not by L2  */
 #endif
+#ifndef CT_ATMEM
+#define CT_ATMEM 0                            /* 1 (K <= 512): the resident row block lives in tensor memory (32 columns per
+                                                 k-block, written once by the epilogue warps with tcgen05.st) and enters the
+                                                 MMAs as a TMEM A operand: the shared-memory port, which bounds this kernel,
+                                                 only carries the streamed side                                          */
+#endif
 #define HD_BLK 16384                          /* 128 rows x 64 bf16                                              */
 #define HD_STAGE_BYTES ((1 + CT_ASTREAM) * HD_BLK)
-#define HD_A_BYTES (CT_ASTREAM ? 0 : CT_KB * HD_BLK)
+#define HD_A_BYTES ((CT_ASTREAM || CT_ATMEM) ? 0 : CT_KB * HD_BLK)
+#define HD_TMEM_A (CT_NBUF * CT_BN)           /* first TMEM column of the resident operand (after the accumulators)   */
 #define HD_QUART (CT_BN / 4)
 #define HD_X_BYTES (3 * 128 * CT_OUTW * 4)    /* sums of column quarters 1..3, added to quarter 0 at the end      */
 #define HD_SMEM_BYTES (1024 + HD_A_BYTES + CT_STAGES * HD_STAGE_BYTES + CT_HS * CT_H_BYTES + HD_X_BYTES + 640) /* mirrored in conv_tc.py */
@@ -572,7 +579,7 @@ __launch_bounds__(CT_THREADS, 1)
 kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_y,
                  const long long nrow, const long long ncol, const long long chunk_cols,
                  const float* __restrict__ bpad, const float* __restrict__ xsq, const float* __restrict__ coef,
-                 float* __restrict__ out) {
+                 float* __restrict__ out, const unsigned int* __restrict__ xbf) {
   extern __shared__ unsigned char ct_raw[];
   const u32 raw = kt_smem(ct_raw);
   const u32 base = (raw + 1023u) & ~1023u;
@@ -603,7 +610,7 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
     for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1 + CT_MC); }
     for (int b = 0; b < CT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, CT_EPI_WARPS); }
     for (int h = 0; h < CT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, CT_EPI_WARPS); }
-    kt_mbar_init(bAFull, 1);
+    kt_mbar_init(bAFull, CT_ATMEM ? CT_EPI_WARPS : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -621,7 +628,7 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-#if !CT_ASTREAM
+#if !CT_ASTREAM && !CT_ATMEM
     if (kt_elect()) {
       kt_mbar_expect_tx(bAFull, HD_A_BYTES);
       for (int kb = 0; kb < CT_KB; kb++) kt_tma_2d(sA + kb * HD_BLK, &map_x, kb * 64, (int)row_base, bAFull);
@@ -660,6 +667,7 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
     // ===================== MMA issuer: a tile accumulates over the CT_KB k-blocks =====================
 #if !CT_ASTREAM
     kt_mbar_wait(bAFull, 0);
+    kt_fence_after();
 #endif
     int it = 0;
     for (int t = 0; t < ntiles; t++) {
@@ -672,11 +680,17 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
         kt_fence_after();
         if (kt_elect()) {
           const u32 d = tmem + (u32)(buf * CT_BN);
-          const u64 ad = kt_smem_desc(CT_ASTREAM ? (sB + s * HD_STAGE_BYTES + HD_BLK) : (sA + kb * HD_BLK), 128);
           const u64 bd = kt_smem_desc(sB + s * HD_STAGE_BYTES, 128);
+#if CT_ATMEM
+#pragma unroll
+          for (int k = 0; k < 4; k++)                      // 16 bf16 of K = 8 TMEM columns per MMA
+            kt_mma_bf16_ts(d, tmem + (u32)(HD_TMEM_A + kb * 32 + k * 8), bd + (u64)(2 * k), CT_IDESC, (u32)((kb | k) != 0));
+#else
+          const u64 ad = kt_smem_desc(CT_ASTREAM ? (sB + s * HD_STAGE_BYTES + HD_BLK) : (sA + kb * HD_BLK), 128);
 #pragma unroll
           for (int k = 0; k < 4; k++)
             kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), CT_IDESC, (u32)((kb | k) != 0));
+#endif
 #if CT_MC
           kt_mma_commit_mc(bEmpty + 8 * s, (unsigned short)3);   // releases the slot in both CTAs of the pair
 #else
@@ -696,6 +710,23 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
     const float cl = coef[0] * CT_LOG2E;
     const float c2 = -2.0f * cl;
     const float rowc = live ? cl * xsq[i] : 0.0f;
+#if CT_ATMEM
+    // the resident operand: this thread's row of bf16 pairs, k-blocks part, part + 4, ... -> 32 TMEM columns each
+    for (int kb = part; kb < CT_KB; kb += 4) {
+      u32 av[32];
+      const uint4* src = reinterpret_cast<const uint4*>(xbf + (live ? i : 0) * (CT_DPG / 2) + kb * 32);
+#pragma unroll
+      for (int v = 0; v < 8; v++) {
+        const uint4 w4 = live ? __ldg(src + v) : make_uint4(0u, 0u, 0u, 0u);
+        av[4 * v + 0] = w4.x; av[4 * v + 1] = w4.y; av[4 * v + 2] = w4.z; av[4 * v + 3] = w4.w;
+      }
+      kt_tmem_st32(tmem + ((u32)(q * 32) << 16) + (u32)(HD_TMEM_A + kb * 32), av);
+    }
+    kt_tmem_wait_st();
+    kt_fence_before();
+    __syncwarp();
+    if (lane == 0) kt_mbar_arrive(bAFull);
+#endif
     float acc[CT_DB];
 #pragma unroll
     for (int d = 0; d < CT_DB; d++) acc[d] = 0.0f;
