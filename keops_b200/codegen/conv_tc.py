@@ -34,7 +34,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-11"
+VERSION = "conv-tc-12"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
@@ -311,6 +311,9 @@ class ConvTensorCore:
         self.mc = 1 if (self.hd and os.environ.get("KB200_CONV_TC_MC", str(MULTICAST)) != "0") else 0
         # resident operand in tensor memory: 32 columns per k-block next to the 2 x 128 accumulator columns (K <= 512)
         self.atmem = 1 if (self.hd and self.KBM + 1 <= 8 and os.environ.get("KB200_CONV_TC_ATMEM", str(ATMEM)) != "0") else 0
+        # 256-row kernel: the same with single-buffered accumulators, when every k-block is 64 columns wide (8 <= D <= 20)
+        self.atmem2 = 1 if (not self.hd and self.REM == 64 and self.PEN == 1
+                            and os.environ.get("KB200_CONV_TC_ATMEM", str(ATMEM)) != "0") else 0
         self.DPG = 64 * self.KBM + self.REM
         self.W = DB + 1 - self.PEN                   # floats per column of the b tile
         with open(_COMMON_PATH) as f:
@@ -320,10 +323,10 @@ class ConvTensorCore:
         self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
         defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
                 "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n#define CT_POLY %d\n#define CT_ASTREAM %d\n"
-                "#define CT_LSE %d\n#define CT_MC %d\n#define CT_ATMEM %d\n"
+                "#define CT_LSE %d\n#define CT_MC %d\n#define CT_ATMEM %d\n#define CT_ATMEM2 %d\n"
                 % (D, DB, self.KBM, self.REM, self.STAGES, HS, int(os.environ.get("CT_DBG", 0)), self.PEN,
                    0 if lse else int(os.environ.get("CT_POLY", POLY)),
-                   1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0, 1 if lse else 0, self.mc, self.atmem))
+                   1 if (self.hd and self.KBM + 1 > HD_MAX_KB) else 0, 1 if lse else 0, self.mc, self.atmem, self.atmem2))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(True), "kb200_convtc", VERSION)
         self.smem = smem_bytes(D, DB, self.STAGES, lse)
@@ -410,7 +413,7 @@ class ConvTensorCore:
             capi.launch(self.fn_conv, stream, (-(-M // BM), nchunks), (THREADS,), self.smem,
                         [map_x, map_xr, map_y, map_yr, i64(M), i64(N), i64(tiles_per_chunk * BN), ptr(bpad.data_ptr()),
                          ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr()),
-                         ptr(clock_probe.data_ptr() if clock_probe is not None else 0)])
+                         ptr(clock_probe.data_ptr() if clock_probe is not None else 0), ptr(xbf.data_ptr())])
         if nchunks > 1:
             capi.launch(self.fn_combine, stream, (-(-(M * self.DB) // 256),), (256,), 0,
                         [i64(M * self.DB), i32(nchunks), ptr(dst.data_ptr()), ptr(out.data_ptr())])

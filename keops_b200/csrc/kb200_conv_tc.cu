@@ -57,7 +57,13 @@
 #endif
 #define CT_BM 256                             /* rows per CTA: two 128-row accumulators                          */
 #define CT_BN 128                             /* columns per tile (= N of one tcgen05.mma)                       */
-#define CT_NBUF 2                             /* TMEM accumulator buffers per row block: 2 x 2 x 128 = 512 cols  */
+#ifndef CT_ATMEM2
+#define CT_ATMEM2 0                           /* kb200_conv_tc (256 rows), CT_REM == 64 only: both resident row blocks in
+                                                 tensor memory (TS-form MMAs), accumulators single-buffered: 2 x 128
+                                                 accumulator + 2 x CT_DPG / 2 operand columns                            */
+#endif
+#define CT_NBUF (CT_ATMEM2 ? 1 : 2)           /* TMEM accumulator buffers per row block (2: 2 x 2 x 128 = 512 cols)      */
+#define CT_TMEM_A2 256                        /* CT_ATMEM2: first operand column                                        */
 #ifndef CT_PEN
 #define CT_PEN 1                              /* 1: -|y|^2/2 rides in three extra K columns; 0: |y|^2 is added in the
                                                  epilogue (one more FFMA per pair) when that saves a K block       */
@@ -68,7 +74,7 @@
 #define CT_TILE_BYTES(rows) ((rows) * 128)
 #define CT_RTILE_BYTES(rows) ((rows) * CT_REM * 2)
 #define CT_BLK_BYTES(rows) (CT_KBM * CT_TILE_BYTES(rows) + CT_RTILE_BYTES(rows))
-#define CT_A_BYTES (2 * CT_BLK_BYTES(128))
+#define CT_A_BYTES (CT_ATMEM2 ? 0 : 2 * CT_BLK_BYTES(128))
 #define CT_B_BYTES CT_BLK_BYTES(CT_BN)
 #define CT_H_BYTES (CT_BN * CT_W * 4)         /* one b tile                                                      */
 #define CT_X_BYTES (CT_BM * CT_OUTW * 4)      /* exchange of the second column half's sums at the end            */
@@ -339,7 +345,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
               const __grid_constant__ KtTensorMap map_y, const __grid_constant__ KtTensorMap map_yr,
               const long long nrow, const long long ncol, const long long chunk_cols,
               const float* __restrict__ bpad, const float* __restrict__ xsq, const float* __restrict__ coef,
-              float* __restrict__ out, unsigned long long* __restrict__ clk) {
+              float* __restrict__ out, unsigned long long* __restrict__ clk, const unsigned int* __restrict__ xbf) {
   extern __shared__ unsigned char ct_raw[];
   const u32 raw = kt_smem(ct_raw);
   const u32 base = (raw + 1023u) & ~1023u;                       // swizzle atoms need (up to) 1024-byte alignment
@@ -379,7 +385,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
     for (int s = 0; s < CT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
     for (int b = 0; b < 2 * CT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, CT_EPI_WARPS / 2); }
     for (int h = 0; h < CT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, CT_EPI_WARPS); }
-    kt_mbar_init(bAFull, 1);
+    kt_mbar_init(bAFull, CT_ATMEM2 ? CT_EPI_WARPS : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -393,7 +399,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
-    if (kt_elect()) {
+    if (!CT_ATMEM2 && kt_elect()) {
       kt_mbar_expect_tx(bAFull, CT_A_BYTES);
       for (int rb = 0; rb < 2; rb++) {
         for (int kb = 0; kb < CT_KBM; kb++)
@@ -419,6 +425,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (converged warp, one elected lane issues) =====================
     kt_mbar_wait(bAFull, 0);
+    kt_fence_after();
     for (int t = 0; t < ntiles; t++) {
       const int s = t % CT_STAGES, buf = t % CT_NBUF;
       kt_mbar_wait(bFull + 8 * s, (t / CT_STAGES) & 1);
@@ -428,6 +435,16 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
         kt_fence_after();
         if (kt_elect()) {
           const u32 d = tmem + (u32)((buf * 2 + rb) * CT_BN);
+#if CT_ATMEM2
+#pragma unroll
+          for (int kb = 0; kb <= CT_KBM; kb++) {       // CT_REM == 64: every k-block is 64 wide, 128-byte swizzled
+            const u64 bd = kt_smem_desc(sB + s * CT_B_BYTES + kb * CT_TILE_BYTES(CT_BN), 128);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              kt_mma_bf16_ts(d, tmem + (u32)(CT_TMEM_A2 + rb * (CT_DPG / 2) + kb * 32 + k * 8), bd + (u64)(2 * k), CT_IDESC,
+                             (u32)((kb | k) != 0));
+          }
+#else
 #pragma unroll
           for (int kb = 0; kb < CT_KBM; kb++) {
             const u64 ad = kt_smem_desc(sA + rb * CT_BLK_BYTES(128) + kb * CT_TILE_BYTES(128), 128);
@@ -443,6 +460,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
             for (int k = 0; k < CT_REM / 16; k++)
               kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), CT_IDESC, (u32)((CT_KBM | k) != 0));
           }
+#endif
           kt_mma_commit(bTFull + 8 * (buf * 2 + rb));  // this accumulator is complete
           if (rb == 1) kt_mma_commit(bEmpty + 8 * s);  // smem stage may be refilled once these MMAs have read it
         }
@@ -460,6 +478,23 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
     const float cl = coef[0] * CT_LOG2E;              // exponent = cl * |x - y|^2  (base 2)
     const float c2 = -2.0f * cl;
     const float rowc = live ? cl * xsq[i] : 0.0f;
+#if CT_ATMEM2
+    // the resident operand: this thread's row of bf16 pairs, k-blocks half, half + 2, ... -> 32 TMEM columns each
+    for (int kb = half; kb <= CT_KBM; kb += 2) {
+      u32 av[32];
+      const uint4* src = reinterpret_cast<const uint4*>(xbf + (live ? i : 0) * (CT_DPG / 2) + kb * 32);
+#pragma unroll
+      for (int v = 0; v < 8; v++) {
+        const uint4 w4 = live ? __ldg(src + v) : make_uint4(0u, 0u, 0u, 0u);
+        av[4 * v + 0] = w4.x; av[4 * v + 1] = w4.y; av[4 * v + 2] = w4.z; av[4 * v + 3] = w4.w;
+      }
+      kt_tmem_st32(tmem + ((u32)(q * 32) << 16) + (u32)(CT_TMEM_A2 + rb * (CT_DPG / 2) + kb * 32), av);
+    }
+    kt_tmem_wait_st();
+    kt_fence_before();
+    __syncwarp();
+    if (lane == 0) kt_mbar_arrive(bAFull);
+#endif
     float acc[CT_DB];
 #pragma unroll
     for (int d = 0; d < CT_DB; d++) acc[d] = 0.0f;
