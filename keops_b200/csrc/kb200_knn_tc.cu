@@ -25,6 +25,10 @@
 //   warps 2..9 = epilogue: one thread per row, tcgen05.ld of its 128 accumulators, FMNMX3 max-reduction against
 //   tau_i; survivors are appended to the row's candidate list and update Theta_i (register-resident list).
 //   4-stage smem ring, double-buffered TMEM accumulators (2 row blocks x 2 buffers x 128 columns = 512).
+//   (Measured alternative, not kept: two threads per row, one per 64-column half as in kb200_conv_tc -- ncu shows the
+//   one-thread-per-row epilogue latency-bound (tensor pipe 47 %, ALU 40 %, issue 32 % busy) -- but each half then
+//   thresholds on its own K-th best bound: 324 instead of ~200 candidates per row at D = 64, K = 10, N = 1e6, the
+//   filter 158 -> 180 ms and most rows overflow the candidate slots.)
 // kb200_knn_prep   : fp32 -> bf16 operand rows (data, penalty columns, zero padding) + per-row penalty terms.
 // kb200_knn_select : one warp per row, exact distances of the candidates + ordered top-K (ties -> smallest j).
 //
