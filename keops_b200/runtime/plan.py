@@ -224,8 +224,8 @@ def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int,
         if ns > 1 and ns * nrow * dimpart * esz > ws_limit_bytes:
             break
         waves = -(-(gx * ns) // slots)
-        # cost in tile units: per-CTA prologue/epilogue overhead ~ 2 tiles, combine ~ ns/8 tiles
-        cost = waves * (tiles_per + 2.0 + (split_penalty_tiles if ns > 1 else 0.0)) + (0.25 * ns if ns > 1 else 0.0)
+        # cost in tile units: per-CTA prologue/epilogue overhead ~ 512 streamed rows, combine ~ 64 rows per split
+        cost = waves * (tiles_per + 512.0 / TJ + (split_penalty_tiles if ns > 1 else 0.0)) + (64.0 / TJ * ns if ns > 1 else 0.0)
         if best is None or cost < best[0] * 0.98:
             best = (cost, ns, tiles_per * TJ)
     return best[1], best[2]
@@ -246,7 +246,8 @@ def launch_segments(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: i
     ns_all, chunk_all = launch_shape(nrow, ncol, rows_per_block, TJ, slots, dimpart, esz, ws_limit_bytes=ws_limit_bytes,
                                      split_penalty_tiles=split_penalty_tiles)
     tiles_all = -(-ntiles // ns_all)
-    cost_all = -(-(gx * ns_all) // slots) * (tiles_all + 2.0 + (split_penalty_tiles if ns_all > 1 else 0.0)) + (0.25 * ns_all if ns_all > 1 else 0.0)
+    ovh, cmb = 512.0 / TJ, 64.0 / TJ
+    cost_all = -(-(gx * ns_all) // slots) * (tiles_all + ovh + (split_penalty_tiles if ns_all > 1 else 0.0)) + (cmb * ns_all if ns_all > 1 else 0.0)
     full_waves, rem = divmod(gx, slots)
     if full_waves == 0 or rem == 0:
         return [(0, nrow, ns_all, chunk_all)]
@@ -255,8 +256,8 @@ def launch_segments(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: i
     ns_b, chunk_b = launch_shape(nrow_b, ncol, rows_per_block, TJ, slots, dimpart, esz, ws_limit_bytes=ws_limit_bytes,
                                  split_penalty_tiles=split_penalty_tiles)
     tiles_b = -(-ntiles // ns_b)
-    cost_tail = full_waves * (ntiles + 2.0) + -(-(rem * ns_b) // slots) * (tiles_b + 2.0 + (split_penalty_tiles if ns_b > 1 else 0.0)) \
-        + (0.25 * ns_b if ns_b > 1 else 0.0) + 1.0
+    cost_tail = full_waves * (ntiles + ovh) + -(-(rem * ns_b) // slots) * (tiles_b + ovh + (split_penalty_tiles if ns_b > 1 else 0.0)) \
+        + (cmb * ns_b if ns_b > 1 else 0.0) + ovh / 2
     if cost_tail < cost_all:
         return [(0, rows_a, 1, ntiles * TJ), (rows_a, nrow, ns_b, chunk_b)]
     return [(0, nrow, ns_all, chunk_all)]
