@@ -347,7 +347,7 @@ class LoadKeOpsB200:
 
     def _genred_lse_tc(self, dev, cl, nrow, ncol, out, args):
         """``Max_SumShiftExp[Weight]`` of ``a_j + c |x_i - y_j|^2`` (soft-min of a Sinkhorn iteration) in dimension
-        D >= 8: the same tensor-core kernels in LSE mode (``codegen/conv_tc.py``), same tolerance guard."""
+        D >= 5: the same tensor-core kernels in LSE mode (``codegen/conv_tc.py``), same tolerance guard."""
         p = self.params
         row_ind, col_ind, D, a_ind, w_ind, DB, terms = cl
         index = dev.index if dev.index is not None else torch.cuda.current_device()

@@ -3,7 +3,7 @@
 ``Sum_Reduction(Exp(c * |x_i - y_j|^2) * b_j, tagI)`` -- the Gaussian convolution / kernel matrix-vector product
 behind ``KernelSolve`` (``pykeops/pykeops/torch/operations.py:29-87``) -- costs the reference's generic
 ``GpuReduc1D`` kernel 2 D + 2 FP32 instructions and one ``ex2`` per pair
-(``keopscore/keopscore/mapreduce/gpu/GpuReduc1D.py:70-90``).  For ``D >= 8`` the squared distance *is* a dense
+(``keopscore/keopscore/mapreduce/gpu/GpuReduc1D.py:70-90``).  For ``D >= 5`` the squared distance *is* a dense
 contraction, so here it runs as a tcgen05 GEMM on three-term bf16 splits of the fp32 coordinates (six
 products: fp32-grade accuracy, see ``keops_b200/csrc/kb200_conv_tc.cu`` for the bound) and the CUDA cores only
 do ``ex2`` + the weighted accumulation: the kernel moves from the FP32-pipe roofline to the MUFU one.
@@ -38,6 +38,9 @@ VERSION = "conv-tc-12"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
+# smallest dimension sent to the tensor cores.  Measured at M = N = 1e6 (tensor-core / CUDA-core kernel): D = 4: 253 / 319 ms,
+# D = 5: 251 / 380 ms, D = 6: 251 / 447 ms, D = 7: 251 / 508 ms, D = 8: 251 / 575 ms; D = 3 stays on the CUDA cores (259 ms)
+DMIN = 5
 ATMEM = 1                  # kb200_conv_tc_hd: resident operand in TMEM (KB200_CONV_TC_ATMEM=0: in shared memory)
 MULTICAST = 0              # kb200_conv_tc_hd: 2-CTA clusters multicasting the streamed k-blocks (KB200_CONV_TC_MC=1 enables).
                            # Correct (tests pass with it on) but no faster: D=64, M=N=1e6 717 ms without, 726 ms with -- the
@@ -132,7 +135,7 @@ def match(red: Reduction):
 def match_lse(red: Reduction):
     """``(row_var, col_var, D, a_var or None, weight_var or None, DB, coef_terms)`` for
     ``Max_SumShiftExp[Weight]_Reduction(a_j + c |x_i - y_j|^2, tagI[, b_j])`` -- the soft-min of a Sinkhorn iteration
-    (BASELINE configs[3] in dimension D >= 8): ``a`` an optional streamed scalar variable (added or the minuend of a
+    (BASELINE configs[3] in dimension D >= 5): ``a`` an optional streamed scalar variable (added or the minuend of a
     subtraction), ``b`` absent (weight 1) or a streamed variable; ``None`` otherwise."""
     if red.kind != "LSE" or red.formula.dim != 1:
         return None
@@ -212,7 +215,7 @@ def coefficient(terms, args, device):
 
 def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, use_fast_math: bool,
              sum_scheme: str = "block_sum", dtype_acc: str = "float32"):
-    """The tensor-core path pays off once 2 D + 2 FP32 instructions per pair exceed the MUFU bound (D >= 8) and the
+    """The tensor-core path pays off once 2 D + 2 FP32 instructions per pair exceed the MUFU bound (measured: from D = 4, used from D = 5) and the
     grid fills the machine with 256-row CTAs; it reproduces the default (block_sum, fp32 accumulation) scheme."""
     if os.environ.get("KB200_CONV_TC", "1") == "0" or dtype != "float32" or nbatch != 1 or not use_fast_math:
         return None
@@ -222,7 +225,7 @@ def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, use_
     if m is None:
         return None
     D = m[2]
-    dmin = int(os.environ.get("KB200_CONV_TC_DMIN", 8))
+    dmin = int(os.environ.get("KB200_CONV_TC_DMIN", DMIN))
     kbm, rem, _ = layout(D)
     if D < dmin or D > HD_MAX_D or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
         return None
@@ -291,7 +294,7 @@ def eligible_lse(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, 
     if m is None:
         return None
     D, DB = m[2], m[5]
-    dmin = int(os.environ.get("KB200_CONV_TC_DMIN", 8))
+    dmin = int(os.environ.get("KB200_CONV_TC_DMIN", DMIN))
     if D < dmin or D > HD_MAX_D or layout(D)[2] != 1 or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
         return None
     if smem_bytes(D, DB, lse=True) > 227 * 1024:

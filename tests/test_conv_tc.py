@@ -110,6 +110,8 @@ CASES = [
     # D, DB, nx, ny, tagI, coefficient spelling
     (16, 1, 9000, 7001, 0, "-Var(3,1,2)*"),           # KernelSolve formula, ragged last tile
     (8, 3, 8192, 4096, 0, "-Var(3,1,2)*"),            # penalty columns inside K, vector b
+    (5, 1, 9000, 5000, 0, "-Var(3,1,2)*"),            # smallest dimension on the tensor cores (K = 33 -> 64)
+    (6, 2, 3000, 8192, 1, "-IntCst(3)*"),             # reduction over i: 8192 output rows follow j
     (13, 2, 8300, 5000, 0, "-IntCst(2)*"),            # constant coefficient, K = 64 + 16
     (20, 1, 8192, 3000, 0, "-Var(3,1,2)*Var(3,1,2)*"),
     (16, 2, 5000, 9000, 1, "-Var(3,1,2)*"),           # reduction over i
