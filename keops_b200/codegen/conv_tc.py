@@ -34,7 +34,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-12"
+VERSION = "conv-tc-13"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
@@ -371,11 +371,11 @@ class ConvTensorCore:
         ysq = torch.empty(N, dtype=torch.float32, device=dev)
         xsq = torch.empty(M, dtype=torch.float32, device=dev)
         bpad = torch.empty(npad * self.W, dtype=torch.float32, device=dev)
-        capi.launch(self.fn_prep, stream, (-(-npad // 256),), (256,), 0,
+        capi.launch(self.fn_prep, stream, (-(-npad // 8),), (256,), 0,            # one warp per row
                     [i64(N), i64(npad), ptr(y.data_ptr()), ptr(shift.data_ptr()), ptr(ybf.data_ptr()), ptr(ysq.data_ptr()),
                      ptr(b.data_ptr()), ptr(bpad.data_ptr()), i32(0), ptr(acol.data_ptr() if acol is not None else 0),
                      ptr(coef.data_ptr())])
-        capi.launch(self.fn_prep, stream, (-(-M // 256),), (256,), 0,
+        capi.launch(self.fn_prep, stream, (-(-M // 8),), (256,), 0,
                     [i64(M), i64(M), ptr(x.data_ptr()), ptr(shift.data_ptr()), ptr(xbf.data_ptr()), ptr(xsq.data_ptr()),
                      ptr(0), ptr(0), i32(1), ptr(0), ptr(coef.data_ptr())])
         tol = float(os.environ.get("KB200_CONV_TC_TOL", TOL))

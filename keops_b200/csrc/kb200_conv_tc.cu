@@ -94,23 +94,25 @@
 //   side 1 (output,   x): [ x1 | x1 | x2 | x1 | x2 | x3 |  1   1   1  | 0 .. ],  sq[r] = |x - shift|^2
 //   (v1, v2, v3 = successive bf16 round-to-nearest remainders of the shifted coordinate)
 // ------------------------------------------------------------------------------------------------
+// One warp per row: lanes stride over the coordinates, so that the fp32 row is read and each of the six bf16 blocks is
+// written with coalesced accesses (a thread per row scatters 2-byte stores 2 * CT_DPG bytes apart: at D = 784 the prep of
+// 1e5 points took longer than a tenth of the main kernel).  The squared norm is a fixed-order lane tree (deterministic).
 extern "C" __global__ void __launch_bounds__(256)
 kb200_conv_prep(const long long n, const long long npad, const float* __restrict__ a, const float* __restrict__ shift,
                 unsigned short* __restrict__ abf, float* __restrict__ sq, const float* __restrict__ b,
                 float* __restrict__ bpad, const int side, const float* __restrict__ acol,
                 const float* __restrict__ coef) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (side == 0 && r < npad) {
-#pragma unroll
-    for (int d = 0; d < CT_DB; d++) bpad[r * CT_W + (1 - CT_PEN) + d] = (r < n) ? b[r * CT_DB + d] : 0.0f;
-    if (CT_PEN == 0 && r >= n) bpad[r * CT_W] = 0.0f;
+    for (int d = lane; d < CT_DB; d += 32) bpad[r * CT_W + (1 - CT_PEN) + d] = (r < n) ? b[r * CT_DB + d] : 0.0f;
+    if (CT_PEN == 0 && r >= n && lane == 0) bpad[r * CT_W] = 0.0f;
   }
   if (r >= n) return;
   const float* row = a + r * CT_D;
   unsigned short* orow = abf + r * CT_DPG;
   float s = 0.0f;
-#pragma unroll 4
-  for (int k = 0; k < CT_D; k++) {
+  for (int k = lane; k < CT_D; k += 32) {
     const float v = row[k] - (shift ? shift[k] : 0.0f);
     s = fmaf(v, v, s);
     const unsigned short p1 = kt_bf16_rn(v);
@@ -125,6 +127,10 @@ kb200_conv_prep(const long long n, const long long npad, const float* __restrict
       orow[3 * CT_D + k] = p1; orow[4 * CT_D + k] = p2; orow[5 * CT_D + k] = p3;
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int k = CT_NCOL + lane; k < CT_DPG; k += 32) orow[k] = 0;
+  if (lane != 0) return;
   if (CT_PEN == 0) {
     if (side == 0) bpad[r * CT_W] = s;
   } else if (side == 0) {
@@ -139,7 +145,6 @@ kb200_conv_prep(const long long n, const long long npad, const float* __restrict
     orow[6 * CT_D] = 0x3F80u; orow[6 * CT_D + 1] = 0x3F80u; orow[6 * CT_D + 2] = 0x3F80u;                   // 1.0
   }
   sq[r] = s;
-  for (int k = CT_NCOL; k < CT_DPG; k++) orow[k] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
