@@ -24,7 +24,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_knn_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")      # PTX wrappers, prepended (NVRTC has no include path)
-VERSION = "knn-tc-5"
+VERSION = "knn-tc-7"
 BM, BN, STAGES, HS = 256, 128, 4, 16
 ROW_BATCH = 1 << 20          # rows per filter launch: bounds the candidate workspace (CAP * 4 bytes per row)
 _lock = threading.RLock()
@@ -56,7 +56,10 @@ def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int) -> O
     if m is None:
         return None
     D = m[2]
-    if D < 16 or D > 141 or red.K > 16 or nrow < 8192 or ncol < 4096 or ncol >= (1 << 31) - BN:
+    # few rows against many columns (the reference's own KNN benchmark shape, 1e4 queries vs 1e6 points): the filter
+    # splits the column range over gridDim.y, so the tensor-core path already pays off from ~1000 rows
+    min_rows = 8192 if ncol < 65536 else 1024
+    if D < 16 or D > 141 or red.K > 16 or nrow < min_rows or ncol < 4096 or ncol >= (1 << 31) - BN:
         return None                      # D <= 141: operand tiles of 2 + 4 stages must fit 227 KB of shared memory
     return m
 
@@ -97,6 +100,8 @@ class KnnTensorCore:
             self.fn_prep = self.module.function("kb200_knn_prep")
             self.fn_filter = self.module.function("kb200_knn_filter")
             self.fn_select = self.module.function("kb200_knn_select")
+            self.fn_merge = self.module.function("kb200_knn_merge")
+            self.sm_count = capi.device_info(device)["sm_count"]
             capi.set_max_dynamic_smem(self.fn_filter, self.smem)
 
     def _maps(self, abf, n, box_rows):
@@ -123,8 +128,15 @@ class KnnTensorCore:
         capi.launch(self.fn_prep, stream, (-(-N // 256),), (256,), 0,
                     [i64(N), ptr(y.data_ptr()), ptr(ybf.data_ptr()), ptr(ypen.data_ptr()), i32(0)])
         map_y, map_yr = self._maps(ybf, N, BN)
+        # column splits: with fewer 256-row blocks than SMs, the column range is divided over gridDim.y
+        nblocks = -(-min(M, ROW_BATCH) // BM)
+        nsplit = 1
+        if os.environ.get("KB200_KNN_TC_SPLIT", "1") != "0" and nblocks < self.sm_count:
+            nsplit = max(1, min(self.sm_count // nblocks, ntiles // 64, 32))
+        tiles_per_split = -(-ntiles // nsplit)
+        nsplit = -(-ntiles // tiles_per_split)
         overflow_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        overflow_rows = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        overflow_rows = torch.empty(max(M, 1) * nsplit, dtype=torch.int32, device=dev)
         for r0 in range(0, M, ROW_BATCH):
             m = min(ROW_BATCH, M - r0)
             xs = x[r0:r0 + m]
@@ -133,40 +145,46 @@ class KnnTensorCore:
             capi.launch(self.fn_prep, stream, (-(-m // 256),), (256,), 0,
                         [i64(m), ptr(xs.data_ptr()), ptr(xbf.data_ptr()), ptr(xpen.data_ptr()), i32(1)])
             map_x, map_xr = self._maps(xbf, m, 128)
-            cand = torch.empty(m * self.cap, dtype=torch.int32, device=dev)
-            count = torch.empty(m, dtype=torch.int32, device=dev)
+            cand = torch.empty(m * nsplit * self.cap, dtype=torch.int32, device=dev)
+            count = torch.empty(m * nsplit, dtype=torch.int32, device=dev)
+            part = torch.empty(m * nsplit * self.K * 2 if nsplit > 1 else 1, dtype=torch.float32, device=dev)
             if os.environ.get("KT_TIME"):
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record(stream_obj)
-            capi.launch(self.fn_filter, stream, (-(-m // BM),), (320,), self.smem,
+            capi.launch(self.fn_filter, stream, (-(-m // BM), nsplit), (320,), self.smem,
                         [map_x, map_xr, map_y, map_yr, i64(m), i64(N), ptr(ypen.data_ptr()), ptr(xpen.data_ptr()),
-                         ptr(cand.data_ptr()), ptr(count.data_ptr())])
+                         ptr(cand.data_ptr()), ptr(count.data_ptr()), i32(tiles_per_split)])
             if os.environ.get("KT_TIME"):
                 ev1.record(stream_obj)
                 torch.cuda.synchronize()
-                print("KT_TIME filter %.3f ms (BN=%d STAGES=%d DBG=%s)" % (ev0.elapsed_time(ev1), BN, self.STAGES, os.environ.get("KT_DBG", "0")))
-            # select writes rows r0.. of `out`; overflow rows are reported relative to the batch
+                print("KT_TIME filter %.3f ms (BN=%d STAGES=%d DBG=%s nsplit=%d)" % (ev0.elapsed_time(ev1), BN, self.STAGES, os.environ.get("KT_DBG", "0"), nsplit))
+            # select writes rows r0.. of `out` (or per-split lists); overflow rows are reported relative to the batch
             ov_before = overflow_count.clone() if r0 else None
-            capi.launch(self.fn_select, stream, (-(-m // 8),), (256,), 0,
+            out_ptr = out.data_ptr() + r0 * self.outw * 4
+            capi.launch(self.fn_select, stream, (-(-(m * nsplit) // 8),), (256,), 0,
                         [i64(m), i64(N), ptr(xs.data_ptr()), ptr(y.data_ptr()), ptr(cand.data_ptr()), ptr(count.data_ptr()),
-                         ptr(out.data_ptr() + r0 * self.outw * 4), ptr(overflow_count.data_ptr()),
-                         ptr(overflow_rows.data_ptr())])
+                         ptr(out_ptr), ptr(overflow_count.data_ptr()), ptr(overflow_rows.data_ptr()), i32(nsplit),
+                         ptr(part.data_ptr())])
+            if nsplit > 1:
+                capi.launch(self.fn_merge, stream, (-(-m // 256),), (256,), 0,
+                            [i64(m), i32(nsplit), ptr(part.data_ptr()), ptr(out_ptr)])
             if r0:
                 # make the batch-relative indices appended by this launch global
                 a, b = int(ov_before.item()), int(overflow_count.item())
                 if b > a:
                     overflow_rows[a:b] += r0
             if os.environ.get("KT_STATS"):
-                cf = count.float()
+                cf = count.view(m, nsplit).sum(1).float()
                 self.stats = dict(mean_candidates=float(cf.mean()), max_candidates=float(cf.max()),
                                   p99=float(cf.kthvalue(max(1, int(0.99 * m))).values))
-            for t in (xbf, xpen, cand, count):
+            for t in (xbf, xpen, cand, count, part):
                 t.record_stream(stream_obj)
         for t in (ybf, ypen):
             t.record_stream(stream_obj)
         n_over = int(overflow_count.item())          # one host sync per call (the reference syncs on every call)
-        self.last = dict(overflow=n_over, ntiles=ntiles, ctas=-(-min(M, ROW_BATCH) // BM))
-        return overflow_rows[:n_over].to(torch.int64)
+        self.last = dict(overflow=n_over, ntiles=ntiles, ctas=nblocks * nsplit, nsplit=nsplit)
+        rows = overflow_rows[:n_over].to(torch.int64)
+        return torch.unique(rows) if nsplit > 1 and n_over else rows      # a row may overflow in several splits
 
 
 _cache: Dict[tuple, KnnTensorCore] = {}

@@ -116,7 +116,8 @@ extern "C" __global__ void __launch_bounds__(320, 1)
 kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_xr,
                  const __grid_constant__ KtTensorMap map_y, const __grid_constant__ KtTensorMap map_yr,
                  const long long nrow, const long long ncol, const float* __restrict__ ypen,
-                 const float* __restrict__ xpen, int* __restrict__ cand, int* __restrict__ cand_count) {
+                 const float* __restrict__ xpen, int* __restrict__ cand, int* __restrict__ cand_count,
+                 const int tiles_per_split) {
   extern __shared__ unsigned char kt_raw[];
   const u32 raw = kt_smem(kt_raw);
   const u32 base = (raw + 1023u) & ~1023u;                       // swizzle atoms need (up to) 1024-byte alignment
@@ -135,7 +136,12 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row_base = (long long)blockIdx.x * KT_BM;
-  const int ntiles = (int)((ncol + KT_BN - 1) / KT_BN);
+  // blockIdx.y = column split (few rows, many columns: the row blocks alone would not fill the machine).  Every split
+  // keeps its own candidate list and threshold; kb200_knn_select evaluates each list exactly and kb200_knn_merge
+  // merges the per-split top-K lists in column order.
+  const int ntiles_all = (int)((ncol + KT_BN - 1) / KT_BN);
+  const int t0 = (int)blockIdx.y * tiles_per_split;
+  const int ntiles = (ntiles_all - t0 < tiles_per_split) ? (ntiles_all - t0) : tiles_per_split;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < KT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
@@ -171,11 +177,11 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
       if (kt_elect()) {
         kt_mbar_expect_tx(bFull + 8 * s, KT_B_BYTES);
         for (int kb = 0; kb < KT_KBM; kb++)
-          kt_tma_2d(sB + s * KT_B_BYTES + kb * KT_TILE_BYTES(KT_BN), &map_y, kb * 64, t * KT_BN, bFull + 8 * s);
-        kt_tma_2d(sB + s * KT_B_BYTES + KT_KBM * KT_TILE_BYTES(KT_BN), &map_yr, 0, t * KT_BN, bFull + 8 * s);
+          kt_tma_2d(sB + s * KT_B_BYTES + kb * KT_TILE_BYTES(KT_BN), &map_y, kb * 64, (t0 + t) * KT_BN, bFull + 8 * s);
+        kt_tma_2d(sB + s * KT_B_BYTES + KT_KBM * KT_TILE_BYTES(KT_BN), &map_yr, 0, (t0 + t) * KT_BN, bFull + 8 * s);
         // column penalties of this tile (only the rare path of the epilogue reads them)
         kt_mbar_expect_tx(bHFull + 8 * h, KT_BN * 4);
-        kt_bulk_1d(sH + h * KT_BN * 4, ypen + (long long)t * KT_BN, KT_BN * 4, bHFull + 8 * h);
+        kt_bulk_1d(sH + h * KT_BN * 4, ypen + (long long)(t0 + t) * KT_BN, KT_BN * 4, bHFull + 8 * h);
       }
       __syncwarp();
     }
@@ -227,7 +233,7 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 #pragma unroll
     for (int l = 0; l < KT_K; l++) lst[l] = -KT_INF;
     int cnt = 0;
-    int* my_cand = cand + (live ? i : 0) * (long long)KT_CAP;
+    int* my_cand = cand + ((live ? i : 0) * (long long)gridDim.y + blockIdx.y) * (long long)KT_CAP;
     const float cy_scale = 2.0f * KT_C / (1.0f - KT_C);   // c|y|^2 = cy_scale * (1-c)|y|^2/2
     for (int t = 0; t < ntiles; t++) {
       const int buf = t % KT_NBUF, hslot = t % KT_HS;
@@ -274,7 +280,7 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
               u32 hits = 0;
 #pragma unroll
               for (int e = 0; e < 8; e++) hits |= (u[8 * g + e] >= tau) ? (1u << e) : 0u;
-              const long long j0 = (long long)t * KT_BN + c * 64 + g * 8;
+              const long long j0 = (long long)(t0 + t) * KT_BN + c * 64 + g * 8;
               while (hits) {
                 const int e = __ffs(hits) - 1;
                 hits &= hits - 1;
@@ -306,7 +312,7 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
     }
-    if (live) cand_count[i] = cnt;
+    if (live) cand_count[i * (long long)gridDim.y + blockIdx.y] = cnt;
   }
   kt_fence_before();
   __syncthreads();
@@ -347,11 +353,14 @@ __device__ __forceinline__ float kt_sqdist(const float (&xr)[KT_D], const float*
 extern "C" __global__ void __launch_bounds__(256)
 kb200_knn_select(const long long nrow, const long long ncol, const float* __restrict__ x, const float* __restrict__ y,
                  const int* __restrict__ cand, const int* __restrict__ cand_count, float* __restrict__ out,
-                 int* __restrict__ overflow_count, int* __restrict__ overflow_rows) {
+                 int* __restrict__ overflow_count, int* __restrict__ overflow_rows, const int nsplit,
+                 float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
-  const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (row, split) pair
+  const long long i = w / nsplit;
   if (i >= nrow) return;
-  const int n = cand_count[i];
+  cand += w * (long long)KT_CAP - i * (long long)KT_CAP;      // below, cand[i * KT_CAP + e] addresses this pair's list
+  const int n = cand_count[w];
   constexpr int OUTW = (KT_OUT == 2) ? 2 * KT_K : KT_K;
   if (n > KT_CAP) {                                   // candidate list overflowed: the caller recomputes this row
     if (lane == 0) { const int s = atomicAdd(overflow_count, 1); overflow_rows[s] = (int)i; }
@@ -397,10 +406,46 @@ kb200_knn_select(const long long nrow, const long long ncol, const float* __rest
       const bool none = (wj == 0x7fffffff);           // fewer than K columns: (inf, 0) like the reference's init
       const float val = none ? KT_INF : wv;
       const float idx = none ? 0.0f : (float)wj;
+      if (nsplit > 1) { part[(w * KT_K + l) * 2] = val; part[(w * KT_K + l) * 2 + 1] = idx; continue; }
       float* po = out + i * OUTW;
       if (KT_OUT == 0) po[l] = idx;
       else if (KT_OUT == 1) po[l] = val;
       else { po[2 * l] = val; po[2 * l + 1] = idx; }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge: the per-split exact top-K lists of a row (ascending (value, index) order, splits in column order) -> its
+// global top-K; ties keep the smallest index because a later split only wins with a strictly smaller value
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(256)
+kb200_knn_merge(const long long nrow, const int nsplit, const float* __restrict__ part, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrow) return;
+  constexpr int OUTW = (KT_OUT == 2) ? 2 * KT_K : KT_K;
+  float v[KT_K], ix[KT_K];
+  const float* p0 = part + i * (long long)nsplit * KT_K * 2;
+#pragma unroll
+  for (int l = 0; l < KT_K; l++) { v[l] = p0[2 * l]; ix[l] = p0[2 * l + 1]; }
+  for (int s = 1; s < nsplit; s++) {
+    const float* ps = p0 + (long long)s * KT_K * 2;
+    for (int l = 0; l < KT_K; l++) {
+      const float f = ps[2 * l], fi = ps[2 * l + 1];
+      if (!(f < v[KT_K - 1])) break;                  // lists are sorted: nothing further can enter
+      // insertion from the tail, strict comparison (the element already present wins ties)
+      float cv = f, ci = fi;
+#pragma unroll
+      for (int m = 0; m < KT_K; m++) {
+        if (cv < v[m]) { const float tv = v[m], ti = ix[m]; v[m] = cv; ix[m] = ci; cv = tv; ci = ti; }
+      }
+    }
+  }
+  float* po = out + i * OUTW;
+#pragma unroll
+  for (int l = 0; l < KT_K; l++) {
+    if (KT_OUT == 0) po[l] = ix[l];
+    else if (KT_OUT == 1) po[l] = v[l];
+    else { po[2 * l] = v[l]; po[2 * l + 1] = ix[l]; }
   }
 }

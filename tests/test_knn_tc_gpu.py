@@ -34,6 +34,9 @@ CASES = [
     ("ArgKMin", 32, 1, 8200, 4100, 0),
     ("ArgKMin", 128, 10, 8192, 4500, 0),
     ("ArgKMin", 61, 4, 5000, 9000, 1),      # reduction over i: the output (and the tensor-core rows) follow j
+    ("ArgKMin", 64, 10, 1500, 70000, 0),    # few rows, many columns: the filter splits the column range (gridDim.y)
+    ("KMin_ArgKMin", 32, 5, 2500, 100001, 0),
+    ("KMin", 100, 3, 1100, 66000, 0),
 ]
 
 
@@ -46,6 +49,8 @@ def test_tensor_core_kmin_identical_to_cuda_core(kind, D, K, M, N, tagI, cuda_de
     f = "%s_Reduction(Sum(Square((Var(0,%d,0) - Var(1,%d,1)))),%d,%d)" % (kind, D, D, K, tagI)
     o_tc, ll = _run(f, 2, (x, y), M, N, cuda_device, True)
     assert ll.get("engine") == "tcgen05", ll          # the tensor-core kernels really ran
+    if (M if tagI == 0 else N) < 8192:
+        assert ll["nsplit"] > 1, ll                   # few rows: column splits + per-split lists + merge
     o_cc, ll2 = _run(f, 2, (x, y), M, N, cuda_device, False)
     assert ll2.get("engine") is None
     assert torch.equal(o_tc, o_cc)
