@@ -227,7 +227,8 @@ def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, use_
     D = m[2]
     dmin = int(os.environ.get("KB200_CONV_TC_DMIN", DMIN))
     kbm, rem, _ = layout(D)
-    if D < dmin or D > HD_MAX_D or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
+    min_rows = 8192 if ncol < 65536 else 1024       # few rows, many columns: column chunks fill the machine
+    if D < dmin or D > HD_MAX_D or nrow < min_rows or ncol < 1024 or ncol >= (1 << 31) - BN:
         return None
     if smem_bytes(D, m[4]) > 227 * 1024:
         return None
@@ -343,6 +344,7 @@ class ConvTensorCore:
             self.fn_prep = self.module.function("kb200_conv_prep")
             self.fn_conv = self.module.function("kb200_conv_tc_hd" if self.hd else "kb200_conv_tc")
             self.fn_combine = self.module.function("kb200_conv_combine")
+            self.sm_count = capi.device_info(device)["sm_count"]
             capi.set_max_dynamic_smem(self.fn_conv, self.smem)
 
     def _maps(self, abf, n, box_rows):
@@ -402,6 +404,10 @@ class ConvTensorCore:
         chunk_bytes = int(os.environ.get("KB200_CONV_TC_CHUNK_MB", CHUNK_MB)) << 20
         tiles_per_chunk = max(1, chunk_bytes // (BN * self.DPG * 2))
         nchunks = 1 if self.lse else -(-ntiles // tiles_per_chunk)   # (m, s) partials have no combine kernel
+        nblocks = -(-M // (128 if self.hd else BM))
+        if not self.lse and nblocks < self.sm_count:
+            # few output rows against many columns: the column chunks also serve to fill the machine
+            nchunks = max(nchunks, min(self.sm_count // nblocks, max(1, ntiles // 16)))
         tiles_per_chunk = -(-ntiles // nchunks)                   # balanced
         nchunks = -(-ntiles // tiles_per_chunk)
         dst = out if nchunks == 1 else torch.empty((nchunks, M, self.DB), dtype=torch.float32, device=dev)

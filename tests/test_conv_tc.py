@@ -56,6 +56,8 @@ def test_layout_and_eligibility():
     assert conv_tc.eligible(red, "float32", 100000, 100000, 1, False) is None      # no fast math: exact expf
     assert conv_tc.eligible(red, "float32", 100000, 100000, 2, True) is None       # batch dimensions
     assert conv_tc.eligible(red, "float32", 1000, 100000, 1, True) is None         # too few rows to fill the machine
+    assert conv_tc.eligible(red, "float32", 2000, 100000, 1, True) is not None     # ... unless the columns can be split
+    assert conv_tc.eligible(red, "float32", 2000, 50000, 1, True) is None
     assert conv_tc.eligible(red, "float32", 100000, 100000, 1, True, "kahan_scheme") is None
     g3 = parse_reduction("Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,1,1)),0)")
     assert conv_tc.eligible(g3, "float32", 100000, 100000, 1, True) is None        # D = 3 stays on the CUDA cores
@@ -121,6 +123,8 @@ CASES = [
     (95, 1, 4000, 8300, 1, "-Var(3,1,2)*"),           # 9 k-blocks (the resident maximum), reduction over i
     (128, 2, 8192, 1300, 0, "-Var(3,1,2)*"),          # 13 k-blocks: both operands stream through the ring
     (300, 1, 8192, 1100, 0, "-Var(3,1,2)*"),          # 29 k-blocks
+    (16, 1, 1500, 70000, 0, "-Var(3,1,2)*"),          # few rows, many columns: column chunks fill the machine
+    (64, 2, 1100, 66000, 0, "-Var(3,1,2)*"),
 ]
 
 
