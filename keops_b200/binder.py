@@ -362,7 +362,8 @@ class LoadKeOpsB200:
         if not ok:
             return False
         self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0, blocks_per_sm=1,
-                                launches=3, engine="tcgen05-lse", error_bound=eng.last_bound, nchunks=1)
+                                launches=3 + (eng.last["nchunks"] > 1), engine="tcgen05-lse", error_bound=eng.last_bound,
+                                nchunks=eng.last["nchunks"])
         return True
 
     def _launch_dense(self, dev, nrow, ncol, nbatch, out, args, strides, tdtype):

@@ -34,7 +34,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_conv_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")
-VERSION = "conv-tc-13"
+VERSION = "conv-tc-14"
 BM, BN, STAGES, HS = 256, 128, 4, 8
 THREADS = 64 + 32 * 16       # TMA warp + MMA warp + 16 epilogue warps (CT_THREADS in the kernel)
 MAX_DB = 8
@@ -296,7 +296,8 @@ def eligible_lse(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, 
         return None
     D, DB = m[2], m[5]
     dmin = int(os.environ.get("KB200_CONV_TC_DMIN", DMIN))
-    if D < dmin or D > HD_MAX_D or layout(D)[2] != 1 or nrow < 8192 or ncol < 1024 or ncol >= (1 << 31) - BN:
+    min_rows = 8192 if ncol < 65536 else 1024
+    if D < dmin or D > HD_MAX_D or layout(D)[2] != 1 or nrow < min_rows or ncol < 1024 or ncol >= (1 << 31) - BN:
         return None
     if smem_bytes(D, DB, lse=True) > 227 * 1024:
         return None
@@ -343,7 +344,7 @@ class ConvTensorCore:
             self.module = capi.Module(cubin, device)
             self.fn_prep = self.module.function("kb200_conv_prep")
             self.fn_conv = self.module.function("kb200_conv_tc_hd" if self.hd else "kb200_conv_tc")
-            self.fn_combine = self.module.function("kb200_conv_combine")
+            self.fn_combine = self.module.function("kb200_conv_combine_lse" if lse else "kb200_conv_combine")
             self.sm_count = capi.device_info(device)["sm_count"]
             capi.set_max_dynamic_smem(self.fn_conv, self.smem)
 
@@ -403,14 +404,14 @@ class ConvTensorCore:
         # (126 MB L2; measured at M = N = 1e6, D = 16: one 256 MB chunk 288 ms, L2-sized chunks %s)
         chunk_bytes = int(os.environ.get("KB200_CONV_TC_CHUNK_MB", CHUNK_MB)) << 20
         tiles_per_chunk = max(1, chunk_bytes // (BN * self.DPG * 2))
-        nchunks = 1 if self.lse else -(-ntiles // tiles_per_chunk)   # (m, s) partials have no combine kernel
+        nchunks = -(-ntiles // tiles_per_chunk)
         nblocks = -(-M // (128 if self.hd else BM))
-        if not self.lse and nblocks < self.sm_count:
+        if nblocks < self.sm_count:
             # few output rows against many columns: the column chunks also serve to fill the machine
             nchunks = max(nchunks, min(self.sm_count // nblocks, max(1, ntiles // 16)))
         tiles_per_chunk = -(-ntiles // nchunks)                   # balanced
         nchunks = -(-ntiles // tiles_per_chunk)
-        dst = out if nchunks == 1 else torch.empty((nchunks, M, self.DB), dtype=torch.float32, device=dev)
+        dst = out if nchunks == 1 else torch.empty((nchunks, M, self.OUTW), dtype=torch.float32, device=dev)
         if self.hd:
             gx = -(-M // 128)
             if self.mc:
@@ -424,8 +425,9 @@ class ConvTensorCore:
                          ptr(xsq.data_ptr()), ptr(coef.data_ptr()), ptr(dst.data_ptr()),
                          ptr(clock_probe.data_ptr() if clock_probe is not None else 0), ptr(xbf.data_ptr())])
         if nchunks > 1:
-            capi.launch(self.fn_combine, stream, (-(-(M * self.DB) // 256),), (256,), 0,
-                        [i64(M * self.DB), i32(nchunks), ptr(dst.data_ptr()), ptr(out.data_ptr())])
+            nel = M if self.lse else M * self.DB          # LSE: one thread per row; Sum: one per output element
+            capi.launch(self.fn_combine, stream, (-(-nel // 256),), (256,), 0,
+                        [i64(nel), i32(nchunks), ptr(dst.data_ptr()), ptr(out.data_ptr())])
         for t in (shift, ybf, xbf, ysq, xsq, bpad, coef, dst):
             t.record_stream(stream_obj)
         self.last = dict(ntiles=ntiles, ctas=-(-M // (128 if self.hd else BM)) * nchunks, nchunks=nchunks)

@@ -551,7 +551,7 @@ kb200_conv_tc(const __grid_constant__ KtTensorMap map_x, const __grid_constant__
     if (half == 0 && live) {
 #if CT_LSE
       ct_lse_merge(M2, acc, xch[rloc * CT_OUTW], xch + rloc * CT_OUTW + 1);
-      out[i * CT_OUTW] = M2 * 0.6931471805599453f;                  // back to natural units: m_i = max_j F_ij
+      out[i * CT_OUTW] = (gridDim.y > 1) ? M2 : M2 * 0.6931471805599453f;   // natural units: m_i = max_j F_ij (chunk partials stay base 2)
 #pragma unroll
       for (int d = 0; d < CT_DB; d++) out[i * CT_OUTW + 1 + d] = acc[d];
 #else
@@ -809,7 +809,7 @@ kb200_conv_tc_hd(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 #pragma unroll
       for (int p_ = 0; p_ < 3; p_++)
         ct_lse_merge(M2, acc, xch[(p_ * 128 + rloc) * CT_OUTW], xch + (p_ * 128 + rloc) * CT_OUTW + 1);
-      out[i * CT_OUTW] = M2 * 0.6931471805599453f;
+      out[i * CT_OUTW] = (gridDim.y > 1) ? M2 : M2 * 0.6931471805599453f;
 #pragma unroll
       for (int d = 0; d < CT_DB; d++) out[i * CT_OUTW + 1 + d] = acc[d];
 #else
@@ -841,3 +841,22 @@ kb200_conv_combine(const long long n, const int nchunks, const float* __restrict
   for (int c = 1; c < nchunks; c++) s += partial[(long long)c * n + e];
   out[e] = s;
 }
+
+#if CT_LSE
+// combine of the column chunks of a LogSumExp reduction: (M2, S) partials in base-2 units, merged in chunk order
+extern "C" __global__ void __launch_bounds__(256)
+kb200_conv_combine_lse(const long long nrow, const int nchunks, const float* __restrict__ partial, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrow) return;
+  float M = partial[i * CT_OUTW], S[CT_DB];
+#pragma unroll
+  for (int d = 0; d < CT_DB; d++) S[d] = partial[i * CT_OUTW + 1 + d];
+  for (int c = 1; c < nchunks; c++) {
+    const float* p = partial + ((long long)c * nrow + i) * CT_OUTW;
+    ct_lse_merge(M, S, p[0], p + 1);
+  }
+  out[i * CT_OUTW] = M * 0.6931471805599453f;
+#pragma unroll
+  for (int d = 0; d < CT_DB; d++) out[i * CT_OUTW + 1 + d] = S[d];
+}
+#endif

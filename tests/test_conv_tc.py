@@ -247,6 +247,7 @@ LSE_CASES = [
     (16, 0, 5000, 9000, 1),
     (64, 0, 8192, 2500, 0),       # high-dimensional kernel
     (128, 3, 8192, 1300, 0),      # both operands streamed
+    (16, 2, 1500, 70000, 0),      # few rows, many columns: column chunks + (m, s) combine
 ]
 
 
@@ -276,6 +277,9 @@ def test_tensor_core_lse_matches_cuda_core(D, DW, nx, ny, tagI, cuda_device):
     assert ll2.get("engine") is None
     # raw (m, s) output: m = max_j F_ij, s = sum_j exp(F_ij - m) b_j
     util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 LSE (m, s) vs CUDA cores")
+    # forced column chunks: the (m, s) partials are merged by kb200_conv_combine_lse
+    o_ch, ll3 = _run(f, len(args), args, nx, ny, dev, True, KB200_CONV_TC_CHUNK_MB=1)
+    util.assert_close(o_ch.cpu().numpy(), o_cc.cpu().numpy(), "float32", "chunked tcgen05 LSE vs CUDA cores")
     lse_tc = o_tc[:, 0] + torch.log(o_tc[:, 1])
     lse_cc = o_cc[:, 0] + torch.log(o_cc[:, 1])
     util.assert_close(lse_tc.cpu().numpy(), lse_cc.cpu().numpy(), "float32", "log-sum-exp")
