@@ -368,6 +368,12 @@ class ConvTensorCore:
         i64, ptr, i32 = C.c_longlong, C.c_void_p, C.c_int
         ntiles = -(-N // BN)
         npad = ntiles * BN
+        # the bf16 operand copies take 2 * CT_DPG bytes per point (24 KB at D = 2048): leave the job to the CUDA-core
+        # kernel rather than exhaust the device
+        free_bytes, _ = torch.cuda.mem_get_info(dev)
+        if (M + N) * self.DPG * 2 + (M + 2 * npad) * 4 * (self.W + 2) > 0.8 * free_bytes:
+            self.last_bound = None
+            return False
         shift = y.mean(dim=0, dtype=torch.float32).contiguous()            # common shift: x - y is unchanged
         ybf = torch.empty((N, self.DPG), dtype=torch.int16, device=dev)
         xbf = torch.empty((M, self.DPG), dtype=torch.int16, device=dev)
