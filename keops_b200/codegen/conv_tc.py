@@ -396,9 +396,11 @@ class ConvTensorCore:
             bound = coef.abs() * (xsq.max() + ysq.max()) * (2.0 ** -22)
             if acol is not None:                   # the column term shares the accumulation: + 2^-22 * 2 max |a_j|
                 bound = bound + acol.abs().max() * (2.0 ** -21)
-            self.last_bound = float(bound.item())
+            self.last_bound, c_abs = torch.stack([bound.reshape(()), coef.abs().reshape(())]).tolist()
             if not self.last_bound <= tol:          # also catches NaN / inf inputs
                 return False
+            if self.lse and acol is not None and not c_abs > 0.0:
+                return False                        # a_j / (2 c) in the penalty columns needs c != 0
         if self.hd:
             pitch = self.DPG * 2
             map_y = capi.tensor_map_2d(ybf.data_ptr(), 2, self.DPG, N, pitch, 64, BN // 2 if self.mc else BN, 128)
