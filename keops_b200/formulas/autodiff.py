@@ -33,6 +33,25 @@ def grad(f: Node, v: Node, gradin: Node) -> Node:
     return _grad(f, v, gradin, {})
 
 
+def diff(f: Node, v: Node, u: Node) -> Node:
+    """Forward-mode differential ``D_v f . u`` (dimension ``f.dim``): the adjoint of the gradient, obtained like the
+    reference does (``keopscore/keopscore/formulas/autodiff/Diff.py:14-36``): back-propagate a placeholder ``g`` through
+    ``f`` -- ``h(g) = [df/dv]^T g`` is linear in ``g`` -- then differentiate ``<h(g), u>`` with respect to ``g``."""
+    if v.op != "Var":
+        raise FormulaError("can only differentiate with respect to a Var")
+    if u.dim != v.dim:
+        raise FormulaError("direction has dimension %d, variable has dimension %d" % (u.dim, v.dim))
+    used = [w.params[0] for w in f.variables() + u.variables()] + [v.params[0]]
+    g = ir.Var(1 + max(used), f.dim, 2)                 # placeholder: it disappears from the result
+    h = grad(f, v, g)
+    if h.is_zero:
+        return ir.Zero(f.dim)
+    res = grad(ir.Scalprod(h, u) if v.dim > 1 else ir.Mult(h, u), g, ir.IntCst(1))
+    if g in res.variables():
+        raise NotImplementedError("Diff: the placeholder did not cancel (an operation's gradient rule is not linear in gradin)")
+    return res
+
+
 def _grad(f: Node, v: Node, g: Node, memo: Dict[Tuple[int, int], Node]) -> Node:
     if g.is_zero or not _depends(f, v):
         return ir.Zero(v.dim)

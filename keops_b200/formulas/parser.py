@@ -25,7 +25,7 @@ _REDUCTIONS = {
         "Sum_Reduction", "Zero_Reduction", "Max_SumShiftExp_Reduction",
         "Max_SumShiftExpWeight_Reduction", "Min_Reduction", "Max_Reduction", "ArgMin_Reduction",
         "ArgMax_Reduction", "Min_ArgMin_Reduction", "Max_ArgMax_Reduction", "KMin_Reduction",
-        "ArgKMin_Reduction", "KMin_ArgKMin_Reduction", "Grad_WithSavedForward", "Grad",
+        "ArgKMin_Reduction", "KMin_ArgKMin_Reduction", "Grad_WithSavedForward", "Grad", "Diff_WithSavedForward", "Diff",
     )
 }
 
@@ -131,6 +131,11 @@ class _Interp(ast.NodeVisitor):
                 raise FormulaError("Grad(f, v, gradin) expects three arguments")
             from .autodiff import grad as _grad_formula
             return _grad_formula(args[0], ir.as_node(args[1]), ir.as_node(args[2]))
+        if name == "Diff" and args and isinstance(args[0], Node):
+            if len(args) != 3:
+                raise FormulaError("Diff(f, v, u) expects three arguments")
+            from .autodiff import diff as _diff_formula
+            return _diff_formula(args[0], ir.as_node(args[1]), ir.as_node(args[2]))
         if name in _REDUCTIONS:
             return self._call_reduction(name, args)
         fn = ir.PUBLIC_OPS.get(name)
@@ -174,7 +179,7 @@ class _Interp(ast.NodeVisitor):
                 return int(c)
             return int(x)
 
-        if name in ("Grad_WithSavedForward", "Grad"):
+        if name in ("Grad_WithSavedForward", "Grad", "Diff_WithSavedForward", "Diff"):
             red = args[0]
             rest = [ir.as_node(a) for a in args[1:]]
             return fn(red, *rest)

@@ -27,7 +27,7 @@ from typing import Optional
 
 from . import ir
 from .ir import Node, FormulaError
-from .autodiff import grad
+from .autodiff import diff, grad
 
 
 @dataclass(frozen=True)
@@ -175,6 +175,25 @@ def Grad_WithSavedForward(red: Reduction, v: Node, gradin: Node, f0: Node) -> Re
     raise NotImplementedError(
         "As of today, KeOps does not support autodiff through the %s reduction." % k
     )
+
+
+def Diff_WithSavedForward(red: Reduction, v: Node, u: Node, f0: Node) -> Reduction:
+    """Forward-mode differential of a reduction (``autodiff/Diff_WithSavedForward.py``; ``Sum_Reduction.py:47-50``,
+    ``Max_SumShiftExpWeight_Reduction.py:105-120``): same reduction index as ``red``."""
+    k = red.kind
+    if k == "Sum":
+        return Sum_Reduction(diff(red.formula, v, u), red.tagI)
+    if k == "LSE":
+        F, G = red.formula, red.weight
+        M = ir.Extract(f0, 0, 1)
+        return Sum_Reduction(diff(ir.Concat(ir.Zero(1), ir.Exp(F - M) * G), v, u), red.tagI)
+    raise NotImplementedError("As of today, KeOps does not support forward-mode autodiff through the %s reduction." % k)
+
+
+def Diff(red_or_formula, v: Node, u: Node):
+    if isinstance(red_or_formula, Reduction):
+        return Diff_WithSavedForward(red_or_formula, v, u, None)
+    return diff(red_or_formula, v, u)
 
 
 def Grad(red_or_formula, v: Node, gradin: Node):

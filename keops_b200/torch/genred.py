@@ -63,23 +63,73 @@ def _set_device(device_id_request: int, args):
     return dev.index, dev
 
 
+def _binder_for(params, args):
+    flags = dict(params.optional_flags)
+    flags["multVar_highdim"] = 1 if params.rec_multVar_highdim else 0
+    tagCPUGPU, tag1D2D, tagHostDevice = _resolve_backend(params.backend, args)
+    nbatchdims = max(len(a.shape) for a in args) - 2
+    use_ranges = nbatchdims > 0 or params.ranges is not None
+    device_id, device_args = _set_device(params.device_id_request, args)
+    binder = LoadKeOpsB200(tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id, params.formula,
+                           params.aliases, len(args), params.dtype, "torch", flags).import_module()
+    return binder, device_args, nbatchdims
+
+
 class GenredAutograd(torch.autograd.Function):
+    """New-style autograd function (``forward`` + ``setup_context``) so that ``torch.func.jvp`` / ``torch.func.vmap`` work
+    like with the reference (``generic_red.py:262-380``): ``backward`` hands ``Grad_WithSavedForward`` reductions to the
+    engine, ``jvp`` hands ``Diff_WithSavedForward`` ones, ``vmap`` turns the mapped dimension into a batch dimension."""
+
     @staticmethod
-    def forward(ctx, params, *args):
-        flags = dict(params.optional_flags)
-        flags["multVar_highdim"] = 1 if params.rec_multVar_highdim else 0
-        tagCPUGPU, tag1D2D, tagHostDevice = _resolve_backend(params.backend, args)
-        nbatchdims = max(len(a.shape) for a in args) - 2
-        use_ranges = nbatchdims > 0 or params.ranges is not None
-        device_id, device_args = _set_device(params.device_id_request, args)
-        binder = LoadKeOpsB200(tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id, params.formula,
-                               params.aliases, len(args), params.dtype, "torch", flags).import_module()
+    def forward(params, *args):
+        binder, device_args, nbatchdims = _binder_for(params, args)
         cargs = tuple(a.detach() if a.is_contiguous() else a.detach().contiguous() for a in args)
-        result = binder.genred_pytorch(device_args, params.ranges, params.nx, params.ny, nbatchdims, params.out, *cargs)
+        return binder.genred_pytorch(device_args, params.ranges, params.nx, params.ny, nbatchdims, params.out, *cargs)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        params, *args = inputs
+        binder, _, _ = _binder_for(params, args)          # memoised: the binder built by forward
         ctx.params = params
         ctx.dimout, ctx.tagIJ = binder.dimout, binder.tagIJ
-        ctx.save_for_backward(*args, result)
-        return result
+        ctx.save_for_backward(*args, output)
+        ctx.save_for_forward(*args, output)
+
+    @staticmethod
+    def vmap(info, in_dims, params, *args):
+        """The mapped dimension becomes a leading batch dimension of every argument (``generic_red.py:304-316``)."""
+        moved = []
+        for a, d in zip(args, in_dims[1:]):
+            moved.append(a[None, ...] if d is None else a.movedim(d, 0).contiguous())
+        p2 = copy.copy(params)
+        p2.out = None
+        return GenredAutograd.apply(p2, *moved), 0
+
+    @staticmethod
+    def jvp(ctx, _params_tangent, *tangents):
+        """Forward-mode: one ``Diff_WithSavedForward`` reduction per input that carries a tangent
+        (``generic_red.py:318-378``)."""
+        params = ctx.params
+        args = ctx.saved_tensors[:-1]
+        result = ctx.saved_tensors[-1].detach()
+        nargs = len(args)
+        check_AD_supported(params.formula)
+        resvar = "Var(%d,%d,%d)" % (nargs + 1, ctx.dimout, ctx.tagIJ)
+        out = None
+        for var_ind, (sig, t) in enumerate(zip(params.aliases, tangents)):
+            if t is None:
+                continue
+            _, cat, dim, pos = get_type(sig, position_in_list=var_ind)
+            var = "Var(%d,%d,%d)" % (pos, dim, cat)
+            eta = "Var(%d,%d,%d)" % (nargs, dim, cat)
+            params_d = copy.copy(params)
+            params_d.formula = "Diff_WithSavedForward(%s,%s,%s,%s)" % (params.formula, var, eta, resvar)
+            params_d.aliases = list(params.aliases) + [eta, resvar]
+            params_d.out = None
+            params_d.rec_multVar_highdim = None
+            d = GenredAutograd.apply(params_d, *args, t.contiguous(), result)
+            out = d if out is None else out + d
+        return out if out is not None else torch.zeros_like(result)
 
     @staticmethod
     def backward(ctx, G):

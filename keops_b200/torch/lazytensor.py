@@ -713,6 +713,11 @@ class LazyTensor:
         variable ``v``, applied to ``e`` (``lazy_tensor.py:1918-1936``; formula-level ``Grad``)."""
         return self.binary(gradin, "Grad", dimres=other.ndim, dimcheck="same", opt_arg=other.formula, opt_pos="middle")
 
+    def diff(self, other, diffin):
+        """Symbolic differential (forward mode): ``x.diff(v, e)`` encodes the differential of ``x`` with respect to the
+        variable ``v``, applied to ``e`` (``lazy_tensor.py:1938-1956``; formula-level ``Diff``)."""
+        return self.binary(diffin, "Diff", dimres=self.ndim, dimcheck=None, opt_arg=other.formula, opt_pos="middle")
+
     def sinc(self):
         """``sin(pi x) / (pi x)`` (``lazy_tensor.py:1267-1274``)."""
         return (math.pi * self).sinxdivx()

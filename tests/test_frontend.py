@@ -127,3 +127,30 @@ def test_high_dimensional_formula_generates():
     red = parse_reduction("Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,600,0),Var(1,600,1)))*Var(2,1,1),0)")
     ks = generate(red, "float32", 4, plan.default_config(red, "float32"))
     assert "kb200_reduce" in ks.source and ks.stride >= 600
+
+
+@pytest.mark.parametrize("formula,var", [
+    ("Sum_Reduction(Exp(-SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,2,1),0)", "Var(0,3,0)"),
+    ("Sum_Reduction(Exp(-SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,2,1),0)", "Var(1,3,1)"),
+    ("Sum_Reduction(Exp(-SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,2,1),0)", "Var(2,2,1)"),
+    ("Sum_Reduction(Sqrt(IntCst(1)+SqDist(Var(0,3,0),Var(1,3,1)))*Sin(Var(2,2,1))/(IntCst(2)+(Var(0,3,0)|Var(1,3,1))**2),1)", "Var(0,3,0)"),
+])
+def test_forward_mode_diff_matches_finite_differences(formula, var):
+    """``Diff_WithSavedForward`` (forward-mode differential, keopscore/keopscore/formulas/autodiff/Diff.py:14-36): the
+    lowered reduction against central finite differences of the forward reduction, in float64."""
+    import re
+    rng = np.random.default_rng(3)
+    M, N = 7, 9
+    x, y, b = rng.standard_normal((M, 3)), rng.standard_normal((N, 3)), rng.standard_normal((N, 2))
+    args = [x, y, b]
+    ind, dim, cat = (int(t) for t in re.findall(r"\d+", var))
+    u = rng.standard_normal(args[ind].shape)
+    tagI = int(formula.rstrip(")").split(",")[-1])
+    fwd = dag_eval.evaluate(formula, [], args, "float64")
+    dform = "Diff_WithSavedForward(%s,%s,Var(3,%d,%d),Var(4,%d,%d))" % (formula, var, dim, cat, fwd.shape[1], tagI)
+    got = dag_eval.evaluate(dform, [], args + [u, fwd], "float64")
+    h = 1e-6
+    ap, am = list(args), list(args)
+    ap[ind], am[ind] = args[ind] + h * u, args[ind] - h * u
+    fd = (dag_eval.evaluate(formula, [], ap, "float64") - dag_eval.evaluate(formula, [], am, "float64")) / (2 * h)
+    np.testing.assert_allclose(got, fd, rtol=1e-6, atol=1e-8)

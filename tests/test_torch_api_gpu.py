@@ -280,3 +280,69 @@ def test_high_dimensional_x_or_b_like_reference_chunk_tests(api, cuda_device, D,
     out = Kxy.__matmul__(b, sum_scheme="block_sum")
     ref = (-((x - y) ** 2).sum(dim=2)).exp() @ b
     assert torch.allclose(out, ref, atol=1e-4)
+
+
+# ---- torch.func transforms (pykeops/pykeops/test/test_torch_func.py, test_vmap.py) ---------------------------------
+def _func_inputs(dev):
+    torch.manual_seed(0)
+    B1, B2, M, N, D = 5, 4, 10, 20, 2
+    mk = lambda *s: torch.randn(*s, device=dev)
+    prim = (mk(B1, B2, M, 1, D), mk(B1, 1, 1, N, D), mk(B1, B2, 1, N, 1), torch.rand(B1, 1, 1, 1, 1, device=dev))
+    tang = (mk(B1, B2, M, 1, D), mk(B1, 1, 1, N, D), mk(B1, B2, 1, N, 1), mk(B1, 1, 1, 1, 1))
+    return prim, tang
+
+
+def _fn_torch(x_i, y_j, b_j, p):
+    K_ij = (-p[..., 0] * ((x_i - y_j) ** 2).sum(-1)).exp()[..., None]
+    return ((K_ij * b_j).sum(2)).norm()
+
+
+def _fn_keops(api):
+    def fn(x_i, y_j, b_j, p):
+        x_i, y_j, b_j, p = api.LazyTensor(x_i), api.LazyTensor(y_j), api.LazyTensor(b_j), api.LazyTensor(p)
+        K_ij = (-p * ((x_i - y_j) ** 2).sum(-1)).exp()
+        return ((K_ij * b_j).sum(2)).norm()
+    return fn
+
+
+def test_torch_func_jvp_grad_vjp(api, cuda_device):
+    prim, tang = _func_inputs(cuda_device)
+    fk = _fn_keops(api)
+    v1, t1 = torch.func.jvp(_fn_torch, prim, tang)
+    v2, t2 = torch.func.jvp(fk, prim, tang)
+    assert torch.allclose(v1, v2, atol=1e-4) and torch.allclose(t1, t2, atol=1e-4)
+    g1 = torch.func.grad(_fn_torch, (0, 1, 2, 3))(*prim)
+    g2 = torch.func.grad(fk, (0, 1, 2, 3))(*prim)
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, atol=1e-4)
+    r1 = torch.func.vjp(_fn_torch, *prim)[1](torch.tensor(1.0, device=cuda_device))[0]
+    r2 = torch.func.vjp(fk, *prim)[1](torch.tensor(1.0, device=cuda_device))[0]
+    assert torch.allclose(r1, r2, atol=1e-4)
+
+
+def test_torch_func_vmap(api, cuda_device):
+    prim, _ = _func_inputs(cuda_device)
+    res1 = torch.func.vmap(_fn_torch)(*prim)
+    res2 = torch.func.vmap(_fn_keops(api))(*prim)
+    assert torch.allclose(res1, res2, atol=1e-4)
+
+    def fn(x_i, x_j, y_j, use_keops):
+        if use_keops:
+            x_i, x_j, y_j = api.LazyTensor(x_i), api.LazyTensor(x_j), api.LazyTensor(y_j)
+        K_ij = (-((x_i - x_j) ** 2).sum(-1)).exp()
+        if not use_keops:
+            K_ij = K_ij[..., None]
+        return (K_ij * y_j).sum(1)
+
+    torch.manual_seed(0)
+    for in_dim, shapes in ((0, ((5, 10, 1, 2), (5, 1, 20, 2), (5, 1, 20, 1))), (1, ((10, 5, 1, 2), (1, 5, 20, 2), (1, 5, 20, 1)))):
+        x_i = torch.randn(*shapes[0], device=cuda_device, dtype=torch.float64, requires_grad=True)
+        x_j = torch.randn(*shapes[1], device=cuda_device, dtype=torch.float64)
+        y_j = torch.randn(*shapes[2], device=cuda_device, dtype=torch.float64)
+        rk = torch.vmap(lambda a, b, c: fn(a, b, c, True), in_dims=in_dim, out_dims=in_dim)(x_i, x_j, y_j)
+        rt = torch.vmap(lambda a, b, c: fn(a, b, c, False), in_dims=in_dim, out_dims=in_dim)(x_i, x_j, y_j)
+        assert torch.allclose(rk, rt)
+        u = torch.rand(rt.shape, device=cuda_device, dtype=torch.float64)
+        (gt,) = torch.autograd.grad(rt, x_i, u)
+        (gk,) = torch.autograd.grad(rk, x_i, u)
+        assert torch.allclose(gk, gt)
