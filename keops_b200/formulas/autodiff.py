@@ -52,6 +52,28 @@ def diff(f: Node, v: Node, u: Node) -> Node:
     return res
 
 
+def divergence(f: Node, v: Node) -> Node:
+    """``sum_k d f_k / d v_k`` -- the trace of the Jacobian (``keopscore/keopscore/formulas/autodiff/Divergence.py``):
+    sum over k of component k of the differential applied to the k-th basis vector."""
+    if v.op != "Var":
+        raise FormulaError("can only differentiate with respect to a Var")
+    if f.dim != v.dim:
+        raise FormulaError("Divergence requires formula and variable to have the same dimension.")
+    total = None
+    for k in range(v.dim):
+        e_k = ir.ElemT(ir.IntCst(1), v.dim, k)
+        term = ir.Elem(diff(f, v, e_k), k)
+        total = term if total is None else ir.Add(total, term)
+    return total
+
+
+def laplacian(f: Node, v: Node) -> Node:
+    """``Divergence(Grad(f, v, 1), v)`` for a scalar formula (``autodiff/Laplacian.py``)."""
+    if f.dim != 1:
+        raise FormulaError("Laplacian is only implemented for scalar formula.")
+    return divergence(grad(f, v, ir.IntCst(1)), v)
+
+
 def _grad(f: Node, v: Node, g: Node, memo: Dict[Tuple[int, int], Node]) -> Node:
     if g.is_zero or not _depends(f, v):
         return ir.Zero(v.dim)

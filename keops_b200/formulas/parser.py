@@ -131,6 +131,13 @@ class _Interp(ast.NodeVisitor):
                 raise FormulaError("Grad(f, v, gradin) expects three arguments")
             from .autodiff import grad as _grad_formula
             return _grad_formula(args[0], ir.as_node(args[1]), ir.as_node(args[2]))
+        if name in ("Factorize", "AutoFactorize") and args and isinstance(args[0], Node):
+            # common sub-expressions are shared by construction (hash-consed DAG + CSE at lowering): factorisation
+            # (keopscore/keopscore/formulas/factorization/) is the identity here
+            return args[0]
+        if name in ("Divergence", "Laplacian") and len(args) == 2 and isinstance(args[0], Node):
+            from . import autodiff as _ad
+            return (_ad.divergence if name == "Divergence" else _ad.laplacian)(args[0], ir.as_node(args[1]))
         if name == "Diff" and args and isinstance(args[0], Node):
             if len(args) != 3:
                 raise FormulaError("Diff(f, v, u) expects three arguments")

@@ -718,6 +718,22 @@ class LazyTensor:
         variable ``v``, applied to ``e`` (``lazy_tensor.py:1938-1956``; formula-level ``Diff``)."""
         return self.binary(diffin, "Diff", dimres=self.ndim, dimcheck=None, opt_arg=other.formula, opt_pos="middle")
 
+    def factorize(self, other):
+        """``x.factorize(y)`` (``lazy_tensor.py:1958-1973``): common sub-expressions are always shared by this engine."""
+        return self.binary(other, "Factorize", dimres=self.ndim, dimcheck=None)
+
+    def auto_factorize(self):
+        """``x.auto_factorize()`` (``lazy_tensor.py:1975-1988``): a no-op here, see :meth:`factorize`."""
+        return self.unary("AutoFactorize", dimres=self.ndim)
+
+    def divergence(self, var):
+        """Symbolic divergence of ``x`` with respect to the variable ``var`` (``lazy_tensor.py:2038-2052``)."""
+        return self.binary(var, "Divergence", dimres=1, dimcheck="same")
+
+    def laplacian(self, var):
+        """Symbolic Laplacian of the scalar ``x`` with respect to ``var`` (``lazy_tensor.py:2054-2068``)."""
+        return self.binary(var, "Laplacian", dimres=1, dimcheck=None)
+
     def sinc(self):
         """``sin(pi x) / (pi x)`` (``lazy_tensor.py:1267-1274``)."""
         return (math.pi * self).sinxdivx()

@@ -154,3 +154,24 @@ def test_forward_mode_diff_matches_finite_differences(formula, var):
     ap[ind], am[ind] = args[ind] + h * u, args[ind] - h * u
     fd = (dag_eval.evaluate(formula, [], ap, "float64") - dag_eval.evaluate(formula, [], am, "float64")) / (2 * h)
     np.testing.assert_allclose(got, fd, rtol=1e-6, atol=1e-8)
+
+
+def test_divergence_laplacian_factorize():
+    """``Divergence`` / ``Laplacian`` (keopscore/keopscore/formulas/autodiff/Divergence.py, Laplacian.py) against closed forms;
+    ``Factorize`` / ``AutoFactorize`` are the identity on a hash-consed DAG."""
+    from keops_b200.formulas.parser import parse_formula
+    rng = np.random.default_rng(8)
+    M, N, D = 6, 5, 3
+    x, y = rng.standard_normal((M, D)), rng.standard_normal((N, D))
+    g = "Exp(-SqDist(Var(0,3,0),Var(1,3,1)))"
+    lap = dag_eval.evaluate("Sum_Reduction(Laplacian(%s,Var(0,3,0)),0)" % g, [], [x, y], "float64")
+    d2 = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(lap[:, 0], ((4 * d2 - 2 * D) * np.exp(-d2)).sum(1), rtol=1e-10)
+    div = dag_eval.evaluate("Sum_Reduction(Divergence(Var(0,3,0)*Exp(-SqDist(Var(0,3,0),Var(1,3,1))),Var(0,3,0)),0)", [],
+                            [x, y], "float64")
+    # div_x (x e^{-|x-y|^2}) = (D - 2 x.(x-y)) e^{-|x-y|^2}
+    xd = (x[:, None, :] * (x[:, None, :] - y[None, :, :])).sum(-1)
+    np.testing.assert_allclose(div[:, 0], ((D - 2 * xd) * np.exp(-d2)).sum(1), rtol=1e-10)
+    f = parse_formula("Exp(Var(0,3,0))+Exp(Var(0,3,0))")
+    assert parse_formula("Factorize(Exp(Var(0,3,0))+Exp(Var(0,3,0)),Exp(Var(0,3,0)))") is f
+    assert parse_formula("AutoFactorize(Exp(Var(0,3,0))+Exp(Var(0,3,0)))") is f

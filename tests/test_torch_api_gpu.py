@@ -346,3 +346,24 @@ def test_torch_func_vmap(api, cuda_device):
         (gt,) = torch.autograd.grad(rt, x_i, u)
         (gk,) = torch.autograd.grad(rk, x_i, u)
         assert torch.allclose(gk, gt)
+
+
+def test_lazytensor_diff_divergence_laplacian(api, cuda_device):
+    """``x.diff(v, e)``, ``x.divergence(v)``, ``x.laplacian(v)``, ``x.factorize(y)`` (lazy_tensor.py:1938-2068) on the GPU."""
+    torch.manual_seed(6)
+    dev = cuda_device
+    x, y = torch.randn(80, 3, device=dev, dtype=torch.float64), torch.randn(70, 3, device=dev, dtype=torch.float64)
+    e = torch.randn(80, 3, device=dev, dtype=torch.float64)
+    x_i, y_j, e_i = api.LazyTensor(x[:, None, :]), api.LazyTensor(y[None, :, :]), api.LazyTensor(e[:, None, :])
+    K = (-((x_i - y_j) ** 2).sum(2)).exp()
+    d2 = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+    lap = K.laplacian(x_i).sum(1).view(-1)
+    torch.testing.assert_close(lap, ((4 * d2 - 6) * torch.exp(-d2)).sum(1), rtol=1e-10, atol=1e-10)
+    dK = K.diff(x_i, e_i).sum(1).view(-1)                     # directional derivative of K along e
+    ref = (-2 * ((x[:, None, :] - y[None, :, :]) * e[:, None, :]).sum(-1) * torch.exp(-d2)).sum(1)
+    torch.testing.assert_close(dK, ref, rtol=1e-10, atol=1e-10)
+    div = (x_i * K).divergence(x_i).sum(1).view(-1)
+    xd = (x[:, None, :] * (x[:, None, :] - y[None, :, :])).sum(-1)
+    torch.testing.assert_close(div, ((3 - 2 * xd) * torch.exp(-d2)).sum(1), rtol=1e-10, atol=1e-10)
+    fac = (K + K).factorize(K).sum(1).view(-1)
+    torch.testing.assert_close(fac, 2 * torch.exp(-d2).sum(1), rtol=1e-10, atol=1e-10)
