@@ -67,6 +67,18 @@ def divergence(f: Node, v: Node) -> Node:
     return total
 
 
+def grad_matrix(f: Node, v: Node) -> Node:
+    """Jacobian of ``f`` w.r.t. ``v`` as a vector of dimension ``f.dim * v.dim``: the gradients of the components of ``f``,
+    concatenated (``keopscore/keopscore/formulas/maths/GradMatrix.py:14-28``)."""
+    res = None
+    for i in range(f.dim):
+        g_i = grad(f, v, ir.ElemT(ir.IntCst(1), f.dim, i))
+        if g_i.is_zero:
+            g_i = ir.SumT(ir.IntCst(0), v.dim) if v.dim > 1 else ir.IntCst(0)
+        res = g_i if res is None else ir.Concat(res, g_i)
+    return res
+
+
 def laplacian(f: Node, v: Node) -> Node:
     """``Divergence(Grad(f, v, 1), v)`` for a scalar formula (``autodiff/Laplacian.py``)."""
     if f.dim != 1:

@@ -135,9 +135,10 @@ class _Interp(ast.NodeVisitor):
             # common sub-expressions are shared by construction (hash-consed DAG + CSE at lowering): factorisation
             # (keopscore/keopscore/formulas/factorization/) is the identity here
             return args[0]
-        if name in ("Divergence", "Laplacian") and len(args) == 2 and isinstance(args[0], Node):
+        if name in ("Divergence", "Laplacian", "GradMatrix") and len(args) == 2 and isinstance(args[0], Node):
             from . import autodiff as _ad
-            return (_ad.divergence if name == "Divergence" else _ad.laplacian)(args[0], ir.as_node(args[1]))
+            fn_ = {"Divergence": _ad.divergence, "Laplacian": _ad.laplacian, "GradMatrix": _ad.grad_matrix}[name]
+            return fn_(args[0], ir.as_node(args[1]))
         if name == "Diff" and args and isinstance(args[0], Node):
             if len(args) != 3:
                 raise FormulaError("Diff(f, v, u) expects three arguments")

@@ -726,6 +726,11 @@ class LazyTensor:
         """``x.auto_factorize()`` (``lazy_tensor.py:1975-1988``): a no-op here, see :meth:`factorize`."""
         return self.unary("AutoFactorize", dimres=self.ndim)
 
+    def grad_matrix(self, other):
+        """Symbolic Jacobian of ``x`` with respect to the variable ``other``, flattened to a vector of dimension
+        ``x.ndim * other.ndim`` (``lazy_tensor.py:1990-2006``)."""
+        return self.unary("GradMatrix", dimres=self.ndim * other.ndim, opt_arg=other.formula)
+
     def divergence(self, var):
         """Symbolic divergence of ``x`` with respect to the variable ``var`` (``lazy_tensor.py:2038-2052``)."""
         return self.binary(var, "Divergence", dimres=1, dimcheck="same")

@@ -175,3 +175,15 @@ def test_divergence_laplacian_factorize():
     f = parse_formula("Exp(Var(0,3,0))+Exp(Var(0,3,0))")
     assert parse_formula("Factorize(Exp(Var(0,3,0))+Exp(Var(0,3,0)),Exp(Var(0,3,0)))") is f
     assert parse_formula("AutoFactorize(Exp(Var(0,3,0))+Exp(Var(0,3,0)))") is f
+
+
+def test_grad_matrix_is_the_jacobian():
+    """``GradMatrix(f, v)`` (keopscore/keopscore/formulas/maths/GradMatrix.py:14-28): f = d |d|^2 with d = x - y has the
+    Jacobian |d|^2 I + 2 d d^T."""
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal((4, 2)), rng.standard_normal((3, 2))
+    out = dag_eval.evaluate("Sum_Reduction(GradMatrix((Var(0,2,0)-Var(1,2,1))*SqDist(Var(0,2,0),Var(1,2,1)), Var(0,2,0)),0)",
+                            [], [x, y], "float64")
+    d = x[:, None, :] - y[None, :, :]
+    J = (d ** 2).sum(-1)[..., None, None] * np.eye(2) + 2 * d[..., :, None] * d[..., None, :]
+    np.testing.assert_allclose(out, J.sum(1).reshape(4, 4), rtol=1e-12)
