@@ -46,6 +46,9 @@ SM_COUNT, SM_MAX_HZ = 148, 1.965e9
 # dram__bytes_read.sum + dram__bytes_write.sum of one kb200_reduce launch of the full-size forward conv, from the
 # committed `ncu --set full` capture profiles/r01_ncu_gauss_fwd_v2.txt (28.148 MB + 42 KB; algorithmic bytes 32 MB)
 NCU_DRAM_BYTES_FWD = 28147968 + 42496
+# measured co-issue ceiling of the conv's instruction mix (8 packed-FP32 lane-ops per MUFU.EX2, independent chains, no
+# memory): 118.6 lane-ops + 14.83 ex2 / clk / SM = 92.7 % of both pipes at once (experiments/ffma2_peak.py on B200)
+MEASURED_MIX_EX2_PER_CLK_SM = 14.83
 ROOFLINE_PAIRS_PER_CLK_SM = {"gauss_fwd": 16.0, "gauss_grad": 128.0 / 11.0, "knn_d3": 128.0 / 7.0}
 
 
@@ -380,7 +383,10 @@ def main():
                      "traffic": NCU_DRAM_BYTES_FWD if (world == 1 and M == M_FULL) else None,
                      "note": "FP32/SFU roofline (SURVEY 8d): 1 MUFU.EX2 per pair at 16/clk/SM x 148 SM x %.0f MHz (max SM clock, %s)"
                              % (sm_hz / 1e6, peaks_src),
-                     "kernel": "kb200_reduce", "ms_per_launch": k_ms},
+                     "kernel": "kb200_reduce", "ms_per_launch": k_ms,
+                     "frac_of_measured_mix_ceiling": achieved / (MEASURED_MIX_EX2_PER_CLK_SM * SM_COUNT * sm_hz),
+                     "measured_mix_ceiling_note": "micro-benchmark of the same 8 FP32 : 1 EX2 mix reaches 14.83 pairs/clk/SM "
+                                                  "(92.7 % of nominal) -- experiments/ffma2_peak.py"},
         "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": float(peaks.get("hbm_gbs", 6650.0)),
                          "unit": "GB/s", "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
                          "traffic": None, "note": "algorithmic unique bytes 4*(M*3+N*4+M) per launch; the kernel is compute-bound (%s peak)" % peaks_src},
