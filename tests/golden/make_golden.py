@@ -121,6 +121,29 @@ for nm in GRAD_OPS:
              aliases=ali + ["Var(3,DIMOUT,0)", "Var(4,DIMOUT,0)"])
 
 
+# ---- forward-mode differentials and the differential operators built on them (added later: these cases draw their inputs
+# from a generator seeded by their own name, so that `make_golden.py fm_ dop_` reproduces them without touching the others)
+G2 = "Sum_Reduction(Exp(-SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,2,1),0)"
+XYB2 = [(3, 0, "u"), (3, 1, "u"), (2, 1, "n")]
+for vname, vstr, tspec in (("x", V(0, 3, 0), (3, 0, "n")), ("y", V(1, 3, 1), (3, 1, "n")), ("b", V(2, 2, 1), (2, 1, "n"))):
+    case("fm_diff_gauss_" + vname, "Diff_WithSavedForward(%s,%s,Var(3,%d,%d),Var(4,2,0))" % (G2, vstr, tspec[0], tspec[1]),
+         XYB2 + [tspec, ("fwd", 0, G2)], dtypes=("float64",))
+case("fm_diff_lse_x", "Diff_WithSavedForward(%s,%s,Var(4,3,0),Var(5,2,0))" % (C4, V(1, 3, 0)),
+     LSE_ARGS + [(3, 0, "n"), ("lse_fwd", 0, C4)], dtypes=("float64",))
+DOPS = {
+    "laplacian": "Sum_Reduction(Laplacian(Exp(-SqDist(x,y)),x)*b,0)",
+    "divergence": "Sum_Reduction(Divergence(x*Exp(-SqDist(x,y)),x)*b,0)",
+    "gradmatrix": "Sum_Reduction(GradMatrix((x-y)*SqDist(x,y),x)*b,0)",
+    "factorize": "Sum_Reduction(Factorize(Exp(-SqDist(x,y))+Exp(-SqDist(x,y))*b,Exp(-SqDist(x,y))),0)",
+    "autofactorize": "Sum_Reduction(AutoFactorize(Exp(-SqDist(x,y))*b+Exp(-SqDist(x,y))),0)",
+    "formula_grad": "Sum_Reduction(Grad(Exp(-SqDist(x,y))*b,x,Var(3,1,0)),0)",
+    "formula_diff": "Sum_Reduction(Diff(Exp(-SqDist(x,y))*b,x,Var(4,3,0)),0)",
+}
+for nm, f in DOPS.items():
+    case("dop_" + nm, f, [(3, 0, "u"), (3, 1, "u"), (1, 1, "p"), (1, 0, "n"), (3, 0, "n")], dtypes=("float64",),
+         aliases=["x=Vi(3)", "y=Vj(3)", "b=Vj(1)", "e=Vi(1)", "u=Vi(3)"])
+
+
 def flags(formula):
     head = formula.split("(")[0]
     sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
@@ -147,6 +170,9 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
+        if c["name"].startswith(("fm_", "dop_")):
+            import zlib
+            rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])
         nx, ny = c["sizes"]
         args = []
