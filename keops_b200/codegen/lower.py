@@ -7,6 +7,8 @@ addition are contracted to FMAs by the emitter exactly as nvcc contracts the ref
 """
 from __future__ import annotations
 
+import struct
+
 from typing import Dict, List
 
 from ..formulas.ir import Node, FormulaError
@@ -44,7 +46,11 @@ class Lowerer:
         if op == "IntCst":
             return [g.const(float(n.params[0]))]
         if op == "RatCst":
-            return [g.const(n.params[0] / n.params[1])]
+            # reference quirk: a rational constant is emitted as ``(float)(p/q)`` whatever the dtype
+            # (keopscore/keopscore/formulas/variables/RatCst.py:22-24) -- and ``x / IntCst(n)`` is rewritten to
+            # ``RatCst(1, n) * x`` (maths/Divide.py:52-53) -- so in float64 these constants carry float32 rounding.
+            # Reproduced here: parity with the reference's outputs is the contract (golden case op2_extractT_cst_float64).
+            return [g.const(struct.unpack("f", struct.pack("f", n.params[0] / n.params[1]))[0])]
         if op == "FloatCst":
             return [g.const(n.params[0])]
 

@@ -124,7 +124,12 @@ class Cst(Op):
         self.val = val
 
     def ev(self, env):
-        return np.full((1, 1, 1), float(self.val), env.dtype)
+        val = float(self.val)
+        if isinstance(self.val, Fraction) and self.val.denominator != 1:
+            # a rational constant is emitted as ``(float)(p/q)`` whatever the dtype
+            # (keopscore/keopscore/formulas/variables/RatCst.py:22-24)
+            val = float(np.float32(val))
+        return np.full((1, 1, 1), val, env.dtype)
 
     def difft(self, v, g):
         return Zero(v.dim)
@@ -230,6 +235,10 @@ class _Divide(_Elementwise):
 def Divide(a, b):
     if a.iszero():
         return Zero(_bd(a, b))
+    if isinstance(b, Cst) and isinstance(b.val, (int, Fraction)) and b.val != 0:
+        # division by an integer / rational constant becomes a product with its (float-rounded) inverse
+        # (keopscore/keopscore/formulas/maths/Divide.py:52-55)
+        return Cst(1 / Fraction(b.val)) * a
     return _Divide(a, b)
 
 def Broadcast(a, dim):
@@ -370,6 +379,94 @@ class LessThan(_Elementwise):
 class LessOrEqual(_Elementwise):
     def f(self, env, a, b): return (a <= b).astype(env.dtype)
     def difft(self, v, g): return Zero(v.dim)
+
+
+class Equal(_Elementwise):
+    def f(self, env, a, b): return (a == b).astype(env.dtype)                    # maths/Equal.py
+    def difft(self, v, g): return Zero(v.dim)
+
+
+class NotEqual(_Elementwise):
+    def f(self, env, a, b): return (a != b).astype(env.dtype)                    # maths/NotEqual.py
+    def difft(self, v, g): return Zero(v.dim)
+
+
+class Atan2(_Elementwise):
+    def f(self, env, a, b): return np.arctan2(a, b)                              # math_functions.py:85
+    def difft(self, v, g):                                                       # maths/Atan2.py: d atan2(y, x) = (x dy - y dx) / (x^2 + y^2)
+        a, b = self.children
+        r2 = Square(a) + Square(b)
+        return a.difft(v, _red(g * b / r2, a.dim)) - b.difft(v, _red(g * a / r2, b.dim))
+
+
+class Mod(_Elementwise):
+    def f(self, env, x, n, d): return x - n * np.floor((x - d) / n)              # math_functions.py:157-160
+    def difft(self, v, g):                                                       # maths/Mod.py: derivative of x only
+        x = self.children[0]
+        return x.difft(v, _red(g, x.dim))
+
+
+class SinXDivX(_Unary):
+    def f(self, env, a):                                                         # math_functions.py:78-81
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(a != 0, np.sin(a) / np.where(a != 0, a, env.dtype.type(1)), env.dtype.type(1))
+    def d(self, a): return Cos(a) / a - Sin(a) / Square(a)                       # maths/SinXDivX.py
+
+
+class _VecReduce(Op):
+    """Max / Min / ArgMax / ArgMin of a vector: sequential scan with a strict comparison, so the first extremum wins
+    (maths/Max.py:25-38, maths/ArgMax.py:29-47)."""
+    arg, sign = False, 1
+
+    def __init__(self, a):
+        self.children = (a,)
+        self.dim = 1
+
+    def ev(self, env):
+        a = self.sign * self.children[0].ev(env)
+        best, idx = a[..., 0:1].copy(), np.zeros_like(a[..., 0:1])
+        for k in range(1, a.shape[-1]):
+            upd = a[..., k:k + 1] > best
+            best = np.where(upd, a[..., k:k + 1], best)
+            idx = np.where(upd, env.dtype.type(k), idx)
+        return idx if self.arg else self.sign * best
+
+    def difft(self, v, g):
+        if self.arg:
+            return Zero(v.dim)
+        a = self.children[0]                                                     # maths/Max.py: gradient through the arg-extremum
+        return a.difft(v, OneHot((ArgMax if self.sign == 1 else ArgMin)(a), a.dim) * g)
+
+
+class Max(_VecReduce):
+    pass
+
+
+class Min(_VecReduce):
+    sign = -1
+
+
+class ArgMax(_VecReduce):
+    arg = True
+
+
+class ArgMin(_VecReduce):
+    arg, sign = True, -1
+
+
+class OneHot(Op):
+    """``out[(int)(a + .5)] = 1`` (maths/OneHot.py:25-37)"""
+
+    def __init__(self, a, dim):
+        self.children, self.dim = (a,), int(dim)
+
+    def ev(self, env):
+        a = self.children[0].ev(env)
+        k = (a + 0.5).astype(np.int64)
+        return (k == np.arange(self.dim).reshape((1,) * (a.ndim - 1) + (self.dim,))).astype(env.dtype)
+
+    def difft(self, v, g):
+        return Zero(v.dim)
 
 
 class IfElse(_Elementwise):
@@ -658,6 +755,69 @@ def Grad_WithSavedForward(red, v, gradin, f0):
     if red.kind in ("ArgMin", "ArgMax", "ArgKMin", "Zero"):
         return Zero_Reduction(v.dim, newtag)
     raise NotImplementedError("no autodiff through " + red.kind)
+
+
+def _placeholder(dim, *forms):
+    """fresh variable used to take adjoints; it must have vanished from the result (autodiff/Diff.py:24-36)"""
+    return Var(10 ** 6 + dim, dim, 2)
+
+
+def Grad(f, v, gradin):
+    """``autodiff/Grad.py:14-27``: formula-level gradient, or the gradient of a reduction."""
+    if isinstance(f, Reduction):
+        return Grad_WithSavedForward(f, v, gradin, None)
+    return f.difft(v, _w(gradin))
+
+
+def Diff(f, v, u):
+    """``autodiff/Diff.py:14-36``: D_v f . u as the adjoint (w.r.t. a placeholder gradin) of the gradient."""
+    if isinstance(f, Reduction):
+        return Diff_WithSavedForward(f, v, u, None)
+    g = _placeholder(f.dim)
+    h = f.difft(v, g)
+    return (Scalprod(h, u) if v.dim > 1 else h * u).difft(g, IntCst(1))
+
+
+def Diff_WithSavedForward(red, v, u, f0):
+    """``reductions/Sum_Reduction.py:47-50``, ``Max_SumShiftExpWeight_Reduction.py:105-120``."""
+    if red.kind == "Sum":
+        return Sum_Reduction(Diff(red.F, v, u), red.tagI)
+    if red.kind == "LSE":
+        M = Extract(f0, 0, 1)
+        return Sum_Reduction(Diff(Concat(Zero(1), Exp(red.F - M) * red.G), v, u), red.tagI)
+    raise NotImplementedError("no forward-mode autodiff through " + red.kind)
+
+
+def Divergence(f, v):
+    """``autodiff/Divergence.py``: trace of the Jacobian."""
+    total = None
+    for k in range(v.dim):
+        term = Elem(Diff(f, v, ElemT(IntCst(1), v.dim, k)), k)
+        total = term if total is None else total + term
+    return total
+
+
+def Laplacian(f, v):
+    """``autodiff/Laplacian.py``"""
+    return Divergence(f.difft(v, IntCst(1)), v)
+
+
+def GradMatrix(f, v):
+    """``maths/GradMatrix.py:14-28``: gradients of the components of f, concatenated."""
+    res = None
+    for i in range(f.dim):
+        g_i = f.difft(v, ElemT(IntCst(1), f.dim, i))
+        res = g_i if res is None else Concat(res, g_i)
+    return res
+
+
+def Factorize(f, g):
+    """``formulas/factorization``: evaluation-order hint only, the value is f."""
+    return f
+
+
+def AutoFactorize(f):
+    return f
 
 
 _NAMESPACE = {k: v for k, v in list(globals().items()) if k[0].isupper() and k not in ("Op", "Reduction", "Fraction")}

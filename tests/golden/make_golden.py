@@ -122,7 +122,7 @@ for nm in GRAD_OPS:
 
 
 # ---- forward-mode differentials and the differential operators built on them (added later: these cases draw their inputs
-# from a generator seeded by their own name, so that `make_golden.py fm_ dop_` reproduces them without touching the others)
+# from a generator seeded by their own name, so that `make_golden.py fm_ dop_ op2_` reproduces them without touching the others)
 G2 = "Sum_Reduction(Exp(-SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,2,1),0)"
 XYB2 = [(3, 0, "u"), (3, 1, "u"), (2, 1, "n")]
 for vname, vstr, tspec in (("x", V(0, 3, 0), (3, 0, "n")), ("y", V(1, 3, 1), (3, 1, "n")), ("b", V(2, 2, 1), (2, 1, "n"))):
@@ -142,6 +142,26 @@ DOPS = {
 for nm, f in DOPS.items():
     case("dop_" + nm, f, [(3, 0, "u"), (3, 1, "u"), (1, 1, "p"), (1, 0, "n"), (3, 0, "n")], dtypes=("float64",),
          aliases=["x=Vi(3)", "y=Vj(3)", "b=Vj(1)", "e=Vi(1)", "u=Vi(3)"])
+
+
+OPS2 = {
+    "asin_acos": "Sum_Reduction(Asin((x|y)/IntCst(4))*Acos(Elem(x,0)*Elem(y,1)/IntCst(2))*b,0)",
+    "atan2": "Sum_Reduction(Atan2(x-y,x+y+IntCst(1))*b,0)",
+    "argminmax_vec": "Sum_Reduction((ArgMax(x-y)+IntCst(3)*ArgMin(x*y)+Max(x+y)+Min(x-y))*b,0)",
+    "clampint": "Sum_Reduction(ClampInt(IntCst(3)*(x-y),-1,1)*b,0)",
+    "diffclampint": "Sum_Reduction(DiffClampInt(IntCst(3)*(x-y),-1,1)*b,0)",
+    "compare": "Sum_Reduction((LessThan(x,y)+LessOrEqual(y,x)*IntCst(2)+Equal(Round(x,0),Round(y,0))*IntCst(4)"
+               "+NotEqual(Floor(IntCst(2)*x),Floor(IntCst(2)*y))*IntCst(8))*b,0)",
+    "extractT_cst": "Sum_Reduction(ExtractT(x,1,5)*b*IntInv(3)+RatCst(2,7),0)",
+    "mod": "Sum_Reduction(Mod(IntCst(5)*(x-y),IntCst(2),IntCst(-1))*b,0)",
+    "onehot": "Sum_Reduction(OneHot(Floor(IntCst(3)*b-IntCst(1)),5)*Elem(x,0),0)",
+    "sinxdivx": "Sum_Reduction(SinXDivX(IntCst(4)*(x-y))*b,0)",
+    "sqnorms": "Sum_Reduction(SqNorm2(x-y)*WeightedSqNorm(b+IntCst(1),x+y)*b,0)",
+    "vecmatmult": "Sum_Reduction(VecMatMult(x,TensorProd(x,y))*b,0)",
+    "zero": "Sum_Reduction(Zero(3)+x*b,0)",
+}
+for nm, f in OPS2.items():
+    case("op2_" + nm, f, [(3, 0, "u"), (3, 1, "u"), (1, 1, "p")], aliases=["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"])
 
 
 def flags(formula):
@@ -170,7 +190,7 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
-        if c["name"].startswith(("fm_", "dop_")):
+        if c["name"].startswith(("fm_", "dop_", "op2_")):
             import zlib
             rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])
