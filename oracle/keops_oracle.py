@@ -857,7 +857,7 @@ class _Env:
         return a[None, :, :]
 
 
-def genred(formula, aliases, args, dtype="float32", chunk_elems=1 << 24):
+def genred(formula, aliases, args, dtype="float32", chunk_elems=1 << 24, sizes=None):
     """Raw kernel output ``(nrow, dim)`` of the reduction string, before any Python post-processing
     (what ``LoadKeOps.genred`` returns, ``pykeops/pykeops/common/keops_io/LoadKeOps.py:177-243``)."""
     red = parse(formula, aliases)
@@ -865,6 +865,8 @@ def genred(formula, aliases, args, dtype="float32", chunk_elems=1 << 24):
     vs = red.vars()
     tagI = red.tagI
     nrow = ncol = None
+    if sizes is not None:                      # (nx, ny) as handed to the binder: needed when a side has no variable
+        nrow, ncol = (sizes[0], sizes[1]) if tagI == 0 else (sizes[1], sizes[0])
     for v in vs.values():
         if v.cat == 2:
             continue

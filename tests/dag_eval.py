@@ -32,7 +32,7 @@ def _fn(op, a, dt):
     return f[op]()
 
 
-def evaluate(formula, aliases, args, dtype="float64", fast=False):
+def evaluate(formula, aliases, args, dtype="float64", fast=False, sizes=None):
     """Dense evaluation of the *lowered* reduction: returns the raw output (nrow, dim)."""
     red = parse_reduction(formula, aliases)
     dt = np.dtype(dtype)
@@ -40,6 +40,8 @@ def evaluate(formula, aliases, args, dtype="float64", fast=False):
     low = lower_reduction(red, fast)
     vs = {v.params[0]: (v.params[1], v.params[2]) for v in red.variables()}
     nrow = ncol = 1
+    if sizes is not None:                      # (nx, ny): a side without variables still has a size
+        nrow, ncol = (sizes[0], sizes[1]) if tagI == 0 else (sizes[1], sizes[0])
     for ind, (dim, cat) in vs.items():
         if cat == tagI:
             nrow = np.asarray(args[ind]).reshape(-1, dim).shape[0]

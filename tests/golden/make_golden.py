@@ -164,6 +164,16 @@ for nm, f in OPS2.items():
     case("op2_" + nm, f, [(3, 0, "u"), (3, 1, "u"), (1, 1, "p")], aliases=["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"])
 
 
+GRAD_OPS2 = ["asin_acos", "atan2", "argminmax_vec", "clampint", "extractT_cst", "mod", "sinxdivx", "sqnorms", "vecmatmult"]
+for nm in GRAD_OPS2:
+    f = OPS2[nm]
+    ali = ["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"]
+    for vname, vstr in (("x", V(0, 3, 0)), ("y", V(1, 3, 1)), ("b", V(2, 1, 1))):
+        case("op2grad_%s_%s" % (nm, vname), "Grad_WithSavedForward(%s,%s,%s,%s)" % (f, vstr, "Var(3,DIMOUT,0)", "Var(4,DIMOUT,0)"),
+             [(3, 0, "u"), (3, 1, "u"), (1, 1, "p"), ("eta", 0, f), ("fwd", 0, f)], dtypes=("float64",),
+             aliases=ali + ["Var(3,DIMOUT,0)", "Var(4,DIMOUT,0)"])
+
+
 def flags(formula):
     head = formula.split("(")[0]
     sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
@@ -190,7 +200,7 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
-        if c["name"].startswith(("fm_", "dop_", "op2_")):
+        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_")):
             import zlib
             rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])

@@ -11,7 +11,7 @@ from tests import util, dag_eval
 @pytest.mark.parametrize("name", util.golden_names())
 def test_lowered_formula_matches_reference(name):
     meta, args, ref = util.load_case(name)
-    got = dag_eval.evaluate(meta["formula"], meta["aliases"], args, "float64", fast=False)
+    got = dag_eval.evaluate(meta["formula"], meta["aliases"], args, "float64", fast=False, sizes=(meta["nx"], meta["ny"]))
     assert got.shape == ref.shape, (got.shape, ref.shape)
     head = meta["formula"].split("(")[0]
     if "Arg" in head or "KMin" in head:
