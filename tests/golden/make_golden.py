@@ -174,6 +174,26 @@ for nm in GRAD_OPS2:
              aliases=ali + ["Var(3,DIMOUT,0)", "Var(4,DIMOUT,0)"])
 
 
+# ---- second-order gradients (what autograd builds for grad-of-grad, cf. test_lazytensor_gaussian_cpu.py) and the gradients
+# of a weighted soft-max reduction
+G1X = "Grad_WithSavedForward(%s,%s,Var(3,1,0),Var(4,1,0))" % (G, V(0, 3, 0))
+G1Y = "Grad_WithSavedForward(%s,%s,Var(3,1,0),Var(4,1,0))" % (G, V(1, 3, 1))
+A5 = XYB + [("eta", 0, G), ("fwd", 0, G)]
+case("so_gauss_xx", "Grad_WithSavedForward(%s,%s,Var(5,3,0),Var(6,3,0))" % (G1X, V(0, 3, 0)),
+     A5 + [("eta", 0, G1X, 5), ("fwd", 0, G1X, 5)], dtypes=("float64",))
+case("so_gauss_xy", "Grad_WithSavedForward(%s,%s,Var(5,3,0),Var(6,3,0))" % (G1X, V(1, 3, 1)),
+     A5 + [("eta", 0, G1X, 5), ("fwd", 0, G1X, 5)], dtypes=("float64",))
+case("so_gauss_x_eta", "Grad_WithSavedForward(%s,%s,Var(5,3,0),Var(6,3,0))" % (G1X, V(3, 1, 0)),
+     A5 + [("eta", 0, G1X, 5), ("fwd", 0, G1X, 5)], dtypes=("float64",))
+case("so_gauss_yb", "Grad_WithSavedForward(%s,%s,Var(5,3,1),Var(6,3,1))" % (G1Y, V(2, 1, 1)),
+     A5 + [("eta", 1, G1Y, 5), ("fwd", 1, G1Y, 5)], dtypes=("float64",))
+SSW = "Max_SumShiftExpWeight_Reduction((Var(0,3,0) | Var(1,3,1)),0,Concat(IntCst(1),Var(2,2,1)))"
+SSW_ARGS = [(3, 0, "n"), (3, 1, "n"), (2, 1, "n")]
+for vname, vstr in (("x", V(0, 3, 0)), ("y", V(1, 3, 1)), ("b", V(2, 2, 1))):
+    case("ssw_grad_" + vname, "Grad_WithSavedForward(%s,%s,Var(3,4,0),Var(4,4,0))" % (SSW, vstr),
+         SSW_ARGS + [(4, 0, "n"), ("fwd", 0, SSW)], dtypes=("float64",))
+
+
 def flags(formula):
     head = formula.split("(")[0]
     sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
@@ -200,7 +220,7 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
-        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_")):
+        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_")):
             import zlib
             rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])
@@ -208,12 +228,13 @@ def main():
         args = []
         formula, aliases = c["formula"], c["aliases"]
         for spec in c["args"]:
-            dim, cat, kind = spec
+            dim, cat, kind = spec[:3]
+            nprev = spec[3] if len(spec) > 3 else None
             n = {0: nx, 1: ny}.get(cat)
             if dim in ("lse_fwd", "fwd", "eta"):
                 # saved forward output (or a random upstream gradient of the same shape)
-                fwd, dimout, _ = run_reference(kind, aliases[:3] if aliases else [], args[:4 if dim == "lse_fwd" else 3],
-                                               c["dtype"], nx, ny)
+                take = nprev if nprev is not None else (4 if dim == "lse_fwd" else 3)
+                fwd, dimout, _ = run_reference(kind, aliases[:take] if aliases else [], args[:take], c["dtype"], nx, ny)
                 if dim == "eta":
                     a = rng.standard_normal(fwd.shape).astype(dt)
                 else:
