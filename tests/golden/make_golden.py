@@ -194,6 +194,15 @@ for vname, vstr in (("x", V(0, 3, 0)), ("y", V(1, 3, 1)), ("b", V(2, 2, 1))):
          SSW_ARGS + [(4, 0, "n"), ("fwd", 0, SSW)], dtypes=("float64",))
 
 
+# ---- exact ties: integer-valued points, so that many columns share the extremal value (the smallest index must win)
+TI = [(3, 0, "i"), (3, 1, "i")]
+case("ties_argmin", "ArgMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),0)", TI, sizes=(64, 301))
+case("ties_min_argmin", "Min_ArgMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),0)", TI, sizes=(64, 301))
+case("ties_max_argmax_axis0", "Max_ArgMax_Reduction((Var(0,3,0) | Var(1,3,1)),1)", TI, sizes=(151, 80))
+case("ties_argkmin", "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),7,0)", TI, sizes=(64, 301))
+case("ties_kmin_argkmin", "KMin_ArgKMin_Reduction(Sum(Abs((Var(0,3,0) - Var(1,3,1)))),5,1)", TI, sizes=(120, 90))
+
+
 def flags(formula):
     head = formula.split("(")[0]
     sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
@@ -220,7 +229,7 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
-        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_")):
+        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_")):
             import zlib
             rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])
@@ -250,6 +259,8 @@ def main():
                 a = 0.5 + 1.5 * rng.random(shape)
             elif kind == "eps":
                 a = np.full(shape, 0.05)
+            elif kind == "i":
+                a = rng.integers(0, 3, shape).astype(np.float64)
             args.append(a.astype(dt))
         if "DIMOUT" in formula:
             dimout = args[-1].shape[1]
