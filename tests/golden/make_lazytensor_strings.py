@@ -38,6 +38,15 @@ EXPRS = {
     "grad": "((-x.sqdist(y)).exp() * b).grad(x, s)",
     "square_abs": "(x - y).square().sum(-1) * abs(x - y).sum(-1)",
     "sum_dim2": "(x * y).sum(2) + (x * y).sum(dim=-1)",
+    "transpose": "((-x.sqdist(y)).exp() * b).t()",
+    "transpose_T": "(x.weightedsqdist(y, s) * b).T",
+    "diff": "((-x.sqdist(y)).exp() * b).diff(x, x - y)",
+    "divergence": "(x * (-x.sqdist(y)).exp()).divergence(x)",
+    "laplacian": "(-x.sqdist(y)).exp().laplacian(x)",
+    # (grad_matrix is left out: the reference's method formats the LazyTensor object itself into the string,
+    #  lazy_tensor.py:2001-2005, so there is no valid reference string to compare with)
+    "factorize": "((-x.sqdist(y)).exp() + (-x.sqdist(y)).exp() * b).factorize((-x.sqdist(y)).exp())",
+    "auto_factorize": "((-x.sqdist(y)).exp() + (-x.sqdist(y)).exp() * b).auto_factorize()",
 }
 REDUCTIONS = {
     "sum1": ("gauss", "sum", dict(dim=1)),
@@ -51,6 +60,11 @@ REDUCTIONS = {
     "kmin": ("sqdist_methods", "Kmin", dict(K=4, dim=1)),
     "argkmin": ("sqdist_methods", "argKmin", dict(K=3, dim=0)),
     "kmin_argkmin": ("sqdist_methods", "Kmin_argKmin", dict(K=2, dim=1)),
+    "sum_reduction": ("gauss", "sum_reduction", dict(axis=1)),
+    "logsumexp_reduction": ("laplace", "logsumexp_reduction", dict(dim=0)),
+    "min_argmin_reduction": ("sqdist_methods", "min_argmin_reduction", dict(axis=1)),
+    "argKmin_reduction": ("sqdist_methods", "argKmin_reduction", dict(K=6, axis=1)),
+    "transposed_sum": ("transpose", "sum", dict(dim=1)),
 }
 
 
@@ -69,10 +83,10 @@ def build(LT):
         kw = dict(kw)
         if "weight" in kw:
             kw["weight"] = env[kw["weight"]]
-        args = (kw.pop("K"),) if "K" in kw else ()
+        args = (kw.pop("K"),) if ("K" in kw and not method.endswith("_reduction")) else ()   # *_reduction(**kwargs) take K= by name
         r = getattr(f, method)(*args, call=False, **kw)
         out["red:" + name] = dict(expr=expr, method=method, kwargs={k: (v if not hasattr(v, "formula") else "b") for k, v in kw.items()},
-                                  K=(args[0] if args else None), formula=r.formula.replace("VarSymb", "Var"),
+                                  K=(args[0] if args else kw.get("K")), formula=r.formula.replace("VarSymb", "Var"),
                                   formula2=(r.formula2.replace("VarSymb", "Var") if getattr(r, "formula2", None) else None),
                                   reduction_op=r.reduction_op, axis=int(r.axis), opt_arg=getattr(r, "opt_arg", None))
     return out
