@@ -76,7 +76,7 @@ def _one_side(ranges_out, ranges_red, keep):
     C_out, C_red = keep.shape
     if C_red == 0 or C_out == 0:
         return (torch.zeros(C_out, dtype=torch.int64, device=keep.device),
-                torch.zeros(0, 2, dtype=torch.int64, device=keep.device))
+                torch.zeros(0, 2, dtype=ranges_red.dtype, device=keep.device))
     k = keep.to(torch.bool)
     prev = torch.zeros_like(k)
     prev[:, 1:] = k[:, :-1]
@@ -90,15 +90,13 @@ def _one_side(ranges_out, ranges_red, keep):
     ends = k & ~(nxt & touch_next[None, :])               # a run ends here
     rs, cs = torch.nonzero(starts, as_tuple=True)          # row-major order: sorted by output cluster, then column
     re_, ce = torch.nonzero(ends, as_tuple=True)
-    red = torch.stack((ranges_red[cs, 0], ranges_red[ce, 1]), dim=1).to(torch.int64)
+    red = torch.stack((ranges_red[cs, 0], ranges_red[ce, 1]), dim=1)    # keeps the caller's integer dtype, like matrix.py:118-130
     slices = torch.cumsum(starts.sum(dim=1), 0).to(torch.int64)
     return slices, red
 
 
 def from_matrix(ranges_i, ranges_j, keep):
     """Boolean (Ci, Cj) mask between i-clusters and j-clusters -> the 6-tuple of ``ranges``."""
-    ranges_i = ranges_i.to(torch.int64)
-    ranges_j = ranges_j.to(torch.int64)
     keep = keep.to(ranges_i.device)
     slices_i, redranges_j = _one_side(ranges_i, ranges_j, keep)
     slices_j, redranges_i = _one_side(ranges_j, ranges_i, keep.t())
