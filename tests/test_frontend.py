@@ -187,3 +187,27 @@ def test_grad_matrix_is_the_jacobian():
     d = x[:, None, :] - y[None, :, :]
     J = (d ** 2).sum(-1)[..., None, None] * np.eye(2) + 2 * d[..., :, None] * d[..., None, :]
     np.testing.assert_allclose(out, J.sum(1).reshape(4, 4), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["f64", "f32", "f32_loose", "zero_rhs"])
+def test_conjugate_gradient_matches_reference(name):
+    """KernelSolve's host loop against recordings of the reference's ``ConjugateGradientSolver``
+    (pykeops/pykeops/common/operations.py:90-114; tests/golden/make_cg.py): same iterates bit for bit on a dense
+    operator, same number of operator applications (the stopping rule)."""
+    import os
+    import torch
+    from keops_b200.torch.kernel_solve import conjugate_gradient
+    rec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cg.npz"))
+    K, b, a_ref = (torch.from_numpy(rec["%s.%s" % (name, k)]) for k in ("K", "b", "a"))
+    calls = [0]
+
+    def linop(v):
+        calls[0] += 1
+        return K @ v
+
+    a = conjugate_gradient(linop, b, eps=float(rec[name + ".eps"]))
+    assert calls[0] == int(rec[name + ".calls"]) == conjugate_gradient.last_iterations
+    assert a.dtype == a_ref.dtype and a.shape == a_ref.shape
+    assert torch.equal(a, a_ref)
+    capped = conjugate_gradient(linop, b, eps=0.0, max_iter=3) if name != "zero_rhs" else None
+    assert capped is None or conjugate_gradient.last_iterations == 3
