@@ -34,6 +34,15 @@ def _is_lt(x):
 
 
 class LazyTensor:
+    # hooks for the numpy front-end (keops_b200/numpy): which callable classes run the reductions, and how a
+    # user-provided array becomes the torch tensor the bookkeeping below works with
+    _Genred = Genred
+    _KernelSolve = KernelSolve
+
+    @staticmethod
+    def _ingest(x):
+        return x
+
     def __init__(self, x=None, axis=None, is_complex=False):
         if is_complex:
             raise NotImplementedError("[KeOps-B200] complex LazyTensors are not implemented.")
@@ -52,6 +61,7 @@ class LazyTensor:
         self.is_complex = False
         if x is None:
             return
+        x = self._ingest(x)
         if isinstance(x, tuple):
             if len(x) != 3 or not all(isinstance(v, int) for v in x):
                 raise ValueError("LazyTensors(tuple) is only valid if tuple = (ind,dim,cat) is a triplet of integers.")
@@ -153,14 +163,14 @@ class LazyTensor:
         return 0 if len(sv) == 0 else 1 + max(v[0] for v in sv)
 
     def _copy_meta(self):
-        r = LazyTensor()
+        r = type(self)()
         for k in ("variables", "symbolic_variables", "ni", "nj", "batchdims", "_dtype", "ranges", "backend"):
             setattr(r, k, getattr(self, k))
         return r
 
     def _join(self, other):
         """Merge the bookkeeping of two operands (``lazy_tensor.py:355-430``)."""
-        r = LazyTensor()
+        r = type(self)()
         seen, vs = set(), []
         for v in self.variables + other.variables:
             if id(v) not in seen:
@@ -188,9 +198,8 @@ class LazyTensor:
         r.backend = self.backend if self.backend is not None else other.backend
         return r
 
-    @staticmethod
-    def _wrap(x):
-        return x if _is_lt(x) else LazyTensor(x)
+    def _wrap(self, x):
+        return x if _is_lt(x) else type(self)(x)
 
     def unary(self, operation, dimres=None, opt_arg=None, opt_arg2=None):
         r = self._copy_meta()
@@ -312,7 +321,7 @@ class LazyTensor:
                 return self.unary("Sqrt")
             if other == -0.5:
                 return self.unary("Rsqrt")
-            other = LazyTensor(other)
+            other = type(self)(other)
         if _is_lt(other):
             if other.ndim in (1, self.ndim):
                 return self.binary(other, "Powf", dimcheck=None)
@@ -519,7 +528,7 @@ class LazyTensor:
         r._init_kwargs = init
         if r._dtype is not None:
             r._fixvariables()
-            r.callfun = Genred(r.formula, [], reduction_op=reduction_op, axis=r.axis, opt_arg=opt_arg,
+            r.callfun = self._Genred(r.formula, [], reduction_op=reduction_op, axis=r.axis, opt_arg=opt_arg,
                                formula2=r.formula2, **init)
         if call and len(r.symbolic_variables) == 0 and r._dtype is not None:
             return r()
@@ -529,13 +538,13 @@ class LazyTensor:
         """``K.solve(b, alpha=...)``: solve ``(alpha Id + K) a = b`` by conjugate gradients
         (``lazy_tensor.py:779-870``)."""
         if not _is_lt(other):
-            other = LazyTensor(other, axis=0)
+            other = type(self)(other, axis=0)
         if len(other.symbolic_variables) == 0 and len(self.symbolic_variables) != 0:
             raise ValueError("If 'self' has symbolic variables, so should 'other'.")
         axis = 1 - other.axis
         if var is None:
             varindex = self.new_variable_index()
-            var = LazyTensor((varindex, other.ndim, axis))
+            var = type(self)((varindex, other.ndim, axis))
             r = self * var
         else:
             varindex = var.symbolic_variables[0][0]
@@ -554,7 +563,7 @@ class LazyTensor:
             r._dtype = other._dtype
         if r._dtype is not None:
             r._fixvariables()
-            r.callfun = KernelSolve(r.formula, [], r.varformula, r.axis, **init)
+            r.callfun = self._KernelSolve(r.formula, [], r.varformula, r.axis, **init)
         if call and len(other.symbolic_variables) == 0 and r._dtype is not None:
             return r()
         return r
@@ -568,12 +577,12 @@ class LazyTensor:
         if self.backend is not None and "backend" not in self.kwargs:
             self.kwargs["backend"] = self.backend
         if self._dtype is None:
-            self._dtype = str(args[0].dtype).split(".")[1]
+            self._dtype = str(args[0].dtype).split(".")[-1]
             self._fixvariables()
             if self.reduction_op == "Solve":
-                self.callfun = KernelSolve(self.formula, [], self.varformula, self.axis, **self._init_kwargs)
+                self.callfun = self._KernelSolve(self.formula, [], self.varformula, self.axis, **self._init_kwargs)
             else:
-                self.callfun = Genred(self.formula, [], reduction_op=self.reduction_op, axis=self.axis,
+                self.callfun = self._Genred(self.formula, [], reduction_op=self.reduction_op, axis=self.axis,
                                       opt_arg=self.opt_arg, formula2=self.formula2, **self._init_kwargs)
         if self.reduction_op == "Solve" and len(self.other.symbolic_variables) == 0:
             if args != ():
@@ -646,6 +655,8 @@ class LazyTensor:
         if self._shape[-1] != 1:
             raise ValueError("The 'K @ v' syntax is only supported for LazyTensors 'K' whose trailing dimension "
                              "is equal to 1. Here, K.shape = {}.".format(self.shape))
+        if not _is_lt(v):
+            v = self._ingest(v)
         if _is_lt(v):
             Kv = self * v
         else:
@@ -653,10 +664,10 @@ class LazyTensor:
                 newdims = (1, v.shape[0], 1)
             else:
                 newdims = tuple(v.shape[:-2]) + (1,) + tuple(v.shape[-2:])
-            Kv = self * LazyTensor(v.view(newdims))
+            Kv = self * type(self)(v.view(newdims))
         out = Kv.sum(Kv.dim() - 2, **kwargs)
         if not _is_lt(v) and v.dim() == 1:
-            out = out.view(-1)
+            out = out.reshape(-1)
         return out
 
     def t(self):
