@@ -10,11 +10,19 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+# The test BODIES below also run unchanged against the real reference on CPU tensors, which pins their expectations:
+#   KT_MODULE=pykeops.torch KB200_TEST_DEVICE=cpu CXX=/usr/bin/g++ PYTHONPATH=/root/reference/keopscore:/root/reference/pykeops \
+#       python -m pytest tests/test_torch_api_gpu.py -m gpu        (20 passed, 4 skipped in this container)
+# Only the documented deviations are switched off there: this engine has no CPU backend and refuses host tensors.
+import os
+AGAINST_REFERENCE = os.environ.get("KT_MODULE", "").startswith("pykeops")
+
 
 @pytest.fixture(scope="module")
 def api(cuda_device):
-    import keops_b200.torch as kt
-    return kt
+    import importlib
+    import os
+    return importlib.import_module(os.environ.get("KT_MODULE", "keops_b200.torch"))
 
 
 def test_install_known_answer(api, cuda_device):
@@ -24,6 +32,7 @@ def test_install_known_answer(api, cuda_device):
     assert out.view(-1).tolist() == [63.0, 90.0]
 
 
+@pytest.mark.skipif(AGAINST_REFERENCE, reason="the shim is this package's own entry point")
 def test_pykeops_shim_runs_reference_style_user_code(cuda_device):
     import keops_b200
     keops_b200.install_as_pykeops()
@@ -66,6 +75,8 @@ def test_lazytensor_gaussian_conv_and_gradients(api, cuda_device, dtype, rtol):
 
 @pytest.mark.parametrize("backend", ["auto", "GPU", "GPU_1D", "GPU_2D"])
 def test_genred_sum_backends(api, cuda_device, backend):
+    if AGAINST_REFERENCE and backend != "auto":
+        pytest.skip("the reference's GPU backends need a GPU")
     torch.manual_seed(1)
     M, N, D = 700, 1900, 3
     x, y, b = torch.rand(M, D, device=cuda_device), torch.rand(N, D, device=cuda_device), torch.rand(N, 2, device=cuda_device)
@@ -74,8 +85,9 @@ def test_genred_sum_backends(api, cuda_device, backend):
     got = conv(x, y, b, p, backend=backend)
     ref = torch.exp(-0.7 * ((x[:, None] - y[None]) ** 2).sum(-1)) @ b
     assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5 * ref.abs().max().item())
-    with pytest.raises(ValueError):
-        conv(x, y, b, p, backend="CPU")
+    if not AGAINST_REFERENCE:                   # documented deviation: no CPU backend here
+        with pytest.raises(ValueError):
+            conv(x, y, b, p, backend="CPU")
 
 
 def test_heterogeneous_aliases_and_out_inplace(api, cuda_device):
@@ -219,8 +231,9 @@ def test_error_behaviour(api, cuda_device):
     x = torch.rand(10, 3, device=cuda_device)
     with pytest.raises(ValueError):
         api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], axis=1)(x)            # wrong number of args
-    with pytest.raises(ValueError):
-        api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], axis=1)(x, x.cpu())   # mixed devices / no CPU path
+    if not AGAINST_REFERENCE:
+        with pytest.raises(ValueError):
+            api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], axis=1)(x, x.cpu())   # mixed devices / no CPU path
     with pytest.raises(ValueError):
         api.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(4)"], axis=1)(x, x)         # wrong vector size
     with pytest.raises(ValueError):
