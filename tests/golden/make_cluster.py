@@ -35,6 +35,23 @@ def main():
                          cc=cluster_centroids(x, lx.long()),
                          r0=rng[0], r1=rng[1], r2=rng[2], r3=rng[3], r4=rng[4], r5=rng[5]).items():
             rec["%s.%s" % (tag, k)] = v.numpy()
+    # the numpy flavour of the same helpers (pykeops/pykeops/numpy/cluster/*.py) on the same points: it anchors the grid
+    # at the origin and does not clamp weights, so its outputs are recorded separately under "np_<tag>"
+    from pykeops.numpy import cluster as npc
+    for tag in sorted({k.split(".")[0] for k in rec}):
+        x, y, w = rec[tag + ".x"], rec[tag + ".y"], rec[tag + ".w"] + 0.05
+        size = float(tag.split("_s")[1].replace("p", "."))
+        lx, ly = npc.grid_cluster(x, size), npc.grid_cluster(y, size)
+        rx, cx, wx = npc.cluster_ranges_centroids(x, lx)
+        ry, cy, wy = npc.cluster_ranges_centroids(y, ly)
+        rxw, cxw, wxw = npc.cluster_ranges_centroids(x, lx, weights=w)
+        (xs, ws), lxs = npc.sort_clusters((x, w), lx)
+        keep = ((cx[:, None] - cy[None]) ** 2).sum(-1) < (1.4 * size) ** 2
+        rng = npc.from_matrix(rx, ry, keep)
+        for k, v in dict(w=w, lx=lx, ly=ly, rx=rx, cx=cx, wx=wx, ry=ry, cy=cy, rxw=rxw, cxw=cxw, wxw=wxw, xs=xs, ws=ws, lxs=lxs,
+                         keep=keep, cr=npc.cluster_ranges(lxs), cc=npc.cluster_centroids(x, lx),
+                         r0=rng[0], r1=rng[1], r2=rng[2], r3=rng[3], r4=rng[4], r5=rng[5]).items():
+            rec["np_%s.%s" % (tag, k)] = np.asarray(v)
     # the worked example of the reference's from_matrix docstring (matrix.py:59-110): gaps between clusters
     r_i = torch.IntTensor([[2, 5], [7, 12]])
     r_j = torch.IntTensor([[1, 4], [4, 9], [20, 30]])

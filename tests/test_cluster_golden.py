@@ -16,7 +16,7 @@ from keops_b200.torch.cluster import (grid_cluster, cluster_ranges_centroids, cl
                                       sort_clusters, from_matrix, swap_axes)
 
 REC = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cluster.npz"))
-TAGS = sorted({k.split(".")[0] for k in REC.files if not k.startswith("doc.")})
+TAGS = sorted({k.split(".")[0] for k in REC.files if not k.startswith(("doc.", "np_"))})
 
 
 def t(tag, k):
@@ -90,3 +90,41 @@ def test_from_matrix(tag):
     assert np.array_equal(covered(mine[0], mine[1], mine[2], n_i, n_j), covered(mine[3], mine[4], mine[5], n_j, n_i).T)
     sw = swap_axes(mine)
     assert all(torch.equal(u, v) for u, v in zip(sw, mine[3:] + mine[:3])) and swap_axes(None) is None
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_numpy_flavour(tag):
+    """keops_b200.numpy.cluster against recordings of ``pykeops.numpy.cluster`` (grid anchored at the origin, weights not
+    clamped, int64 everywhere): same exact / semantic split as the torch flavour above."""
+    from keops_b200.numpy import cluster as npc
+    x, y = REC[tag + ".x"], REC[tag + ".y"]
+    r = lambda k: REC["np_%s.%s" % (tag, k)]
+    size = float(tag.split("_s")[1].replace("p", "."))
+    w = r("w")
+    lx, ly = npc.grid_cluster(x, size), npc.grid_cluster(y, size)
+    assert lx.dtype == r("lx").dtype and np.array_equal(lx, r("lx")) and np.array_equal(ly, r("ly"))
+    rx, cx, wx = npc.cluster_ranges_centroids(x, lx)
+    assert rx.dtype == r("rx").dtype and np.array_equal(rx, r("rx")) and cx.dtype == r("cx").dtype
+    np.testing.assert_allclose(cx, r("cx"), rtol=1e-6, atol=1e-6)
+    assert wx.dtype == r("wx").dtype and np.array_equal(wx, r("wx"))
+    rxw, cxw, wxw = npc.cluster_ranges_centroids(x, lx, weights=w)
+    assert np.array_equal(rxw, r("rxw"))
+    np.testing.assert_allclose(cxw, r("cxw"), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(wxw, r("wxw"), rtol=1e-6)
+    np.testing.assert_allclose(npc.cluster_centroids(x, lx), r("cc"), rtol=1e-6, atol=1e-6)
+    (xs, ws), lxs = npc.sort_clusters((x, w), lx)
+    assert np.array_equal(lxs, r("lxs")) and np.array_equal(npc.cluster_ranges(lxs), r("cr"))
+    for a, b in r("cr").tolist():
+        assert sorted(np.concatenate((xs[a:b], ws[a:b, None]), 1).tolist()) == \
+               sorted(np.concatenate((r("xs")[a:b], r("ws")[a:b, None]), 1).tolist())
+    xl, _ = npc.sort_clusters([x, w], lx)
+    assert isinstance(xl, list) and np.array_equal(xl[0], xs)
+    ry = npc.cluster_ranges_centroids(y, ly)[0]
+    mine = npc.from_matrix(rx, ry, r("keep"))
+    ref = tuple(r("r%d" % k) for k in range(6))
+    assert all(m.dtype == q.dtype for m, q in zip(mine, ref))
+    assert np.array_equal(mine[0], ref[0]) and np.array_equal(mine[3], ref[3])
+    for side, (n_out, n_red) in ((0, (x.shape[0], y.shape[0])), (3, (y.shape[0], x.shape[0]))):
+        a = covered(mine[side], mine[side + 1], mine[side + 2], n_out, n_red)
+        assert a.max() <= 1 and np.array_equal(a, covered(ref[side], ref[side + 1], ref[side + 2], n_out, n_red))
+    assert all(u is v for u, v in zip(npc.swap_axes(mine), mine[3:] + mine[:3])) and npc.swap_axes(None) is None
