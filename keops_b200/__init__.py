@@ -16,7 +16,10 @@ def install_as_pykeops():
     this package, so existing user code runs unchanged on the B200 engine."""
     import sys
     import types
+    from . import numpy as _n
     from . import torch as _t
+    from .numpy import cluster as _nc
+    from .torch import cluster as _tc
 
     if "pykeops" in sys.modules and not getattr(sys.modules["pykeops"], "__kb200_shim__", False):
         raise RuntimeError("a real pykeops is already imported; use keops_b200.register_into_pykeops() instead")
@@ -24,16 +27,30 @@ def install_as_pykeops():
     root.__kb200_shim__ = True
     root.__version__ = "2.3+kb200." + __version__
     root.torch = _t
+    root.numpy = _n
     root.clean_pykeops = clean_cache
     root.test_torch_bindings = lambda: _smoke_install()
+    root.test_numpy_bindings = lambda: _smoke_install(numpy=True)
     sys.modules["pykeops"] = root
     sys.modules["pykeops.torch"] = _t
+    sys.modules["pykeops.numpy"] = _n
+    sys.modules["pykeops.torch.cluster"] = _tc          # the very same module objects, not second copies found via __path__
+    sys.modules["pykeops.numpy.cluster"] = _nc
     return root
 
 
-def _smoke_install():
-    """Same known answer as ``pykeops/pykeops/torch/test_install.py:5-25``."""
+def _smoke_install(numpy=False):
+    """Same known answer as ``pykeops/pykeops/torch/test_install.py:5-25`` / ``numpy/test_install.py:5-25``."""
     import torch as th
+    if numpy:
+        import numpy as np
+        from .numpy import Genred as NpGenred
+        x = np.arange(1, 10).reshape(-1, 3).astype("float32")
+        y = np.arange(3, 9).reshape(-1, 3).astype("float32")
+        out = NpGenred("SqNorm2(x-y)", ["x=Vi(3)", "y=Vj(3)"], reduction_op="Sum", axis=0)(x, y)
+        ok = bool(np.allclose(out.reshape(-1), [63.0, 90.0]))
+        print("pyKeOps-B200 with numpy bindings is working!" if ok else "pyKeOps-B200: outputs wrong values...")
+        return ok
     from .torch import Genred
     x = th.arange(1, 10, dtype=th.float32).view(-1, 3).cuda()
     y = th.arange(3, 9, dtype=th.float32).view(-1, 3).cuda()

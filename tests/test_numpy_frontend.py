@@ -85,3 +85,26 @@ def test_no_cpu_backend():
         kn.Vi(x).sqdist(kn.Vj(y)).argKmin(2, dim=1)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         (-kn.Vi(x).sqdist(kn.Vj(x))).exp().solve(kn.Vi(x), alpha=0.1)
+
+
+def test_pykeops_shim_exposes_numpy_and_cluster_modules():
+    """``keops_b200.install_as_pykeops()``: the user's unchanged ``from pykeops.numpy import ...`` /
+    ``from pykeops.torch.cluster import ...`` lines resolve to this package's module objects."""
+    import sys
+    import keops_b200
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "pykeops" or k.startswith("pykeops.")}
+    try:
+        root = keops_b200.install_as_pykeops()
+        from pykeops.numpy import LazyTensor, Genred, Vi                      # noqa: F401
+        from pykeops.numpy.cluster import grid_cluster as g_np
+        from pykeops.torch.cluster import from_matrix as fm_t
+        from pykeops.torch import LazyTensor as LT_t
+        import keops_b200.numpy.cluster as nc
+        import keops_b200.torch.cluster as tc
+        assert LazyTensor is kn.LazyTensor and Genred is kn.Genred and LT_t is kt.LazyTensor
+        assert g_np is nc.grid_cluster and fm_t is tc.from_matrix
+        assert root.numpy is kn and callable(root.test_numpy_bindings)
+    finally:
+        for k in [k for k in sys.modules if k == "pykeops" or k.startswith("pykeops.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
