@@ -145,3 +145,28 @@ def test_block_sparse_ranges(kn):
     mask[100:, 250:] = True
     ref = (gauss(x, y) * mask) @ b
     assert np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_non_contiguous_inputs_and_inplace_out(kn):
+    """pykeops/pykeops/test/test_contiguous_numpy.py and test_lazytensor_gaussian_numpy_inplace.py."""
+    rng = np.random.default_rng(6)
+    a1 = rng.random((2, 500, 5)).astype("float32")
+    a2 = np.ascontiguousarray(a1.transpose(2, 0, 1)).transpose(1, 2, 0)
+    assert not a2.flags["C_CONTIGUOUS"] and np.array_equal(a1, a2)
+    b, c = rng.random((2, 500, 5)).astype("float32"), rng.random((2, 500, 5)).astype("float32")
+    b_j = kn.LazyTensor(b[:, None])
+    d1 = (-kn.LazyTensor(a1[:, :, None]).sqdist(b_j)).exp() @ c
+    d2 = (-kn.LazyTensor(a2[:, :, None]).sqdist(b_j)).exp() @ c
+    ref = np.einsum("bmn,bnd->bmd", np.exp(-((a1[:, :, None] - b[:, None]) ** 2).sum(-1)), c)
+    assert d1.shape == (2, 500, 5) and np.array_equal(d1, d2)
+    assert np.abs(d1 - ref).max() <= 1e-5 * np.abs(ref).max()
+
+    M, N = 300, 200
+    x = rng.random((M, 1, 3)).astype("float32") / np.sqrt(3).astype("float32")
+    y = rng.random((1, N, 3)).astype("float32") / np.sqrt(3).astype("float32")
+    w = rng.standard_normal((N, 1)).astype("float32")
+    a = np.empty((M, 1), dtype="float32")
+    K = (-((kn.LazyTensor(x) - kn.LazyTensor(y)) ** 2).sum(axis=2)).exp()
+    ret = K.__matmul__(w, out=a)
+    assert ret is a
+    assert np.abs(a - np.exp(-((x - y) ** 2).sum(-1)) @ w).max() <= 1e-5

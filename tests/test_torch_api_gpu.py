@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 # The test BODIES below also run unchanged against the real reference on CPU tensors, which pins their expectations:
 #   KT_MODULE=pykeops.torch KB200_TEST_DEVICE=cpu CXX=/usr/bin/g++ PYTHONPATH=/root/reference/keopscore:/root/reference/pykeops \
-#       python -m pytest tests/test_torch_api_gpu.py -m gpu        (20 passed, 4 skipped in this container)
+#       python -m pytest tests/test_torch_api_gpu.py -m gpu        (21 passed, 4 skipped in this container)
 # Only the documented deviations are switched off there: this engine has no CPU backend and refuses host tensors.
 import os
 AGAINST_REFERENCE = os.environ.get("KT_MODULE", "").startswith("pykeops")
@@ -380,3 +380,32 @@ def test_lazytensor_diff_divergence_laplacian(api, cuda_device):
     torch.testing.assert_close(div, ((3 - 2 * xd) * torch.exp(-d2)).sum(1), rtol=1e-10, atol=1e-10)
     fac = (K + K).factorize(K).sum(1).view(-1)
     torch.testing.assert_close(fac, 2 * torch.exp(-d2).sum(1), rtol=1e-10, atol=1e-10)
+
+
+def test_non_contiguous_inputs_and_lazytensor_inplace_out(api, cuda_device):
+    """pykeops/pykeops/test/test_contiguous_torch.py (a permuted view of a batch variable gives the same result as its
+    contiguous copy) and test_lazytensor_gaussian_inplace.py (``K.__matmul__(b, sum_scheme=..., out=a)`` writes into ``a``)."""
+    torch.manual_seed(0)
+    a1 = torch.rand(2, 1000, 5, device=cuda_device)
+    a2 = a1.permute(2, 0, 1).contiguous().permute(1, 2, 0)
+    assert not a2.is_contiguous() and torch.equal(a1, a2)
+    b, c = torch.rand(2, 1000, 5, device=cuda_device), torch.rand(2, 1000, 5, device=cuda_device)
+    b_j = api.LazyTensor(b[:, None])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d1 = (-api.LazyTensor(a1[:, :, None]).sqdist(b_j)).exp() @ c
+        d2 = (-api.LazyTensor(a2[:, :, None]).sqdist(b_j)).exp() @ c
+    ref = torch.einsum("bmn,bnd->bmd", torch.exp(-((a1[:, :, None] - b[:, None]) ** 2).sum(-1)), c)
+    assert d1.shape == (2, 1000, 5) and torch.equal(d1, d2)
+    torch.testing.assert_close(d1, ref, rtol=1e-5, atol=1e-5 * ref.abs().max().item())
+
+    M, N, D = 20, 30, 3
+    x = torch.rand(M, 1, D, device=cuda_device) / math.sqrt(D)
+    y = torch.rand(1, N, D, device=cuda_device) / math.sqrt(D)
+    w = torch.randn(N, 1, device=cuda_device)
+    a = torch.empty(M, 1, device=cuda_device)
+    K = (-((api.LazyTensor(x) - api.LazyTensor(y)).square()).sum(dim=2)).exp()
+    ret = K.__matmul__(w, sum_scheme="block_sum", out=a)
+    assert ret.data_ptr() == a.data_ptr()
+    torch.testing.assert_close(a, torch.exp(-((x - y) ** 2).sum(-1)) @ w, rtol=1e-5, atol=1e-5)
