@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 # The test BODIES below also run unchanged against the real reference on CPU tensors, which pins their expectations:
 #   KT_MODULE=pykeops.torch KB200_TEST_DEVICE=cpu CXX=/usr/bin/g++ PYTHONPATH=/root/reference/keopscore:/root/reference/pykeops \
-#       python -m pytest tests/test_torch_api_gpu.py -m gpu        (21 passed, 4 skipped in this container)
+#       python -m pytest tests/test_torch_api_gpu.py -m gpu        (22 passed, 4 skipped in this container)
 # Only the documented deviations are switched off there: this engine has no CPU backend and refuses host tensors.
 import os
 AGAINST_REFERENCE = os.environ.get("KT_MODULE", "").startswith("pykeops")
@@ -409,3 +409,38 @@ def test_non_contiguous_inputs_and_lazytensor_inplace_out(api, cuda_device):
     ret = K.__matmul__(w, sum_scheme="block_sum", out=a)
     assert ret.data_ptr() == a.data_ptr()
     torch.testing.assert_close(a, torch.exp(-((x - y) ** 2).sum(-1)) @ w, rtol=1e-5, atol=1e-5)
+
+
+def test_lazytensor_clamp_and_broadcast_grads(api, cuda_device):
+    """pykeops/pykeops/test/test_lazytensor_clamp.py (forward + gradient through ``clamp``) and test_lazytensor_grad.py
+    (a dimension-1 j-variable broadcast against ``cos(x_i)``, first and second order gradients)."""
+    torch.manual_seed(0)
+    x = torch.randn(1000, 1, 3, requires_grad=True, device=cuda_device)
+    y = torch.randn(1, 1000, 3, device=cuda_device)
+
+    def fun(x, y, lazy):
+        if lazy:
+            x, y = api.LazyTensor(x), api.LazyTensor(y)
+        Dxy = ((x * y).clamp(-1.23, 1.54)).sum(dim=2)
+        return (-(Dxy ** 2)).exp().sum(dim=1)
+
+    out = [fun(x, y, lazy).squeeze() for lazy in (False, True)]
+    g = [torch.autograd.grad((o ** 2).sum(), [x])[0] for o in out]
+    assert torch.allclose(out[0], out[1])
+    assert torch.allclose(g[0], g[1], atol=0.01, rtol=0.001)
+
+    x = torch.rand(100, 1, 3, requires_grad=True, device=cuda_device)
+    y = torch.rand(1, 100, 1, device=cuda_device)
+    b = torch.randn(100, 1, device=cuda_device)
+
+    def fun2(x, y, b, lazy):
+        if lazy:
+            x, y = api.LazyTensor(x), api.LazyTensor(y)
+        return ((x.cos() - y).sum(dim=2) @ b).squeeze()
+
+    out = [fun2(x, y, b, lazy) for lazy in (True, False)]
+    g1 = [torch.autograd.grad((o ** 2).sum(), [x], create_graph=True)[0] for o in out]
+    g2 = [torch.autograd.grad((g ** 2).sum(), [x])[0] for g in g1]
+    assert torch.allclose(out[0], out[1], rtol=1e-4)
+    assert torch.allclose(g1[0], g1[1], rtol=1e-4)
+    assert torch.allclose(g2[0], g2[1], rtol=1e-3)
