@@ -82,3 +82,94 @@ def test_real_reference_front_end_reaches_our_binder(tmp_path):
     for rec in recs:
         assert rec["ours"] == rec["theirs"], rec
         assert rec["cpu_refused"]                            # the reference's CPU argument list is refused: no CPU path here
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# call-time contract: what each front-end hands to ``binder.genred_pytorch`` for the same user calls
+# ---------------------------------------------------------------------------------------------------------------------
+USER_CALLS = r'''
+def user_calls(torch, Genred, LazyTensor):
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.rand(*s, generator=g)
+    x, y, b = r(10, 3), r(12, 3), r(12, 2)
+    conv = Genred("Exp(-SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(2)"], reduction_op="Sum", axis=1)
+    ranges = (torch.tensor([[0, 4], [4, 10]]), torch.tensor([1, 2]), torch.tensor([[0, 5], [5, 12]]),
+              torch.tensor([[0, 5], [5, 12]]), torch.tensor([1, 2]), torch.tensor([[0, 4], [4, 10]]))
+    xb, yb, bb = r(4, 1, 7, 1, 3), r(1, 5, 1, 9, 3), r(4, 5, 1, 9, 2)
+    return [
+        ("plain", lambda: conv(x, y, b)),
+        ("out", lambda: conv(x, y, b, out=torch.empty(10, 2))),
+        ("ranges", lambda: conv(x, y, b, ranges=ranges)),
+        ("axis0", lambda: Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], reduction_op="ArgKMin", axis=0, opt_arg=2)(x, y)),
+        ("batch", lambda: ((-((LazyTensor(xb) - LazyTensor(yb)) ** 2).sum(-1)).exp() * LazyTensor(bb)).sum(3)),
+        ("batch_genred", lambda: conv(r(6, 10, 3), r(1, 12, 3), r(6, 12, 2))),
+        ("param", lambda: Genred("Exp(-p*SqDist(x,y))", ["x=Vi(3)", "y=Vj(3)", "p=Pm(1)"], axis=1)(x, y, torch.tensor([0.5]))),
+    ]
+
+def describe(device_args, ranges, nx, ny, nbatchdims, out, *args):
+    return dict(ranges=None if ranges is None else [list(t.shape) for t in ranges], nx=int(nx), ny=int(ny),
+                nbatchdims=int(nbatchdims), out=None if out is None else list(out.shape),
+                args=[list(a.shape) for a in args], contiguous=all(a.is_contiguous() for a in args))
+'''
+
+REF_CALLS = USER_CALLS + r'''
+import json, torch
+from pykeops.common import keops_io
+class Stop(Exception):
+    pass
+seen = []
+class Spy:
+    def __init__(self, *a):
+        pass
+    def import_module(self):
+        return self
+    def genred_pytorch(self, *a):
+        seen.append(describe(*a))
+        raise Stop
+keops_io.keops_binder["cpp"] = Spy
+from pykeops.torch import Genred, LazyTensor
+out = {}
+for name, f in user_calls(torch, Genred, LazyTensor):
+    try:
+        f()
+    except Stop:
+        out[name] = seen[-1]
+print("CALLS" + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pykeops")), reason="reference checkout not mounted")
+def test_both_front_ends_hand_the_same_call_to_the_binder(tmp_path, monkeypatch):
+    env = dict(os.environ, CXX="/usr/bin/g++", KEOPS_CACHE_FOLDER=os.environ.get("KEOPS_CACHE_FOLDER", "/tmp/keops_cache"),
+               PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=os.pathsep.join((REF + "/keopscore", REF + "/pykeops", ROOT)))
+    r = subprocess.run([sys.executable, "-c", REF_CALLS], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    theirs = json.loads([l for l in r.stdout.splitlines() if l.startswith("CALLS")][-1][5:])
+    assert len(theirs) == 7
+
+    # the same user calls through this package's front-end, stopped at the binder in the same way (the device checks
+    # that refuse CPU tensors are bypassed: nothing is computed)
+    import torch
+    import keops_b200.torch as kt
+    from keops_b200.binder import LoadKeOpsB200
+    from keops_b200.torch import genred as G
+    ns = {}
+    exec(USER_CALLS, ns)
+
+    class Stop(Exception):
+        pass
+    seen = []
+
+    def record(self, *a):
+        seen.append(ns["describe"](*a))
+        raise Stop
+    monkeypatch.setattr(G, "_resolve_backend", lambda backend, args: (1, 0, 1))
+    monkeypatch.setattr(G, "_set_device", lambda req, args: (0, torch.device("cpu")))
+    monkeypatch.setattr(LoadKeOpsB200, "genred_pytorch", record)
+    ours = {}
+    for name, f in ns["user_calls"](torch, kt.Genred, kt.LazyTensor):
+        with pytest.raises(Stop):
+            f()
+        ours[name] = seen[-1]
+    for name in theirs:
+        assert ours[name] == theirs[name], (name, ours[name], theirs[name])
