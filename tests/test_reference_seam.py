@@ -15,6 +15,19 @@ import pytest
 REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+
+def _run_reference(script, tmp_path, tag, timeout):
+    """Run ``script`` with the real reference importable; returns the JSON payload printed after ``tag``.  An environment
+    in which the reference itself cannot run (no compiler, read-only cache ...) skips; a failed assertion fails."""
+    env = dict(os.environ, CXX="/usr/bin/g++", KEOPS_CACHE_FOLDER=os.environ.get("KEOPS_CACHE_FOLDER", "/tmp/keops_cache"),
+               PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=os.pathsep.join((REF + "/keopscore", REF + "/pykeops", ROOT)))
+    r = subprocess.run([sys.executable, "-c", script], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        if "AssertionError" in r.stderr or "keops_b200" in r.stderr.split("Traceback")[-1]:
+            pytest.fail(r.stdout[-2000:] + r.stderr[-2000:])
+        pytest.skip("the reference could not run in this environment: " + (r.stderr.strip().splitlines() or ["?"])[-1][:200])
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith(tag)][-1][len(tag):])
+
 SCRIPT = r'''
 import json, torch
 import pykeops
@@ -70,11 +83,7 @@ print("SEAM" + json.dumps(out))
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pykeops")), reason="reference checkout not mounted")
 def test_real_reference_front_end_reaches_our_binder(tmp_path):
-    env = dict(os.environ, CXX="/usr/bin/g++", KEOPS_CACHE_FOLDER=os.environ.get("KEOPS_CACHE_FOLDER", "/tmp/keops_cache"),
-               PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=os.pathsep.join((REF + "/keopscore", REF + "/pykeops", ROOT)))
-    r = subprocess.run([sys.executable, "-c", SCRIPT], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    recs = json.loads([l for l in r.stdout.splitlines() if l.startswith("SEAM")][-1][4:])
+    recs = _run_reference(SCRIPT, tmp_path, "SEAM", 900)
     assert len(recs) == 6
     kinds = [rec["formula"].split("_Reduction")[0] for rec in recs]
     assert kinds == ["Sum", "ArgKMin", "Max_SumShiftExp", "Min_ArgMin", "Sum", "Sum"]
@@ -140,11 +149,7 @@ print("CALLS" + json.dumps(out))
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pykeops")), reason="reference checkout not mounted")
 def test_both_front_ends_hand_the_same_call_to_the_binder(tmp_path, monkeypatch):
-    env = dict(os.environ, CXX="/usr/bin/g++", KEOPS_CACHE_FOLDER=os.environ.get("KEOPS_CACHE_FOLDER", "/tmp/keops_cache"),
-               PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=os.pathsep.join((REF + "/keopscore", REF + "/pykeops", ROOT)))
-    r = subprocess.run([sys.executable, "-c", REF_CALLS], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    theirs = json.loads([l for l in r.stdout.splitlines() if l.startswith("CALLS")][-1][5:])
+    theirs = _run_reference(REF_CALLS, tmp_path, "CALLS", 900)
     assert len(theirs) == 7
 
     # the same user calls through this package's front-end, stopped at the binder in the same way (the device checks
@@ -173,3 +178,80 @@ def test_both_front_ends_hand_the_same_call_to_the_binder(tmp_path, monkeypatch)
         ours[name] = seen[-1]
     for name in theirs:
         assert ours[name] == theirs[name], (name, ours[name], theirs[name])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# autograd glue: which reductions each front-end asks the binder for during backward
+# ---------------------------------------------------------------------------------------------------------------------
+GRAD_CALLS = r'''
+def grad_calls(torch, Genred, LazyTensor):
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.rand(*s, generator=g).requires_grad_(True)
+    x, y, b, p = r(10, 3), r(12, 3), r(12, 2), torch.tensor([0.5], requires_grad=True)
+    def conv():
+        out = Genred("Exp(-p*SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(2)", "p=Pm(1)"], reduction_op="Sum", axis=1)(x, y, b, p)
+        torch.autograd.grad(out.sum(), [x, y, b, p])
+    def lse():
+        out = (-((LazyTensor(x[:, None]) - LazyTensor(y[None])) ** 2).sum(-1)).logsumexp(dim=1, weight=LazyTensor(b[None]))
+        torch.autograd.grad(out.sum(), [x, b])
+    def second_order():
+        out = ((-((LazyTensor(x[:, None]) - LazyTensor(y[None])) ** 2).sum(-1)).exp() * LazyTensor(b[None])).sum(dim=1)
+        gx, = torch.autograd.grad((out ** 2).sum(), [x], create_graph=True)
+        torch.autograd.grad((gx ** 2).sum(), [b])
+    return [("conv", conv), ("lse", lse), ("second_order", second_order)]
+'''
+
+REF_GRADS = GRAD_CALLS + r'''
+import json, torch
+from pykeops.common import keops_io
+real_cpp = keops_io.keops_binder["cpp"]
+seen = []
+def spy(*a):
+    seen.append([a[5], list(a[6]), a[7], a[8], a[10]["sum_scheme"]])
+    return real_cpp(*a)
+keops_io.keops_binder["cpp"] = spy
+from pykeops.torch import Genred, LazyTensor
+out = {}
+for name, f in grad_calls(torch, Genred, LazyTensor):
+    start = len(seen)
+    f()
+    out[name] = seen[start:]
+print("GRADS" + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pykeops")), reason="reference checkout not mounted")
+def test_backward_asks_the_binder_for_the_same_reductions(tmp_path, monkeypatch):
+    theirs = _run_reference(REF_GRADS, tmp_path, "GRADS", 1500)
+
+    # ours: the binder is replaced by a recorder whose "kernel" returns zeros of the right shape, so that autograd runs
+    import torch
+    import keops_b200.torch as kt
+    from keops_b200.binder import LoadKeOpsB200
+    from keops_b200.torch import genred as G
+    ns = {}
+    exec(GRAD_CALLS, ns)
+    seen = []
+
+    def recording_binder(*a):
+        seen.append([a[5], list(a[6]), a[7], a[8], a[10]["sum_scheme"]])
+        return LoadKeOpsB200(*a)
+
+    def fake_kernel(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
+        return torch.zeros(nx if self.tagIJ == 0 else ny, self.dimout, dtype=args[0].dtype)
+    monkeypatch.setattr(G, "LoadKeOpsB200", recording_binder)
+    monkeypatch.setattr(G, "_resolve_backend", lambda backend, args: (1, 0, 1))
+    monkeypatch.setattr(G, "_set_device", lambda req, args: (0, torch.device("cpu")))
+    monkeypatch.setattr(LoadKeOpsB200, "genred_pytorch", fake_kernel)
+    from keops_b200.formulas.parser import parse_reduction
+    for name, f in ns["grad_calls"](torch, kt.Genred, kt.LazyTensor):
+        start = len(seen)
+        f()
+        mine = seen[start:]
+        # setup_context looks the (memoised) binder up a second time: drop immediate repeats
+        mine = [c for k, c in enumerate(mine) if k == 0 or c != mine[k - 1]]
+        ref = [c for k, c in enumerate(theirs[name]) if k == 0 or c != theirs[name][k - 1]]
+        assert len(mine) == len(ref), (name, [c[0] for c in mine], [c[0] for c in ref])
+        for a, b in zip(mine, ref):
+            assert a[1:] == b[1:], (name, a, b)                              # aliases, nargs, dtype, sum scheme
+            assert parse_reduction(a[0], a[1]) is parse_reduction(b[0], b[1]) or a[0] == b[0], (name, a[0], b[0])
