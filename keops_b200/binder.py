@@ -20,13 +20,12 @@ from __future__ import annotations
 import os
 import threading
 import types
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
 from .formulas.parser import parse_reduction, parse_alias
 from .formulas.reductions import Reduction
-from .formulas.ir import FormulaError
 from .codegen.emit import generate, KernelSource
 from .codegen import conv_tc, knn_tc
 from .runtime import plan, capi

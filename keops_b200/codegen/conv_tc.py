@@ -25,7 +25,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
-from typing import Callable, Dict, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 from ..formulas.ir import Node
 from ..formulas.reductions import Reduction

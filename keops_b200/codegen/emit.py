@@ -20,7 +20,7 @@ import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
-from ..formulas.ir import Node, FormulaError
+from ..formulas.ir import FormulaError
 from ..formulas.reductions import Reduction
 from .lower import Lowerer
 from .scalar import Graph, SNode, SV, C, P, I, J, IJ, topo_order

@@ -16,7 +16,6 @@ order of a subtraction, in a hoisted (non per-pair) operand, or in the final acc
 from __future__ import annotations
 
 import math
-from fractions import Fraction
 from typing import Dict, List, Optional, Sequence, Tuple
 
 from ..formulas.ir import FormulaError

@@ -14,7 +14,7 @@ autodiff output small (zero / one propagation) are applied at construction time.
 from __future__ import annotations
 
 from fractions import Fraction
-from typing import Dict, Iterable, List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 
 class FormulaError(ValueError):

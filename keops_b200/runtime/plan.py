@@ -14,9 +14,9 @@ import math
 import os
 import threading
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
-from ..codegen.emit import KernelConfig, KernelSource, generate, GENERATOR_VERSION
+from ..codegen.emit import KernelConfig, KernelSource, GENERATOR_VERSION
 from ..formulas.reductions import Reduction
 from . import capi
 

@@ -19,7 +19,6 @@ from __future__ import annotations
 import copy
 import math
 import re
-from typing import Optional
 
 import torch
 
