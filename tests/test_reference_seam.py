@@ -255,3 +255,64 @@ def test_backward_asks_the_binder_for_the_same_reductions(tmp_path, monkeypatch)
         for a, b in zip(mine, ref):
             assert a[1:] == b[1:], (name, a, b)                              # aliases, nargs, dtype, sum scheme
             assert parse_reduction(a[0], a[1]) is parse_reduction(b[0], b[1]) or a[0] == b[0], (name, a[0], b[0])
+
+
+KSOLVE_CALLS = r'''
+def ksolve_call(torch, KernelSolve):
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(15, 3, generator=g).requires_grad_(True)
+    b = torch.rand(15, 2, generator=g).requires_grad_(True)
+    p = torch.tensor([0.5], requires_grad=True)
+    Kinv = KernelSolve("Exp(-p*SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(2)", "p=Pm(1)"], "b", axis=1)
+    c = Kinv(x, x, b, p, alpha=0.1)
+    torch.autograd.grad(c.sum(), [x, b, p])
+'''
+
+REF_KSOLVE = KSOLVE_CALLS + r'''
+import json, torch
+from pykeops.common import keops_io
+real_cpp = keops_io.keops_binder["cpp"]
+seen = []
+def spy(*a):
+    seen.append([a[5], list(a[6]), a[7], a[8], a[10]["sum_scheme"]])
+    return real_cpp(*a)
+keops_io.keops_binder["cpp"] = spy
+from pykeops.torch import KernelSolve
+ksolve_call(torch, KernelSolve)
+print("KSOLVE" + json.dumps(seen))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pykeops")), reason="reference checkout not mounted")
+def test_kernel_solve_backward_asks_for_the_same_reductions(tmp_path, monkeypatch):
+    """``KernelSolveAutograd`` (pykeops/pykeops/torch/operations.py:29-180): forward solve, a second solve for the
+    upstream gradient, then one ``Grad_WithSavedForward`` reduction per differentiated variable."""
+    theirs = _run_reference(REF_KSOLVE, tmp_path, "KSOLVE", 1500)
+    import torch
+    import keops_b200.torch as kt
+    from keops_b200.binder import LoadKeOpsB200
+    from keops_b200.torch import genred as G, kernel_solve as KS
+    ns = {}
+    exec(KSOLVE_CALLS, ns)
+    seen = []
+
+    def recording_binder(*a):
+        seen.append([a[5], list(a[6]), a[7], a[8], a[10]["sum_scheme"]])
+        return LoadKeOpsB200(*a)
+
+    def fake_kernel(self, device_args, ranges, nx, ny, nbatchdims, out, *args):   # K = 0: the solver sees alpha * Id
+        return torch.zeros(nx if self.tagIJ == 0 else ny, self.dimout, dtype=args[0].dtype)
+    for mod in (G, KS):
+        monkeypatch.setattr(mod, "LoadKeOpsB200", recording_binder)
+        monkeypatch.setattr(mod, "_resolve_backend", lambda backend, args: (1, 0, 1))
+        monkeypatch.setattr(mod, "_set_device", lambda req, args: (0, torch.device("cpu")))
+    monkeypatch.setattr(LoadKeOpsB200, "genred_pytorch", fake_kernel)
+    ns["ksolve_call"](torch, kt.KernelSolve)
+    from keops_b200.formulas.parser import parse_reduction
+    dedup = lambda calls: [c for k, c in enumerate(calls) if k == 0 or c != calls[k - 1]]
+    mine, ref = dedup(seen), dedup(theirs)
+    key = lambda c: (c[0], tuple(c[1]))
+    assert sorted(map(key, mine)) == sorted(map(key, ref)) or len(mine) == len(ref), ([c[0] for c in mine], [c[0] for c in ref])
+    for a, b in zip(sorted(mine, key=key), sorted(ref, key=key)):
+        assert a[1:] == b[1:], (a, b)
+        assert a[0] == b[0] or parse_reduction(a[0], a[1]) is parse_reduction(b[0], b[1]), (a[0], b[0])
