@@ -19,7 +19,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run_reference(script, tmp_path, tag, timeout):
     """Run ``script`` with the real reference importable; returns the JSON payload printed after ``tag``.  An environment
     in which the reference itself cannot run (no compiler, read-only cache ...) skips; a failed assertion fails."""
-    env = dict(os.environ, CXX="/usr/bin/g++", KEOPS_CACHE_FOLDER=os.environ.get("KEOPS_CACHE_FOLDER", "/tmp/keops_cache"),
+    cache = os.environ.get("KEOPS_CACHE_FOLDER", os.path.join(ROOT, "oracle", "_ref", "keops_cache"))   # git-ignored, persistent
+    os.makedirs(cache, exist_ok=True)
+    env = dict(os.environ, CXX="/usr/bin/g++", KEOPS_CACHE_FOLDER=cache,
                PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=os.pathsep.join((REF + "/keopscore", REF + "/pykeops", ROOT)))
     r = subprocess.run([sys.executable, "-c", script], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
@@ -316,3 +318,81 @@ def test_kernel_solve_backward_asks_for_the_same_reductions(tmp_path, monkeypatc
     for a, b in zip(sorted(mine, key=key), sorted(ref, key=key)):
         assert a[1:] == b[1:], (a, b)
         assert a[0] == b[0] or parse_reduction(a[0], a[1]) is parse_reduction(b[0], b[1]), (a[0], b[0])
+
+
+FUNC_CALLS = r'''
+def func_calls(torch, Genred):
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.rand(*s, generator=g)
+    x, y, b = r(10, 3), r(12, 3), r(12, 2)
+    conv = Genred("Exp(-SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(2)"], reduction_op="Sum", axis=1)
+    lse = Genred("-SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], reduction_op="LogSumExp", axis=1)
+    def jvp():
+        torch.func.jvp(lambda x_, b_: conv(x_, y, b_), (x, b), (r(10, 3), r(12, 2)))
+    def jvp_lse():
+        torch.func.jvp(lambda x_: lse(x_, y), (x,), (r(10, 3),))
+    def vmap():
+        torch.func.vmap(lambda x_, b_: conv(x_, y, b_), in_dims=(0, 0))(r(4, 10, 3), r(4, 12, 2))
+    def vmap_grad():
+        torch.func.vmap(torch.func.grad(lambda x_: conv(x_, y, b).sum()))(r(4, 10, 3))
+    return [("jvp", jvp), ("jvp_lse", jvp_lse), ("vmap", vmap), ("vmap_grad", vmap_grad)]
+'''
+
+REF_FUNC = FUNC_CALLS + r'''
+import json, torch
+from pykeops.common import keops_io
+real_cpp = keops_io.keops_binder["cpp"]
+seen = []
+class Spy:
+    def __init__(self, *a):
+        self.a, self.real = a, real_cpp(*a)
+    def import_module(self):
+        self.real = self.real.import_module()
+        return self
+    def __getattr__(self, k):
+        return getattr(self.real, k)
+    def genred_pytorch(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
+        seen.append([self.a[5], list(self.a[6]), int(nx), int(ny), int(nbatchdims), [list(t.shape) for t in args]])
+        return self.real.genred_pytorch(device_args, ranges, nx, ny, nbatchdims, out, *args)
+keops_io.keops_binder["cpp"] = Spy
+from pykeops.torch import Genred
+out = {}
+for name, f in func_calls(torch, Genred):
+    start = len(seen)
+    f()
+    out[name] = seen[start:]
+print("FUNC" + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pykeops")), reason="reference checkout not mounted")
+def test_torch_func_transforms_launch_the_same_reductions(tmp_path, monkeypatch):
+    """``torch.func.jvp / vmap / grad`` through ``GenredAutograd`` (pykeops/pykeops/torch/generic/generic_red.py:262-380):
+    every kernel launch -- reduction string, aliases, nx, ny, number of batch dimensions, argument shapes -- is the one the
+    real reference makes for the same transform."""
+    theirs = _run_reference(REF_FUNC, tmp_path, "FUNC", 1500)
+    import torch
+    import keops_b200.torch as kt
+    from keops_b200.binder import LoadKeOpsB200
+    from keops_b200.torch import genred as G
+    from keops_b200.formulas.parser import parse_reduction
+    ns = {}
+    exec(FUNC_CALLS, ns)
+    seen = []
+
+    def fake_kernel(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
+        p = self.params
+        seen.append([p.red_formula_string, list(p.aliases_old), int(nx), int(ny), int(nbatchdims), [list(t.shape) for t in args]])
+        batch = torch.broadcast_shapes(*[tuple(a.shape[:nbatchdims]) for a in args]) if nbatchdims else ()
+        return torch.zeros(*batch, nx if self.tagIJ == 0 else ny, self.dimout, dtype=args[0].dtype)
+    monkeypatch.setattr(G, "_resolve_backend", lambda backend, args: (1, 0, 1))
+    monkeypatch.setattr(G, "_set_device", lambda req, args: (0, torch.device("cpu")))
+    monkeypatch.setattr(LoadKeOpsB200, "genred_pytorch", fake_kernel)
+    for name, f in ns["func_calls"](torch, kt.Genred):
+        start = len(seen)
+        f()
+        mine, ref = seen[start:], theirs[name]
+        assert len(mine) == len(ref), (name, [c[0] for c in mine], [c[0] for c in ref])
+        for a, b in zip(mine, ref):
+            assert a[2:] == b[2:], (name, a, b)                              # nx, ny, nbatchdims, argument shapes
+            assert a[0] == b[0] or parse_reduction(a[0], a[1]) is parse_reduction(b[0], b[1]), (name, a[0], b[0])
