@@ -72,3 +72,23 @@ def test_binder_refuses_cpu_backend():
     flags = dict(dtype_acc="auto", sum_scheme="auto", use_fast_math=1, enable_chunks=1, multVar_highdim=0)
     with pytest.raises(ValueError):
         LoadKeOpsB200(0, 0, 0, False, -1, "Sum_Reduction(Var(0,1,0)*Var(1,1,1),0)", [], 2, "float32", "torch", flags)
+
+
+def test_double_accumulator_and_kahan_kernels_compile():
+    """``dtype_acc="float64"`` (fp32 data, fp64 accumulators: pykeops/pykeops/common/parse_type.py:195-207,
+    keopscore/keopscore/formulas/reductions/Sum_Reduction.py:10-50) and ``sum_scheme="kahan_scheme"``
+    (keopscore/keopscore/formulas/reductions/sum_schemes.py:74-86) generate valid sm_100a kernels with fp64 adds
+    (respectively the compensation subtractions) in the reduction."""
+    from keops_b200.formulas.parser import parse_reduction
+    from keops_b200.codegen.emit import generate
+    from keops_b200.runtime import capi, plan
+    red = parse_reduction("Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,2,1)),0)")
+    cfg = plan.default_config(red, "float32")
+    plain = generate(red, "float32", 3, cfg)
+    acc64 = generate(red, "float32", 3, cfg, dtype_acc="float64")
+    kahan = generate(red, "float32", 3, cfg, sum_scheme="kahan_scheme")
+    assert "double" in acc64.source and acc64.source != plain.source and kahan.source != plain.source
+    for ks in (acc64, kahan):
+        assert capi.compile_to_cubin(ks.source, plan.nvrtc_options(True))[:4] == b"\x7fELF"
+    with pytest.raises(ValueError):
+        generate(red, "float32", 3, cfg, sum_scheme="nope")
