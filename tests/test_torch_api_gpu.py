@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 # The test BODIES below also run unchanged against the real reference on CPU tensors, which pins their expectations:
 #   KT_MODULE=pykeops.torch KB200_TEST_DEVICE=cpu CXX=/usr/bin/g++ PYTHONPATH=/root/reference/keopscore:/root/reference/pykeops \
-#       python -m pytest tests/test_torch_api_gpu.py -m gpu        (22 passed, 4 skipped in this container)
+#       python -m pytest tests/test_torch_api_gpu.py -m gpu        (23 passed, 4 skipped in this container)
 # Only the documented deviations are switched off there: this engine has no CPU backend and refuses host tensors.
 import os
 AGAINST_REFERENCE = os.environ.get("KT_MODULE", "").startswith("pykeops")
@@ -444,3 +444,27 @@ def test_lazytensor_clamp_and_broadcast_grads(api, cuda_device):
     assert torch.allclose(out[0], out[1], rtol=1e-4)
     assert torch.allclose(g1[0], g1[1], rtol=1e-4)
     assert torch.allclose(g2[0], g2[1], rtol=1e-3)
+
+
+def test_accumulator_options(api, cuda_device):
+    """``dtype_acc="float64"`` / ``use_double_acc=True`` (fp32 data, fp64 accumulators) and ``sum_scheme="kahan_scheme"``
+    (pykeops/pykeops/torch/generic/generic_red.py:437-520, test_torch.py:417-445): all agree with a float64 dense sum,
+    the wide accumulators more closely than plain fp32 block sums."""
+    torch.manual_seed(5)
+    M, N = 200, 20000
+    x, y = torch.rand(M, 3, device=cuda_device), torch.rand(N, 3, device=cuda_device)
+    b = torch.rand(N, 1, device=cuda_device) + 1.0
+    ref = (torch.exp(-((x.double()[:, None] - y.double()[None]) ** 2).sum(-1)) @ b.double())
+    al = ["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"]
+    err = {}
+    for name, kw in (("block", {}), ("direct", dict(sum_scheme="direct_sum")), ("kahan", dict(sum_scheme="kahan_scheme")),
+                     ("acc64", dict(dtype_acc="float64")), ("double_acc", dict(use_double_acc=True))):
+        out = api.Genred("Exp(-SqDist(x,y))*b", al, reduction_op="Sum", axis=1, **kw)(x, y, b)
+        assert out.dtype == torch.float32 and out.shape == (M, 1)
+        err[name] = ((out.double() - ref).abs() / ref.abs()).max().item()
+    assert max(err.values()) < 1e-5, err
+    assert err["acc64"] < 1e-6 and err["double_acc"] < 1e-6 and err["kahan"] < 1e-6, err
+    with pytest.raises(ValueError):
+        api.Genred("Exp(-SqDist(x,y))*b", al, reduction_op="Sum", axis=1, dtype_acc="float64", use_double_acc=True)
+    with pytest.raises(ValueError):
+        api.Genred("SqDist(x,y)", al[:2], reduction_op="Min", axis=1, dtype_acc="float64")
