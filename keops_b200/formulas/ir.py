@@ -309,20 +309,18 @@ def _unary(op: str):
 
 
 def Square(a: Node) -> Node:
+    # constants are NOT folded here: the reference folds rational constants only in Add / Subtract / Mult / Minus /
+    # Divide-by-constant (``maths/Square.py:27-31``, ``maths/Inv.py``), and a folded ``RatCst`` is emitted float-rounded in
+    # every dtype (``variables/RatCst.py:22-24``) -- folding more than the reference does would change fp64 results
+    # (``2 / (1 + Square(2))`` is an exact 0.4 there).  The scalar DAG folds the value itself, without the rounding.
     if a.is_zero:
         return a
-    c = a.const_value()
-    if c is not None:
-        return _const(c * c)
     return Node("Square", (a,), (), a.dim)
 
 
 def Inv(a: Node) -> Node:
-    c = a.const_value()
-    if c is not None:
-        if c == 0:
-            raise FormulaError("division by zero")
-        return _const(1 / c)
+    if a.is_zero:
+        raise FormulaError("division by zero")
     return Node("Inv", (a,), (), a.dim)
 
 

@@ -175,11 +175,24 @@ class _Add(_Elementwise):
 
 
 
+def _rat(x):
+    """exact value of an integer / rational constant node, else None"""
+    return Fraction(x.val) if isinstance(x, Cst) and isinstance(x.val, (int, Fraction)) else None
+
+
+def _mkcst(fr):
+    """the reference's IntCst / RatCst constructors: 0 -> Zero, q == 1 -> IntCst (variables/RatCst.py:31-39, IntCst.py:30-34)"""
+    fr = Fraction(fr)
+    return Zero(1) if fr == 0 else Cst(int(fr) if fr.denominator == 1 else fr)
+
+
 def Add(a, b):
     if a.iszero():
         return Broadcast(b, _bd(a, b))
     if b.iszero():
         return Broadcast(a, _bd(a, b))
+    if _rat(a) is not None and _rat(b) is not None:                              # maths/Add.py:64-77: m + n, m + p/q, ...
+        return _mkcst(_rat(a) + _rat(b))
     return _Add(a, b)
 
 class _Subtract(_Elementwise):
@@ -196,6 +209,8 @@ def Subtract(a, b):
         return Broadcast(a, _bd(a, b))
     if a.iszero():
         return Minus(Broadcast(b, _bd(a, b)))
+    if _rat(a) is not None and _rat(b) is not None:                              # maths/Subtract.py:62-75
+        return _mkcst(_rat(a) - _rat(b))
     return _Subtract(a, b)
 
 class _Minus(_Elementwise):
@@ -207,7 +222,11 @@ class _Minus(_Elementwise):
 
 
 def Minus(a):
-    return a if a.iszero() else _Minus(a)
+    if a.iszero():
+        return a
+    if _rat(a) is not None:                                                      # maths/Minus.py:48-54: -(n), -(p/q)
+        return _mkcst(-_rat(a))
+    return _Minus(a)
 
 class _Mult(_Elementwise):
 
@@ -221,6 +240,17 @@ class _Mult(_Elementwise):
 def Mult(a, b):
     if _z(a, b):
         return Zero(_bd(a, b))
+    if _rat(a) is not None and _rat(b) is not None:                              # maths/Mult.py:60-78: mn, m(p/q), (p/q)(m/n)
+        return _mkcst(_rat(a) * _rat(b))
+    if isinstance(b, Cst) and isinstance(b.val, int):                            # f*n -> n*f, integers only (maths/Mult.py:73-75)
+        return Mult(b, a)
+    if isinstance(b, _Mult) and _rat(b.children[0]) is not None:                 # maths/Mult.py:79-93
+        c, g = b.children
+        if _rat(a) is not None and (isinstance(a.val, int) or isinstance(c.val, Fraction)):
+            return Mult(Mult(a, c), g)                                           # m*(n*g) -> (mn)*g,  m*(r*g) -> (m*r)*g
+        return Mult(c, Mult(a, g))                                               # f*(n*g) -> n*(f*g)
+    if isinstance(a, _Mult) and _rat(a.children[0]) is not None and not isinstance(b, Exp):
+        return Mult(a.children[0], Mult(a.children[1], b))                       # (n*f)*g -> n*(f*g)  (maths/Mult.py:94-99)
     return _Mult(a, b)
 
 class _Divide(_Elementwise):

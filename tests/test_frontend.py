@@ -211,3 +211,26 @@ def test_conjugate_gradient_matches_reference(name):
     assert torch.equal(a, a_ref)
     capped = conjugate_gradient(linop, b, eps=0.0, max_iter=3) if name != "zero_rhs" else None
     assert capped is None or conjugate_gradient.last_iterations == 3
+
+
+def _constant_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "constants.json")) as f:
+        rec = json.load(f)
+    return rec["x"], [c for c in rec["cases"] if "out" in c]
+
+
+@pytest.mark.parametrize("case", _constant_cases()[1], ids=lambda c: c["formula"][:40])
+def test_constant_folding_matches_reference(case):
+    """Integer / rational constants in float64 against the real reference (tests/golden/make_constants.py): the reference
+    folds rationals in Add / Subtract / Mult / Minus / Divide-by-constant only and emits a folded ``RatCst`` float-rounded
+    (keopscore/keopscore/formulas/variables/RatCst.py:22-24), so folding in other places -- or not folding where it does --
+    shows in the 8th digit.  Both this package's lowering and the oracle must reproduce the reference to the last bits."""
+    from oracle import keops_oracle as ko
+    x = np.array(_constant_cases()[0]).reshape(-1, 1)
+    y = np.zeros((2, 1))
+    ref = np.array([float.fromhex(v) for v in case["out"]]).reshape(-1, 1)
+    f = "Sum_Reduction(%s+Var(1,1,1),0)" % case["formula"]
+    for who, got in (("lowering", dag_eval.evaluate(f, [], [x, y], "float64")), ("oracle", ko.genred(f, [], [x, y], "float64"))):
+        assert np.abs(got - ref).max() <= 4e-16 * np.abs(ref).max(), (who, case["formula"], got.ravel().tolist(), ref.ravel().tolist())
