@@ -667,7 +667,10 @@ class _ReductionCode:
         self.scheme = sum_scheme if self.kind in ("Sum", "LSE") else "direct_sum"
         if self.scheme not in ("block_sum", "direct_sum", "kahan_scheme"):
             raise ValueError('invalid value for option sum_scheme : should be one of "auto", "direct_sum", "block_sum" or "kahan_scheme".')
-        self.acc64 = (not f64) and dtype_acc in ("float64", "double") and self.kind == "Sum"
+        # fp32 data with fp64 accumulators (reference: MapReduce.py:74 declares ``acc`` in dtypeacc for every reduction;
+        # only the sum-like ones have an accumulator whose precision matters)
+        self.acc64 = (not f64) and dtype_acc in ("float64", "double") and self.kind in ("Sum", "LSE")
+        self.kahan = self.scheme == "kahan_scheme"
         self.dimF = red.dimF
         k = self.kind
         if k == "Sum":
@@ -713,14 +716,17 @@ class _ReductionCode:
             else:
                 W("V acc[%d];" % n)
                 W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) acc[k_] = kb_bcast_v((real)0);" % n)
-            if self.scheme == "kahan_scheme":
-                W("V comp[%d];" % n)
-                W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) comp[k_] = kb_bcast_v((real)0);" % n)
+            self._declare_comp(W, n)
         elif k == "LSE":
             n = len(self.acc_terms)
             W("V mx = kb_bcast_v(-KB_INF);")
-            W("V acc[%d];" % n)
-            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) acc[k_] = kb_bcast_v((real)0);" % n)
+            if self.acc64:
+                W("double accd[%d][KB_R];" % n)
+                W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) accd[k_][q] = 0.0;" % n)
+            else:
+                W("V acc[%d];" % n)
+                W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) acc[k_] = kb_bcast_v((real)0);" % n)
+            self._declare_comp(W, n)
         elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
             init = "-KB_INF" if self.is_max else "KB_INF"
             W("V best[%d]; int bidx[%d][KB_R];" % (d, d))
@@ -741,6 +747,26 @@ class _ReductionCode:
                 W("  KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++)" % d)
                 W("    if (row0 + (long long)q * KB_T < nrow) thr[k_].l[q] = kb_next_up(__ldcg(shp + q * (KB_T * %d) + k_)); }" % d)
 
+    def _declare_comp(self, W, n):
+        """Kahan compensation terms, held in the accumulator's precision (Sum_Reduction.py:31-40)."""
+        if not self.kahan:
+            return
+        if self.acc64:
+            W("double compd[%d][KB_R];" % n)
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) compd[k_][q] = 0.0;" % n)
+        else:
+            W("V comp[%d];" % n)
+            W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) comp[k_] = kb_bcast_v((real)0);" % n)
+
+    def _kahan_add(self, W, i, val):
+        """acc[i] (+)= val with compensation; ``val`` is a V expression."""
+        if self.acc64:
+            W("{ const V v_ = %s; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) { const double a_ = (double)v_.l[q] - compd[%d][q]; "
+              "const double b_ = accd[%d][q] + a_; compd[%d][q] = (b_ - accd[%d][q]) - a_; accd[%d][q] = b_; } }" % (val, i, i, i, i, i))
+        else:
+            W("{ const V a_ = kb_sub_v(%s, comp[%d]); const V b_ = kb_add_v(acc[%d], a_); comp[%d] = kb_sub_v(kb_sub_v(b_, acc[%d]), a_); acc[%d] = b_; }"
+              % (val, i, i, i, i, i))
+
     def tile_begin(self, W):
         if self.kind in ("Sum", "LSE") and self.scheme == "block_sum":
             n = len(self.acc_terms)
@@ -758,8 +784,7 @@ class _ReductionCode:
                     val = self._term_value(term)
                     if val is None:
                         continue
-                    W("{ const V a_ = kb_sub_v(%s, comp[%d]); const V b_ = kb_add_v(acc[%d], a_); comp[%d] = kb_sub_v(kb_sub_v(b_, acc[%d]), a_); acc[%d] = b_; }"
-                      % (val, i, i, i, i, i))
+                    self._kahan_add(W, i, val)
                 return
             if self.acc64 and self.scheme != "block_sum":
                 for i, term in enumerate(self.acc_terms):
@@ -783,24 +808,39 @@ class _ReductionCode:
             W("{ bool any_ = false; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (f_.l[q] > mx.l[q]);")
             W("  if (any_) { KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) if (f_.l[q] > mx.l[q]) {")
             W("      const real sc_ = kb_exp(mx.l[q] - f_.l[q]); mx.l[q] = f_.l[q];")
-            W("      KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { acc[k_].l[q] *= sc_;%s }" % (n, " tmp[k_].l[q] *= sc_;" if a == "tmp" else ""))
+            resc = "accd[k_][q] *= (double)sc_;" if self.acc64 else "acc[k_].l[q] *= sc_;"
+            if a == "tmp":
+                resc += " tmp[k_].l[q] *= sc_;"
+            if self.kahan:
+                resc += " compd[k_][q] *= (double)sc_;" if self.acc64 else " comp[k_].l[q] *= sc_;"
+            W("      KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { %s }" % (n, resc))
             W("  } } }")
             if self.fast:
                 W("const V e_ = kb_ex2_v(kb_mul_v(kb_sub_v(f_, mx), %s));" % _lit(1.4426950408889634, self.f64))
             else:
                 W("const V e_ = kb_exp_v(kb_sub_v(f_, mx));")
+            direct64 = self.acc64 and a == "acc"          # direct_sum into fp64 accumulators: per-lane adds
             for i, term in enumerate(self.acc_terms):
                 mode, nodes, _ = term
                 if mode == "zero":
                     continue
                 if mode == "fma":
-                    W("%s[%d] = kb_fma_v(kb_mul_v(%s, %s), e_, %s[%d]);" % (a, i, self.pr.ref(nodes[0]), self.pr.ref(nodes[1]), a, i))
+                    val = "kb_mul_v(kb_mul_v(%s, %s), e_)" % (self.pr.ref(nodes[0]), self.pr.ref(nodes[1]))
+                    upd = "kb_fma_v(kb_mul_v(%s, %s), e_, %s[%d])" % (self.pr.ref(nodes[0]), self.pr.ref(nodes[1]), a, i)
                 else:
                     nd = nodes[0]
                     if nd.op == "const" and nd.val == 1.0:
-                        W("%s[%d] = kb_add_v(%s[%d], e_);" % (a, i, a, i))
+                        val = "e_"
+                        upd = "kb_add_v(%s[%d], e_)" % (a, i)
                     else:
-                        W("%s[%d] = kb_fma_v(%s, e_, %s[%d]);" % (a, i, self.pr.ref(nd), a, i))
+                        val = "kb_mul_v(%s, e_)" % self.pr.ref(nd)
+                        upd = "kb_fma_v(%s, e_, %s[%d])" % (self.pr.ref(nd), a, i)
+                if self.kahan:
+                    self._kahan_add(W, i, val)
+                elif direct64:
+                    W("{ const V v_ = %s; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) accd[%d][q] += (double)v_.l[q]; }" % (val, i))
+                else:
+                    W("%s[%d] = %s;" % (a, i, upd))
         elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
             cmp = ">" if self.is_max else "<"
             for i, nd in enumerate(self.values):
@@ -905,7 +945,7 @@ class _ReductionCode:
         elif k == "LSE":
             W("po[0] = mx.l[q];")
             for i, s in enumerate(self._signs()):
-                W("po[%d] = %sacc[%d].l[q];" % (1 + i, s, i))
+                W("po[%d] = %s%s;" % (1 + i, s, "(real)accd[%d][q]" % i if self.acc64 else "acc[%d].l[q]" % i))
         elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
             W("if (gridDim.y == 1) {")
             W.indent()

@@ -205,7 +205,10 @@ def _rule(f: Node, v: Node, g: Node, memo) -> Node:
         return _grad(alt, v, g, memo)
     if op == "Mod":
         x, n, d = f.args
-        return G(x, g)
+        # the reference differentiates the alternative form x - n*Floor((x-d)/n) (``maths/Mod.py:14-20``), which also
+        # carries the derivative with respect to the modulus n: -Floor((x-d)/n) * g
+        alt = x - n * ir.Floor((x - d) / n)
+        return _grad(alt, v, g, memo)
 
     if op == "Sum":
         (a,) = f.args

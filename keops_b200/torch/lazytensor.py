@@ -516,8 +516,9 @@ class LazyTensor:
         if other is None:
             r = self._copy_meta()
         else:
-            r = self._join(self._wrap(other))
-            r.formula2 = self._wrap(other).formula
+            o = self._wrap(other)        # wrap ONCE: a fresh wrap of a float / array creates a new variable identity
+            r = self._join(o)
+            r.formula2 = o.formula
         r.formula = self.formula
         r.ndim = self.ndim
         r.reduction_op = reduction_op

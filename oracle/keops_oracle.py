@@ -431,9 +431,9 @@ class Atan2(_Elementwise):
 
 class Mod(_Elementwise):
     def f(self, env, x, n, d): return x - n * np.floor((x - d) / n)              # math_functions.py:157-160
-    def difft(self, v, g):                                                       # maths/Mod.py: derivative of x only
-        x = self.children[0]
-        return x.difft(v, _red(g, x.dim))
+    def difft(self, v, g):                                                       # maths/Mod.py:14-20: gradient of the
+        x, n, d = self.children                                                  # alternative form x - n*Floor((x-d)/n)
+        return (x - n * Floor((x - d) / n)).difft(v, g)
 
 
 class SinXDivX(_Unary):

@@ -154,6 +154,7 @@ OPS2 = {
                "+NotEqual(Floor(IntCst(2)*x),Floor(IntCst(2)*y))*IntCst(8))*b,0)",
     "extractT_cst": "Sum_Reduction(ExtractT(x,1,5)*b*IntInv(3)+RatCst(2,7),0)",
     "mod": "Sum_Reduction(Mod(IntCst(5)*(x-y),IntCst(2),IntCst(-1))*b,0)",
+    "modvar": "Sum_Reduction(Mod(IntCst(5)*(x-y),y+IntCst(1),IntCst(-1))*b,0)",     # variable modulus: d/dn = -Floor((x-d)/n)
     "onehot": "Sum_Reduction(OneHot(Floor(IntCst(3)*b-IntCst(1)),5)*Elem(x,0),0)",
     "sinxdivx": "Sum_Reduction(SinXDivX(IntCst(4)*(x-y))*b,0)",
     "sqnorms": "Sum_Reduction(SqNorm2(x-y)*WeightedSqNorm(b+IntCst(1),x+y)*b,0)",
@@ -164,7 +165,7 @@ for nm, f in OPS2.items():
     case("op2_" + nm, f, [(3, 0, "u"), (3, 1, "u"), (1, 1, "p")], aliases=["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"])
 
 
-GRAD_OPS2 = ["asin_acos", "atan2", "argminmax_vec", "clampint", "extractT_cst", "mod", "sinxdivx", "sqnorms", "vecmatmult"]
+GRAD_OPS2 = ["asin_acos", "atan2", "argminmax_vec", "clampint", "extractT_cst", "mod", "modvar", "sinxdivx", "sqnorms", "vecmatmult"]
 for nm in GRAD_OPS2:
     f = OPS2[nm]
     ali = ["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"]

@@ -92,3 +92,28 @@ def test_double_accumulator_and_kahan_kernels_compile():
         assert capi.compile_to_cubin(ks.source, plan.nvrtc_options(True))[:4] == b"\x7fELF"
     with pytest.raises(ValueError):
         generate(red, "float32", 3, cfg, sum_scheme="nope")
+
+
+@pytest.mark.parametrize("head", ["Sum", "LSE", "LSEW"])
+def test_sum_scheme_x_dtype_acc_matrix_compiles(head):
+    """Every (sum_scheme, dtype_acc) pair that ``get_optional_flags`` accepts
+    (pykeops/pykeops/common/parse_type.py:195-207) yields a kernel that compiles, for the sum-like reductions whose
+    accumulator the options act on (reference: ``acc`` is declared in dtypeacc for every reduction,
+    keopscore/keopscore/mapreduce/MapReduce.py:74; Kahan for LSE: Max_SumShiftExpWeight_Reduction.py:65-85)."""
+    from keops_b200.formulas.parser import parse_reduction
+    from keops_b200.codegen.emit import generate
+    from keops_b200.runtime import capi, plan
+    f = {"Sum": "Sum_Reduction((Exp(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1)))))) * Var(2,2,1)),0)",
+         "LSE": "Max_SumShiftExp_Reduction(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1))))),0)",
+         "LSEW": "Max_SumShiftExpWeight_Reduction(Minus(Sum(Square((Var(0,3,0) - Var(1,3,1))))),0,Var(2,2,1))"}[head]
+    red = parse_reduction(f)
+    cfg = plan.default_config(red, "float32")
+    seen = set()
+    for scheme in ("block_sum", "direct_sum", "kahan_scheme"):
+        for acc in ("auto", "float32", "float64"):
+            ks = generate(red, "float32", 3, cfg, sum_scheme=scheme, dtype_acc=acc)
+            assert capi.compile_to_cubin(ks.source, plan.nvrtc_options(True))[:4] == b"\x7fELF", (scheme, acc)
+            seen.add(ks.hash)
+            if acc == "float64":
+                assert "double accd" in ks.source, (scheme, acc)
+    assert len(seen) == 6        # auto == float32; every other combination is a different kernel

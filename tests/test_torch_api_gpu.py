@@ -468,3 +468,21 @@ def test_accumulator_options(api, cuda_device):
         api.Genred("Exp(-SqDist(x,y))*b", al, reduction_op="Sum", axis=1, dtype_acc="float64", use_double_acc=True)
     with pytest.raises(ValueError):
         api.Genred("SqDist(x,y)", al[:2], reduction_op="Min", axis=1, dtype_acc="float64")
+    # the same options act on the (m, s) accumulator of the LogSumExp reductions (reference: acc is declared in dtypeacc
+    # for every reduction, MapReduce.py:74; Kahan: Max_SumShiftExpWeight_Reduction.py:65-85) -- plus the combination
+    # kahan_scheme + dtype_acc="float64", which get_optional_flags accepts
+    D2 = ((x.double()[:, None] - y.double()[None]) ** 2).sum(-1)
+    ref_lse = torch.logsumexp(-D2, dim=1, keepdim=True)
+    ref_w = (torch.softmax(-D2, dim=1) @ b.double())
+    for name, kw in (("block", {}), ("direct", dict(sum_scheme="direct_sum")), ("kahan", dict(sum_scheme="kahan_scheme")),
+                     ("acc64", dict(dtype_acc="float64")), ("kahan64", dict(sum_scheme="kahan_scheme", dtype_acc="float64")),
+                     ("direct64", dict(sum_scheme="direct_sum", dtype_acc="float64"))):
+        out = api.Genred("-SqDist(x,y)", al[:2], reduction_op="LogSumExp", axis=1, **kw)(x, y)
+        e1 = ((out.double() - ref_lse).abs() / ref_lse.abs()).max().item()
+        out = api.Genred("-SqDist(x,y)", al, reduction_op="SumSoftMaxWeight", axis=1, formula2="b", **kw)(x, y, b)
+        e2 = ((out.double() - ref_w).abs() / ref_w.abs()).max().item()
+        assert e1 < 1e-5 and e2 < 1e-5, (name, e1, e2)
+        if name in ("acc64", "kahan64", "direct64", "kahan"):
+            assert e2 < 2e-6, (name, e2)
+    out = api.Genred("Exp(-SqDist(x,y))*b", al, reduction_op="Sum", axis=1, sum_scheme="kahan_scheme", dtype_acc="float64")(x, y, b)
+    assert ((out.double() - ref).abs() / ref.abs()).max().item() < 1e-6
