@@ -1035,3 +1035,44 @@ def dense(formula, aliases, args, dtype="float64"):
             ncol = n
     env = _Env(args, np.dtype(dtype), tagI, slice(0, nrow))
     return np.broadcast_to(red.F.ev(env), (nrow, ncol, red.F.dim)).copy()
+
+
+def abs_scale(formula, aliases, args, dtype="float64", sizes=None, chunk_elems=1 << 24):
+    """Per-output *condition scale* ``A`` of a reduction, same shape as :func:`genred`'s result: the value against which a
+    relative error of the summation is meaningful.  ``Sum``: ``A_i = sum_j |F_ij|`` (equals ``|out_i|`` when all terms
+    have one sign; when terms cancel, an error of ``rtol * A_i`` is what a ``rtol``-accurate evaluation of every term
+    can guarantee).  ``LSE``: ``A = (|m|, sum_j |exp(F-m) G|)``.  Extremum-type reductions: ``A = |value|`` (index slots: 0).
+    Evaluated in ``dtype`` (float64 by default) -- test infrastructure for the element-wise parity gate."""
+    red = parse(formula, aliases)
+    dtype = np.dtype(dtype)
+    tagI, F, G, K, kind = red.tagI, red.F, red.G, red.K, red.kind
+    nrow = ncol = None
+    if sizes is not None:
+        nrow, ncol = (sizes[0], sizes[1]) if tagI == 0 else (sizes[1], sizes[0])
+    for v in red.vars().values():
+        if v.cat == 2:
+            continue
+        n = np.asarray(args[v.ind]).reshape(-1, v.dim).shape[0]
+        if v.cat == tagI:
+            nrow = n
+        else:
+            ncol = n
+    ref = genred(formula, aliases, args, dtype, chunk_elems=chunk_elems, sizes=sizes)
+    if kind not in ("Sum", "LSE") or nrow == 0 or ncol == 0:
+        return np.abs(ref)
+    d = F.dim
+    out = np.zeros_like(ref)
+    step = max(1, chunk_elems // max(1, ncol * max(d, 1)))
+    for r0 in range(0, nrow, step):
+        rows = slice(r0, min(nrow, r0 + step))
+        nr = rows.stop - rows.start
+        env = _Env(args, dtype, tagI, rows)
+        Fv = np.broadcast_to(F.ev(env), (nr, ncol, d))
+        if kind == "Sum":
+            out[rows] = np.abs(Fv).sum(axis=1, dtype=np.float64)
+        else:
+            Gv = np.broadcast_to(G.ev(env), (nr, ncol, G.dim))
+            m = Fv.max(axis=1)
+            out[rows, 0:1] = np.abs(m)
+            out[rows, 1:] = np.abs(np.exp(Fv - m[:, None, :]) * Gv).sum(axis=1, dtype=np.float64)
+    return out

@@ -41,3 +41,26 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.fail("GPU test selected but no CUDA device is visible (there is no CPU fallback)")
     return torch.device("cuda:0")
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Print (and save under gpurun_out/) the ACHIEVED element-wise parity errors, not only pass / fail."""
+    try:
+        from tests import util
+    except Exception:
+        return
+    if not util.ACHIEVED:
+        return
+    import json
+    worst = sorted(util.ACHIEVED.items(), key=lambda kv: -kv[1])
+    terminalreporter.write_line("achieved parity (max |got - ref| / condition scale) -- %d checks, worst 12:" % len(worst))
+    for what, v in worst[:12]:
+        terminalreporter.write_line("  %.3e  %s" % (v, what))
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        tag = "gpu" if "gpu" in (config.getoption("-m") or "") and "not gpu" not in (config.getoption("-m") or "") else "cpu"
+        with open(os.path.join(out, "parity_achieved_%s.json" % tag), "w") as f:
+            json.dump(dict(worst), f, indent=0)
+    except OSError:
+        pass

@@ -108,6 +108,20 @@ def _run(formula, nargs, args, nx, ny, dev, tc, **env):
         return out, dict(bd.last_launch)
 
 
+def _scale(formula, nargs, args, nx, ny, dev):
+    """Condition scale sum_j |F_ij| (CUDA-core evaluation; tests/util.py::gpu_abs_scale) as a numpy array."""
+    with _env(KB200_CONV_TC="0"):
+        return util.gpu_abs_scale(formula, nargs, "float32", dev, nx, ny, *args).cpu().numpy()
+
+
+def _ms_scale(o):
+    """(m, s) outputs of a LogSumExp reduction with positive weights: s is compared relatively, the running maximum m
+    (an exponent, possibly close to 0) with an absolute floor of 1."""
+    sc = np.abs(o)
+    sc[:, 0] = np.maximum(sc[:, 0], 1.0)
+    return sc
+
+
 CASES = [
     # D, DB, nx, ny, tagI, coefficient spelling
     (16, 1, 9000, 7001, 0, "-Var(3,1,2)*"),           # KernelSolve formula, ragged last tile
@@ -143,12 +157,14 @@ def test_tensor_core_conv_matches_cuda_core(D, DB, nx, ny, tagI, coef, cuda_devi
     assert ll["error_bound"] <= 5e-6
     o_cc, ll2 = _run(f, 4, (x, y, b, g), nx, ny, dev, False)
     assert ll2.get("engine") is None
-    util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 conv vs CUDA cores")
+    sc = _scale(f, 4, (x, y, b, g), nx, ny, dev)
+    tag = " D=%d DB=%d %dx%d tagI=%d" % (D, DB, nx, ny, tagI)
+    util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 conv vs CUDA cores" + tag, scale=sc)
     # several column chunks (forced) give the same sums up to fp32 re-association
     o_ch, ll3 = _run(f, 4, (x, y, b, g), nx, ny, dev, True, KB200_CONV_TC_CHUNK_MB=1)
     if (ny if tagI == 0 else nx) * 2 * (64 * conv_tc.layout(D)[0] + conv_tc.layout(D)[1]) > (1 << 20):
         assert ll3["nchunks"] > 1
-    util.assert_close(o_ch.cpu().numpy(), o_cc.cpu().numpy(), "float32", "chunked tcgen05 conv vs CUDA cores")
+    util.assert_close(o_ch.cpu().numpy(), o_cc.cpu().numpy(), "float32", "chunked tcgen05 conv vs CUDA cores" + tag, scale=sc)
     # sampled rows against the numpy oracle (reference operation order, exact exp)
     from oracle import keops_oracle as ko
     rows = slice(0, 48)
@@ -157,7 +173,7 @@ def test_tensor_core_conv_matches_cuda_core(D, DB, nx, ny, tagI, coef, cuda_devi
         ref = ko.genred(f, [], [xa[rows], ya, ba, ga], "float32")
     else:
         ref = ko.genred(f, [], [xa, ya[rows], ba, ga], "float32")
-    util.assert_close(o_tc[rows].cpu().numpy(), ref, "float32", "tcgen05 conv vs oracle")
+    util.assert_close(o_tc[rows].cpu().numpy(), ref, "float32", "tcgen05 conv vs oracle" + tag, scale=sc[rows])
 
 
 @pytest.mark.gpu
@@ -176,11 +192,12 @@ def test_tensor_core_conv_vs_reference_code(cuda_device):
     assert ll.get("engine") == "tcgen05-conv"
     ref = ref_runner.RefCuda("gauss16_pm_f32", 0)([x, y, b, g], nx, ny)
     torch.cuda.synchronize()
-    util.assert_close(o_tc.cpu().numpy(), ref.cpu().numpy(), "float32", "tcgen05 conv vs reference CUDA")
+    sc = _scale(KS, 4, (x, y, b, g), nx, ny, dev)
+    util.assert_close(o_tc.cpu().numpy(), ref.cpu().numpy(), "float32", "tcgen05 conv D=16 vs reference CUDA", scale=sc)
     rows = np.arange(0, nx, 157)
     cpu = ref_runner.run_cpu("gauss16_pm_f32", [x.cpu().numpy()[rows], y.cpu().numpy(), b.cpu().numpy(), g.cpu().numpy()],
                              len(rows), ny)
-    util.assert_close(o_tc.cpu().numpy()[rows], cpu, "float32", "tcgen05 conv vs reference CPU")
+    util.assert_close(o_tc.cpu().numpy()[rows], cpu, "float32", "tcgen05 conv D=16 vs reference CPU", scale=sc[rows])
 
 
 @pytest.mark.gpu
@@ -203,7 +220,8 @@ def test_accuracy_guard_falls_back_to_cuda_cores(cuda_device):
     o2, ll2 = _run(KS, 4, (x2, y2, b, g), nx, ny, dev, True)
     assert ll2.get("engine") == "tcgen05-conv" and ll2["error_bound"] <= 5e-6
     o2_cc, _ = _run(KS, 4, (x2, y2, b, g), nx, ny, dev, False)
-    util.assert_close(o2.cpu().numpy(), o2_cc.cpu().numpy(), "float32", "shifted cloud")
+    util.assert_close(o2.cpu().numpy(), o2_cc.cpu().numpy(), "float32", "tcgen05 conv, shifted cloud",
+                      scale=_scale(KS, 4, (x2, y2, b, g), nx, ny, dev))
 
 
 @pytest.mark.gpu
@@ -219,7 +237,9 @@ def test_tensor_core_conv_is_deterministic_and_linear(cuda_device):
     assert torch.equal(o1, o1b)
     o2, _ = _run(KS, 4, (x, y, b2, g), nx, ny, dev, True)
     o12, _ = _run(KS, 4, (x, y, b1 + 2.0 * b2, g), nx, ny, dev, True)
-    util.assert_close(o12.cpu().numpy(), (o1 + 2.0 * o2).cpu().numpy(), "float32", "linearity in b")
+    sc = _scale(KS, 4, (x, y, b1, g), nx, ny, dev) + 2.0 * _scale(KS, 4, (x, y, b2, g), nx, ny, dev)
+    util.assert_close(o12.cpu().numpy(), (o1 + 2.0 * o2).cpu().numpy(), "float32", "tcgen05 conv, linearity in b", scale=sc,
+                      rtol=2e-5)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -276,13 +296,17 @@ def test_tensor_core_lse_matches_cuda_core(D, DW, nx, ny, tagI, cuda_device):
     o_cc, ll2 = _run(f, len(args), args, nx, ny, dev, False)
     assert ll2.get("engine") is None
     # raw (m, s) output: m = max_j F_ij, s = sum_j exp(F_ij - m) b_j
-    util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 LSE (m, s) vs CUDA cores")
+    tag = " D=%d DW=%d %dx%d tagI=%d" % (D, DW, nx, ny, tagI)
+    util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 LSE (m, s) vs CUDA cores" + tag,
+                      scale=_ms_scale(o_cc.cpu().numpy()))
     # forced column chunks: the (m, s) partials are merged by kb200_conv_combine_lse
     o_ch, ll3 = _run(f, len(args), args, nx, ny, dev, True, KB200_CONV_TC_CHUNK_MB=1)
-    util.assert_close(o_ch.cpu().numpy(), o_cc.cpu().numpy(), "float32", "chunked tcgen05 LSE vs CUDA cores")
+    util.assert_close(o_ch.cpu().numpy(), o_cc.cpu().numpy(), "float32", "chunked tcgen05 LSE vs CUDA cores" + tag,
+                      scale=_ms_scale(o_cc.cpu().numpy()))
     lse_tc = o_tc[:, 0] + torch.log(o_tc[:, 1])
     lse_cc = o_cc[:, 0] + torch.log(o_cc[:, 1])
-    util.assert_close(lse_tc.cpu().numpy(), lse_cc.cpu().numpy(), "float32", "log-sum-exp")
+    util.assert_close(lse_tc.cpu().numpy(), lse_cc.cpu().numpy(), "float32", "tcgen05 log-sum-exp vs CUDA cores" + tag,
+                      scale=np.maximum(np.abs(lse_cc.cpu().numpy()), 1.0))
     from oracle import keops_oracle as ko
     rows = slice(0, 40)
     host = [t.cpu().numpy() for t in args]
@@ -291,7 +315,7 @@ def test_tensor_core_lse_matches_cuda_core(D, DW, nx, ny, tagI, cuda_device):
     else:
         host[1] = host[1][rows]
     ref = ko.genred(f, [], host, "float32")
-    util.assert_close(o_tc[rows].cpu().numpy(), ref, "float32", "tcgen05 LSE vs oracle")
+    util.assert_close(o_tc[rows].cpu().numpy(), ref, "float32", "tcgen05 LSE vs oracle" + tag, scale=_ms_scale(ref))
 
 
 @pytest.mark.gpu

@@ -20,7 +20,7 @@ def test_lowered_formula_matches_reference(name):
         assert same.mean() > 0.999
     else:
         rtol = 2e-5 if meta["dtype"] == "float32" else util.rtol_for(meta) * 50
-        util.assert_close(got, ref, "float64", name, rtol=rtol)
+        util.assert_close(got, ref, "float64", name, rtol=rtol, **util.golden_scale(meta, args))
 
 
 @pytest.mark.parametrize("fast", [False, True])
@@ -29,7 +29,7 @@ def test_lowered_formula_matches_reference(name):
 def test_fast_math_regrouping_preserves_values(name, fast):
     meta, args, ref = util.load_case(name)
     got = dag_eval.evaluate(meta["formula"], meta["aliases"], args, "float64", fast=fast)
-    util.assert_close(got, ref, "float64", name, rtol=2e-5)
+    util.assert_close(got, ref, "float64", name, rtol=2e-5, **util.golden_scale(meta, args))
 
 
 def test_metadata_matches_reference():

@@ -65,6 +65,7 @@ def gauss(cuda_device):
     dev = cuda_device
     t = dict(x=x.to(dev), y=y.to(dev), b=b.to(dev), eta=eta.to(dev))
     t["fwd"] = run(binder(GAUSS, 3), dev, M, N, t["x"], t["y"], t["b"])
+    t["scale"] = util.gpu_abs_scale(GAUSS, 3, "float32", dev, M, N, t["x"], t["y"], t["b"])     # sum_j |k_ij b_j|
     t["np"] = [x.numpy(), y.numpy(), b.numpy(), eta.numpy()]
     return t
 
@@ -73,7 +74,8 @@ def test_gauss_forward_sampled_rows_vs_reference_cpu(gauss, cuda_device):
     rows = sample_rows(M, 384)
     ref = ref_rows("gauss_fwd_f32", GAUSS, gauss["np"][:3], rows, "float32", {0})
     got = gauss["fwd"][torch.from_numpy(rows[:len(ref)]).to(cuda_device)].cpu().numpy()
-    util.assert_close(got, ref, "float32", "gauss fwd 1e6, sampled rows")
+    sc = gauss["scale"][torch.from_numpy(rows[:len(ref)]).to(cuda_device)].cpu().numpy()
+    util.assert_close(got, ref, "float32", "gauss fwd 1e6, sampled rows vs reference CPU", scale=sc)
 
 
 def test_gauss_forward_all_rows_vs_reference_cuda(gauss, cuda_device):
@@ -82,7 +84,8 @@ def test_gauss_forward_all_rows_vs_reference_cuda(gauss, cuda_device):
         pytest.skip("oracle/_ref not built")
     ref = ref_runner.RefCuda("gauss_fwd_f32", 0)([gauss["x"], gauss["y"], gauss["b"]], M, N)
     torch.cuda.synchronize()
-    util.assert_close(gauss["fwd"].cpu().numpy(), ref.cpu().numpy(), "float32", "gauss fwd 1e6 vs reference CUDA")
+    util.assert_close(gauss["fwd"].cpu().numpy(), ref.cpu().numpy(), "float32", "gauss fwd 1e6, all rows vs reference CUDA",
+                      scale=gauss["scale"].cpu().numpy())
 
 
 def test_gauss_linearity_and_idempotence(gauss, cuda_device):
@@ -90,7 +93,9 @@ def test_gauss_linearity_and_idempotence(gauss, cuda_device):
     b2 = torch.randn(N, 1, device=dev)
     o2 = run(bd, dev, M, N, gauss["x"], gauss["y"], b2)
     o12 = run(bd, dev, M, N, gauss["x"], gauss["y"], gauss["b"] + 2.0 * b2)
-    util.assert_close(o12.cpu().numpy(), (gauss["fwd"] + 2.0 * o2).cpu().numpy(), "float32", "linearity in b")
+    sc = gauss["scale"] + 2.0 * util.gpu_abs_scale(GAUSS, 3, "float32", dev, M, N, gauss["x"], gauss["y"], b2)
+    util.assert_close(o12.cpu().numpy(), (gauss["fwd"] + 2.0 * o2).cpu().numpy(), "float32", "gauss fwd 1e6, linearity in b",
+                      scale=sc.cpu().numpy(), rtol=2e-5)
     again = run(bd, dev, M, N, gauss["x"], gauss["y"], gauss["b"])
     assert torch.equal(again, gauss["fwd"]), "two launches on the same inputs must be bit-identical"
 
@@ -115,12 +120,20 @@ def test_gauss_gradients_full_size(gauss, cuda_device):
     rows = sample_rows(M, 256, seed=4)
     args = gauss["np"] + [fwd.cpu().numpy()]
     ref = ref_rows("gauss_dx_f32", GRAD % "Var(0,3,0)", args, rows, "float32", {0, 3, 4})
-    util.assert_close(gx[torch.from_numpy(rows[:len(ref)]).to(dev)].cpu().numpy(), ref, "float32", "grad_x 1e6, sampled rows")
+    rsel = torch.from_numpy(rows[:len(ref)]).to(dev)
+    scx = util.gpu_abs_scale(GRAD % "Var(0,3,0)", 5, "float32", dev, M, N, x, y, b, eta, fwd)
+    util.assert_close(gx[rsel].cpu().numpy(), ref, "float32", "grad_x 1e6, sampled rows vs reference CPU", scale=scx[rsel].cpu().numpy())
     from oracle import ref_runner
     if ref_runner.available():
         refy = ref_runner.RefCuda("gauss_dy_f32", 0)([x, y, b, eta, fwd], M, N)
         torch.cuda.synchronize()
-        util.assert_close(gy.cpu().numpy(), refy.cpu().numpy(), "float32", "grad_y 1e6 vs reference CUDA")
+        scy = util.gpu_abs_scale(GRAD % "Var(1,3,1)", 5, "float32", dev, M, N, x, y, b, eta, fwd)
+        util.assert_close(gy.cpu().numpy(), refy.cpu().numpy(), "float32", "grad_y 1e6, all rows vs reference CUDA",
+                          scale=scy.cpu().numpy())
+        refx = ref_runner.RefCuda("gauss_dx_f32", 0)([x, y, b, eta, fwd], M, N)
+        torch.cuda.synchronize()
+        util.assert_close(gx.cpu().numpy(), refx.cpu().numpy(), "float32", "grad_x 1e6, all rows vs reference CUDA",
+                          scale=scx.cpu().numpy())
 
 
 def _check_knn_rows(got_rows, ref_rows_, xs, y, what):
@@ -184,7 +197,7 @@ def test_lse_softmin_full_size(dtype, key, cuda_device):
     rows = sample_rows(M, 256 if dtype == "float32" else 128, seed=7)
     ref = ref_rows(key, LSE, [a.numpy() for a in (f, x, y, eps)], rows, dtype, {1})
     refv = ref[:, 0] + np.log(ref[:, 1])
-    util.assert_close(got[rows[:len(ref)]], refv, dtype, "softmin %s 1e6, sampled rows" % dtype)
+    util.assert_close(got[rows[:len(ref)]], refv, dtype, "softmin %s 1e6, sampled rows vs reference CPU" % dtype)
     # shift property: adding a constant c to the potential f shifts the log-sum-exp by exactly c
     c = 0.75
     ms2 = run(binder(LSE, 4, dtype), dev, M, N, targs[0] + c, *targs[1:])

@@ -24,15 +24,21 @@ def run_binder(meta, args, device, flags=None):
     return b, out.cpu().numpy()
 
 
-def check_indices(meta, args, got_idx, ref_idx, slot_to_comp, what):
-    """Indices must match bit-exactly unless the two candidates are a near-tie in value."""
-    if np.array_equal(got_idx, ref_idx):
+def check_indices(meta, args, got_idx, ref_idx, slot_to_comp, what, ulps=1.0, max_frac=1e-3):
+    """Indices must match bit-exactly.  The one admissible difference: two columns whose exact (fp64) values agree to
+    within ``ulps`` fp32 ulps (1 by default; ~sqrt(D) for a D-term sum, whose rounding error grows like that), where the golden CPU code (no FMA contraction, x86-64 baseline ISA) and a GPU kernel (FMA, like
+    the reference's own nvcc build) may legitimately order them differently -- float32 fixtures only, never for float64,
+    and the number of such entries is recorded next to the achieved parity errors (``index_ties:<case>``)."""
+    nbad = int((got_idx != ref_idx).sum())
+    util.ACHIEVED["index_ties:" + what] = float(nbad)
+    if nbad == 0:
         return
+    assert meta["dtype"] == "float32", "%s: %d index mismatches in float64" % (what, nbad)
     from oracle import keops_oracle as ko
     F = ko.dense(meta["formula"], meta["aliases"], args, "float64")
     bad = np.argwhere(got_idx != ref_idx)
-    assert len(bad) <= max(1, got_idx.size // 200), "%s: %d index mismatches" % (what, len(bad))
-    eps = 2.0 ** -22 if meta["dtype"] == "float32" else 2.0 ** -50
+    assert len(bad) <= max(1, int(got_idx.size * max_frac)), "%s: %d index mismatches" % (what, len(bad))
+    eps = ulps * 2.0 ** -23
     for r, s in bad:
         c = slot_to_comp(s)
         j1, j2 = int(got_idx[r, s]), int(ref_idx[r, s])
@@ -54,7 +60,7 @@ def test_cuda_matches_reference(name, cuda_device):
     elif head == "ArgKMin_Reduction":
         check_indices(meta, args, got, ref, lambda s: s % d, name)
     elif head in ("Min_ArgMin_Reduction", "Max_ArgMax_Reduction"):
-        util.assert_close(got[:, :d], ref[:, :d], meta["dtype"], name)
+        util.assert_close(got[:, :d], ref[:, :d], meta["dtype"], name)      # values: pure element-wise relative error
         check_indices(meta, args, got[:, d:], ref[:, d:], lambda s: s, name)
     elif head == "KMin_ArgKMin_Reduction":
         g3, r3 = got.reshape(len(got), -1, 2, d), ref.reshape(len(ref), -1, 2, d)
@@ -62,7 +68,7 @@ def test_cuda_matches_reference(name, cuda_device):
         check_indices(meta, args, g3[:, :, 1].reshape(len(got), -1), r3[:, :, 1].reshape(len(ref), -1),
                       lambda s: s % d, name)
     else:
-        util.assert_close(got, ref, meta["dtype"], name, rtol=util.rtol_for(meta))
+        util.assert_close(got, ref, meta["dtype"], name, rtol=util.rtol_for(meta), **util.golden_scale(meta, args))
 
 
 @pytest.mark.parametrize("name", [n for n in util.golden_names() if n.startswith(("gauss_sum_float", "lse_softmin", "argkmin_K10_D3"))])
@@ -72,13 +78,12 @@ def test_option_variants(name, flags, cuda_device):
     head = meta["formula"].split("(")[0]
     if "sum_scheme" in flags and head not in ("Sum_Reduction", "Max_SumShiftExp_Reduction"):
         pytest.skip("sum schemes only apply to sum-type reductions")
-    if flags.get("sum_scheme") == "kahan_scheme" and head != "Sum_Reduction":
-        pytest.skip("kahan implemented for Sum only")
     b, got = run_binder(meta, args, cuda_device, flags)
+    tag = name + "/" + ",".join("%s=%s" % kv for kv in flags.items())
     if head == "ArgKMin_Reduction":
-        check_indices(meta, args, got, ref, lambda s: s % b.red.dimF, name)
+        check_indices(meta, args, got, ref, lambda s: s % b.red.dimF, tag)
     else:
-        util.assert_close(got, ref, meta["dtype"], name)
+        util.assert_close(got, ref, meta["dtype"], tag, **util.golden_scale(meta, args))
 
 
 @pytest.mark.gpu
@@ -98,7 +103,8 @@ def test_high_dimensional_gaussian_vs_oracle(cuda_device):
     targs = [torch.from_numpy(a).to(cuda_device) for a in (x, y, b, g)]
     out = get_binder(f, [], 4, "float32").genred_pytorch(cuda_device, None, M, N, 0, None, *targs)
     torch.cuda.synchronize()
-    util.assert_close(out.cpu().numpy(), ko.genred(f, [], [x, y, b, g], "float32"), "float32", "gaussian D=300")
+    util.assert_close(out.cpu().numpy(), ko.genred(f, [], [x, y, b, g], "float32"), "float32", "gaussian D=300",
+                      scale=ko.abs_scale(f, [], [x, y, b, g]))
 
 
 @pytest.mark.gpu
@@ -121,14 +127,15 @@ def test_wide_streamed_factor_is_chunked(tagI, cuda_device):
     out = bd.genred_pytorch(cuda_device, None, M, N, 0, None, *targs)
     assert bd.last_launch.get("wide_chunks") == 10, bd.last_launch
     ref = ko.genred(f, [], [x, y, b], "float32")
-    util.assert_close(out.cpu().numpy(), ref, "float32", "wide b, chunked")
+    A = ko.abs_scale(f, [], [x, y, b])
+    util.assert_close(out.cpu().numpy(), ref, "float32", "wide b, chunked", scale=A)
     os.environ["KB200_WIDE_CHUNKS"] = "0"
     try:
         plain = bd.genred_pytorch(cuda_device, None, M, N, 0, None, *targs)
         assert bd.last_launch.get("wide_chunks") is None
     finally:
         os.environ.pop("KB200_WIDE_CHUNKS", None)
-    util.assert_close(out.cpu().numpy(), plain.cpu().numpy(), "float32", "wide b, chunked vs unchunked")
+    util.assert_close(out.cpu().numpy(), plain.cpu().numpy(), "float32", "wide b, chunked vs unchunked", scale=A)
     dst = torch.empty_like(out)
     res = bd.genred_pytorch(cuda_device, None, M, N, 0, dst, *targs)
     assert res.data_ptr() == dst.data_ptr() and torch.equal(dst, out)
@@ -149,5 +156,8 @@ def test_high_dimensional_argkmin_vs_oracle(cuda_device):
                                                          torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device))
     torch.cuda.synchronize()
     ref = ko.genred(f, [], [x, y], "float32")
-    agree = (out.cpu().numpy() == ref).all(axis=1).mean()
-    assert agree > 0.97, agree          # fp32 near-ties may swap between FMA and non-FMA evaluation orders
+    # fp32 near-ties may swap between FMA and non-FMA evaluation orders of a 200-term sum: every differing entry must be
+    # such a tie (values equal to ~sqrt(D) ulps in exact arithmetic); the count is recorded with the parity errors
+    meta = dict(formula=f, aliases=[], dtype="float32")
+    check_indices(meta, [x, y], out.cpu().numpy(), ref, lambda s: 0, "argkmin D=200 vs oracle", ulps=2.0 * np.sqrt(D),
+                  max_frac=0.01)
