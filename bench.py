@@ -9,16 +9,21 @@ forward reduction over the whole problem = 10^12 pair evaluations.  ``value`` is
 inputs resident in HBM; ``e2e`` is the same metric through the public ``Genred`` call with pinned HOST
 buffers (H2D of x, y, b and D2H of the result inside the timed region).
 
-N > 1 (torchrun, one rank per GPU): the *output index* is sharded -- rank r owns rows
-[r*M/N, (r+1)*M/N) of x and of the output -- and the streamed operands (y, b) are replicated with one
-NCCL broadcast per step inside the timed region; there is no cross-GPU reduction.  Total work is fixed
-("scaling": "strong").
+N > 1 (torchrun, one rank per GPU) goes through the product's multi-GPU API, ``keops_b200.distributed``: every array is
+row-sharded by its own index (rank r owns slab r of x, y, b, ...), ``ShardedGenred`` shards the *output index* and
+replicates the streamed operands with one NCCL ``all_gather`` per operand per step INSIDE the timed region; there is no
+cross-GPU reduction.  Total work is fixed ("scaling": "strong").
 
-Extra keys: ``roofline`` (FP32/SFU roofline of SURVEY.md 8(d): 16 pairs/clk/SM -- one MUFU.EX2 per
-pair), ``roofline_hbm`` (algorithmic unique bytes vs measured copy bandwidth: shows the kernel is not
-HBM-bound), ``cpu_baseline`` (the reference's own CpuReduc code on the host cores, bounded sample),
-``ref_cuda`` (the reference's own generated GpuConv1DOnDevice kernel on the same GPU), ``knn``
-(ArgKMin K=10 queries/s, configs[2]) and ``fwd_bwd`` (forward + grad_x + grad_y rate).
+Legs, each at every N and each through the sharded API (``legs`` key; median of >= 10 CUDA-event-timed repetitions, L2
+flushed in between, max over ranks): ``fwd_bwd`` (forward + grad_x sharded by i + grad_y sharded by j,
+``ShardedGenred.gradient``), ``knn`` / ``knn_d64`` (ArgKMin K=10, D = 3 / 64), ``lse_softmin`` (LogSumExp, D = 3) and
+``ksolve`` (``ShardedKernelSolve``, Gaussian kernel D = 16, time per CG iteration).
+
+Extra keys: ``roofline`` (FP32/SFU roofline of SURVEY.md 8(d): 16 pairs/clk/SM -- one MUFU.EX2 per pair),
+``roofline_hbm`` (algorithmic unique bytes vs measured copy bandwidth: shows the kernel is not HBM-bound),
+``cpu_baseline`` (the reference's own CpuReduc code on the host cores, bounded sample, thread count reported by OpenMP
+itself), ``parity`` (achieved max errors of every BASELINE config against the reference's CPU code and CUDA kernel) and,
+at N = 1, ``ref_cuda`` (the reference's own generated GpuConv1DOnDevice kernel on the same GPU).
 
 ``--impl reference`` times the reference's CPU implementation (oracle/_ref, built from the unmodified
 reference code generator by oracle/build_ref.py) on all host cores, on a bounded sample of the same
@@ -42,6 +47,8 @@ GRAD_X = "Grad_WithSavedForward(%s,Var(0,3,0),Var(3,1,0),Var(4,1,0))" % GAUSS
 GRAD_Y = "Grad_WithSavedForward(%s,Var(1,3,1),Var(3,1,0),Var(4,1,0))" % GAUSS
 KNN = "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)"
 KSOLVE = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)"    # BASELINE configs[4] matvec
+KSOLVE_G = "Sum_Reduction(Exp(-g*SqDist(x,y))*b,0)"
+LSE = "Max_SumShiftExp_Reduction((Var(0,1,1) - ((Sum(Square((Var(1,3,0) - Var(2,3,1)))) / IntCst(2)) / Var(3,1,2))),0)"
 SM_COUNT, SM_MAX_HZ = 148, 1.965e9
 # dram__bytes_read.sum + dram__bytes_write.sum of one kb200_reduce launch of the full-size forward conv, from the
 # committed `ncu --set full` capture profiles/r01_ncu_gauss_fwd_v2.txt (28.148 MB + 42 KB; algorithmic bytes 32 MB)
@@ -126,17 +133,43 @@ def dist_env():
 # ---------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU code (oracle/_ref) on the host cores
 # ---------------------------------------------------------------------------------------------
-def reference_cpu_rate(budget_s, full=False):
+def host_threads():
+    """Host cores this process may run on (torchrun does not pin ranks; cgroup limits show up in the affinity mask)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def openmp_use_all_cores():
+    """``torch.distributed.run`` exports OMP_NUM_THREADS=1 to every rank, which silently turned the reference's OpenMP code
+    into a single-thread run.  Set the thread count explicitly -- in the environment (read by libgomp when
+    oracle/_ref/libkeops_ref_cpu.so pulls it in) AND through omp_set_num_threads of that same libgomp.so.1 (in case it is
+    already loaded) -- and return the count OpenMP itself reports."""
+    import ctypes
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_dynamic(0)
+        gomp.omp_set_num_threads(int(n))
+        return int(gomp.omp_get_max_threads()), n
+    except OSError:
+        return None, n
+
+
+def reference_cpu_rate(budget_s):
     """pair-evals/s of the reference CpuReduc code on a bounded sample: rows of the M=N=1e6 problem."""
     import numpy as np
     from oracle import ref_runner
     if not ref_runner.available():
         return None
+    omp_threads, cores = openmp_use_all_cores()
     rng = np.random.default_rng(0)
     N = N_FULL
     y = rng.standard_normal((N, 3)).astype(np.float32)
     b = rng.standard_normal((N, 1)).astype(np.float32)
-    cores = os.cpu_count() or 1
     rows = max(64, 8 * cores)
     x = rng.standard_normal((rows, 3)).astype(np.float32)
     ref_runner.run_cpu("gauss_fwd_f32", [x, y, b], rows, N)            # warm-up (thread pool start)
@@ -153,9 +186,10 @@ def reference_cpu_rate(budget_s, full=False):
         ref_runner.run_cpu("gauss_fwd_f32", [x, y, b], rows2, N)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return dict(value=rows2 * N / best, unit="pair-evals/s", cores=cores, kind="reference",
-                sample="%d of %d rows x all %d columns (%.2e pairs), best of 2, OpenMP threads = all %d cores"
-                       % (rows2, M_FULL, N, rows2 * N, cores), seconds=best, rows=rows2)
+    return dict(value=rows2 * N / best, unit="pair-evals/s", cores=omp_threads or cores, kind="reference",
+                sample="%d of %d rows x all %d columns (%.2e pairs), best of 2; OpenMP threads %s (omp_get_max_threads) on %d usable host cores"
+                       % (rows2, M_FULL, N, rows2 * N, omp_threads, cores), seconds=best, rows=rows2,
+                omp_max_threads=omp_threads, host_cores=cores)
 
 
 def run_reference_arm(args):
@@ -167,9 +201,9 @@ def run_reference_arm(args):
     if not ref_runner.available():
         emit_json({"impl": "reference", "unavailable": "oracle/_ref was not built (run oracle/build_ref.py where /root/reference is mounted)"})
         return 0
+    omp_threads, cores = openmp_use_all_cores()
     rng = np.random.default_rng(0)
     N = N_FULL
-    cores = os.cpu_count() or 1
     y = rng.standard_normal((N, 3)).astype(np.float32)
     b = rng.standard_normal((N, 1)).astype(np.float32)
     probe = reference_cpu_rate(2.0)
@@ -184,14 +218,16 @@ def run_reference_arm(args):
         ref_runner.run_cpu("gauss_fwd_f32", [x, y, b], rows, N)
     dt = time.perf_counter() - t0
     value = args.steps * rows * N / dt
-    sample = "%d of %d rows x all %d columns per step, OpenMP over %d host cores" % (rows, M_FULL, N, cores)
+    sample = ("%d of %d rows x all %d columns per step; OpenMP threads %s (omp_get_max_threads) on %d usable host cores, "
+              "OMP_NUM_THREADS reset from the launcher's value" % (rows, M_FULL, N, omp_threads, cores))
     line = {
         "impl": "reference", "metric": "gaussian_conv_pair_evals_per_s", "value": value, "unit": "pair-evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "gaussian_conv_fwd M=N=1e6 D=3 fp32 (reference CpuReduc, bounded row sample)",
                    "M": M_FULL, "N": N_FULL, "D": 3, "sample_rows": rows},
-        "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": omp_threads or cores, "kind": "reference",
+                         "sample": sample, "omp_max_threads": omp_threads, "host_cores": cores},
         "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -202,6 +238,50 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+class Ctx:
+    """Per-rank state of a run: device, world, the L2-flush buffer, and the timing helpers."""
+
+    def __init__(self, torch, dist, rank, world, dev):
+        self.torch, self.dist, self.rank, self.world, self.dev = torch, dist, rank, world, dev
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def slab(self, n):
+        from keops_b200.distributed import shard_bounds
+        return shard_bounds(n, self.world, self.rank)
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def time_leg(self, fn, reps=10, warm=1):
+        """Median over ``reps`` of (max over ranks of) the CUDA-event time of ``fn()`` -- collectives included -- with the L2
+        flushed and the ranks aligned before every repetition."""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.sync_all()
+        ms = []
+        for _ in range(reps):
+            self.flush.zero_()
+            self.sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        ms = sorted(self.max_over_ranks(ms))
+        return ms[len(ms) // 2], ms[0]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,7 +289,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kb200", choices=["kb200", "reference"])
     ap.add_argument("--size", type=int, default=M_FULL, help="M = N (default: the BASELINE size 10^6)")
-    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / ref_cuda / knn / fwd_bwd legs")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e only (no legs / comparators / parity)")
+    ap.add_argument("--legs", default="fwd_bwd,knn,knn_d64,lse_softmin,ksolve", help="comma-separated legs to run")
+    ap.add_argument("--reps", type=int, default=10, help="timed repetitions per leg (median reported)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kb200" else args.warmup
     # the driver parses ONE JSON line from stdout: libraries that print to fd 1 (NCCL's version banner)
@@ -224,7 +306,7 @@ def main():
     import torch
     import torch.distributed as dist
     from keops_b200.binder import get_binder
-    from keops_b200.torch import Genred
+    from keops_b200.distributed import ShardedGenred, ShardedKernelSolve
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -234,130 +316,170 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    cx = Ctx(torch, dist, rank, world, dev)
     M = N = args.size
-    # ---- synthetic data (same bytes on every rank: seed 0), row slab of this rank
+    legs_wanted = [] if args.no_extras else [s for s in args.legs.split(",") if s]
+    # ---- synthetic data (same bytes on every rank: seed 0); every array is row-sharded by its own index
     g = torch.Generator(device="cpu").manual_seed(0)
     hx = torch.randn(M, 3, generator=g)
     hy = torch.randn(N, 3, generator=g)
     hb = torch.randn(N, 1, generator=g)
-    r0, r1 = rank * M // world, (rank + 1) * M // world
-    hx_slab = hx[r0:r1].contiguous().pin_memory()
-    hy_p, hb_p = hy.pin_memory(), hb.pin_memory()
-    x = hx_slab.to(dev)
-    if world > 1:
-        # rank 0 owns the streamed operands; replicas are (re)filled by the broadcast of each step
-        y = hy.to(dev) if rank == 0 else torch.empty(N, 3, device=dev)
-        b = hb.to(dev) if rank == 0 else torch.empty(N, 1, device=dev)
-    else:
-        y, b = hy.to(dev), hb.to(dev)
-    Ms = r1 - r0
-    binder = get_binder(GAUSS, [], 3, "float32")
+    heta = torch.randn(M, 1, generator=g)
+    i0, i1 = cx.slab(M)
+    j0, j1 = cx.slab(N)
+    hx_s, hy_s, hb_s = (t.contiguous().pin_memory() for t in (hx[i0:i1], hy[j0:j1], hb[j0:j1]))
+    x, y, b = hx_s.to(dev), hy_s.to(dev), hb_s.to(dev)
+    Ms = i1 - i0
+    al = ["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"]
+    conv = ShardedGenred("Exp(-SqDist(x,y))*b", al, "Sum", axis=1)
     out = torch.empty(Ms, 1, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step():
-        if world > 1:
-            dist.broadcast(y, 0)
-            dist.broadcast(b, 0)
-        binder.genred_pytorch(dev, None, Ms, N, 0, out, x, y, b)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        conv(x, y, b, n_streamed=N, mode="all_gather", out=out)
 
     for _ in range(args.warmup):
-        flush.zero_()
+        cx.flush.zero_()
         step()
-    sync_all()
+    cx.sync_all()
+    fwd_binder = get_binder(GAUSS, [], 3, "float32")
+    launches_per_step = int(fwd_binder.last_launch["launches"])
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
+    cx.sync_all()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        flush.zero_()                      # L2 flush between timed iterations (inputs are 28 MB < L2)
+        cx.flush.zero_()                   # L2 flush between timed iterations (inputs are 28 MB < 126 MB L2)
         ev[k][0].record()
         step()
         ev[k][1].record()
-    sync_all()
+    cx.sync_all()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = [a.elapsed_time(b_) for a, b_ in ev]
-    tot_ms = torch.tensor([sum(dev_ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
-    tot_s = float(tot_ms.item()) * 1e-3
+    tot_s = cx.max_over_ranks([sum(dev_ms)])[0] * 1e-3
     value = args.steps * float(M) * float(N) / tot_s
-    launches_per_step = binder.last_launch["launches"]
     kernel_launches = args.steps * launches_per_step
 
-    # ---- e2e through the public API with host buffers ------------------------------------------
-    conv = Genred("Exp(-SqDist(x,y))*b", ["x=Vi(3)", "y=Vj(3)", "b=Vj(1)"], reduction_op="Sum", axis=1)
+    # ---- e2e through the public API with host buffers: every rank uploads ITS slabs from pinned memory, the sharded call
+    # replicates the streamed ones over NVLink, the result slab goes back to pinned host memory
     hout = torch.empty(Ms, 1).pin_memory()
 
     def e2e_step():
-        xd = hx_slab.to(dev, non_blocking=True)
-        if world > 1:
-            yd = hy_p.to(dev, non_blocking=True) if rank == 0 else torch.empty(N, 3, device=dev)
-            bd = hb_p.to(dev, non_blocking=True) if rank == 0 else torch.empty(N, 1, device=dev)
-            dist.broadcast(yd, 0)
-            dist.broadcast(bd, 0)
-        else:
-            yd, bd = hy_p.to(dev, non_blocking=True), hb_p.to(dev, non_blocking=True)
-        res = conv(xd, yd, bd)
+        xd = hx_s.to(dev, non_blocking=True)
+        yd = hy_s.to(dev, non_blocking=True)
+        bd = hb_s.to(dev, non_blocking=True)
+        res = conv(xd, yd, bd, n_streamed=N, mode="all_gather")
         hout.copy_(res, non_blocking=True)
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
-    sync_all()
+    cx.sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-    sync_all()
-    e2e_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    cx.sync_all()
+    e2e_t = cx.max_over_ranks([time.perf_counter() - t0])[0]
+    e2e_value = e2e_steps * float(M) * float(N) / e2e_t
+    h2d = 4 * (M * 3 + N * 3 + N * 1)          # whole job: the slabs of all ranks
+    d2h = 4 * M
+
+    peaks, peaks_src = measured_peaks()
+    sm_hz = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    cc_peak = lambda ops: 128.0 / ops * SM_COUNT * sm_hz * world        # FP32-pipe roofline of an `ops`-instruction pair
+    legs = {}
+
+    # ---- forward + backward (BASELINE configs[1]): grad_x stays sharded by i, grad_y is sharded by j ------------------
+    fwd_slab = None
+    if "fwd_bwd" in legs_wanted:
+        eta = heta[i0:i1].to(dev)
+        fwd_slab = conv(x, y, b, n_streamed=N).clone()
+        gx_op, gy_op = conv.gradient("x"), conv.gradient("y")
+        f_ms, _ = cx.time_leg(step, args.reps)
+        gx_ms, _ = cx.time_leg(lambda: gx_op(x, y, b, eta, fwd_slab, n_i=M, n_j=N), args.reps)
+        gy_ms, _ = cx.time_leg(lambda: gy_op(x, y, b, eta, fwd_slab, n_i=M, n_j=N), args.reps)
+        legs["fwd_bwd"] = {"value": 3.0 * M * N / ((f_ms + gx_ms + gy_ms) * 1e-3), "unit": "pair-evals/s", "n_gpus": world,
+                           "fwd_ms": f_ms, "grad_x_ms": gx_ms, "grad_y_ms": gy_ms,
+                           "sharding": "fwd and grad_x by i (all_gather y, b); grad_y by j (all_gather x, eta, saved forward)",
+                           "grad_x_frac_of_roofline": M * N / (gx_ms * 1e-3) / (ROOFLINE_PAIRS_PER_CLK_SM["gauss_grad"] * SM_COUNT * sm_hz * world),
+                           "grad_y_frac_of_roofline": M * N / (gy_ms * 1e-3) / (ROOFLINE_PAIRS_PER_CLK_SM["gauss_grad"] * SM_COUNT * sm_hz * world)}
+
+    # ---- KNN K=10 (BASELINE configs[2]): every rank answers its slab of queries against the all-gathered database -------
+    def knn_leg(D):
+        gg = torch.Generator(device=dev).manual_seed(D)
+        q_full = torch.randn(M, D, generator=gg, device=dev)
+        d_full = torch.randn(N, D, generator=gg, device=dev)
+        q, d = q_full[i0:i1].contiguous(), d_full[j0:j1].contiguous()
+        del q_full, d_full
+        op = ShardedGenred("SqDist(x,y)", ["x=Vi(%d)" % D, "y=Vj(%d)" % D], "ArgKMin", axis=1, opt_arg=10)
+        ms, _ = cx.time_leg(lambda: op(q, d, n_streamed=N), args.reps)
+        kb_ = get_binder("ArgKMin_Reduction(SqDist(Var(0,%d,0),Var(1,%d,1)),10,0)" % (D, D), [], 2, "float32")
+        engine = (kb_.last_launch or {}).get("engine") or "cuda-core"
+        res = {"metric": "knn_k10_queries_per_s", "value": M / (ms * 1e-3), "unit": "queries/s", "D": D, "K": 10, "ms": ms,
+               "pair_evals_per_s": float(M) * N / (ms * 1e-3), "n_gpus": world, "engine": engine}
+        if engine == "cuda-core":
+            res["frac_of_roofline"] = float(M) * N / (ms * 1e-3) / cc_peak(2 * D + 1)
+        else:
+            from keops_b200.codegen import knn_tc
+            kdim = knn_tc.KnnTensorCore(D, 10, "ArgKMin", True, device=-1).DPG
+            tflops = 2.0 * M * N * kdim / (ms * 1e-3) / 1e12
+            res["roofline"] = {"bound": "tensor", "achieved": tflops, "peak": float(peaks.get("bf16_tflops", 1646.4)) * world,
+                               "unit": "TFLOP/s", "frac": tflops / (float(peaks.get("bf16_tflops", 1646.4)) * world),
+                               "note": "bf16 filter GEMM 2*M*N*%d flops (D + 3 penalty columns, padded) over the whole call "
+                                       "(prep + filter + exact select) vs the measured cuBLAS bf16 burst peak (%s)" % (kdim, peaks_src)}
+            res["x_cuda_core_fp32_roofline"] = float(M) * N / (ms * 1e-3) / cc_peak(2 * D + 1)
+        return res
+
+    for name, D in (("knn", 3), ("knn_d64", 64)):
+        if name in legs_wanted:
+            try:
+                legs[name] = knn_leg(D)
+            except Exception as e:
+                legs[name] = {"unavailable": repr(e)[:300]}
+
+    # ---- LogSumExp soft-min (BASELINE configs[3]) -------------------------------------------------------------------------
+    if "lse_softmin" in legs_wanted:
+        gg = torch.Generator(device=dev).manual_seed(7)
+        lf, lx, ly = torch.rand(N, 1, generator=gg, device=dev), torch.rand(M, 3, generator=gg, device=dev), torch.rand(N, 3, generator=gg, device=dev)
+        lf, lx, ly = lf[j0:j1].contiguous(), lx[i0:i1].contiguous(), ly[j0:j1].contiguous()
+        eps = torch.tensor([0.05], device=dev)
+        op = ShardedGenred("f - SqDist(x,y)/IntCst(2)/e", ["f=Vj(1)", "x=Vi(3)", "y=Vj(3)", "e=Pm(1)"], "LogSumExp", axis=1)
+        ms, _ = cx.time_leg(lambda: op(lf, lx, ly, eps, n_streamed=N), args.reps)
+        legs["lse_softmin"] = {"workload": "LogSumExp soft-min M=N=%d D=3 fp32 (BASELINE configs[3])" % M, "ms": ms,
+                               "value": float(M) * N / (ms * 1e-3), "unit": "pair-evals/s", "n_gpus": world,
+                               "frac_of_roofline": float(M) * N / (ms * 1e-3) / cc_peak(12)}
+        del lf, lx, ly
+
+    # ---- KernelSolve (BASELINE configs[4]): row-sharded CG, Gaussian kernel D = 16; one iteration = M*N pairs -------------
+    if "ksolve" in legs_wanted:
+        try:
+            gg = torch.Generator(device=dev).manual_seed(16)
+            kx = torch.rand(M, 16, generator=gg, device=dev)[i0:i1].contiguous()
+            rhs = torch.randn(M, 1, generator=gg, device=dev)[i0:i1].contiguous()
+            kg = torch.tensor([1.0], device=dev)
+            ITER = 4
+            ks = ShardedKernelSolve("Exp(-g*SqDist(x,y))*b", ["x=Vi(16)", "y=Vj(16)", "b=Vj(1)", "g=Pm(1)"], "b", axis=1)
+            ms, _ = cx.time_leg(lambda: ks(kx, kx, rhs, kg, n_total=M, alpha=0.8, eps=0.0, max_iter=ITER), max(3, args.reps // 2))
+            kb_ = get_binder(KSOLVE_G, [], 4, "float32")
+            engine = (kb_.last_launch or {}).get("engine") or "cuda-core"
+            legs["ksolve"] = {"workload": "ShardedKernelSolve, Gaussian kernel D=16, N=%d fp32: %d CG iterations (all_gather of the "
+                                          "point cloud once, of the search direction every iteration)" % (M, ITER),
+                              "ms_per_iteration": ms / ITER, "iterations": ks.last_iterations, "value": ITER * float(M) * M / (ms * 1e-3),
+                              "unit": "pair-evals/s", "n_gpus": world, "engine": engine,
+                              "frac_of_mufu_roofline": ITER * float(M) * M / (ms * 1e-3) / (16.0 * SM_COUNT * sm_hz * world),
+                              "x_cuda_core_fp32_roofline": ITER * float(M) * M / (ms * 1e-3) / cc_peak(34)}
+            del kx, rhs
+        except Exception as e:
+            legs["ksolve"] = {"unavailable": repr(e)[:300]}
+
     if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_steps * float(M) * float(N) / float(e2e_t.item())
-    h2d = hx_slab.numel() * 4 + (hy_p.numel() + hb_p.numel()) * 4 * (1 if (world == 1 or rank == 0) else 0)
-    d2h = hout.numel() * 4
-
-    # ---- KNN K=10 (BASELINE configs[2], D=3) on the same sharding: each rank answers its slab of
-    # queries against the full (replicated) database; max over ranks; aggregate queries/s
-    knn_line = None
-    if not args.no_extras:
-        knn_b = get_binder(KNN, [], 2, "float32")
-        ko = knn_b.genred_pytorch(dev, None, Ms, N, 0, None, x, y)
-        sync_all()
-        knn_ms = []
-        for _ in range(3):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            if world > 1:
-                dist.broadcast(y, 0)
-            knn_b.genred_pytorch(dev, None, Ms, N, 0, ko, x, y)
-            e1.record()
-            sync_all()
-            knn_ms.append(e0.elapsed_time(e1))
-        kt = torch.tensor([min(knn_ms)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(kt, op=dist.ReduceOp.MAX)
-        knn_t = float(kt.item())
-        knn_line = {"metric": "knn_k10_queries_per_s", "value": M / (knn_t * 1e-3), "unit": "queries/s", "D": 3, "K": 10,
-                    "ms": knn_t, "pair_evals_per_s": float(M) * N / (knn_t * 1e-3), "n_gpus": world,
-                    "frac_of_roofline": float(M) * N / (knn_t * 1e-3) / (ROOFLINE_PAIRS_PER_CLK_SM["knn_d3"] * SM_COUNT * SM_MAX_HZ * world)}
-        del ko
-
+        cx.sync_all()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peaks, peaks_src = measured_peaks()
-    sm_hz = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
     # roofline of the dominant kernel (kb200_reduce of the forward conv): measured live on this rank
     k_ms = sum(dev_ms) / len(dev_ms)
     pairs_per_launch = float(Ms) * float(N)
@@ -369,20 +491,22 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "gaussian_conv_fwd M=N=%d D=3 fp32 (BASELINE configs[1], forward reduction)" % M,
-                   "M": M, "N": N, "D": 3, "sharding": "output rows over %d GPU(s); y,b replicated by NCCL broadcast" % world,
+                   "M": M, "N": N, "D": 3,
+                   "api": "keops_b200.distributed.ShardedGenred (output rows over %d GPU(s); y, b all-gathered over NCCL inside the timed step)" % world,
                    "l2": "256 MiB memset between timed steps (inputs are 28 MB < 126 MB L2)",
-                   "kernel_config": binder.ks.cfg.key(), "nsplit": binder.last_launch["nsplit"],
-                   "regs": binder.last_launch["regs"], "blocks_per_sm": binder.last_launch["blocks_per_sm"]},
+                   "kernel_config": fwd_binder.ks.cfg.key(), "nsplit": fwd_binder.last_launch.get("nsplit"),
+                   "engine": fwd_binder.last_launch.get("engine") or "cuda-core",
+                   "regs": fwd_binder.last_launch.get("regs"), "blocks_per_sm": fwd_binder.last_launch.get("blocks_per_sm")},
         "wall_ms_per_step": wall / args.steps * 1e3,
         "e2e": {"value": e2e_value, "unit": "pair-evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "api": "keops_b200.torch.Genred (pinned host buffers -> device -> result back to host)"},
+                "api": "ShardedGenred / Genred: pinned host slabs -> device -> (all_gather) -> reduction -> result slab back to pinned host"},
         "gpu_launches": int(kernel_launches),
         "clocks": clocks,
         "roofline": {"bound": "sfu", "achieved": achieved, "peak": peak_pairs, "unit": "pair-evals/s",
                      "frac": achieved / peak_pairs,
                      "traffic": NCU_DRAM_BYTES_FWD if (world == 1 and M == M_FULL) else None,
-                     "note": "FP32/SFU roofline (SURVEY 8d): 1 MUFU.EX2 per pair at 16/clk/SM x 148 SM x %.0f MHz (max SM clock, %s)"
-                             % (sm_hz / 1e6, peaks_src),
+                     "note": "FP32/SFU roofline (SURVEY 8d): 1 MUFU.EX2 per pair at 16/clk/SM x 148 SM x %.0f MHz (max SM clock, %s); "
+                             "per-GPU: rank 0's rows / rank 0's mean step time" % (sm_hz / 1e6, peaks_src),
                      "kernel": "kb200_reduce", "ms_per_launch": k_ms,
                      "frac_of_measured_mix_ceiling": achieved / (MEASURED_MIX_EX2_PER_CLK_SM * SM_COUNT * sm_hz),
                      "measured_mix_ceiling_note": "micro-benchmark of the same 8 FP32 : 1 EX2 mix reaches 14.83 pairs/clk/SM "
@@ -390,122 +514,144 @@ def main():
         "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": float(peaks.get("hbm_gbs", 6650.0)),
                          "unit": "GB/s", "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
                          "traffic": None, "note": "algorithmic unique bytes 4*(M*3+N*4+M) per launch; the kernel is compute-bound (%s peak)" % peaks_src},
+        "legs": legs,
     }
     if clocks and clocks.get("sm_mhz"):
         line["roofline"]["frac_at_sustained_clock"] = achieved / (ROOFLINE_PAIRS_PER_CLK_SM["gauss_fwd"] * SM_COUNT * clocks["sm_mhz"] * 1e6)
+    for k_ in ("knn", "knn_d64", "lse_softmin", "fwd_bwd", "ksolve"):      # r1 key names kept at top level
+        if k_ in legs:
+            line[k_] = legs[k_]
+    if world > 1:
+        dist.destroy_process_group()       # the other ranks are done; rank 0 goes on alone with the host-side comparators
 
-    if knn_line is not None:
-        line["knn"] = knn_line
-    if not args.no_extras and world == 1:
-        # ---- backward reductions + KNN (device-resident, CUDA events) -----------------------------
-        def time_binder(bd, nrow, ncol, targs, reps=3):
-            o = bd.genred_pytorch(dev, None, nrow, ncol, 0, None, *targs)
-            torch.cuda.synchronize()
-            best = None
-            for _ in range(reps):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                bd.genred_pytorch(dev, None, nrow, ncol, 0, o, *targs)
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1)
-                best = ms if best is None else min(best, ms)
-            return best, o
-        eta = torch.randn(M, 1, device=dev)
-        fwd_ms, fwd = time_binder(binder, M, N, (x, y, b))
-        gx_ms, _ = time_binder(get_binder(GRAD_X, [], 5, "float32"), M, N, (x, y, b, eta, fwd))
-        gy_ms, _ = time_binder(get_binder(GRAD_Y, [], 5, "float32"), M, N, (x, y, b, eta, fwd))
-        pk = ROOFLINE_PAIRS_PER_CLK_SM["gauss_grad"] * SM_COUNT * sm_hz
-        line["fwd_bwd"] = {"value": 3.0 * M * N / ((fwd_ms + gx_ms + gy_ms) * 1e-3), "unit": "pair-evals/s",
-                           "fwd_ms": fwd_ms, "grad_x_ms": gx_ms, "grad_y_ms": gy_ms,
-                           "grad_x_frac_of_roofline": M * N / (gx_ms * 1e-3) / pk,
-                           "grad_y_frac_of_roofline": M * N / (gy_ms * 1e-3) / pk}
-        # ---- the other BASELINE configs at full size: KNN K=10 in D=64 (configs[2]) and the LogSumExp soft-min (configs[3])
-        try:
-            KNN64 = "ArgKMin_Reduction(Sum(Square((Var(0,64,0) - Var(1,64,1)))),10,0)"
-            qx, qy = torch.randn(M, 64, device=dev), torch.randn(N, 64, device=dev)
-            kb64 = get_binder(KNN64, [], 2, "float32")
-            k64_ms, _ = time_binder(kb64, M, N, (qx, qy))
-            line["knn_d64"] = {"metric": "knn_k10_queries_per_s", "value": M / (k64_ms * 1e-3), "unit": "queries/s", "D": 64,
-                               "K": 10, "ms": k64_ms, "pair_evals_per_s": float(M) * N / (k64_ms * 1e-3),
-                               "engine": kb64.last_launch.get("engine") or "cuda-core",
-                               "x_cuda_core_fp32_roofline": float(M) * N / (k64_ms * 1e-3) / (128.0 / 129.0 * SM_COUNT * sm_hz)}
-            del qx, qy
-            LSE = "Max_SumShiftExp_Reduction((Var(0,1,1) - ((Sum(Square((Var(1,3,0) - Var(2,3,1)))) / IntCst(2)) / Var(3,1,2))),0)"
-            lf, lx, ly = torch.rand(N, 1, device=dev), torch.rand(M, 3, device=dev), torch.rand(N, 3, device=dev)
-            lse_ms, _ = time_binder(get_binder(LSE, [], 4, "float32"), M, N, (lf, lx, ly, torch.tensor([0.05], device=dev)))
-            line["lse_softmin"] = {"workload": "LogSumExp soft-min M=N=%d D=3 fp32 (BASELINE configs[3])" % M, "ms": lse_ms,
-                                   "value": float(M) * N / (lse_ms * 1e-3), "unit": "pair-evals/s",
-                                   "frac_of_roofline": float(M) * N / (lse_ms * 1e-3) / (128.0 / 12.0 * SM_COUNT * sm_hz)}
-            del lf, lx, ly
-        except Exception as e:
-            line["knn_d64"] = {"unavailable": str(e)[:300]}
-        # ---- KernelSolve matvec (BASELINE configs[4]): Gaussian kernel, D = 16, one CG iteration = M*N pairs.
-        # Tensor-core path (tcgen05 GEMM for |x-y|^2, MUFU-bound) vs the CUDA-core kernel (FP32-pipe-bound, 34 ops/pair)
-        try:
-            kx, ky = torch.rand(M, 16, device=dev), torch.rand(N, 16, device=dev)
-            kb_, kg = torch.randn(N, 1, device=dev), torch.tensor([1.0], device=dev)
-            ks_b = get_binder(KSOLVE, [], 4, "float32")
-            probe = torch.zeros(2, dtype=torch.int64, device=dev)
-            ks_b.clock_probe = probe
-            tc_ms, o_tc = time_binder(ks_b, M, N, (kx, ky, kb_, kg))
-            engine, ebound = ks_b.last_launch.get("engine"), ks_b.last_launch.get("error_bound")
-            cyc, ns = (int(v) for v in probe.tolist())
-            real_hz = cyc / (ns * 1e-9) if ns > 0 else None
-            os.environ["KB200_CONV_TC"] = "0"
-            try:
-                cc_ms, o_cc = time_binder(ks_b, M, N, (kx, ky, kb_, kg), reps=1)
-            finally:
-                os.environ.pop("KB200_CONV_TC", None)
-            mufu_peak = 16.0 * SM_COUNT
-            line["ksolve_matvec"] = {
-                "workload": "Gaussian kernel matvec D=16 M=N=%d fp32 (one KernelSolve CG iteration)" % M,
-                "value": M * N / (tc_ms * 1e-3), "unit": "pair-evals/s", "ms": tc_ms, "engine": engine,
-                "cuda_core_ms": cc_ms, "speedup_vs_cuda_core": cc_ms / tc_ms,
-                "max_rel_diff_vs_cuda_core": float((o_tc - o_cc).abs().max() / o_cc.abs().max()),
-                "error_bound": ebound,
-                "roofline": {"bound": "sfu", "note": "1 MUFU.EX2 per pair at 16/clk/SM (measured 15.9, experiments/mufu_peak.py)",
-                             "frac_at_max_clock": M * N / (tc_ms * 1e-3) / (mufu_peak * sm_hz),
-                             "sm_clock_hz_measured_in_kernel": real_hz,
-                             "frac_at_measured_clock": (M * N / (tc_ms * 1e-3) / (mufu_peak * real_hz)) if real_hz else None},
-                "cuda_core_frac_of_fp32_roofline": M * N / (cc_ms * 1e-3) / (128.0 / 34.0 * SM_COUNT * sm_hz)}
-            del kx, ky, kb_, o_tc, o_cc
-        except Exception as e:
-            line["ksolve_matvec"] = {"unavailable": str(e)[:300]}
-        # ---- the reference's own CUDA kernel on the same GPU ---------------------------------------
-        try:
-            from oracle import ref_runner
-            if ref_runner.available():
-                rc = ref_runner.RefCuda("gauss_fwd_f32", local_rank)
-                o = rc([x, y, b], M, N)
-                torch.cuda.synchronize()
-                best = None
-                for _ in range(2):
-                    flush.zero_()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    rc([x, y, b], M, N, out=o)
-                    e1.record()
-                    torch.cuda.synchronize()
-                    ms = e0.elapsed_time(e1)
-                    best = ms if best is None else min(best, ms)
-                err = float((o - fwd).abs().max() / fwd.abs().max())
-                line["ref_cuda"] = {"value": M * N / (best * 1e-3), "unit": "pair-evals/s", "ms": best,
-                                    "kernel": "reference GpuConv1DOnDevice (GpuReduc1D, block 192, -use_fast_math), same GPU",
-                                    "max_rel_diff_vs_ours": err, "speedup_ours": best / fwd_ms}
-        except Exception as e:  # comparator only
-            line["ref_cuda"] = {"unavailable": str(e)[:200]}
+    if not args.no_extras:
+        # ---- the reference CPU code beside it, at EVERY N (rank 0's host cores; OpenMP thread count set explicitly) ------
         try:
             cb = reference_cpu_rate(12.0)
             if cb is not None:
-                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "omp_max_threads", "host_cores")}
         except Exception as e:
-            line["cpu_baseline"] = {"unavailable": str(e)[:200]}
+            line["cpu_baseline"] = {"unavailable": repr(e)[:200]}
+    if not args.no_extras and world == 1:
+        try:
+            line["parity"] = parity_report(torch, dev, cx, M, N, (hx, hy, hb, heta), line)
+        except Exception as e:
+            line["parity"] = {"unavailable": repr(e)[:300]}
     emit_json(line)
-    if world > 1:
-        dist.destroy_process_group()
     return 0
+
+
+def parity_report(torch, dev, cx, M, N, host, line):
+    """Achieved errors of every BASELINE config at full size against the reference's own code: its generated CPU code on a
+    sample of output rows and its generated CUDA kernel on all rows (oracle/_ref).  Sum-type outputs: max over entries of
+    |ours - ref| / sum_j |F_ij| (the condition scale, evaluated by an Abs-reduction on the GPU); LogSumExp: max relative
+    error of m + log s; K-min: number of differing indices.  Also times the reference CUDA kernels (``ref_cuda``)."""
+    import numpy as np
+    from keops_b200.binder import get_binder
+    from oracle import ref_runner
+    if not ref_runner.available():
+        return {"unavailable": "oracle/_ref not built"}
+    from keops_b200.formulas.parser import parse_reduction
+    hx, hy, hb, heta = host
+    x, y, b, eta = (t.to(dev) for t in (hx, hy, hb, heta))
+    rep = {"definition": "sum-type: max |ours-ref| / sum_j|F_ij|; lse: max rel. error of m+log(s); knn: differing indices / compared",
+           "cpu_sample_rows": 256}
+    rows = np.sort(np.random.default_rng(3).choice(M, size=256, replace=False))
+    rsel = torch.from_numpy(rows).to(dev)
+
+    def run(formula, nargs, *targs, dtype="float32"):
+        o = get_binder(formula, [], nargs, dtype).genred_pytorch(dev, None, M, N, 0, None, *targs)
+        torch.cuda.synchronize()
+        return o
+
+    def abs_scale(formula, nargs, *targs):
+        red = parse_reduction(formula, [])
+        return run("Sum_Reduction(Abs(%r),%d)" % (red.formula, red.tagI), nargs, *targs)
+
+    def ref_cuda(key, targs, reps=1):
+        rc = ref_runner.RefCuda(key, dev.index or 0)
+        o = rc(targs, M, N)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            cx.flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc(targs, M, N, out=o)
+            e1.record()
+            torch.cuda.synchronize()
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        return o, best
+
+    def sum_case(name, key, formula, nargs, targs, i_pos):
+        ours = run(formula, nargs, *targs)
+        sc = abs_scale(formula, nargs, *targs)
+        tagI = parse_reduction(formula, []).tagI
+        entry = {}
+        refc, ms = ref_cuda(key, list(targs), reps=2 if name == "gauss_fwd" else 1)
+        entry["vs_ref_cuda_all_rows"] = float(((ours - refc).abs() / sc).max())
+        entry["ref_cuda_ms"] = ms
+        if tagI == 0:                      # CPU sample: restrict the i-indexed arrays to the sampled rows
+            sub = [t[rsel].cpu().numpy() if k in i_pos else t.cpu().numpy() for k, t in enumerate(targs)]
+            cpu = ref_runner.run_cpu(key, sub, len(rows), N)
+            entry["vs_ref_cpu_sampled_rows"] = float(((ours[rsel].cpu() - torch.from_numpy(cpu)).abs() / sc[rsel].cpu()).max())
+        rep[name] = entry
+        return ours, ms
+
+    fwd, fwd_ref_ms = sum_case("gauss_fwd", "gauss_fwd_f32", GAUSS, 3, (x, y, b), {0})
+    sum_case("gauss_grad_x", "gauss_dx_f32", GRAD_X, 5, (x, y, b, eta, fwd), {0, 3, 4})
+    sum_case("gauss_grad_y", "gauss_dy_f32", GRAD_Y, 5, (x, y, b, eta, fwd), {0, 3, 4})
+    ours_ms = line["roofline"]["ms_per_launch"]
+    line["ref_cuda"] = {"value": M * N / (fwd_ref_ms * 1e-3), "unit": "pair-evals/s", "ms": fwd_ref_ms,
+                        "kernel": "reference GpuConv1DOnDevice (GpuReduc1D, block 192, -use_fast_math), same GPU",
+                        "max_err_vs_ours_over_condition_scale": rep["gauss_fwd"]["vs_ref_cuda_all_rows"],
+                        "speedup_ours": fwd_ref_ms / ours_ms}
+    # K-min: indices
+    for D, key in ((3, "argkmin10_d3_f32"), (64, "argkmin10_d64_f32")):
+        gg = torch.Generator(device=dev).manual_seed(D)
+        q, d = torch.randn(M, D, generator=gg, device=dev), torch.randn(N, D, generator=gg, device=dev)
+        f = "ArgKMin_Reduction(Sum(Square((Var(0,%d,0) - Var(1,%d,1)))),10,0)" % (D, D)
+        ours = run(f, 2, q, d)
+        cpu = ref_runner.run_cpu(key, [q[rsel].cpu().numpy(), d.cpu().numpy()], len(rows), N)
+        entry = {"vs_ref_cpu_sampled_rows": "%d / %d" % (int((ours[rsel].cpu() != torch.from_numpy(cpu)).sum()), cpu.size)}
+        nq = M if D == 3 else 50000
+        rc = ref_runner.RefCuda(key, dev.index or 0)
+        refc = rc([q[:nq].contiguous(), d], nq, N)
+        torch.cuda.synchronize()
+        entry["vs_ref_cuda"] = "%d / %d" % (int((ours[:nq] != refc).sum()), refc.numel())
+        rep["knn_d%d" % D] = entry
+        del q, d
+    # LogSumExp fp32 / fp64
+    for dtype, key in (("float32", "lse_f32"), ("float64", "lse_f64")):
+        tdt = torch.float32 if dtype == "float32" else torch.float64
+        gg = torch.Generator(device=dev).manual_seed(7)
+        lf = torch.rand(N, 1, generator=gg, device=dev, dtype=tdt)
+        lx, ly = torch.rand(M, 3, generator=gg, device=dev, dtype=tdt), torch.rand(N, 3, generator=gg, device=dev, dtype=tdt)
+        eps = torch.tensor([0.05], device=dev, dtype=tdt)
+        ms_ = run(LSE, 4, lf, lx, ly, eps, dtype=dtype)
+        ours = ms_[:, 0] + ms_[:, 1].log()
+        cpu = ref_runner.run_cpu(key, [lf.cpu().numpy(), lx[rsel].cpu().numpy(), ly.cpu().numpy(), eps.cpu().numpy()], len(rows), N)
+        refv = torch.from_numpy(cpu[:, 0] + np.log(cpu[:, 1]))
+        entry = {"vs_ref_cpu_sampled_rows": float(((ours[rsel].cpu() - refv).abs() / refv.abs()).max())}
+        if dtype == "float32":
+            refc, _ = ref_cuda(key, [lf, lx, ly, eps])
+            rv = refc[:, 0] + refc[:, 1].log()
+            entry["vs_ref_cuda_all_rows"] = float(((ours - rv).abs() / rv.abs()).max())
+        rep["lse_" + dtype] = entry
+        del lf, lx, ly
+    # KernelSolve matvec, D = 16 (tensor-core path, stated tolerance 5e-6)
+    gg = torch.Generator(device=dev).manual_seed(16)
+    kx, kb_ = torch.rand(M, 16, generator=gg, device=dev), torch.randn(M, 1, generator=gg, device=dev)
+    kg = torch.tensor([1.0], device=dev)
+    ours = run(KSOLVE, 4, kx, kx, kb_, kg)
+    sc = abs_scale(KSOLVE, 4, kx, kx, kb_, kg)
+    cpu = ref_runner.run_cpu("gauss16_pm_f32", [kx[rsel].cpu().numpy(), kx.cpu().numpy(), kb_.cpu().numpy(), kg.cpu().numpy()], len(rows), N)
+    entry = {"vs_ref_cpu_sampled_rows": float(((ours[rsel].cpu() - torch.from_numpy(cpu)).abs() / sc[rsel].cpu()).max())}
+    refc, ms = ref_cuda("gauss16_pm_f32", [kx, kx, kb_, kg])
+    entry["vs_ref_cuda_all_rows"] = float(((ours - refc).abs() / sc).max())
+    entry["ref_cuda_ms"] = ms
+    rep["ksolve_matvec_d16"] = entry
+    return rep
 
 
 if __name__ == "__main__":

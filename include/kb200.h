@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB200_ABI_VERSION 3
+#define KB200_ABI_VERSION 4
 
 #define KB200_OK 0
 #define KB200_ENOCUDA 20001  /* libcuda.so.1 could not be loaded / cuInit failed        */
@@ -129,6 +129,17 @@ int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, voi
                         int64_t nrow, int64_t ncol, int rows_per_block, int block, int nsplit,
                         int64_t col_chunk, void* out, void* workspace, int nargs,
                         const void* const* args, int nbatch, const int64_t* batch_strides);
+
+/* Same launch with `dynamic_smem_bytes` of dynamic shared memory for kb200_reduce: kernels whose staged tile exceeds the
+ * 48 KB static limit (streamed rows of several hundred reals) declare it `extern __shared__` and are opted in with
+ * kb200_function_set_max_dynamic_smem.  The reference sizes its tile as blockDim * dimY * sizeof(T) of dynamic shared
+ * memory under a 48 KB assumption and shrinks the block size to fit (keopscore/keopscore/binders/nvrtc/keops_nvrtc.cpp:441-458,
+ * keopscore/keopscore/include/CudaSizes.h:11-31).                                                                     */
+int kb200_genred_launch_smem(kb200_function reduce_fn, kb200_function combine_fn, void* stream,
+                             int64_t nrow, int64_t ncol, int rows_per_block, int block, int nsplit,
+                             int64_t col_chunk, void* out, void* workspace, int nargs,
+                             const void* const* args, int nbatch, const int64_t* batch_strides,
+                             unsigned dynamic_smem_bytes);
 
 /* Block-sparse map-reduce launch: row-range k = rows [ranges_x[2k], ranges_x[2k+1]) is reduced over the
  * union of the column ranges ranges_y[2l .. 2l+1], l in [slices_x[k-1], slices_x[k]) (slices_x[-1] = 0).

@@ -425,7 +425,8 @@ class LoadKeOpsB200:
                     ptrs = [a.data_ptr() + (b0 * strides[k] + r0 * row_dims.get(k, 0)) * esz for k, a in enumerate(args)]
                     capi.genred_launch(lk.fn_reduce, lk.fn_combine, stream, nseg, ncol, rows_per_block, ks.cfg.T,
                                        nsplit, max(col_chunk, 1), out_flat[b0].data_ptr() + r0 * p.dim * esz,
-                                       ws.data_ptr() if ws is not None else 0, ptrs, bn, strides)
+                                       ws.data_ptr() if ws is not None else 0, ptrs, bn, strides,
+                                       dynamic_smem=ks.dynamic_smem)
                     launches += 2 if nsplit > 1 else 1
                     if ws is not None:
                         ws.record_stream(torch.cuda.current_stream(dev))
@@ -455,13 +456,13 @@ class LoadKeOpsB200:
             ptrs = [a.data_ptr() + r0 * row_dims.get(k, 0) * esz for k, a in enumerate(args)]
             if nsplit == 1:          # nothing to share: the plain entry point (fewer registers)
                 capi.genred_launch(lk.fn_reduce, lk.fn_combine, stream, nseg, ncol, rows_per_block, T, 1,
-                                   max(col_chunk, 1), out_ptr, 0, ptrs, 1, strides)
+                                   max(col_chunk, 1), out_ptr, 0, ptrs, 1, strides, dynamic_smem=ks.dynamic_smem)
                 count += 1
                 continue
             params = [i64(nseg), i64(ncol), i64(max(col_chunk, 1)), ptr(out_ptr), ptr(ws.data_ptr() if ws is not None else 0)]
             params += [ptr(q) for q in ptrs] + [i64(int(st)) for st in strides]
             params += [ptr(shthr.data_ptr() + r0 * d * esz), i32(0)]
-            capi.launch(lk.fn_seeded, stream, (-(-nseg // rows_per_block), nsplit, 1), (T,), 0, params)
+            capi.launch(lk.fn_seeded, stream, (-(-nseg // rows_per_block), nsplit, 1), (T,), ks.dynamic_smem, params)
             count += 1
             if nsplit > 1:
                 capi.launch(lk.fn_combine, stream, (-(-nseg // 256), 1, 1), (256,), 0,
@@ -499,6 +500,9 @@ class LoadKeOpsB200:
         if nranges == 0:
             return out
         lk = self._kernel_ranges(dev.index if dev.index is not None else torch.cuda.current_device())
+        if self.ks_ranges.dynamic_smem:
+            raise ValueError("[KeOps-B200] block-sparse reductions are limited to streamed rows that fit 48 KB of shared memory "
+                             "(%d components here)." % self.ks_ranges.stride)
         cfg = self.ks_ranges.cfg
         rpb = cfg.T * cfg.R
         key = (rx_user.data_ptr(), rx_user._version, nranges, rpb)
@@ -537,7 +541,14 @@ def get_binder(formula: str, aliases: Sequence[str], nargs: int, dtype: str, opt
 def register_into_pykeops():
     """Install this engine as the GPU binder of an importable reference ``pykeops``:
     ``keops_binder['nvrtc'] = LoadKeOpsB200`` (``pykeops/pykeops/common/keops_io/__init__.py:6-13``)."""
+    import pykeops  # type: ignore
     from pykeops.common import keops_io  # type: ignore
 
     keops_io.keops_binder["nvrtc"] = LoadKeOpsB200
+    # The reference resolves backend="auto"/"GPU" through ``pykeops.config.gpu_available``
+    # (``pykeops/pykeops/common/get_options.py:84-86``), which it sets from its OWN CUDA probing (libcuda + libnvrtc found by
+    # ``ctypes.util.find_library`` and its nvrtc binder built, ``keopscore/keopscore/config/cuda.py:117-150``).  This engine is
+    # the GPU backend now, so availability follows the CUDA driver this engine uses.
+    if torch.cuda.is_available():
+        pykeops.config.gpu_available = True
     return keops_io.keops_binder

@@ -26,6 +26,7 @@ from .lower import Lowerer
 from .scalar import Graph, SNode, SV, C, P, I, J, IJ, topo_order
 
 GENERATOR_VERSION = "kb200-gen-5"
+MAX_SMEM_BYTES = 227 * 1024        # per-CTA shared memory on sm_100a (opt-in maximum)
 
 _PRELUDE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "kb200_device.cuh")
 _prelude_cache: Optional[str] = None
@@ -72,6 +73,7 @@ class KernelSource:
     smem_bytes: int
     is_zero: bool = False
     hash: str = ""
+    dynamic_smem: int = 0  # > 0: the staged tile is `extern __shared__` (beyond the 48 KB static limit), launch with this many bytes
 
 
 # ------------------------------------------------------------------------------------------
@@ -381,6 +383,17 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
         W("}")
 
     arg_decl = "".join(", const real* __restrict__ a%d_" % k for k in range(nargs))
+    smem_bytes = 2 * cfg.TJ * stride * (8 if f64 else 4)
+    dynamic_smem = smem_bytes if smem_bytes > 48 * 1024 else 0
+    if dynamic_smem > MAX_SMEM_BYTES:
+        raise FormulaError("the streamed variables have %d components in total: one double-buffered tile of %d rows does not "
+                           "fit the %d KB of shared memory of an SM" % (stride, cfg.TJ, MAX_SMEM_BYTES // 1024))
+    if dynamic_smem:
+        # beyond the 48 KB static limit the tile is dynamic shared memory (opt-in up to 227 KB per CTA on sm_100a)
+        sm_decl = ("extern __shared__ __align__(16) real kb_sm_dyn[]; "
+                   "real (*sm)[KB_TJ * KB_STRIDE] = reinterpret_cast<real (*)[KB_TJ * KB_STRIDE]>(kb_sm_dyn);")
+    else:
+        sm_decl = "__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];"
     if not ranges:
         # ---------------- dense kernel ----------------
         stride_decl = "".join(", const long long bs%d" % k for k in range(nargs))
@@ -397,7 +410,7 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
               % (kname, arg_decl, stride_decl))
         W("{")
         W.indent()
-        W("__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
+        W(sm_decl)
         W("const int tid = threadIdx.x;")
         W("// batch index = blockIdx.z; bs<k> is the element stride of argument k between batches (0 = shared)")
         for k in range(nargs):
@@ -445,7 +458,7 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
           % (kname, arg_decl))
         W("{")
         W.indent()
-        W("__shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
+        W(sm_decl)
         W("const int tid = threadIdx.x;")
         for k in range(nargs):
             W("const real* __restrict__ a%d = a%d_;" % (k, k))
@@ -483,7 +496,7 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
     src = hdr + W.text()
     h = hashlib.sha256((GENERATOR_VERSION + src).encode()).hexdigest()[:16]
     return KernelSource(source=src, kernel_name=kname, combine_name=cname, dimpart=red_code.dimpart,
-                        stride=stride, smem_bytes=2 * cfg.TJ * stride * (8 if f64 else 4), hash=h, **base)
+                        stride=stride, smem_bytes=smem_bytes, hash=h, dynamic_smem=dynamic_smem, **base)
 
 
 @dataclass

@@ -24,7 +24,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_knn_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")      # PTX wrappers, prepended (NVRTC has no include path)
-VERSION = "knn-tc-7"
+VERSION = "knn-tc-8"
 BM, BN, STAGES, HS = 256, 128, 4, 16
 ROW_BATCH = 1 << 20          # rows per filter launch: bounds the candidate workspace (CAP * 4 bytes per row)
 _lock = threading.RLock()
@@ -89,6 +89,7 @@ class KnnTensorCore:
         self.STAGES = int(os.environ.get("KT_STAGES", STAGES if self.BN == 128 else 6))
         defs += "#define KT_BN %d\n#define KT_STAGES %d\n#define KT_DBG %d\n" % (self.BN, self.STAGES, int(os.environ.get("KT_DBG", 0)))
         defs += "#define KT_SPIN %d\n" % int(os.environ.get("KT_SPIN", 0))
+        defs += "#define KT_PIPE %d\n" % int(os.environ.get("KT_PIPE", 1))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(fast), "kb200_knntc", VERSION)
         blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K
@@ -133,6 +134,8 @@ class KnnTensorCore:
         nsplit = 1
         if os.environ.get("KB200_KNN_TC_SPLIT", "1") != "0" and nblocks < self.sm_count:
             nsplit = max(1, min(self.sm_count // nblocks, ntiles // 64, 32))
+        if os.environ.get("KB200_KNN_TC_NSPLIT"):          # experiments: forced column chunks (L2-sized y slabs)
+            nsplit = max(1, min(int(os.environ["KB200_KNN_TC_NSPLIT"]), ntiles))
         tiles_per_split = -(-ntiles // nsplit)
         nsplit = -(-ntiles // tiles_per_split)
         overflow_count = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -52,6 +52,9 @@
 #ifndef KT_BN
 #define KT_BN 128                             /* columns per tile (= N of one tcgen05.mma): 64 or 128           */
 #endif
+#ifndef KT_PIPE
+#define KT_PIPE 1                             /* 1: software-pipelined TMEM reads in the filter's epilogue       */
+#endif
 #ifndef KT_DBG
 #define KT_DBG 0                              /* 1: no rare path, 2: TMEM loads only, 3: no TMEM loads (timing experiments) */
 #endif
@@ -235,6 +238,92 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
     int cnt = 0;
     int* my_cand = cand + ((live ? i : 0) * (long long)gridDim.y + blockIdx.y) * (long long)KT_CAP;
     const float cy_scale = 2.0f * KT_C / (1.0f - KT_C);   // c|y|^2 = cy_scale * (1-c)|y|^2/2
+    // One 64-column chunk of a tile: FMNMX max-reduction against tau_i, rare path for the survivors.
+    auto process = [&](const float* u, const int t, const int c, const float* hyt, const int hslot, bool& hy_ready) {
+      float mg[8];                                    // maxima of the eight 8-column sub-groups
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        float m = fmaxf(fmaxf(u[8 * g + 0], u[8 * g + 1]), u[8 * g + 2]);
+        m = fmaxf(fmaxf(m, u[8 * g + 3]), u[8 * g + 4]);
+        m = fmaxf(fmaxf(m, u[8 * g + 5]), u[8 * g + 6]);
+        mg[g] = fmaxf(m, u[8 * g + 7]);
+      }
+      const float m01 = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
+      const float m23 = fmaxf(fmaxf(mg[4], mg[5]), fmaxf(mg[6], mg[7]));
+#if KT_DBG >= 2
+      if (fmaxf(m01, m23) == 12345.678f) cnt++;
+#endif
+      if (KT_DBG == 0 && fmaxf(m01, m23) >= tau) {
+        // rare path (a few hundred times per row over the whole stream): everything statically indexed
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+          if (mg[g] >= tau) {
+            u32 hits = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) hits |= (u[8 * g + e] >= tau) ? (1u << e) : 0u;
+            const long long j0 = (long long)(t0 + t) * KT_BN + c * 64 + g * 8;
+            while (hits) {
+              const int e = __ffs(hits) - 1;
+              hits &= hits - 1;
+              // 8 -> 1 select tree instead of a dynamically indexed (local-memory) array
+              const float a0 = (e & 1) ? u[8 * g + 1] : u[8 * g + 0], a1 = (e & 1) ? u[8 * g + 3] : u[8 * g + 2];
+              const float a2 = (e & 1) ? u[8 * g + 5] : u[8 * g + 4], a3 = (e & 1) ? u[8 * g + 7] : u[8 * g + 6];
+              const float b0 = (e & 2) ? a1 : a0, b1 = (e & 2) ? a3 : a2;
+              const float ue = (e & 4) ? b1 : b0;
+              if (ue >= tau && j0 + e < ncol) {
+                if (cnt < KT_CAP) my_cand[cnt] = (int)(j0 + e);
+                cnt++;
+                if (!hy_ready) { kt_mbar_wait(bHFull + 8 * hslot, (t / KT_HS) & 1); hy_ready = true; }
+                const float lo = ue - cy_scale * hyt[c * 64 + g * 8 + e];
+                if (lo > lst[KT_K - 1]) {
+#pragma unroll
+                  for (int l = KT_K - 1; l > 0; --l) {
+                    if (lo > lst[l - 1]) lst[l] = lst[l - 1];
+                    else if (lo > lst[l]) lst[l] = lo;
+                  }
+                  if (lo > lst[0]) lst[0] = lo;
+                  tau = lst[KT_K - 1] - cx;
+                }
+              }
+            }
+          }
+        }
+      }
+    };
+#if KT_PIPE && KT_BN == 128 && KT_DBG < 3
+    // Software-pipelined TMEM reads (ncu of the un-pipelined loop: every epilogue warp idles ~2.4 cycles per issued
+    // instruction on the tcgen05.ld round trip -- long_scoreboard -- with only two such warps per scheduler): the 64-column
+    // half that is processed next is always in flight while the current one is reduced, across tile boundaries too.
+    // uA / uB are two statically indexed register buffers; tcgen05.wait::ld retires every load issued so far.
+    float uA[64], uB[64];
+    if (ntiles > 0) {
+      kt_mbar_wait(bTFull + 8 * (0 * 2 + rb), 0);
+      kt_fence_after();
+      kt_tmem_ld64_nowait(tmem + ((u32)(q * 32) << 16) + (u32)((0 * 2 + rb) * KT_BN), uA);
+    }
+    for (int t = 0; t < ntiles; t++) {
+      const int buf = t % KT_NBUF, hslot = t % KT_HS;
+      const float* hyt = hy + hslot * KT_BN;
+      bool hy_ready = false;                          // the penalty tile is waited for on first use only
+      const u32 tbase = tmem + ((u32)(q * 32) << 16) + (u32)((buf * 2 + rb) * KT_BN);
+      kt_tmem_wait_ld();                              // uA = columns 0..63 of tile t
+      kt_tmem_ld64_nowait(tbase + 64u, uB);           // columns 64..127 fly while uA is reduced
+      process(uA, t, 0, hyt, hslot, hy_ready);
+      kt_tmem_wait_ld();                              // uB landed: the accumulator buffer goes back to the MMA warp
+      kt_fence_before();
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));
+      if (t + 1 < ntiles) {
+        const int nb = (t + 1) % KT_NBUF;
+        kt_mbar_wait(bTFull + 8 * (nb * 2 + rb), ((t + 1) / KT_NBUF) & 1);
+        kt_fence_after();
+        kt_tmem_ld64_nowait(tmem + ((u32)(q * 32) << 16) + (u32)((nb * 2 + rb) * KT_BN), uA);
+      }
+      process(uB, t, 1, hyt, hslot, hy_ready);
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
+    }
+#else
     for (int t = 0; t < ntiles; t++) {
       const int buf = t % KT_NBUF, hslot = t % KT_HS;
       kt_mbar_wait(bTFull + 8 * (buf * 2 + rb), (t / KT_NBUF) & 1);
@@ -257,61 +346,11 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));
 #pragma unroll
-      for (int c = 0; c < KT_BN / 64; c++) {
-        float* u = uu + c * 64;                       // U_ij of 64 columns (the penalty is already inside)
-        float mg[8];                                  // maxima of the eight 8-column sub-groups
-#pragma unroll
-        for (int g = 0; g < 8; g++) {
-          float m = fmaxf(fmaxf(u[8 * g + 0], u[8 * g + 1]), u[8 * g + 2]);
-          m = fmaxf(fmaxf(m, u[8 * g + 3]), u[8 * g + 4]);
-          m = fmaxf(fmaxf(m, u[8 * g + 5]), u[8 * g + 6]);
-          mg[g] = fmaxf(m, u[8 * g + 7]);
-        }
-        const float m01 = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
-        const float m23 = fmaxf(fmaxf(mg[4], mg[5]), fmaxf(mg[6], mg[7]));
-#if KT_DBG >= 2
-        if (fmaxf(m01, m23) == 12345.678f) cnt++;
-#endif
-        if (KT_DBG == 0 && fmaxf(m01, m23) >= tau) {
-          // rare path (a few hundred times per row over the whole stream): everything statically indexed
-#pragma unroll
-          for (int g = 0; g < 8; g++) {
-            if (mg[g] >= tau) {
-              u32 hits = 0;
-#pragma unroll
-              for (int e = 0; e < 8; e++) hits |= (u[8 * g + e] >= tau) ? (1u << e) : 0u;
-              const long long j0 = (long long)(t0 + t) * KT_BN + c * 64 + g * 8;
-              while (hits) {
-                const int e = __ffs(hits) - 1;
-                hits &= hits - 1;
-                // 8 -> 1 select tree instead of a dynamically indexed (local-memory) array
-                const float a0 = (e & 1) ? u[8 * g + 1] : u[8 * g + 0], a1 = (e & 1) ? u[8 * g + 3] : u[8 * g + 2];
-                const float a2 = (e & 1) ? u[8 * g + 5] : u[8 * g + 4], a3 = (e & 1) ? u[8 * g + 7] : u[8 * g + 6];
-                const float b0 = (e & 2) ? a1 : a0, b1 = (e & 2) ? a3 : a2;
-                const float ue = (e & 4) ? b1 : b0;
-                if (ue >= tau && j0 + e < ncol) {
-                  if (cnt < KT_CAP) my_cand[cnt] = (int)(j0 + e);
-                  cnt++;
-                  if (!hy_ready) { kt_mbar_wait(bHFull + 8 * hslot, (t / KT_HS) & 1); hy_ready = true; }
-                  const float lo = ue - cy_scale * hyt[c * 64 + g * 8 + e];
-                  if (lo > lst[KT_K - 1]) {
-#pragma unroll
-                    for (int l = KT_K - 1; l > 0; --l) {
-                      if (lo > lst[l - 1]) lst[l] = lst[l - 1];
-                      else if (lo > lst[l]) lst[l] = lo;
-                    }
-                    if (lo > lst[0]) lst[0] = lo;
-                    tau = lst[KT_K - 1] - cx;
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
+      for (int c = 0; c < KT_BN / 64; c++) process(uu + c * 64, t, c, hyt, hslot, hy_ready);
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
     }
+#endif
     if (live) cand_count[i * (long long)gridDim.y + blockIdx.y] = cnt;
   }
   kt_fence_before();

@@ -389,6 +389,14 @@ int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, voi
                         int64_t ncol, int rows_per_block, int block, int nsplit, int64_t col_chunk, void* out,
                         void* workspace, int nargs, const void* const* args, int nbatch,
                         const int64_t* batch_strides) {
+  return kb200_genred_launch_smem(reduce_fn, combine_fn, stream, nrow, ncol, rows_per_block, block, nsplit, col_chunk, out,
+                                  workspace, nargs, args, nbatch, batch_strides, 0u);
+}
+
+int kb200_genred_launch_smem(kb200_function reduce_fn, kb200_function combine_fn, void* stream, int64_t nrow,
+                             int64_t ncol, int rows_per_block, int block, int nsplit, int64_t col_chunk, void* out,
+                             void* workspace, int nargs, const void* const* args, int nbatch,
+                             const int64_t* batch_strides, unsigned dynamic_smem_bytes) {
   int st = driver();
   if (st) return st;
   if (!reduce_fn || !out || rows_per_block <= 0 || block <= 0 || nsplit <= 0 || nargs < 0 || nargs > 60 ||
@@ -416,7 +424,7 @@ int kb200_genred_launch(kb200_function reduce_fn, kb200_function combine_fn, voi
   }
   unsigned gx = (unsigned)((nrow + rows_per_block - 1) / rows_per_block);
   CU_TRY(g_drv.LaunchKernel(reinterpret_cast<CUfunction>(reduce_fn), gx, (unsigned)nsplit, (unsigned)nbatch, (unsigned)block,
-                            1, 1, 0, reinterpret_cast<CUstream>(stream), params, nullptr),
+                            1, 1, dynamic_smem_bytes, reinterpret_cast<CUstream>(stream), params, nullptr),
          "cuLaunchKernel(kb200_reduce)");
   if (nsplit > 1) {
     int ns = nsplit;

@@ -54,22 +54,51 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tens
     return torch.cat([full[r * hmax: r * hmax + (b - a)] for r, (a, b) in enumerate(sizes)], dim=0)
 
 
+def _replicate(a, k, cat_dims, n_total, mode, src, ref, group):
+    """One streamed operand made complete on every rank: all_gather of row slabs / broadcast from ``src`` / already there."""
+    if mode == "replicated":
+        return a
+    if n_total is None:
+        raise ValueError("the global size of the gathered index is required")
+    if mode == "all_gather":
+        return all_gather_rows(a, n_total, group)
+    if mode != "broadcast":
+        raise ValueError("mode must be 'all_gather', 'broadcast' or 'replicated'")
+    rank = dist.get_rank(group)
+    if rank == src:
+        buf = a.contiguous()
+    else:
+        buf = torch.empty((n_total, cat_dims[k]), dtype=ref.dtype, device=ref.device)
+    dist.broadcast(buf, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    return buf
+
+
 class ShardedGenred:
     """``ShardedGenred(formula, aliases, reduction_op, axis, ...)(*local_args, n_streamed=N, mode=...)``.
 
     ``local_args``: output-side variables = this rank's row slab; streamed variables = this rank's slab
     (``mode="all_gather"``), the full array on ``src`` and anything/None elsewhere (``mode="broadcast"``),
-    or the full array everywhere (``mode="replicated"``); parameters = full.  Returns this rank's slab
+    or the full array everywhere (``mode="replicated"``); parameters = full.  ``mode`` may also be a dict
+    ``{argument position: mode}`` (other streamed arguments: ``"all_gather"``), e.g. a point cloud that was replicated
+    once and a vector that changes every call.  Returns this rank's slab
     of the output.  ``compute`` (default: the CUDA ``Genred``) is injectable so that the sharding and
-    collective logic can be tested on CPU with the ``gloo`` backend."""
+    collective logic can be tested on CPU with the ``gloo`` backend.
+
+    ``gradient(var)`` returns the reduction the reference's backward would launch for that input
+    (``Grad_WithSavedForward``, ``pykeops/pykeops/torch/generic/generic_red.py:190-214``), sharded by the *differentiated
+    variable's own index*: a gradient w.r.t. a streamed variable ``y_j`` is a reduction over ``i`` whose output is indexed by
+    ``j`` (``keopscore/keopscore/formulas/reductions/Sum_Reduction.py:42-45``), so every rank produces its own slab of
+    ``d/dy`` from its slab of ``y`` and the gathered ``i``-side arrays -- still no cross-GPU reduction."""
 
     def __init__(self, formula: str, aliases: Sequence[str], reduction_op: str = "Sum", axis: int = 0,
                  group=None, compute: Optional[Callable] = None, **genred_kwargs):
         self.formula, self.reduction_op, self.axis = formula, reduction_op, axis
         self.group = group
         red_internal, formula2 = preprocess(reduction_op, genred_kwargs.get("formula2"))
-        probe = "%s_Reduction(%s,%d%s)" % (red_internal, formula, axis2cat(axis), ",%s" % formula2 if formula2 else "")
-        self.aliases = complete_aliases(probe, list(aliases))
+        opt_arg = genred_kwargs.get("opt_arg")
+        self.red_formula = "%s_Reduction(%s%s,%d%s)" % (red_internal, formula, ",%s" % opt_arg if opt_arg else "",
+                                                       axis2cat(axis), ",%s" % formula2 if formula2 else "")
+        self.aliases = complete_aliases(self.red_formula, list(aliases))
         self.cats, self.dims = [], []
         for k, sig in enumerate(self.aliases):
             _, cat, dim, pos = get_type(sig, position_in_list=k)
@@ -78,36 +107,97 @@ class ShardedGenred:
             self.cats.append(cat)
             self.dims.append(dim)
         self.out_cat = axis2cat(axis)          # category of the output index
+        self._genred_kwargs = dict(genred_kwargs)
+        self._user_compute = compute is not None
         if compute is None:
             from .torch import Genred
             compute = Genred(formula, list(aliases), reduction_op=reduction_op, axis=axis, **genred_kwargs)
         self.compute = compute
 
-    def __call__(self, *local_args, n_streamed: Optional[int] = None, mode: str = "all_gather", src: int = 0,
+    def _mode_of(self, mode, k):
+        if isinstance(mode, dict):
+            return mode.get(k, "all_gather")
+        return mode
+
+    def __call__(self, *local_args, n_streamed: Optional[int] = None, mode="all_gather", src: int = 0,
                  **call_kwargs):
-        if mode not in ("all_gather", "broadcast", "replicated"):
+        if not isinstance(mode, dict) and mode not in ("all_gather", "broadcast", "replicated"):
             raise ValueError("mode must be 'all_gather', 'broadcast' or 'replicated'")
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         args: List[torch.Tensor] = []
         ref = next(a for a, c in zip(local_args, self.cats) if c == self.out_cat and a is not None)
         for k, (a, cat) in enumerate(zip(local_args, self.cats)):
-            if cat == self.out_cat or cat == 2 or world == 1 or mode == "replicated":
+            if cat == self.out_cat or cat == 2 or world == 1:
                 args.append(a)
-                continue
-            if n_streamed is None:
-                raise ValueError("n_streamed (global size of the reduced index) is required")
-            if mode == "all_gather":
-                args.append(all_gather_rows(a, n_streamed, self.group))
             else:
-                if rank == src:
-                    buf = a.contiguous()
-                else:
-                    buf = torch.empty((n_streamed, self.dims[k]), dtype=ref.dtype, device=ref.device)
-                dist.broadcast(buf, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
-                               group=self.group)
-                args.append(buf)
+                args.append(_replicate(a, k, self.dims, n_streamed, self._mode_of(mode, k), src, ref, self.group))
         return self.compute(*args, **call_kwargs)
+
+    def gradient(self, var, compute: Optional[Callable] = None) -> "ShardedGradient":
+        """``var``: position (or alias name) of the input to differentiate with respect to."""
+        if isinstance(var, str):
+            var = [s[:s.find("=")].strip() for s in self.aliases].index(var)
+        return ShardedGradient(self, int(var), compute)
+
+
+class ShardedGradient:
+    """``g = ShardedGenred(...).gradient(var)``; ``g(*local_args, eta_local, fwd_local, n_i=M, n_j=N)`` -> this rank's slab of
+    the gradient of ``<eta, Reduction(...)>`` with respect to input ``var``.
+
+    Every array is row-sharded by its OWN index (``i``-indexed arrays over M, ``j``-indexed ones over N; ``eta`` and the
+    saved forward ``fwd`` follow the forward's output index).  The gradient reduction's output is indexed like ``var``:
+    arrays of that category stay local, the others are all-gathered (``mode``: as for :class:`ShardedGenred`, the positions
+    ``nargs`` / ``nargs + 1`` standing for ``eta`` / ``fwd``).  A gradient w.r.t. a parameter is the sum over all output rows:
+    local reduction + one all-reduce of ``dim`` numbers (the reference sums in Python, ``generic_red.py:216-235``)."""
+
+    def __init__(self, parent: ShardedGenred, var: int, compute: Optional[Callable] = None):
+        from .formulas.parser import parse_reduction
+        from .binder import _normalise_aliases
+        self.parent, self.var = parent, var
+        red = parse_reduction(parent.red_formula, _normalise_aliases(parent.aliases))
+        self.dimout, self.tagIJ = red.dim, red.tagI
+        nargs = len(parent.aliases)
+        cat, dim = parent.cats[var], parent.dims[var]
+        self.var_cat = cat
+        eta = "Var(%d,%d,%d)" % (nargs, self.dimout, self.tagIJ)
+        res = "Var(%d,%d,%d)" % (nargs + 1, self.dimout, self.tagIJ)
+        self.red_formula = "Grad_WithSavedForward(%s,Var(%d,%d,%d),%s,%s)" % (parent.red_formula, var, dim, cat, eta, res)
+        self.aliases = list(parent.aliases) + [eta, res]
+        self.cats = list(parent.cats) + [self.tagIJ, self.tagIJ]
+        self.dims = list(parent.dims) + [self.dimout, self.dimout]
+        # a parameter's gradient is reduced like the forward (output indexed by the forward's index), then summed over rows
+        self.out_cat = cat if cat in (0, 1) else self.tagIJ
+        if compute is None:
+            from .torch.genred import RawReduction
+            from .common import get_optional_flags
+            kw = parent._genred_kwargs
+            red_internal, _ = preprocess(parent.reduction_op, kw.get("formula2"))
+            flags = get_optional_flags(red_internal, kw.get("dtype_acc", "auto"), kw.get("use_double_acc", False),
+                                       kw.get("sum_scheme", "auto"), kw.get("enable_chunks", True), kw.get("use_fast_math", True))
+            compute = RawReduction(self.red_formula, self.aliases, flags)
+        self.compute = compute
+
+    def __call__(self, *local_args, n_i: Optional[int] = None, n_j: Optional[int] = None, mode="all_gather", src: int = 0,
+                 **call_kwargs):
+        if len(local_args) != len(self.aliases):
+            raise ValueError("expected the forward's %d arguments followed by eta and the saved forward" % (len(self.aliases) - 2))
+        group = self.parent.group
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n_of = {0: n_i, 1: n_j}
+        ref = next(a for a, c in zip(local_args, self.cats) if c == self.out_cat and a is not None)
+        args: List[torch.Tensor] = []
+        for k, (a, cat) in enumerate(zip(local_args, self.cats)):
+            if cat == self.out_cat or cat == 2 or world == 1:
+                args.append(a)
+            else:
+                args.append(_replicate(a, k, self.dims, n_of[cat], self.parent._mode_of(mode, k), src, ref, group))
+        g = self.compute(*args, **call_kwargs)
+        if self.var_cat == 2:
+            g = (1.0 * g).sum(-2)
+            if world > 1:
+                dist.all_reduce(g, group=group)
+            g = g.reshape(local_args[self.var].shape)
+        return g
 
 
 class ShardedKernelSolve:

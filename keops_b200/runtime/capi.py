@@ -57,6 +57,7 @@ def _load() -> C.CDLL:
         "kb200_function_set_max_dynamic_smem": (i, [vp, i]),
         "kb200_tensor_map_2d": (i, [vp, i, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, i]),
         "kb200_genred_launch": (i, [vp, vp, vp, i64, i64, i, i, i, i64, vp, vp, i, C.POINTER(vp), i, C.POINTER(i64)]),
+        "kb200_genred_launch_smem": (i, [vp, vp, vp, i64, i64, i, i, i, i64, vp, vp, i, C.POINTER(vp), i, C.POINTER(i64), u]),
         "kb200_genred_launch_ranges": (i, [vp, vp, i64, i64, i, i64, vp, i, C.POINTER(vp), vp, vp, vp, vp, i]),
     }
     for name, (res, args) in sig.items():
@@ -71,7 +72,7 @@ EXPORTED_SYMBOLS = (
     "kb200_abi_version", "kb200_last_error", "kb200_compile", "kb200_compile_to_memory", "kb200_free",
     "kb200_module_load", "kb200_module_load_file", "kb200_module_unload", "kb200_module_get_function",
     "kb200_function_info", "kb200_max_active_blocks", "kb200_device_info", "kb200_launch",
-    "kb200_genred_launch", "kb200_genred_launch_ranges", "kb200_function_set_max_dynamic_smem", "kb200_tensor_map_2d",
+    "kb200_genred_launch", "kb200_genred_launch_smem", "kb200_genred_launch_ranges", "kb200_function_set_max_dynamic_smem", "kb200_tensor_map_2d",
 )
 
 
@@ -145,12 +146,13 @@ def device_info(device: int):
 def genred_launch(reduce_fn: int, combine_fn: Optional[int], stream: int, nrow: int, ncol: int,
                   rows_per_block: int, block: int, nsplit: int, col_chunk: int, out_ptr: int,
                   workspace_ptr: int, arg_ptrs: Sequence[int], nbatch: int = 1,
-                  batch_strides: Optional[Sequence[int]] = None):
+                  batch_strides: Optional[Sequence[int]] = None, dynamic_smem: int = 0):
     n = len(arg_ptrs)
     arr = (C.c_void_p * max(n, 1))(*arg_ptrs)
     bs = None if batch_strides is None else (C.c_int64 * max(n, 1))(*batch_strides)
-    check(lib.kb200_genred_launch(reduce_fn, combine_fn or None, stream or None, nrow, ncol, rows_per_block,
-                                  block, nsplit, col_chunk, out_ptr, workspace_ptr or None, n, arr, nbatch, bs))
+    check(lib.kb200_genred_launch_smem(reduce_fn, combine_fn or None, stream or None, nrow, ncol, rows_per_block,
+                                       block, nsplit, col_chunk, out_ptr, workspace_ptr or None, n, arr, nbatch, bs,
+                                       int(dynamic_smem)))
 
 
 def genred_launch_ranges(reduce_fn: int, stream: int, nrow: int, ncol: int, block: int, grid_x: int, out_ptr: int,

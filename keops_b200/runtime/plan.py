@@ -145,6 +145,8 @@ def default_config(red: Reduction, dtype: str) -> KernelConfig:
     # TJ = 256 / 512 / 1024: ArgKMin D=3 232.1 / 228.5 / 222.7 ms, LSE 350.1 / 349.3 / 342.8 ms, Gaussian conv 262.6 / 259.0 / 261.4 ms
     tj_cap = 256 if f64 else (512 if red.kind == "Sum" else 1024)     # fp64 LSE: 1604 ms at 256, 1615 ms at 512
     TJ = max(8, min(tj_cap, 1 << int(math.log2(max(TJ, 1)))))
+    while TJ > 1 and 2 * TJ * stride * esz > 200 * 1024:      # very wide streamed rows: keep the double buffer inside one SM
+        TJ //= 2
     body = max(1, dimx + dimy) * (R // (1 if f64 else 2))
     unroll = 8 if body <= 16 else (4 if body <= 64 else (2 if body <= 160 else 1))
     if red.kind in ("KMin", "ArgKMin", "KMin_ArgKMin"):
@@ -192,11 +194,15 @@ def load_kernel(ks: KernelSource, fast: bool, device: int) -> LoadedKernel:
             fr = mod.function(ks.kernel_name)
             fc = mod.function(ks.combine_name) if ks.combine_name else 0
             regs, _, _ = capi.function_info(fr)
-            bps = max(1, capi.max_active_blocks(fr, ks.cfg.T, 0))
+            if ks.dynamic_smem:
+                capi.set_max_dynamic_smem(fr, ks.dynamic_smem)
+            bps = max(1, capi.max_active_blocks(fr, ks.cfg.T, ks.dynamic_smem))
             sm = capi.device_info(device)["sm_count"]
             fs = 0
             if ks.kernel_name == "kb200_reduce" and "kb200_reduce_seeded" in ks.source:
                 fs = mod.function("kb200_reduce_seeded")
+                if ks.dynamic_smem:
+                    capi.set_max_dynamic_smem(fs, ks.dynamic_smem)
             lk = LoadedKernel(ks, mod, fr, fc, regs, bps, sm, fs)
             _modules[key] = lk
         return lk

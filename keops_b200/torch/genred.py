@@ -216,6 +216,36 @@ class Genred:
         return postprocess(res, self.reduction_op, self.opt_arg)
 
 
+class RawReduction:
+    """A reduction given by its full reduction string -- what the reference's backward hands to the engine
+    (``Grad_WithSavedForward(<reduction>, <var>, <eta>, <res>)``, ``generic_red.py:190-214``) -- as a differentiable callable
+    returning the raw ``(n, dim)`` result (no post-processing).  Used by ``keops_b200.distributed`` to run a gradient
+    reduction sharded by the differentiated variable's own index."""
+
+    def __init__(self, red_formula: str, aliases, optional_flags=None, rec_multVar_highdim=False):
+        self.formula = red_formula
+        self.aliases = list(aliases)
+        self.nargs = len(self.aliases)
+        self.optional_flags = dict(optional_flags) if optional_flags is not None else \
+            get_optional_flags("Sum", "auto", False, "auto", True, True)
+        self.rec_multVar_highdim = rec_multVar_highdim
+
+    def __call__(self, *args, backend="auto", device_id=-1, ranges=None, out=None):
+        if len(args) != self.nargs:
+            raise ValueError("Invalid number of arguments (should be %d and got %d)." % (self.nargs, len(args)))
+        params = GenredParameters()
+        params.formula, params.aliases = self.formula, self.aliases
+        params.backend = backend
+        params.dtype = str(args[0].dtype).split(".")[1]
+        params.device_id_request = device_id
+        params.ranges = ranges
+        params.optional_flags = self.optional_flags
+        params.rec_multVar_highdim = self.rec_multVar_highdim
+        params.nx, params.ny = get_sizes(self.aliases, *args)
+        params.out = out
+        return genred_apply(params, *args)
+
+
 def generic_sum(formula, output, *aliases, **kwargs):
     _, cat, _, _ = get_type(output)
     return Genred(formula, aliases, reduction_op="Sum", axis=1 - cat if cat in (0, 1) else 0, **kwargs)

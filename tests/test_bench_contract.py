@@ -45,3 +45,22 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     r = _run(["--steps", "1", "--warmup", "3"])
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_env():
+    """``torch.distributed.run`` exports OMP_NUM_THREADS=1 to every rank; the reference arm must reset the OpenMP thread
+    count itself (the N >= 2 reference lines ran on one thread) and report the count OpenMP really uses."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref not built")
+    cores = len(os.sched_getaffinity(0))
+    if cores < 2:
+        pytest.skip("single-core container")
+    vals = {}
+    for tag, env in (("plain", {}), ("torchrun", {"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})):
+        r = _run(["--impl", "reference", "--gpus", "2" if env else "1", "--steps", "1", "--warmup", "0"], env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+        assert d["cpu_baseline"]["omp_max_threads"] == cores and d["cpu_baseline"]["cores"] == cores, d["cpu_baseline"]
+        vals[tag] = d["value"]
+    assert vals["torchrun"] > 0.6 * vals["plain"], vals       # same machine, same thread count: same rate

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libkb200.so does not export %s" % s
     assert set(syms) == set(capi.EXPORTED_SYMBOLS)
-    assert lib.kb200_abi_version() == 3
+    assert lib.kb200_abi_version() == 4
 
 
 def test_compute_entry_points_fail_loudly_without_gpu():
