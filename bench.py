@@ -341,7 +341,8 @@ def main():
         cx.flush.zero_()
         step()
     cx.sync_all()
-    fwd_binder = get_binder(GAUSS, [], 3, "float32")
+    from keops_b200.torch import genred as genred_mod
+    fwd_binder = genred_mod.LAST_BINDER                 # the binder the public API call really used
     launches_per_step = int(fwd_binder.last_launch["launches"])
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -414,8 +415,7 @@ def main():
         del q_full, d_full
         op = ShardedGenred("SqDist(x,y)", ["x=Vi(%d)" % D, "y=Vj(%d)" % D], "ArgKMin", axis=1, opt_arg=10)
         ms, _ = cx.time_leg(lambda: op(q, d, n_streamed=N), args.reps)
-        kb_ = get_binder("ArgKMin_Reduction(SqDist(Var(0,%d,0),Var(1,%d,1)),10,0)" % (D, D), [], 2, "float32")
-        engine = (kb_.last_launch or {}).get("engine") or "cuda-core"
+        engine = (getattr(genred_mod.LAST_BINDER, "last_launch", None) or {}).get("engine") or "cuda-core"
         res = {"metric": "knn_k10_queries_per_s", "value": M / (ms * 1e-3), "unit": "queries/s", "D": D, "K": 10, "ms": ms,
                "pair_evals_per_s": float(M) * N / (ms * 1e-3), "n_gpus": world, "engine": engine}
         if engine == "cuda-core":
@@ -461,8 +461,7 @@ def main():
             ITER = 4
             ks = ShardedKernelSolve("Exp(-g*SqDist(x,y))*b", ["x=Vi(16)", "y=Vj(16)", "b=Vj(1)", "g=Pm(1)"], "b", axis=1)
             ms, _ = cx.time_leg(lambda: ks(kx, kx, rhs, kg, n_total=M, alpha=0.8, eps=0.0, max_iter=ITER), max(3, args.reps // 2))
-            kb_ = get_binder(KSOLVE_G, [], 4, "float32")
-            engine = (kb_.last_launch or {}).get("engine") or "cuda-core"
+            engine = (getattr(genred_mod.LAST_BINDER, "last_launch", None) or {}).get("engine") or "cuda-core"
             legs["ksolve"] = {"workload": "ShardedKernelSolve, Gaussian kernel D=16, N=%d fp32: %d CG iterations (all_gather of the "
                                           "point cloud once, of the search direction every iteration)" % (M, ITER),
                               "ms_per_iteration": ms / ITER, "iterations": ks.last_iterations, "value": ITER * float(M) * M / (ms * 1e-3),
@@ -514,13 +513,11 @@ def main():
         "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": float(peaks.get("hbm_gbs", 6650.0)),
                          "unit": "GB/s", "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
                          "traffic": None, "note": "algorithmic unique bytes 4*(M*3+N*4+M) per launch; the kernel is compute-bound (%s peak)" % peaks_src},
-        "legs": legs,
+        "legs": sorted(legs),
     }
     if clocks and clocks.get("sm_mhz"):
         line["roofline"]["frac_at_sustained_clock"] = achieved / (ROOFLINE_PAIRS_PER_CLK_SM["gauss_fwd"] * SM_COUNT * clocks["sm_mhz"] * 1e6)
-    for k_ in ("knn", "knn_d64", "lse_softmin", "fwd_bwd", "ksolve"):      # r1 key names kept at top level
-        if k_ in legs:
-            line[k_] = legs[k_]
+    line.update(legs)                      # one top-level key per leg: fwd_bwd, knn, knn_d64, lse_softmin, ksolve
     if world > 1:
         dist.destroy_process_group()       # the other ranks are done; rank 0 goes on alone with the host-side comparators
 

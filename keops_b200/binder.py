@@ -27,7 +27,7 @@ import torch
 from .formulas.parser import parse_reduction, parse_alias
 from .formulas.reductions import Reduction
 from .codegen.emit import generate, KernelSource
-from .codegen import conv_tc, knn_tc
+from .codegen import conv_tc, knn_tc, emit_chunked
 from .runtime import plan, capi
 
 _binder_cache: Dict[tuple, "LoadKeOpsB200"] = {}
@@ -66,8 +66,6 @@ class LoadKeOpsB200:
               nargs, dtype, lang, optional_flags):
         if tagCPUGPU == 0:
             raise ValueError("[KeOps-B200] this engine has no CPU backend (backend='CPU' is not available).")
-        if tagHostDevice == 0:
-            raise ValueError("[KeOps-B200] input arrays must be CUDA tensors (GPU_*_host modes were dropped).")
         if lang not in ("torch", "pytorch"):
             raise ValueError("[KeOps-B200] only the torch binding is implemented.")
         if dtype not in ("float32", "float64"):
@@ -128,6 +126,10 @@ class LoadKeOpsB200:
         self._init_args = (tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id_request, lang)
         self._wide = self._detect_wide(red)
         self._wide_binders: Dict[int, "LoadKeOpsB200"] = {}
+        # high-dimensional Sum / Scalprod sub-formulas: the chunked kernel (the reference's chunk mode, switched by the same
+        # ``enable_chunks`` flag: get_keops_dll.py:101-111)
+        self._chunk_plan = emit_chunked.plan_chunks(red) if (p.enable_chunks and not self.ks.is_zero) else None
+        self.ks_chunked: Optional[KernelSource] = None
 
     # ---- wide streamed factor (the reference's "final chunks" mode, GpuReduc1D_finalchunks.py) ----------------
     # measured on B200 (D = 3 Gaussian, M = N = 5e4; experiments/wide_b_sweep.py), single kernel vs chunks of 32:
@@ -178,7 +180,7 @@ class LoadKeOpsB200:
                 self._wide_binders[w] = sub
             a2 = list(args)
             a2[ind] = b[..., c0:c0 + w].contiguous()
-            so = sub.genred(device_args, ranges, nx, ny, nbatchdims, None, *a2)
+            so = sub._genred_device(device_args, ranges, nx, ny, nbatchdims, None, *a2)
             launches += sub.last_launch.get("launches", 1)
             if res is None:
                 res = torch.empty(tuple(so.shape[:-1]) + (DV,), dtype=so.dtype, device=so.device)
@@ -202,7 +204,31 @@ class LoadKeOpsB200:
             self._loaded[device] = lk
         return lk
 
+    def _genred_from_host(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
+        """``tagHostDevice == 0`` (the reference's ``GPU_1D_host`` / ``GPU_2D_host`` modes, what ``backend="auto"`` resolves
+        to for host tensors on a GPU machine, ``pykeops/pykeops/common/get_options.py:84-120``): the reference's launcher
+        copies the arrays to the device, runs the CUDA kernel and copies the result back
+        (``keopscore/keopscore/binders/nvrtc/keops_nvrtc.cpp:470-507,617-631``).  Same here -- the computation is still this
+        engine's CUDA path; there is no CPU code."""
+        p = self.params
+        if not torch.cuda.is_available():
+            raise ValueError("[KeOps-B200] no CUDA device: this engine has no CPU backend.")
+        index = p.device_id_request if (p.device_id_request is not None and p.device_id_request >= 0) else torch.cuda.current_device()
+        dev = torch.device("cuda", index)
+        dargs = [a.to(dev, non_blocking=True) if isinstance(a, torch.Tensor) else a for a in args]
+        host = next((a.device for a in args if isinstance(a, torch.Tensor)), torch.device("cpu"))
+        res = self._genred_device(dev, ranges, nx, ny, nbatchdims, None, *dargs)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res.to(host)
+
     def genred(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
+        if self.params.tagHostDevice == 0 and not any(isinstance(a, torch.Tensor) and a.is_cuda for a in args):
+            return self._genred_from_host(device_args, ranges, nx, ny, nbatchdims, out, *args)
+        return self._genred_device(device_args, ranges, nx, ny, nbatchdims, out, *args)
+
+    def _genred_device(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
         p = self.params
         if self._wide is not None and len(args) == p.nargs and os.environ.get("KB200_WIDE_CHUNKS", "1") != "0":
             return self._genred_wide(device_args, ranges, nx, ny, nbatchdims, out, *args)
@@ -302,7 +328,65 @@ class LoadKeOpsB200:
             cl = conv_tc.eligible_lse(self.red, p.dtype, nrow, ncol, nbatch, p.use_fast_math, p.sum_scheme, p.dtype_acc)
             if cl is not None and self._genred_lse_tc(dev, cl, nrow, ncol, out, args):
                 return out
+        if self._chunk_plan is not None and os.environ.get("KB200_CHUNKS", "1") != "0":
+            if self._launch_chunked(dev, nrow, ncol, nbatch, out, args, strides, tdtype):
+                return out
         return self._launch_dense(dev, nrow, ncol, nbatch, out, args, strides, tdtype)
+
+    def _launch_chunked(self, dev, nrow, ncol, nbatch, out, args, strides, tdtype) -> bool:
+        """High-dimensional formulas on the chunked kernel (``codegen/emit_chunked.py``); False when the formula is outside
+        that scheme (the generic kernel then runs)."""
+        import ctypes as C
+        p = self.params
+        if self.ks_chunked is None:
+            ks = emit_chunked.generate_chunked(self.red, self._chunk_plan, p.dtype, p.nargs, use_fast_math=p.use_fast_math,
+                                               sum_scheme=p.sum_scheme, dtype_acc=p.dtype_acc)
+            if ks is None:
+                self._chunk_plan = None
+                return False
+            self.ks_chunked = ks
+        ks = self.ks_chunked
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        lk = self._loaded.get(("chunked", index))
+        if lk is None:
+            lk = plan.load_kernel(ks, p.use_fast_math and p.dtype == "float32", index)
+            self._loaded[("chunked", index)] = lk
+        ch = ks.chunk
+        esz = 4 if p.dtype == "float32" else 8
+        args = list(args)
+        if ch["align16"]:
+            for ind in ch["hd_j"]:
+                if args[ind].data_ptr() % 16:
+                    args[ind] = args[ind].clone()         # 16-byte cp.async needs an aligned base (offset views)
+        G, rows_pb, TJ = ch["G"], ch["ROWS"], ch["TJ"]
+        slots = max(1, (lk.sm_count * lk.blocks_per_sm) // min(nbatch, lk.sm_count * lk.blocks_per_sm))
+        nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_pb, TJ, slots, ks.dimpart * G, esz,
+                                              ws_limit_bytes=max(1, (2 << 30) // nbatch))
+        ntot = nsplit * G
+        i64, ptr, i32 = C.c_longlong, C.c_void_p, C.c_int
+        gx = -(-nrow // rows_pb)
+        launches = 0
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            out_flat = out.view(nbatch, nrow * p.dim)
+            for b0 in range(0, nbatch, 65535):
+                bn = min(65535, nbatch - b0)
+                ws = torch.empty(bn * ntot * nrow * ks.dimpart, dtype=tdtype, device=dev) if ntot > 1 else None
+                out_ptr = out_flat[b0].data_ptr()
+                params = [i64(nrow), i64(ncol), i64(max(col_chunk, 1)), ptr(out_ptr), ptr(ws.data_ptr() if ws is not None else 0)]
+                params += [ptr(a.data_ptr() + b0 * strides[k] * esz) for k, a in enumerate(args)]
+                params += [i64(int(st)) for st in strides]
+                capi.launch(lk.fn_reduce, stream, (gx, nsplit, bn), (ks.cfg.T,), ks.dynamic_smem, params)
+                launches += 1
+                if ws is not None:
+                    capi.launch(lk.fn_combine, stream, (-(-nrow // 256), 1, bn), (256,), 0,
+                                [i64(nrow), i32(ntot), ptr(ws.data_ptr()), ptr(out_ptr)])
+                    launches += 1
+                    ws.record_stream(torch.cuda.current_stream(dev))
+        self.last_launch = dict(nsplit=nsplit, col_chunk=col_chunk, grid_x=gx, nbatch=nbatch, regs=lk.regs,
+                                blocks_per_sm=lk.blocks_per_sm, launches=launches, engine="cuda-core/chunked",
+                                chunk=dict(D=ch["D"], rows=rows_pb, groups=G, tile=TJ))
+        return True
 
     def _genred_knn_tc(self, dev, tc, nrow, ncol, out, args, strides, tdtype):
         """K-min of a squared distance in large dimension: tcgen05 filter + exact re-evaluation

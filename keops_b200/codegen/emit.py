@@ -509,13 +509,14 @@ class LoweredReduction:
     row_scales: List[Optional[SNode]] = field(default_factory=list)  # Sum: per-term row-side factor applied at write-back
 
 
-def lower_reduction(red: Reduction, fast: bool) -> Optional[LoweredReduction]:
+def lower_reduction(red: Reduction, fast: bool, g: Optional[Graph] = None, L: Optional[Lowerer] = None) -> Optional[LoweredReduction]:
     """Vector IR -> optimised scalar DAG.  Returns None when the reduction is structurally zero.
 
     Sum terms and LSE weights accumulate the *unsigned* product / value and the pulled-out sign is
     applied once at write-back (negation is free there, not in the packed FFMA2 loop)."""
-    g = Graph(fast=fast, tagI=red.tagI)
-    L = Lowerer(g)
+    if g is None:
+        g = Graph(fast=fast, tagI=red.tagI)
+        L = Lowerer(g)
     F = L(red.formula)
     G = L(red.weight) if red.weight is not None else []
     kind = red.kind
@@ -934,18 +935,21 @@ class _ReductionCode:
     def _signs(self):
         return ["-" if t[2] else "" for t in self.acc_terms]
 
-    def finalize(self, W, row_limit: str = "nrow", allow_partial: bool = True):
+    def finalize(self, W, row_limit: str = "nrow", allow_partial: bool = True, row_expr: str = "row0 + (long long)q * KB_T",
+                 split_expr: str = "(long long)blockIdx.y", final_expr: Optional[str] = None):
         """Write either the final output (gridDim.y == 1) or this split's partial accumulator."""
         k, d = self.kind, self.dimF
         W("KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) {")
         W.indent()
-        W("const long long r_ = row0 + (long long)q * KB_T;")
+        W("const long long r_ = %s;" % row_expr)
         W("if (r_ < %s) {" % row_limit)
         W.indent()
         final = "(gridDim.y == 1 && !force_partial)" if (self.seeded and allow_partial) else "(gridDim.y == 1)"
+        if final_expr is not None:
+            final = final_expr
         self._final_cond = final
         if allow_partial:
-            W("real* po = %s ? (out + r_ * %d) : (partial + ((long long)blockIdx.y * nrow + r_) * %d);" % (final, self.red.dim, self.dimpart))
+            W("real* po = %s ? (out + r_ * %d) : (partial + (%s * nrow + r_) * %d);" % (final, self.red.dim, split_expr, self.dimpart))
         else:
             W("real* po = out + r_ * %d;" % self.red.dim)
         if k == "Sum":
@@ -960,7 +964,7 @@ class _ReductionCode:
             for i, s in enumerate(self._signs()):
                 W("po[%d] = %s%s;" % (1 + i, s, "(real)accd[%d][q]" % i if self.acc64 else "acc[%d].l[q]" % i))
         elif k in ("Min", "Max", "ArgMin", "ArgMax", "Min_ArgMin", "Max_ArgMax"):
-            W("if (gridDim.y == 1) {")
+            W("if %s {" % final)
             W.indent()
             for i in range(d):
                 if k in ("Min", "Max"):
@@ -1003,9 +1007,10 @@ class _ReductionCode:
         W.dedent()
         W("}")
 
-    def combine_kernel(self, W, cname: str):
+    def combine_kernel(self, W, cname: str, tie_by_index: bool = False):
         """One thread per output row merges the ``nsplit`` partial accumulators in split order
-        (so ties still resolve to the smallest index)."""
+        (so ties still resolve to the smallest index).  ``tie_by_index``: the splits hold *interleaved* column sets (chunked
+        kernel: the warp groups of a CTA share every tile), so on equal values the smaller index is chosen explicitly."""
         k, d, dp, dim = self.kind, self.dimF, self.dimpart, self.red.dim
         W("extern \"C\" __global__ void __launch_bounds__(256)")
         W("%s(const long long nrow, const int nsplit, const real* __restrict__ partial, real* __restrict__ out)" % cname)
@@ -1037,7 +1042,8 @@ class _ReductionCode:
             W("real v_[%d], ix_[%d];" % (d, d))
             W("KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { v_[k_] = pp[k_]; ix_[k_] = pp[%d + k_]; }" % (d, d))
             W("for (int s_ = 1; s_ < nsplit; s_++) { const real* ps = pp + s_ * sstride;")
-            W("  KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) if (ps[k_] %s v_[k_]) { v_[k_] = ps[k_]; ix_[k_] = ps[%d + k_]; } }" % (d, cmp, d))
+            tie = (" || (ps[k_] == v_[k_] && ps[%d + k_] < ix_[k_])" % d) if tie_by_index else ""
+            W("  KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) if (ps[k_] %s v_[k_]%s) { v_[k_] = ps[k_]; ix_[k_] = ps[%d + k_]; } }" % (d, cmp, tie, d))
             for i in range(d):
                 if k in ("Min", "Max"):
                     W("po[%d] = v_[%d];" % (i, i))
@@ -1051,8 +1057,13 @@ class _ReductionCode:
             W("  real v_[%d], ix_[%d];" % (K, K))
             W("  KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { v_[l_] = pp[l_ * %d + k_]; ix_[l_] = pp[l_ * %d + %d + k_]; }" % (K, 2 * d, 2 * d, d))
             W("  for (int s_ = 1; s_ < nsplit; s_++) { const real* ps = pp + s_ * sstride;")
-            W("    for (int l_ = 0; l_ < %d; l_++) { const real f_ = ps[l_ * %d + k_]; if (!(f_ < v_[%d])) break;" % (K, 2 * d, K - 1))
-            W("      kb_kmin_insert<%d, real>(v_, ix_, f_, ps[l_ * %d + %d + k_]); } }" % (K, 2 * d, d))
+            if tie_by_index:
+                W("    for (int l_ = 0; l_ < %d; l_++) { const real f_ = ps[l_ * %d + k_], fi_ = ps[l_ * %d + %d + k_];" % (K, 2 * d, 2 * d, d))
+                W("      if (!(f_ < v_[%d] || (f_ == v_[%d] && fi_ < ix_[%d]))) break;" % (K - 1, K - 1, K - 1))
+                W("      kb_kmin_insert_tie<%d>(v_, ix_, f_, fi_); } }" % K)
+            else:
+                W("    for (int l_ = 0; l_ < %d; l_++) { const real f_ = ps[l_ * %d + k_]; if (!(f_ < v_[%d])) break;" % (K, 2 * d, K - 1))
+                W("      kb_kmin_insert<%d, real>(v_, ix_, f_, ps[l_ * %d + %d + k_]); } }" % (K, 2 * d, d))
             W("  KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) {" % K)
             if k == "KMin":
                 W("    po[l_ * %d + k_] = v_[l_];" % d)

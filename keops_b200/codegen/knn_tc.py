@@ -89,7 +89,7 @@ class KnnTensorCore:
         self.STAGES = int(os.environ.get("KT_STAGES", STAGES if self.BN == 128 else 6))
         defs += "#define KT_BN %d\n#define KT_STAGES %d\n#define KT_DBG %d\n" % (self.BN, self.STAGES, int(os.environ.get("KT_DBG", 0)))
         defs += "#define KT_SPIN %d\n" % int(os.environ.get("KT_SPIN", 0))
-        defs += "#define KT_PIPE %d\n" % int(os.environ.get("KT_PIPE", 1))
+        defs += "#define KT_PIPE %d\n" % int(os.environ.get("KT_PIPE", 0))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(fast), "kb200_knntc", VERSION)
         blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K

@@ -108,7 +108,15 @@ class Graph:
         return SV(self._mk("const", (), v, C))
 
     def load(self, ind: int, comp: int, cat: int) -> SV:
-        if cat == 2:
+        """cat 0 / 1 / 2: i-, j-indexed variable, parameter.  Chunked mode (``codegen/emit_chunked.py``) adds cat 3: a
+        per-pair placeholder (the value of a chunked ``Sum`` / ``Scalprod``, like the reference's ``Var(ind,1,3)``,
+        ``keopscore/keopscore/formulas/Chunkable_Op.py:50-57``) and cat 4 / 5: the current component of a high-dimensional
+        i- / j-indexed variable inside the chunk loop."""
+        if cat == 3:
+            cls = IJ
+        elif cat in (4, 5):
+            cls = I if (cat - 4) == self.tagI else J
+        elif cat == 2:
             cls = P
         elif cat == self.tagI:
             cls = I

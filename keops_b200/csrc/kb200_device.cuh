@@ -227,3 +227,17 @@ KB_DEV void kb_kmin_insert(real (&val)[K], IDX (&idx)[K], real f, IDX j) {
   }
   if (f < val[0]) { val[0] = f; idx[0] = j; }
 }
+
+// Same insertion with (value, index) lexicographic order: used when partial lists over *interleaved* column sets are merged
+// (chunked kernel), where "earlier list wins ties" would not mean "smaller index wins ties".
+template <int K>
+KB_DEV void kb_kmin_insert_tie(real (&val)[K], real (&idx)[K], real f, real j) {
+  KB_UNROLL_ALL
+  for (int l = K - 1; l > 0; --l) {
+    const bool before_prev = (f < val[l - 1]) || (f == val[l - 1] && j < idx[l - 1]);
+    const bool before_here = (f < val[l]) || (f == val[l] && j < idx[l]);
+    if (before_prev) { val[l] = val[l - 1]; idx[l] = idx[l - 1]; }
+    else if (before_here) { val[l] = f; idx[l] = j; }
+  }
+  if ((f < val[0]) || (f == val[0] && j < idx[0])) { val[0] = f; idx[0] = j; }
+}

@@ -53,7 +53,9 @@
 #define KT_BN 128                             /* columns per tile (= N of one tcgen05.mma): 64 or 128           */
 #endif
 #ifndef KT_PIPE
-#define KT_PIPE 1                             /* 1: software-pipelined TMEM reads in the filter's epilogue       */
+#define KT_PIPE 0                             /* 1: software-pipelined TMEM reads in the filter's epilogue (measured
+                                                 on B200, D = 64, M = N = 1e6: 183 ms vs 162 ms un-pipelined -- kept as an
+                                                 opt-in experiment)                                              */
 #endif
 #ifndef KT_DBG
 #define KT_DBG 0                              /* 1: no rare path, 2: TMEM loads only, 3: no TMEM loads (timing experiments) */

@@ -75,6 +75,9 @@ def _binder_for(params, args):
     return binder, device_args, nbatchdims
 
 
+LAST_BINDER = None        # the binder of the most recent forward launch (introspection: bench.py, tests)
+
+
 class GenredAutograd(torch.autograd.Function):
     """New-style autograd function (``forward`` + ``setup_context``) so that ``torch.func.jvp`` / ``torch.func.vmap`` work
     like with the reference (``generic_red.py:262-380``): ``backward`` hands ``Grad_WithSavedForward`` reductions to the
@@ -82,7 +85,9 @@ class GenredAutograd(torch.autograd.Function):
 
     @staticmethod
     def forward(params, *args):
+        global LAST_BINDER
         binder, device_args, nbatchdims = _binder_for(params, args)
+        LAST_BINDER = binder
         cargs = tuple(a.detach() if a.is_contiguous() else a.detach().contiguous() for a in args)
         return binder.genred_pytorch(device_args, params.ranges, params.nx, params.ny, nbatchdims, params.out, *cargs)
 

@@ -137,13 +137,20 @@ def main(argv):
         def __init__(self):
             self.outcomes = {}
 
+        def pytest_runtest_setup(self, item):
+            # several reference tests draw unseeded data against fixed tolerances (the block-sparse cutoff test sits at
+            # 0.15-0.25 % of its 0.2 % bar depending on the draw): seed every test so that a run is reproducible
+            import numpy as np
+            torch.manual_seed(0)
+            np.random.seed(0)
+
         def pytest_runtest_logreport(self, report):
             if report.when == "call" or (report.when == "setup" and report.outcome != "passed"):
                 self.outcomes[report.nodeid.split("baseline/_ref/")[-1]] = report.outcome
 
     col = Collect()
     files = [os.path.join(REF, f) for f in FILES if os.path.exists(os.path.join(REF, f))]
-    args = files + ["-q", "-p", "no:cacheprovider", "--no-header", "-k", " and ".join("not " + d for d in DESELECT)] + argv
+    args = files + ["-q", "-p", "no:cacheprovider", "--no-header", "--continue-on-collection-errors", "-k", " and ".join("not " + d for d in DESELECT)] + argv
     rc = pytest.main(args, plugins=[col])
     summary = {
         "reference_version": pykeops.__version__, "reference_path": os.path.relpath(os.path.dirname(pykeops.__file__), ROOT),
