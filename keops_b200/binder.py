@@ -128,6 +128,7 @@ class LoadKeOpsB200:
         self._wide_binders: Dict[int, "LoadKeOpsB200"] = {}
         # high-dimensional Sum / Scalprod sub-formulas: the chunked kernel (the reference's chunk mode, switched by the same
         # ``enable_chunks`` flag: get_keops_dll.py:101-111)
+        self._prescale_ks = None         # None: not tried yet; False: the formula does not have the Gaussian shape
         self._chunk_plan = emit_chunked.plan_chunks(red) if (p.enable_chunks and not self.ks.is_zero) else None
         self.ks_chunked: Optional[KernelSource] = None
 
@@ -449,8 +450,81 @@ class LoadKeOpsB200:
                                 nchunks=eng.last["nchunks"])
         return True
 
+    # ---- pre-scaled Gaussian-type sums in low dimension (codegen/emit.py::_prescale_rewrite) ------------------------
+    # Taken when the problem is large enough to amortise the pack kernel, the statistics and one host read-back, and when
+    # the run-time bound on the rounding of the scaled coordinates is small: per-term relative error <= PRESCALE_TOL in the
+    # worst case (all six coordinate roundings aligned); measured on the BASELINE data (randn clouds, M = N = 1e6) the
+    # reduced sums differ from the reference's CUDA / CPU code by ~2e-7 of sum_j |F_ij| (bench.py "parity").
+    PRESCALE_MIN_PAIRS = 2e10
+    PRESCALE_TOL = 3e-5
+
+    def _launch_prescaled(self, dev, nrow, ncol, out, args, tdtype) -> bool:
+        import ctypes as C
+        import math
+        p = self.params
+        if self._prescale_ks is None:
+            ks = generate(self.red, p.dtype, p.nargs, self.ks.cfg, use_fast_math=True, sum_scheme=p.sum_scheme,
+                          dtype_acc=p.dtype_acc, prescale=True)
+            pairs = ks.prescale["pairs"] if ks is not None else []
+            if ks is None or len({q[0] for q in pairs}) != 1 or len({q[2] for q in pairs}) != 1:
+                self._prescale_ks = False
+                return False
+            self._prescale_ks = ks
+        ks = self._prescale_ks
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        lk = self._loaded.get(("prescaled", index))
+        if lk is None:
+            lk = plan.load_kernel(ks, True, index)
+            lk.fn_pack = lk.module.function("kb200_pack")
+            self._loaded[("prescaled", index)] = lk
+        pairs, stride = ks.prescale["pairs"], ks.prescale["stride"]
+        ix, iy = pairs[0][0], pairs[0][2]
+        cx, cy = [q[1] for q in pairs], [q[3] for q in pairs]
+        xa, ya = args[ix], args[iy]
+        xv = xa if cx == list(range(xa.shape[1])) else xa[:, cx]
+        yv = ya if cy == list(range(ya.shape[1])) else ya[:, cy]
+        i64, ptr = C.c_longlong, C.c_void_p
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            shf = yv.mean(0).contiguous()                                   # common shift: the streamed cloud's mean
+            ypk = torch.empty(ncol * stride, dtype=tdtype, device=dev)
+            info = torch.empty(2, dtype=tdtype, device=dev)
+            capi.launch(lk.fn_pack, stream, (-(-ncol // 256), 1, 1), (256,), 0,
+                        [i64(ncol), ptr(ypk.data_ptr()), ptr(shf.data_ptr()), ptr(info.data_ptr())] + [ptr(a.data_ptr()) for a in args])
+            # bound on the exponent error of a term: 4 * 2^-24 |d'| (|x'| + |y'|) with |d'| <= min(|x'| + |y'|, 11.3) for every
+            # term that does not underflow (2^-126); times ln 2 for the relative error of the term
+            t = ((xv - shf).square().sum(1).amax().sqrt() + (yv - shf).square().sum(1).amax().sqrt()) * info[1]
+            bound = (4.0 * 2.0 ** -24 * math.log(2.0)) * t.clamp(max=11.3) * t
+            k_val, b_val = torch.stack([info[0].reshape(()), bound.reshape(())]).tolist()     # one host read-back per call
+            if not (k_val > 0.0 and b_val <= self.PRESCALE_TOL):            # also catches NaN / inf
+                self._prescale_rejected = dict(K=k_val, bound=b_val)
+                return False
+            rows_per_block = ks.cfg.T * ks.cfg.R
+            slots = lk.sm_count * lk.blocks_per_sm
+            nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, 4)
+            ws = torch.empty(nsplit * nrow * ks.dimpart, dtype=tdtype, device=dev) if nsplit > 1 else None
+            params = [i64(nrow), i64(ncol), i64(max(col_chunk, 1)), ptr(out.data_ptr()), ptr(ws.data_ptr() if ws is not None else 0)]
+            params += [ptr(a.data_ptr()) for a in args] + [i64(0)] * p.nargs + [ptr(ypk.data_ptr()), ptr(shf.data_ptr())]
+            gx = -(-nrow // rows_per_block)
+            capi.launch(lk.fn_reduce, stream, (gx, nsplit, 1), (ks.cfg.T,), ks.dynamic_smem, params)
+            if ws is not None:
+                capi.launch(lk.fn_combine, stream, (-(-nrow // 256), 1, 1), (256,), 0,
+                            [i64(nrow), C.c_int(nsplit), ptr(ws.data_ptr()), ptr(out.data_ptr())])
+                ws.record_stream(torch.cuda.current_stream(dev))
+            for t_ in (ypk, shf, info):
+                t_.record_stream(torch.cuda.current_stream(dev))
+        self.last_launch = dict(nsplit=nsplit, col_chunk=col_chunk, grid_x=gx, nbatch=1, regs=lk.regs,
+                                blocks_per_sm=lk.blocks_per_sm, launches=2 + (nsplit > 1), engine="cuda-core/prescaled",
+                                error_bound=b_val)
+        return True
+
     def _launch_dense(self, dev, nrow, ncol, nbatch, out, args, strides, tdtype):
         p = self.params
+        if (self._prescale_ks is not False and self.red.kind == "Sum" and p.dtype == "float32" and p.use_fast_math
+                and nbatch == 1 and p.tag1D2D == 0 and float(nrow) * float(ncol) >= self.PRESCALE_MIN_PAIRS
+                and os.environ.get("KB200_PRESCALE", "1") != "0"):
+            if self._launch_prescaled(dev, nrow, ncol, out, args, tdtype):
+                return out
         lk = self._kernel(dev.index if dev.index is not None else torch.cuda.current_device())
         ks = self.ks
         rows_per_block = ks.cfg.T * ks.cfg.R

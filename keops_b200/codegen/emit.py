@@ -147,6 +147,9 @@ class _Rewriter:
             out = self._sub(n.args[0], n.args[1], n.cls)
         elif n.op == "neg":
             out = self.neg_of(n.args[0])
+        elif n.op == "ex2" and n.args[0].op == "neg" and n.args[0].args[0].op in ("add", "fma") and self.g.fast:
+            # 2^(-s) of a sum: the negation is a free source modifier of MUFU.EX2 (pre-scaled squared distances)
+            out = g._mk("ex2n", (self.rw(n.args[0].args[0]),), None, n.cls)
         else:
             out = g._mk(n.op, tuple(self.rw(a) for a in n.args), n.val, n.cls)
         self.memo[n.uid] = out
@@ -172,7 +175,7 @@ def _lit(v: float, f64: bool) -> str:
     return s + "f"
 
 
-_FN1 = {"rcp", "exp", "ex2", "log", "lg2", "sqrt", "rsqrt", "sin", "cos", "asin", "acos", "atan", "abs",
+_FN1 = {"rcp", "exp", "ex2", "ex2n", "sqrt_rn", "keep", "log", "lg2", "sqrt", "rsqrt", "sin", "cos", "asin", "acos", "atan", "abs",
         "sign", "step", "relu", "floor", "round0", "xlogx", "sinxdivx"}
 _FN2 = {"div", "atan2", "powf", "fmax", "fmin", "lt", "le", "eq", "ne"}
 _FN3 = {"sel_ge0", "clamp", "inrange", "mod"}
@@ -218,10 +221,17 @@ def _collect_vars(red: Reduction):
 
 
 def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast_math: bool = True,
-             sum_scheme: str = "block_sum", dtype_acc: str = "auto", ranges: bool = False) -> KernelSource:
+             sum_scheme: str = "block_sum", dtype_acc: str = "auto", ranges: bool = False,
+             prescale: bool = False) -> Optional[KernelSource]:
     """``ranges=True`` emits the block-sparse variant ``kb200_reduce_ranges`` (reference:
     ``keopscore/keopscore/mapreduce/gpu/GpuReduc1D_ranges.py:77-172``) instead of the dense pair
-    ``kb200_reduce`` / ``kb200_combine``."""
+    ``kb200_reduce`` / ``kb200_combine``.
+
+    ``prescale=True`` emits the *pre-scaled, packed* variant for Gaussian-type sums in low dimension
+    (``_prescale_rewrite``): a third kernel ``kb200_pack`` writes all streamed variables of a column -- the distance
+    coordinates shifted and scaled -- into one padded row of ``ypk``, which ``kb200_reduce`` stages with one 16-byte
+    ``cp.async`` per 4 reals (instead of one 4-byte request per element from several arrays).  Returns None when the formula
+    does not have that shape."""
     if dtype not in ("float32", "float64"):
         raise ValueError("dtype %s is not implemented (float32 / float64 only)" % dtype)
     # the scalar DAG of a D-dimensional left-to-right sum is D levels deep and the rewriters below are recursive:
@@ -252,8 +262,12 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
         return KernelSource(source="", kernel_name="", combine_name="", dimpart=0, stride=0, smem_bytes=0,
                             is_zero=True, **base)
 
-    low = lower_reduction(red, fast)
+    if prescale and (f64 or not fast or ranges or kind != "Sum"):
+        return None
+    low = lower_reduction(red, fast, prescale=prescale)
     if low is None:
+        if prescale:
+            return None
         return KernelSource(source="", kernel_name="", combine_name="", dimpart=0, stride=0, smem_bytes=0,
                             is_zero=True, **base)
     g, acc_terms, value_nodes, order = low.graph, low.acc_terms, low.value_nodes, low.order
@@ -267,25 +281,44 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
     for ind, d in col_vars:
         col_off[ind] = off
         off += d
+    # packed mode: one slot per streamed value the formula reads -- (index, component, scaled copy?) -- in first-use order
+    slots: List[Tuple[int, int, bool]] = []
+    if prescale:
+        for n in order:
+            if n.op == "load" and n.cls == J:
+                key = (n.val[0], n.val[1], n.val[2] == 7)
+                if key not in slots:
+                    slots.append(key)
+        stride = max(4, (len(slots) + 3) // 4 * 4)
 
     # --- statements per region ----------------------------------------------------------------
     pre: List[str] = []      # before the loop: P scalars, I vectors
     body_j: List[str] = []   # per streamed row: J scalars
     body_ij: List[str] = []  # per pair
     used_col: Dict[Tuple[int, int], str] = {}
+    used_pos: Dict[int, str] = {}     # packed mode: slot position -> name
+    pre_p: List[str] = []             # the constant / parameter-only statements (also needed by kb200_pack)
     for n in order:
         if n.op == "const":
             continue
         if n.op == "load":
             ind, comp, cat = n.val
-            if n.cls == P:
+            if cat == 6:
+                nm = "sh%d" % ind
+                pre.append("const real %s = shf[%d];" % (nm, ind))
+                pre_p.append(pre[-1])
+            elif n.cls == P:
                 nm = "p%d_%d" % (ind, comp)
                 pre.append("const real %s = a%d[%d];" % (nm, ind, comp))
+                pre_p.append(pre[-1])
             elif n.cls == I:
                 nm = "x%d_%d" % (ind, comp)
                 d = varinfo[ind][0]
                 pre.append("V %s; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) %s.l[q] = a%d[rowc[q] * %d + %d];"
                            % (nm, nm, ind, d, comp))
+            elif prescale:
+                nm = ("ys%d_%d" if cat == 7 else "y%d_%d") % (ind, comp)
+                used_pos[slots.index((ind, comp, cat == 7))] = nm
             else:
                 nm = "y%d_%d" % (ind, comp)
                 used_col[(ind, comp)] = nm
@@ -298,6 +331,8 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
         stmt = "const %s %s = %s;" % (ty, nm, pr.expr(n))
         if n.cls in (C, P, I):
             pre.append(stmt)
+            if n.cls in (C, P):
+                pre_p.append(stmt)
         elif n.cls == J:
             body_j.append(stmt)
         else:
@@ -307,11 +342,11 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
     vec = 2 if f64 else 4
     vty = "double2" if f64 else "float4"
     comp_names = ["x", "y", "z", "w"]
-    need_chunks = sorted({(col_off[ind] + comp) // vec for (ind, comp) in used_col})
+    positions = dict(used_pos) if prescale else {col_off[ind] + comp: nm for (ind, comp), nm in used_col.items()}
+    need_chunks = sorted({pos // vec for pos in positions})
     def row_loads_from(ptr: str) -> List[str]:
         out = ["const %s q%d = %s[%d];" % (vty, c, ptr, c) for c in need_chunks]
-        for (ind, comp), nm in sorted(used_col.items()):
-            pos = col_off[ind] + comp
+        for pos, nm in sorted(positions.items()):
             out.append("const real %s = q%d.%s;" % (nm, pos // vec, comp_names[pos % vec]))
         return out
 
@@ -323,17 +358,28 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
 
     red_code = _ReductionCode(red, pr, acc_terms, value_nodes, sum_scheme, dtype_acc, f64, fast, row_scales)
 
+    def stage_tile(jbase: str, buf: str):
+        if not prescale:
+            _stage(W, col_vars, col_off, jbase, buf)
+            return
+        # packed rows: KB_STRIDE / 4 aligned 16-byte requests per streamed row, coalesced, no bank conflicts
+        W("for (int e = tid; e < KB_TJ * (KB_STRIDE / 4); e += KB_T) {")
+        W("  const int jr_ = e / (KB_STRIDE / 4), c_ = (e - jr_ * (KB_STRIDE / 4)) * 4;")
+        W("  const long long j_ = (%s) + jr_; const bool ok_ = j_ < jend;" % jbase)
+        W("  kb_cp_async16(&sm[%s][jr_ * KB_STRIDE + c_], ypk + (ok_ ? (j_ * KB_STRIDE + c_) : 0), ok_);" % buf)
+        W("}")
+
     def tile_loop():
         """Stage + stream the column range [jbeg, jend) through the double-buffered tile."""
         W("// ---- stage the first tile")
-        _stage(W, col_vars, col_off, "jbeg", "0")
+        stage_tile("jbeg", "0")
         W("kb_cp_commit(); kb_cp_wait_all(); __syncthreads();")
         W("int buf = 0;")
         W("for (long long jt = jbeg; jt < jend; jt += KB_TJ) {")
         W.indent()
         W("if (jt + KB_TJ < jend) {")
         W.indent()
-        _stage(W, col_vars, col_off, "jt + KB_TJ", "buf ^ 1")
+        stage_tile("jt + KB_TJ", "buf ^ 1")
         W.dedent()
         W("}")
         W("kb_cp_commit();")
@@ -397,6 +443,8 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
     if not ranges:
         # ---------------- dense kernel ----------------
         stride_decl = "".join(", const long long bs%d" % k for k in range(nargs))
+        if prescale:
+            stride_decl += ", const real* __restrict__ ypk, const real* __restrict__ shf"
         kfam = kind in ("KMin", "ArgKMin", "KMin_ArgKMin")
         red_code.seeded = kfam
         if kfam:
@@ -447,6 +495,35 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
             W("")
         # ---------------- combine kernel (merges split-j partials) ----------------
         red_code.combine_kernel(W, cname)
+        if prescale:
+            # ---------------- pack kernel: streamed variables -> padded rows (shifted / scaled distance coordinates) ----------
+            pinfo = low.prescale
+            W("")
+            W("// One thread per streamed row: slot s of ypk[j] holds the s-th streamed value the formula reads; the distance")
+            W("// coordinates are stored as (y - shift) * sigma.  Thread 0 also reports K (the exponent's scale, sigma^2).")
+            W("extern \"C\" __global__ void __launch_bounds__(256)")
+            W("kb200_pack(const long long ncol, real* __restrict__ ypk_out, const real* __restrict__ shf, real* __restrict__ info%s)"
+              % "".join(", const real* __restrict__ a%d" % k for k in range(nargs)))
+            W("{")
+            W.indent()
+            W("const long long j_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+            for s_ in pre_p:
+                W(s_)
+            W("if (j_ == 0) { info[0] = %s; info[1] = %s; }" % (pr.ref(pinfo["K"]), pr.ref(pinfo["sigma"])))
+            W("if (j_ >= ncol) return;")
+            W("real row_[KB_STRIDE];")
+            W("KB_UNROLL_ALL for (int s_ = 0; s_ < KB_STRIDE; s_++) row_[s_] = (real)0;")
+            for pos, (ind, comp, scaled) in enumerate(slots):
+                d = varinfo[ind][0]
+                if scaled:
+                    k = [(q[2], q[3]) for q in pinfo["pairs"]].index((ind, comp))
+                    W("row_[%d] = (a%d[j_ * %d + %d] - shf[%d]) * %s;" % (pos, ind, d, comp, k, pr.ref(pinfo["sigma"])))
+                else:
+                    W("row_[%d] = a%d[j_ * %d + %d];" % (pos, ind, d, comp))
+            W("float4* dst_ = reinterpret_cast<float4*>(ypk_out + j_ * KB_STRIDE);")
+            W("KB_UNROLL_ALL for (int s_ = 0; s_ < KB_STRIDE / 4; s_++) dst_[s_] = make_float4(row_[4 * s_], row_[4 * s_ + 1], row_[4 * s_ + 2], row_[4 * s_ + 3]);")
+            W.dedent()
+            W("}")
     else:
         # ---------------- block-sparse kernel ----------------
         kname, cname = "kb200_reduce_ranges", ""
@@ -495,8 +572,11 @@ def generate(red: Reduction, dtype: str, nargs: int, cfg: KernelConfig, use_fast
 
     src = hdr + W.text()
     h = hashlib.sha256((GENERATOR_VERSION + src).encode()).hexdigest()[:16]
-    return KernelSource(source=src, kernel_name=kname, combine_name=cname, dimpart=red_code.dimpart,
-                        stride=stride, smem_bytes=smem_bytes, hash=h, dynamic_smem=dynamic_smem, **base)
+    ks = KernelSource(source=src, kernel_name=kname, combine_name=cname, dimpart=red_code.dimpart,
+                      stride=stride, smem_bytes=smem_bytes, hash=h, dynamic_smem=dynamic_smem, **base)
+    if prescale:
+        ks.prescale = dict(pairs=low.prescale["pairs"], slots=slots, stride=stride)
+    return ks
 
 
 @dataclass
@@ -507,9 +587,11 @@ class LoweredReduction:
     value_nodes: List[SNode]                                # LSE exponent / Min / KMin values
     order: List[SNode]                                      # topological order of everything needed
     row_scales: List[Optional[SNode]] = field(default_factory=list)  # Sum: per-term row-side factor applied at write-back
+    prescale: Optional[dict] = None     # pre-scaled squared distance (``_prescale_rewrite``): sigma node, coordinate pairs
 
 
-def lower_reduction(red: Reduction, fast: bool, g: Optional[Graph] = None, L: Optional[Lowerer] = None) -> Optional[LoweredReduction]:
+def lower_reduction(red: Reduction, fast: bool, g: Optional[Graph] = None, L: Optional[Lowerer] = None,
+                    prescale: bool = False) -> Optional[LoweredReduction]:
     """Vector IR -> optimised scalar DAG.  Returns None when the reduction is structurally zero.
 
     Sum terms and LSE weights accumulate the *unsigned* product / value and the pulled-out sign is
@@ -522,6 +604,12 @@ def lower_reduction(red: Reduction, fast: bool, g: Optional[Graph] = None, L: Op
     kind = red.kind
     if kind == "Sum" and all(sv.const() == 0.0 for sv in F):
         return None
+    pre_info = None
+    if prescale:
+        hit = _prescale_rewrite(g, F) if (kind == "Sum" and fast) else None
+        if hit is None:
+            return None              # the caller asked for the pre-scaled variant and it does not apply
+        F, pre_info = hit
     rwt = _Rewriter(g)
     acc_terms: List[Tuple[str, Tuple[SNode, ...], bool]] = []
     value_nodes: List[SNode] = []
@@ -547,7 +635,129 @@ def lower_reduction(red: Reduction, fast: bool, g: Optional[Graph] = None, L: Op
     for mode, nodes, _ in acc_terms:
         roots.extend(nodes)
     roots.extend(h for h in row_scales if h is not None)
-    return LoweredReduction(g, acc_terms, value_nodes, topo_order(roots), row_scales)
+    if pre_info is not None:
+        pre_info["sigma"] = rwt.rw(pre_info["sigma"])
+        pre_info["K"] = rwt.rw(pre_info["K"])
+        roots.extend([pre_info["sigma"], pre_info["K"]])
+    return LoweredReduction(g, acc_terms, value_nodes, topo_order(roots), row_scales, pre_info)
+
+
+PRESCALE_MAX_DIM = 8
+
+
+def _prescale_rewrite(g: Graph, F: Sequence[SV]):
+    """``2^(-K |x_i - y_j|^2)`` with the scale folded into the coordinates: ``x' = (x - m) sigma``, ``y' = (y - m) sigma``
+    with ``sigma = sqrt(K)``, so that the exponent is ``-(sum_k (x'_k - y'_k)^2)`` -- the ``K *`` multiply of the pair loop
+    (one of 8 FP32-pipe operations per pair of the Gaussian convolution in D = 3, which co-limits with the MUFU pipe)
+    disappears; the negation is a free source modifier of MUFU.EX2 (``ex2n``).  ``m`` is a common shift (the streamed
+    cloud's mean, passed at run time) that keeps the rounding of the scaled coordinates relative to the cloud's extent.
+    Other uses of the differences ``d_k`` (gradients) become ``(1 / sigma) d'_k``, a hoistable factor.
+
+    The scaled streamed coordinates are produced once per call by ``kb200_pack`` (cat-7 loads); the scaled output-side
+    coordinates are hoisted per thread.  Rounding: each scaled coordinate carries a relative error <= 2^-23, i.e. the
+    exponent an absolute error <= 4 * 2^-24 |d'| (|x'| + |y'|) -- the caller evaluates this bound on the data and falls
+    back to the exact-order kernel when it is not small (``binder._prescale_guard``).
+
+    Matches: exactly one ``(K, S)`` pair over all ``ex2`` nodes, ``ex2(neg(mul(K, S)))`` with ``K`` a positive constant or a
+    parameter-only value (its sign is checked at run time) and ``S = sum_k (a_k - b_k)^2``, ``a_k`` / ``b_k`` plain components
+    of an output-side / a streamed variable, at most ``PRESCALE_MAX_DIM`` terms.  Returns ``(F', info)`` or None."""
+    roots = [sv.n for sv in F]
+    found = None
+    for n in topo_order(roots):
+        if n.op != "ex2":
+            continue
+        a = n.args[0]
+        if a.op != "neg" or a.args[0].op != "mul":
+            return None              # an exponential of something else: leave the formula alone
+        p, q = a.args[0].args
+        K, S = (p, q) if p.cls <= P else (q, p)
+        if K.cls > P or S.cls != IJ:
+            return None
+        if found is not None and (found[0] is not K or found[1] is not S):
+            return None
+        found = (K, S)
+    if found is None:
+        return None
+    K, S = found
+    # S: nested adds of squares of differences
+    leaves, stack = [], [S]
+    while stack:
+        t = stack.pop()
+        if t.op == "add":
+            stack.extend(t.args)
+        else:
+            leaves.append(t)
+    if not (1 <= len(leaves) <= PRESCALE_MAX_DIM):
+        return None
+    pairs = []          # (d node, a node (row side), b node (streamed side), a_first)
+    for t in leaves:
+        if t.op != "mul" or t.args[0] is not t.args[1] or t.args[0].op != "sub":
+            return None
+        d = t.args[0]
+        u, v = d.args
+        if u.op != "load" or v.op != "load" or {u.cls, v.cls} != {I, J} or u.val[2] not in (0, 1) or v.val[2] not in (0, 1):
+            return None
+        pairs.append((d, u, v) if u.cls == I else (d, v, u))
+    if len({id(p[0]) for p in pairs}) != len(pairs):
+        return None
+    pairs.sort(key=lambda p: (p[1].val[0], p[1].val[1]))
+    sigma = g.sqrt_rn(SV(K))
+    inv_sigma = g.rcp(sigma) if sigma.const() is None else g.const(1.0 / sigma.const())
+    dmap: Dict[int, SV] = {}
+    sq: Dict[int, SV] = {}
+    for k, (d, a, b) in enumerate(pairs):
+        shift = g.load(k, 0, 6)
+        # hoisted per thread; "keep" stops the FMA contraction from pulling this product back into the pair loop
+        a2 = SV(g._mk("keep", (g.materialize(g.mul(g.sub(SV(a), shift), sigma)),)))
+        b2 = g.load(b.val[0], b.val[1], 7)                           # (b - shift) * sigma, from the packed tile
+        d2 = g.sub(a2, b2) if d.args[0] is a else g.sub(b2, a2)
+        dmap[d.uid] = d2
+        sq[d.uid] = g.mul(d2, d2)
+    # S' with the original association
+    smemo: Dict[int, SV] = {}
+
+    def rebuild_S(t: SNode) -> SV:
+        r = smemo.get(t.uid)
+        if r is None:
+            r = g.add(rebuild_S(t.args[0]), rebuild_S(t.args[1])) if t.op == "add" else sq[t.args[0].uid]
+            smemo[t.uid] = r
+        return r
+
+    S2 = rebuild_S(S)
+    memo: Dict[int, SV] = {}
+
+    def rebuild(n: SNode) -> SV:
+        r = memo.get(n.uid)
+        if r is not None:
+            return r
+        if n.op == "ex2":
+            r = SV(g._mk("ex2", (g.materialize(-S2),)))
+        elif n.uid in dmap:
+            r = g.mul(inv_sigma, dmap[n.uid])
+        elif n.op in ("const", "load"):
+            r = SV(n)
+        else:
+            args = [rebuild(x) for x in n.args]
+            if n.op == "add":
+                r = g.add(args[0], args[1])
+            elif n.op == "sub":
+                r = g.sub(args[0], args[1])
+            elif n.op == "mul":
+                r = g.mul(args[0], args[1])
+            elif n.op == "neg":
+                r = -args[0]
+            else:
+                r = SV(g._mk(n.op, tuple(g.materialize(x) for x in args), n.val))
+        memo[n.uid] = r
+        return r
+
+    F2 = []
+    for sv in F:
+        r = rebuild(sv.n)
+        F2.append(-r if sv.neg else r)
+    info = dict(sigma=g.materialize(sigma), K=K,
+                pairs=[(a.val[0], a.val[1], b.val[0], b.val[1]) for _, a, b in pairs])
+    return F2, info
 
 
 def _pair_cost(acc_terms) -> int:

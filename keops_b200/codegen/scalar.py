@@ -116,6 +116,10 @@ class Graph:
             cls = IJ
         elif cat in (4, 5):
             cls = I if (cat - 4) == self.tagI else J
+        elif cat == 6:
+            cls = P          # pre-scaled mode (emit.py): component ``ind`` of the common shift of both clouds
+        elif cat == 7:
+            cls = J          # pre-scaled mode: shifted + scaled copy of a streamed component, read from the packed tile
         elif cat == 2:
             cls = P
         elif cat == self.tagI:
@@ -264,6 +268,13 @@ class Graph:
 
     def sqrt(self, a: SV) -> SV:
         return SV(self._mk("sqrt", (self.materialize(a),)))
+
+    def sqrt_rn(self, a: SV) -> SV:
+        """Correctly rounded square root even under ``use_fast_math`` (hoisted scale factors: an error here is systematic)."""
+        c = a.const()
+        if c is not None and c >= 0:
+            return self.const(math.sqrt(c))
+        return SV(self._mk("sqrt_rn", (self.materialize(a),)))
 
     def rsqrt(self, a: SV) -> SV:
         # guarded: 0 -> 0  (``keopscore/keopscore/utils/math_functions.py:104-108``)

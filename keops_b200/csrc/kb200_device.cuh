@@ -146,6 +146,21 @@ KB_DEV real kb_fmin(real a, real b) { return fminf(a, b); }
 #define KB_INF (__int_as_float(0x7f800000))
 #endif
 
+// correctly rounded square root whatever the fast-math setting (hoisted scale factors), and ex2 of the negated argument:
+// the negation is free as a source modifier of MUFU.EX2, whereas the packed FMUL2 / FFMA2 have none
+#if KB_F64
+KB_DEV real kb_sqrt_rn(real x) { return sqrt(x); }
+KB_DEV real kb_ex2n(real x) { return exp2(-x); }
+#else
+KB_DEV real kb_sqrt_rn(real x) { return (real)sqrt((double)x); }
+#if KB_FAST
+// (neg.f32 without .ftz: ptxas folds it into the MUFU source modifier; neg.ftz.f32 after a packed producer costs an FADD)
+KB_DEV real kb_ex2n(real x) { real r; asm("{ .reg .f32 t; neg.f32 t, %1; ex2.approx.ftz.f32 %0, t; }" : "=f"(r) : "f"(x)); return r; }
+#else
+KB_DEV real kb_ex2n(real x) { return exp2f(-x); }
+#endif
+#endif
+
 // smallest representable value above s (s itself when it is +inf or NaN), and an atomic minimum on reals (ordered-integer
 // trick: non-negative floats order like signed ints, negative ones like reversed unsigned ints): the thresholds that the
 // column splits of a K-min reduction share through global memory
@@ -188,7 +203,9 @@ KB_DEV real kb_mod(real x, real n, real d) { return x - n * kb_floor((x - d) / n
 KB_LIFT1(kb_rcp) KB_LIFT1(kb_exp) KB_LIFT1(kb_ex2) KB_LIFT1(kb_log) KB_LIFT1(kb_lg2) KB_LIFT1(kb_sqrt)
 KB_LIFT1(kb_rsqrt) KB_LIFT1(kb_sin) KB_LIFT1(kb_cos) KB_LIFT1(kb_asin) KB_LIFT1(kb_acos) KB_LIFT1(kb_atan)
 KB_LIFT1(kb_abs) KB_LIFT1(kb_floor) KB_LIFT1(kb_round0) KB_LIFT1(kb_sign) KB_LIFT1(kb_step) KB_LIFT1(kb_relu)
-KB_LIFT1(kb_xlogx) KB_LIFT1(kb_sinxdivx)
+KB_LIFT1(kb_xlogx) KB_LIFT1(kb_sinxdivx) KB_LIFT1(kb_ex2n) KB_LIFT1(kb_sqrt_rn)
+KB_DEV real kb_keep(real x) { return x; }          // identity: marks a hoisted value the emitter must not re-fuse
+KB_DEV V kb_keep_v(const V& a) { return a; }
 KB_LIFT2(kb_div) KB_LIFT2(kb_atan2) KB_LIFT2(kb_powf) KB_LIFT2(kb_fmax) KB_LIFT2(kb_fmin) KB_LIFT2(kb_lt)
 KB_LIFT2(kb_le) KB_LIFT2(kb_eq) KB_LIFT2(kb_ne)
 KB_LIFT3(kb_sel_ge0) KB_LIFT3(kb_clamp) KB_LIFT3(kb_inrange) KB_LIFT3(kb_mod)

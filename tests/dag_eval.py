@@ -13,7 +13,8 @@ def _fn(op, a, dt):
     f = {
         "add": lambda: a[0] + a[1], "sub": lambda: a[0] - a[1], "mul": lambda: a[0] * a[1],
         "fma": lambda: a[0] * a[1] + a[2], "neg": lambda: -a[0], "rcp": lambda: one / a[0], "div": lambda: a[0] / a[1],
-        "exp": lambda: np.exp(a[0]), "ex2": lambda: np.exp2(a[0]), "log": lambda: np.log(a[0]), "lg2": lambda: np.log2(a[0]),
+        "exp": lambda: np.exp(a[0]), "ex2": lambda: np.exp2(a[0]), "ex2n": lambda: np.exp2(-a[0]), "keep": lambda: a[0],
+        "sqrt_rn": lambda: np.sqrt(a[0]), "log": lambda: np.log(a[0]), "lg2": lambda: np.log2(a[0]),
         "sqrt": lambda: np.sqrt(a[0]), "rsqrt": lambda: np.where(a[0] == 0, zero, one / np.sqrt(np.where(a[0] == 0, one, a[0]))),
         "sin": lambda: np.sin(a[0]), "cos": lambda: np.cos(a[0]), "asin": lambda: np.arcsin(a[0]), "acos": lambda: np.arccos(a[0]),
         "atan": lambda: np.arctan(a[0]), "atan2": lambda: np.arctan2(a[0], a[1]), "abs": lambda: np.abs(a[0]),
@@ -32,12 +33,16 @@ def _fn(op, a, dt):
     return f[op]()
 
 
-def evaluate(formula, aliases, args, dtype="float64", fast=False, sizes=None):
-    """Dense evaluation of the *lowered* reduction: returns the raw output (nrow, dim)."""
+def evaluate(formula, aliases, args, dtype="float64", fast=False, sizes=None, prescale=False):
+    """Dense evaluation of the *lowered* reduction: returns the raw output (nrow, dim).  ``prescale=True`` evaluates the
+    pre-scaled variant (``emit._prescale_rewrite``) the way ``kb200_pack`` + ``kb200_reduce`` do: common shift = mean of
+    the streamed distance coordinates, scaled copies ``(y - shift) * sigma`` rounded to ``dtype``."""
     red = parse_reduction(formula, aliases)
     dt = np.dtype(dtype)
     tagI = red.tagI
-    low = lower_reduction(red, fast)
+    low = lower_reduction(red, fast, prescale=prescale)
+    if prescale and low is None:
+        return None
     vs = {v.params[0]: (v.params[1], v.params[2]) for v in red.variables()}
     nrow = ncol = 1
     if sizes is not None:                      # (nx, ny): a side without variables still has a size
@@ -50,11 +55,35 @@ def evaluate(formula, aliases, args, dtype="float64", fast=False, sizes=None):
     if low is None or red.kind == "Zero":
         return np.zeros((nrow, red.dim), dt)
     val = {}
+    shift = {}
+    if prescale:
+        for k, (ix, cx, iy, cy) in enumerate(low.prescale["pairs"]):
+            shift[k] = np.asarray(args[iy], dtype=dt).reshape(ncol, -1)[:, cy].mean(dtype=np.float64).astype(dt)
+    def ev_p(n):
+        """A constant / parameter-only node, whatever its place in the evaluation order."""
+        if n.uid not in val:
+            if n.op == "const":
+                val[n.uid] = np.full((1, 1), n.val, dt)
+            elif n.op == "load":
+                val[n.uid] = np.asarray(args[n.val[0]], dtype=dt).reshape(-1)[n.val[1]].reshape(1, 1)
+            else:
+                val[n.uid] = np.asarray(_fn(n.op, [ev_p(x) for x in n.args], dt), dtype=dt)
+        return val[n.uid]
+
     for n in low.order:
         if n.op == "const":
             val[n.uid] = np.full((1, 1), n.val, dt)
         elif n.op == "load":
             ind, comp, cat = n.val
+            if cat == 6:
+                val[n.uid] = np.full((1, 1), shift[ind], dt)
+                continue
+            if cat == 7:
+                k = [(q[2], q[3]) for q in low.prescale["pairs"]].index((ind, comp))
+                sig = ev_p(low.prescale["sigma"])
+                col = np.asarray(args[ind], dtype=dt).reshape(ncol, -1)[:, comp].reshape(1, ncol)
+                val[n.uid] = ((col - shift[k]).astype(dt) * sig).astype(dt)
+                continue
             a = np.asarray(args[ind], dtype=dt)
             if cat == 2:
                 val[n.uid] = a.reshape(-1)[comp].reshape(1, 1)

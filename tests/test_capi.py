@@ -117,3 +117,26 @@ def test_sum_scheme_x_dtype_acc_matrix_compiles(head):
             if acc == "float64":
                 assert "double accd" in ks.source, (scheme, acc)
     assert len(seen) == 6        # auto == float32; every other combination is a different kernel
+
+
+def test_tensor_core_kernels_are_blackwell_native_sass():
+    """The hand-written tensor-core kernels really are tcgen05 / TMA / TMEM code: their sm_100a SASS carries the 5th-generation
+    MMA (UTCHMMA), TMA tensor loads (UTMALDG), tensor-memory loads / stores (LDTM / STTM) and the MMA-completion barrier
+    (UTCBAR) -- not mma.sync (HMMA) recompiled for a newer architecture.  (Mnemonics: /opt/skills/guides/B200_PROFILING.md.)"""
+    from keops_b200.codegen import conv_tc, knn_tc
+    blobs = {"kb200_knn_tc": knn_tc.KnnTensorCore(64, 10, "ArgKMin", True, device=-1).cubin,
+             "kb200_conv_tc": conv_tc.ConvTensorCore(16, 1, device=-1).cubin}
+    for name, cubin in blobs.items():
+        path = "/tmp/kb200_tc_%d.cubin" % os.getpid()
+        open(path, "wb").write(cubin)
+        try:
+            sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+        except FileNotFoundError:
+            pytest.skip("cuobjdump not available")
+        finally:
+            os.remove(path)
+        for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS"):
+            assert mnemonic in sass, (name, mnemonic)
+        assert "HMMA." not in sass.replace("UTCHMMA", ""), name            # no legacy mma.sync tensor-core path
+        if name == "kb200_conv_tc":
+            assert "STTM" in sass, name                                     # the row block is written to tensor memory once

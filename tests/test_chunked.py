@@ -78,8 +78,10 @@ def _inputs(formula, sizes, dtype, seed=0, integer=False):
             a = rng.integers(0, 2, shape).astype(np.float64)
         elif cat == 2:
             a = np.full(shape, 0.7)
-        else:
+        elif "SqDist" in formula or "Abs" in formula or "|" in formula or "Square((Var(0,200" in formula or "301" in formula:
             a = rng.random(shape) / np.sqrt(dim) if dim >= 100 else rng.standard_normal(shape)
+        else:
+            a = rng.standard_normal(shape)        # well-separated values (no fp32-level near-ties between columns)
         args[ind] = a.astype(dtype)
     return [args[k] for k in sorted(args)]
 

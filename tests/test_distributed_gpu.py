@@ -12,6 +12,14 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, world, port, q):
+    import traceback
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception:                                   # report instead of leaving the parent waiting on the queue
+        q.put((rank, ["EXCEPTION on rank %d:\n%s" % (rank, traceback.format_exc()[-3000:])]))
+
+
+def _worker_body(rank, world, port, q):
     import torch.distributed as dist
     from keops_b200.distributed import ShardedGenred, ShardedKernelSolve, shard_bounds, all_gather_rows
     from keops_b200.torch import Genred, KernelSolve
@@ -105,7 +113,7 @@ def test_two_rank_nccl_sharded_reduction(cuda_device):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(2)]
+    res = [q.get(timeout=420) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
     assert all(not fails for _, fails in res), res

@@ -234,3 +234,51 @@ def test_constant_folding_matches_reference(case):
     f = "Sum_Reduction(%s+Var(1,1,1),0)" % case["formula"]
     for who, got in (("lowering", dag_eval.evaluate(f, [], [x, y], "float64")), ("oracle", ko.genred(f, [], [x, y], "float64"))):
         assert np.abs(got - ref).max() <= 4e-16 * np.abs(ref).max(), (who, case["formula"], got.ravel().tolist(), ref.ravel().tolist())
+
+
+@pytest.mark.parametrize("name", ["gauss_sum_float32", "gauss_grad_x_float32", "gauss_grad_y_float32", "gauss_grad_b_float32",
+                                  "gauss_sum_axis0_float32", "gauss_randn_200x300_float32", "gauss_vec_b_float32"])
+def test_prescaled_rewrite_matches_reference(name):
+    """The pre-scaled variant (``emit._prescale_rewrite``: exponent scale folded into shifted + scaled coordinates, one
+    FP32 operation fewer per pair) evaluated in float32 -- rounding of the scaled coordinates included -- against the
+    reference's outputs: element-wise within 1e-5 of the condition scale; and it really drops the multiply."""
+    from keops_b200.codegen.emit import lower_reduction
+    from keops_b200.codegen.scalar import IJ, topo_order
+    from keops_b200.formulas.parser import parse_reduction
+    meta, args, ref = util.load_case(name)
+    got = dag_eval.evaluate(meta["formula"], meta["aliases"], args, "float32", fast=True, sizes=(meta["nx"], meta["ny"]), prescale=True)
+    assert got is not None, "the Gaussian-type formula %s must match the pre-scale pattern" % name
+    util.assert_close(got, ref, "float32", "prescaled " + name, **util.golden_scale(meta, args))
+    from keops_b200.binder import _normalise_aliases
+    red = parse_reduction(meta["formula"], _normalise_aliases(meta["aliases"]))
+
+    def pair_ops(low):
+        roots = [n for _, nodes, _ in low.acc_terms for n in nodes]
+        return sum(1 for n in topo_order(roots) if n.cls == IJ and n.op not in ("const", "load"))
+    assert pair_ops(lower_reduction(red, True, prescale=True)) == pair_ops(lower_reduction(red, True)) - 1
+
+
+def test_prescaled_rewrite_with_a_parameter_scale_and_an_offset_cloud():
+    """``Exp(-g * SqDist)`` with a run-time parameter (sigma = sqrt(g log2 e), correctly rounded) on clouds far from the
+    origin: the common shift keeps the rounding of the scaled coordinates relative to the clouds' extent."""
+    from oracle import keops_oracle as ko
+    rng = np.random.default_rng(5)
+    f = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,2,1),0)"
+    x = (rng.random((70, 3)) + 500.0).astype(np.float32)
+    y = (rng.random((90, 3)) + 500.0).astype(np.float32)
+    b = rng.standard_normal((90, 2)).astype(np.float32)
+    g = np.array([3.7], np.float32)
+    got = dag_eval.evaluate(f, [], [x, y, b, g], "float32", fast=True, prescale=True)
+    ref = ko.genred(f, [], [x, y, b, g], "float64")
+    util.assert_close(got, ref, "float32", "prescaled, parameter scale, offset clouds", scale=ko.abs_scale(f, [], [x, y, b, g]))
+
+
+def test_prescale_does_not_apply_to_other_formulas():
+    from keops_b200.codegen.emit import lower_reduction
+    from keops_b200.formulas.parser import parse_reduction
+    for f in ("Sum_Reduction(Exp(-Sqrt(SqDist(Var(0,3,0),Var(1,3,1))))*Var(2,1,1),0)",          # Laplacian: exp of a sqrt
+              "Sum_Reduction(Exp(Var(0,3,0)|Var(1,3,1))*Var(2,1,1),0)",                          # exp of a scalar product
+              "Sum_Reduction(SqDist(Var(0,3,0),Var(1,3,1))*Var(2,1,1),0)",                       # no exponential
+              "Sum_Reduction(Exp(-SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)",               # dimension > 8
+              "ArgKMin_Reduction(SqDist(Var(0,3,0),Var(1,3,1)),3,0)"):
+        assert lower_reduction(parse_reduction(f), True, prescale=True) is None, f
