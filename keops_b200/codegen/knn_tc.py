@@ -24,8 +24,11 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_knn_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")      # PTX wrappers, prepended (NVRTC has no include path)
-VERSION = "knn-tc-8"
-BM, BN, STAGES, HS = 256, 128, 4, 16
+VERSION = "knn-tc-9"
+BM, BN, STAGES, HS, KP, THREADS = 256, 128, 4, 8, 16, 576
+MAX_SMEM = 227 * 1024
+RESIDENT_MAX_COLS = 160      # D + 3 <= 160: the CTA's row operand stays in shared memory (>= 3 ring stages); beyond, k-blocks are streamed
+MAX_D = 1021                 # operand rows of at most 1024 bf16 columns
 ROW_BATCH = 1 << 20          # rows per filter launch: bounds the candidate workspace (CAP * 4 bytes per row)
 _lock = threading.RLock()
 
@@ -59,8 +62,8 @@ def eligible(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int) -> O
     # few rows against many columns (the reference's own KNN benchmark shape, 1e4 queries vs 1e6 points): the filter
     # splits the column range over gridDim.y, so the tensor-core path already pays off from ~1000 rows
     min_rows = 8192 if ncol < 65536 else 1024
-    if D < 16 or D > 141 or red.K > 16 or nrow < min_rows or ncol < 4096 or ncol >= (1 << 31) - BN:
-        return None                      # D <= 141: operand tiles of 2 + 4 stages must fit 227 KB of shared memory
+    if D < 16 or D > MAX_D or red.K > 16 or nrow < min_rows or ncol < 4096 or ncol >= (1 << 27):
+        return None                      # candidate tokens carry the 8-column group index in 24 bits
     return m
 
 
@@ -71,29 +74,41 @@ class KnnTensorCore:
         self.D, self.K, self.kind, self.fast, self.cap = D, K, kind, fast, cap
         # operand rows: D data columns + 3 penalty columns, as KBM 64-column blocks + one remainder block
         total = D + 3
+        self.stream = total > RESIDENT_MAX_COLS
         full, r = divmod(total, 64)
-        if r == 0:
+        if self.stream:                          # large D: whole 64-column k-blocks, streamed through the ring
+            self.KBM, self.REM = full + (1 if r else 0), 0
+        elif r == 0:
             self.KBM, self.REM = full - 1, 64
         else:
             self.KBM, self.REM = full, (16 if r <= 16 else (32 if r <= 32 else 64))
         self.DPG = 64 * self.KBM + self.REM
         self.outw = 2 * K if kind == "KMin_ArgKMin" else K
         out_code = {"ArgKMin": 0, "KMin": 1, "KMin_ArgKMin": 2}[kind]
+        # filter margin c: two bf16 roundings per product (2 u + u^2, u = 2^-8 -> 0.0078278) + fp32 accumulation over the
+        # K columns and the rounding of the exact path (each below D 2^-23 of sum |x_k y_k|)
+        self.c = 0.008 if D <= 160 else 0.00783 + D * 2.0 ** -21
+        self.BN = BN
+        blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K
+        state = BM * (KP + 3) * 4
+        fixed = 1024 + HS * BN * 4 + state + 640
+        if self.stream:
+            a_bytes, b_bytes = 0, (BM + BN) * 128
+        else:
+            a_bytes, b_bytes = 2 * blk(128), blk(BN)
+        self.STAGES = int(os.environ.get("KT_STAGES", min(STAGES, (MAX_SMEM - fixed - a_bytes) // b_bytes)))
+        assert self.STAGES >= 2, (D, self.STAGES)
         with open(_COMMON_PATH) as f:
             body = f.read()
         with open(_SRC_PATH) as f:
             body += f.read()
         defs = ("#define KT_D %d\n#define KT_KBM %d\n#define KT_REM %d\n#define KT_K %d\n#define KT_CAP %d\n"
                 "#define KT_OUT %d\n#define KT_FAST %d\n" % (D, self.KBM, self.REM, K, cap, out_code, 1 if fast else 0))
-        self.BN = int(os.environ.get("KT_BN", BN))
-        self.STAGES = int(os.environ.get("KT_STAGES", STAGES if self.BN == 128 else 6))
-        defs += "#define KT_BN %d\n#define KT_STAGES %d\n#define KT_DBG %d\n" % (self.BN, self.STAGES, int(os.environ.get("KT_DBG", 0)))
+        defs += "#define KT_STREAM %d\n#define KT_STAGES %d\n#define KT_C %.9gf\n" % (int(self.stream), self.STAGES, self.c)
         defs += "#define KT_SPIN %d\n" % int(os.environ.get("KT_SPIN", 0))
-        defs += "#define KT_PIPE %d\n" % int(os.environ.get("KT_PIPE", 0))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(fast), "kb200_knntc", VERSION)
-        blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K
-        self.smem = 1024 + 2 * blk(128) + self.STAGES * blk(self.BN) + HS * self.BN * 4 + 640
+        self.smem = fixed + a_bytes + self.STAGES * b_bytes
         self.smem = max(self.smem, 120 * 1024)     # one CTA per SM: each CTA allocates all 512 TMEM columns
         self.module = None
         if device >= 0:
@@ -109,6 +124,9 @@ class KnnTensorCore:
         """TMA descriptors of a bf16 operand array (n, DPG): the 64-column main blocks (128-byte swizzle) and the
         remainder block (swizzled at its own width), with boxes of ``box_rows`` rows."""
         pitch = self.DPG * 2
+        if self.REM == 0:              # streamed k-blocks: no remainder block
+            main = capi.tensor_map_2d(abf.data_ptr(), 2, 64 * self.KBM, n, pitch, 64, box_rows, 128)
+            return main, main
         rem = capi.tensor_map_2d(abf.data_ptr() + 128 * self.KBM, 2, self.REM, n, pitch, self.REM, box_rows, self.REM * 2)
         if self.KBM == 0:
             return rem, rem            # the main map is never dereferenced
@@ -154,13 +172,13 @@ class KnnTensorCore:
             if os.environ.get("KT_TIME"):
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record(stream_obj)
-            capi.launch(self.fn_filter, stream, (-(-m // BM), nsplit), (320,), self.smem,
+            capi.launch(self.fn_filter, stream, (-(-m // BM), nsplit), (THREADS,), self.smem,
                         [map_x, map_xr, map_y, map_yr, i64(m), i64(N), ptr(ypen.data_ptr()), ptr(xpen.data_ptr()),
                          ptr(cand.data_ptr()), ptr(count.data_ptr()), i32(tiles_per_split)])
             if os.environ.get("KT_TIME"):
                 ev1.record(stream_obj)
                 torch.cuda.synchronize()
-                print("KT_TIME filter %.3f ms (BN=%d STAGES=%d DBG=%s nsplit=%d)" % (ev0.elapsed_time(ev1), BN, self.STAGES, os.environ.get("KT_DBG", "0"), nsplit))
+                print("KT_TIME filter %.3f ms (STAGES=%d stream=%d nsplit=%d)" % (ev0.elapsed_time(ev1), self.STAGES, int(self.stream), nsplit))
             # select writes rows r0.. of `out` (or per-split lists); overflow rows are reported relative to the batch
             ov_before = overflow_count.clone() if r0 else None
             out_ptr = out.data_ptr() + r0 * self.outw * 4

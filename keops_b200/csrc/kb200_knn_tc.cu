@@ -22,21 +22,29 @@
 //
 // kb200_knn_filter : one CTA = 256 rows (two 128-row accumulators) x all columns, streamed in 128-column
 //   tiles.  Warp 0 = TMA producer (y tiles, 128B-swizzled, + the per-column penalty), warp 1 = MMA issuer,
-//   warps 2..9 = epilogue: one thread per row, tcgen05.ld of its 128 accumulators, FMNMX3 max-reduction against
-//   tau_i; survivors are appended to the row's candidate list and update Theta_i (register-resident list).
+//   warps 2..17 = epilogue: TWO threads per row, one per 64-column half of a tile: tcgen05.ld of its 64 accumulators,
+//   FMNMX3 max-reduction against tau_i.  The row's state (K best lower bounds, tau_i, candidate count) lives in shared
+//   memory and is shared by the row's two threads: a survivor group is appended as one token (8-column group index +
+//   8-bit hit mask) and its best lower bound is inserted into the row's list under a per-row lock.
 //   4-stage smem ring, double-buffered TMEM accumulators (2 row blocks x 2 buffers x 128 columns = 512).
-//   (Measured alternative, not kept: two threads per row, one per 64-column half as in kb200_conv_tc -- ncu shows the
-//   one-thread-per-row epilogue latency-bound (tensor pipe 47 %, ALU 40 %, issue 32 % busy) -- but each half then
-//   thresholds on its own K-th best bound: 324 instead of ~200 candidates per row at D = 64, K = 10, N = 1e6, the
-//   filter 158 -> 180 ms and most rows overflow the candidate slots.)
+//   Why this shape (ncu source view of the previous one-thread-per-row epilogue, profiles/r01_ncu_knn_filter_d64.txt:
+//   tensor pipe 47 % busy): the 8 epilogue warps were the critical path and latency-bound -- per tile each spent
+//   ~160 clk waiting for tcgen05.ld, ~255 clk in the FMNMX3 reduction, ~400 clk in the divergent survivor path (52
+//   instructions at ~8 clk each: select tree, penalty load, sorted insertion) and 440 clk waiting for the next
+//   accumulator, because the MMA warp in turn waited for the slowest of the four warps of a row block.  Two threads
+//   per row halve the per-warp work, give every scheduler four warps to overlap TMEM reads with the reductions, and the
+//   shared row state keeps ONE threshold per row (two private lists per row had cost 324 instead of ~200 candidates).
 // kb200_knn_prep   : fp32 -> bf16 operand rows (data, penalty columns, zero padding) + per-row penalty terms.
-// kb200_knn_select : one warp per row, exact distances of the candidates + ordered top-K (ties -> smallest j).
+// kb200_knn_select : one warp per row, exact distances of the candidates (tokens decoded) + ordered top-K (ties ->
+//   smallest j).
 //
 // Compile-time parameters (defined by keops_b200/codegen/knn_tc.py): KT_D (true dimension); the bf16 operand
 // rows hold D + 3 columns padded to KT_DPG = 64 * KT_KBM + KT_REM (KT_KBM 128-byte-swizzled 64-column blocks
-// plus one remainder block of KT_REM = 16 / 32 / 64 columns swizzled at its own width); KT_K, KT_CAP (candidate
-// slots per row, multiple of 32), KT_OUT (0 ArgKMin, 1 KMin, 2 KMin_ArgKMin), KT_FAST (1: FTZ arithmetic of
-// --use_fast_math, like the CUDA-core kernel).
+// plus one remainder block of KT_REM = 0 / 16 / 32 / 64 columns swizzled at its own width); KT_STREAM (0: the CTA's
+// row operand stays resident in shared memory for all of K; 1: large D -- both operands go through the ring one
+// 64-column k-block at a time and a tile accumulates over the k-blocks in TMEM; KT_REM = 0); KT_STAGES; KT_K, KT_CAP
+// (candidate tokens per row, multiple of 32), KT_OUT (0 ArgKMin, 1 KMin, 2 KMin_ArgKMin), KT_FAST (1: FTZ arithmetic
+// of --use_fast_math, like the CUDA-core kernel), KT_C (the filter's relative margin c, as a float literal).
 
 #ifndef KT_D
 #define KT_D 64
@@ -46,37 +54,44 @@
 #define KT_CAP 320
 #define KT_OUT 0
 #define KT_FAST 1
+#define KT_STREAM 0
+#define KT_STAGES 4
+#define KT_C 0.008f
 #endif
 
 #define KT_BM 256                             /* rows per CTA: two 128-row accumulators                         */
-#ifndef KT_BN
-#define KT_BN 128                             /* columns per tile (= N of one tcgen05.mma): 64 or 128           */
-#endif
-#ifndef KT_PIPE
-#define KT_PIPE 0                             /* 1: software-pipelined TMEM reads in the filter's epilogue (measured
-                                                 on B200, D = 64, M = N = 1e6: 183 ms vs 162 ms un-pipelined -- kept as an
-                                                 opt-in experiment)                                              */
-#endif
-#ifndef KT_DBG
-#define KT_DBG 0                              /* 1: no rare path, 2: TMEM loads only, 3: no TMEM loads (timing experiments) */
-#endif
-#define KT_NBUF (512 / (2 * KT_BN))           /* TMEM accumulator buffers per row block (all 512 columns used)   */
+#define KT_BN 128                             /* columns per tile (= N of one tcgen05.mma)                      */
+#define KT_NBUF 2                             /* TMEM accumulator buffers per row block (2 x 2 x 128 = 512 columns) */
 #define KT_DPG (64 * KT_KBM + KT_REM)
-#ifndef KT_STAGES
-#define KT_STAGES 4
-#endif
-#define KT_HS 16                              /* slots of the column-penalty ring                               */
-#define KT_C 0.008f
+#define KT_HS 8                               /* slots of the column-penalty ring                               */
+#define KT_KP 16                              /* row stride (floats) of the shared lists of lower bounds: K <= 16 */
+#define KT_EPI_WARPS 16                       /* epilogue warps: (lane quarter) x (row block) x (column half)   */
+#define KT_THREADS (64 + 32 * KT_EPI_WARPS)
 #define KT_TILE_BYTES(rows) ((rows) * 128)                    /* rows x 64 bf16                                 */
 #define KT_RTILE_BYTES(rows) ((rows) * KT_REM * 2)            /* rows x KT_REM bf16                             */
 #define KT_BLK_BYTES(rows) (KT_KBM * KT_TILE_BYTES(rows) + KT_RTILE_BYTES(rows))   /* one operand block, all of K */
+#if KT_STREAM
+#define KT_A_BYTES 0
+#define KT_B_BYTES KT_TILE_BYTES(KT_BM + KT_BN)               /* one ring stage: a k-block of both operands     */
+#else
 #define KT_A_BYTES (2 * KT_BLK_BYTES(128))
 #define KT_B_BYTES KT_BLK_BYTES(KT_BN)
-#define KT_SMEM_BYTES (1024 + KT_A_BYTES + KT_STAGES * KT_B_BYTES + KT_HS * KT_BN * 4 + 640) /* mirrored in knn_tc.py */
-
+#endif
+#define KT_STATE_BYTES (KT_BM * (KT_KP + 3) * 4)              /* lists + tau + count + lock of the CTA's rows   */
+/* mirrored in knn_tc.py */
+#define KT_SMEM_BYTES (1024 + KT_A_BYTES + KT_STAGES * KT_B_BYTES + KT_HS * KT_BN * 4 + KT_STATE_BYTES + 640)
 
 // bf16 x bf16 -> f32, A and B K-major, M = 128, N = KT_BN
 #define KT_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | (((u32)KT_BN >> 3) << 17) | ((128u >> 4) << 24))
+
+__device__ __forceinline__ float4 kt_lds128_volatile(u32 addr) {
+  float4 v;
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void kt_sts128_volatile(u32 addr, float a, float b, float c, float d) {
+  asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // prep: fp32 rows -> bf16 operand rows of KT_DPG columns + fp32 penalty
@@ -117,7 +132,7 @@ kb200_knn_prep(const long long n, const float* __restrict__ a, unsigned short* _
 // ------------------------------------------------------------------------------------------------
 // filter
 // ------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(320, 1)
+extern "C" __global__ void __launch_bounds__(KT_THREADS, 1)
 kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constant__ KtTensorMap map_xr,
                  const __grid_constant__ KtTensorMap map_y, const __grid_constant__ KtTensorMap map_yr,
                  const long long nrow, const long long ncol, const float* __restrict__ ypen,
@@ -127,17 +142,23 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
   const u32 raw = kt_smem(kt_raw);
   const u32 base = (raw + 1023u) & ~1023u;                       // swizzle atoms need (up to) 1024-byte alignment
   unsigned char* gbase = kt_raw + (base - raw);
-  const u32 sA = base;                                           // 2 row blocks x [KBM main tiles | remainder tile]
-  const u32 sB = sA + KT_A_BYTES;                                // STAGES x [KBM main tiles | remainder tile]
+  const u32 sA = base;                                           // resident mode: 2 row blocks x [KBM main tiles | remainder tile]
+  const u32 sB = sA + KT_A_BYTES;                                // STAGES x stage (see KT_B_BYTES)
   const u32 sH = sB + KT_STAGES * KT_B_BYTES;                    // ring of column penalties (KT_HS x KT_BN floats)
   const float* hy = reinterpret_cast<const float*>(gbase + KT_A_BYTES + KT_STAGES * KT_B_BYTES);
-  const u32 sBar = sH + KT_HS * KT_BN * 4;
-  // barriers (8 bytes each): full[8] @0, empty[8] @64, tfull[buf][rb] (<= 8) @128, tempty[buf][rb] @192,
-  //                          hfull[16] @256, hempty[16] @384, afull @512, tmem pointer @520
+  // per-row state shared by the row's two epilogue threads: K best lower bounds (descending), tau, token count, lock
+  const u32 sLst = sH + KT_HS * KT_BN * 4;
+  unsigned char* gstate = gbase + KT_A_BYTES + KT_STAGES * KT_B_BYTES + KT_HS * KT_BN * 4;
+  volatile float* lst_s = reinterpret_cast<volatile float*>(gstate);
+  volatile float* tau_s = reinterpret_cast<volatile float*>(gstate + KT_BM * KT_KP * 4);
+  int* cnt_s = reinterpret_cast<int*>(gstate + KT_BM * (KT_KP + 1) * 4);
+  int* lock_s = reinterpret_cast<int*>(gstate + KT_BM * (KT_KP + 2) * 4);
+  const u32 sBar = sLst + KT_STATE_BYTES;
+  // barriers (8 bytes each): full[8] @0, empty[8] @64, tfull[buf][rb] (4) @128, tempty[buf][rb] @192,
+  //                          hfull[8] @256, afull @512, tmem pointer @520
   const u32 bFull = sBar, bEmpty = sBar + 64, bTFull = sBar + 128, bTEmpty = sBar + 192, bAFull = sBar + 512;
-  const u32 bHFull = sBar + 256, bHEmpty = sBar + 384;
-  volatile u32* tmem_slot =
-      reinterpret_cast<volatile u32*>(gbase + KT_A_BYTES + KT_STAGES * KT_B_BYTES + KT_HS * KT_BN * 4 + 520);
+  const u32 bHFull = sBar + 256;
+  volatile u32* tmem_slot = reinterpret_cast<volatile u32*>(gstate + KT_STATE_BYTES + 520);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row_base = (long long)blockIdx.x * KT_BM;
@@ -150,14 +171,21 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < KT_STAGES; s++) { kt_mbar_init(bFull + 8 * s, 1); kt_mbar_init(bEmpty + 8 * s, 1); }
-    for (int b = 0; b < 2 * KT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, 4); }
-    for (int h = 0; h < KT_HS; h++) { kt_mbar_init(bHFull + 8 * h, 1); kt_mbar_init(bHEmpty + 8 * h, 8); }
+    for (int b = 0; b < 2 * KT_NBUF; b++) { kt_mbar_init(bTFull + 8 * b, 1); kt_mbar_init(bTEmpty + 8 * b, KT_EPI_WARPS / 2); }
+    for (int h = 0; h < KT_HS; h++) kt_mbar_init(bHFull + 8 * h, 1);
     kt_mbar_init(bAFull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sBar + 520), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int r = threadIdx.x; r < KT_BM; r += KT_THREADS) {
+    tau_s[r] = (row_base + r < nrow) ? -KT_INF : KT_INF;         // rows past the end never produce a candidate
+    cnt_s[r] = 0;
+    lock_s[r] = 0;
+#pragma unroll
+    for (int l = 0; l < KT_KP; l++) lst_s[r * KT_KP + l] = -KT_INF;
   }
   kt_fence_before();
   __syncthreads();
@@ -166,6 +194,7 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
+#if !KT_STREAM
     if (kt_elect()) {
       kt_mbar_expect_tx(bAFull, KT_A_BYTES);
       for (int rb = 0; rb < 2; rb++) {
@@ -175,74 +204,159 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
       }
     }
     __syncwarp();
+#endif
+    // The ring of column penalties needs no "empty" barrier: a slot is refilled KT_HS = 8 tiles later, and by then the
+    // wait on this tile's operand stage has ordered the producer behind the MMA warp (at most KT_STAGES tiles ahead of
+    // it), which is itself at most KT_NBUF tiles ahead of the slowest epilogue warp: KT_STAGES + KT_NBUF + 1 <= KT_HS.
     for (int t = 0; t < ntiles; t++) {
-      const int s = t % KT_STAGES, h = t % KT_HS;
+      const int h = t % KT_HS;
+#if KT_STREAM
+      for (int kb = 0; kb < KT_KBM; kb++) {
+        const int it = t * KT_KBM + kb, s = it % KT_STAGES;
+        kt_mbar_wait(bEmpty + 8 * s, ((it / KT_STAGES) & 1) ^ 1);
+        if (kt_elect()) {
+          const u32 st = sB + s * KT_B_BYTES;
+          kt_mbar_expect_tx(bFull + 8 * s, KT_B_BYTES);
+          kt_tma_2d(st, &map_x, kb * 64, (int)row_base, bFull + 8 * s);
+          kt_tma_2d(st + KT_TILE_BYTES(128), &map_x, kb * 64, (int)(row_base + 128), bFull + 8 * s);
+          kt_tma_2d(st + KT_TILE_BYTES(256), &map_y, kb * 64, (t0 + t) * KT_BN, bFull + 8 * s);
+          if (kb == 0) {       // column penalties of this tile (only the survivor path of the epilogue reads them)
+            kt_mbar_expect_tx(bHFull + 8 * h, KT_BN * 4);
+            kt_bulk_1d(sH + h * KT_BN * 4, ypen + (long long)(t0 + t) * KT_BN, KT_BN * 4, bHFull + 8 * h);
+          }
+        }
+        __syncwarp();
+      }
+#else
+      const int s = t % KT_STAGES;
       kt_mbar_wait(bEmpty + 8 * s, ((t / KT_STAGES) & 1) ^ 1);
-      kt_mbar_wait(bHEmpty + 8 * h, ((t / KT_HS) & 1) ^ 1);
       if (kt_elect()) {
         kt_mbar_expect_tx(bFull + 8 * s, KT_B_BYTES);
         for (int kb = 0; kb < KT_KBM; kb++)
           kt_tma_2d(sB + s * KT_B_BYTES + kb * KT_TILE_BYTES(KT_BN), &map_y, kb * 64, (t0 + t) * KT_BN, bFull + 8 * s);
+#if KT_REM
         kt_tma_2d(sB + s * KT_B_BYTES + KT_KBM * KT_TILE_BYTES(KT_BN), &map_yr, 0, (t0 + t) * KT_BN, bFull + 8 * s);
-        // column penalties of this tile (only the rare path of the epilogue reads them)
+#endif
+        // column penalties of this tile (only the survivor path of the epilogue reads them)
         kt_mbar_expect_tx(bHFull + 8 * h, KT_BN * 4);
         kt_bulk_1d(sH + h * KT_BN * 4, ypen + (long long)(t0 + t) * KT_BN, KT_BN * 4, bHFull + 8 * h);
       }
       __syncwarp();
+#endif
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
-    kt_mbar_wait(bAFull, 0);
-    for (int t = 0; t < ntiles; t++) {
-      const int s = t % KT_STAGES, buf = t % KT_NBUF;
-      kt_mbar_wait(bFull + 8 * s, (t / KT_STAGES) & 1);
-#pragma unroll
-      for (int rb = 0; rb < 2; rb++) {
-        // each (buffer, row block) accumulator has its own full / empty pair: the other row block's MMAs
-        // cover the commit -> epilogue -> release round trip of this one
-        kt_mbar_wait(bTEmpty + 8 * (buf * 2 + rb), ((t / KT_NBUF) & 1) ^ 1);
+    // ===================== MMA issuer: ONE elected thread runs the whole loop =====================
+    // (ncu source view of the first version of this kernel: with one warp-wide elect + reconvergence per accumulator and
+    // the stage / buffer / parity arithmetic in the tile loop, the issuing warp executed ~200 dependent instructions per
+    // tile -- ~880 clk against 640 clk of tensor-pipe work -- and WAS the critical path.  Now the tile loop is unrolled over
+    // the stage x buffer period, so every descriptor is a loop-invariant base plus a compile-time constant.)
+    if (kt_elect()) {
+#if KT_STREAM
+      const u64 d0 = kt_smem_desc(sB, 128);
+      for (int t = 0; t < ntiles; t++) {
+        const int buf = t % KT_NBUF;
+        kt_mbar_wait(bTEmpty + 8 * (buf * 2 + 0), ((t / KT_NBUF) & 1) ^ 1);
+        kt_mbar_wait(bTEmpty + 8 * (buf * 2 + 1), ((t / KT_NBUF) & 1) ^ 1);
         kt_fence_after();
-        if (kt_elect()) {
-          const u32 d = tmem + (u32)((buf * 2 + rb) * KT_BN);
+        const u32 dt = tmem + (u32)(buf * 2 * KT_BN);
+        const int it0 = t * KT_KBM;
+#pragma unroll 1
+        for (int kb0 = 0; kb0 < KT_KBM; kb0 += KT_STAGES) {
 #pragma unroll
-          for (int kb = 0; kb < KT_KBM; kb++) {
-            const u64 ad = kt_smem_desc(sA + rb * KT_BLK_BYTES(128) + kb * KT_TILE_BYTES(128), 128);
-            const u64 bd = kt_smem_desc(sB + s * KT_B_BYTES + kb * KT_TILE_BYTES(KT_BN), 128);
+          for (int u = 0; u < KT_STAGES; u++) {
+            const int kb = kb0 + u;
+            if (kb < KT_KBM) {
+              const int it = it0 + kb, s = it % KT_STAGES;
+              kt_mbar_wait(bFull + 8 * s, (it / KT_STAGES) & 1);
+              kt_fence_after();
+              const u64 st = d0 + (u64)((u32)(s * KT_B_BYTES) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {            // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
-              if (KT_DBG != 6) kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), KT_IDESC, (u32)((kb | k) != 0));
-              if (KT_DBG == 7) kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), KT_IDESC, 1u);
+              for (int rb = 0; rb < 2; rb++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  kt_mma_bf16(dt + (u32)(rb * KT_BN), st + (u64)((rb * KT_TILE_BYTES(128)) >> 4) + (u64)(2 * k),
+                              st + (u64)(KT_TILE_BYTES(256) >> 4) + (u64)(2 * k), KT_IDESC, (u32)((kb | k) != 0));
+              }
+              kt_mma_commit(bEmpty + 8 * s);               // the stage may be refilled once these MMAs have read it
             }
           }
-          {
-            const u64 ad = kt_smem_desc(sA + rb * KT_BLK_BYTES(128) + KT_KBM * KT_TILE_BYTES(128), KT_REM * 2);
-            const u64 bd = kt_smem_desc(sB + s * KT_B_BYTES + KT_KBM * KT_TILE_BYTES(KT_BN), KT_REM * 2);
-#pragma unroll
-            for (int k = 0; k < KT_REM / 16; k++)
-              kt_mma_bf16(d, ad + (u64)(2 * k), bd + (u64)(2 * k), KT_IDESC, (u32)((KT_KBM | k) != 0));
-          }
-          kt_mma_commit(bTFull + 8 * (buf * 2 + rb));  // this accumulator is complete
-          if (rb == 1) kt_mma_commit(bEmpty + 8 * s);  // smem stage may be refilled once these MMAs have read it
         }
-        __syncwarp();
+        kt_mma_commit(bTFull + 8 * (buf * 2 + 0));         // both accumulators of the tile are complete
+        kt_mma_commit(bTFull + 8 * (buf * 2 + 1));
       }
+#else
+      // period of (stage, buffer): tiles t = KT_PER * it + u use stage u % KT_STAGES and buffer u % KT_NBUF
+      constexpr int KT_PER = (KT_STAGES % KT_NBUF == 0) ? KT_STAGES : KT_STAGES * KT_NBUF;
+      const u64 a0 = kt_smem_desc(sA, 128), b0 = kt_smem_desc(sB, 128);
+#if KT_REM
+      const u64 ar0 = kt_smem_desc(sA + KT_KBM * KT_TILE_BYTES(128), KT_REM * 2);
+      const u64 br0 = kt_smem_desc(sB + KT_KBM * KT_TILE_BYTES(KT_BN), KT_REM * 2);
+#endif
+      kt_mbar_wait(bAFull, 0);
+#pragma unroll 1
+      for (int tt = 0, it = 0; tt < ntiles; tt += KT_PER, it++) {
+#pragma unroll
+        for (int u = 0; u < KT_PER; u++) {
+          if (tt + u < ntiles) {
+            const int s = u % KT_STAGES, buf = u % KT_NBUF;
+            // (t / KT_STAGES) & 1 and ((t / KT_NBUF) & 1) ^ 1 for t = KT_PER * it + u
+            const u32 pf = ((u32)(it * (KT_PER / KT_STAGES)) + (u32)(u / KT_STAGES)) & 1u;
+            const u32 pe = (((u32)(it * (KT_PER / KT_NBUF)) + (u32)(u / KT_NBUF)) & 1u) ^ 1u;
+            kt_mbar_wait(bFull + 8 * s, pf);
+#pragma unroll
+            for (int rb = 0; rb < 2; rb++) {
+              // each (buffer, row block) accumulator has its own full / empty pair: the other row block's MMAs
+              // cover the commit -> epilogue -> release round trip of this one
+              kt_mbar_wait(bTEmpty + 8 * (buf * 2 + rb), pe);
+              kt_fence_after();
+              const u32 d = tmem + (u32)((buf * 2 + rb) * KT_BN);
+#pragma unroll
+              for (int kb = 0; kb < KT_KBM; kb++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)            // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
+                  kt_mma_bf16(d, a0 + (u64)((rb * KT_BLK_BYTES(128) + kb * KT_TILE_BYTES(128)) >> 4) + (u64)(2 * k),
+                              b0 + (u64)((s * KT_B_BYTES + kb * KT_TILE_BYTES(KT_BN)) >> 4) + (u64)(2 * k), KT_IDESC,
+                              (u32)((kb | k) != 0));
+              }
+#if KT_REM
+#pragma unroll
+              for (int k = 0; k < KT_REM / 16; k++)
+                kt_mma_bf16(d, ar0 + (u64)((rb * KT_BLK_BYTES(128)) >> 4) + (u64)(2 * k),
+                            br0 + (u64)((s * KT_B_BYTES) >> 4) + (u64)(2 * k), KT_IDESC, (u32)((KT_KBM | k) != 0));
+#endif
+              kt_mma_commit(bTFull + 8 * (buf * 2 + rb));  // this accumulator is complete
+              if (rb == 1) kt_mma_commit(bEmpty + 8 * s);  // smem stage may be refilled once these MMAs have read it
+            }
+          }
+        }
+      }
+#endif
     }
+    __syncwarp();
   } else {
-    // ===================== epilogue: one thread per row =====================
-    const int q = warp & 3, rb = (warp - 2) >> 2;
-    const long long i = row_base + rb * 128 + q * 32 + lane;
+    // ===================== epilogue: two threads per row, one per 64-column half of every tile =====================
+    // (a warp reads the TMEM lanes 32 * (warp % 4) .. + 31)
+    const int ew = warp - 2, q = warp & 3, rb = (ew >> 2) & 1, half = ew >> 3;
+    const int rl = rb * 128 + q * 32 + lane;                       // row inside the CTA
+    const long long i = row_base + rl;
     const bool live = i < nrow;
     const float cx = live ? xpen[i] : 0.0f;
-    float tau = live ? -KT_INF : KT_INF;
-    float lst[KT_K];                                  // K largest lower bounds, descending
-#pragma unroll
-    for (int l = 0; l < KT_K; l++) lst[l] = -KT_INF;
-    int cnt = 0;
     int* my_cand = cand + ((live ? i : 0) * (long long)gridDim.y + blockIdx.y) * (long long)KT_CAP;
-    const float cy_scale = 2.0f * KT_C / (1.0f - KT_C);   // c|y|^2 = cy_scale * (1-c)|y|^2/2
-    // One 64-column chunk of a tile: FMNMX max-reduction against tau_i, rare path for the survivors.
-    auto process = [&](const float* u, const int t, const int c, const float* hyt, const int hslot, bool& hy_ready) {
-      float mg[8];                                    // maxima of the eight 8-column sub-groups
+    const float cy_scale = 2.0f * KT_C / (1.0f - KT_C);            // c|y|^2 = cy_scale * (1-c)|y|^2/2
+    const u32 my_lst = sLst + (u32)(rl * KT_KP * 4);
+    for (int t = 0; t < ntiles; t++) {
+      const int buf = t % KT_NBUF, hslot = t % KT_HS;
+      kt_mbar_wait(bTFull + 8 * (buf * 2 + rb), (t / KT_NBUF) & 1);
+      kt_fence_after();
+      float u[64];
+      kt_tmem_ld64_nowait(tmem + ((u32)(q * 32) << 16) + (u32)((buf * 2 + rb) * KT_BN + half * 64), u);
+      float tau = tau_s[rl];                          // the row's current threshold (only ever grows: a stale value is safe)
+      kt_tmem_wait_ld();
+      // the accumulator buffer goes back to the MMA warp before any (data-dependent) candidate processing
+      kt_fence_before();
+      __syncwarp();
+      if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));
+      float mg[8];                                    // maxima of the eight 8-column groups
 #pragma unroll
       for (int g = 0; g < 8; g++) {
         float m = fmaxf(fmaxf(u[8 * g + 0], u[8 * g + 1]), u[8 * g + 2]);
@@ -252,111 +366,66 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
       }
       const float m01 = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
       const float m23 = fmaxf(fmaxf(mg[4], mg[5]), fmaxf(mg[6], mg[7]));
-#if KT_DBG >= 2
-      if (fmaxf(m01, m23) == 12345.678f) cnt++;
-#endif
-      if (KT_DBG == 0 && fmaxf(m01, m23) >= tau) {
-        // rare path (a few hundred times per row over the whole stream): everything statically indexed
+      if (fmaxf(m01, m23) >= tau) {
+        // survivor path (a few hundred times per row over the whole stream): everything statically indexed
+        const float* hyt = hy + hslot * KT_BN + half * 64;
+        bool hy_ready = false;                        // the penalty tile is waited for on first use only
 #pragma unroll
         for (int g = 0; g < 8; g++) {
           if (mg[g] >= tau) {
-            u32 hits = 0;
+            u32 mask = 0;
 #pragma unroll
-            for (int e = 0; e < 8; e++) hits |= (u[8 * g + e] >= tau) ? (1u << e) : 0u;
-            const long long j0 = (long long)(t0 + t) * KT_BN + c * 64 + g * 8;
-            while (hits) {
-              const int e = __ffs(hits) - 1;
-              hits &= hits - 1;
-              // 8 -> 1 select tree instead of a dynamically indexed (local-memory) array
-              const float a0 = (e & 1) ? u[8 * g + 1] : u[8 * g + 0], a1 = (e & 1) ? u[8 * g + 3] : u[8 * g + 2];
-              const float a2 = (e & 1) ? u[8 * g + 5] : u[8 * g + 4], a3 = (e & 1) ? u[8 * g + 7] : u[8 * g + 6];
-              const float b0 = (e & 2) ? a1 : a0, b1 = (e & 2) ? a3 : a2;
-              const float ue = (e & 4) ? b1 : b0;
-              if (ue >= tau && j0 + e < ncol) {
-                if (cnt < KT_CAP) my_cand[cnt] = (int)(j0 + e);
-                cnt++;
+            for (int e = 0; e < 8; e++) mask |= (u[8 * g + e] >= tau) ? (1u << e) : 0u;
+            const long long j0 = (long long)(t0 + t) * KT_BN + half * 64 + g * 8;
+            const bool whole = j0 + 8 <= ncol;        // the group lies inside the column range
+            if (!whole) mask = (ncol > j0) ? (mask & ((1u << (int)(ncol - j0)) - 1u)) : 0u;
+            if (mask) {
+              // one token per surviving group: 8-column group index (24 bits) | hit mask (8 bits)
+              const int slot = atomicAdd(&cnt_s[rl], 1);
+              if (slot < KT_CAP) my_cand[slot] = (int)((((u32)(j0 >> 3)) << 8) | mask);
+              if (whole) {
                 if (!hy_ready) { kt_mbar_wait(bHFull + 8 * hslot, (t / KT_HS) & 1); hy_ready = true; }
-                const float lo = ue - cy_scale * hyt[c * 64 + g * 8 + e];
-                if (lo > lst[KT_K - 1]) {
+                // lower bound of the group's best column: its U is mg[g], its penalty is at most the largest of the hits'
+                float hm = 0.0f;
+                for (u32 mm = mask; mm; mm &= mm - 1) hm = fmaxf(hm, hyt[g * 8 + __ffs(mm) - 1]);
+                const float lo = mg[g] - cy_scale * hm;
+                if (lo > lst_s[rl * KT_KP + KT_K - 1]) {
+                  // sorted insertion into the row's shared list under the row's lock (contended only by the thread
+                  // that owns the other column half of this row)
+                  bool done = false;
+                  while (!done) {
+                    if (atomicCAS(&lock_s[rl], 0, 1) == 0) {
+                      float l[KT_KP];
 #pragma unroll
-                  for (int l = KT_K - 1; l > 0; --l) {
-                    if (lo > lst[l - 1]) lst[l] = lst[l - 1];
-                    else if (lo > lst[l]) lst[l] = lo;
+                      for (int v4 = 0; v4 < (KT_K + 3) / 4; v4++) {
+                        const float4 w = kt_lds128_volatile(my_lst + 16 * v4);
+                        l[4 * v4] = w.x; l[4 * v4 + 1] = w.y; l[4 * v4 + 2] = w.z; l[4 * v4 + 3] = w.w;
+                      }
+                      float v = lo;
+#pragma unroll
+                      for (int k = 0; k < KT_K; k++) { const float hi = fmaxf(l[k], v); v = fminf(l[k], v); l[k] = hi; }
+#pragma unroll
+                      for (int v4 = 0; v4 < (KT_K + 3) / 4; v4++)
+                        kt_sts128_volatile(my_lst + 16 * v4, l[4 * v4], l[4 * v4 + 1], l[4 * v4 + 2], l[4 * v4 + 3]);
+                      tau = l[KT_K - 1] - cx;
+                      tau_s[rl] = tau;
+                      __threadfence_block();
+                      atomicExch(&lock_s[rl], 0);
+                      done = true;
+                    }
                   }
-                  if (lo > lst[0]) lst[0] = lo;
-                  tau = lst[KT_K - 1] - cx;
                 }
               }
             }
           }
         }
       }
-    };
-#if KT_PIPE && KT_BN == 128 && KT_DBG < 3
-    // Software-pipelined TMEM reads (ncu of the un-pipelined loop: every epilogue warp idles ~2.4 cycles per issued
-    // instruction on the tcgen05.ld round trip -- long_scoreboard -- with only two such warps per scheduler): the 64-column
-    // half that is processed next is always in flight while the current one is reduced, across tile boundaries too.
-    // uA / uB are two statically indexed register buffers; tcgen05.wait::ld retires every load issued so far.
-    float uA[64], uB[64];
-    if (ntiles > 0) {
-      kt_mbar_wait(bTFull + 8 * (0 * 2 + rb), 0);
-      kt_fence_after();
-      kt_tmem_ld64_nowait(tmem + ((u32)(q * 32) << 16) + (u32)((0 * 2 + rb) * KT_BN), uA);
     }
-    for (int t = 0; t < ntiles; t++) {
-      const int buf = t % KT_NBUF, hslot = t % KT_HS;
-      const float* hyt = hy + hslot * KT_BN;
-      bool hy_ready = false;                          // the penalty tile is waited for on first use only
-      const u32 tbase = tmem + ((u32)(q * 32) << 16) + (u32)((buf * 2 + rb) * KT_BN);
-      kt_tmem_wait_ld();                              // uA = columns 0..63 of tile t
-      kt_tmem_ld64_nowait(tbase + 64u, uB);           // columns 64..127 fly while uA is reduced
-      process(uA, t, 0, hyt, hslot, hy_ready);
-      kt_tmem_wait_ld();                              // uB landed: the accumulator buffer goes back to the MMA warp
-      kt_fence_before();
-      __syncwarp();
-      if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));
-      if (t + 1 < ntiles) {
-        const int nb = (t + 1) % KT_NBUF;
-        kt_mbar_wait(bTFull + 8 * (nb * 2 + rb), ((t + 1) / KT_NBUF) & 1);
-        kt_fence_after();
-        kt_tmem_ld64_nowait(tmem + ((u32)(q * 32) << 16) + (u32)((nb * 2 + rb) * KT_BN), uA);
-      }
-      process(uB, t, 1, hyt, hslot, hy_ready);
-      __syncwarp();
-      if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
-    }
-#else
-    for (int t = 0; t < ntiles; t++) {
-      const int buf = t % KT_NBUF, hslot = t % KT_HS;
-      kt_mbar_wait(bTFull + 8 * (buf * 2 + rb), (t / KT_NBUF) & 1);
-      kt_fence_after();
-      const float* hyt = hy + hslot * KT_BN;
-      bool hy_ready = false;                          // the penalty tile is waited for on first use only
-      const u32 tbase = tmem + ((u32)(q * 32) << 16) + (u32)((buf * 2 + rb) * KT_BN);
-      // the whole row of this tile goes to registers first, so that the accumulator buffer is handed back to
-      // the MMA warp before any (data-dependent) candidate processing
-      float uu[KT_BN];
-#if KT_DBG >= 3
-#pragma unroll
-      for (int e = 0; e < KT_BN; e++) uu[e] = -1.0f;
-#else
-#pragma unroll
-      for (int c = 0; c < KT_BN / 64; c++) kt_tmem_ld64_nowait(tbase + (u32)(c * 64), uu + c * 64);
-      kt_tmem_wait_ld();
-#endif
-      kt_fence_before();
-      __syncwarp();
-      if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));
-#pragma unroll
-      for (int c = 0; c < KT_BN / 64; c++) process(uu + c * 64, t, c, hyt, hslot, hy_ready);
-      __syncwarp();
-      if (lane == 0) kt_mbar_arrive(bHEmpty + 8 * hslot);
-    }
-#endif
-    if (live) cand_count[i * (long long)gridDim.y + blockIdx.y] = cnt;
   }
   kt_fence_before();
   __syncthreads();
+  if (threadIdx.x < KT_BM && row_base + threadIdx.x < nrow)
+    cand_count[(row_base + threadIdx.x) * (long long)gridDim.y + blockIdx.y] = cnt_s[threadIdx.x];
   if (warp == 0) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -367,7 +436,13 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
 // select: exact fp32 distances of the candidates (the CUDA-core kernel's operation order: d0*d0, then
 // fma(d_k, d_k, acc) for k = 1..D-1) and the K smallest in (distance, index) order
 // ------------------------------------------------------------------------------------------------
-// x row in registers (loaded once per warp row), y row streamed with 16-byte loads when D allows it
+#if KT_D <= 160
+#define KT_XREG 1                             /* the x row lives in registers (loaded once per warp row)        */
+#else
+#define KT_XREG 0                             /* large D: x is re-read through L1 (same address in every lane)  */
+#endif
+// y row streamed with 16-byte loads when D allows it
+#if KT_XREG
 __device__ __forceinline__ float kt_sqdist(const float (&xr)[KT_D], const float* __restrict__ yr) {
   float acc = 0.0f;
 #if KT_D % 4 == 0
@@ -390,6 +465,41 @@ __device__ __forceinline__ float kt_sqdist(const float (&xr)[KT_D], const float*
 #endif
   return acc;
 }
+#else
+__device__ __forceinline__ float kt_sqdist(const float* __restrict__ xr, const float* __restrict__ yr) {
+#if KT_D % 4 == 0
+  const float4* x4 = reinterpret_cast<const float4*>(xr);
+  const float4* y4 = reinterpret_cast<const float4*>(yr);
+  float acc;
+  {
+    const float4 a = __ldg(x4), v = __ldg(y4);
+    const float d0 = a.x - v.x, d1 = a.y - v.y, d2 = a.z - v.z, d3 = a.w - v.w;
+    acc = d0 * d0;
+    acc = fmaf(d1, d1, acc);
+    acc = fmaf(d2, d2, acc);
+    acc = fmaf(d3, d3, acc);
+  }
+#pragma unroll 8
+  for (int k4 = 1; k4 < KT_D / 4; k4++) {
+    const float4 a = __ldg(x4 + k4), v = __ldg(y4 + k4);
+    const float d0 = a.x - v.x, d1 = a.y - v.y, d2 = a.z - v.z, d3 = a.w - v.w;
+    acc = fmaf(d0, d0, acc);
+    acc = fmaf(d1, d1, acc);
+    acc = fmaf(d2, d2, acc);
+    acc = fmaf(d3, d3, acc);
+  }
+#else
+  const float d0 = __ldg(xr) - __ldg(yr);
+  float acc = d0 * d0;
+#pragma unroll 8
+  for (int k = 1; k < KT_D; k++) {
+    const float d = __ldg(xr + k) - __ldg(yr + k);
+    acc = fmaf(d, d, acc);
+  }
+#endif
+  return acc;
+}
+#endif
 
 extern "C" __global__ void __launch_bounds__(256)
 kb200_knn_select(const long long nrow, const long long ncol, const float* __restrict__ x, const float* __restrict__ y,
@@ -400,48 +510,58 @@ kb200_knn_select(const long long nrow, const long long ncol, const float* __rest
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (row, split) pair
   const long long i = w / nsplit;
   if (i >= nrow) return;
-  cand += w * (long long)KT_CAP - i * (long long)KT_CAP;      // below, cand[i * KT_CAP + e] addresses this pair's list
+  const int* tok = cand + w * (long long)KT_CAP;      // this pair's token list
   const int n = cand_count[w];
   constexpr int OUTW = (KT_OUT == 2) ? 2 * KT_K : KT_K;
-  if (n > KT_CAP) {                                   // candidate list overflowed: the caller recomputes this row
+  if (n > KT_CAP) {                                   // token list overflowed: the caller recomputes this row
     if (lane == 0) { const int s = atomicAdd(overflow_count, 1); overflow_rows[s] = (int)i; }
     return;
   }
-  constexpr int PER = KT_CAP / 32;
-  float dv[PER];
-  int dj[PER];
+  // every lane keeps the K best (distance, index) pairs of the candidates it evaluated, ascending
+  float lv[KT_K];
+  int lj[KT_K];
+#pragma unroll
+  for (int l = 0; l < KT_K; l++) { lv[l] = KT_INF; lj[l] = 0x7fffffff; }
+#if KT_XREG
   float xr[KT_D];
 #pragma unroll
   for (int k = 0; k < KT_D; k++) xr[k] = __ldg(x + i * KT_D + k);
+#else
+  const float* xr = x + i * KT_D;
+#endif
+  for (int p = lane; p < n; p += 32) {
+    const u32 tk = (u32)tok[p];
+    const long long j8 = (long long)(tk >> 8) << 3;
+    for (u32 mask = tk & 0xffu; mask; mask &= mask - 1) {
+      const int j = (int)(j8 + __ffs(mask) - 1);
+      const float d = kt_sqdist(xr, y + (long long)j * KT_D);
+      if (d < lv[KT_K - 1] || (d == lv[KT_K - 1] && j < lj[KT_K - 1])) {
+        float cv = d;
+        int cj = j;
 #pragma unroll
-  for (int p = 0; p < PER; p++) {
-    const int e = p * 32 + lane;
-    dv[p] = KT_INF;
-    dj[p] = 0x7fffffff;
-    if (e < n) {
-      const int j = cand[i * (long long)KT_CAP + e];
-      dj[p] = j;
-      dv[p] = kt_sqdist(xr, y + (long long)j * KT_D);
+        for (int m = 0; m < KT_K; m++) {                // statically indexed insertion
+          if (cv < lv[m] || (cv == lv[m] && cj < lj[m])) {
+            const float tv = lv[m]; const int tj = lj[m];
+            lv[m] = cv; lj[m] = cj; cv = tv; cj = tj;
+          }
+        }
+      }
     }
   }
   for (int l = 0; l < KT_K; l++) {
-    float bv = dv[0];
-    int bj = dj[0], bp = 0;
-#pragma unroll
-    for (int p = 1; p < PER; p++)
-      if (dv[p] < bv || (dv[p] == bv && dj[p] < bj)) { bv = dv[p]; bj = dj[p]; bp = p; }
-    float wv = bv;
-    int wj = bj;
+    float wv = lv[0];
+    int wj = lj[0];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
       const int oj = __shfl_xor_sync(0xffffffffu, wj, o);
       if (ov < wv || (ov == wv && oj < wj)) { wv = ov; wj = oj; }
     }
-    if (wj == bj && bj != 0x7fffffff) {               // this lane owned the winner: retire it
+    if (wj == lj[0] && wj != 0x7fffffff) {            // this lane owned the winner (column indices are unique): pop it
 #pragma unroll
-      for (int p = 0; p < PER; p++)
-        if (p == bp) { dv[p] = KT_INF; dj[p] = 0x7fffffff; }
+      for (int m = 0; m + 1 < KT_K; m++) { lv[m] = lv[m + 1]; lj[m] = lj[m + 1]; }
+      lv[KT_K - 1] = KT_INF;
+      lj[KT_K - 1] = 0x7fffffff;
     }
     if (lane == 0) {
       const bool none = (wj == 0x7fffffff);           // fewer than K columns: (inf, 0) like the reference's init
