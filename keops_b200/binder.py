@@ -501,7 +501,7 @@ class LoadKeOpsB200:
                 return False
             rows_per_block = ks.cfg.T * ks.cfg.R
             slots = lk.sm_count * lk.blocks_per_sm
-            nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, 4)
+            nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, 4, sms=lk.sm_count)
             ws = torch.empty(nsplit * nrow * ks.dimpart, dtype=tdtype, device=dev) if nsplit > 1 else None
             params = [i64(nrow), i64(ncol), i64(max(col_chunk, 1)), ptr(out.data_ptr()), ptr(ws.data_ptr() if ws is not None else 0)]
             params += [ptr(a.data_ptr()) for a in args] + [i64(0)] * p.nargs + [ptr(ypk.data_ptr()), ptr(shf.data_ptr())]
@@ -544,10 +544,11 @@ class LoadKeOpsB200:
             # restart cost of a K-min list, in tile units: ~ K * log(N/K) insertions per row, each stalling its warp
             penalty = (kpen * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0
             segments = plan.launch_segments(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
-                                            split_penalty_tiles=penalty, ws_limit_bytes=ws_limit)
+                                            split_penalty_tiles=penalty, ws_limit_bytes=ws_limit,
+                                            sms=lk.sm_count if nbatch == 1 else 0)
         else:
             nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
-                                                  ws_limit_bytes=ws_limit,
+                                                  ws_limit_bytes=ws_limit, sms=lk.sm_count if nbatch == 1 else 0,
                                                   split_penalty_tiles=(kpen * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0)
             if p.tag1D2D == 1 and nsplit == 1 and ncol > 4 * ks.cfg.TJ:
                 # backend="GPU_2D": the caller asked for the split-column scheme explicitly

@@ -19,6 +19,8 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -179,6 +181,38 @@ struct kb200_module {
   CUdevice dev = 0;
 };
 
+// Kernel handle -> context that owns it.  Driver calls that take a CUfunction (attribute queries, occupancy, launches) need
+// that context current on the CALLING thread; PyTorch's autograd worker threads -- where every backward reduction is
+// issued -- may have no current driver context at all (seen on a 2-GPU NCCL job: cuOccupancyMaxActiveBlocksPerMultiprocessor
+// -> CUDA_ERROR_INVALID_CONTEXT).  CtxScope makes the owner current for the duration of one entry point when it is not.
+static std::mutex g_fn_mutex;
+static std::unordered_map<CUfunction, CUcontext> g_fn_ctx;
+
+struct CtxScope {
+  bool pushed = false;
+  explicit CtxScope(kb200_function fn) {
+    CUcontext want = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_fn_mutex);
+      auto it = g_fn_ctx.find(reinterpret_cast<CUfunction>(fn));
+      if (it != g_fn_ctx.end()) want = it->second;
+    }
+    if (!want) return;
+    CUcontext cur = nullptr;
+    if (g_drv.CtxGetCurrent(&cur) == CUDA_SUCCESS && cur == want) return;
+    pushed = g_drv.CtxPushCurrent(want) == CUDA_SUCCESS;
+  }
+  ~CtxScope() {
+    if (pushed) {
+      CUcontext dummy;
+      g_drv.CtxPopCurrent(&dummy);
+    }
+  }
+  CtxScope(const CtxScope&) = delete;
+  CtxScope& operator=(const CtxScope&) = delete;
+};
+
+
 extern "C" {
 
 int kb200_abi_version(void) { return KB200_ABI_VERSION; }
@@ -316,6 +350,10 @@ int kb200_module_get_function(kb200_module* m, const char* name, kb200_function*
   if (!m || !name || !fn) return fail(KB200_EINVAL, "kb200_module_get_function: null argument");
   CUfunction f;
   CU_TRY(g_drv.ModuleGetFunction(&f, m->mod, name), "cuModuleGetFunction");
+  {
+    std::lock_guard<std::mutex> lock(g_fn_mutex);
+    g_fn_ctx[f] = m->ctx;
+  }
   *fn = reinterpret_cast<kb200_function>(f);
   return 0;
 }
@@ -324,6 +362,7 @@ int kb200_function_info(kb200_function fn, int* num_regs, int* static_smem_bytes
   int st = driver();
   if (st) return st;
   CUfunction f = reinterpret_cast<CUfunction>(fn);
+  CtxScope scope(fn);
   if (num_regs) CU_TRY(g_drv.FuncGetAttribute(num_regs, CU_FUNC_ATTRIBUTE_NUM_REGS, f), "cuFuncGetAttribute");
   if (static_smem_bytes)
     CU_TRY(g_drv.FuncGetAttribute(static_smem_bytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, f), "cuFuncGetAttribute");
@@ -337,6 +376,7 @@ int kb200_max_active_blocks(kb200_function fn, int block_size, size_t dynamic_sm
   int st = driver();
   if (st) return st;
   if (!blocks_per_sm) return fail(KB200_EINVAL, "null argument");
+  CtxScope scope(fn);
   CU_TRY(g_drv.OccupancyMaxActiveBlocks(blocks_per_sm, reinterpret_cast<CUfunction>(fn), block_size,
                                         dynamic_smem_bytes),
          "cuOccupancyMaxActiveBlocksPerMultiprocessor");
@@ -379,6 +419,7 @@ int kb200_launch(kb200_function fn, void* stream, unsigned gx, unsigned gy, unsi
   int st = driver();
   if (st) return st;
   if (!fn) return fail(KB200_EINVAL, "kb200_launch: null function");
+  CtxScope scope(fn);
   CU_TRY(g_drv.LaunchKernel(reinterpret_cast<CUfunction>(fn), gx, gy, gz, bx, by, bz, dynamic_smem_bytes,
                             reinterpret_cast<CUstream>(stream), params, nullptr),
          "cuLaunchKernel");
@@ -405,6 +446,7 @@ int kb200_genred_launch_smem(kb200_function reduce_fn, kb200_function combine_fn
   if (nsplit > 1 && (!workspace || !combine_fn))
     return fail(KB200_EINVAL, "kb200_genred_launch: split reduction needs a workspace and a combine kernel");
   if (nrow <= 0) return 0;
+  CtxScope scope(reduce_fn);
   long long nrow_ = nrow, ncol_ = ncol, chunk_ = col_chunk;
   void* out_ = out;
   void* ws_ = workspace;
@@ -442,6 +484,7 @@ int kb200_function_set_max_dynamic_smem(kb200_function fn, int bytes) {
   int st = driver();
   if (st) return st;
   if (!fn || bytes < 0) return fail(KB200_EINVAL, "kb200_function_set_max_dynamic_smem: invalid argument");
+  CtxScope scope(fn);
   CU_TRY(g_drv.FuncSetAttribute(reinterpret_cast<CUfunction>(fn), CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, bytes),
          "cuFuncSetAttribute(MAX_DYNAMIC_SHARED_SIZE_BYTES)");
   return 0;
@@ -489,6 +532,7 @@ int kb200_genred_launch_ranges(kb200_function reduce_fn, void* stream, int64_t n
       grid_x > 2147483647LL || (nranges > 0 && (!ranges_x || !slices_x || !ranges_y || !block_ends)))
     return fail(KB200_EINVAL, "kb200_genred_launch_ranges: invalid argument");
   if (nrow <= 0 || nranges == 0 || grid_x == 0) return 0;
+  CtxScope scope(reduce_fn);
   long long nrow_ = nrow, ncol_ = ncol;
   void* out_ = out;
   const void* argv[64];

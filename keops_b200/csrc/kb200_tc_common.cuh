@@ -49,6 +49,20 @@ __device__ __forceinline__ void kt_mbar_wait(u32 bar, u32 parity) {
     if (spins > (1u << 28)) __trap();
   }
 }
+// non-blocking probe of a barrier phase
+__device__ __forceinline__ bool kt_mbar_test(u32 bar, u32 parity) {
+  u32 done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void kt_tma_2d(u32 dst, const KtTensorMap* map, int c0, int c1, u32 bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),

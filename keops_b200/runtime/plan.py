@@ -208,17 +208,37 @@ def load_kernel(ks: KernelSource, fast: bool, device: int) -> LoadedKernel:
         return lk
 
 
-def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int, dimpart: int, esz: int,
-                 max_split: int = 64, ws_limit_bytes: int = 2 << 30, split_penalty_tiles: float = 0.0) -> Tuple[int, int]:
-    """Choose the number of column splits so that the grid fills an integer number of waves.
+def _sm_rounds(nblocks: int, slots: int, sms: int) -> float:
+    """Duration of a grid of ``nblocks`` equal CTAs in units of one CTA running alone at full occupancy.
 
-    All CTAs do the same amount of work, so wall time ~ waves * work-per-CTA.  Without splitting,
-    ``gx`` CTAs over ``slots`` resident slots waste up to one whole wave (M=1e6 rows -> 1.65 waves
-    -> 2).  Splitting the streamed range into ``ns`` chunks multiplies the CTA count and lets the
-    last wave be (nearly) full; partials are merged by ``kb200_combine``.
-    Returns (nsplit, col_chunk)."""
+    Measured on B200 (experiments/shard_sweep.py, 125 000-row shard of the Gaussian conv, 4 CTAs / SM): co-resident CTAs
+    share their SM's pipes, so the time follows the work of the most loaded SM -- ``ceil(nblocks / sms)`` CTAs -- and not
+    whole waves of ``slots`` CTAs in lockstep: 1476 CTAs (9.97 per SM) 29.3 ms, 1722 (11.6 -> 12) 30.0 ms,
+    2091 (14.1 -> 15) 30.9 ms, 2952 (19.9 -> 20) 29.2 ms.  With ``sms = 0`` the older whole-wave model is used."""
+    if sms <= 0:
+        return float(-(-nblocks // slots))
+    bps = max(1, slots // sms)
+    per_sm = -(-nblocks // sms)
+    # a CTA that is alone on its SM runs ~3.7x faster than with three neighbours (same sweep: 5 CTAs per SM at 4 resident
+    # cost 1.27 rounds, not 2): the time is proportional to the CTAs of the most loaded SM, whatever the residency
+    return per_sm / float(bps) * (1.0 if per_sm % bps == 0 else 1.02)
+
+
+def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int, dimpart: int, esz: int,
+                 max_split: int = 64, ws_limit_bytes: int = 2 << 30, split_penalty_tiles: float = 0.0,
+                 sms: int = 0) -> Tuple[int, int]:
+    """Choose the number of column splits so that every SM gets the same number of CTAs.
+
+    All CTAs do the same amount of work, so wall time ~ rounds * work-per-CTA (``_sm_rounds``).  Without splitting,
+    ``gx`` CTAs over ``slots`` resident slots leave SMs idle at the end (M=1e6 rows -> 1.65 waves -> 2).  Splitting the
+    streamed range into ``ns`` chunks multiplies the CTA count and evens the load out; partials are merged by
+    ``kb200_combine``.  Returns (nsplit, col_chunk)."""
     gx = -(-nrow // rows_per_block)
     ntiles = max(1, -(-ncol // TJ))
+    forced = os.environ.get("KB200_FORCE_NSPLIT")          # tuning experiments (experiments/shard_sweep.py)
+    if forced:
+        tiles_per = -(-ntiles // max(1, min(int(forced), ntiles)))
+        return -(-ntiles // tiles_per), tiles_per * TJ
     best = None
     for ns in range(1, max_split + 1):
         if ns > ntiles:
@@ -229,16 +249,18 @@ def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int,
             continue
         if ns > 1 and ns * nrow * dimpart * esz > ws_limit_bytes:
             break
-        waves = -(-(gx * ns) // slots)
+        rounds = _sm_rounds(gx * ns, slots, sms)
         # cost in tile units: per-CTA prologue/epilogue overhead ~ 512 streamed rows, combine ~ 64 rows per split
-        cost = waves * (tiles_per + 512.0 / TJ + (split_penalty_tiles if ns > 1 else 0.0)) + (64.0 / TJ * ns if ns > 1 else 0.0)
-        if best is None or cost < best[0] * 0.98:
+        cost = rounds * (tiles_per + 512.0 / TJ + (split_penalty_tiles if ns > 1 else 0.0)) + (64.0 / TJ * ns if ns > 1 else 0.0)
+        if sms > 0:
+            cost += 0.03 * tiles_per       # SMs do not finish together: a few % of a CTA's duration (same sweep: ns = 6 vs 24)
+        if best is None or cost < best[0] * (0.995 if sms > 0 else 0.98):
             best = (cost, ns, tiles_per * TJ)
     return best[1], best[2]
 
 
 def launch_segments(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int, dimpart: int, esz: int,
-                    split_penalty_tiles: float = 0.0, ws_limit_bytes: int = 2 << 30):
+                    split_penalty_tiles: float = 0.0, ws_limit_bytes: int = 2 << 30, sms: int = 0):
     """Row segments ``[(row_begin, row_end, nsplit, col_chunk), ...]`` covering ``[0, nrow)``.
 
     Splitting the column range of *every* CTA fixes wave quantisation but makes each split restart its
@@ -250,19 +272,19 @@ def launch_segments(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: i
     gx = -(-nrow // rows_per_block)
     ntiles = max(1, -(-ncol // TJ))
     ns_all, chunk_all = launch_shape(nrow, ncol, rows_per_block, TJ, slots, dimpart, esz, ws_limit_bytes=ws_limit_bytes,
-                                     split_penalty_tiles=split_penalty_tiles)
+                                     split_penalty_tiles=split_penalty_tiles, sms=sms)
     tiles_all = -(-ntiles // ns_all)
     ovh, cmb = 512.0 / TJ, 64.0 / TJ
-    cost_all = -(-(gx * ns_all) // slots) * (tiles_all + ovh + (split_penalty_tiles if ns_all > 1 else 0.0)) + (cmb * ns_all if ns_all > 1 else 0.0)
+    cost_all = _sm_rounds(gx * ns_all, slots, sms) * (tiles_all + ovh + (split_penalty_tiles if ns_all > 1 else 0.0)) + (cmb * ns_all if ns_all > 1 else 0.0)
     full_waves, rem = divmod(gx, slots)
     if full_waves == 0 or rem == 0:
         return [(0, nrow, ns_all, chunk_all)]
     rows_a = full_waves * slots * rows_per_block
     nrow_b = nrow - rows_a
     ns_b, chunk_b = launch_shape(nrow_b, ncol, rows_per_block, TJ, slots, dimpart, esz, ws_limit_bytes=ws_limit_bytes,
-                                 split_penalty_tiles=split_penalty_tiles)
+                                 split_penalty_tiles=split_penalty_tiles, sms=sms)
     tiles_b = -(-ntiles // ns_b)
-    cost_tail = full_waves * (ntiles + ovh) + -(-(rem * ns_b) // slots) * (tiles_b + ovh + (split_penalty_tiles if ns_b > 1 else 0.0)) \
+    cost_tail = full_waves * (ntiles + ovh) + _sm_rounds(rem * ns_b, slots, sms) * (tiles_b + ovh + (split_penalty_tiles if ns_b > 1 else 0.0)) \
         + (cmb * ns_b if ns_b > 1 else 0.0) + ovh / 2
     if cost_tail < cost_all:
         return [(0, rows_a, 1, ntiles * TJ), (rows_a, nrow, ns_b, chunk_b)]

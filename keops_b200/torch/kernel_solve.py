@@ -19,12 +19,18 @@ from ..common import axis2cat, complete_aliases, get_optional_flags, get_sizes, 
 from .genred import GenredAutograd, GenredParameters, _resolve_backend, _set_device
 
 
-def conjugate_gradient(linop, b, eps=1e-6, max_iter=None, dot=None, numel=None):
+def conjugate_gradient(linop, b, eps=1e-6, max_iter=None, dot=None, numel=None, sync_every=1):
     """Same recurrence and stopping rule as ``ConjugateGradientSolver`` (``common/operations.py:90-114``).
 
     ``dot(u, v)`` (default: the local sum of products) and ``numel`` (default ``b.numel()``) are
     injectable so that the row-sharded solver (``keops_b200.distributed.ShardedKernelSolve``) can run the
-    very same recurrence with all-reduced scalars."""
+    very same recurrence with all-reduced scalars.
+
+    ``sync_every``: the reference compares ``|r|^2`` with the tolerance on the host after every iteration -- one
+    device-to-host synchronisation per map-reduce launch.  With ``sync_every = n > 1`` the test runs ON THE DEVICE: every
+    update is masked by an ``active`` flag (an iteration after convergence adds exactly zero), and the host reads the flag
+    only every ``n`` iterations.  Iterates and the iteration count are bit-identical to the host-tested loop; at most
+    ``n - 1`` launches after convergence are wasted, so this is for small systems whose launch is cheaper than a sync."""
     if dot is None:
         def dot(u, v):
             return (u * v).sum()
@@ -33,6 +39,8 @@ def conjugate_gradient(linop, b, eps=1e-6, max_iter=None, dot=None, numel=None):
     r = b.clone()
     nr2 = dot(r, r)
     conjugate_gradient.last_iterations = 0
+    if sync_every > 1:
+        return _conjugate_gradient_device_test(linop, a, r, nr2, delta, max_iter, dot, int(sync_every))
     if nr2 < delta:
         return a
     p = r.clone()
@@ -49,6 +57,32 @@ def conjugate_gradient(linop, b, eps=1e-6, max_iter=None, dot=None, numel=None):
         p = r + (nr2new / nr2) * p
         nr2 = nr2new
     conjugate_gradient.last_iterations = k
+    return a
+
+
+def _conjugate_gradient_device_test(linop, a, r, nr2, delta, max_iter, dot, sync_every):
+    """The loop of :func:`conjugate_gradient` with the convergence test on the device (see there)."""
+    active = ~(nr2 < delta)                      # 0-d bool tensor; the reference returns zeros when b is already small
+    zero = torch.zeros_like(nr2)
+    p = r.clone()
+    count = torch.zeros((), dtype=torch.int64, device=r.device)
+    k = 0
+    while True:
+        if k % sync_every == 0 and not bool(active):         # the only host synchronisation
+            break
+        if max_iter is not None and k >= max_iter:
+            break
+        Mp = linop(p)
+        alp = torch.where(active, nr2 / dot(p, Mp), zero)
+        a.add_(alp * p)
+        r.sub_(alp * Mp)
+        nr2new = dot(r, r)
+        count += active
+        k += 1
+        active = active & ~(nr2new < delta)      # the reference leaves the loop before it updates p
+        p = torch.where(active, r + (nr2new / nr2) * p, p)
+        nr2 = torch.where(active, nr2new, nr2)
+    conjugate_gradient.last_iterations = int(count)
     return a
 
 
@@ -74,7 +108,9 @@ class KernelSolveAutograd(torch.autograd.Function):
                 res += params.alpha * var
             return res
 
-        result = conjugate_gradient(linop, varinv, params.eps)
+        # small systems: the launch is cheaper than a host synchronisation -- test convergence on the device
+        sync_every = 1 if float(params.nx) * float(params.ny) >= 2.5e9 else 8
+        result = conjugate_gradient(linop, varinv, params.eps, sync_every=sync_every)
         ctx.save_for_backward(*args, result)
         return result
 

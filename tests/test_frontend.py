@@ -211,6 +211,13 @@ def test_conjugate_gradient_matches_reference(name):
     assert torch.equal(a, a_ref)
     capped = conjugate_gradient(linop, b, eps=0.0, max_iter=3) if name != "zero_rhs" else None
     assert capped is None or conjugate_gradient.last_iterations == 3
+    # convergence test on the device, host read-back every 4 iterations: same iterates, same count; the wasted operator
+    # applications after convergence add exactly zero
+    calls[0] = 0
+    a_dev = conjugate_gradient(linop, b, eps=float(rec[name + ".eps"]), sync_every=4)
+    assert conjugate_gradient.last_iterations == int(rec[name + ".calls"])
+    assert int(rec[name + ".calls"]) <= calls[0] <= int(rec[name + ".calls"]) + 3
+    assert torch.equal(a_dev, a_ref)
 
 
 def _constant_cases():
