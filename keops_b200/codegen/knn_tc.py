@@ -24,7 +24,7 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_knn_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")      # PTX wrappers, prepended (NVRTC has no include path)
-VERSION = "knn-tc-9"
+VERSION = "knn-tc-14"
 BM, BN, STAGES, HS, KP, THREADS = 256, 128, 4, 8, 16, 576
 MAX_SMEM = 227 * 1024
 RESIDENT_MAX_COLS = 160      # D + 3 <= 160: the CTA's row operand stays in shared memory (>= 3 ring stages); beyond, k-blocks are streamed
@@ -90,7 +90,7 @@ class KnnTensorCore:
         self.c = 0.008 if D <= 160 else 0.00783 + D * 2.0 ** -21
         self.BN = BN
         blk = lambda rows: self.KBM * rows * 128 + rows * self.REM * 2      # one operand block, all of K
-        state = BM * (KP + 3) * 4
+        state = BM * (KP + 3) * 4                # per-row lists, threshold, token count, lock
         fixed = 1024 + HS * BN * 4 + state + 640
         if self.stream:
             a_bytes, b_bytes = 0, (BM + BN) * 128
@@ -105,6 +105,7 @@ class KnnTensorCore:
         defs = ("#define KT_D %d\n#define KT_KBM %d\n#define KT_REM %d\n#define KT_K %d\n#define KT_CAP %d\n"
                 "#define KT_OUT %d\n#define KT_FAST %d\n" % (D, self.KBM, self.REM, K, cap, out_code, 1 if fast else 0))
         defs += "#define KT_STREAM %d\n#define KT_STAGES %d\n#define KT_C %.9gf\n" % (int(self.stream), self.STAGES, self.c)
+        defs += "#define KT_DBG %d\n" % int(os.environ.get("KT_DBG", 0))
         defs += "#define KT_SPIN %d\n" % int(os.environ.get("KT_SPIN", 0))
         src = defs + body
         self.cubin = cubin = plan.compile_cached(src, plan.nvrtc_options(fast), "kb200_knntc", VERSION)

@@ -29,11 +29,21 @@
 //   4-stage smem ring, double-buffered TMEM accumulators (2 row blocks x 2 buffers x 128 columns = 512).
 //   Why this shape (ncu source view of the previous one-thread-per-row epilogue, profiles/r01_ncu_knn_filter_d64.txt:
 //   tensor pipe 47 % busy): the 8 epilogue warps were the critical path and latency-bound -- per tile each spent
-//   ~160 clk waiting for tcgen05.ld, ~255 clk in the FMNMX3 reduction, ~400 clk in the divergent survivor path (52
-//   instructions at ~8 clk each: select tree, penalty load, sorted insertion) and 440 clk waiting for the next
-//   accumulator, because the MMA warp in turn waited for the slowest of the four warps of a row block.  Two threads
-//   per row halve the per-warp work, give every scheduler four warps to overlap TMEM reads with the reductions, and the
-//   shared row state keeps ONE threshold per row (two private lists per row had cost 324 instead of ~200 candidates).
+//   ~160 clk waiting for tcgen05.ld, ~255 clk in the FMNMX3 reduction, ~400 clk in the divergent survivor path and 440 clk
+//   waiting for the next accumulator, because the MMA warp in turn waited for the slowest of the four warps of a row
+//   block.  Two threads per row halve the per-warp work and give every scheduler four warps; the shared row state keeps
+//   ONE threshold per row (two private lists per row had cost 324 instead of ~200 candidates).
+//   Where the time goes now (B200, D = 64, K = 10, M = N = 1e6; KT_DBG builds, profiles/r02_knn_filter_experiments.md):
+//   with the survivor path disabled the kernel takes 101 ms, with the max-reduction disabled too 96 ms -- tensor pipe 95 %
+//   busy at an SM clock that the power cap has pulled down to 1.45 GHz, i.e. 1.67 PFLOP/s, the throughput cuBLAS reaches
+//   on this GPU (MEASURED_PEAKS.json).  That is the floor; the full kernel takes 134-138 ms (0.70-0.72 of it), the
+//   difference being the survivor handling: ~150 groups per row, each costing its warp ~500 clk, with only two accumulator
+//   buffers per row block between the warps and the MMA issuer.  Measured and rejected on the way (all bit-identical):
+//   parking survivor groups in registers and handling them in batches (178 ms: fewer but ~3x longer stalls, which the two
+//   buffers absorb worse), mailing them to two helper warps that own the lists (152-156 ms: their polling and the extra
+//   warps cost clock under the power cap), 32-column TMEM reads overlapped with the reductions (156 ms: the accumulator
+//   is released later), private token sub-lists instead of a shared counter (no change), L2-sized column chunks (272 ms:
+//   every chunk replays the transient of an empty list).
 // kb200_knn_prep   : fp32 -> bf16 operand rows (data, penalty columns, zero padding) + per-row penalty terms.
 // kb200_knn_select : one warp per row, exact distances of the candidates (tokens decoded) + ordered top-K (ties ->
 //   smallest j).
@@ -57,6 +67,9 @@
 #define KT_STREAM 0
 #define KT_STAGES 4
 #define KT_C 0.008f
+#endif
+#ifndef KT_DBG
+#define KT_DBG 0                              /* timing experiments: 1 = no survivors at all, 2 = TMEM loads + release only */
 #endif
 
 #define KT_BM 256                             /* rows per CTA: two 128-row accumulators                         */
@@ -181,7 +194,11 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int r = threadIdx.x; r < KT_BM; r += KT_THREADS) {
+#if KT_DBG == 1                                                     /* timing experiment: no survivors at all */
+    tau_s[r] = KT_INF;
+#else
     tau_s[r] = (row_base + r < nrow) ? -KT_INF : KT_INF;         // rows past the end never produce a candidate
+#endif
     cnt_s[r] = 0;
     lock_s[r] = 0;
 #pragma unroll
@@ -356,6 +373,10 @@ kb200_knn_filter(const __grid_constant__ KtTensorMap map_x, const __grid_constan
       kt_fence_before();
       __syncwarp();
       if (lane == 0) kt_mbar_arrive(bTEmpty + 8 * (buf * 2 + rb));
+#if KT_DBG == 2                                                     /* timing experiment: TMEM loads + release only */
+      if (u[0] == 12345.678f && u[63] == 1.0f) tau_s[rl] = u[5];
+      continue;
+#endif
       float mg[8];                                    // maxima of the eight 8-column groups
 #pragma unroll
       for (int g = 0; g < 8; g++) {
