@@ -156,7 +156,7 @@ def test_tensor_core_conv_matches_cuda_core(D, DB, nx, ny, tagI, coef, cuda_devi
     assert ll.get("engine") == "tcgen05-conv", ll         # the tensor-core kernels really ran
     assert ll["error_bound"] <= 5e-6
     o_cc, ll2 = _run(f, 4, (x, y, b, g), nx, ny, dev, False)
-    assert ll2.get("engine") is None
+    assert ll2.get("engine") in (None, "cuda-core/chunked"), ll2      # the comparator ran on the CUDA cores
     sc = _scale(f, 4, (x, y, b, g), nx, ny, dev)
     tag = " D=%d DB=%d %dx%d tagI=%d" % (D, DB, nx, ny, tagI)
     util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 conv vs CUDA cores" + tag, scale=sc)
@@ -294,7 +294,7 @@ def test_tensor_core_lse_matches_cuda_core(D, DW, nx, ny, tagI, cuda_device):
     o_tc, ll = _run(f, len(args), args, nx, ny, dev, True)
     assert ll.get("engine") == "tcgen05-lse", ll
     o_cc, ll2 = _run(f, len(args), args, nx, ny, dev, False)
-    assert ll2.get("engine") is None
+    assert ll2.get("engine") in (None, "cuda-core/chunked"), ll2      # the comparator ran on the CUDA cores
     # raw (m, s) output: m = max_j F_ij, s = sum_j exp(F_ij - m) b_j
     tag = " D=%d DW=%d %dx%d tagI=%d" % (D, DW, nx, ny, tagI)
     util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32", "tcgen05 LSE (m, s) vs CUDA cores" + tag,
