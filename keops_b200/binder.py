@@ -129,6 +129,8 @@ class LoadKeOpsB200:
         # high-dimensional Sum / Scalprod sub-formulas: the chunked kernel (the reference's chunk mode, switched by the same
         # ``enable_chunks`` flag: get_keops_dll.py:101-111)
         self._prescale_ks = None         # None: not tried yet; False: the formula does not have the Gaussian shape
+        # gradient of a Gaussian-kernel sum w.r.t. a position variable in dimension 8..64: assembled from tensor-core sums
+        self._conv_grad = conv_tc.match_grad(red) if (dtype == "float32" and not self.ks.is_zero) else None
         self._chunk_plan = emit_chunked.plan_chunks(red) if (p.enable_chunks and not self.ks.is_zero) else None
         self.ks_chunked: Optional[KernelSource] = None
 
@@ -321,6 +323,12 @@ class LoadKeOpsB200:
         tc = knn_tc.eligible(self.red, p.dtype, nrow, ncol, nbatch)
         if tc is not None:
             return self._genred_knn_tc(dev, tc, nrow, ncol, out, args, strides, tdtype)
+        if (self._conv_grad is not None and nbatch == 1 and p.use_fast_math and p.sum_scheme in ("block_sum", "auto")
+                and p.dtype_acc in ("float32", "auto") and os.environ.get("KB200_CONV_TC", "1") != "0"
+                and os.environ.get("KB200_CONV_TC_GRAD", "1") != "0"
+                and nrow >= (8192 if ncol < 65536 else 1024) and ncol >= 1024 and ncol < (1 << 31) - 128):
+            if self._genred_conv_tc_grad(dev, self._conv_grad, nrow, ncol, out, args):
+                return out
         ct = conv_tc.eligible(self.red, p.dtype, nrow, ncol, nbatch, p.use_fast_math, p.sum_scheme, p.dtype_acc)
         if ct is not None:
             if self._genred_conv_tc(dev, ct, nrow, ncol, out, args):
@@ -428,6 +436,57 @@ class LoadKeOpsB200:
         self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0, blocks_per_sm=1,
                                 launches=3 + (eng.last["nchunks"] > 1), engine="tcgen05-conv",
                                 error_bound=eng.last_bound, nchunks=eng.last["nchunks"])
+        return True
+
+    def _genred_conv_tc_grad(self, dev, gp, nrow, ncol, out, args):
+        """Gradient of ``sum_j exp(c |x_i - y_j|^2) b_j`` w.r.t. ``x`` or ``y`` from forward-type sums on the tensor cores
+        (``conv_tc.match_grad`` has the algebra and the error estimate).  False: the accuracy guard refused -- the caller
+        runs the CUDA-core gradient kernel."""
+        kind, row_ind, col_ind, D, b_ind, eta_ind, fwd_ind, terms = gp
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        chunk = conv_tc.grad_chunk(D)
+        if chunk is None:
+            return False
+        MAXDB, stages = chunk
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            coef = conv_tc.coefficient(terms, args, dev)
+            xr, yc, b, eta = args[row_ind], args[col_ind], args[b_ind], args[eta_ind]
+            if kind == "x":
+                # rows = the forward's rows; streamed side = (y, b):  2 c e_i [ (x_i - m) S0_i - sum_j k_ij b_j (y_j - m) ]
+                rows, cols, lead_w, scale_rows = xr, yc, b, eta
+                s0 = args[fwd_ind] if fwd_ind is not None else None
+            else:
+                # rows = the forward's streamed points y_j; streamed side = (x, e): 2 c b_j [ (y_j - m') T0_j - sum_i k_ij e_i (x_i - m') ]
+                rows, cols, lead_w, scale_rows = yc, xr, eta, b
+                s0 = None
+            m = cols.mean(dim=0, dtype=torch.float32)
+            w = lead_w * (cols - m)                                    # (ncol, D) weights of the D-wide sum
+            if s0 is None:                                             # the scalar sum rides in the first chunk
+                w = torch.cat([lead_w, w], dim=1)
+            nw = w.shape[1]
+            sums = torch.empty((nrow, nw), dtype=torch.float32, device=dev)
+            launches, bound, nchunks = 0, 0.0, 0
+            for c0 in range(0, nw, MAXDB):
+                c1 = min(nw, c0 + MAXDB)
+                eng = conv_tc.get(D, c1 - c0, index, stages=stages)
+                part = sums if (c0 == 0 and c1 == nw) else torch.empty((nrow, c1 - c0), dtype=torch.float32, device=dev)
+                if not eng.run(rows, cols, w[:, c0:c1].contiguous(), coef, part, stream):
+                    return False
+                if part is not sums:
+                    sums[:, c0:c1] = part
+                launches += 3 + (eng.last["nchunks"] > 1)
+                nchunks = max(nchunks, eng.last["nchunks"])
+                bound = max(bound, eng.last_bound or 0.0)
+            if s0 is None:
+                s0, s1 = sums[:, :1], sums[:, 1:]
+            else:
+                s1 = sums
+            res = (2.0 * coef) * scale_rows * ((rows - m) * s0 - s1)
+            out.view(nrow, D).copy_(res)
+        self.last_launch = dict(nsplit=1, col_chunk=ncol, grid_x=-(-nrow // 256), nbatch=1, regs=0, blocks_per_sm=1,
+                                launches=launches, engine="tcgen05-conv-grad", error_bound=bound, nchunks=nchunks,
+                                weight_columns=nw)
         return True
 
     def _genred_lse_tc(self, dev, cl, nrow, ncol, out, args):

@@ -169,6 +169,71 @@ def match_lse(red: Reduction):
     return None
 
 
+# dimensions in which the gradient is assembled from tensor-core sums (see match_grad).  Measured on B200 (experiments/
+# conv_grad_check.py, M = N = 1e6): D = 16: d/dx 1321 ms in two 8-column launches vs 1579 ms for the CUDA-core gradient kernel
+# (x 1.20), d/dy (17 columns, three launches) 1582 vs 1574 ms; D = 8: d/dx 656 vs 810 ms (x 1.24), d/dy 903 vs 806 ms;
+# D = 32, 5e5 points (high-dimensional kernel): 718 vs 863 ms and 822 vs 861 ms.  A launch with 8 weight columns costs 2.5 x a
+# launch with one (660 vs 260 ms at D = 16): per pair the epilogue issues 8 scalar FFMA and 2 broadcast LDS.128 wavefronts
+# that every one of the 16 epilogue warps repeats -- LSU- and issue-bound, not FMA-bound (9 of 128 lanes per clock).  So
+# only d/dx (whose scalar sum is the saved forward) is routed here; d/dy stays on the CUDA cores.
+GRAD_DMIN, GRAD_DMAX = 8, 21
+
+
+def grad_chunk(D: int):
+    """``(weight columns per launch, ring stages)`` of the gradient's forward-type sums: the widest chunk that fits shared
+    memory, giving up one ring stage before narrowing the chunk (fewer launches win: each one redoes the GEMM)."""
+    for db in range(MAX_DB, 0, -1):
+        for st in (STAGES, STAGES - 1):
+            if smem_bytes(D, db, st) <= 227 * 1024:
+                return db, st
+    return None
+
+
+def match_grad(red: Reduction):
+    """Gradient of a Gaussian-kernel sum with respect to a position variable, recognised STRUCTURALLY from the
+    provenance that ``Grad_WithSavedForward`` records (``Reduction.origin``) -- the differentiated formula itself is a
+    D-vector expression that the pattern of :func:`match` does not cover.
+
+    For ``out_i = sum_j exp(c |x_i - y_j|^2) b_j`` (dim b = 1) and upstream gradient ``e_i``
+    (``pykeops/pykeops/torch/generic/generic_red.py:190-214`` requests exactly this reduction in every backward pass,
+    ``pykeops/pykeops/torch/operations.py:107-147`` for ``KernelSolve``):
+
+    * ``d/dx_i = 2 c e_i [ (x_i - m) S0_i - S1_i ]``, ``S0_i = sum_j k_ij b_j`` (the saved forward) and
+      ``S1_i = sum_j k_ij b_j (y_j - m)`` -- a forward-type sum with a D-wide weight;
+    * ``d/dy_j = 2 c b_j [ (y_j - m') T0_j - T1_j ]``, ``T0_j = sum_i k_ij e_i``, ``T1_j = sum_i k_ij e_i (x_i - m')``;
+
+    ``m`` / ``m'`` = mean of the streamed cloud (the shift the tensor-core kernel applies anyway).  The sums run on
+    ``kb200_conv_tc*`` in chunks of ``MAX_DB`` weight columns instead of 2 D + 2 FP32 instructions per pair on the CUDA cores.
+    Cancellation: both terms of a bracket are at most ``R sum_j |k_ij b_j|`` (R = radius of the shifted clouds) while the
+    gradient's own scale is ``delta sum_j |k_ij b_j|`` with ``delta ~ |c|^-1/2`` the distance of the pairs that matter; the
+    accuracy guard of the sums bounds ``|c| R^2 <= 2^22 TOL ~ 21``, i.e. at most ~4.6 x the sums' own relative error
+    (measured 1e-7 .. 1e-6) -- inside the fp32 parity bar; `tests/test_conv_tc.py` pins it against the CUDA-core kernel.
+
+    Returns ``(kind, row_var, col_var, D, b_var, eta_var, fwd_var or None, coef_terms)`` with kind "x" (the output-side
+    position of the forward) or "y" (the streamed one), or ``None``."""
+    o = getattr(red, "origin", None)
+    if not o or o[0] != "grad" or red.kind != "Sum":
+        return None
+    _, inner, v, gradin, f0 = o
+    m = match(inner)
+    if m is None:
+        return None
+    row, col, D, bi, DB, terms = m
+    if DB != 1 or inner.dim != 1 or not (GRAD_DMIN <= D <= GRAD_DMAX):
+        return None
+    if v.op != "Var" or gradin.op != "Var" or gradin.params[1] != 1 or gradin.params[2] != inner.tagI:
+        return None
+    fwd = None
+    if f0 is not None and f0.op == "Var" and f0.params[1] == 1 and f0.params[2] == inner.tagI:
+        fwd = f0.params[0]
+    kind = "x" if v.params[0] == row else ("y" if v.params[0] == col else None)
+    if kind is None or v.params[1] != D:
+        return None
+    if kind == "y" and os.environ.get("KB200_CONV_TC_GRAD_Y", "0") != "1":
+        return None                      # measured no faster than the CUDA-core kernel (see GRAD_DMIN above)
+    return kind, row, col, D, bi, gradin.params[0], fwd, terms
+
+
 def _eval_scalar(node: Node, args):
     """one-element fp32 tensor (or python float) value of a scalar parameter expression -- device ops only"""
     if node.op == "Var":
@@ -307,7 +372,7 @@ def eligible_lse(red: Reduction, dtype: str, nrow: int, ncol: int, nbatch: int, 
 class ConvTensorCore:
     """Compiled kernels for one (D, dim b, Sum | LSE) combination on one device."""
 
-    def __init__(self, D: int, DB: int, device: int, lse: bool = False):
+    def __init__(self, D: int, DB: int, device: int, lse: bool = False, stages: Optional[int] = None):
         self.D, self.DB, self.lse = D, DB, bool(lse)
         self.OUTW = DB + (1 if lse else 0)
         self.KBM, self.REM, self.PEN = layout(D)
@@ -325,7 +390,7 @@ class ConvTensorCore:
             body = f.read()
         with open(_SRC_PATH) as f:
             body += f.read()
-        self.STAGES = int(os.environ.get("CT_STAGES", STAGES))
+        self.STAGES = int(os.environ.get("CT_STAGES", stages or STAGES))
         defs = ("#define CT_D %d\n#define CT_DB %d\n#define CT_KBM %d\n#define CT_REM %d\n#define CT_STAGES %d\n"
                 "#define CT_HS %d\n#define CT_DBG %d\n#define CT_PEN %d\n#define CT_POLY %d\n#define CT_ASTREAM %d\n"
                 "#define CT_LSE %d\n#define CT_MC %d\n#define CT_ATMEM %d\n#define CT_ATMEM2 %d\n"
@@ -445,12 +510,12 @@ class ConvTensorCore:
 _cache: Dict[tuple, ConvTensorCore] = {}
 
 
-def get(D: int, DB: int, device: int, lse: bool = False) -> ConvTensorCore:
+def get(D: int, DB: int, device: int, lse: bool = False, stages: Optional[int] = None) -> ConvTensorCore:
     key = (D, DB, device, bool(lse), os.environ.get("KB200_CONV_TC_MC", str(MULTICAST)), os.environ.get("CT_POLY", str(POLY)),
-           os.environ.get("KB200_CONV_TC_ATMEM", str(ATMEM)))
+           os.environ.get("KB200_CONV_TC_ATMEM", str(ATMEM)), stages)
     with _lock:
         k = _cache.get(key)
         if k is None:
-            k = ConvTensorCore(D, DB, device, lse)
+            k = ConvTensorCore(D, DB, device, lse, stages)
             _cache[key] = k
         return k

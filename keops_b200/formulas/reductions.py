@@ -22,7 +22,7 @@ Zero                      --                                        zeros (no ke
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field, replace as _dc_replace
 from typing import Optional
 
 from . import ir
@@ -37,6 +37,9 @@ class Reduction:
     tagI: int
     K: int = 1                # for the K-min family
     weight: Optional[Node] = None  # G for LSE
+    # provenance, not part of the reduction's identity: ("grad", reduction, variable, gradin, saved forward) when this
+    # reduction was produced by Grad_WithSavedForward (lets the binder recognise gradients of known kernels structurally)
+    origin: Optional[tuple] = field(default=None, compare=False, repr=False)
 
     # ---- dimensions ---------------------------------------------------------------------
     @property
@@ -164,7 +167,7 @@ def Grad_WithSavedForward(red: Reduction, v: Node, gradin: Node, f0: Node) -> Re
     new_tag = v.params[2] % 2
     k = red.kind
     if k == "Sum":
-        return Sum_Reduction(grad(red.formula, v, gradin), new_tag)
+        return _dc_replace(Sum_Reduction(grad(red.formula, v, gradin), new_tag), origin=("grad", red, v, gradin, f0))
     if k == "LSE":
         F, G = red.formula, red.weight
         M = ir.Extract(f0, 0, 1)

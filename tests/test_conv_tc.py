@@ -45,6 +45,36 @@ def test_match_rejects_other_formulas(formula):
     assert conv_tc.match(parse_reduction(formula)) is None
 
 
+def test_match_grad_recognises_position_gradients_structurally():
+    """``Grad_WithSavedForward`` of the Gaussian sum w.r.t. x / y (what the backward of ``Genred`` / ``KernelSolve`` requests,
+    pykeops/pykeops/torch/generic/generic_red.py:190-214) is recognised from the provenance the parser records; gradients
+    w.r.t. b already have the forward's shape (transposed) and match the plain pattern; a parameter gradient does not."""
+    g = "Grad_WithSavedForward(" + KS + ",%s,Var(4,1,0),Var(5,1,0))"
+    mx = conv_tc.match_grad(parse_reduction(g % "Var(0,16,0)"))
+    assert mx[:7] == ("x", 0, 1, 16, 2, 4, 5)
+    assert conv_tc.match_grad(parse_reduction(g % "Var(1,16,1)")) is None      # d/dy: measured no faster, not routed
+    os.environ["KB200_CONV_TC_GRAD_Y"] = "1"
+    try:
+        my = conv_tc.match_grad(parse_reduction(g % "Var(1,16,1)"))
+    finally:
+        del os.environ["KB200_CONV_TC_GRAD_Y"]
+    assert my[:7] == ("y", 0, 1, 16, 2, 4, 5)
+    rb = parse_reduction(g % "Var(2,1,1)")
+    assert conv_tc.match_grad(rb) is None and conv_tc.match(rb) is not None and rb.tagI == 1
+    assert conv_tc.match_grad(parse_reduction(g % "Var(3,1,2)")) is None
+    assert conv_tc.match_grad(parse_reduction(KS)) is None
+    # dim b = 2 (the upstream gradient is a vector), D = 3: outside the path
+    g2 = "Grad_WithSavedForward(Sum_Reduction(Exp(-SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,2,1),0),Var(0,16,0),Var(3,2,0),Var(4,2,0))"
+    g3 = "Grad_WithSavedForward(Sum_Reduction(Exp(-SqDist(Var(0,3,0),Var(1,3,1)))*Var(2,1,1),0),Var(0,3,0),Var(3,1,0),Var(4,1,0))"
+    assert conv_tc.match_grad(parse_reduction(g2)) is None and conv_tc.match_grad(parse_reduction(g3)) is None
+    # provenance is not part of a reduction's identity
+    assert parse_reduction(g % "Var(2,1,1)") == parse_reduction(str_of_grad_b())
+
+
+def str_of_grad_b():
+    return "Sum_Reduction(Var(4,1,0)*Exp(-Var(3,1,2)*SqDist(Var(0,16,0),Var(1,16,1))),1)"
+
+
 def test_layout_and_eligibility():
     assert conv_tc.layout(16) == (1, 64, 1)        # 96 product + 3 penalty columns, padded to 128
     assert conv_tc.layout(21) == (1, 64, 0)        # 126 product columns; |y|^2 goes to the epilogue
@@ -333,3 +363,48 @@ def test_cluster_multicast_variant_is_identical(cuda_device):
     o0, ll0 = _run(f, 4, (x, y, b, g), nx, ny, dev, True, KB200_CONV_TC_MC=0)
     assert ll1.get("engine") == ll0.get("engine") == "tcgen05-conv"
     assert torch.equal(o1, o0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,var,nx,ny", [
+    (16, "x", 9000, 7001),                              # the KernelSolve backward, ragged tiles, two weight chunks
+    (8, "x", 8192, 4096), (21, "x", 8300, 5000),        # one weight chunk; widest operand rows
+    (21, "y", 5000, 8300), (12, "y", 4000, 9000),       # opt-in d/dy (KB200_CONV_TC_GRAD_Y): reduction over i
+])
+def test_tensor_core_position_gradient_matches_cuda_core(D, var, nx, ny, cuda_device):
+    """Gradient of the Gaussian sum w.r.t. x / y assembled from tensor-core sums against the CUDA-core gradient kernel
+    (generated from the differentiated formula, pinned against the reference by the golden gradient fixtures): inside the
+    fp32 parity bar element-wise, relative to sum_j |F_ij| of every component."""
+    import torch
+    torch.manual_seed(D + len(var))
+    dev = cuda_device
+    x, y = torch.rand(nx, D, device=dev), torch.rand(ny, D, device=dev)
+    b, eta = torch.randn(ny, 1, device=dev), torch.randn(nx, 1, device=dev)
+    g = torch.tensor([0.7 if D <= 21 else 8.0 / D], device=dev)
+    F = "Sum_Reduction(Exp(-Var(3,1,2)*SqDist(Var(0,%d,0),Var(1,%d,1)))*Var(2,1,1),0)" % (D, D)
+    fwd, _ = _run(F, 4, (x, y, b, g), nx, ny, dev, True)
+    v = "Var(0,%d,0)" % D if var == "x" else "Var(1,%d,1)" % D
+    f = "Grad_WithSavedForward(%s,%s,Var(4,1,0),Var(5,1,0))" % (F, v)
+    args = (x, y, b, g, eta, fwd)
+    if var == "y":
+        os.environ["KB200_CONV_TC_GRAD_Y"] = "1"
+    try:
+        o_tc, ll = _run(f, 6, args, nx, ny, dev, True)
+    finally:
+        os.environ.pop("KB200_CONV_TC_GRAD_Y", None)
+    assert ll.get("engine") == "tcgen05-conv-grad", ll
+    assert ll["weight_columns"] == (D if var == "x" else D + 1)      # the saved forward spares the scalar sum for d/dx
+    old = os.environ.get("KB200_CONV_TC_GRAD")
+    os.environ["KB200_CONV_TC_GRAD"] = "0"
+    try:
+        o_cc, ll2 = _run(f, 6, args, nx, ny, dev, True)
+    finally:
+        if old is None:
+            os.environ.pop("KB200_CONV_TC_GRAD", None)
+        else:
+            os.environ["KB200_CONV_TC_GRAD"] = old
+    assert ll2.get("engine") in (None, "cuda-core/chunked"), ll2
+    assert o_tc.shape == o_cc.shape == ((nx if var == "x" else ny), D)
+    scale = util.gpu_abs_scale(f, 6, "float32", dev, nx, ny, *args).cpu().numpy()
+    util.assert_close(o_tc.cpu().numpy(), o_cc.cpu().numpy(), "float32",
+                      "tcgen05 gradient d/d%s vs CUDA cores D=%d %dx%d" % (var, D, nx, ny), scale=scale)
