@@ -26,8 +26,8 @@ import torch
 
 from .formulas.parser import parse_reduction, parse_alias
 from .formulas.reductions import Reduction
-from .codegen.emit import generate, KernelSource
-from .codegen import conv_tc, knn_tc, emit_chunked
+from .codegen.emit import KernelConfig, generate, KernelSource
+from .codegen import conv_tc, knn_tc, emit_chunked, emit_kmin_filter
 from .runtime import plan, capi
 
 _binder_cache: Dict[tuple, "LoadKeOpsB200"] = {}
@@ -129,6 +129,9 @@ class LoadKeOpsB200:
         # high-dimensional Sum / Scalprod sub-formulas: the chunked kernel (the reference's chunk mode, switched by the same
         # ``enable_chunks`` flag: get_keops_dll.py:101-111)
         self._prescale_ks = None         # None: not tried yet; False: the formula does not have the Gaussian shape
+        # K nearest neighbours in dimension <= 3: filtered kernel (codegen/emit_kmin_filter.py), generated on first use
+        self._kf_match = emit_kmin_filter.match(red) if (dtype == "float32" and p.use_fast_math and not self.ks.is_zero) else None
+        self.ks_kfilter: Optional[KernelSource] = None
         # gradient of a Gaussian-kernel sum w.r.t. a position variable in dimension 8..64: assembled from tensor-core sums
         self._conv_grad = conv_tc.match_grad(red) if (dtype == "float32" and not self.ks.is_zero) else None
         self._chunk_plan = emit_chunked.plan_chunks(red) if (p.enable_chunks and not self.ks.is_zero) else None
@@ -584,8 +587,17 @@ class LoadKeOpsB200:
                 and os.environ.get("KB200_PRESCALE", "1") != "0"):
             if self._launch_prescaled(dev, nrow, ncol, out, args, tdtype):
                 return out
-        lk = self._kernel(dev.index if dev.index is not None else torch.cuda.current_device())
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        lk = self._kernel(index)
         ks = self.ks
+        engine = None
+        if (self._kf_match is not None and nbatch == 1 and p.tag1D2D == 0 and float(nrow) * float(ncol) >= self.KFILTER_MIN_PAIRS
+                and os.environ.get("KB200_KMIN_FILTER", "1") != "0"):
+            kf = self._kmin_filter_setup(dev, index, ncol, args, tdtype)
+            if kf is not None:
+                lk, ks, extra = kf
+                args, strides = list(args) + extra, list(strides) + [0, 0]
+                engine = "cuda-core/kmin-filter"
         rows_per_block = ks.cfg.T * ks.cfg.R
         esz = 4 if p.dtype == "float32" else 8
         slots = max(1, (lk.sm_count * lk.blocks_per_sm) // min(nbatch, lk.sm_count * lk.blocks_per_sm))
@@ -628,7 +640,7 @@ class LoadKeOpsB200:
             stream = torch.cuda.current_stream(dev).cuda_stream
             out_flat = out.view(nbatch, nrow * p.dim)
             if n_seed:
-                launches += self._launch_kmin_seeded(lk, stream, dev, tdtype, esz, nrow, ncol, n_seed, segments, out_flat,
+                launches += self._launch_kmin_seeded(lk, ks, stream, dev, tdtype, esz, nrow, ncol, n_seed, segments, out_flat,
                                                      args, strides, row_dims, rows_per_block)
                 segments_to_run = []
             else:
@@ -652,16 +664,61 @@ class LoadKeOpsB200:
         self.last_launch = dict(nsplit=nsplit, col_chunk=col_chunk, grid_x=-(-nrow // rows_per_block),
                                 nbatch=nbatch, regs=lk.regs, blocks_per_sm=lk.blocks_per_sm, launches=launches,
                                 segments=[(a, b, c) for a, b, c, _ in segments], kmin_seed_columns=n_seed)
+        if engine is not None:
+            self.last_launch["engine"] = engine
+            self.last_launch["launches"] = launches + 1            # + kb200_kfpack
+            for t_ in args[-2:]:
+                t_.record_stream(torch.cuda.current_stream(dev))
         return out
 
-    def _launch_kmin_seeded(self, lk, stream, dev, tdtype, esz, nrow, ncol, n_seed, segments, out_flat, args, strides,
+    # ---- K nearest neighbours in dimension <= 3: filtered kernel (codegen/emit_kmin_filter.py) ----------------------------
+    KFILTER_MIN_PAIRS = 1e8        # below, the pack launch and the mean are not worth it
+
+    def _kmin_filter_setup(self, dev, index, ncol, args, tdtype):
+        """``(loaded kernel, kernel source, [packed rows, info])`` of the filtered K-min kernel for this call, after
+        ``kb200_kfpack`` has written the shifted streamed rows and the largest squared norm; ``None`` if the kernel does
+        not apply."""
+        import ctypes as C
+        p = self.params
+        if self.ks_kfilter is None:
+            # 128-thread CTAs, three per SM: 170 registers per thread keep the K-lists of four rows without spills
+            # (256 threads x 2 CTAs cap at 128 registers: 20 values spill inside the pair loop)
+            c0 = self.ks.cfg
+            cfg = KernelConfig(T=int(os.environ.get("KB200_KF_T", 128)), R=c0.R, TJ=c0.TJ, unroll=c0.unroll,
+                               min_blocks=int(os.environ.get("KB200_KF_B", 3)), group=c0.group)
+            ks = emit_kmin_filter.generate_filtered(self.red, p.nargs, cfg, self.ks)
+            self.ks_kfilter = ks if ks is not None else False
+        ks = self.ks_kfilter
+        if ks is False:
+            return None
+        lk = self._loaded.get(("kfilter", index))
+        if lk is None:
+            lk = plan.load_kernel(ks, True, index)
+            lk.fn_pack = lk.module.function("kb200_kfpack")
+            self._loaded[("kfilter", index)] = lk
+        D, iy = ks.kfilter["D"], ks.kfilter["col"]
+        y = args[iy]
+        i64, ptr = C.c_longlong, C.c_void_p
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            info = torch.zeros(4 + -(-ncol // 256), dtype=tdtype, device=dev)     # [shift (4), max |y'|^2 per 256 columns]
+            # common shift (x - y is unchanged): the mean of the streamed cloud, non-finite entries counted as 0 -- any finite
+            # vector near the cloud will do, the margin is computed from what the shift leaves
+            info[:D] = torch.nan_to_num(torch.nan_to_num(y, nan=0.0, posinf=0.0, neginf=0.0).mean(dim=0, dtype=torch.float32),
+                                        nan=0.0, posinf=0.0, neginf=0.0)
+            ypk = torch.empty(ncol * 4, dtype=tdtype, device=dev)
+            capi.launch(lk.fn_pack, stream, (-(-ncol // 256), 1, 1), (256,), 0,
+                        [i64(ncol), ptr(y.data_ptr()), ptr(ypk.data_ptr()), ptr(info.data_ptr())])
+        return lk, ks, [ypk, info]
+
+    def _launch_kmin_seeded(self, lk, ks, stream, dev, tdtype, esz, nrow, ncol, n_seed, segments, out_flat, args, strides,
                             row_dims, rows_per_block):
         """Row segments through ``kb200_reduce_seeded`` / ``kb200_combine``: the column splits of a row publish their
         K-th smallest value to ``shthr[row][component]`` (atomic min, starts at +inf) and skip candidates above the
         smallest value published so far -- an upper bound of the final K-th value, so the result is exactly the
         unsplit kernel's while each split is spared the transient of a list that starts empty."""
         import ctypes as C
-        p, ks = self.params, self.ks
+        p = self.params
         i64, ptr, i32 = C.c_longlong, C.c_void_p, C.c_int
         d = self.red.dimF
         T = ks.cfg.T

@@ -1,0 +1,272 @@
+"""Filtered K-min kernels for squared Euclidean distances in dimension 1..3 (the K-nearest-neighbour search of BASELINE
+configs[2]: ``ArgKMin_Reduction(SqDist(x_i, y_j), K)`` in D = 3).
+
+The reference evaluates ``|x_i - y_j|^2`` as D subtractions, one multiplication and D - 1 FMAs per pair and tests every
+value against the row's K-th smallest (``keopscore/keopscore/mapreduce/gpu/GpuReduc1D.py:70-90``,
+``keopscore/keopscore/formulas/reductions/KMin_ArgKMin_Reduction.py:71-100``); the generic kernel of this package does the same
+with packed instructions: 2 D packed operations + 1 compare per pair, 0.85 of that roofline (ncu: FMA pipe 75 %, issue 70 %).
+
+Here the pair loop evaluates a *filter* instead: with both clouds shifted by the streamed cloud's mean ``m``,
+
+    s_ij = |y'_j|^2 - 2 x'_i . y'_j   ( = |x_i - y_j|^2 - |x'_i|^2 ),      x' = x - m,  y' = y - m
+
+costs D FMAs per pair -- the streamed row ``(y'_0 .. y'_{D-1}, |y'|^2)`` is one 16-byte shared-memory read, written once per
+call by ``kb200_kfpack`` -- and is compared with ``thr_i - |x'_i|^2 + margin_i``.  Only pairs that pass (a few hundred per
+row over the whole stream) are evaluated exactly, with the generic kernel's own packed operations in the reference's order, and
+go through the same insertion: **the output is bit-identical to the generic kernel's** (``tests/test_kmin_filter_gpu.py``),
+hence to the reference's wherever that one is.
+
+Margin (fp32, round to nearest, flush-to-zero harmless): let ``A = (|x'_i| + max_j |y'_j|)^2``.  The FMA chain and
+``|y'|^2`` carry at most 6 * 2^-24 A, ``|x'|^2`` 3 * 2^-24 A, the shift of the coordinates 2 * 2^-24 A, the exact value itself
+5 * 2^-24 A against the real ``|x - y|^2``, forming the threshold (``thr_i + (margin_i - |x'_i|^2)``) 3 * 2^-24 A: 19 * 2^-24 A in
+all.  ``margin_i = 2^-18 (|x'_i|^2 + max_j |y'_j|^2) + 1e-30 >= 32 * 2^-24 A``, with the
+maximum taken over the streamed tile at hand (1024 columns), so that an outlier loosens the filter of its own tile only.  A pair with ``d_ij < thr_i`` therefore always passes; columns with non-finite
+coordinates never pass, exactly as they never satisfy ``d_ij < thr_i``.  For O(1) clouds of 1e6 points the margin widens the
+tested radius by a few percent: a handful of extra exact evaluations per row.
+
+Column splits, shared thresholds between the splits (``kb200_reduce_seeded``), the partial format and ``kb200_combine`` are the
+generic kernel's: the binder launches this source through the same code path with two extra pointer arguments (packed rows,
+``[m_0 .. m_{D-1}, pad, max |y'|^2 per block of 256 columns]``).
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Optional, Tuple
+
+from ..formulas.reductions import Reduction
+from .emit import GENERATOR_VERSION, KernelConfig, KernelSource, prelude
+
+VERSION = "kmin-filter-5"
+MAX_D = 3
+
+
+def match(red: Reduction) -> Optional[Tuple[int, int, int]]:
+    """``(row_var, col_var, D)`` for a K-min family reduction of ``Sum(Square(Var - Var))`` between an output-side and a
+    streamed variable of dimension <= 3 (either order of the subtraction: the squares are the same)."""
+    if red.kind not in ("KMin", "ArgKMin", "KMin_ArgKMin") or red.dimF != 1 or not (1 <= red.K <= 16):
+        return None
+    f = red.formula
+    if f.op != "Sum" or len(f.args) != 1 or f.args[0].op != "Square":
+        return None
+    sub = f.args[0].args[0]
+    if sub.op != "Subtract" or len(sub.args) != 2 or any(a.op != "Var" for a in sub.args):
+        return None
+    (ia, da, ca), (ib, db, cb) = sub.args[0].params, sub.args[1].params
+    if da != db or {ca, cb} != {0, 1} or not (1 <= da <= MAX_D):
+        return None
+    row, col = (ia, ib) if ca == red.tagI else (ib, ia)
+    return row, col, da
+
+
+def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: KernelSource) -> Optional[KernelSource]:
+    """The filtered kernel for ``red`` (fp32, fast math), same entry points and calling convention as ``generic`` plus two
+    pointer arguments; ``None`` when the reduction does not have the shape."""
+    m = match(red)
+    if m is None or generic.dtype != "float32" or generic.is_zero:
+        return None
+    ix, iy, D = m
+    first_is_row = red.formula.args[0].args[0].args[0].params[0] == ix      # x - y or y - x in the formula
+    K, R, T, TJ = red.K, cfg.R, cfg.T, cfg.TJ
+    assert R % 2 == 0
+    NA = nargs + 2                         # a<nargs> = packed rows, a<nargs + 1> = [m_0 .. m_{D-1}, pad, block maxima of |y'|^2]
+    kind = red.kind
+    dimout = {"KMin": K, "ArgKMin": K, "KMin_ArgKMin": 2 * K}[kind]
+    cname = generic.combine_name
+    marker = 'extern "C" __global__ void __launch_bounds__(256)\n' + cname
+    if marker not in generic.source:
+        return None
+    combine_src = generic.source[generic.source.index(marker):]          # identical partial format -> identical combine
+
+    ptr_args = ", ".join("const real* __restrict__ a%d_" % k for k in range(NA))
+    str_args = ", ".join("const long long bs%d" % k for k in range(NA))
+    call_args = ", ".join(["a%d_" % k for k in range(NA)] + ["bs%d" % k for k in range(NA)])
+
+    def sub(a: str, b: str) -> str:        # the subtraction of the formula, in its own order
+        return "kb_sub_v(%s, %s)" % ((a, b) if first_is_row else (b, a))
+
+    L = []
+    W = L.append
+    W("#define KB_T %d\n#define KB_R %d\n#define KB_TJ %d\n#define KB_STRIDE 4\n#define KB_F64 0\n#define KB_FAST 1" % (T, R, TJ))
+    W(prelude())
+    # ---- pack kernel -------------------------------------------------------------------------------------------------
+    W("// one thread per streamed point: shifted coordinates + squared norm as one 16-byte row; max |y'|^2 over the finite rows")
+    W('extern "C" __global__ void __launch_bounds__(256)')
+    W("kb200_kfpack(const long long ncol, const real* __restrict__ y, real* __restrict__ ypk, real* __restrict__ info)")
+    W("{")
+    W("  // info = [m_0 .. m_{D-1}, pad to 4, then one maximum of |y'|^2 per block of 256 columns (zero-initialised)]")
+    W("  const long long j_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+    W("  real s_ = 0.0f;")
+    W("  if (j_ < ncol) {")
+    W("    real r_[4] = {0.0f, 0.0f, 0.0f, 0.0f};")
+    for k in range(D):
+        W("    r_[%d] = y[j_ * %d + %d] - info[%d];" % (k, D, k, k))
+    W("    s_ = r_[0] * r_[0];")
+    for k in range(1, D):
+        W("    s_ = fmaf(r_[%d], r_[%d], s_);" % (k, k))
+    W("    r_[3] = s_;")
+    W("    *reinterpret_cast<float4*>(ypk + j_ * 4) = make_float4(r_[0], r_[1], r_[2], r_[3]);")
+    W("    if (!(s_ < KB_INF)) s_ = 0.0f;                 // non-finite rows never pass the filter: keep them out of the margin")
+    W("  }")
+    W("  KB_UNROLL_ALL for (int o_ = 16; o_ > 0; o_ >>= 1) s_ = fmaxf(s_, __shfl_xor_sync(0xffffffffu, s_, o_));")
+    W("  if ((threadIdx.x & 31) == 0 && s_ > 0.0f) atomicMax(reinterpret_cast<int*>(info) + 4 + blockIdx.x, __float_as_int(s_));")
+    W("}")
+    W("")
+    # ---- reduce body -------------------------------------------------------------------------------------------------
+    W("__device__ __forceinline__ void kb200_reduce_body(const long long nrow, const long long ncol, const long long col_chunk, "
+      "real* __restrict__ out, real* __restrict__ partial, %s, %s, real* __restrict__ shthr, const int force_partial)" % (ptr_args, str_args))
+    W("{")
+    W("  __shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
+    W("  const int tid = threadIdx.x;")
+    W("  const real* __restrict__ ax = a%d_ + (long long)blockIdx.z * bs%d;" % (ix, ix))
+    W("  const real* __restrict__ ay = a%d_ + (long long)blockIdx.z * bs%d;" % (iy, iy))
+    W("  const real* __restrict__ ypk = a%d_;" % nargs)
+    W("  const real* __restrict__ info = a%d_;" % (nargs + 1))
+    W("  out += (long long)blockIdx.z * nrow * %d;" % dimout)
+    W("  partial += (long long)blockIdx.z * gridDim.y * nrow * %d;" % (2 * K))
+    W("  const long long row0 = (long long)blockIdx.x * (KB_T * KB_R) + tid;")
+    W("#define KF_ROW(q) ((row0 + (long long)(q) * KB_T < nrow) ? (row0 + (long long)(q) * KB_T) : (nrow - 1))   /* recomputed, not kept */")
+    W("  const long long jbeg = (long long)blockIdx.y * col_chunk;")
+    W("  const long long jend = (jbeg + col_chunk < ncol) ? (jbeg + col_chunk) : ncol;")
+    W("  // ---- hoisted row values: -2 x' (filter) and tbase = 2^-18 |x'|^2 + 1e-30 - |x'|^2; the filter threshold of a tile is")
+    W("  // thr + tbase + 2^-18 max_{j in tile} |y'_j|^2 (the exact path re-reads x: registers are scarce)")
+    W("  V tbase;")
+    W("  { V xsq = kb_bcast_v(0.0f);")
+    for k in range(D):
+        W("    KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) { const real xs_ = ax[KF_ROW(q) * %d + %d] - info[%d]; xsq.l[q] = fmaf(xs_, xs_, xsq.l[q]); }" % (D, k, k))
+    W("    KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) tbase.l[q] = fmaf(3.814697265625e-06f, xsq.l[q], 1e-30f) - xsq.l[q]; }")
+    for k in range(D):
+        W("  V m2x%d; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) m2x%d.l[q] = -2.0f * (ax[KF_ROW(q) * %d + %d] - info[%d]);" % (k, k, D, k, k))
+    W("  real ctmax = 0.0f;                               // 2^-18 x the largest |y'|^2 of the current tile")
+    W("  // ---- accumulators: K smallest values + indices per row, strict threshold thr, filter threshold thrp")
+    W("  real kval[KB_R][%d]; int kidx[KB_R][%d]; V thr = kb_bcast_v(KB_INF), thrp;" % (K, K))
+    W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { kval[q][l_] = KB_INF; kidx[q][l_] = 0; }" % K)
+    W("#define KF_THRP(q) thrp.l[q] = (thr.l[q] + tbase.l[q]) + ctmax")
+    W("  real* const shp = (shthr != nullptr) ? (shthr + row0) : nullptr;")
+    W("  if (shp != nullptr) {")
+    W("    KB_UNROLL_ALL for (int q = 0; q < KB_R; q++)")
+    W("      if (row0 + (long long)q * KB_T < nrow) thr.l[q] = kb_next_up(__ldcg(shp + q * KB_T)); }")
+    W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KF_THRP(q);")
+
+    def stage(jbase: str, buf: str):
+        W("    for (int e = tid; e < KB_TJ; e += KB_T) {")
+        W("      const long long j_ = (%s) + e;" % jbase)
+        W("      const bool ok_ = j_ < jend;")
+        W("      kb_cp_async16(&sm[%s][e * 4], ypk + (ok_ ? j_ * 4 : 0), ok_);" % buf)
+        W("    }")
+
+    def filt(dst: str, src: str):
+        e = "%s.w" % src
+        for k in reversed(range(D)):
+            e = "kb_fma_v(m2x%d, %s.%s, %s)" % (k, src, "xyz"[k], e)
+        W("        %s = %s;" % (dst, e))
+
+    def exact(col: str, pre: str = "        "):
+        # the generic kernel's own evaluation, on all KB_R rows of the thread, then the same test and insertion
+        W(pre + "{ const long long jc_ = %s;" % col)
+        for k in range(D):
+            W(pre + "  V x%d_; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) x%d_.l[q] = __ldg(ax + KF_ROW(q) * %d + %d);" % (k, k, D, k))
+            W(pre + "  const V d%d_ = %s;" % (k, sub("x%d_" % k, "__ldg(ay + jc_ * %d + %d)" % (D, k))))
+        W(pre + "  V f_ = kb_mul_v(d0_, d0_);")
+        for k in range(1, D):
+            W(pre + "  f_ = kb_fma_v(d%d_, d%d_, f_);" % (k, k))
+        W(pre + "  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) if (f_.l[q] < thr.l[q]) {")
+        W(pre + "    kb_kmin_insert<%d, int>(kval[q], kidx[q], f_.l[q], (int)jc_); thr.l[q] = kb_fmin(kval[q][%d], thr.l[q]); KF_THRP(q); } }" % (K, K - 1))
+
+    W("  // ---- stage the first tile")
+    W("  {")
+    stage("jbeg", "0")
+    W("  }")
+    W("  kb_cp_commit(); kb_cp_wait_all(); __syncthreads();")
+    W("  int buf = 0;")
+    W("  for (long long jt = jbeg; jt < jend; jt += KB_TJ) {")
+    W("    if (jt + KB_TJ < jend) {")
+    stage("jt + KB_TJ", "buf ^ 1")
+    W("    }")
+    W("    kb_cp_commit();")
+    W("    const int jn = (int)((jend - jt < KB_TJ) ? (jend - jt) : KB_TJ);")
+    W("    { real tm_ = 0.0f;                               // per-tile margin: an outlier only loosens the filter of its own tile")
+    W("      KB_UNROLL_ALL for (int b_ = 0; b_ < KB_TJ / 256; b_++) { const long long jb_ = jt / 256 + b_; if (jb_ * 256 < ncol) tm_ = fmaxf(tm_, __ldg(info + 4 + jb_)); }")
+    W("      ctmax = 3.814697265625e-06f * tm_;")
+    W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KF_THRP(q); }")
+    W("    const float4* yrow = reinterpret_cast<const float4*>(&sm[buf][0]);")
+    W("    int jr = 0;")
+    W("    #pragma unroll 1")
+    W("    for (; jr + 4 <= jn; jr += 4, yrow += 4) {")
+    W("      V fg_[4];")
+    W("      KB_UNROLL_ALL for (int g_ = 0; g_ < 4; g_++) {")
+    W("        const float4 q0 = yrow[g_];")
+    filt("fg_[g_]", "q0")
+    W("      }")
+    W("      bool any_ = false;")
+    W("      // one compare per row: the smallest of its four filter values (FMNMX3 + FMNMX instead of four FSETP + predicate logic)")
+    W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) {")
+    W("        const real m_ = fminf(fminf(fminf(fg_[0].l[q], fg_[1].l[q]), fg_[2].l[q]), fg_[3].l[q]);")
+    W("        any_ |= (m_ < thrp.l[q]); }")
+    W("      if (any_) {")
+    W("        KB_UNROLL_ALL for (int g_ = 0; g_ < 4; g_++) {")
+    W("          bool hit_ = false;")
+    W("          KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) hit_ |= (fg_[g_].l[q] < thrp.l[q]);")
+    W("          if (hit_)")
+    exact("jt + jr + g_", "          ")
+    W("        }")
+    W("      }")
+    W("    }")
+    W("    #pragma unroll 1")
+    W("    for (; jr < jn; jr++, yrow += 1) {")
+    W("      const float4 q0 = yrow[0];")
+    W("      V f1_;")
+    filt("f1_", "q0")
+    W("      bool any_ = false;")
+    W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (f1_.l[q] < thrp.l[q]);")
+    W("      if (any_)")
+    exact("jt + jr", "      ")
+    W("    }")
+    W("    if (shp != nullptr) {")
+    W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++)")
+    W("        if (row0 + (long long)q * KB_T < nrow) {")
+    W("          real* a_ = shp + q * KB_T; real s_ = __ldcg(a_);")
+    W("          if (kval[q][%d] < s_) { kb_atomic_min(a_, kval[q][%d]); s_ = kval[q][%d]; }" % (K - 1, K - 1, K - 1))
+    W("          thr.l[q] = kb_fmin(thr.l[q], kb_next_up(s_)); KF_THRP(q); } }")
+    W("    kb_cp_wait_all(); __syncthreads();")
+    W("    buf ^= 1;")
+    W("  }")
+    W("  // ---- write back")
+    W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) {")
+    W("    const long long r_ = row0 + (long long)q * KB_T;")
+    W("    if (r_ < nrow) {")
+    W("      if (gridDim.y == 1 && !force_partial) {")
+    W("        real* po = out + r_ * %d;" % dimout)
+    if kind == "ArgKMin":
+        W("        KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) po[l_] = (real)kidx[q][l_];" % K)
+    elif kind == "KMin":
+        W("        KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) po[l_] = kval[q][l_];" % K)
+    else:
+        W("        KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { po[l_ * 2] = kval[q][l_]; po[l_ * 2 + 1] = (real)kidx[q][l_]; }" % K)
+    W("      } else {")
+    W("        real* po = partial + ((long long)blockIdx.y * nrow + r_) * %d;" % (2 * K))
+    W("        KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { po[l_ * 2] = kval[q][l_]; po[l_ * 2 + 1] = (real)kidx[q][l_]; }" % K)
+    W("      }")
+    W("    }")
+    W("  }")
+    W("#undef KF_THRP")
+    W("#undef KF_ROW")
+    W("}")
+    W("")
+    sig = ("(const long long nrow, const long long ncol, const long long col_chunk, real* __restrict__ out, "
+           "real* __restrict__ partial, %s, %s" % (ptr_args, str_args))
+    W('extern "C" __global__ void __launch_bounds__(KB_T, %d)' % cfg.min_blocks)
+    W("%s%s)" % (generic.kernel_name, sig))
+    W("{ kb200_reduce_body(nrow, ncol, col_chunk, out, partial, %s, nullptr, 0); }" % call_args)
+    W('extern "C" __global__ void __launch_bounds__(KB_T, %d)' % cfg.min_blocks)
+    W("kb200_reduce_seeded%s, real* __restrict__ shthr, const int force_partial)" % sig)
+    W("{ kb200_reduce_body(nrow, ncol, col_chunk, out, partial, %s, shthr, force_partial); }" % call_args)
+    W("")
+    W(combine_src)
+    src = "\n".join(L)
+    h = hashlib.sha256((GENERATOR_VERSION + VERSION + src).encode()).hexdigest()[:16]
+    ks = KernelSource(source=src, kernel_name=generic.kernel_name, combine_name=cname, cfg=cfg, dtype="float32",
+                      tagI=red.tagI, dim=generic.dim, dimred=generic.dimred, dimpart=2 * K, nargs=NA,
+                      row_vars=generic.row_vars, col_vars=generic.col_vars, par_vars=generic.par_vars, stride=4,
+                      smem_bytes=2 * TJ * 4 * 4, hash=h)
+    ks.kfilter = dict(row=ix, col=iy, D=D)
+    return ks
