@@ -684,7 +684,8 @@ class LoadKeOpsB200:
             # 128-thread CTAs, three per SM: 170 registers per thread keep the K-lists of four rows without spills
             # (256 threads x 2 CTAs cap at 128 registers: 20 values spill inside the pair loop)
             c0 = self.ks.cfg
-            cfg = KernelConfig(T=int(os.environ.get("KB200_KF_T", 128)), R=c0.R, TJ=c0.TJ, unroll=c0.unroll,
+            cfg = KernelConfig(T=int(os.environ.get("KB200_KF_T", 128)), R=int(os.environ.get("KB200_KF_R", c0.R)),
+                               TJ=int(os.environ.get("KB200_KF_TJ", c0.TJ)), unroll=c0.unroll,
                                min_blocks=int(os.environ.get("KB200_KF_B", 3)), group=c0.group)
             ks = emit_kmin_filter.generate_filtered(self.red, p.nargs, cfg, self.ks)
             self.ks_kfilter = ks if ks is not None else False
@@ -706,7 +707,7 @@ class LoadKeOpsB200:
             # vector near the cloud will do, the margin is computed from what the shift leaves
             info[:D] = torch.nan_to_num(torch.nan_to_num(y, nan=0.0, posinf=0.0, neginf=0.0).mean(dim=0, dtype=torch.float32),
                                         nan=0.0, posinf=0.0, neginf=0.0)
-            ypk = torch.empty(ncol * 4, dtype=tdtype, device=dev)
+            ypk = torch.empty(ncol * 8, dtype=tdtype, device=dev)      # per column: the filter's row + the coordinates
             capi.launch(lk.fn_pack, stream, (-(-ncol // 256), 1, 1), (256,), 0,
                         [i64(ncol), ptr(y.data_ptr()), ptr(ypk.data_ptr()), ptr(info.data_ptr())])
         return lk, ks, [ypk, info]

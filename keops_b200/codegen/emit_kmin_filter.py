@@ -11,7 +11,8 @@ Here the pair loop evaluates a *filter* instead: with both clouds shifted by the
     s_ij = |y'_j|^2 - 2 x'_i . y'_j   ( = |x_i - y_j|^2 - |x'_i|^2 ),      x' = x - m,  y' = y - m
 
 costs D FMAs per pair -- the streamed row ``(y'_0 .. y'_{D-1}, |y'|^2)`` is one 16-byte shared-memory read, written once per
-call by ``kb200_kfpack`` -- and is compared with ``thr_i - |x'_i|^2 + margin_i``.  Only pairs that pass (a few hundred per
+call by ``kb200_kfpack`` -- and only the smallest value of a row over a group of 8 columns is compared with
+``thr_i - |x'_i|^2 + margin_i`` (FMNMX3: two columns per instruction; the next group's FMAs are issued before the test).  Only pairs that pass (a few hundred per
 row over the whole stream) are evaluated exactly, with the generic kernel's own packed operations in the reference's order, and
 go through the same insertion: **the output is bit-identical to the generic kernel's** (``tests/test_kmin_filter_gpu.py``),
 hence to the reference's wherever that one is.
@@ -36,7 +37,7 @@ from typing import Optional, Tuple
 from ..formulas.reductions import Reduction
 from .emit import GENERATOR_VERSION, KernelConfig, KernelSource, prelude
 
-VERSION = "kmin-filter-5"
+VERSION = "kmin-filter-7"
 MAX_D = 3
 
 
@@ -86,7 +87,7 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
 
     L = []
     W = L.append
-    W("#define KB_T %d\n#define KB_R %d\n#define KB_TJ %d\n#define KB_STRIDE 4\n#define KB_F64 0\n#define KB_FAST 1" % (T, R, TJ))
+    W("#define KB_T %d\n#define KB_R %d\n#define KB_TJ %d\n#define KB_STRIDE 8\n#define KB_F64 0\n#define KB_FAST 1" % (T, R, TJ))
     W(prelude())
     # ---- pack kernel -------------------------------------------------------------------------------------------------
     W("// one thread per streamed point: shifted coordinates + squared norm as one 16-byte row; max |y'|^2 over the finite rows")
@@ -104,7 +105,10 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     for k in range(1, D):
         W("    s_ = fmaf(r_[%d], r_[%d], s_);" % (k, k))
     W("    r_[3] = s_;")
-    W("    *reinterpret_cast<float4*>(ypk + j_ * 4) = make_float4(r_[0], r_[1], r_[2], r_[3]);")
+    W("    real o_[4] = {0.0f, 0.0f, 0.0f, 0.0f};")
+    W("    KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) o_[k_] = y[j_ * %d + k_];" % (D, D))
+    W("    *reinterpret_cast<float4*>(ypk + j_ * 8) = make_float4(r_[0], r_[1], r_[2], r_[3]);      // the filter's row")
+    W("    *reinterpret_cast<float4*>(ypk + j_ * 8 + 4) = make_float4(o_[0], o_[1], o_[2], o_[3]);  // the untouched coordinates (exact path)")
     W("    if (!(s_ < KB_INF)) s_ = 0.0f;                 // non-finite rows never pass the filter: keep them out of the margin")
     W("  }")
     W("  KB_UNROLL_ALL for (int o_ = 16; o_ > 0; o_ >>= 1) s_ = fmaxf(s_, __shfl_xor_sync(0xffffffffu, s_, o_));")
@@ -115,7 +119,9 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("__device__ __forceinline__ void kb200_reduce_body(const long long nrow, const long long ncol, const long long col_chunk, "
       "real* __restrict__ out, real* __restrict__ partial, %s, %s, real* __restrict__ shthr, const int force_partial)" % (ptr_args, str_args))
     W("{")
-    W("  __shared__ __align__(16) real sm[2][KB_TJ * KB_STRIDE];")
+    W("  // 2 x 1024 columns x 32 bytes = 64 KB: dynamic shared memory (beyond the 48 KB static limit)")
+    W("  extern __shared__ __align__(16) real kb_sm_dyn[];")
+    W("  real (*sm)[KB_TJ * KB_STRIDE] = reinterpret_cast<real (*)[KB_TJ * KB_STRIDE]>(kb_sm_dyn);")
     W("  const int tid = threadIdx.x;")
     W("  const real* __restrict__ ax = a%d_ + (long long)blockIdx.z * bs%d;" % (ix, ix))
     W("  const real* __restrict__ ay = a%d_ + (long long)blockIdx.z * bs%d;" % (iy, iy))
@@ -148,30 +154,41 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KF_THRP(q);")
 
     def stage(jbase: str, buf: str):
-        W("    for (int e = tid; e < KB_TJ; e += KB_T) {")
-        W("      const long long j_ = (%s) + e;" % jbase)
+        W("    for (int e = tid; e < 2 * KB_TJ; e += KB_T) {")
+        W("      const long long j_ = (%s) + (e >> 1);" % jbase)
         W("      const bool ok_ = j_ < jend;")
-        W("      kb_cp_async16(&sm[%s][e * 4], ypk + (ok_ ? j_ * 4 : 0), ok_);" % buf)
+        W("      kb_cp_async16(&sm[%s][e * 4], ypk + (ok_ ? j_ * 8 + (e & 1) * 4 : 0), ok_);" % buf)
         W("    }")
 
-    def filt(dst: str, src: str):
+    def filt(src: str) -> str:
         e = "%s.w" % src
         for k in reversed(range(D)):
             e = "kb_fma_v(m2x%d, %s.%s, %s)" % (k, src, "xyz"[k], e)
-        W("        %s = %s;" % (dst, e))
+        return e
 
-    def exact(col: str, pre: str = "        "):
-        # the generic kernel's own evaluation, on all KB_R rows of the thread, then the same test and insertion
-        W(pre + "{ const long long jc_ = %s;" % col)
+    def load_x(pre: str):
+        # output-side coordinates of the thread's rows (L1 / L2): once per rare-path entry, not kept across the pair loop
         for k in range(D):
-            W(pre + "  V x%d_; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) x%d_.l[q] = __ldg(ax + KF_ROW(q) * %d + %d);" % (k, k, D, k))
-            W(pre + "  const V d%d_ = %s;" % (k, sub("x%d_" % k, "__ldg(ay + jc_ * %d + %d)" % (D, k))))
+            W(pre + "V x%d_; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) x%d_.l[q] = __ldg(ax + KF_ROW(q) * %d + %d);" % (k, k, D, k))
+
+    def exact(col: str, yrow: str, pre: str):
+        # the generic kernel's own evaluation, on all KB_R rows of the thread, then the same test and insertion
+        W(pre + "{ const long long jc_ = %s; const float4 yo_ = %s;" % (col, yrow))
+        for k in range(D):
+            W(pre + "  const V d%d_ = %s;" % (k, sub("x%d_" % k, "yo_.%s" % "xyz"[k])))
         W(pre + "  V f_ = kb_mul_v(d0_, d0_);")
         for k in range(1, D):
             W(pre + "  f_ = kb_fma_v(d%d_, d%d_, f_);" % (k, k))
         W(pre + "  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) if (f_.l[q] < thr.l[q]) {")
         W(pre + "    kb_kmin_insert<%d, int>(kval[q], kidx[q], f_.l[q], (int)jc_); thr.l[q] = kb_fmin(kval[q][%d], thr.l[q]); KF_THRP(q); } }" % (K, K - 1))
 
+    GC = 8                                # columns per group: one compare per row and group
+    W("  // smallest filter value of every row over the %d columns starting at tile row `r0_` (FMNMX3: two columns per instruction)" % GC)
+    W("#define KF_GROUP_MIN(dst, r0_) { const float4* yg_ = yrow + 2 * (r0_); dst = kb_bcast_v(KB_INF); \\")
+    for c in range(0, GC, 2):
+        W("    { const float4 qa_ = yg_[%d], qb_ = yg_[%d]; const V fa_ = %s; const V fb_ = %s; \\" % (2 * c, 2 * c + 2, filt("qa_"), filt("qb_")))
+        W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) dst.l[q] = fminf(fminf(dst.l[q], fa_.l[q]), fb_.l[q]); } \\")
+    W("  }")
     W("  // ---- stage the first tile")
     W("  {")
     stage("jbeg", "0")
@@ -188,38 +205,50 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("      KB_UNROLL_ALL for (int b_ = 0; b_ < KB_TJ / 256; b_++) { const long long jb_ = jt / 256 + b_; if (jb_ * 256 < ncol) tm_ = fmaxf(tm_, __ldg(info + 4 + jb_)); }")
     W("      ctmax = 3.814697265625e-06f * tm_;")
     W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KF_THRP(q); }")
-    W("    const float4* yrow = reinterpret_cast<const float4*>(&sm[buf][0]);")
-    W("    int jr = 0;")
+    W("    const float4* yrow = reinterpret_cast<const float4*>(&sm[buf][0]);      // two float4 per column: filter row, coordinates")
+    W("    const int jg = jn & ~%d;                        // whole groups" % (GC - 1))
+    W("    // software pipeline: the next group's filter values are issued before this group's minima are tested, so that the")
+    W("    // compare / branch chain overlaps independent FFMA2 work (ncu of the unpipelined loop: issue 54 %, fixed-latency waits)")
+    W("    V mn_;")
+    W("    if (jg > 0) KF_GROUP_MIN(mn_, 0)")
     W("    #pragma unroll 1")
-    W("    for (; jr + 4 <= jn; jr += 4, yrow += 4) {")
-    W("      V fg_[4];")
-    W("      KB_UNROLL_ALL for (int g_ = 0; g_ < 4; g_++) {")
-    W("        const float4 q0 = yrow[g_];")
-    filt("fg_[g_]", "q0")
-    W("      }")
+    W("    for (int jr = 0; jr < jg; jr += %d) {" % GC)
+    W("      V nx_ = kb_bcast_v(KB_INF);")
+    W("      if (jr + %d < jg) KF_GROUP_MIN(nx_, jr + %d)" % (GC, GC))
     W("      bool any_ = false;")
-    W("      // one compare per row: the smallest of its four filter values (FMNMX3 + FMNMX instead of four FSETP + predicate logic)")
-    W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) {")
-    W("        const real m_ = fminf(fminf(fminf(fg_[0].l[q], fg_[1].l[q]), fg_[2].l[q]), fg_[3].l[q]);")
-    W("        any_ |= (m_ < thrp.l[q]); }")
+    W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (mn_.l[q] < thrp.l[q]);")
     W("      if (any_) {")
-    W("        KB_UNROLL_ALL for (int g_ = 0; g_ < 4; g_++) {")
+    W("        // rare (~5 % of the groups): which columns of the group pass?  All eight filter values again, straight-line (the")
+    W("        // looped version serialised eight shared-memory round trips), then the exact evaluation of the few that do")
+    W("        unsigned hits_ = 0u;")
+    W("        KB_UNROLL_ALL for (int g_ = 0; g_ < %d; g_++) {" % GC)
+    W("          const float4 q0 = yrow[2 * (jr + g_)];")
+    W("          const V fv_ = %s;" % filt("q0"))
     W("          bool hit_ = false;")
-    W("          KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) hit_ |= (fg_[g_].l[q] < thrp.l[q]);")
-    W("          if (hit_)")
-    exact("jt + jr + g_", "          ")
+    W("          KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) hit_ |= (fv_.l[q] < thrp.l[q]);")
+    W("          hits_ |= hit_ ? (1u << g_) : 0u;")
+    W("        }")
+    W("        if (hits_) {")
+    load_x("          ")
+    W("          #pragma unroll 1")
+    W("          for (; hits_; hits_ &= hits_ - 1) {")
+    W("            const int g_ = __ffs(hits_) - 1;")
+    exact("jt + jr + g_", "yrow[2 * (jr + g_) + 1]", "            ")
+    W("          }")
     W("        }")
     W("      }")
+    W("      mn_ = nx_;")
     W("    }")
     W("    #pragma unroll 1")
-    W("    for (; jr < jn; jr++, yrow += 1) {")
-    W("      const float4 q0 = yrow[0];")
-    W("      V f1_;")
-    filt("f1_", "q0")
+    W("    for (int jr = jg; jr < jn; jr++) {")
+    W("      const float4 q0 = yrow[2 * jr];")
+    W("      const V fv_ = %s;" % filt("q0"))
     W("      bool any_ = false;")
-    W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (f1_.l[q] < thrp.l[q]);")
-    W("      if (any_)")
-    exact("jt + jr", "      ")
+    W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (fv_.l[q] < thrp.l[q]);")
+    W("      if (any_) {")
+    load_x("        ")
+    exact("jt + jr", "yrow[2 * jr + 1]", "        ")
+    W("      }")
     W("    }")
     W("    if (shp != nullptr) {")
     W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++)")
@@ -230,6 +259,7 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("    kb_cp_wait_all(); __syncthreads();")
     W("    buf ^= 1;")
     W("  }")
+    W("#undef KF_GROUP_MIN")
     W("  // ---- write back")
     W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) {")
     W("    const long long r_ = row0 + (long long)q * KB_T;")
@@ -267,6 +297,6 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     ks = KernelSource(source=src, kernel_name=generic.kernel_name, combine_name=cname, cfg=cfg, dtype="float32",
                       tagI=red.tagI, dim=generic.dim, dimred=generic.dimred, dimpart=2 * K, nargs=NA,
                       row_vars=generic.row_vars, col_vars=generic.col_vars, par_vars=generic.par_vars, stride=4,
-                      smem_bytes=2 * TJ * 4 * 4, hash=h)
+                      smem_bytes=2 * TJ * 8 * 4, hash=h, dynamic_smem=2 * TJ * 8 * 4)
     ks.kfilter = dict(row=ix, col=iy, D=D)
     return ks
