@@ -420,6 +420,12 @@ def main():
                "pair_evals_per_s": float(M) * N / (ms * 1e-3), "n_gpus": world, "engine": engine}
         if engine == "cuda-core":
             res["frac_of_roofline"] = float(M) * N / (ms * 1e-3) / cc_peak(2 * D + 1)
+        elif engine == "cuda-core/kmin-filter":
+            # filtered kernel (codegen/emit_kmin_filter.py): D FMAs per pair on the FP32 pipe (+ 1/2 FMNMX3 on the ALU pipe)
+            res["frac_of_roofline"] = float(M) * N / (ms * 1e-3) / cc_peak(D)
+            res["roofline_note"] = ("FP32-pipe roofline of the %d-FMA filter (128 / %d pairs/clk/SM); against the reference's "
+                                    "%d-operation pair (the round-1 roofline) the rate is %.2f" %
+                                    (D, D, 2 * D + 1, float(M) * N / (ms * 1e-3) / cc_peak(2 * D + 1)))
         else:
             from keops_b200.codegen import knn_tc
             kdim = knn_tc.KnnTensorCore(D, 10, "ArgKMin", True, device=-1).DPG
