@@ -591,8 +591,10 @@ class LoadKeOpsB200:
         lk = self._kernel(index)
         ks = self.ks
         engine = None
-        if (self._kf_match is not None and nbatch == 1 and p.tag1D2D == 0 and float(nrow) * float(ncol) >= self.KFILTER_MIN_PAIRS
-                and os.environ.get("KB200_KMIN_FILTER", "1") != "0"):
+        kf_env = os.environ.get("KB200_KMIN_FILTER", "1")
+        if (self._kf_match is not None and nbatch == 1 and p.tag1D2D == 0 and kf_env != "0"
+                and (kf_env == "force" or (float(nrow) * float(ncol) >= self.KFILTER_MIN_PAIRS
+                                           and ncol >= self.KFILTER_MIN_COLS * max(1, self.red.K // 2)))):
             kf = self._kmin_filter_setup(dev, index, ncol, args, tdtype)
             if kf is not None:
                 lk, ks, extra = kf
@@ -673,6 +675,10 @@ class LoadKeOpsB200:
 
     # ---- K nearest neighbours in dimension <= 3: filtered kernel (codegen/emit_kmin_filter.py) ----------------------------
     KFILTER_MIN_PAIRS = 1e8        # below, the pack launch and the mean are not worth it
+    # The filter pays once survivors are rare per WARP: a warp's 128 rows together see ~128 K ln(N / K) list updates whatever
+    # N is, against N / 8 column groups.  Measured (experiments/kmeans_check.py, ArgMin, D = 3): 1e6 x 1e6 204.8 -> 134.9 ms,
+    # but 1e7 points against 1000 centroids 2.59 -> 3.54 ms (every group of the short stream holds an update for some lane).
+    KFILTER_MIN_COLS = 50000       # streamed points, times K / 2 for lists (K = 10: 250 000)
 
     def _kmin_filter_setup(self, dev, index, ncol, args, tdtype):
         """``(loaded kernel, kernel source, [packed rows, info])`` of the filtered K-min kernel for this call, after
@@ -684,9 +690,11 @@ class LoadKeOpsB200:
             # 128-thread CTAs, three per SM: 170 registers per thread keep the K-lists of four rows without spills
             # (256 threads x 2 CTAs cap at 128 registers: 20 values spill inside the pair loop)
             c0 = self.ks.cfg
+            lists = emit_kmin_filter.KINDS[self.red.kind][1]
+            # (Min / ArgMin keep one value per row: 89 registers, five 128-thread CTAs per SM, 32 KB tiles)
             cfg = KernelConfig(T=int(os.environ.get("KB200_KF_T", 128)), R=int(os.environ.get("KB200_KF_R", c0.R)),
-                               TJ=int(os.environ.get("KB200_KF_TJ", c0.TJ)), unroll=c0.unroll,
-                               min_blocks=int(os.environ.get("KB200_KF_B", 3)), group=c0.group)
+                               TJ=int(os.environ.get("KB200_KF_TJ", 1024 if lists else 512)), unroll=c0.unroll,
+                               min_blocks=int(os.environ.get("KB200_KF_B", 3 if lists else 5)), group=c0.group)
             ks = emit_kmin_filter.generate_filtered(self.red, p.nargs, cfg, self.ks)
             self.ks_kfilter = ks if ks is not None else False
         ks = self.ks_kfilter

@@ -1,5 +1,5 @@
-"""Filtered K-min kernels for squared Euclidean distances in dimension 1..3 (the K-nearest-neighbour search of BASELINE
-configs[2]: ``ArgKMin_Reduction(SqDist(x_i, y_j), K)`` in D = 3).
+"""Filtered K-min / Min / ArgMin kernels for squared Euclidean distances in dimension 2..3 (the K-nearest-neighbour search of
+BASELINE configs[2]: ``ArgKMin_Reduction(SqDist(x_i, y_j), K)`` in D = 3; ``ArgMin``: the assignment step of K-means).
 
 The reference evaluates ``|x_i - y_j|^2`` as D subtractions, one multiplication and D - 1 FMAs per pair and tests every
 value against the row's K-th smallest (``keopscore/keopscore/mapreduce/gpu/GpuReduc1D.py:70-90``,
@@ -37,14 +37,18 @@ from typing import Optional, Tuple
 from ..formulas.reductions import Reduction
 from .emit import GENERATOR_VERSION, KernelConfig, KernelSource, prelude
 
-VERSION = "kmin-filter-7"
+VERSION = "kmin-filter-8"
 MAX_D = 3
+# reduction kind -> (what a row of the output holds, is it a list of K).  Min / ArgMin / Min_ArgMin (nearest neighbour, the
+# assignment step of K-means) are the K = 1 case: same strict '<' update, same (value, index) partials.
+KINDS = {"KMin": ("val", True), "ArgKMin": ("idx", True), "KMin_ArgKMin": ("both", True),
+         "Min": ("val", False), "ArgMin": ("idx", False), "Min_ArgMin": ("both", False)}
 
 
 def match(red: Reduction) -> Optional[Tuple[int, int, int]]:
     """``(row_var, col_var, D)`` for a K-min family reduction of ``Sum(Square(Var - Var))`` between an output-side and a
     streamed variable of dimension <= 3 (either order of the subtraction: the squares are the same)."""
-    if red.kind not in ("KMin", "ArgKMin", "KMin_ArgKMin") or red.dimF != 1 or not (1 <= red.K <= 16):
+    if red.kind not in KINDS or red.dimF != 1 or not (1 <= red.K <= 16):
         return None
     f = red.formula
     if f.op != "Sum" or len(f.args) != 1 or f.args[0].op != "Square":
@@ -67,11 +71,11 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
         return None
     ix, iy, D = m
     first_is_row = red.formula.args[0].args[0].args[0].params[0] == ix      # x - y or y - x in the formula
-    K, R, T, TJ = red.K, cfg.R, cfg.T, cfg.TJ
-    assert R % 2 == 0
+    what, is_list = KINDS[red.kind]
+    K, R, T, TJ = (red.K if is_list else 1), cfg.R, cfg.T, cfg.TJ
+    assert R % 2 == 0 and TJ % 256 == 0
     NA = nargs + 2                         # a<nargs> = packed rows, a<nargs + 1> = [m_0 .. m_{D-1}, pad, block maxima of |y'|^2]
-    kind = red.kind
-    dimout = {"KMin": K, "ArgKMin": K, "KMin_ArgKMin": 2 * K}[kind]
+    dimout = 2 * K if what == "both" else K
     cname = generic.combine_name
     marker = 'extern "C" __global__ void __launch_bounds__(256)\n' + cname
     if marker not in generic.source:
@@ -266,9 +270,9 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("    if (r_ < nrow) {")
     W("      if (gridDim.y == 1 && !force_partial) {")
     W("        real* po = out + r_ * %d;" % dimout)
-    if kind == "ArgKMin":
+    if what == "idx":
         W("        KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) po[l_] = (real)kidx[q][l_];" % K)
-    elif kind == "KMin":
+    elif what == "val":
         W("        KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) po[l_] = kval[q][l_];" % K)
     else:
         W("        KB_UNROLL_ALL for (int l_ = 0; l_ < %d; l_++) { po[l_ * 2] = kval[q][l_]; po[l_ * 2 + 1] = (real)kidx[q][l_]; }" % K)

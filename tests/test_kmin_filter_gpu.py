@@ -17,9 +17,10 @@ def test_match_and_cross_compile():
     from keops_b200.runtime import plan
     assert emit_kmin_filter.match(parse_reduction("ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)")) == (0, 1, 3)
     assert emit_kmin_filter.match(parse_reduction("KMin_ArgKMin_Reduction(SqDist(Var(1,2,1),Var(0,2,0)),5,1)")) == (1, 0, 2)
+    assert emit_kmin_filter.match(parse_reduction("ArgMin_Reduction(SqDist(Var(0,3,0),Var(1,3,1)),0)")) == (0, 1, 3)
     for f in ("ArgKMin_Reduction(Sum(Square((Var(0,4,0) - Var(1,4,1)))),10,0)",            # D = 4
               "ArgKMin_Reduction(Sum(Abs((Var(0,3,0) - Var(1,3,1)))),10,0)",               # not a squared distance
-              "ArgMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),0)",                # not the K-min family
+              "Max_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),0)",                   # not a minimum
               "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,0)))),10,0)"):           # both operands on one side
         assert emit_kmin_filter.match(parse_reduction(f)) is None
     bd = get_binder("KMin_ArgKMin_Reduction(Sum(Square((Var(1,2,1) - Var(0,2,0)))),5,1)", [], 2, "float32")
@@ -35,7 +36,7 @@ def _run(formula, args, M, N, dev, filtered):
     import torch
     from keops_b200.binder import get_binder
     old = os.environ.get("KB200_KMIN_FILTER")
-    os.environ["KB200_KMIN_FILTER"] = "1" if filtered else "0"
+    os.environ["KB200_KMIN_FILTER"] = "force" if filtered else "0"      # "force": the test shapes are below the size heuristics
     try:
         bd = get_binder(formula, [], 2, "float32")
         out = bd.genred_pytorch(dev, None, M, N, 0, None, *args)
@@ -58,6 +59,10 @@ CASES = [
     ("ArgKMin", 3, 10, 20000, 20000, 0, "xy", "grid"),             # integer-valued points: exact ties -> smallest index
     ("KMin_ArgKMin", 3, 4, 20000, 20000, 0, "xy", "nonfinite"),    # NaN / inf columns are never selected, as in the generic kernel
     ("ArgKMin", 2, 1, 40000, 10000, 0, "xy", "outlier"),           # one huge point inflates the margin: still exact
+    # nearest neighbour / K-means assignment: the K = 1 case of the same kernel (K is ignored in the formula string)
+    ("ArgMin", 3, 0, 300000, 1000, 0, "xy", "randn"),
+    ("Min_ArgMin", 2, 0, 20000, 30000, 1, "yx", "grid"),
+    ("Min", 3, 0, 1500, 200000, 0, "xy", "uniform"),               # few rows: column splits + combine
 ]
 
 
@@ -66,7 +71,7 @@ CASES = [
 def test_filtered_kmin_identical_to_generic_kernel(kind, D, K, nx, ny, tagI, order, data, cuda_device):
     import torch
     dev = cuda_device
-    torch.manual_seed(D * 100 + K)
+    torch.manual_seed(D * 100 + K + len(kind))
     if data == "uniform":
         x, y = torch.rand(nx, D, device=dev), torch.rand(ny, D, device=dev)
     elif data == "grid":
@@ -84,11 +89,14 @@ def test_filtered_kmin_identical_to_generic_kernel(kind, D, K, nx, ny, tagI, ord
     if data == "outlier":
         streamed[3] = 1.0e6
     sub = "(Var(0,%d,0) - Var(1,%d,1))" % (D, D) if order == "xy" else "(Var(1,%d,1) - Var(0,%d,0))" % (D, D)
-    f = "%s_Reduction(Sum(Square(%s)),%d,%d)" % (kind, sub, K, tagI)
+    if K:
+        f = "%s_Reduction(Sum(Square(%s)),%d,%d)" % (kind, sub, K, tagI)
+    else:
+        f = "%s_Reduction(Sum(Square(%s)),%d)" % (kind, sub, tagI)
     o_f, ll = _run(f, (x, y), nx, ny, dev, True)
     assert ll.get("engine") == "cuda-core/kmin-filter", ll
     if (nx if tagI == 0 else ny) < 2000:
-        assert ll["nsplit"] > 1 and ll["kmin_seed_columns"] == 1, ll
+        assert ll["nsplit"] > 1 and ll["kmin_seed_columns"] == (1 if K else 0), ll
     o_g, ll2 = _run(f, (x, y), nx, ny, dev, False)
     assert ll2.get("engine") is None, ll2
     if data == "nonfinite":                                   # NaN != NaN: compare bit patterns
