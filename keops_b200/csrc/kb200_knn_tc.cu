@@ -42,7 +42,8 @@
 //   parking survivor groups in registers and handling them in batches (178 ms: fewer but ~3x longer stalls, which the two
 //   buffers absorb worse), mailing them to two helper warps that own the lists (152-156 ms: their polling and the extra
 //   warps cost clock under the power cap), 32-column TMEM reads overlapped with the reductions (156 ms: the accumulator
-//   is released later), private token sub-lists instead of a shared counter (no change), L2-sized column chunks (272 ms:
+//   is released later), private token sub-lists instead of a shared counter (no change), 512-row CTAs with four single-buffered
+//   row blocks and one thread per row (144.7 ms: same cycles per row, 13.2 -> 14 waves), L2-sized column chunks (272 ms:
 //   every chunk replays the transient of an empty list).
 // kb200_knn_prep   : fp32 -> bf16 operand rows (data, penalty columns, zero padding) + per-row penalty terms.
 // kb200_knn_select : one warp per row, exact distances of the candidates (tokens decoded) + ordered top-K (ties ->
