@@ -680,12 +680,8 @@ class LoadKeOpsB200:
     # but 1e7 points against 1000 centroids 2.59 -> 3.54 ms (every group of the short stream holds an update for some lane).
     KFILTER_MIN_COLS = 50000       # streamed points, times K / 2 for lists (K = 10: 250 000)
 
-    def _kmin_filter_setup(self, dev, index, ncol, args, tdtype):
-        """``(loaded kernel, kernel source, [packed rows, info])`` of the filtered K-min kernel for this call, after
-        ``kb200_kfpack`` has written the shifted streamed rows and the largest squared norm; ``None`` if the kernel does
-        not apply."""
-        import ctypes as C
-        p = self.params
+    def _kfilter_source(self) -> Optional[KernelSource]:
+        """The filtered kernel's source for this reduction (generated once), or None when it does not apply."""
         if self.ks_kfilter is None:
             # 128-thread CTAs, three per SM: 170 registers per thread keep the K-lists of four rows without spills
             # (256 threads x 2 CTAs cap at 128 registers: 20 values spill inside the pair loop)
@@ -695,10 +691,18 @@ class LoadKeOpsB200:
             cfg = KernelConfig(T=int(os.environ.get("KB200_KF_T", 128)), R=int(os.environ.get("KB200_KF_R", c0.R)),
                                TJ=int(os.environ.get("KB200_KF_TJ", 1024 if lists else 512)), unroll=c0.unroll,
                                min_blocks=int(os.environ.get("KB200_KF_B", 3 if lists else 5)), group=c0.group)
-            ks = emit_kmin_filter.generate_filtered(self.red, p.nargs, cfg, self.ks)
+            ks = emit_kmin_filter.generate_filtered(self.red, self.params.nargs, cfg, self.ks)
             self.ks_kfilter = ks if ks is not None else False
-        ks = self.ks_kfilter
-        if ks is False:
+        return self.ks_kfilter or None
+
+    def _kmin_filter_setup(self, dev, index, ncol, args, tdtype):
+        """``(loaded kernel, kernel source, [packed rows, info])`` of the filtered K-min kernel for this call, after
+        ``kb200_kfpack`` has written the shifted streamed rows and the largest squared norm; ``None`` if the kernel does
+        not apply."""
+        import ctypes as C
+        p = self.params
+        ks = self._kfilter_source()
+        if ks is None:
             return None
         lk = self._loaded.get(("kfilter", index))
         if lk is None:
