@@ -411,7 +411,7 @@ class LoadKeOpsB200:
             over = eng.run(args[row_ind], args[col_ind], out.view(nrow, p.dim), torch.cuda.current_stream(dev))
         self.last_launch = dict(nsplit=eng.last["nsplit"], col_chunk=ncol, grid_x=eng.last["ctas"], nbatch=1, regs=0,
                                 blocks_per_sm=1, launches=4 + (eng.last["nsplit"] > 1), engine="tcgen05",
-                                overflow_rows=eng.last["overflow"])
+                                overflow_rows=eng.last["overflow"], segments=eng.last["segments"])
         if over.numel():
             sub = list(args)
             sub[row_ind] = args[row_ind][over].contiguous()

@@ -24,12 +24,13 @@ from ..runtime import capi, plan
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 _SRC_PATH = os.path.join(_CSRC, "kb200_knn_tc.cu")
 _COMMON_PATH = os.path.join(_CSRC, "kb200_tc_common.cuh")      # PTX wrappers, prepended (NVRTC has no include path)
-VERSION = "knn-tc-14"
+VERSION = "knn-tc-17"
 BM, BN, STAGES, HS, KP, THREADS = 256, 128, 4, 8, 16, 576
 MAX_SMEM = 227 * 1024
 RESIDENT_MAX_COLS = 160      # D + 3 <= 160: the CTA's row operand stays in shared memory (>= 3 ring stages); beyond, k-blocks are streamed
 MAX_D = 1021                 # operand rows of at most 1024 bf16 columns
 ROW_BATCH = 1 << 20          # rows per filter launch: bounds the candidate workspace (CAP * 4 bytes per row)
+TAIL_MAX_WAVES = int(os.environ.get("KB200_KNN_TC_TAIL_WAVES", 16))   # split the last partial wave only below this many waves of row blocks
 _lock = threading.RLock()
 
 
@@ -148,19 +149,41 @@ class KnnTensorCore:
         capi.launch(self.fn_prep, stream, (-(-N // 256),), (256,), 0,
                     [i64(N), ptr(y.data_ptr()), ptr(ybf.data_ptr()), ptr(ypen.data_ptr()), i32(0)])
         map_y, map_yr = self._maps(ybf, N, BN)
-        # column splits: with fewer 256-row blocks than SMs, the column range is divided over gridDim.y
-        nblocks = -(-min(M, ROW_BATCH) // BM)
-        nsplit = 1
-        if os.environ.get("KB200_KNN_TC_SPLIT", "1") != "0" and nblocks < self.sm_count:
-            nsplit = max(1, min(self.sm_count // nblocks, ntiles // 64, 32))
-        if os.environ.get("KB200_KNN_TC_NSPLIT"):          # experiments: forced column chunks (L2-sized y slabs)
-            nsplit = max(1, min(int(os.environ["KB200_KNN_TC_NSPLIT"]), ntiles))
-        tiles_per_split = -(-ntiles // nsplit)
-        nsplit = -(-ntiles // tiles_per_split)
-        overflow_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        overflow_rows = torch.empty(max(M, 1) * nsplit, dtype=torch.int32, device=dev)
+        # Row segments (first row, rows, column splits).  With fewer 256-row blocks than SMs the column range is divided over
+        # gridDim.y; with many, the LAST partial wave of row blocks is split so that it also fills the machine: 489 row blocks
+        # (one GPU's shard of an 8-GPU run at M = 1e6) are 3 full waves + 45 blocks -- unsplit that is 4 waves, with the tail
+        # split 3-way 3.33 (the splits of a row keep their own candidate lists and are merged, so only the tail's rows pay the
+        # restart of an empty list).
+        def small_split(nb):
+            return max(1, min(self.sm_count // nb, ntiles // 64, 32))
+        forced = os.environ.get("KB200_KNN_TC_NSPLIT")      # experiments: forced column chunks (L2-sized y slabs)
+        segments = []
         for r0 in range(0, M, ROW_BATCH):
             m = min(ROW_BATCH, M - r0)
+            nb = -(-m // BM)
+            if forced:
+                segments.append((r0, m, max(1, min(int(forced), ntiles))))
+            elif nb < self.sm_count:
+                segments.append((r0, m, small_split(nb) if os.environ.get("KB200_KNN_TC_SPLIT", "1") != "0" else 1))
+            else:
+                full = (nb // self.sm_count) * self.sm_count
+                rem = nb - full
+                ns_tail = min(small_split(rem), 4) if rem else 1
+                # (measured, experiments/knn_d64_shards.py, D = 64, N = 1e6, median of 7: 125 000 rows = 3.3 waves 22.97 -> 20.62 ms;
+                # 500 000 rows = 13.2 waves 83.1 -> 80.9 ms; 1e6 rows = 26.4 waves 162.3 -> 161.7 ms: not worth a second launch)
+                if (rem and ns_tail >= 2 and nb < TAIL_MAX_WAVES * self.sm_count
+                        and os.environ.get("KB200_KNN_TC_TAIL", "1") != "0"):
+                    segments += [(r0, full * BM, 1), (r0 + full * BM, m - full * BM, ns_tail)]
+                else:
+                    segments.append((r0, m, 1))
+        max_split = max(sg[2] for sg in segments)
+        overflow_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        overflow_rows = torch.empty(max(M, 1) * max_split, dtype=torch.int32, device=dev)
+        ctas = 0
+        for r0, m, nsplit in segments:
+            tiles_per_split = -(-ntiles // nsplit)
+            nsplit = -(-ntiles // tiles_per_split)
+            ctas += -(-m // BM) * nsplit
             xs = x[r0:r0 + m]
             xbf = torch.empty((m, self.DPG), dtype=torch.int16, device=dev)
             xpen = torch.empty(m, dtype=torch.float32, device=dev)
@@ -179,22 +202,16 @@ class KnnTensorCore:
             if os.environ.get("KT_TIME"):
                 ev1.record(stream_obj)
                 torch.cuda.synchronize()
-                print("KT_TIME filter %.3f ms (STAGES=%d stream=%d nsplit=%d)" % (ev0.elapsed_time(ev1), self.STAGES, int(self.stream), nsplit))
-            # select writes rows r0.. of `out` (or per-split lists); overflow rows are reported relative to the batch
-            ov_before = overflow_count.clone() if r0 else None
+                print("KT_TIME filter %.3f ms (rows %d..%d STAGES=%d stream=%d nsplit=%d)" % (ev0.elapsed_time(ev1), r0, r0 + m, self.STAGES, int(self.stream), nsplit))
+            # select writes rows r0.. of `out` (or per-split lists); overflowed rows are reported with their global index
             out_ptr = out.data_ptr() + r0 * self.outw * 4
             capi.launch(self.fn_select, stream, (-(-(m * nsplit) // 8),), (256,), 0,
                         [i64(m), i64(N), ptr(xs.data_ptr()), ptr(y.data_ptr()), ptr(cand.data_ptr()), ptr(count.data_ptr()),
                          ptr(out_ptr), ptr(overflow_count.data_ptr()), ptr(overflow_rows.data_ptr()), i32(nsplit),
-                         ptr(part.data_ptr())])
+                         ptr(part.data_ptr()), i64(r0)])
             if nsplit > 1:
                 capi.launch(self.fn_merge, stream, (-(-m // 256),), (256,), 0,
                             [i64(m), i32(nsplit), ptr(part.data_ptr()), ptr(out_ptr)])
-            if r0:
-                # make the batch-relative indices appended by this launch global
-                a, b = int(ov_before.item()), int(overflow_count.item())
-                if b > a:
-                    overflow_rows[a:b] += r0
             if os.environ.get("KT_STATS"):
                 cf = count.view(m, nsplit).sum(1).float()
                 self.stats = dict(mean_candidates=float(cf.mean()), max_candidates=float(cf.max()),
@@ -204,9 +221,10 @@ class KnnTensorCore:
         for t in (ybf, ypen):
             t.record_stream(stream_obj)
         n_over = int(overflow_count.item())          # one host sync per call (the reference syncs on every call)
-        self.last = dict(overflow=n_over, ntiles=ntiles, ctas=nblocks * nsplit, nsplit=nsplit)
+        self.last = dict(overflow=n_over, ntiles=ntiles, ctas=ctas, nsplit=max_split,
+                         segments=[(a_, a_ + m_, n_) for a_, m_, n_ in segments])
         rows = overflow_rows[:n_over].to(torch.int64)
-        return torch.unique(rows) if nsplit > 1 and n_over else rows      # a row may overflow in several splits
+        return torch.unique(rows) if max_split > 1 and n_over else rows      # a row may overflow in several splits
 
 
 _cache: Dict[tuple, KnnTensorCore] = {}

@@ -527,7 +527,7 @@ extern "C" __global__ void __launch_bounds__(256)
 kb200_knn_select(const long long nrow, const long long ncol, const float* __restrict__ x, const float* __restrict__ y,
                  const int* __restrict__ cand, const int* __restrict__ cand_count, float* __restrict__ out,
                  int* __restrict__ overflow_count, int* __restrict__ overflow_rows, const int nsplit,
-                 float* __restrict__ part) {
+                 float* __restrict__ part, const long long row_offset) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (row, split) pair
   const long long i = w / nsplit;
@@ -536,7 +536,7 @@ kb200_knn_select(const long long nrow, const long long ncol, const float* __rest
   const int n = cand_count[w];
   constexpr int OUTW = (KT_OUT == 2) ? 2 * KT_K : KT_K;
   if (n > KT_CAP) {                                   // token list overflowed: the caller recomputes this row
-    if (lane == 0) { const int s = atomicAdd(overflow_count, 1); overflow_rows[s] = (int)i; }
+    if (lane == 0) { const int s = atomicAdd(overflow_count, 1); overflow_rows[s] = (int)(i + row_offset); }   // global row index
     return;
   }
   // every lane keeps the K best (distance, index) pairs of the candidates it evaluated, ascending

@@ -42,6 +42,8 @@ CASES = [
     ("ArgKMin", 200, 10, 8192, 5000, 0),
     ("KMin_ArgKMin", 784, 5, 8192, 4500, 0),  # MNIST-sized rows
     ("ArgKMin", 300, 3, 1200, 66000, 0),      # streamed k-blocks + column splits
+    # 176 row blocks = one full wave of 148 + a tail of 28: the tail's column range is split so that it fills the machine too
+    ("ArgKMin", 64, 10, 45000, 20000, 0),
 ]
 
 
@@ -56,6 +58,8 @@ def test_tensor_core_kmin_identical_to_cuda_core(kind, D, K, M, N, tagI, cuda_de
     assert ll.get("engine") == "tcgen05", ll          # the tensor-core kernels really ran
     if (M if tagI == 0 else N) < 8192:
         assert ll["nsplit"] > 1, ll                   # few rows: column splits + per-split lists + merge
+    if (M if tagI == 0 else N) == 45000:
+        assert [sg[2] for sg in ll["segments"]] == [1, 2] and ll["segments"][0][1] == 148 * 256, ll
     o_cc, ll2 = _run(f, 2, (x, y), M, N, cuda_device, False)
     assert ll2.get("engine") in (None, "cuda-core/chunked"), ll2      # the comparator ran on the CUDA cores
     assert torch.equal(o_tc, o_cc)
