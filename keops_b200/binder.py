@@ -687,10 +687,18 @@ class LoadKeOpsB200:
             # (256 threads x 2 CTAs cap at 128 registers: 20 values spill inside the pair loop)
             c0 = self.ks.cfg
             lists = emit_kmin_filter.KINDS[self.red.kind][1]
-            # (Min / ArgMin keep one value per row: 89 registers, five 128-thread CTAs per SM, 32 KB tiles)
-            cfg = KernelConfig(T=int(os.environ.get("KB200_KF_T", 128)), R=int(os.environ.get("KB200_KF_R", c0.R)),
-                               TJ=int(os.environ.get("KB200_KF_TJ", 1024 if lists else 512)), unroll=c0.unroll,
-                               min_blocks=int(os.environ.get("KB200_KF_B", 3 if lists else 5)), group=c0.group)
+            D = self._kf_match[2]
+            s4 = -(-(D + 1) // 4) + -(-D // 4)               # float4 per staged column: filter row + coordinates
+            # D <= 3: four rows per thread, 1024-column tiles (64 KB), three 128-thread CTAs per SM (170 registers keep the
+            # K-lists of four rows without spills; Min / ArgMin: 89 registers, five CTAs, 512-column tiles).  4 <= D <= 15: two
+            # rows per thread (the -2 x' values alone take 2 D registers), tiles sized to ~48-64 KB
+            if D <= 3:
+                R, TJ, B = c0.R, (1024 if lists else 512), (3 if lists else 5)
+            else:
+                R, TJ, B = 2, (512 if s4 <= 4 else 256), 3
+            cfg = KernelConfig(T=int(os.environ.get("KB200_KF_T", 128)), R=int(os.environ.get("KB200_KF_R", R)),
+                               TJ=int(os.environ.get("KB200_KF_TJ", TJ)), unroll=c0.unroll,
+                               min_blocks=int(os.environ.get("KB200_KF_B", B)), group=c0.group)
             ks = emit_kmin_filter.generate_filtered(self.red, self.params.nargs, cfg, self.ks)
             self.ks_kfilter = ks if ks is not None else False
         return self.ks_kfilter or None
@@ -714,12 +722,12 @@ class LoadKeOpsB200:
         i64, ptr = C.c_longlong, C.c_void_p
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            info = torch.zeros(4 + -(-ncol // 256), dtype=tdtype, device=dev)     # [shift (4), max |y'|^2 per 256 columns]
+            info = torch.zeros(16 + -(-ncol // 256), dtype=tdtype, device=dev)    # [shift (16), max |y'|^2 per 256 columns]
             # common shift (x - y is unchanged): the mean of the streamed cloud, non-finite entries counted as 0 -- any finite
             # vector near the cloud will do, the margin is computed from what the shift leaves
             info[:D] = torch.nan_to_num(torch.nan_to_num(y, nan=0.0, posinf=0.0, neginf=0.0).mean(dim=0, dtype=torch.float32),
                                         nan=0.0, posinf=0.0, neginf=0.0)
-            ypk = torch.empty(ncol * 8, dtype=tdtype, device=dev)      # per column: the filter's row + the coordinates
+            ypk = torch.empty(ncol * ks.kfilter["stride"], dtype=tdtype, device=dev)   # per column: the filter's row + the coordinates
             capi.launch(lk.fn_pack, stream, (-(-ncol // 256), 1, 1), (256,), 0,
                         [i64(ncol), ptr(y.data_ptr()), ptr(ypk.data_ptr()), ptr(info.data_ptr())])
         return lk, ks, [ypk, info]

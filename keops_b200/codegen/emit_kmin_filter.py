@@ -1,4 +1,4 @@
-"""Filtered K-min / Min / ArgMin kernels for squared Euclidean distances in dimension 2..3 (the K-nearest-neighbour search of
+"""Filtered K-min / Min / ArgMin kernels for squared Euclidean distances in dimension 2..15 (the K-nearest-neighbour search of
 BASELINE configs[2]: ``ArgKMin_Reduction(SqDist(x_i, y_j), K)`` in D = 3; ``ArgMin``: the assignment step of K-means).
 
 The reference evaluates ``|x_i - y_j|^2`` as D subtractions, one multiplication and D - 1 FMAs per pair and tests every
@@ -23,7 +23,9 @@ Margin (fp32, round to nearest, flush-to-zero harmless): let ``A = (|x'_i| + max
 all.  ``margin_i = 2^-18 (|x'_i|^2 + max_j |y'_j|^2) + 1e-30 >= 32 * 2^-24 A``, with the
 maximum taken over the streamed tile at hand (1024 columns), so that an outlier loosens the filter of its own tile only.  A pair with ``d_ij < thr_i`` therefore always passes; columns with non-finite
 coordinates never pass, exactly as they never satisfy ``d_ij < thr_i``.  For O(1) clouds of 1e6 points the margin widens the
-tested radius by a few percent: a handful of extra exact evaluations per row.
+tested radius by a few percent: a handful of extra exact evaluations per row.  In dimension D > 3 the same count gives
+``(4 D + 8) 2^-24 A`` (D roundings each in the FMA chain, the two squared norms and the exact value); the constant used is
+``max(2^-18, (4 D + 8) 2^-23)``.
 
 Column splits, shared thresholds between the splits (``kb200_reduce_seeded``), the partial format and ``kb200_combine`` are the
 generic kernel's: the binder launches this source through the same code path with two extra pointer arguments (packed rows,
@@ -37,8 +39,8 @@ from typing import Optional, Tuple
 from ..formulas.reductions import Reduction
 from .emit import GENERATOR_VERSION, KernelConfig, KernelSource, prelude
 
-VERSION = "kmin-filter-8"
-MAX_D = 3
+VERSION = "kmin-filter-10"
+MAX_D = 15                   # from D = 16 the tensor-core filter takes over (codegen/knn_tc.py)
 # reduction kind -> (what a row of the output holds, is it a list of K).  Min / ArgMin / Min_ArgMin (nearest neighbour, the
 # assignment step of K-means) are the K = 1 case: same strict '<' update, same (value, index) partials.
 KINDS = {"KMin": ("val", True), "ArgKMin": ("idx", True), "KMin_ArgKMin": ("both", True),
@@ -74,6 +76,14 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     what, is_list = KINDS[red.kind]
     K, R, T, TJ = (red.K if is_list else 1), cfg.R, cfg.T, cfg.TJ
     assert R % 2 == 0 and TJ % 256 == 0
+    F4, C4 = -(-(D + 1) // 4), -(-D // 4)          # float4 per column: filter row (y', |y'|^2), coordinates
+    S4 = F4 + C4
+    GC = 8 if D <= 3 else 4                        # columns per group: one compare per row and group
+    # margin constant: 2^-18 in dimension <= 3 (derivation in the module docstring); (4 D + 8) 2^-23 beyond -- D roundings each
+    # in the FMA chain, |y'|^2, |x'|^2 and the exact value, + the shift and the threshold, relative to (|x'| + |y'|)^2
+    cm = max(2.0 ** -18, (4 * D + 8) * 2.0 ** -23)
+    CM = "%.9ef" % cm
+    comp = lambda src, k: "%s%d.%s" % (src, k // 4, "xyzw"[k % 4])      # component k of a group of float4 registers
     NA = nargs + 2                         # a<nargs> = packed rows, a<nargs + 1> = [m_0 .. m_{D-1}, pad, block maxima of |y'|^2]
     dimout = 2 * K if what == "both" else K
     cname = generic.combine_name
@@ -91,39 +101,38 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
 
     L = []
     W = L.append
-    W("#define KB_T %d\n#define KB_R %d\n#define KB_TJ %d\n#define KB_STRIDE 8\n#define KB_F64 0\n#define KB_FAST 1" % (T, R, TJ))
+    W("#define KB_T %d\n#define KB_R %d\n#define KB_TJ %d\n#define KB_STRIDE %d\n#define KB_F64 0\n#define KB_FAST 1" % (T, R, TJ, 4 * S4))
     W(prelude())
     # ---- pack kernel -------------------------------------------------------------------------------------------------
     W("// one thread per streamed point: shifted coordinates + squared norm as one 16-byte row; max |y'|^2 over the finite rows")
     W('extern "C" __global__ void __launch_bounds__(256)')
     W("kb200_kfpack(const long long ncol, const real* __restrict__ y, real* __restrict__ ypk, real* __restrict__ info)")
     W("{")
-    W("  // info = [m_0 .. m_{D-1}, pad to 4, then one maximum of |y'|^2 per block of 256 columns (zero-initialised)]")
+    W("  // info = [m_0 .. m_{D-1}, pad to 16, then one maximum of |y'|^2 per block of 256 columns (zero-initialised)]")
     W("  const long long j_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
     W("  real s_ = 0.0f;")
     W("  if (j_ < ncol) {")
-    W("    real r_[4] = {0.0f, 0.0f, 0.0f, 0.0f};")
-    for k in range(D):
-        W("    r_[%d] = y[j_ * %d + %d] - info[%d];" % (k, D, k, k))
+    W("    real r_[%d], o_[%d];" % (4 * F4, 4 * C4))
+    W("    KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) r_[k_] = 0.0f;" % (4 * F4))
+    W("    KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) o_[k_] = 0.0f;" % (4 * C4))
+    W("    KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) { o_[k_] = y[j_ * %d + k_]; r_[k_] = o_[k_] - info[k_]; }" % (D, D))
     W("    s_ = r_[0] * r_[0];")
-    for k in range(1, D):
-        W("    s_ = fmaf(r_[%d], r_[%d], s_);" % (k, k))
-    W("    r_[3] = s_;")
-    W("    real o_[4] = {0.0f, 0.0f, 0.0f, 0.0f};")
-    W("    KB_UNROLL_ALL for (int k_ = 0; k_ < %d; k_++) o_[k_] = y[j_ * %d + k_];" % (D, D))
-    W("    *reinterpret_cast<float4*>(ypk + j_ * 8) = make_float4(r_[0], r_[1], r_[2], r_[3]);      // the filter's row")
-    W("    *reinterpret_cast<float4*>(ypk + j_ * 8 + 4) = make_float4(o_[0], o_[1], o_[2], o_[3]);  // the untouched coordinates (exact path)")
+    W("    KB_UNROLL_ALL for (int k_ = 1; k_ < %d; k_++) s_ = fmaf(r_[k_], r_[k_], s_);" % D)
+    W("    r_[%d] = s_;" % D)
+    W("    float4* dst_ = reinterpret_cast<float4*>(ypk + j_ * KB_STRIDE);")
+    W("    KB_UNROLL_ALL for (int v_ = 0; v_ < %d; v_++) dst_[v_] = make_float4(r_[4 * v_], r_[4 * v_ + 1], r_[4 * v_ + 2], r_[4 * v_ + 3]);   // the filter's row" % F4)
+    W("    KB_UNROLL_ALL for (int v_ = 0; v_ < %d; v_++) dst_[%d + v_] = make_float4(o_[4 * v_], o_[4 * v_ + 1], o_[4 * v_ + 2], o_[4 * v_ + 3]);   // the untouched coordinates (exact path)" % (C4, F4))
     W("    if (!(s_ < KB_INF)) s_ = 0.0f;                 // non-finite rows never pass the filter: keep them out of the margin")
     W("  }")
     W("  KB_UNROLL_ALL for (int o_ = 16; o_ > 0; o_ >>= 1) s_ = fmaxf(s_, __shfl_xor_sync(0xffffffffu, s_, o_));")
-    W("  if ((threadIdx.x & 31) == 0 && s_ > 0.0f) atomicMax(reinterpret_cast<int*>(info) + 4 + blockIdx.x, __float_as_int(s_));")
+    W("  if ((threadIdx.x & 31) == 0 && s_ > 0.0f) atomicMax(reinterpret_cast<int*>(info) + 16 + blockIdx.x, __float_as_int(s_));")
     W("}")
     W("")
     # ---- reduce body -------------------------------------------------------------------------------------------------
     W("__device__ __forceinline__ void kb200_reduce_body(const long long nrow, const long long ncol, const long long col_chunk, "
       "real* __restrict__ out, real* __restrict__ partial, %s, %s, real* __restrict__ shthr, const int force_partial)" % (ptr_args, str_args))
     W("{")
-    W("  // 2 x 1024 columns x 32 bytes = 64 KB: dynamic shared memory (beyond the 48 KB static limit)")
+    W("  // two tiles of KB_TJ columns x KB_STRIDE reals: dynamic shared memory (it can pass the 48 KB static limit)")
     W("  extern __shared__ __align__(16) real kb_sm_dyn[];")
     W("  real (*sm)[KB_TJ * KB_STRIDE] = reinterpret_cast<real (*)[KB_TJ * KB_STRIDE]>(kb_sm_dyn);")
     W("  const int tid = threadIdx.x;")
@@ -143,7 +152,7 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("  { V xsq = kb_bcast_v(0.0f);")
     for k in range(D):
         W("    KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) { const real xs_ = ax[KF_ROW(q) * %d + %d] - info[%d]; xsq.l[q] = fmaf(xs_, xs_, xsq.l[q]); }" % (D, k, k))
-    W("    KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) tbase.l[q] = fmaf(3.814697265625e-06f, xsq.l[q], 1e-30f) - xsq.l[q]; }")
+    W("    KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) tbase.l[q] = fmaf(%s, xsq.l[q], 1e-30f) - xsq.l[q]; }" % CM)
     for k in range(D):
         W("  V m2x%d; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) m2x%d.l[q] = -2.0f * (ax[KF_ROW(q) * %d + %d] - info[%d]);" % (k, k, D, k, k))
     W("  real ctmax = 0.0f;                               // 2^-18 x the largest |y'|^2 of the current tile")
@@ -158,16 +167,24 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KF_THRP(q);")
 
     def stage(jbase: str, buf: str):
-        W("    for (int e = tid; e < 2 * KB_TJ; e += KB_T) {")
-        W("      const long long j_ = (%s) + (e >> 1);" % jbase)
+        W("    for (int e = tid; e < %d * KB_TJ; e += KB_T) {" % S4)
+        if S4 & (S4 - 1) == 0:
+            W("      const int c_ = e >> %d, v_ = e & %d;" % (S4.bit_length() - 1, S4 - 1))
+        else:
+            W("      const int c_ = e / %d, v_ = e - c_ * %d;" % (S4, S4))
+        W("      const long long j_ = (%s) + c_;" % jbase)
         W("      const bool ok_ = j_ < jend;")
-        W("      kb_cp_async16(&sm[%s][e * 4], ypk + (ok_ ? j_ * 8 + (e & 1) * 4 : 0), ok_);" % buf)
+        W("      kb_cp_async16(&sm[%s][e * 4], ypk + (ok_ ? j_ * KB_STRIDE + v_ * 4 : 0), ok_);" % buf)
         W("    }")
 
+    def load_row(pre: str, name: str, col: str, first: int, count: int):
+        # `count` float4 of the staged column `col` (tile row index), starting at float4 `first` of the column
+        W(pre + " ".join("const float4 %s%d = yrow[%d * (%s) + %d];" % (name, v, S4, col, first + v) for v in range(count)))
+
     def filt(src: str) -> str:
-        e = "%s.w" % src
+        e = comp(src, D)                    # |y'|^2
         for k in reversed(range(D)):
-            e = "kb_fma_v(m2x%d, %s.%s, %s)" % (k, src, "xyz"[k], e)
+            e = "kb_fma_v(m2x%d, %s, %s)" % (k, comp(src, k), e)
         return e
 
     def load_x(pre: str):
@@ -175,22 +192,24 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
         for k in range(D):
             W(pre + "V x%d_; KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) x%d_.l[q] = __ldg(ax + KF_ROW(q) * %d + %d);" % (k, k, D, k))
 
-    def exact(col: str, yrow: str, pre: str):
+    def exact(col: str, trow: str, pre: str):
         # the generic kernel's own evaluation, on all KB_R rows of the thread, then the same test and insertion
-        W(pre + "{ const long long jc_ = %s; const float4 yo_ = %s;" % (col, yrow))
+        W(pre + "{ const long long jc_ = %s;" % col)
+        load_row(pre + "  ", "yo", trow, F4, C4)
         for k in range(D):
-            W(pre + "  const V d%d_ = %s;" % (k, sub("x%d_" % k, "yo_.%s" % "xyz"[k])))
+            W(pre + "  const V d%d_ = %s;" % (k, sub("x%d_" % k, comp("yo", k))))
         W(pre + "  V f_ = kb_mul_v(d0_, d0_);")
         for k in range(1, D):
             W(pre + "  f_ = kb_fma_v(d%d_, d%d_, f_);" % (k, k))
         W(pre + "  KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) if (f_.l[q] < thr.l[q]) {")
         W(pre + "    kb_kmin_insert<%d, int>(kval[q], kidx[q], f_.l[q], (int)jc_); thr.l[q] = kb_fmin(kval[q][%d], thr.l[q]); KF_THRP(q); } }" % (K, K - 1))
 
-    GC = 8                                # columns per group: one compare per row and group
     W("  // smallest filter value of every row over the %d columns starting at tile row `r0_` (FMNMX3: two columns per instruction)" % GC)
-    W("#define KF_GROUP_MIN(dst, r0_) { const float4* yg_ = yrow + 2 * (r0_); dst = kb_bcast_v(KB_INF); \\")
+    W("#define KF_GROUP_MIN(dst, r0_) { const float4* yg_ = yrow + %d * (r0_); dst = kb_bcast_v(KB_INF); \\" % S4)
     for c in range(0, GC, 2):
-        W("    { const float4 qa_ = yg_[%d], qb_ = yg_[%d]; const V fa_ = %s; const V fb_ = %s; \\" % (2 * c, 2 * c + 2, filt("qa_"), filt("qb_")))
+        la = " ".join("const float4 qa%d = yg_[%d];" % (v, S4 * c + v) for v in range(F4))
+        lb = " ".join("const float4 qb%d = yg_[%d];" % (v, S4 * (c + 1) + v) for v in range(F4))
+        W("    { %s %s const V fa_ = %s; const V fb_ = %s; \\" % (la, lb, filt("qa"), filt("qb")))
         W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) dst.l[q] = fminf(fminf(dst.l[q], fa_.l[q]), fb_.l[q]); } \\")
     W("  }")
     W("  // ---- stage the first tile")
@@ -206,10 +225,10 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("    kb_cp_commit();")
     W("    const int jn = (int)((jend - jt < KB_TJ) ? (jend - jt) : KB_TJ);")
     W("    { real tm_ = 0.0f;                               // per-tile margin: an outlier only loosens the filter of its own tile")
-    W("      KB_UNROLL_ALL for (int b_ = 0; b_ < KB_TJ / 256; b_++) { const long long jb_ = jt / 256 + b_; if (jb_ * 256 < ncol) tm_ = fmaxf(tm_, __ldg(info + 4 + jb_)); }")
-    W("      ctmax = 3.814697265625e-06f * tm_;")
+    W("      KB_UNROLL_ALL for (int b_ = 0; b_ < KB_TJ / 256; b_++) { const long long jb_ = jt / 256 + b_; if (jb_ * 256 < ncol) tm_ = fmaxf(tm_, __ldg(info + 16 + jb_)); }")
+    W("      ctmax = %s * tm_;" % CM)
     W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) KF_THRP(q); }")
-    W("    const float4* yrow = reinterpret_cast<const float4*>(&sm[buf][0]);      // two float4 per column: filter row, coordinates")
+    W("    const float4* yrow = reinterpret_cast<const float4*>(&sm[buf][0]);      // %d float4 per column: filter row, coordinates" % S4)
     W("    const int jg = jn & ~%d;                        // whole groups" % (GC - 1))
     W("    // software pipeline: the next group's filter values are issued before this group's minima are tested, so that the")
     W("    // compare / branch chain overlaps independent FFMA2 work (ncu of the unpipelined loop: issue 54 %, fixed-latency waits)")
@@ -226,8 +245,8 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("        // looped version serialised eight shared-memory round trips), then the exact evaluation of the few that do")
     W("        unsigned hits_ = 0u;")
     W("        KB_UNROLL_ALL for (int g_ = 0; g_ < %d; g_++) {" % GC)
-    W("          const float4 q0 = yrow[2 * (jr + g_)];")
-    W("          const V fv_ = %s;" % filt("q0"))
+    load_row("          ", "q", "jr + g_", 0, F4)
+    W("          const V fv_ = %s;" % filt("q"))
     W("          bool hit_ = false;")
     W("          KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) hit_ |= (fv_.l[q] < thrp.l[q]);")
     W("          hits_ |= hit_ ? (1u << g_) : 0u;")
@@ -237,7 +256,7 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("          #pragma unroll 1")
     W("          for (; hits_; hits_ &= hits_ - 1) {")
     W("            const int g_ = __ffs(hits_) - 1;")
-    exact("jt + jr + g_", "yrow[2 * (jr + g_) + 1]", "            ")
+    exact("jt + jr + g_", "jr + g_", "            ")
     W("          }")
     W("        }")
     W("      }")
@@ -245,13 +264,13 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     W("    }")
     W("    #pragma unroll 1")
     W("    for (int jr = jg; jr < jn; jr++) {")
-    W("      const float4 q0 = yrow[2 * jr];")
-    W("      const V fv_ = %s;" % filt("q0"))
+    load_row("      ", "q", "jr", 0, F4)
+    W("      const V fv_ = %s;" % filt("q"))
     W("      bool any_ = false;")
     W("      KB_UNROLL_ALL for (int q = 0; q < KB_R; q++) any_ |= (fv_.l[q] < thrp.l[q]);")
     W("      if (any_) {")
     load_x("        ")
-    exact("jt + jr", "yrow[2 * jr + 1]", "        ")
+    exact("jt + jr", "jr", "        ")
     W("      }")
     W("    }")
     W("    if (shp != nullptr) {")
@@ -300,7 +319,7 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     h = hashlib.sha256((GENERATOR_VERSION + VERSION + src).encode()).hexdigest()[:16]
     ks = KernelSource(source=src, kernel_name=generic.kernel_name, combine_name=cname, cfg=cfg, dtype="float32",
                       tagI=red.tagI, dim=generic.dim, dimred=generic.dimred, dimpart=2 * K, nargs=NA,
-                      row_vars=generic.row_vars, col_vars=generic.col_vars, par_vars=generic.par_vars, stride=4,
-                      smem_bytes=2 * TJ * 8 * 4, hash=h, dynamic_smem=2 * TJ * 8 * 4)
-    ks.kfilter = dict(row=ix, col=iy, D=D)
+                      row_vars=generic.row_vars, col_vars=generic.col_vars, par_vars=generic.par_vars, stride=4 * S4,
+                      smem_bytes=2 * TJ * 4 * S4 * 4, hash=h, dynamic_smem=2 * TJ * 4 * S4 * 4)
+    ks.kfilter = dict(row=ix, col=iy, D=D, stride=4 * S4)
     return ks

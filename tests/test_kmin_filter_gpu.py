@@ -18,7 +18,8 @@ def test_match_and_cross_compile():
     assert emit_kmin_filter.match(parse_reduction("ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),10,0)")) == (0, 1, 3)
     assert emit_kmin_filter.match(parse_reduction("KMin_ArgKMin_Reduction(SqDist(Var(1,2,1),Var(0,2,0)),5,1)")) == (1, 0, 2)
     assert emit_kmin_filter.match(parse_reduction("ArgMin_Reduction(SqDist(Var(0,3,0),Var(1,3,1)),0)")) == (0, 1, 3)
-    for f in ("ArgKMin_Reduction(Sum(Square((Var(0,4,0) - Var(1,4,1)))),10,0)",            # D = 4
+    assert emit_kmin_filter.match(parse_reduction("ArgKMin_Reduction(SqDist(Var(0,15,0),Var(1,15,1)),10,0)")) == (0, 1, 15)
+    for f in ("ArgKMin_Reduction(Sum(Square((Var(0,16,0) - Var(1,16,1)))),10,0)",          # D = 16: the tensor-core filter's
               "ArgKMin_Reduction(Sum(Abs((Var(0,3,0) - Var(1,3,1)))),10,0)",               # not a squared distance
               "Max_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),0)",                   # not a minimum
               "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,0)))),10,0)"):           # both operands on one side
@@ -63,6 +64,12 @@ CASES = [
     ("ArgMin", 3, 0, 300000, 1000, 0, "xy", "randn"),
     ("Min_ArgMin", 2, 0, 20000, 30000, 1, "yx", "grid"),
     ("Min", 3, 0, 1500, 200000, 0, "xy", "uniform"),               # few rows: column splits + combine
+    # 4 <= D <= 15: two rows per thread, several 16-byte reads per column (filter row / coordinates: 2+2, 3+2, 4+3, 4+4 float4)
+    ("ArgKMin", 5, 10, 20000, 30000, 0, "xy", "randn"),
+    ("KMin_ArgKMin", 8, 4, 15000, 25001, 1, "yx", "offset"),
+    ("ArgKMin", 12, 16, 12000, 20000, 0, "xy", "grid"),
+    ("KMin", 15, 10, 20000, 20000, 0, "xy", "nonfinite"),
+    ("ArgMin", 10, 0, 1500, 100000, 0, "xy", "outlier"),
 ]
 
 
