@@ -19,13 +19,13 @@ hence to the reference's wherever that one is.
 
 Margin (fp32, round to nearest, flush-to-zero harmless): let ``A = (|x'_i| + max_j |y'_j|)^2``.  The FMA chain and
 ``|y'|^2`` carry at most 6 * 2^-24 A, ``|x'|^2`` 3 * 2^-24 A, the shift of the coordinates 2 * 2^-24 A, the exact value itself
-5 * 2^-24 A against the real ``|x - y|^2``, forming the threshold (``thr_i + (margin_i - |x'_i|^2)``) 3 * 2^-24 A: 19 * 2^-24 A in
-all.  ``margin_i = 2^-18 (|x'_i|^2 + max_j |y'_j|^2) + 1e-30 >= 32 * 2^-24 A``, with the
+5 * 2^-24 A against the real ``|x - y|^2``, forming the threshold (``thr_i + (margin_i - |x'_i|^2)``) at most 12 * 2^-24 A: 28 *
+2^-24 A in all.  ``margin_i = 2^-18 (|x'_i|^2 + max_j |y'_j|^2) + 1e-30 >= 32 * 2^-24 A``, with the
 maximum taken over the streamed tile at hand (1024 columns), so that an outlier loosens the filter of its own tile only.  A pair with ``d_ij < thr_i`` therefore always passes; columns with non-finite
 coordinates never pass, exactly as they never satisfy ``d_ij < thr_i``.  For O(1) clouds of 1e6 points the margin widens the
-tested radius by a few percent: a handful of extra exact evaluations per row.  In dimension D > 3 the same count gives
-``(4 D + 8) 2^-24 A`` (D roundings each in the FMA chain, the two squared norms and the exact value); the constant used is
-``max(2^-18, (4 D + 8) 2^-23)``.
+tested radius by a few percent: a handful of extra exact evaluations per row.  In dimension D the same count gives
+``(4 D + 18) 2^-24 A`` (D roundings each in the FMA chain, the two squared norms and the exact value, the rest as above with
+the threshold counted at its worst); the constant used is ``max(2^-18, (4 D + 20) 2^-23)``.
 
 Column splits, shared thresholds between the splits (``kb200_reduce_seeded``), the partial format and ``kb200_combine`` are the
 generic kernel's: the binder launches this source through the same code path with two extra pointer arguments (packed rows,
@@ -39,7 +39,7 @@ from typing import Optional, Tuple
 from ..formulas.reductions import Reduction
 from .emit import GENERATOR_VERSION, KernelConfig, KernelSource, prelude
 
-VERSION = "kmin-filter-10"
+VERSION = "kmin-filter-11"
 MAX_D = 15                   # from D = 16 the tensor-core filter takes over (codegen/knn_tc.py)
 # reduction kind -> (what a row of the output holds, is it a list of K).  Min / ArgMin / Min_ArgMin (nearest neighbour, the
 # assignment step of K-means) are the K = 1 case: same strict '<' update, same (value, index) partials.
@@ -79,9 +79,11 @@ def generate_filtered(red: Reduction, nargs: int, cfg: KernelConfig, generic: Ke
     F4, C4 = -(-(D + 1) // 4), -(-D // 4)          # float4 per column: filter row (y', |y'|^2), coordinates
     S4 = F4 + C4
     GC = 8 if D <= 3 else 4                        # columns per group: one compare per row and group
-    # margin constant: 2^-18 in dimension <= 3 (derivation in the module docstring); (4 D + 8) 2^-23 beyond -- D roundings each
-    # in the FMA chain, |y'|^2, |x'|^2 and the exact value, + the shift and the threshold, relative to (|x'| + |y'|)^2
-    cm = max(2.0 ** -18, (4 * D + 8) * 2.0 ** -23)
+    # margin constant: in units of 2^-24 (|x'| + |y'|)^2 the filter and the exact value differ by at most D (FMA chain) + D (|y'|^2)
+    # + D (|x'|^2) + 4 (shifted coordinates) + D + 2 (the exact value against the real |x - y|^2) + 12 (forming thr + tbase + ctmax
+    # when thr <= 4 (|x'| + |y'|)^2; a larger thr passes trivially) = 4 D + 18; (|x'|^2 + max |y'|^2) >= (|x'| + |y'|)^2 / 2, so
+    # (4 D + 20) 2^-23 covers it.  D <= 3: 2^-18 = 64 2^-24 (>= 2 x 30).
+    cm = max(2.0 ** -18, (4 * D + 20) * 2.0 ** -23)
     CM = "%.9ef" % cm
     comp = lambda src, k: "%s%d.%s" % (src, k // 4, "xyzw"[k % 4])      # component k of a group of float4 registers
     NA = nargs + 2                         # a<nargs> = packed rows, a<nargs + 1> = [m_0 .. m_{D-1}, pad, block maxima of |y'|^2]
