@@ -64,7 +64,7 @@ def main():
             rec = {"case": name, "world": world, "ms": round(ms, 3), "speedup_vs_1": round(base / ms, 3), "nsplit": ll.get("nsplit"),
                    "grid_x": ll.get("grid_x"), "blocks_per_sm": ll.get("blocks_per_sm"), "engine": ll.get("engine"), "segments": ll.get("segments")}
             print(json.dumps(rec, default=str), flush=True)
-            if world > 1 and os.environ.get("SWEEP", "1") == "1":
+            if (world > 1 or os.environ.get("SWEEP_ALL") == "1") and os.environ.get("SWEEP", "1") == "1":
                 sweep = {}
                 for ns in [int(v) for v in os.environ.get("NS", "4,6,8,10,12,14,17,19,22,24,29,34,39,48").split(",")]:
                     os.environ["KB200_FORCE_NSPLIT"] = str(ns)

@@ -618,7 +618,7 @@ class LoadKeOpsB200:
             penalty = (kpen * (-(-ncol // ks.cfg.TJ))) if kfam else 0.0
             segments = plan.launch_segments(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
                                             split_penalty_tiles=penalty, ws_limit_bytes=ws_limit,
-                                            sms=lk.sm_count if nbatch == 1 else 0)
+                                            sms=lk.sm_count if nbatch == 1 else 0, prefer_uniform=engine is not None)
         else:
             nsplit, col_chunk = plan.launch_shape(nrow, ncol, rows_per_block, ks.cfg.TJ, slots, ks.dimpart, esz,
                                                   ws_limit_bytes=ws_limit, sms=lk.sm_count if nbatch == 1 else 0,

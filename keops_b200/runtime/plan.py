@@ -260,7 +260,8 @@ def launch_shape(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int,
 
 
 def launch_segments(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: int, dimpart: int, esz: int,
-                    split_penalty_tiles: float = 0.0, ws_limit_bytes: int = 2 << 30, sms: int = 0):
+                    split_penalty_tiles: float = 0.0, ws_limit_bytes: int = 2 << 30, sms: int = 0,
+                    prefer_uniform: bool = False):
     """Row segments ``[(row_begin, row_end, nsplit, col_chunk), ...]`` covering ``[0, nrow)``.
 
     Splitting the column range of *every* CTA fixes wave quantisation but makes each split restart its
@@ -286,6 +287,9 @@ def launch_segments(nrow: int, ncol: int, rows_per_block: int, TJ: int, slots: i
     tiles_b = -(-ntiles // ns_b)
     cost_tail = full_waves * (ntiles + ovh) + _sm_rounds(rem * ns_b, slots, sms) * (tiles_b + ovh + (split_penalty_tiles if ns_b > 1 else 0.0)) \
         + (cmb * ns_b if ns_b > 1 else 0.0) + ovh / 2
-    if cost_tail < cost_all:
+    # ``prefer_uniform``: the uniform split wins ties and near-ties: its short CTAs backfill and even out per-SM speed differences.  Measured with the
+    # filtered K-min kernel, whose splits share thresholds (experiments/shard_sweep.py, M x 1e6, D = 3, K = 10): M = 1e6 158.7 ms
+    # (3 uniform splits) vs 159.1 (4 unsplit waves + split tail); 5e5: 80.6 vs 83.1; 2.5e5: 41.6 vs 44.0
+    if cost_tail < (0.95 if prefer_uniform else 1.0) * cost_all:
         return [(0, rows_a, 1, ntiles * TJ), (rows_a, nrow, ns_b, chunk_b)]
     return [(0, nrow, ns_all, chunk_all)]
