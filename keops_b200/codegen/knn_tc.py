@@ -235,6 +235,9 @@ def get(D: int, K: int, kind: str, fast: bool, device: int) -> KnnTensorCore:
     with _lock:
         k = _cache.get(key)
         if k is None:
-            k = KnnTensorCore(D, K, kind, fast, device)
+            # candidate tokens per row: ~ K ln(N / K) list updates + the filter's false positives (measured at K = 10, N = 1e6:
+            # mean 153, maximum 238 of 320 slots); longer lists get proportionally more slots.  Rows that overflow are
+            # recomputed by the CUDA-core kernel -- correct, but slow.
+            k = KnnTensorCore(D, K, kind, fast, device, cap=320 if K <= 10 else 512)
             _cache[key] = k
         return k
