@@ -66,8 +66,8 @@ class LoadKeOpsB200:
               nargs, dtype, lang, optional_flags):
         if tagCPUGPU == 0:
             raise ValueError("[KeOps-B200] this engine has no CPU backend (backend='CPU' is not available).")
-        if lang not in ("torch", "pytorch"):
-            raise ValueError("[KeOps-B200] only the torch binding is implemented.")
+        if lang not in ("torch", "pytorch", "numpy"):
+            raise ValueError("[KeOps-B200] unknown binding %r (torch or numpy expected)." % (lang,))
         if dtype not in ("float32", "float64"):
             raise ValueError("not implemented")
         p = types.SimpleNamespace()
@@ -260,7 +260,8 @@ class LoadKeOpsB200:
         if dev is None:
             raise ValueError("[KeOps-B200] at least one argument is required")
         nx, ny = int(nx), int(ny)
-        nb = int(nbatchdims or 0)
+        # the front-end computes max(arg.ndim) - 2 (generic_red.py:82): -1 when every argument is a parameter vector
+        nb = max(0, int(nbatchdims or 0))
         # ---- shapes: [batch..., n, dim] for variables, [batch..., dim] for parameters
         #      (subset of Sizes<T>, keopscore/keopscore/include/Sizes.h:262-411)
         batch_shape = ()
@@ -824,6 +825,20 @@ class LoadKeOpsB200:
         return out
 
     genred_pytorch = genred
+
+    def genred_numpy(self, device_args, ranges, nx, ny, nbatchdims, out, *args):
+        """The same call as made by the reference's numpy front-end (``LoadKeOps.py:246``,
+        ``pykeops/pykeops/numpy/generic/generic_red.py:357``): host numpy arrays (and numpy ``ranges``) in, numpy array out.
+        The arrays are staged on the CUDA device for the call, as the reference's ``*_host`` launch modes do."""
+        import numpy as np
+        targs = [torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a for a in args]
+        if ranges is not None and len(ranges):
+            ranges = tuple(torch.from_numpy(np.ascontiguousarray(r)) if isinstance(r, np.ndarray) else r for r in ranges)
+        res = self._genred_from_host(device_args, ranges, nx, ny, nbatchdims, None, *targs).numpy()
+        if out is not None:
+            out[...] = res
+            return out
+        return res
 
 
 def get_binder(formula: str, aliases: Sequence[str], nargs: int, dtype: str, optional_flags: Optional[dict] = None,

@@ -170,6 +170,17 @@ class Lowerer:
         if op == "TensorProd":
             a, b = L(n.args[0]), L(n.args[1])
             return [g.mul(x, y) for x in a for y in b]
+        if op == "TensorDot":
+            from ..formulas.ir import TensorDotLayout
+            a, b = L(n.args[0]), L(n.args[1])
+            out = [None] * n.dim
+            for o, prods in TensorDotLayout(*n.params).terms():
+                (ia, ib), rest = prods[0], prods[1:]
+                acc = g.mul(a[ia], b[ib])
+                for ia, ib in rest:
+                    acc = g.add(acc, g.mul(a[ia], b[ib]))
+                out[o] = acc
+            return out
         raise NotImplementedError("operation %s is not supported by the sm_100a code generator" % op)
 
 

@@ -243,4 +243,10 @@ def _rule(f: Node, v: Node, g: Node, memo) -> Node:
     if op == "TensorProd":
         a, b = f.args
         return G(a, ir.MatVecMult(g, b)) + G(b, ir.VecMatMult(a, g))
+    if op == "TensorDot":
+        # the adjoint of a contraction is the contraction of the incoming gradient with the other operand over that
+        # operand's kept axes, stored back in the layout of the differentiated operand (``maths/TensorDot.py:189-216``)
+        a, b = f.args
+        lay = ir.TensorDotLayout(*f.params)
+        return G(a, ir.TensorDot(g, b, *lay.adjoint(0))) + G(b, ir.TensorDot(g, a, *lay.adjoint(1)))
     raise NotImplementedError("no differentiation rule for operation " + op)

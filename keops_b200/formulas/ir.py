@@ -76,7 +76,8 @@ class Node:
             return "IntCst(%d)" % self.params
         if self.op == "RatCst":
             return "RatCst(%d,%d)" % self.params
-        inner = ",".join([repr(a) for a in self.args] + [repr(p) for p in self.params])
+        inner = ",".join([repr(a) for a in self.args] +
+                         [("[%s]" % ",".join(map(str, p)) if isinstance(p, tuple) else repr(p)) for p in self.params])
         return "%s(%s)" % (self.op, inner)
 
     # ---- python operators (used by the parser and by autodiff) ---------------------------
@@ -564,11 +565,123 @@ def TensorProd(a: Node, b: Node) -> Node:
     return Node("TensorProd", (a, b), (), a.dim * b.dim)
 
 
+# ------------------------------------------------------------------------------------------
+# tensor contraction on the internal dimension (``keopscore/keopscore/formulas/maths/TensorDot.py``, ``Kron.py``)
+# ------------------------------------------------------------------------------------------
+def _row_major_strides(shape) -> List[int]:
+    out, s = [], 1
+    for n in reversed(shape):
+        out.append(s)
+        s *= n
+    return out[::-1]
+
+
+def _argsort(seq) -> List[int]:
+    return sorted(range(len(seq)), key=seq.__getitem__)
+
+
+class TensorDotLayout:
+    """Index bookkeeping of ``TensorDot(a, b, dimsfa, dimsfb, contfa, contfb, permute)``.
+
+    ``a`` / ``b`` are row-major tensors of shapes ``dimsfa`` / ``dimsfb`` stored flat; axes ``contfa[c]`` of ``a`` and
+    ``contfb[c]`` of ``b`` are contracted pairwise.  The *natural* result has the kept axes of ``a`` (ascending) followed
+    by the kept axes of ``b`` (as ``numpy.tensordot``); natural axis ``t`` is stored at axis ``permute[t]`` of the
+    row-major output (``TensorDot.py:88-103,160-172``: the output strides are those of the shape ``natural`` scattered
+    by ``permute``).  ``terms()`` lists, for every output component in natural row-major order, the ``(out, ia, ib)``
+    flat indices of its products in the order the reference's loop nest adds them (kept axes outside, contracted
+    axes inside in ``contfa`` order, ``TensorDot.py:155-187``).
+    """
+
+    def __init__(self, dimsfa, dimsfb, contfa, contfb, permute=None):
+        self.dimsfa, self.dimsfb = [int(d) for d in dimsfa], [int(d) for d in dimsfb]
+        self.contfa, self.contfb = [int(c) for c in contfa], [int(c) for c in contfb]
+        if len(self.contfa) != len(self.contfb) or len(set(self.contfa)) != len(self.contfa) \
+                or len(set(self.contfb)) != len(self.contfb) \
+                or any(not 0 <= c < len(self.dimsfa) for c in self.contfa) \
+                or any(not 0 <= c < len(self.dimsfb) for c in self.contfb) \
+                or [self.dimsfa[c] for c in self.contfa] != [self.dimsfb[c] for c in self.contfb]:
+            raise FormulaError("TensorDot: contracted dimensions of the two operands do not match")
+        self.keep_a = [k for k in range(len(self.dimsfa)) if k not in self.contfa]
+        self.keep_b = [k for k in range(len(self.dimsfb)) if k not in self.contfb]
+        self.natural = [self.dimsfa[k] for k in self.keep_a] + [self.dimsfb[k] for k in self.keep_b]
+        nk = len(self.natural)
+        self.permute = list(range(nk)) if permute is None else [int(p) for p in permute]
+        if sorted(self.permute) != list(range(nk)):
+            raise FormulaError("TensorDot: permute must be a permutation of the %d kept axes" % nk)
+        self.out_shape = [0] * nk
+        for t, p in enumerate(self.permute):
+            self.out_shape[p] = self.natural[t]
+        self.cont_shape = [self.dimsfa[c] for c in self.contfa]
+        self.dim = 1
+        for n in self.natural:
+            self.dim *= n
+
+    def params(self) -> tuple:
+        return (tuple(self.dimsfa), tuple(self.dimsfb), tuple(self.contfa), tuple(self.contfb), tuple(self.permute))
+
+    def terms(self):
+        import itertools
+        sa, sb, so = _row_major_strides(self.dimsfa), _row_major_strides(self.dimsfb), _row_major_strides(self.out_shape)
+        na = len(self.keep_a)
+        groups = []
+        for kept in itertools.product(*[range(n) for n in self.natural]):
+            o = sum(kept[t] * so[self.permute[t]] for t in range(len(kept)))
+            a0 = sum(kept[t] * sa[ax] for t, ax in enumerate(self.keep_a))
+            b0 = sum(kept[na + t] * sb[ax] for t, ax in enumerate(self.keep_b))
+            prods = []
+            for cont in itertools.product(*[range(n) for n in self.cont_shape]):
+                prods.append((a0 + sum(cont[c] * sa[ax] for c, ax in enumerate(self.contfa)),
+                              b0 + sum(cont[c] * sb[ax] for c, ax in enumerate(self.contfb))))
+            groups.append((o, prods))
+        return groups
+
+    def adjoint(self, wrt: int) -> tuple:
+        """Parameters ``(dims_g, dims_other, cont_g, cont_other, permute)`` of the contraction of the incoming gradient
+        (shape ``out_shape``) with the *other* operand that yields the gradient w.r.t. operand ``wrt`` in that operand's
+        own layout (``TensorDot.py:105-139,189-216``)."""
+        na = len(self.keep_a)
+        if wrt == 0:
+            cont_g = [self.permute[na + t] for t in range(len(self.keep_b))]
+            back = [self.keep_a[t] for t in _argsort(self.permute[:na])] + \
+                   [self.contfa[c] for c in _argsort(self.contfb)]
+            return (self.out_shape, self.dimsfb, cont_g, self.keep_b, back)
+        cont_g = [self.permute[t] for t in range(na)]
+        back = [self.keep_b[t] for t in _argsort(self.permute[na:])] + \
+               [self.contfb[c] for c in _argsort(self.contfa)]
+        return (self.out_shape, self.dimsfa, cont_g, self.keep_a, back)
+
+
+def _prod(seq) -> int:
+    out = 1
+    for n in seq:
+        out *= int(n)
+    return out
+
+
+def TensorDot(a: Node, b: Node, dimsfa, dimsfb, contfa, contfb, permute=None) -> Node:
+    lay = TensorDotLayout(dimsfa, dimsfb, contfa, contfb, permute)
+    if a.dim != _prod(lay.dimsfa) or b.dim != _prod(lay.dimsfb):
+        raise FormulaError("TensorDot: operand dimensions %d, %d do not match the shapes %s, %s"
+                           % (a.dim, b.dim, lay.dimsfa, lay.dimsfb))
+    if a.is_zero or b.is_zero:
+        return Zero(lay.dim)
+    return Node("TensorDot", (a, b), lay.params(), lay.dim)
+
+
+def Kron(a: Node, b: Node, dimsfa, dimsfb) -> Node:
+    """``numpy.kron`` of two tensors with the same number of axes = an outer product whose axes are interleaved
+    (``maths/Kron.py:17-31``)."""
+    if len(dimsfa) != len(dimsfb):
+        raise FormulaError("Kron: the two operands must have the same number of axes")
+    n = len(dimsfa)
+    return TensorDot(a, b, dimsfa, dimsfb, (), (), list(range(0, 2 * n, 2)) + list(range(1, 2 * n, 2)))
+
+
 # names visible to the formula parser -------------------------------------------------------
 PUBLIC_OPS = {
     name: obj
     for name, obj in list(globals().items())
     if callable(obj) and name[0].isupper() and name not in ("Node", "FormulaError", "Fraction")
 }
-for _hidden in ("Broadcast", "Dict", "Iterable", "List", "Optional", "Tuple"):
+for _hidden in ("Broadcast", "Dict", "Iterable", "List", "Optional", "Tuple", "TensorDotLayout"):
     PUBLIC_OPS.pop(_hidden, None)

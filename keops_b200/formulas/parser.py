@@ -68,6 +68,21 @@ class _Interp(ast.NodeVisitor):
             return node.value
         raise FormulaError("unsupported constant in formula: %r" % (node.value,))
 
+    def visit_List(self, node):
+        # integer sequences: the shape / axis arguments of TensorDot and Kron, ``[2,3]`` (``lazy_tensor.py:1834-1849``)
+        out = []
+        for e in node.elts:
+            v = self.visit(e)
+            if isinstance(v, Node):
+                c = v.const_value()
+                v = int(c) if c is not None and c.denominator == 1 else v
+            if not isinstance(v, int):
+                raise FormulaError("only integers are allowed in a [...] argument")
+            out.append(v)
+        return tuple(out)
+
+    visit_Tuple = visit_List
+
     def visit_Name(self, node):
         if node.id in self.names:
             return self.names[node.id]
@@ -155,7 +170,7 @@ class _Interp(ast.NodeVisitor):
     _N_FORMULA_ARGS = {
         "Var": 0, "Zero": 0, "IntCst": 0, "RatCst": 0, "IntInv": 0, "FloatCst": 0,
         "Pow": 1, "Round": 1, "SumT": 1, "Extract": 1, "ExtractT": 1, "Elem": 1, "ElemT": 1,
-        "OneHot": 1, "ClampInt": 1, "DiffClampInt": 1,
+        "OneHot": 1, "ClampInt": 1, "DiffClampInt": 1, "TensorDot": 2, "Kron": 2,
     }
 
     def _call_op(self, name, fn, args):
@@ -170,6 +185,8 @@ class _Interp(ast.NodeVisitor):
                     if c is None or c.denominator != 1:
                         raise FormulaError("parameter of %s must be an integer" % name)
                     p = int(c)
+                if name in ("TensorDot", "Kron") and isinstance(p, int):
+                    p = (p,)
                 conv.append(p)
         try:
             return fn(*conv)

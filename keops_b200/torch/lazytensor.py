@@ -462,6 +462,28 @@ class LazyTensor:
         other = self._wrap(other)
         return self.binary(other, "TensorProd", dimres=self.ndim * other.ndim, dimcheck=None)
 
+    def keops_tensordot(self, other, dimfa, dimfb, contfa, contfb, *args):
+        """Tensor contraction over paired axes of the internal dimension, viewed as row-major tensors of shapes ``dimfa``
+        and ``dimfb``; an optional last argument permutes the kept axes (``lazy_tensor.py:1816-1849``)."""
+        def seq(v):
+            return "[" + ",".join(str(int(k)) for k in ((v,) if isinstance(v, int) else v)) + "]"
+        opt_arg = ", ".join(seq(v) for v in (dimfa, dimfb, contfa, contfb) + args)
+        da, db = [int(k) for k in dimfa], [int(k) for k in dimfb]
+        dimres = 1
+        for k in da + db:
+            dimres *= k
+        for c in ((contfa,) if isinstance(contfa, int) else contfa):
+            dimres //= da[int(c)] ** 2
+        return self.binary(other, "TensorDot", dimres=dimres, dimcheck=None, opt_arg=opt_arg)
+
+    def keops_kron(self, other, dimfself, dimfother):
+        """Kronecker product (``numpy.kron``) of the internal dimensions viewed as tensors of shapes ``dimfself`` and
+        ``dimfother`` with the same number of axes (``lazy_tensor.py:1851-1907``, ``maths/Kron.py``)."""
+        if isinstance(dimfself, int) or isinstance(dimfother, int):
+            raise ValueError("For keops_Kronecker, dimfself and dimfother must be tuple/list of int")
+        opt_arg = ", ".join("[" + ",".join(str(int(k)) for k in v) + "]" for v in (dimfself, dimfother))
+        return self.binary(other, "Kron", dimres=self.ndim * self._wrap(other).ndim, dimcheck=None, opt_arg=opt_arg)
+
     # ------------------------------------------------------------------------------------------
     # reductions
     # ------------------------------------------------------------------------------------------

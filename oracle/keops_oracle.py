@@ -723,6 +723,58 @@ class VecMatMult(Op):
         return A.difft(v, TensorProd(b, g)) + b.difft(v, MatVecMult(A, g))
 
 
+class TensorDot(Op):
+    """``maths/TensorDot.py``: contraction of two flat row-major tensors over paired axes.  The reference's loop nest
+    (``:155-187``) runs over the kept axes of ``a``, then of ``b`` (outer), then the contracted axes (inner) and does
+    ``out[o] += a[ia] * b[ib]``; kept axis number ``t`` (in that order) lands on axis ``permute[t]`` of the output."""
+    def __init__(self, a, b, dimsfa, dimsfb, contfa, contfb, permute=None):
+        self.children = (a, b)
+        self.da, self.db = [int(d) for d in dimsfa], [int(d) for d in dimsfb]
+        self.ca, self.cb = [int(c) for c in contfa], [int(c) for c in contfb]
+        assert a.dim == int(np.prod(self.da, dtype=np.int64)) and b.dim == int(np.prod(self.db, dtype=np.int64))
+        assert [self.da[c] for c in self.ca] == [self.db[c] for c in self.cb]
+        self.ka = [k for k in range(len(self.da)) if k not in self.ca]
+        self.kb = [k for k in range(len(self.db)) if k not in self.cb]
+        kept = [self.da[k] for k in self.ka] + [self.db[k] for k in self.kb]
+        self.perm = list(range(len(kept))) if permute is None else [int(q) for q in permute]
+        assert sorted(self.perm) == list(range(len(kept)))
+        self.oshape = [kept[self.perm.index(q)] for q in range(len(kept))]
+        self.dim = int(np.prod(kept, dtype=np.int64))
+        # flat index tables over the loop nest (kept..., contracted...)
+        loop = kept + [self.da[c] for c in self.ca]
+        grid = np.indices(loop).reshape(len(loop), -1) if loop else np.zeros((0, 1), dtype=np.int64)
+        nka, nk = len(self.ka), len(kept)
+        ia = [None] * len(self.da)
+        for t, ax in enumerate(self.ka): ia[ax] = grid[t]
+        for c, ax in enumerate(self.ca): ia[ax] = grid[nk + c]
+        ib = [None] * len(self.db)
+        for t, ax in enumerate(self.kb): ib[ax] = grid[nka + t]
+        for c, ax in enumerate(self.cb): ib[ax] = grid[nk + c]
+        io = [grid[self.perm.index(q)] for q in range(nk)]
+        flat = lambda idx, shape: np.ravel_multi_index(idx, shape) if shape else np.zeros(grid.shape[1], dtype=np.int64)
+        self.ia, self.ib, self.io = flat(ia, self.da), flat(ib, self.db), flat(io, self.oshape)
+    def ev(self, env):
+        a, b = [c.ev(env) for c in self.children]
+        lead = np.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+        out = np.zeros(lead + (self.dim,), dtype=env.dtype)
+        for o, i, j in zip(self.io, self.ia, self.ib):                           # the reference's order of additions
+            out[..., o] += a[..., i] * b[..., j]
+        return out
+    def difft(self, v, g):
+        a, b = self.children                                                     # TensorDot.py:105-139,189-216
+        nka = len(self.ka)
+        order = lambda keys: sorted(range(len(keys)), key=keys.__getitem__)
+        back_a = [self.ka[t] for t in order(self.perm[:nka])] + [self.ca[c] for c in order(self.cb)]
+        back_b = [self.kb[t] for t in order(self.perm[nka:])] + [self.cb[c] for c in order(self.ca)]
+        return a.difft(v, TensorDot(g, b, self.oshape, self.db, self.perm[nka:], self.kb, back_a)) + \
+            b.difft(v, TensorDot(g, a, self.oshape, self.da, self.perm[:nka], self.ka, back_b))
+
+
+def Kron(a, b, dimsfa, dimsfb):                                                  # maths/Kron.py:17-31
+    n = len(dimsfa)
+    return TensorDot(a, b, dimsfa, dimsfb, [], [], list(range(0, 2 * n, 2)) + list(range(1, 2 * n, 2)))
+
+
 def Elem(a, m): return Extract(a, m, 1)
 def ElemT(a, n, m): return ExtractT(a, m, n)
 def SqNorm2(a): return Sum(Square(a))                                            # maths/SqNorm2.py

@@ -204,6 +204,28 @@ case("ties_argkmin", "ArgKMin_Reduction(Sum(Square((Var(0,3,0) - Var(1,3,1)))),7
 case("ties_kmin_argkmin", "KMin_ArgKMin_Reduction(Sum(Abs((Var(0,3,0) - Var(1,3,1)))),5,1)", TI, sizes=(120, 90))
 
 
+# ---- tensor contractions on the internal dimension (maths/TensorDot.py, maths/Kron.py): the matrix-vector special case of
+# test_lazytensor_tensordot.py, the permuted 3-axis contraction of test_torch.py:680-730, the Kronecker products of test_kron.py
+TD = {
+    "matvec": ("TensorDot(x,y,[4,7],[7],[1],[0])", 28, 7),
+    "matmat_w": ("TensorDot(x,y,[2,3],[3,2],[1],[0])*Exp(-SqDist(Extract(x,0,3),Extract(y,0,3)))", 6, 6),
+    "permute": ("TensorDot(x,y,[2,3,2,2,4],[2,4,2,3,2,3],[4,0,2],[1,4,2],[4,3,2,0,1])", 96, 288),
+    "outer_perm": ("TensorDot(x,y,[2,3],[2,2],[],[],[0,2,1,3])", 6, 4),
+    "kron2": ("Kron(x,y,[2,3],[2,2])", 6, 4),
+    "kron3": ("Kron(x,y,[2,3,2],[2,2,3])", 12, 12),
+    "full": ("TensorDot(x,y,[3,4],[4,3],[0,1],[1,0])*x", 12, 12),
+}
+for nm, (f, dx, dy) in TD.items():
+    ali = ["x=Vi(0,%d)" % dx, "y=Vj(1,%d)" % dy]
+    red = "Sum_Reduction(%s,0)" % f
+    case("td_" + nm, red, [(dx, 0, "n"), (dy, 1, "n")], aliases=ali, sizes=(23, 31))
+    if nm in ("matmat_w", "permute", "kron2", "full"):
+        for vname, vstr in (("x", V(0, dx, 0)), ("y", V(1, dy, 1))):
+            case("td_grad_%s_%s" % (nm, vname), "Grad_WithSavedForward(%s,%s,%s,%s)" % (red, vstr, "Var(2,DIMOUT,0)", "Var(3,DIMOUT,0)"),
+                 [(dx, 0, "n"), (dy, 1, "n"), ("eta", 0, red, 2), ("fwd", 0, red, 2)], dtypes=("float64",),
+                 aliases=ali + ["Var(2,DIMOUT,0)", "Var(3,DIMOUT,0)"], sizes=(23, 31))
+
+
 def flags(formula):
     head = formula.split("(")[0]
     sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
@@ -230,7 +252,7 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
-        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_")):
+        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_", "td_")):
             import zlib
             rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])

@@ -289,3 +289,57 @@ def test_prescale_does_not_apply_to_other_formulas():
               "Sum_Reduction(Exp(-SqDist(Var(0,16,0),Var(1,16,1)))*Var(2,1,1),0)",               # dimension > 8
               "ArgKMin_Reduction(SqDist(Var(0,3,0),Var(1,3,1)),3,0)"):
         assert lower_reduction(parse_reduction(f), True, prescale=True) is None, f
+
+
+@pytest.mark.parametrize("da,db,ca,cb,perm", [
+    ((4, 7), (7,), (1,), (0,), None),
+    ((2, 3, 2, 2, 4), (2, 4, 2, 3, 2, 3), (4, 0, 2), (1, 4, 2), (4, 3, 2, 0, 1)),
+    ((2, 3), (2, 2), (), (), (0, 2, 1, 3)),
+    ((3, 4), (4, 3), (0, 1), (1, 0), None),
+    ((), (4, 3), (), (), (1, 0)),
+])
+def test_tensordot_layout_and_adjoints_against_numpy(da, db, ca, cb, perm):
+    """``TensorDot`` index bookkeeping (keopscore/keopscore/formulas/maths/TensorDot.py:56-139): values against
+    ``numpy.tensordot`` + transposition, adjoint parameters against the explicit sums they must reproduce."""
+    from keops_b200.formulas import ir
+    rng = np.random.default_rng(3)
+    lay = ir.TensorDotLayout(da, db, ca, cb, perm)
+
+    def ev(lay, a, b):
+        out = np.zeros(lay.dim)
+        for o, prods in lay.terms():
+            out[o] = sum(a[i] * b[j] for i, j in prods)
+        return out
+
+    a, b = rng.standard_normal(int(np.prod(da))), rng.standard_normal(int(np.prod(db)))
+    nat = np.tensordot(a.reshape(da), b.reshape(db), axes=(list(ca), list(cb)))
+    ref = nat.transpose(np.argsort(lay.permute)) if nat.ndim else nat
+    assert list(ref.shape) == lay.out_shape
+    np.testing.assert_allclose(ev(lay, a, b), ref.ravel(), rtol=1e-13, atol=1e-13)
+    g = rng.standard_normal(lay.dim)
+    ga, gb = np.zeros_like(a), np.zeros_like(b)
+    for o, prods in lay.terms():
+        for i, j in prods:
+            ga[i] += g[o] * b[j]
+            gb[j] += g[o] * a[i]
+    np.testing.assert_allclose(ev(ir.TensorDotLayout(*lay.adjoint(0)), g, b), ga, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(ev(ir.TensorDotLayout(*lay.adjoint(1)), g, a), gb, rtol=1e-13, atol=1e-13)
+
+
+def test_tensordot_parsing_and_errors():
+    from keops_b200.formulas import ir
+    from keops_b200.formulas.parser import parse_formula, FormulaError
+    al = ["x=Vi(0,6)", "y=Vj(1,4)"]
+    f = parse_formula("TensorDot(x, y, [2, 3], [2, 2], [], [], [0, 2, 1, 3])", al)
+    assert f is parse_formula("Kron(x, y, [2,3], [2,2])", al) and f.dim == 24
+    assert parse_formula(repr(f)) is f                               # the printed form parses back to the same node
+    assert parse_formula("TensorDot(x, y, (2, 3), (2, 2), (0,), (1,))", al).dim == 6          # tuples as well as lists
+    assert parse_formula("TensorDot(x, Zero(4), [2,3], [2,2], [], [])", al).is_zero
+    for bad in ("TensorDot(x, y, [2, 3], [2, 2], [1], [0])",           # contracted sizes differ (3 vs 2)
+                "TensorDot(x, y, [2, 2], [2, 2], [], [])",             # shape does not match the operand dimension
+                "TensorDot(x, y, [2, 3], [2, 2], [], [], [0, 1, 2, 2])",   # not a permutation
+                "TensorDot(x, y, [2, 3], [2, 2], [0], [0, 1])",        # unpaired axes
+                "Kron(x, y, [2, 3], [4])",                             # different numbers of axes
+                "TensorDot(x, y, [2, 3.5], [2, 2], [], [])"):
+        with pytest.raises(FormulaError):
+            parse_formula(bad, al)

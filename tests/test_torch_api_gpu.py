@@ -486,3 +486,53 @@ def test_accumulator_options(api, cuda_device):
             assert e2 < 2e-6, (name, e2)
     out = api.Genred("Exp(-SqDist(x,y))*b", al, reduction_op="Sum", axis=1, sum_scheme="kahan_scheme", dtype_acc="float64")(x, y, b)
     assert ((out.double() - ref).abs() / ref.abs()).max().item() < 1e-6
+
+
+def test_tensordot_with_permute_and_gradients(api, cuda_device):
+    # test_torch.py:680-730 (contraction over three paired axes, permuted kept axes, both gradients) and
+    # test_lazytensor_tensordot.py (matrix-vector product as a contraction)
+    import numpy as np
+    torch.manual_seed(0)
+    M, N = 40, 50
+    x = torch.randn(M, 2, 3, 2, 2, 4, dtype=torch.float64, device=cuda_device, requires_grad=True)
+    y = torch.randn(N, 2, 4, 2, 3, 2, 3, dtype=torch.float64, device=cuda_device, requires_grad=True)
+    dimfa, dimfb = tuple(x.shape[1:]), tuple(y.shape[1:])
+    contfa, contfb = [5, 1, 3], [2, 5, 3]
+    perm = [4, 3, 2, 0, 1]
+    perm_torch = (0,) + tuple(int(i) + 1 for i in np.argsort(perm))
+    ref = torch.tensordot(x, y, dims=(contfa, contfb)).sum(3).permute(perm_torch)
+    f = api.LazyTensor(x.reshape(M, 1, -1)).keops_tensordot(
+        api.LazyTensor(y.reshape(1, N, -1)), dimfa, dimfb, tuple(c - 1 for c in contfa), tuple(c - 1 for c in contfb),
+        tuple(perm))
+    out = f.sum_reduction(dim=1)
+    assert out.shape == (M, 108)
+    assert torch.allclose(out.flatten(), ref.flatten(), rtol=1e-10, atol=1e-10)
+    e = torch.randn_like(ref)
+    for v in (x, y):
+        gk = torch.autograd.grad(out, v, e.reshape(M, -1), retain_graph=True)[0]
+        gt = torch.autograd.grad(ref, v, e, retain_graph=True)[0]
+        assert torch.allclose(gk.flatten(), gt.flatten(), rtol=1e-9, atol=1e-9)
+    a = torch.randn(4 * 7, dtype=torch.float64, device=cuda_device)
+    b = torch.randn(7, dtype=torch.float64, device=cuda_device)
+    C = api.LazyTensor(a[None, None, :]).keops_tensordot(api.LazyTensor(b[None, None, :]), (4, 7), (7,), (1,), (0,)).sum_reduction(dim=1)
+    assert torch.allclose(C.flatten(), a.reshape(4, 7) @ b)
+
+
+def test_kron(api, cuda_device):
+    # test_kron.py: numpy.kron of the internal dimensions, through the LazyTensor method and through both Genred spellings
+    torch.manual_seed(1)
+    M, N = 11, 150
+    for dimfa, dimfb in (([2, 3], [2, 2]), ([3, 1, 3, 2], [3, 3, 2, 1])):
+        da, db = math.prod(dimfa), math.prod(dimfb)
+        x = torch.rand(M, da, device=cuda_device)
+        y = torch.rand(N, db, device=cuda_device)
+        ref = torch.stack([sum(torch.kron(x[i].reshape(dimfa), y[j].reshape(dimfb)).flatten() for j in range(N))
+                           for i in range(M)])
+        out = api.LazyTensor(x[:, None, :]).keops_kron(api.LazyTensor(y[None, :, :]), dimfa, dimfb).sum(axis=1)
+        assert out.shape == (M, da * db)
+        assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+    al = ["x=Vi(0,6)", "y=Vj(1,4)"]
+    x, y = torch.rand(M, 6, device=cuda_device), torch.rand(N, 4, device=cuda_device)
+    o1 = api.Genred("Kron(x, y, [2, 3], [2, 2])", al, reduction_op="Sum", axis=1)(x, y)
+    o2 = api.Genred("TensorDot(x, y, [2, 3], [2, 2], [], [], [0, 2, 1, 3])", al, reduction_op="Sum", axis=1)(x, y)
+    assert torch.equal(o1, o2)
