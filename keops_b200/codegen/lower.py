@@ -170,6 +170,31 @@ class Lowerer:
         if op == "TensorProd":
             a, b = L(n.args[0]), L(n.args[1])
             return [g.mul(x, y) for x in a for y in b]
+        if op == "BSpline":
+            # de Boor's recursion, in place on knots.dim - 1 values; the first knots.dim - order - 1 are the result
+            # (maths/BSpline.py:44-95).  omega(i, k) = (x - t_i) / (t_{i+k} - t_i), 0 on an empty knot span.
+            t, x = L(n.args[0]), L(n.args[1])[0]
+            (order,) = n.params
+            half, zero, one = g.const(0.5), g.const(0.0), g.const(1.0)
+
+            def omega(i, k):
+                nonempty = g.sub(g.fn2("lt", t[i], t[i + k]), half)
+                return g.select_ge0(nonempty, g.div(g.sub(x, t[i]), g.sub(t[i + k], t[i])), zero)
+
+            out = [g.mul(g.fn2("le", t[j], x), g.fn2("lt", x, t[j + 1])) for j in range(len(t) - 1)]
+            for k in range(1, order + 1):
+                w1 = omega(0, k)
+                for i in range(len(out) - k):
+                    w2 = omega(i + 1, k)
+                    out[i] = g.add(g.mul(w1, out[i]), g.mul(g.sub(one, w2), out[i + 1]))
+                    w1 = w2
+            return out[:n.dim]
+        if op in ("SoftDTW_SqDist", "GradSoftDTW_SqDist"):
+            x, y, gam = L(n.args[0]), L(n.args[1]), L(n.args[2])[0]
+            r = _softdtw_table(g, x, y, gam)
+            if op == "SoftDTW_SqDist":
+                return [r[len(x) - 1][len(y) - 1]]
+            return _softdtw_gradient(g, x, y, gam, r)
         if op == "TensorDot":
             from ..formulas.ir import TensorDotLayout
             a, b = L(n.args[0]), L(n.args[1])
@@ -182,6 +207,67 @@ class Lowerer:
                 out[o] = acc
             return out
         raise NotImplementedError("operation %s is not supported by the sm_100a code generator" % op)
+
+
+def _softdtw_table(g: Graph, x: List[SV], y: List[SV], gam: SV) -> List[List[SV]]:
+    """``r[i][j]``: soft-DTW value of the prefixes ``x[:i+1]``, ``y[:j+1]`` -- the recursion, the operand order of the
+    three-term soft-min and its shift by the hard minimum follow ``maths/SoftDTW_SqDist.py:33-93`` (which keeps one column
+    in registers; the values are the same)."""
+    n, m = len(x), len(y)
+
+    def cost(i, j):
+        return g.square(g.sub(x[i], y[j]))
+
+    r = [[None] * m for _ in range(n)]
+    r[0][0] = cost(0, 0)
+    for i in range(1, n):
+        r[i][0] = g.add(cost(i, 0), r[i - 1][0])
+    for j in range(1, m):
+        r[0][j] = g.add(cost(0, j), r[0][j - 1])
+        for i in range(1, n):
+            diag, left, up = r[i - 1][j - 1], r[i][j - 1], r[i - 1][j]
+            lo = g.fn2("fmin", g.fn2("fmin", diag, left), up)
+            s = g.add(g.add(g.exp(g.div(g.sub(lo, diag), gam)), g.exp(g.div(g.sub(lo, up), gam))),
+                      g.exp(g.div(g.sub(lo, left), gam)))
+            r[i][j] = g.add(cost(i, j), g.sub(lo, g.mul(gam, g.log(s))))
+    return r
+
+
+def _softdtw_gradient(g: Graph, x: List[SV], y: List[SV], gam: SV, r: List[List[SV]]) -> List[SV]:
+    """Backward sweep over the alignment matrix: ``e[i][j]`` = d r[n-1][m-1] / d r[i][j]``, then the chain rule through the
+    ground costs (``maths/SoftDTW_SqDist.py:159-211``); accumulation orders as there (columns from the last to the first,
+    rows from the last to the first inside a column)."""
+    n, m = len(x), len(y)
+    two = g.const(2.0)
+
+    def diff(i, j):
+        return g.sub(x[i], y[j])
+
+    def weight(i1, j1, i, j):
+        # exp((r[i1][j1] - r[i][j] - cost(i1, j1)) / gamma): share of (i, j) in the soft-min that produced r[i1][j1]
+        return g.exp(g.div(g.sub(g.sub(r[i1][j1], r[i][j]), g.square(diff(i1, j1))), gam))
+
+    e = [[None] * m for _ in range(n)]
+    gx, gy = [None] * n, [None] * m
+
+    def emit(i, j):
+        t = g.mul(g.mul(two, diff(i, j)), e[i][j])
+        gx[i] = t if gx[i] is None else g.add(gx[i], t)
+        gy[j] = -t if gy[j] is None else g.sub(gy[j], t)
+
+    e[n - 1][m - 1] = g.const(1.0)
+    emit(n - 1, m - 1)
+    for i in range(n - 2, -1, -1):
+        e[i][m - 1] = g.mul(weight(i + 1, m - 1, i, m - 1), e[i + 1][m - 1])
+        emit(i, m - 1)
+    for j in range(m - 2, -1, -1):
+        e[n - 1][j] = g.mul(weight(n - 1, j + 1, n - 1, j), e[n - 1][j + 1])
+        emit(n - 1, j)
+        for i in range(n - 2, -1, -1):
+            a, b, c = weight(i + 1, j, i, j), weight(i, j + 1, i, j), weight(i + 1, j + 1, i, j)
+            e[i][j] = g.add(g.add(g.mul(a, e[i + 1][j]), g.mul(b, e[i][j + 1])), g.mul(c, e[i + 1][j + 1]))
+            emit(i, j)
+    return gx + gy
 
 
 def _pow(g: Graph, x: SV, n: Node) -> SV:

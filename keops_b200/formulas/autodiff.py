@@ -243,6 +243,17 @@ def _rule(f: Node, v: Node, g: Node, memo) -> Node:
     if op == "TensorProd":
         a, b = f.args
         return G(a, ir.MatVecMult(g, b)) + G(b, ir.VecMatMult(a, g))
+    if op == "BSpline":
+        raise NotImplementedError("KeOps BSplines are not yet differentiable. Please consider disabling autograd for the "
+                                  "relevant variables with 'x.detach()'.")       # maths/BSpline.py:97-103
+    if op == "SoftDTW_SqDist":
+        x, y, gamma = f.args
+        if v in gamma.variables():
+            raise FormulaError("autograd wrt gamma in SoftDTW_SqDist operation not implemented.")
+        full = ir.GradSoftDTW_SqDist(x, y, gamma) * g                            # SoftDTW_SqDist.py:95-106
+        return G(x, ir.Extract(full, 0, x.dim)) + G(y, ir.Extract(full, x.dim, y.dim))
+    if op == "GradSoftDTW_SqDist":
+        raise FormulaError("autograd for GradSoftDTW_SqDist operation not implemented.")
     if op == "TensorDot":
         # the adjoint of a contraction is the contraction of the incoming gradient with the other operand over that
         # operand's kept axes, stored back in the layout of the differentiated operand (``maths/TensorDot.py:189-216``)

@@ -677,6 +677,38 @@ def Kron(a: Node, b: Node, dimsfa, dimsfb) -> Node:
     return TensorDot(a, b, dimsfa, dimsfb, (), (), list(range(0, 2 * n, 2)) + list(range(1, 2 * n, 2)))
 
 
+# ------------------------------------------------------------------------------------------
+# soft dynamic time warping between two vectors (``keopscore/keopscore/formulas/maths/SoftDTW_SqDist.py``)
+# ------------------------------------------------------------------------------------------
+def SoftDTW_SqDist(x: Node, y: Node, gamma: Node) -> Node:
+    """Soft-DTW discrepancy (soft-min of smoothness ``gamma`` over all monotone alignments of the entries of ``x`` and
+    ``y``, squared difference as the ground cost) -- a scalar (``SoftDTW_SqDist.py:19-93``)."""
+    if gamma.dim != 1:
+        raise FormulaError("input gamma should be scalar")
+    return Node("SoftDTW_SqDist", (x, y, gamma), (), 1)
+
+
+def GradSoftDTW_SqDist(x: Node, y: Node, gamma: Node) -> Node:
+    """Gradient of :func:`SoftDTW_SqDist` with respect to ``x`` and ``y``, concatenated (``SoftDTW_SqDist.py:109-216``)."""
+    if gamma.dim != 1:
+        raise FormulaError("input gamma should be scalar")
+    return Node("GradSoftDTW_SqDist", (x, y, gamma), (), x.dim + y.dim)
+
+
+def BSpline(knots: Node, x: Node, order: int) -> Node:
+    """The ``knots.dim - order - 1`` B-spline basis functions of the given order on the knot vector ``knots``, sampled at the
+    scalar ``x`` (de Boor's recursion, ``keopscore/keopscore/formulas/maths/BSpline.py:19-126``)."""
+    order = int(order)
+    if order < 0:
+        raise FormulaError("The order of a BSpline must be >= 0, but received %d." % order)
+    if x.dim != 1:
+        raise FormulaError("BSplines must be sampled at scalar values, but received a vector of size %d." % x.dim)
+    if knots.dim < order + 2:
+        raise FormulaError("BSplines of order %d require at least %d knots, but only received a vector of size %d."
+                           % (order, order + 2, knots.dim))
+    return Node("BSpline", (knots, x), (order,), knots.dim - order - 1)
+
+
 # names visible to the formula parser -------------------------------------------------------
 PUBLIC_OPS = {
     name: obj

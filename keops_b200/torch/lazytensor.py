@@ -462,6 +462,20 @@ class LazyTensor:
         other = self._wrap(other)
         return self.binary(other, "TensorProd", dimres=self.ndim * other.ndim, dimcheck=None)
 
+    def bspline(self, x, k=0):
+        """Vector of B-spline basis functions of order ``k`` for the knots ``self``, evaluated at the scalar ``x``
+        (``lazy_tensor.py:1706-1714``)."""
+        x = self._wrap(x)
+        if x.ndim != 1:
+            raise ValueError("Operation BSpline expects a vector and a scalar input (of dimension 1). Received %d and %d."
+                             % (self.ndim, x.ndim))
+        return self.binary(x, "BSpline", dimres=self.ndim - k - 1, dimcheck=None, opt_arg="%d" % k)
+
+    def softdtw_sqdist(self, other, gamma):
+        """Soft-DTW discrepancy between the vectors ``self`` and ``other`` with smoothness ``gamma``, squared difference
+        as the ground cost (``lazy_tensor.py:1599-1612``)."""
+        return self.ternary(other, gamma, "SoftDTW_SqDist", dimres=1)
+
     def keops_tensordot(self, other, dimfa, dimfb, contfa, contfb, *args):
         """Tensor contraction over paired axes of the internal dimension, viewed as row-major tensors of shapes ``dimfa``
         and ``dimfb``; an optional last argument permutes the kept axes (``lazy_tensor.py:1816-1849``)."""

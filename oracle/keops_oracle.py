@@ -775,6 +775,130 @@ def Kron(a, b, dimsfa, dimsfb):                                                 
     return TensorDot(a, b, dimsfa, dimsfb, [], [], list(range(0, 2 * n, 2)) + list(range(1, 2 * n, 2)))
 
 
+def _softdtw_forward(env, x, y, gam):
+    """All prefix values r[j][i] of ``maths/SoftDTW_SqDist.py:33-93`` (same recursion as ``:132-157``), on (M, N) arrays."""
+    n, m = x.shape[-1], y.shape[-1]
+    X = lambda i: x[..., i]
+    Y = lambda j: y[..., j]
+    r = [[None] * n for _ in range(m)]
+    d = X(0) - Y(0)
+    r[0][0] = d * d
+    for i in range(1, n):
+        d = X(i) - Y(0)
+        r[0][i] = d * d + r[0][i - 1]
+    for j in range(1, m):
+        d = X(0) - Y(j)
+        r[j][0] = d * d + r[j - 1][0]
+        for i in range(1, n):
+            d = X(i) - Y(j)
+            a, b, c = r[j - 1][i - 1], r[j - 1][i], r[j][i - 1]
+            # MIN3 goes through fminf, i.e. float32 even for double data; it only shifts the log-sum-exp
+            mn = np.minimum(np.minimum(a.astype(np.float32), b.astype(np.float32)), c.astype(np.float32)).astype(env.dtype)
+            r[j][i] = d * d + (mn - gam * np.log(np.exp((mn - a) / gam) + np.exp((mn - c) / gam) + np.exp((mn - b) / gam)))
+    return r
+
+
+class SoftDTW_SqDist(Op):
+    def __init__(self, x, y, gamma):
+        assert gamma.dim == 1
+        self.children = (x, y, gamma)
+        self.dim = 1
+    def ev(self, env):
+        x, y, gam = [c.ev(env) for c in self.children]
+        r = _softdtw_forward(env, x, y, gam[..., 0])
+        return r[-1][-1][..., None]
+    def difft(self, v, g):
+        x, y, gamma = self.children                                               # SoftDTW_SqDist.py:95-106
+        assert v.ind not in gamma.vars(), "autograd wrt gamma in SoftDTW_SqDist operation not implemented."
+        full = GradSoftDTW_SqDist(x, y, gamma) * g
+        return x.difft(v, Extract(full, 0, x.dim)) + y.difft(v, Extract(full, x.dim, y.dim))
+
+
+class GradSoftDTW_SqDist(Op):
+    def __init__(self, x, y, gamma):
+        self.children = (x, y, gamma)
+        self.dim = x.dim + y.dim
+    def ev(self, env):                                                            # SoftDTW_SqDist.py:124-211
+        x, y, gam = [c.ev(env) for c in self.children]
+        gam = gam[..., 0]
+        n, m = x.shape[-1], y.shape[-1]
+        r = _softdtw_forward(env, x, y, gam)
+        X = lambda i: x[..., i]
+        Y = lambda j: y[..., j]
+        gx, gy = [None] * n, [None] * m
+        ejp1 = [None] * n
+        eij = np.ones(np.broadcast_shapes(x.shape[:-1], y.shape[:-1]), dtype=env.dtype)
+        eip1j = eij
+        d = X(n - 1) - Y(m - 1)
+        gx[n - 1] = 2 * d * eij
+        gy[m - 1] = -2 * d * eij
+        for i in range(n - 2, -1, -1):
+            a = np.exp((r[m - 1][i + 1] - r[m - 1][i] - d * d) / gam)
+            eij = a * eip1j
+            ejp1[i + 1] = eip1j
+            eip1j = eij
+            d = X(i) - Y(m - 1)
+            gx[i] = 2 * d * eij
+            gy[m - 1] = gy[m - 1] - 2 * d * eij
+        ejp1[0] = eij
+        for j in range(m - 2, -1, -1):
+            d = X(n - 1) - Y(j + 1)
+            b = np.exp((r[j + 1][n - 1] - r[j][n - 1] - d * d) / gam)
+            eij = b * ejp1[n - 1]
+            eip1j = eij
+            d = X(n - 1) - Y(j)
+            gx[n - 1] = gx[n - 1] + 2 * d * eij
+            gy[j] = -2 * d * eij
+            for i in range(n - 2, -1, -1):
+                a = np.exp((r[j][i + 1] - r[j][i] - d * d) / gam)
+                d = X(i) - Y(j + 1)
+                b = np.exp((r[j + 1][i] - r[j][i] - d * d) / gam)
+                d = X(i + 1) - Y(j + 1)
+                c = np.exp((r[j + 1][i + 1] - r[j][i] - d * d) / gam)
+                eij = a * eip1j + b * ejp1[i] + c * ejp1[i + 1]
+                ejp1[i + 1] = eip1j
+                eip1j = eij
+                d = X(i) - Y(j)
+                gx[i] = gx[i] + 2 * d * eij
+                gy[j] = gy[j] - 2 * d * eij
+            ejp1[0] = eij
+        shape = np.broadcast_shapes(x.shape[:-1], y.shape[:-1])
+        return np.stack([np.broadcast_to(t, shape) for t in gx + gy], axis=-1).astype(env.dtype)
+    def difft(self, v, g):
+        raise ValueError("autograd for GradSoftDTW_SqDist operation not implemented.")
+
+
+class BSpline(Op):
+    """``maths/BSpline.py:19-126``: one-hot of the knot span containing x, then ``order`` sweeps of
+    ``out[i] = w(i,k) out[i] + (1 - w(i+1,k)) out[i+1]`` with ``w(i,k) = (x - t[i]) / (t[i+k] - t[i])`` (0 if the span is empty);
+    the reference keeps x and the ratios in C ``float`` -- and does not generate at all for double inputs."""
+    def __init__(self, knots, x, order):
+        order = int(order)
+        assert order >= 0 and x.dim == 1 and knots.dim >= order + 2
+        self.children = (knots, x)
+        self.order = order
+        self.dim = knots.dim - order - 1
+    def ev(self, env):
+        t, x = [c.ev(env) for c in self.children]
+        x = x[..., 0]
+        T = lambda i: t[..., i]
+        nb = t.shape[-1] - 1
+        out = [((T(j) <= x) & (x < T(j + 1))).astype(env.dtype) for j in range(nb)]
+        def w(i, k):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                return np.where(T(i) < T(i + k), (x - T(i)) / (T(i + k) - T(i)), env.dtype.type(0)).astype(env.dtype)
+        for k in range(1, self.order + 1):
+            r1 = w(0, k)
+            for i in range(nb - k):
+                r2 = w(i + 1, k)
+                out[i] = r1 * out[i] + (env.dtype.type(1) - r2) * out[i + 1]
+                r1 = r2
+        shape = np.broadcast_shapes(*[o.shape for o in out[:self.dim]])
+        return np.stack([np.broadcast_to(o, shape) for o in out[:self.dim]], axis=-1)
+    def difft(self, v, g):
+        raise NotImplementedError("KeOps BSplines are not yet differentiable.")
+
+
 def Elem(a, m): return Extract(a, m, 1)
 def ElemT(a, n, m): return ExtractT(a, m, n)
 def SqNorm2(a): return Sum(Square(a))                                            # maths/SqNorm2.py

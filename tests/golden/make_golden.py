@@ -226,6 +226,32 @@ for nm, (f, dx, dy) in TD.items():
                  aliases=ali + ["Var(2,DIMOUT,0)", "Var(3,DIMOUT,0)"], sizes=(23, 31))
 
 
+# ---- soft dynamic time warping (maths/SoftDTW_SqDist.py): value and gradients with respect to both series.
+# The operands are expressions (2x, y+y), not bare variables: the reference's CPU backend reads bare variables straight from
+# the argument arrays as ``(arg[0]+i*5)[k]``, and the loop counters ``int i`` / ``int j`` that SoftDTW_SqDist.py:46-75
+# declares shadow the row / column indices in that expression, so on bare variables the CPU reference indexes out of its
+# rows.  Expressions are evaluated into local arrays first, which is also what its CUDA backend does for every variable.
+XS, YS = "(IntCst(2)*x)", "(y+y)"
+SDTW = "Sum_Reduction(SoftDTW_SqDist(%s,%s,g)*b,0)" % (XS, YS)
+SDTW_ALI = ["x=Vi(0,5)", "y=Vj(1,4)", "g=Pm(2,1)", "b=Vj(3,1)"]
+SDTW_ARGS = [(5, 0, "n"), (4, 1, "n"), (1, 2, "p"), (1, 1, "p")]
+case("sdtw_value", SDTW, SDTW_ARGS, aliases=SDTW_ALI, sizes=(23, 31))
+case("sdtw_series_of_1", "Sum_Reduction(SoftDTW_SqDist(%s,Elem(%s,0),g)+SoftDTW_SqDist(Elem(%s,1),%s,g),0)" % (XS, YS, XS, YS),
+     SDTW_ARGS[:3], aliases=SDTW_ALI[:3], sizes=(23, 31))
+for vname, vstr in (("x", V(0, 5, 0)), ("y", V(1, 4, 1)), ("b", V(3, 1, 1))):
+    case("sdtw_grad_" + vname, "Grad_WithSavedForward(%s,%s,Var(4,1,0),Var(5,1,0))" % (SDTW, vstr),
+         SDTW_ARGS + [("eta", 0, SDTW, 4), ("fwd", 0, SDTW, 4)], dtypes=("float64",),
+         aliases=SDTW_ALI + ["Var(4,1,0)", "Var(5,1,0)"], sizes=(23, 31))
+
+
+# ---- B-spline basis functions (maths/BSpline.py): float32 only -- the reference's generator refuses double inputs (its
+# ratios are C floats, "subtraction of two c_variable is only possible with same dtype"); one knot is repeated (empty span)
+for order in (0, 1, 3):
+    case("bspline_order%d" % order, "Sum_Reduction(BSpline(t,x-y,%d)*b,0)" % order,
+         [(8, 2, "knots"), (1, 0, "u"), (1, 1, "u"), (1, 1, "p")], dtypes=("float32",),
+         aliases=["t=Pm(0,8)", "x=Vi(1,1)", "y=Vj(2,1)", "b=Vj(3,1)"], sizes=(23, 31))
+
+
 def flags(formula):
     head = formula.split("(")[0]
     sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
@@ -252,7 +278,7 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
-        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_", "td_")):
+        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_", "td_", "sdtw_", "bspline_")):
             import zlib
             rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])
@@ -282,6 +308,9 @@ def main():
                 a = 0.5 + 1.5 * rng.random(shape)
             elif kind == "eps":
                 a = np.full(shape, 0.05)
+            elif kind == "knots":
+                a = np.sort(rng.random(shape) * 2.2 - 1.1)      # covers the range of x - y; one empty span
+                a[..., 3] = a[..., 2]
             elif kind == "i":
                 a = rng.integers(0, 3, shape).astype(np.float64)
             args.append(a.astype(dt))

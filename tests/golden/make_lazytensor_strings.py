@@ -45,6 +45,7 @@ EXPRS = {
     "laplacian": "(-x.sqdist(y)).exp().laplacian(x)",
     # (grad_matrix is left out: the reference's method formats the LazyTensor object itself into the string,
     #  lazy_tensor.py:2001-2005, so there is no valid reference string to compare with)
+    "bspline_softdtw": "A.bspline(s, 2).sum(-1) + A.bspline(b).sum(-1) + x.softdtw_sqdist(y, p) + A.softdtw_sqdist(x, 0.5)",
     "tensordot": "A.keops_tensordot(x, (3, 3), (3,), (1,), (0,)).sum(-1) + x.keops_tensordot(y, (3,), (3,), (), (), (1, 0)).sum(-1)",
     "kron": "A.keops_kron(x.tensorprod(y), [3, 3], [3, 3]).sum(-1) + x.keops_kron(y, (3,), (3,)).sum(-1)",
     "factorize": "((-x.sqdist(y)).exp() + (-x.sqdist(y)).exp() * b).factorize((-x.sqdist(y)).exp())",

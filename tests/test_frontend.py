@@ -343,3 +343,43 @@ def test_tensordot_parsing_and_errors():
                 "TensorDot(x, y, [2, 3.5], [2, 2], [], [])"):
         with pytest.raises(FormulaError):
             parse_formula(bad, al)
+
+
+def test_bspline_and_softdtw_rules():
+    """B-splines: partition of unity inside the knot range, argument checks, no derivative (maths/BSpline.py:24-41,97-103).
+    Soft-DTW: small-gamma limit = hard DTW by dynamic programming; no derivative with respect to gamma
+    (maths/SoftDTW_SqDist.py:95-101)."""
+    from keops_b200.formulas import autodiff, ir
+    from keops_b200.formulas.parser import parse_formula, FormulaError
+    rng = np.random.default_rng(11)
+    t = np.sort(rng.random(9))
+    x = (t[3] + (t[5] - t[3]) * rng.random((40, 1)))
+    for order in (0, 1, 2, 3):
+        got = dag_eval.evaluate("Sum_Reduction(BSpline(Var(0,9,2),Var(1,1,0),%d),0)" % order, [], [t, x], "float64", sizes=(40, 1))
+        assert got.shape == (40, 9 - order - 1)
+        np.testing.assert_allclose(got.sum(1), 1.0, rtol=1e-12)
+        assert (got >= 0).all()
+    al = ["t=Pm(0,5)", "x=Vi(1,1)", "v=Vi(2,3)"]
+    for bad in ("BSpline(t,x,-1)", "BSpline(t,v,1)", "BSpline(t,x,4)"):
+        with pytest.raises(FormulaError):
+            parse_formula(bad, al)
+    with pytest.raises(NotImplementedError):
+        autodiff.grad(parse_formula("BSpline(t,x,2)", al), ir.Var(1, 1, 0), ir.Var(3, 2, 0))
+
+    a, b = rng.standard_normal((6, 5)), rng.standard_normal((7, 4))
+    got = dag_eval.evaluate("Min_Reduction(SoftDTW_SqDist(Var(0,5,0),Var(1,4,1),Var(2,1,2)),0)", [], [a, b, np.array([1e-3])], "float64")
+    for i in range(6):
+        best = np.inf
+        for j in range(7):
+            r = np.full((6, 5), np.inf)
+            r[0, 0] = 0.0
+            for p in range(1, 6):
+                for q in range(1, 5):
+                    r[p, q] = (a[i, p - 1] - b[j, q - 1]) ** 2 + min(r[p - 1, q - 1], r[p - 1, q], r[p, q - 1])
+            best = min(best, r[5, 4])
+        assert abs(got[i, 0] - best) < 5e-3 * (1 + best)
+    f = parse_formula("SoftDTW_SqDist(Var(0,5,0),Var(1,4,1),Var(2,1,2))")
+    with pytest.raises(FormulaError):
+        autodiff.grad(f, ir.Var(2, 1, 2), ir.Var(3, 1, 0))
+    with pytest.raises(FormulaError):
+        autodiff.grad(autodiff.grad(f, ir.Var(0, 5, 0), ir.Var(3, 1, 0)), ir.Var(1, 4, 1), ir.Var(4, 5, 0))
