@@ -22,11 +22,21 @@ REFERENCE = "/root/reference"
 TARGET = os.path.join(HERE, "_ref")
 
 
+def stage_core_tests():
+    """``keopscore/setup.py`` does not list ``keopscore.test`` among its packages, so the wheel leaves out the reference's
+    per-operation harness (``keopscore/keopscore/test/test_op.py``); copy it next to the installed package, unmodified."""
+    src = os.path.join(REFERENCE, "keopscore", "keopscore", "test")
+    dst = os.path.join(TARGET, "keopscore", "test")
+    if os.path.isdir(src) and os.path.isdir(os.path.join(TARGET, "keopscore")) and not os.path.isdir(dst):
+        shutil.copytree(src, dst, ignore=shutil.ignore_patterns("__pycache__"))
+
+
 def main():
     if not os.path.isdir(REFERENCE):
         print("stage_ref: %s is not mounted; keeping the existing baseline/_ref" % REFERENCE)
         return 0
     if os.path.exists(os.path.join(TARGET, "pykeops", "keops_version")) and "--force" not in sys.argv:
+        stage_core_tests()
         print("stage_ref: baseline/_ref already staged (use --force to redo)")
         return 0
     tmp = tempfile.mkdtemp(prefix="kb200_refsrc_")
@@ -40,6 +50,7 @@ def main():
         subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+    stage_core_tests()
     for root, dirs, _ in os.walk(TARGET):
         for d in dirs:
             if d == "__pycache__":

@@ -197,6 +197,11 @@ class Graph:
         p, q = n.args
         for a, other in ((p, q), (q, p)):
             if max(a.cls, w.cls) < n.cls and (self.fast or (a.op == "const" and w.op == "const")):
+                if join_cls(a.cls, w.cls) >= n.cls and other.cls < n.cls:
+                    # a row-side and a streamed-side factor: their product is per-pair like ``n`` itself, nothing is gained,
+                    # and ``other`` would qualify for the mirror-image move next -- (a*w)*other <-> (a*other)*w without end
+                    # (d/dv of u/v with u row-indexed and v streamed).  Try the other factor: other*w does leave the loop.
+                    continue
                 return self.mul(self.mul(SV(a), SV(w)), SV(other))
         if not self.fast:
             return None

@@ -383,3 +383,22 @@ def test_bspline_and_softdtw_rules():
         autodiff.grad(f, ir.Var(2, 1, 2), ir.Var(3, 1, 0))
     with pytest.raises(FormulaError):
         autodiff.grad(autodiff.grad(f, ir.Var(0, 5, 0), ir.Var(3, 1, 0)), ir.Var(1, 4, 1), ir.Var(4, 5, 0))
+
+
+def test_product_regrouping_terminates_with_one_row_side_and_two_streamed_factors():
+    """(a_i * o_j) * w_j: the streamed factors meet (o_j * w_j leaves the pair loop); moving w_j onto a_i gains nothing and
+    used to ping-pong with the mirror-image move without end -- found by the reference's own per-operation harness
+    (keopscore/keopscore/test/test_op.py) on d/dv of ``Divide(u_i, v_j)`` and on the bounds of ``Clamp``."""
+    from keops_b200.codegen.scalar import Graph, I, J, IJ
+    g = Graph(fast=True)
+    a, w, o = g.load(0, 0, 0), g.load(1, 0, 1), g.load(2, 0, 1)
+    r = g.mul(g.mul(a, o), w)
+    assert r.n.cls == IJ and sorted(x.cls for x in r.n.args) == [I, J]
+    g = Graph(fast=True)
+    a, w, o = g.load(0, 0, 1), g.load(1, 0, 0), g.load(2, 0, 0)
+    r = g.mul(g.mul(a, o), w)
+    assert r.n.cls == IJ and sorted(x.cls for x in r.n.args) == [I, J]
+    x, y, e = np.random.default_rng(0).random((3, 7, 3)) + 0.5
+    got = dag_eval.evaluate("Grad_WithSavedForward(Sum_Reduction(Divide(Var(0,3,0),Var(1,3,1)),0),Var(1,3,1),Var(2,3,0),Var(3,3,0))",
+                            [], [x, y, e, e], "float64", fast=True)
+    np.testing.assert_allclose(got, -(e[:, None, :] * x[:, None, :] / y[None, :, :] ** 2).sum(0), rtol=1e-12)
