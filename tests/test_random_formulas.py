@@ -2,7 +2,8 @@
 (elementwise maths, vector reductions, scalar products, constants, parameters) are pushed through this package's parser,
 autodiff and lowering (evaluated with tests/dag_eval.py) and through the oracle (oracle/keops_oracle.py, pinned against
 the real reference on 193 fixtures): forward values for Sum / LogSumExp / Min reductions and ``Grad_WithSavedForward``
-gradients with respect to an i-variable, a j-variable and a parameter must agree in float64.  The 193 fixtures cover each
+gradients with respect to an i-variable, two j-variables and a parameter must agree in float64, through the plain and the
+``use_fast_math`` lowering.  The 193 fixtures cover each
 operation on its own; this covers what only shows up in combinations (common-subexpression sharing, sign pull-out, constant
 folding, broadcasting of dimension-1 operands, gradients flowing through several uses of one variable)."""
 import random
@@ -94,19 +95,22 @@ def test_random_formula_forward_and_gradients(seed):
     rng = random.Random(1000 + seed)
     dim, F = (3, vec(rng, 3)) if seed % 2 else (1, sca(rng, 3))
     args = data(seed)
+    # half of the seeds go through the ``use_fast_math`` lowering (products re-associated so that hoistable factors meet,
+    # reciprocal + multiply for divisions: what float32 kernels are generated from); evaluated in float64 both agree to rounding
+    fast = seed % 4 < 2
     for tagI in (0, 1):
         fwd = "Sum_Reduction(%s,%d)" % (F, tagI)
         out = ko.genred(fwd, [], args, "float64", sizes=(7, 9))
-        close(dag_eval.evaluate(fwd, [], args, "float64", sizes=(7, 9)), out, fwd)
+        close(dag_eval.evaluate(fwd, [], args, "float64", fast=fast, sizes=(7, 9)), out, fwd)
         # gradients of the Sum reduction with respect to x_i, y_j and the parameter, upstream gradient eta
         eta = np.random.default_rng(seed + 7).uniform(-1, 1, out.shape)
-        for var in (X, Y, P):
+        for var in (X, Y, P, B):
             g = "Grad_WithSavedForward(%s,%s,Var(4,%d,%d),Var(5,%d,%d))" % (fwd, var, dim, tagI, dim, tagI)
             try:
                 ref = ko.genred(g, [], args + [eta, out], "float64", sizes=(7, 9))
             except ZeroDivisionError:
                 continue
-            close(dag_eval.evaluate(g, [], args + [eta, out], "float64", sizes=(7, 9)), ref, g)
+            close(dag_eval.evaluate(g, [], args + [eta, out], "float64", fast=fast, sizes=(7, 9)), ref, g)
     if dim == 1:
         for red in ("Max_SumShiftExp_Reduction(%s,0)", "Min_Reduction(%s,1)", "Max_ArgMax_Reduction(%s,0)", "KMin_Reduction(%s,3,0)"):
             f = red % F
