@@ -28,7 +28,14 @@ def install_as_pykeops():
     root.__version__ = "2.3+kb200." + __version__
     root.torch = _t
     root.numpy = _n
-    root.clean_pykeops = clean_cache
+    root.clean_pykeops = lambda recompile_jit_binaries=True: (clean_cache(), LoadKeOpsB200.reset())[0]
+    root.verbose = True
+    root.default_device_id = 0
+    root.set_verbose = lambda val: setattr(root, "verbose", val)
+    root.set_build_folder = _set_build_folder
+    root.get_build_folder = _get_build_folder
+    root.check_health = _check_health
+    root.config = types.SimpleNamespace(gpu_available=_cuda_available(), torch_found=True, numpy_found=True)
     root.test_torch_bindings = lambda: _smoke_install()
     root.test_numpy_bindings = lambda: _smoke_install(numpy=True)
     sys.modules["pykeops"] = root
@@ -37,6 +44,42 @@ def install_as_pykeops():
     sys.modules["pykeops.torch.cluster"] = _tc          # the very same module objects, not second copies found via __path__
     sys.modules["pykeops.numpy.cluster"] = _nc
     return root
+
+
+def _cuda_available():
+    import torch as th
+    return bool(th.cuda.is_available())
+
+
+def _set_build_folder(path=None):
+    """``pykeops.set_build_folder`` (``pykeops/pykeops/__init__.py:83-93``): the folder that receives compiled kernels --
+    here the cubin cache; ``None`` goes back to the default (in-tree) cache."""
+    import os
+    if path is None:
+        os.environ.pop("KB200_CACHE_DIR", None)
+        LoadKeOpsB200.reset()
+    else:
+        LoadKeOpsB200.reset(new_save_folder=path)
+
+
+def _get_build_folder():
+    from .runtime.plan import cache_dir
+    return cache_dir()
+
+
+def _check_health():
+    """``pykeops.check_health`` (``pykeops/pykeops/__init__.py:64-80``): what this engine depends on, printed."""
+    import torch as th
+    from .runtime import capi
+    print("keops_b200 %s: runtime library %s" % (__version__, capi.library_path() if hasattr(capi, "library_path") else "loaded"))
+    print("  cubin cache: %s" % _get_build_folder())
+    if th.cuda.is_available():
+        for k in range(th.cuda.device_count()):
+            cc = th.cuda.get_device_capability(k)
+            print("  cuda:%d %s, compute capability %d.%d%s" % (k, th.cuda.get_device_name(k), cc[0], cc[1],
+                                                                "" if cc == (10, 0) else "  (kernels are built for sm_100a only)"))
+    else:
+        print("  no CUDA device: every reduction will raise (there is no CPU backend)")
 
 
 def _smoke_install(numpy=False):

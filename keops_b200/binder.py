@@ -200,8 +200,26 @@ class LoadKeOpsB200:
     def import_module(self):
         return self
 
-    def reset(self):
-        self._loaded.clear()
+    class _Reset:
+        """``reset`` is called both ways by the reference: on a binder object, and on the ``keops_binder[...]`` entry itself
+        -- there a ``Cache_partial`` -- by ``pykeops.clean_pykeops()`` / ``pykeops.set_build_folder(path)``
+        (``pykeops/pykeops/__init__.py:47-61,83-93``, ``keopscore/utils/Cache.py:99-109``), which for this engine is the
+        class.  Instance: forget the loaded modules.  Class: forget every memoised binder; a new save folder becomes the
+        cubin cache directory."""
+
+        def __get__(self, obj, cls):
+            if obj is not None:
+                return obj._loaded.clear
+
+            def reset_all(new_save_folder=None):
+                with _cache_lock:
+                    _binder_cache.clear()
+                if new_save_folder is not None:
+                    os.makedirs(new_save_folder, exist_ok=True)
+                    os.environ["KB200_CACHE_DIR"] = str(new_save_folder)
+            return reset_all
+
+    reset = _Reset()
 
     def _kernel(self, device: int) -> plan.LoadedKernel:
         lk = self._loaded.get(device)

@@ -87,7 +87,7 @@ def test_no_cpu_backend():
         (-kn.Vi(x).sqdist(kn.Vj(x))).exp().solve(kn.Vi(x), alpha=0.1)
 
 
-def test_pykeops_shim_exposes_numpy_and_cluster_modules():
+def test_pykeops_shim_exposes_numpy_and_cluster_modules(tmp_path):
     """``keops_b200.install_as_pykeops()``: the user's unchanged ``from pykeops.numpy import ...`` /
     ``from pykeops.torch.cluster import ...`` lines resolve to this package's module objects."""
     import sys
@@ -104,6 +104,27 @@ def test_pykeops_shim_exposes_numpy_and_cluster_modules():
         assert LazyTensor is kn.LazyTensor and Genred is kn.Genred and LT_t is kt.LazyTensor
         assert g_np is nc.grid_cluster and fm_t is tc.from_matrix
         assert root.numpy is kn and callable(root.test_numpy_bindings)
+        # housekeeping entry points user scripts call (pykeops/pykeops/__init__.py:20-23,47-104)
+        import os
+        import pykeops
+        from keops_b200.runtime import plan
+        pykeops.set_verbose(False)
+        assert pykeops.verbose is False
+        default = pykeops.get_build_folder()
+        assert default == plan.cache_dir()
+        prev = os.environ.get("KB200_CACHE_DIR")
+        try:
+            pykeops.set_build_folder(str(tmp_path / "kernels"))
+            assert pykeops.get_build_folder() == str(tmp_path / "kernels") and os.path.isdir(pykeops.get_build_folder())
+            pykeops.set_build_folder()
+            assert pykeops.get_build_folder() == default or prev is not None
+        finally:
+            if prev is None:
+                os.environ.pop("KB200_CACHE_DIR", None)
+            else:
+                os.environ["KB200_CACHE_DIR"] = prev
+        pykeops.check_health()
+        assert isinstance(pykeops.config.gpu_available, bool)
     finally:
         for k in [k for k in sys.modules if k == "pykeops" or k.startswith("pykeops.")]:
             del sys.modules[k]

@@ -396,3 +396,33 @@ def test_torch_func_transforms_launch_the_same_reductions(tmp_path, monkeypatch)
         for a, b in zip(mine, ref):
             assert a[2:] == b[2:], (name, a, b)                              # nx, ny, nbatchdims, argument shapes
             assert a[0] == b[0] or parse_reduction(a[0], a[1]) is parse_reduction(b[0], b[1]), (name, a[0], b[0])
+
+
+HOUSEKEEPING = r'''
+import json, os, sys, tempfile
+import pykeops
+from pykeops.common import keops_io
+from keops_b200 import binder as kb
+kb.register_into_pykeops()
+fl = dict(dtype_acc="auto", sum_scheme="auto", use_fast_math=1, enable_chunks=1, multVar_highdim=0)
+mk = lambda: kb.LoadKeOpsB200(1, 0, 1, False, -1, "Sum_Reduction(SqDist(x,y),0)", ["x=Vi(0,3)", "y=Vj(1,3)"], 2, "float32", "torch", fl)
+b1 = mk()
+assert mk() is b1                                       # memoised per argument tuple
+b1.reset()                                              # the per-object form (pykeops/__init__.py:57-59 on a binder object)
+pykeops.clean_pykeops(recompile_jit_binaries=False)     # calls keops_binder[key].reset() on every entry, ours included
+b2 = mk()
+assert b2 is not b1
+folder = tempfile.mkdtemp(prefix="kb200_build_folder_")
+pykeops.set_build_folder(folder)                        # calls keops_binder[key].reset(new_save_folder=...)
+from keops_b200.runtime import plan
+assert os.path.realpath(plan.cache_dir()) == os.path.realpath(folder), plan.cache_dir()
+assert mk() is not b2
+print("HOUSE" + json.dumps({"ok": True, "build_folder": pykeops.get_build_folder()}))
+'''
+
+
+def test_clean_pykeops_and_set_build_folder_reach_the_registered_binder(tmp_path):
+    """``pykeops.clean_pykeops()`` and ``pykeops.set_build_folder()`` call ``.reset(...)`` on every ``keops_binder`` entry
+    (pykeops/pykeops/__init__.py:47-61,83-93): with this engine registered that entry is the class itself."""
+    rec = _run_reference(HOUSEKEEPING, tmp_path, "HOUSE", 900)
+    assert rec["ok"]
