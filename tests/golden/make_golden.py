@@ -327,9 +327,13 @@ def main():
         np.savez_compressed(path, out=out, meta=json.dumps(meta), **{"arg%d" % k: a for k, a in enumerate(args)})
         index.append(meta)
         print("%-40s out %s  tagIJ=%d" % (c["name"], out.shape, tagIJ))
-    if not only:
-        with open(os.path.join(HERE, "index.json"), "w") as f:
-            json.dump(index, f, indent=1)
+    # index.json lists every committed case (also after a partial regeneration)
+    import glob
+    metas = []
+    for path in sorted(glob.glob(os.path.join(OUT, "*.npz"))):
+        metas.append(json.loads(str(np.load(path)["meta"])))
+    with open(os.path.join(HERE, "index.json"), "w") as f:
+        json.dump(metas, f, indent=1)
     print("wrote %d cases" % len(index))
 
 
