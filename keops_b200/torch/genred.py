@@ -36,28 +36,39 @@ class GenredParameters:
 
 
 def _resolve_backend(backend: str, args):
-    """Only GPU backends exist here; ``"CPU"`` is refused (no fallback).  ``GPU_2D`` merely forces the
-    split-column launch shape; the tuner may choose it on its own for ``auto`` / ``GPU_1D``."""
+    """Only GPU backends exist here; ``"CPU"`` is refused (no fallback).  ``GPU_2D`` merely forces the split-column launch
+    shape; the tuner may choose it on its own for ``auto`` / ``GPU_1D``.  Memory location as in the reference
+    (``pykeops/pykeops/common/get_options.py:54-120``): all tensors on a CUDA device -> device mode; all on the host ->
+    the ``*_host`` mode, in which the binder stages them on the GPU for the call and copies the result back (the reference's
+    launcher does the same, ``keops_nvrtc.cpp:470-507,617-631``); a mixture is an error."""
     options = ("auto", "CPU", "GPU", "GPU_1D", "GPU_1D_device", "GPU_1D_host", "GPU_2D", "GPU_2D_device", "GPU_2D_host")
     if backend not in options:
         raise ValueError("Invalid backend. Should be one of ", options)
     if backend == "CPU":
         raise ValueError("[KeOps-B200] backend='CPU' is not available: this engine is CUDA (sm_100a) only.")
-    if backend.endswith("_host"):
-        raise ValueError("[KeOps-B200] host-memory GPU modes were dropped: pass CUDA tensors.")
-    if not all(isinstance(a, torch.Tensor) and a.is_cuda for a in args):
-        raise ValueError("[KeOps-B200] all inputs must be CUDA tensors (no CPU fallback). "
-                         "At least two input variables have different memory locations (Cpu/Gpu)."
-                         if any(isinstance(a, torch.Tensor) and a.is_cuda for a in args) else
-                         "[KeOps-B200] all inputs must be CUDA tensors (no CPU fallback).")
-    return 1, (1 if "2D" in backend else 0), 1
+    if not all(isinstance(a, torch.Tensor) for a in args):
+        raise TypeError("All variables should either be numpy arrays or torch tensors.")
+    on_gpu = [a.is_cuda for a in args]
+    if any(on_gpu) and not all(on_gpu):
+        raise ValueError("At least two input variables have different memory locations (Cpu/Gpu).")
+    host = not any(on_gpu)
+    if backend.endswith("_device") and host or backend.endswith("_host") and not host:
+        raise ValueError("[KeOps-B200] backend %r does not match the memory location of the inputs (%s)."
+                         % (backend, "host" if host else "device"))
+    if host and not torch.cuda.is_available():
+        raise ValueError("[KeOps-B200] all inputs must be CUDA tensors (no CPU fallback): no CUDA device to stage host tensors on.")
+    return 1, (1 if "2D" in backend else 0), (0 if host else 1)
 
 
 def _set_device(device_id_request: int, args):
+    """``set_device`` of the reference (``generic_red.py:46-67``): device tensors decide, host tensors go to the requested
+    device (default: device 0)."""
     dev = args[0].device
     for a in args[1:]:
         if a.device != dev:
             raise ValueError("[KeOps] Input arrays must be all located on the same device.")
+    if not dev.type == "cuda":
+        return (0 if device_id_request in (-1, None) else int(device_id_request)), dev
     if device_id_request not in (-1, None) and dev.index != device_id_request:
         raise ValueError("[KeOps] Gpu device id of arrays is different from device id requested for computation.")
     return dev.index, dev

@@ -536,3 +536,46 @@ def test_kron(api, cuda_device):
     o1 = api.Genred("Kron(x, y, [2, 3], [2, 2])", al, reduction_op="Sum", axis=1)(x, y)
     o2 = api.Genred("TensorDot(x, y, [2, 3], [2, 2], [], [], [0, 2, 1, 3])", al, reduction_op="Sum", axis=1)(x, y)
     assert torch.equal(o1, o2)
+
+
+def test_host_tensors_and_the_multi_gpu_thread_pattern(api, cuda_device):
+    # examples/pytorch/plot_multi_gpu.py:40-96 -- the reference's only multi-GPU code: host tensors, ``device_id=gpuid``, one
+    # thread per GPU, blocks of the reduction index summed on the host / blocks of the output index concatenated.
+    # With one visible GPU both workers land on device 0 (still two threads launching concurrently).
+    from concurrent.futures import ThreadPoolExecutor, wait
+    if AGAINST_REFERENCE and not torch.cuda.is_available():
+        pytest.skip("device_id needs the reference's CUDA backend")
+    torch.manual_seed(0)
+    ngpus = max(1, torch.cuda.device_count())
+    workers = max(2, ngpus)
+    M, N = 6000, 9000
+    x, y = torch.randn(M, 3), torch.randn(N, 3)
+
+    def gauss_kernel_sum(x, y, gpuid=-1):
+        x_i, y_j = api.LazyTensor(x[:, None, :]), api.LazyTensor(y[None, :, :])
+        return (-((x_i - y_j) ** 2).sum(dim=2)).exp().sum(dim=1, device_id=gpuid)
+
+    ref = torch.exp(-torch.cdist(x.double(), y.double()) ** 2).sum(1, keepdim=True)
+    out = gauss_kernel_sum(x, y)                     # host in, host out, computed on the default GPU
+    assert out.device.type == "cpu" and out.shape == (M, 1)
+    assert torch.allclose(out.double(), ref, rtol=1e-5)
+    for gpuid in range(ngpus):
+        gauss_kernel_sum(x[:100], y[:100], gpuid)
+    pool = ThreadPoolExecutor(workers)
+    step = -(-N // workers)
+    futs = [pool.submit(gauss_kernel_sum, x, y[k * step:(k + 1) * step], k % ngpus) for k in range(workers)]
+    wait(futs)
+    assert torch.allclose(sum(f.result().cpu() for f in futs).double(), ref, rtol=1e-5)
+    step = -(-M // workers)
+    futs = [pool.submit(gauss_kernel_sum, x[k * step:(k + 1) * step], y, k % ngpus) for k in range(workers)]
+    wait(futs)
+    assert torch.allclose(torch.cat([f.result().cpu() for f in futs]).double(), ref, rtol=1e-5)
+    # gradients flow through the staged call as well
+    xg = x[:500].clone().requires_grad_(True)
+    gauss_kernel_sum(xg, y).sum().backward()
+    xd = x[:500].double().requires_grad_(True)
+    torch.exp(-torch.cdist(xd, y.double()) ** 2).sum().backward()
+    assert xg.grad.device.type == "cpu" and torch.allclose(xg.grad.double(), xd.grad, rtol=1e-4, atol=1e-4 * xd.grad.abs().max().item())
+    if not AGAINST_REFERENCE:
+        with pytest.raises(ValueError):
+            gauss_kernel_sum(x.to(cuda_device), y)                       # mixed memory locations
