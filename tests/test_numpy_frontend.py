@@ -129,3 +129,30 @@ def test_pykeops_shim_exposes_numpy_and_cluster_modules(tmp_path):
         for k in [k for k in sys.modules if k == "pykeops" or k.startswith("pykeops.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_torch_front_end_memory_location_rules():
+    """``backend`` / memory-location resolution of the torch front-end (pykeops/pykeops/common/get_options.py:54-120,
+    torch/generic/generic_red.py:46-67): host tensors select the staged ``*_host`` mode on ``device_id`` (default 0) -- and
+    raise where there is no CUDA device to stage them on; explicit ``*_device`` / ``*_host`` backends must match."""
+    import torch
+    from keops_b200.torch import genred
+    x, y = torch.rand(4, 3), torch.rand(5, 3)
+    assert genred._set_device(-1, (x, y)) == (0, x.device)
+    assert genred._set_device(3, (x, y)) == (3, x.device)
+    with pytest.raises(ValueError, match="backend='CPU' is not available"):
+        genred._resolve_backend("CPU", (x, y))
+    with pytest.raises(ValueError, match="Invalid backend"):
+        genred._resolve_backend("TPU", (x, y))
+    with pytest.raises(ValueError, match="does not match the memory location"):
+        genred._resolve_backend("GPU_1D_device", (x, y))
+    with pytest.raises(TypeError):
+        genred._resolve_backend("auto", (x, y.numpy()))
+    if not torch.cuda.is_available():
+        with pytest.raises(ValueError, match="no CPU fallback"):
+            genred._resolve_backend("auto", (x, y))
+        with pytest.raises(ValueError, match="no CPU fallback"):
+            kt.Genred("SqDist(x,y)", ["x=Vi(3)", "y=Vj(3)"], reduction_op="Sum", axis=1)(x, y)
+    else:
+        assert genred._resolve_backend("auto", (x, y)) == (1, 0, 0)
+        assert genred._resolve_backend("GPU_2D_host", (x, y)) == (1, 1, 0)
