@@ -69,7 +69,7 @@ class LoadKeOpsB200:
         if lang not in ("torch", "pytorch", "numpy"):
             raise ValueError("[KeOps-B200] unknown binding %r (torch or numpy expected)." % (lang,))
         if dtype not in ("float32", "float64"):
-            raise ValueError("not implemented")
+            raise ValueError("[KeOps-B200] dtype %r is not implemented (float32 and float64 only; no half2 kernels)." % (dtype,))
         p = types.SimpleNamespace()
         p.aliases_old = list(aliases)
         p.aliases = _normalise_aliases(aliases)

@@ -170,6 +170,8 @@ class Lowerer:
         if op == "TensorProd":
             a, b = L(n.args[0]), L(n.args[1])
             return [g.mul(x, y) for x in a for y in b]
+        if op.startswith("Complex") or op in ("Real2Complex", "Imag2Complex", "Conj"):
+            return self._lower_complex(n)
         if op == "BSpline":
             # de Boor's recursion, in place on knots.dim - 1 values; the first knots.dim - order - 1 are the result
             # (maths/BSpline.py:44-95).  omega(i, k) = (x - t_i) / (t_{i+k} - t_i), 0 on an empty knot span.
@@ -207,6 +209,62 @@ class Lowerer:
                 out[o] = acc
             return out
         raise NotImplementedError("operation %s is not supported by the sm_100a code generator" % op)
+
+
+def _lower_complex(self, n: Node) -> List[SV]:
+    """Complex arithmetic on interleaved (re, im) components (``keopscore/keopscore/formulas/complex/*.py``); a size-2 operand
+    of a binary operation is one complex number broadcast over the other operand's pairs."""
+    g, op = self.g, n.op
+    a = self(n.args[0])
+    zero = g.const(0.0)
+    pairs = lambda v: [(v[k], v[k + 1]) for k in range(0, len(v), 2)]
+    flat = lambda ps: [c for p in ps for c in p]
+    if op == "ComplexReal":
+        return a[0::2]
+    if op == "ComplexImag":
+        return a[1::2]
+    if op == "Real2Complex":
+        return flat((x, zero) for x in a)
+    if op == "Imag2Complex":
+        return flat((zero, x) for x in a)
+    if op == "Conj":
+        return flat((re, -im) for re, im in pairs(a))
+    if op == "ComplexSquareAbs":
+        return [g.add(g.mul(re, re), g.mul(im, im)) for re, im in pairs(a)]
+    if op == "ComplexExp":
+        out = []
+        for re, im in pairs(a):
+            r = g.exp(re)
+            out += [g.mul(r, g.fn1("cos", im, parity=1)), g.mul(r, g.fn1("sin", im, parity=-1))]
+        return out
+    if op == "ComplexExp1j":
+        return flat((g.fn1("cos", x, parity=1), g.fn1("sin", x, parity=-1)) for x in a)
+    if op == "ComplexSum":
+        ps = pairs(a)
+        re, im = ps[0]
+        for r2, i2 in ps[1:]:
+            re, im = g.add(re, r2), g.add(im, i2)
+        return [re, im]
+    if op == "ComplexSumT":
+        return list(a) * (n.dim // 2)
+    b = self(n.args[1])
+    if op == "ComplexRealScal":
+        return [g.mul(a[0], x) for x in b]
+    pa, pb = pairs(a), pairs(b)
+    npair = n.dim // 2
+    pa = pa * npair if len(pa) == 1 else pa
+    pb = pb * npair if len(pb) == 1 else pb
+    if op == "ComplexAdd":
+        return flat((g.add(x[0], y[0]), g.add(x[1], y[1])) for x, y in zip(pa, pb))
+    if op == "ComplexSubtract":
+        return flat((g.sub(x[0], y[0]), g.sub(x[1], y[1])) for x, y in zip(pa, pb))
+    if op == "ComplexMult":
+        return flat((g.sub(g.mul(x[0], y[0]), g.mul(x[1], y[1])), g.add(g.mul(x[0], y[1]), g.mul(x[1], y[0])))
+                    for x, y in zip(pa, pb))
+    raise NotImplementedError("operation %s is not supported by the sm_100a code generator" % op)
+
+
+Lowerer._lower_complex = _lower_complex
 
 
 def _softdtw_table(g: Graph, x: List[SV], y: List[SV], gam: SV) -> List[List[SV]]:

@@ -243,6 +243,54 @@ def _rule(f: Node, v: Node, g: Node, memo) -> Node:
     if op == "TensorProd":
         a, b = f.args
         return G(a, ir.MatVecMult(g, b)) + G(b, ir.VecMatMult(a, g))
+    # ---- complex arithmetic (keopscore/keopscore/formulas/complex/*.py).  The reference adds the two partial gradients of a
+    # binary complex operation with ComplexAdd, which refuses odd sizes (a real variable of size 1 or 3); they are gradients
+    # with respect to the same variable, of the same size, so a plain sum is the same thing wherever the reference works.
+    if op == "ComplexReal":
+        return G(f.args[0], ir.Real2Complex(g))
+    if op == "ComplexImag":
+        return G(f.args[0], ir.Imag2Complex(g))
+    if op == "Real2Complex":
+        return G(f.args[0], ir.ComplexReal(g))
+    if op == "Imag2Complex":
+        return G(f.args[0], ir.ComplexImag(g))
+    if op == "Conj":
+        return G(f.args[0], ir.Conj(g))
+    if op == "ComplexSquareAbs":
+        (a,) = f.args
+        return _grad(ir.ComplexReal(ir.ComplexMult(a, ir.Conj(a))), v, g, memo)
+    if op == "ComplexMult":
+        a, b = f.args
+        ga, gb = ir.ComplexMult(ir.Conj(b), g), ir.ComplexMult(ir.Conj(a), g)
+        if a.dim == 2 and b.dim > 2:
+            ga = ir.ComplexSum(ga)
+        elif b.dim == 2 and a.dim > 2:
+            gb = ir.ComplexSum(gb)
+        return G(a, ga) + G(b, gb)
+    if op in ("ComplexAdd", "ComplexSubtract"):
+        a, b = f.args
+        ga, gb = g, g
+        if a.dim == 2 and b.dim > 2:
+            ga = ir.ComplexSum(g)
+        elif b.dim == 2 and a.dim > 2:
+            gb = ir.ComplexSum(g)
+        return G(a, ga) + G(b, gb) if op == "ComplexAdd" else G(a, ga) - G(b, gb)
+    if op == "ComplexRealScal":
+        a, b = f.args
+        return _grad(ir.ComplexMult(ir.Real2Complex(a), b), v, g, memo)
+    if op == "ComplexExp":
+        (a,) = f.args
+        mod = ir.Exp(ir.ComplexReal(a))
+        alt = ir.Real2Complex(mod * ir.Cos(ir.ComplexImag(a))) + ir.Imag2Complex(mod * ir.Sin(ir.ComplexImag(a)))
+        return _grad(alt, v, g, memo)
+    if op == "ComplexExp1j":
+        (a,) = f.args
+        return _grad(ir.Real2Complex(ir.Cos(a)) + ir.Imag2Complex(ir.Sin(a)), v, g, memo)
+    if op == "ComplexSum":
+        (a,) = f.args
+        return G(a, ir.ComplexSumT(g, a.dim))
+    if op == "ComplexSumT":
+        return G(f.args[0], ir.ComplexSum(g))
     if op == "BSpline":
         raise NotImplementedError("KeOps BSplines are not yet differentiable. Please consider disabling autograd for the "
                                   "relevant variables with 'x.detach()'.")       # maths/BSpline.py:97-103

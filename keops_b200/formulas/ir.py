@@ -709,6 +709,112 @@ def BSpline(knots: Node, x: Node, order: int) -> Node:
     return Node("BSpline", (knots, x), (order,), knots.dim - order - 1)
 
 
+# ------------------------------------------------------------------------------------------
+# complex arithmetic on interleaved (re, im) pairs (``keopscore/keopscore/formulas/complex/*.py``)
+# ------------------------------------------------------------------------------------------
+def _even(f: Node, what: str) -> None:
+    if f.dim % 2 != 0:
+        raise FormulaError("Dimension of F must be even (%s of a vector of size %d)" % (what, f.dim))
+
+
+def _complex_dims(name: str, *args: Node) -> int:
+    """Broadcast rule of the reference's ``VectorizedComplexScalarOp`` (``formulas/VectorizedComplexScalarOp.py:11-21``):
+    all operands have the same even size, or some are one complex number (size 2)."""
+    dims = set(a.dim for a in args)
+    if max(dims) % 2 != 0 or len(dims) > 2 or (len(dims) == 2 and min(dims) != 2):
+        raise FormulaError("dimensions are not compatible for VectorizedComplexScalarOp (%s)" % name)
+    return max(dims)
+
+
+def ComplexReal(f: Node) -> Node:
+    _even(f, "ComplexReal")
+    return Zero(f.dim // 2) if f.is_zero else Node("ComplexReal", (f,), (), f.dim // 2)
+
+
+def ComplexImag(f: Node) -> Node:
+    _even(f, "ComplexImag")
+    return Zero(f.dim // 2) if f.is_zero else Node("ComplexImag", (f,), (), f.dim // 2)
+
+
+def Real2Complex(f: Node) -> Node:
+    return Zero(2 * f.dim) if f.is_zero else Node("Real2Complex", (f,), (), 2 * f.dim)
+
+
+def Imag2Complex(f: Node) -> Node:
+    return Zero(2 * f.dim) if f.is_zero else Node("Imag2Complex", (f,), (), 2 * f.dim)
+
+
+def Conj(f: Node) -> Node:
+    _complex_dims("Conj", f)
+    return f if f.is_zero else Node("Conj", (f,), (), f.dim)
+
+
+def ComplexSquareAbs(f: Node) -> Node:
+    _even(f, "ComplexSquareAbs")
+    return Zero(f.dim // 2) if f.is_zero else Node("ComplexSquareAbs", (f,), (), f.dim // 2)
+
+
+def ComplexAbs(f: Node) -> Node:
+    return Sqrt(ComplexSquareAbs(f))
+
+
+def ComplexAngle(f: Node) -> Node:
+    return Atan2(ComplexImag(f), ComplexReal(f))
+
+
+def ComplexMult(f: Node, g: Node) -> Node:
+    dim = _complex_dims("ComplexMult", f, g)
+    if f.is_zero or g.is_zero:
+        return Zero(dim)
+    return Node("ComplexMult", (f, g), (), dim)
+
+
+def ComplexDivide(f: Node, g: Node) -> Node:
+    return ComplexMult(Real2Complex(Inv(ComplexSquareAbs(g))), ComplexMult(f, Conj(g)))
+
+
+def ComplexAdd(f: Node, g: Node) -> Node:
+    return Node("ComplexAdd", (f, g), (), _complex_dims("ComplexAdd", f, g))
+
+
+def ComplexSubtract(f: Node, g: Node) -> Node:
+    return Node("ComplexSubtract", (f, g), (), _complex_dims("ComplexSubtract", f, g))
+
+
+def ComplexRealScal(f: Node, g: Node) -> Node:
+    """real scalar times complex vector, in either argument order (``complex/ComplexRealScal.py:54-55``)"""
+    if f.dim != 1:
+        f, g = g, f
+    if f.dim != 1:
+        raise FormulaError("Dimension of F must be 1")
+    _even(g, "ComplexRealScal")
+    if f.is_zero or g.is_zero:
+        return Zero(g.dim)
+    return Node("ComplexRealScal", (f, g), (), g.dim)
+
+
+def ComplexExp(f: Node) -> Node:
+    return Node("ComplexExp", (f,), (), _complex_dims("ComplexExp", f))
+
+
+def ComplexExp1j(f: Node) -> Node:
+    return Node("ComplexExp1j", (f,), (), 2 * f.dim)
+
+
+def ComplexSum(f: Node) -> Node:
+    _even(f, "ComplexSum")
+    return Zero(2) if f.is_zero else Node("ComplexSum", (f,), (), 2)
+
+
+def ComplexSumT(f: Node, dim: int) -> Node:
+    if f.dim != 2:
+        raise FormulaError("Dimension of F must be 2")
+    dim = int(dim)
+    if dim % 2 != 0:
+        raise FormulaError("ComplexSumT: the output dimension must be even")
+    return Zero(dim) if f.is_zero else Node("ComplexSumT", (f,), (dim,), dim)
+
+
 # names visible to the formula parser -------------------------------------------------------
 PUBLIC_OPS = {
     name: obj

@@ -170,7 +170,7 @@ class _Interp(ast.NodeVisitor):
     _N_FORMULA_ARGS = {
         "Var": 0, "Zero": 0, "IntCst": 0, "RatCst": 0, "IntInv": 0, "FloatCst": 0,
         "Pow": 1, "Round": 1, "SumT": 1, "Extract": 1, "ExtractT": 1, "Elem": 1, "ElemT": 1,
-        "OneHot": 1, "ClampInt": 1, "DiffClampInt": 1, "TensorDot": 2, "Kron": 2, "BSpline": 2,
+        "OneHot": 1, "ClampInt": 1, "DiffClampInt": 1, "TensorDot": 2, "Kron": 2, "BSpline": 2, "ComplexSumT": 1,
     }
 
     def _call_op(self, name, fn, args):

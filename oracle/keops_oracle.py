@@ -899,6 +899,182 @@ class BSpline(Op):
         raise NotImplementedError("KeOps BSplines are not yet differentiable.")
 
 
+# ---- complex arithmetic on interleaved (re, im) pairs: keopscore/keopscore/formulas/complex/*.py ----------------------------
+def _cdims(*ops):
+    dims = set(o.dim for o in ops)
+    assert max(dims) % 2 == 0 and len(dims) <= 2 and (len(dims) == 1 or min(dims) == 2), "VectorizedComplexScalarOp dims"
+    return max(dims)
+
+
+def _cpairs(a, dim):
+    """(..., 2) or (..., dim) interleaved -> (re, im) arrays of trailing size dim // 2 (a single complex number broadcasts)"""
+    return a[..., 0::2], a[..., 1::2]
+
+
+def _cjoin(re, im):
+    shape = np.broadcast_shapes(re.shape, im.shape)
+    out = np.empty(shape[:-1] + (2 * shape[-1],), dtype=np.result_type(re, im))
+    out[..., 0::2], out[..., 1::2] = re, im
+    return out
+
+
+class ComplexReal(Op):
+    def __init__(self, f):
+        assert f.dim % 2 == 0
+        self.children, self.dim = (f,), f.dim // 2
+    def ev(self, env): return self.children[0].ev(env)[..., 0::2]
+    def difft(self, v, g): return self.children[0].difft(v, Real2Complex(g))
+
+
+class ComplexImag(Op):
+    def __init__(self, f):
+        assert f.dim % 2 == 0
+        self.children, self.dim = (f,), f.dim // 2
+    def ev(self, env): return self.children[0].ev(env)[..., 1::2]
+    def difft(self, v, g): return self.children[0].difft(v, Imag2Complex(g))
+
+
+class Real2Complex(Op):
+    def __init__(self, f): self.children, self.dim = (f,), 2 * f.dim
+    def ev(self, env):
+        a = self.children[0].ev(env)
+        return _cjoin(a, np.zeros_like(a))
+    def difft(self, v, g): return self.children[0].difft(v, ComplexReal(g))
+
+
+class Imag2Complex(Op):
+    def __init__(self, f): self.children, self.dim = (f,), 2 * f.dim
+    def ev(self, env):
+        a = self.children[0].ev(env)
+        return _cjoin(np.zeros_like(a), a)
+    def difft(self, v, g): return self.children[0].difft(v, ComplexImag(g))
+
+
+class Conj(Op):
+    def __init__(self, f): self.children, self.dim = (f,), _cdims(f)
+    def ev(self, env):
+        re, im = _cpairs(self.children[0].ev(env), self.dim)
+        return _cjoin(re, -im)
+    def difft(self, v, g): return self.children[0].difft(v, Conj(g))
+
+
+class ComplexSquareAbs(Op):
+    def __init__(self, f):
+        assert f.dim % 2 == 0
+        self.children, self.dim = (f,), f.dim // 2
+    def ev(self, env):
+        re, im = _cpairs(self.children[0].ev(env), 2 * self.dim)
+        return re * re + im * im
+    def difft(self, v, g):
+        f = self.children[0]                                                      # ComplexSquareAbs.py: alternative formula
+        return ComplexReal(ComplexMult(f, Conj(f))).difft(v, g)
+
+
+def ComplexAbs(f): return Sqrt(ComplexSquareAbs(f))
+def ComplexAngle(f): return Atan2(ComplexImag(f), ComplexReal(f))
+
+
+class _ComplexBinary(Op):
+    def __init__(self, f, g):
+        self.children, self.dim = (f, g), _cdims(f, g)
+    def ev(self, env):
+        a, b = [c.ev(env) for c in self.children]
+        return _cjoin(*self.f(_cpairs(a, self.dim), _cpairs(b, self.dim)))
+    def _split(self, g):
+        f, h = self.children
+        gf = ComplexSum(g) if (f.dim == 2 and h.dim > 2) else g
+        gh = ComplexSum(g) if (h.dim == 2 and f.dim > 2) else g
+        return gf, gh
+
+
+class ComplexAdd(_ComplexBinary):
+    def f(self, a, b): return a[0] + b[0], a[1] + b[1]
+    def difft(self, v, g):
+        gf, gh = self._split(g)
+        return self.children[0].difft(v, gf) + self.children[1].difft(v, gh)
+
+
+class ComplexSubtract(_ComplexBinary):
+    def f(self, a, b): return a[0] - b[0], a[1] - b[1]
+    def difft(self, v, g):
+        gf, gh = self._split(g)
+        return self.children[0].difft(v, gf) - self.children[1].difft(v, gh)
+
+
+class ComplexMult(_ComplexBinary):
+    def f(self, a, b): return a[0] * b[0] - a[1] * b[1], a[0] * b[1] + a[1] * b[0]
+    def difft(self, v, g):
+        f, h = self.children                                                      # ComplexMult.py:30-50
+        gf, gh = ComplexMult(Conj(h), g), ComplexMult(Conj(f), g)
+        if f.dim == 2 and h.dim > 2:
+            gf = ComplexSum(gf)
+        elif h.dim == 2 and f.dim > 2:
+            gh = ComplexSum(gh)
+        return f.difft(v, gf) + h.difft(v, gh)
+
+
+def ComplexDivide(f, g): return ComplexMult(Real2Complex(Inv(ComplexSquareAbs(g))), ComplexMult(f, Conj(g)))
+
+
+class _ComplexRealScal(Op):
+    def __init__(self, f, g):
+        assert f.dim == 1 and g.dim % 2 == 0
+        self.children, self.dim = (f, g), g.dim
+    def ev(self, env):
+        a, b = [c.ev(env) for c in self.children]
+        return a * b
+    def difft(self, v, g):
+        f, h = self.children
+        return ComplexMult(Real2Complex(f), h).difft(v, g)
+
+
+def ComplexRealScal(f, g): return _ComplexRealScal(f, g) if f.dim == 1 else _ComplexRealScal(g, f)
+
+
+class ComplexExp(Op):
+    def __init__(self, f): self.children, self.dim = (f,), _cdims(f)
+    def ev(self, env):
+        re, im = _cpairs(self.children[0].ev(env), self.dim)
+        r = np.exp(re)
+        return _cjoin(r * np.cos(im), r * np.sin(im))
+    def difft(self, v, g):
+        f = self.children[0]                                                      # ComplexExp.py: alternative formula
+        mod = Exp(ComplexReal(f))
+        alt = Real2Complex(mod * Cos(ComplexImag(f))) + Imag2Complex(mod * Sin(ComplexImag(f)))
+        return alt.difft(v, g)
+
+
+class ComplexExp1j(Op):
+    def __init__(self, f): self.children, self.dim = (f,), 2 * f.dim
+    def ev(self, env):
+        a = self.children[0].ev(env)
+        return _cjoin(np.cos(a), np.sin(a))
+    def difft(self, v, g):
+        f = self.children[0]
+        return (Real2Complex(Cos(f)) + Imag2Complex(Sin(f))).difft(v, g)
+
+
+class ComplexSum(Op):
+    def __init__(self, f):
+        assert f.dim % 2 == 0
+        self.children, self.dim = (f,), 2
+    def ev(self, env):
+        a = self.children[0].ev(env)
+        re, im = np.zeros(a.shape[:-1], env.dtype), np.zeros(a.shape[:-1], env.dtype)
+        for k in range(0, a.shape[-1], 2):
+            re, im = re + a[..., k], im + a[..., k + 1]
+        return np.stack([re, im], axis=-1)
+    def difft(self, v, g): return self.children[0].difft(v, ComplexSumT(g, self.children[0].dim))
+
+
+class ComplexSumT(Op):
+    def __init__(self, f, dim):
+        assert f.dim == 2
+        self.children, self.dim = (f,), int(dim)
+    def ev(self, env): return np.tile(self.children[0].ev(env), self.dim // 2)
+    def difft(self, v, g): return self.children[0].difft(v, ComplexSum(g))
+
+
 def Elem(a, m): return Extract(a, m, 1)
 def ElemT(a, n, m): return ExtractT(a, m, n)
 def SqNorm2(a): return Sum(Square(a))                                            # maths/SqNorm2.py

@@ -252,6 +252,30 @@ for order in (0, 1, 3):
          aliases=["t=Pm(0,8)", "x=Vi(1,1)", "y=Vj(2,1)", "b=Vj(3,1)"], sizes=(23, 31))
 
 
+# ---- complex arithmetic on interleaved (re, im) pairs (formulas/complex/*.py): the non-uniform Fourier sum of
+# test_complex.py, every operation once, and gradients with respect to complex and real (even-sized) variables
+CPLX = {
+    "nufft": "ComplexMult(z,ComplexExp1j(IntCst(-6)*p*f))",
+    "exp_scal": "ComplexRealScal(f,ComplexExp(ComplexMult(z,w)))+ComplexRealScal(ComplexExp(Conj(w)),p)",
+    "div_abs_angle": "Concat(ComplexDivide(z,w),Concat(ComplexAbs(z-w),ComplexAngle(ComplexAdd(z,ComplexSum(w)))))",
+    "parts": "ComplexSubtract(Real2Complex(ComplexReal(z)*ComplexImag(w)),Imag2Complex(ComplexSquareAbs(ComplexMult(z,Elem(w,0)|Elem(w,1)*IntCst(0)+ComplexSumT(ComplexSum(w),4)))))",
+    "sum_sumT": "ComplexMult(ComplexSum(z),w)+ComplexSumT(ComplexSum(ComplexMult(z,Conj(w))),4)",
+}
+CPLX["parts"] = "ComplexSubtract(Real2Complex(ComplexReal(z)*ComplexImag(w)),Imag2Complex(ComplexSquareAbs(ComplexMult(z,ComplexSumT(ComplexSum(w),4)))))"
+CPLX_ALI = ["z=Vj(0,4)", "w=Vi(1,4)", "p=Vj(2,1)", "f=Vi(3,1)"]
+CPLX_ARGS = [(4, 1, "n"), (4, 0, "n"), (1, 1, "u"), (1, 0, "u")]
+for nm, f in CPLX.items():
+    red = "Sum_Reduction(%s,0)" % f
+    case("cplx_" + nm, red, CPLX_ARGS, aliases=CPLX_ALI, sizes=(23, 31))
+    if nm in ("nufft", "exp_scal", "div_abs_angle", "sum_sumT"):
+        for vname, vstr in (("z", V(0, 4, 1)), ("w", V(1, 4, 0))):
+            if (nm, vname) == ("nufft", "w"):
+                continue                    # w does not occur in that formula
+            case("cplx_grad_%s_%s" % (nm, vname), "Grad_WithSavedForward(%s,%s,%s,%s)" % (red, vstr, "Var(4,DIMOUT,0)", "Var(5,DIMOUT,0)"),
+                 CPLX_ARGS + [("eta", 0, red, 4), ("fwd", 0, red, 4)], dtypes=("float64",),
+                 aliases=CPLX_ALI + ["Var(4,DIMOUT,0)", "Var(5,DIMOUT,0)"], sizes=(23, 31))
+
+
 def flags(formula):
     head = formula.split("(")[0]
     sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
@@ -278,7 +302,7 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
-        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_", "td_", "sdtw_", "bspline_")):
+        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_", "td_", "sdtw_", "bspline_", "cplx_")):
             import zlib
             rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])

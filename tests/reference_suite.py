@@ -48,6 +48,9 @@ FILES = [
     "pykeops/test/test_lazytensor_gaussian_numpy_inplace.py",
     "pykeops/test/test_gpu_cpu.py",
     "pykeops/numpy/test_install.py",
+    # complex LazyTensors (the reference's ComplexLazyTensor front-end over this engine's interleaved (re, im) operations)
+    "pykeops/test/test_complex.py",
+    "pykeops/test/test_complex_numpy.py",
     # the reference's per-operation harness: every operation of keopscore.formulas.maths (forward and, where it has one,
     # gradient) as a Genred Sum reduction against the operation's torch equivalent
     "keopscore/test/test_op.py",

@@ -16,10 +16,11 @@ REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_reference(script, tmp_path, tag, timeout):
+def _run_reference(script, tmp_path, tag, timeout, cache=None):
     """Run ``script`` with the real reference importable; returns the JSON payload printed after ``tag``.  An environment
     in which the reference itself cannot run (no compiler, read-only cache ...) skips; a failed assertion fails."""
-    cache = os.environ.get("KEOPS_CACHE_FOLDER", os.path.join(ROOT, "oracle", "_ref", "keops_cache"))   # git-ignored, persistent
+    if cache is None:
+        cache = os.environ.get("KEOPS_CACHE_FOLDER", os.path.join(ROOT, "oracle", "_ref", "keops_cache"))   # git-ignored, persistent
     os.makedirs(cache, exist_ok=True)
     env = dict(os.environ, CXX="/usr/bin/g++", KEOPS_CACHE_FOLDER=cache,
                PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=os.pathsep.join((REF + "/keopscore", REF + "/pykeops", ROOT)))
@@ -424,5 +425,6 @@ print("HOUSE" + json.dumps({"ok": True, "build_folder": pykeops.get_build_folder
 def test_clean_pykeops_and_set_build_folder_reach_the_registered_binder(tmp_path):
     """``pykeops.clean_pykeops()`` and ``pykeops.set_build_folder()`` call ``.reset(...)`` on every ``keops_binder`` entry
     (pykeops/pykeops/__init__.py:47-61,83-93): with this engine registered that entry is the class itself."""
-    rec = _run_reference(HOUSEKEEPING, tmp_path, "HOUSE", 900)
+    # its own throw-away reference cache: clean_pykeops() empties the folder it is pointed at
+    rec = _run_reference(HOUSEKEEPING, tmp_path, "HOUSE", 900, cache=str(tmp_path / "keops_cache"))
     assert rec["ok"]
