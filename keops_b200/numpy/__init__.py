@@ -117,6 +117,14 @@ class LazyTensor(_TorchLazyTensor):
             return x.item()
         return torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
 
+    @staticmethod
+    def _view_as_complex(res):
+        """interleaved (re, im) pairs -> complex array (``pykeops/pykeops/numpy/utils.py``, ``view_as_complex``)"""
+        if isinstance(res, np.ndarray) and not np.iscomplexobj(res):
+            res = np.ascontiguousarray(res)
+            return res.view({"float32": "complex64", "float64": "complex128"}[str(res.dtype)])
+        return res
+
 
 def Vi(x_or_ind, dim=None):
     """``Vi(x)`` for an (M, D) array, or the symbolic ``Vi(ind, dim)``."""

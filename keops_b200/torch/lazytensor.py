@@ -11,8 +11,9 @@ Supported surface: constructors from tensors / floats / ints / lists / ``(ind, d
 ``Vi / Vj / Pm``, element-wise arithmetic and math functions, ``sum(-1)``, ``|``, ``@``,
 concatenation / extraction, all reductions of the engine (sum, logsumexp, sumsoftmaxweight, min,
 argmin, min_argmin, max, argmax, max_argmax, Kmin, argKmin, Kmin_argKmin), ``solve`` and batch
-dimensions, block-sparse ``ranges`` (helpers in :mod:`keops_b200.torch.cluster`).  Not carried over: complex
-numbers, float16, TensorDot / Kron / BSpline / SoftDTW.
+dimensions, block-sparse ``ranges`` (helpers in :mod:`keops_b200.torch.cluster`), tensor contractions (``keops_tensordot``,
+``keops_kron``), ``bspline``, ``softdtw_sqdist``, and complex numbers (``ComplexLazyTensor``: complex tensors are viewed as
+interleaved (re, im) pairs, ``lazy_tensor.py:2669-2823``).  Not carried over: float16.
 """
 from __future__ import annotations
 
@@ -32,6 +33,20 @@ def _is_lt(x):
     return isinstance(x, LazyTensor)
 
 
+def _is_scalar(x, val=None):
+    ok = isinstance(x, (int, float, complex)) and not isinstance(x, bool)
+    return ok if val is None else (ok and x == val)
+
+
+def _detect_complex(x):
+    """``torchtools.detect_complex`` (``pykeops/pykeops/torch/utils.py:99-105``)"""
+    if isinstance(x, list):
+        return any(type(v) == complex for v in x)
+    if isinstance(x, torch.Tensor):
+        return torch.is_complex(x)
+    return type(x) == complex
+
+
 class LazyTensor:
     # hooks for the numpy front-end (keops_b200/numpy): which callable classes run the reductions, and how a
     # user-provided array becomes the torch tensor the bookkeeping below works with
@@ -43,8 +58,6 @@ class LazyTensor:
         return x
 
     def __init__(self, x=None, axis=None, is_complex=False):
-        if is_complex:
-            raise NotImplementedError("[KeOps-B200] complex LazyTensors are not implemented.")
         self.variables = ()
         self.symbolic_variables = ()
         self.formula = None
@@ -61,6 +74,15 @@ class LazyTensor:
         if x is None:
             return
         x = self._ingest(x)
+        if is_complex or _detect_complex(x):
+            # complex data are stored as interleaved (re, im) pairs along the last dimension (lazy_tensor.py:2672-2687)
+            self.is_complex = True
+            if type(x) == complex:
+                x = [x]
+            if isinstance(x, list):
+                x = [c for v in x for c in (complex(v).real, complex(v).imag)]
+            elif isinstance(x, torch.Tensor) and torch.is_complex(x):
+                x = torch.view_as_real(x).reshape(tuple(x.shape[:-1]) + (2 * x.shape[-1],)) if x.dim() else torch.view_as_real(x)
         if isinstance(x, tuple):
             if len(x) != 3 or not all(isinstance(v, int) for v in x):
                 raise ValueError("LazyTensors(tuple) is only valid if tuple = (ind,dim,cat) is a triplet of integers.")
@@ -151,6 +173,8 @@ class LazyTensor:
     def shape(self):
         """(batch..., M, N, D), the trailing D being dropped when it is 1 (``lazy_tensor.py:1003-1009``)."""
         s = self._shape
+        if self.is_complex:
+            s = s[:-1] + (s[-1] // 2,)
         return s[:-1] if s[-1] == 1 else s
 
     def dim(self):
@@ -200,15 +224,20 @@ class LazyTensor:
     def _wrap(self, x):
         return x if _is_lt(x) else type(self)(x)
 
-    def unary(self, operation, dimres=None, opt_arg=None, opt_arg2=None):
+    def unary(self, operation, dimres=None, opt_arg=None, opt_arg2=None, is_complex=False):
         r = self._copy_meta()
+        r.is_complex = is_complex
         r.ndim = self.ndim if dimres is None else dimres
         extra = "".join(",%s" % a for a in (opt_arg, opt_arg2) if a is not None)
         r.formula = "%s(%s%s)" % (operation, self.formula, extra)
         return r
 
-    def binary(self, other, operation, is_operator=False, dimres=None, dimcheck="sameor1", opt_arg=None, opt_pos="last"):
+    def binary(self, other, operation, is_operator=False, dimres=None, dimcheck="sameor1", opt_arg=None, opt_pos="last",
+               is_complex=False, rversion=False):
         other = self._wrap(other)
+        if rversion:                     # "other <op> self" (lazy_tensor.py:540-545)
+            return other.binary(self, operation, is_operator=is_operator, dimres=dimres, dimcheck=dimcheck, opt_arg=opt_arg,
+                                opt_pos=opt_pos, is_complex=is_complex)
         if dimres is None:
             dimres = max(self.ndim, other.ndim)
         if dimcheck == "same" and self.ndim != other.ndim:
@@ -217,6 +246,7 @@ class LazyTensor:
             raise ValueError("Operation %s expects inputs of the same dimension or dimension 1. Received %d and %d."
                              % (operation, self.ndim, other.ndim))
         r = self._join(other)
+        r.is_complex = is_complex
         r.ndim = dimres
         if is_operator:
             r.formula = "(%s %s %s)" % (self.formula, operation, other.formula)
@@ -244,64 +274,154 @@ class LazyTensor:
     # ------------------------------------------------------------------------------------------
     # arithmetic
     # ------------------------------------------------------------------------------------------
+    # The four arithmetic operators dispatch on complex operands the way the reference does (lazy_tensor.py:1023-1175,
+    # 2775-2807): a real operand meeting a complex one is promoted (real2complex) -- except in a product, where a real
+    # scalar factor becomes ComplexRealScal; python complex numbers become complex parameter LazyTensors.
+    def _addop(self, other, **kw):
+        if self.is_complex:
+            other = self._wrap(other)
+            if not other.is_complex:
+                return self._addop(other.real2complex(), **kw)
+            return self.binary(other, "ComplexAdd", is_complex=True, dimcheck=None, **kw)
+        return self.binary(other, "+", is_operator=True, **kw)
+
+    def _subop(self, other, **kw):
+        if self.is_complex:
+            other = self._wrap(other)
+            if not other.is_complex:
+                return self._subop(other.real2complex(), **kw)
+            return self.binary(other, "ComplexSubtract", is_complex=True, dimcheck=None, **kw)
+        return self.binary(other, "-", is_operator=True, **kw)
+
+    def _mulop(self, other, **kw):
+        if self.is_complex:
+            other = self._wrap(other)
+            if other._shape[-1] == 1:
+                return other.binary(self, "ComplexRealScal", is_complex=True, **kw)
+            if not other.is_complex:
+                return self._mulop(other.real2complex(), **kw)
+            return self.binary(other, "ComplexMult", is_complex=True, dimcheck=None, **kw)
+        return self.binary(other, "*", is_operator=True, **kw)
+
+    def _divop(self, other, **kw):
+        if self.is_complex:
+            other = self._wrap(other)
+            if not other.is_complex:
+                return self._divop(other.real2complex(), **kw)
+            return self.binary(other, "ComplexDivide", is_complex=True, dimcheck=None, **kw)
+        return self.binary(other, "/", is_operator=True, **kw)
+
+    def _other_is_complex(self, other):
+        return _is_lt(other) and other.is_complex
+
     def __add__(self, other):
-        if isinstance(other, (int, float)) and other == 0:
+        if _is_scalar(other, 0):
             return self
-        return self.binary(other, "+", is_operator=True)
+        if self._other_is_complex(other) and not self.is_complex:
+            return self.real2complex()._addop(other)
+        return self._addop(other)
 
     def __radd__(self, other):
-        if isinstance(other, (int, float)) and other == 0:
+        if _is_scalar(other, 0):
             return self
-        return self._wrap(other).binary(self, "+", is_operator=True)
+        return self._addop(other, rversion=True)
 
     def __sub__(self, other):
-        if isinstance(other, (int, float)) and other == 0:
+        if _is_scalar(other, 0):
             return self
-        return self.binary(other, "-", is_operator=True)
+        if self._other_is_complex(other) and not self.is_complex:
+            return self.real2complex()._subop(other)
+        return self._subop(other)
 
     def __rsub__(self, other):
-        if isinstance(other, (int, float)) and other == 0:
-            return -self
-        return self._wrap(other).binary(self, "-", is_operator=True)
+        if _is_scalar(other, 0):
+            return self.unary("Minus")
+        return self._subop(other, rversion=True)
 
     def __mul__(self, other):
-        if isinstance(other, (int, float)):
-            if other == 0:
-                return 0
-            if other == 1:
-                return self
-            if other == -1:
-                return -self
-        return self.binary(other, "*", is_operator=True)
+        if _is_scalar(other, 0):
+            return 0
+        if _is_scalar(other, 1):
+            return self
+        if _is_scalar(other, -1):
+            return self.unary("Minus")
+        if self._other_is_complex(other) and not self.is_complex:
+            return other._mulop(self)
+        if _detect_complex(other) and not self.is_complex:
+            return type(self)(other)._mulop(self)
+        return self._mulop(other)
 
     def __rmul__(self, other):
-        if isinstance(other, (int, float)):
-            if other == 0:
-                return 0
-            if other == 1:
-                return self
-            if other == -1:
-                return -self
-        return self._wrap(other).binary(self, "*", is_operator=True)
+        if _is_scalar(other, 0):
+            return 0
+        if _is_scalar(other, 1):
+            return self
+        if _is_scalar(other, -1):
+            return self.unary("Minus")
+        if _detect_complex(other) and not self.is_complex:
+            return self.real2complex()._mulop(type(self)(other))
+        return self._mulop(other, rversion=True)
 
     def __truediv__(self, other):
-        if isinstance(other, (int, float)) and other == 1:
+        if _is_scalar(other, 1):
             return self
-        return self.binary(other, "/", is_operator=True)
+        if self._other_is_complex(other) and not self.is_complex:
+            return self.real2complex()._divop(other)
+        return self._divop(other)
 
     def __rtruediv__(self, other):
-        if isinstance(other, (int, float)):
-            if other == 0:
-                return 0
-            if other == 1:
-                return self.unary("Inv")
-        return self._wrap(other).binary(self, "/", is_operator=True)
+        if _is_scalar(other, 0):
+            return 0
+        if _is_scalar(other, 1):
+            return self.unary("Inv")
+        return self._divop(other, rversion=True)
 
     def __neg__(self):
         return self.unary("Minus")
 
     def __abs__(self):
+        if self.is_complex:
+            return self.unary("ComplexAbs", dimres=self.ndim // 2)
         return self.unary("Abs")
+
+    # ---- complex numbers (lazy_tensor.py:1357-1400, 2669-2823) ----------------------------------
+    def _need_complex(self, what):
+        if not self.is_complex:
+            raise ValueError("%s is only defined for complex LazyTensors." % what)
+
+    def _need_real(self, what):
+        if self.is_complex:
+            raise ValueError("%s cannot be applied to a complex LazyTensor." % what)
+
+    @property
+    def real(self):
+        self._need_complex("real")
+        return self.unary("ComplexReal", dimres=self.ndim // 2)
+
+    @property
+    def imag(self):
+        self._need_complex("imag")
+        return self.unary("ComplexImag", dimres=self.ndim // 2)
+
+    def angle(self):
+        self._need_complex("angle")
+        return self.unary("ComplexAngle", dimres=self.ndim // 2)
+
+    def conj(self):
+        self._need_complex("conj")
+        return self.unary("Conj", dimres=self.ndim, is_complex=True)
+
+    def real2complex(self):
+        self._need_real("real2complex")
+        return self.unary("Real2Complex", dimres=2 * self.ndim, is_complex=True)
+
+    def imag2complex(self):
+        self._need_real("imag2complex")
+        return self.unary("Imag2Complex", dimres=2 * self.ndim, is_complex=True)
+
+    def exp1j(self):
+        self._need_real("exp1j")
+        return self.unary("ComplexExp1j", dimres=2 * self.ndim, is_complex=True)
 
     def abs(self):
         return abs(self)
@@ -351,7 +471,7 @@ class LazyTensor:
     __hash__ = object.__hash__
 
     # ---- element-wise math -------------------------------------------------------------------
-    def exp(self): return self.unary("Exp")
+    def exp(self): return self.unary("ComplexExp", dimres=self.ndim, is_complex=True) if self.is_complex else self.unary("Exp")
     def log(self): return self.unary("Log")
     def xlogx(self): return self.unary("XLogX")
     def cos(self): return self.unary("Cos")
@@ -477,6 +597,11 @@ class LazyTensor:
         return self.ternary(other, gamma, "SoftDTW_SqDist", dimres=1)
 
     def keops_tensordot(self, other, dimfa, dimfb, contfa, contfb, *args):
+        if self.is_complex or (_is_lt(other) and other.is_complex):
+            raise ValueError("keops_tensordot is not implemented for complex LazyTensors")
+        return self._keops_tensordot(other, dimfa, dimfb, contfa, contfb, *args)
+
+    def _keops_tensordot(self, other, dimfa, dimfb, contfa, contfb, *args):
         """Tensor contraction over paired axes of the internal dimension, viewed as row-major tensors of shapes ``dimfa``
         and ``dimfb``; an optional last argument permutes the kept axes (``lazy_tensor.py:1816-1849``)."""
         def seq(v):
@@ -557,6 +682,7 @@ class LazyTensor:
             r.formula2 = o.formula
         r.formula = self.formula
         r.ndim = self.ndim
+        r.is_complex = self.is_complex
         r.reduction_op = reduction_op
         r.axis = axis - self.nbatchdims
         r.opt_arg = opt_arg
@@ -624,7 +750,15 @@ class LazyTensor:
             if args != ():
                 raise ValueError("no input required")
             args = (self.other.variables[0],)
-        return self.callfun(*args, *self.variables, **self.kwargs)
+        res = self.callfun(*args, *self.variables, **self.kwargs)
+        return self._view_as_complex(res) if self.is_complex else res
+
+    @staticmethod
+    def _view_as_complex(res):
+        """interleaved (re, im) pairs -> complex tensor (``pykeops/pykeops/torch/utils.py:107-113``)"""
+        if isinstance(res, torch.Tensor) and not torch.is_complex(res):
+            return torch.view_as_complex(res.reshape(tuple(res.shape[:-1]) + (res.shape[-1] // 2, 2)).contiguous())
+        return res
 
     def __str__(self):
         tail = ""
@@ -639,6 +773,8 @@ class LazyTensor:
         if dim is not None:
             axis = dim
         if axis in (-1, 2 + self.nbatchdims):
+            if self.is_complex:
+                return self.unary("ComplexSum", dimres=2, is_complex=True)
             return self.unary("Sum", dimres=1)
         return self.reduction("Sum", axis=axis, **kwargs)
 
@@ -789,6 +925,14 @@ class LazyTensor:
     def sinc(self):
         """``sin(pi x) / (pi x)`` (``lazy_tensor.py:1267-1274``)."""
         return (math.pi * self).sinxdivx()
+
+
+class ComplexLazyTensor(LazyTensor):
+    """``ComplexLazyTensor(x)``: a LazyTensor forced to be complex (``lazy_tensor.py:2669-2687``).  Complex-ness is a flag of
+    :class:`LazyTensor` here, so this constructor simply returns ``LazyTensor(x, axis, is_complex=True)``."""
+
+    def __new__(cls, x=None, axis=None):
+        return LazyTensor(x, axis, is_complex=True)
 
 
 def Vi(x_or_ind, dim=None):

@@ -46,6 +46,11 @@ EXPRS = {
     # (grad_matrix is left out: the reference's method formats the LazyTensor object itself into the string,
     #  lazy_tensor.py:2001-2005, so there is no valid reference string to compare with)
     "bspline_softdtw": "A.bspline(s, 2).sum(-1) + A.bspline(b).sum(-1) + x.softdtw_sqdist(y, p) + A.softdtw_sqdist(x, 0.5)",
+    # complex LazyTensors: z (Vj, 2 complex numbers), w (Vi, 2 complex numbers), c (Vi, one complex number)
+    "cplx_arith": "z * w + z / w - w * c + (z - c) * b",
+    "cplx_mixed": "z * b + x.real2complex().sum(-1) * c + (b * z) - y.extract(0, 2).imag2complex() + z * (p * b).exp1j()",
+    "cplx_parts": "z.real * w.imag + abs(z) + z.angle() + (z.conj() * w).real + z.exp().imag + (z * w).sum(-1).real",
+    "cplx_python_scalars": "(2j * b) * z + (b * (1 + 2j)) * z + (-2 * 3.14 * 1j * p * b).exp() * z",
     "tensordot": "A.keops_tensordot(x, (3, 3), (3,), (1,), (0,)).sum(-1) + x.keops_tensordot(y, (3,), (3,), (), (), (1, 0)).sum(-1)",
     "kron": "A.keops_kron(x.tensorprod(y), [3, 3], [3, 3]).sum(-1) + x.keops_kron(y, (3,), (3,)).sum(-1)",
     "factorize": "((-x.sqdist(y)).exp() + (-x.sqdist(y)).exp() * b).factorize((-x.sqdist(y)).exp())",
@@ -72,7 +77,8 @@ REDUCTIONS = {
 
 
 def symbols(LT):
-    return dict(x=LT((0, 3, 0)), y=LT((1, 3, 1)), b=LT((2, 1, 1)), p=LT((3, 1, 2)), A=LT((4, 9, 1)), s=LT((5, 1, 0)), LT=LT)
+    return dict(x=LT((0, 3, 0)), y=LT((1, 3, 1)), b=LT((2, 1, 1)), p=LT((3, 1, 2)), A=LT((4, 9, 1)), s=LT((5, 1, 0)), LT=LT,
+                z=LT((6, 4, 1), is_complex=True), w=LT((7, 4, 0), is_complex=True), c=LT((8, 2, 0), is_complex=True))
 
 
 def build(LT):
@@ -80,7 +86,8 @@ def build(LT):
     out = {}
     for name, src in EXPRS.items():
         f = eval(src, dict(env))
-        out["expr:" + name] = dict(src=src, formula=f.formula.replace("VarSymb", "Var"), ndim=int(f.ndim))
+        out["expr:" + name] = dict(src=src, formula=f.formula.replace("VarSymb", "Var"), ndim=int(f.ndim),
+                                   is_complex=bool(getattr(f, "is_complex", False)), shape=list(f.shape))
     for name, (expr, method, kw) in REDUCTIONS.items():
         f = eval(EXPRS[expr], dict(env))
         kw = dict(kw)

@@ -46,6 +46,7 @@ def _same_tree(a, b):
 def test_expression_maps_to_the_reference_operation_tree(key, ours):
     ref, got = RECORDED[key], ours[key]
     assert got["ndim"] == ref["ndim"], (got, ref)
+    assert got["is_complex"] == ref["is_complex"] and got["shape"] == ref["shape"], (got, ref)
     assert _same_tree(got["formula"], ref["formula"]), "\nours: %s\nref:  %s" % (got["formula"], ref["formula"])
 
 

@@ -579,3 +579,33 @@ def test_host_tensors_and_the_multi_gpu_thread_pattern(api, cuda_device):
     if not AGAINST_REFERENCE:
         with pytest.raises(ValueError):
             gauss_kernel_sum(x.to(cuda_device), y)                       # mixed memory locations
+
+
+def test_complex_lazytensors_nonuniform_fourier_sum(api, cuda_device):
+    # test_complex.py: X_k = sum_n x_n exp(-2 i pi p_n f_k) with complex x -- complex tensors are carried as interleaved
+    # (re, im) pairs, python complex scalars become complex parameters; plus real / imag / abs / conj and the gradient
+    # with respect to the complex signal
+    torch.manual_seed(0)
+    M, N = 300, 400
+    x = torch.rand(1, N, 1, dtype=torch.complex64, device=cuda_device, requires_grad=True)
+    p = torch.rand(1, N, 1, dtype=torch.float32, device=cuda_device)
+    f = torch.rand(M, 1, 1, dtype=torch.float32, device=cuda_device)
+
+    def fun(x, p, f, lazy):
+        if lazy:
+            x, p, f = api.LazyTensor(x), api.LazyTensor(p), api.LazyTensor(f)
+        return (x * (-2 * math.pi * 1j * p * f).exp()).sum(dim=1)
+
+    got, ref = fun(x, p, f, True).squeeze(), fun(x, p, f, False).squeeze()
+    assert got.dtype == torch.complex64 and got.shape == ref.shape == (M,)
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
+    X, P, F = api.LazyTensor(x), api.LazyTensor(p), api.LazyTensor(f)
+    K = X * (P * F).exp1j()
+    assert torch.allclose((K.real * K.imag + abs(K)).sum(dim=1).squeeze(),
+                          ((x * torch.exp(1j * p * f)).real * (x * torch.exp(1j * p * f)).imag + (x * torch.exp(1j * p * f)).abs()).sum(1).squeeze(),
+                          rtol=1e-4, atol=1e-4)
+    assert torch.allclose((K.conj() * X).sum(dim=1).squeeze(), ((x * torch.exp(1j * p * f)).conj() * x).sum(1).squeeze(), rtol=1e-4, atol=1e-4)
+    if not AGAINST_REFERENCE:       # the reference's own backward test is commented out (test_complex.py:45-58)
+        g1 = torch.autograd.grad((got.real ** 2 + got.imag ** 2).sum(), [x])[0]
+        g2 = torch.autograd.grad((ref.real ** 2 + ref.imag ** 2).sum(), [x])[0]
+        assert torch.allclose(g1, g2, rtol=1e-3, atol=1e-3 * g2.abs().max().item())
