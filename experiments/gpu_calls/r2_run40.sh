@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call 40: full GPU suite (with the TensorDot / Kron / SoftDTW / BSpline cases and the extended reference suite), smoke, bench N=1
+# round 2, GPU calls 40 and 46: full GPU suite (with the TensorDot / Kron / SoftDTW / BSpline / complex cases and the extended reference suite), smoke, bench N=1
 mkdir -p gpurun_out
 echo "== pytest -m gpu (all)"
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "rc=$?"
