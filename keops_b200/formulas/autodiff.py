@@ -86,6 +86,68 @@ def laplacian(f: Node, v: Node) -> Node:
     return divergence(grad(f, v, ir.IntCst(1)), v)
 
 
+_LINEAR_IF_ALL = frozenset(("Add", "Subtract", "Minus", "Sum", "SumT", "Extract", "ExtractT", "Concat"))
+_LINEAR_IF_ONE = frozenset(("Mult", "Scalprod", "MatVecMult", "VecMatMult", "TensorProd", "TensorDot"))
+
+
+def is_linear(f: Node, v: Node) -> bool:
+    """Structural linearity of ``f`` in the variable ``v``, by the reference's rules (``formulas/Operation.py:16-27`` and the
+    ``linearity_type`` of each operation: sums need every term linear, products exactly one factor, quotients the numerator)."""
+    if f.op == "Var":
+        return f is v
+    if f.op == "Zero":
+        return True
+    if f.op in _LINEAR_IF_ALL:
+        return all(is_linear(a, v) for a in f.args)
+    if f.op in _LINEAR_IF_ONE:
+        return sum(is_linear(a, v) for a in f.args) == 1
+    if f.op == "Divide":
+        return is_linear(f.args[0], v)
+    return False
+
+
+def adjoint_operator(f: Node, v: Node, u: Node) -> Node:
+    """``AdjointOperator(f, v, u)``: for ``f`` linear in ``v`` (matrix ``M``, ``f.dim x v.dim``), the vector ``M^T u``
+    (``keopscore/keopscore/formulas/LinearOperators/AdjointOperator.py``).  The adjoint of a linear map is its transposed
+    Jacobian applied to ``u``: the reverse-mode gradient."""
+    if v.op != "Var":
+        raise FormulaError("can only take the adjoint with respect to a Var")
+    if not is_linear(f, v):
+        raise FormulaError("Formula is not linear with respect to variable.")
+    if u.dim != f.dim:
+        raise FormulaError("AdjointOperator: the argument has dimension %d, the formula has dimension %d" % (u.dim, f.dim))
+    return grad(f, v, u)
+
+
+def trace_operator(f: Node, v: Node, w: Node = None) -> Node:
+    """``TraceOperator(f, v, w=1)`` for ``f`` linear in ``v`` with matrix ``M`` (``LinearOperators/TraceOperator.py:30-52``):
+    ``f.dim == v.dim``: ``tr(diag(w) M)`` (``w * tr(M)`` for a scalar ``w``); ``f.dim == 1`` (``M`` is a row): ``sum_i w_i M_i``.
+    Entries of ``M`` are read off the transposed Jacobian: ``M_kk = [M^T e_k]_k``, ``M_i = [M^T 1]_i``."""
+    if v.op != "Var":
+        raise FormulaError("can only take the trace with respect to a Var")
+    if not is_linear(f, v):
+        raise FormulaError("Formula is not linear with respect to variable.")
+    d = v.dim
+    wdim = 1 if w is None else w.dim
+    if wdim not in (1, d):
+        raise FormulaError("Dimension of argument w should be 1 or equal dimension of v.")
+    if f.dim not in (1, d):
+        raise FormulaError("Output dimension should be 1 or %d (%s, dim %d)." % (d, f.op, f.dim))
+    if f.dim == 1:
+        row = grad(f, v, ir.IntCst(1))                                   # M^T 1 = the row itself
+        if w is None:
+            return ir.Sum(row)
+        return ir.Mult(w, ir.Sum(row)) if wdim == 1 and d > 1 else ir.Sum(ir.Mult(w, row))
+    total = None
+    for k in range(d):
+        m_kk = ir.Elem(grad(f, v, ir.ElemT(ir.IntCst(1), d, k)), k)
+        if w is not None and wdim == d:
+            m_kk = ir.Mult(ir.Elem(w, k), m_kk)
+        total = m_kk if total is None else ir.Add(total, m_kk)
+    return ir.Mult(w, total) if (w is not None and wdim == 1) else total
+
+
+
 def _grad(f: Node, v: Node, g: Node, memo: Dict[Tuple[int, int], Node]) -> Node:
     if g.is_zero or not _depends(f, v):
         return ir.Zero(v.dim)

@@ -154,6 +154,18 @@ class _Interp(ast.NodeVisitor):
             from . import autodiff as _ad
             fn_ = {"Divergence": _ad.divergence, "Laplacian": _ad.laplacian, "GradMatrix": _ad.grad_matrix}[name]
             return fn_(args[0], ir.as_node(args[1]))
+        if name in ("TraceOperator", "AdjointOperator") and args and isinstance(args[0], Node):
+            # symbolic operators on a formula that is linear in a (placeholder) variable -- the variable disappears from the
+            # result (keopscore/keopscore/formulas/LinearOperators/, lazy_tensor.py:2007-2037)
+            from . import autodiff as _ad
+            rest = [ir.as_node(a) for a in args[1:]]
+            if name == "AdjointOperator":
+                if len(rest) != 2:
+                    raise FormulaError("AdjointOperator(f, v, u) expects three arguments")
+                return _ad.adjoint_operator(args[0], *rest)
+            if len(rest) not in (1, 2):
+                raise FormulaError("TraceOperator(f, v[, w]) expects two or three arguments")
+            return _ad.trace_operator(args[0], *rest)
         if name == "Diff" and args and isinstance(args[0], Node):
             if len(args) != 3:
                 raise FormulaError("Diff(f, v, u) expects three arguments")

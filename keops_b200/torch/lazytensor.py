@@ -582,6 +582,18 @@ class LazyTensor:
         other = self._wrap(other)
         return self.binary(other, "TensorProd", dimres=self.ndim * other.ndim, dimcheck=None)
 
+    def trace_operator(self, var):
+        """Symbolic trace of ``self``, a linear function of the symbolic variable ``var`` (``lazy_tensor.py:2007-2037``).  The
+        variable disappears from the result: it leaves the list of symbolic variables and its index is made negative so that
+        it is never mistaken for an argument."""
+        if not _is_lt(var) or len(var.symbolic_variables) != 1 or not hasattr(var, "ind"):
+            raise ValueError("trace_operator expects a symbolic variable, e.g. Vi(2, 3).")
+        res = self.binary(var, "TraceOperator", dimres=1, dimcheck="same")
+        res.symbolic_variables = tuple(v for v in res.symbolic_variables if v not in var.symbolic_variables)
+        if var.ind >= 0:
+            res.formula = res.formula.replace(var.formula, "VarSymb(-%d-1,%d,%d)" % (var.ind, var.ndim, var.axis))
+        return res
+
     def bspline(self, x, k=0):
         """Vector of B-spline basis functions of order ``k`` for the knots ``self``, evaluated at the scalar ``x``
         (``lazy_tensor.py:1706-1714``)."""

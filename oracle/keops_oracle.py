@@ -1075,6 +1075,71 @@ class ComplexSumT(Op):
     def difft(self, v, g): return self.children[0].difft(v, ComplexSum(g))
 
 
+# ---- symbolic operators on a formula that is linear in a placeholder variable (formulas/LinearOperators/*.py).  Restated
+# numerically: the matrix M of v -> f(v) is read off column by column by evaluating f at the basis vectors e_k.
+class _EnvWith:
+    def __init__(self, env, ind, arr):
+        self._env, self._ind, self._arr = env, ind, arr
+    def __getattr__(self, name):
+        return getattr(self._env, name)
+    def var(self, v):
+        return self._arr if v.ind == self._ind else self._env.var(v)
+
+
+class _LinearOperator(Op):
+    def _columns(self, env):
+        f, v = self.f, self.v
+        for k in range(v.dim):
+            e_k = np.zeros((1, 1, v.dim), dtype=env.dtype)
+            e_k[..., k] = 1
+            yield k, f.ev(_EnvWith(env, v.ind, e_k))                              # column k of M, shape (..., f.dim)
+    def vars(self):
+        out = dict(self.f.vars())
+        out.pop(self.v.ind, None)
+        for c in self.children:
+            out.update(c.vars())
+        return out
+    def difft(self, v, g):
+        raise ValueError("differentiation through TraceOperator / AdjointOperator is not restated in the oracle")
+
+
+class _TraceOperator(_LinearOperator):
+    """TraceOperator.py:30-52: f.dim == v.dim: tr(diag(w) M); f.dim == 1: sum_i w_i M_i (w scalar or of size v.dim)."""
+    def __init__(self, f, v, w=1):
+        self.f, self.v = f, v
+        self.w = None if (isinstance(w, int) and w == 1) else _w(w)
+        assert f.dim in (1, v.dim) and (self.w is None or self.w.dim in (1, v.dim))
+        self.children = () if self.w is None else (self.w,)
+        self.dim = 1
+    def ev(self, env):
+        w = None if self.w is None else self.w.ev(env)
+        total = 0
+        for k, col in self._columns(env):
+            term = col[..., k] if self.f.dim == self.v.dim and self.v.dim > 1 else col[..., 0]
+            if w is not None:
+                term = term * (w[..., k] if w.shape[-1] > 1 else w[..., 0])
+            total = total + term
+        return np.asarray(total, dtype=env.dtype)[..., None]
+
+
+class _AdjointOperator(_LinearOperator):
+    """AdjointOperator.py: (M^T u)_k = <column k of M, u>."""
+    def __init__(self, f, v, u):
+        self.f, self.v, self.u = f, v, _w(u)
+        assert self.u.dim == f.dim
+        self.children = (self.u,)
+        self.dim = v.dim
+    def ev(self, env):
+        u = self.u.ev(env)
+        cols = [(col * u).sum(-1) for _, col in self._columns(env)]
+        shape = np.broadcast_shapes(*[c.shape for c in cols])
+        return np.stack([np.broadcast_to(c, shape) for c in cols], axis=-1).astype(env.dtype)
+
+
+def TraceOperator(f, v, w=1): return _TraceOperator(f, v, w)
+def AdjointOperator(f, v, u): return _AdjointOperator(f, v, u)
+
+
 def Elem(a, m): return Extract(a, m, 1)
 def ElemT(a, n, m): return ExtractT(a, m, n)
 def SqNorm2(a): return Sum(Square(a))                                            # maths/SqNorm2.py

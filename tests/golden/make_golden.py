@@ -276,6 +276,22 @@ for nm, f in CPLX.items():
                  aliases=CPLX_ALI + ["Var(4,DIMOUT,0)", "Var(5,DIMOUT,0)"], sizes=(23, 31))
 
 
+# ---- symbolic operators on formulas that are linear in a placeholder variable u = Var(4,3,0), which disappears from the
+# result (formulas/LinearOperators/TraceOperator.py, AdjointOperator.py; LazyTensor.trace_operator)
+LINOP_ALI = ["A=Vj(0,9)", "b=Vj(1,1)", "x=Vi(2,3)", "y=Vj(3,3)", "u=Vi(4,3)"]
+LINOP_ARGS = [(9, 1, "n"), (1, 1, "p"), (3, 0, "n"), (3, 1, "n")]
+LINOP = {
+    "trace_diag": "TraceOperator((x*u)*b-u,u)*y+TraceOperator(u/(IntCst(1)+SqDist(x,y)),u)",
+    "trace_weighted": "TraceOperator(u*y+SumT(Sum(u*x),3),u,x*y)",
+    "trace_row": "TraceOperator((x|u)*b,u)+TraceOperator(Sum(u*y),u,y)",
+    "trace_scalar_weight": "TraceOperator(u*Exp(-SqDist(x,y)),u,b)",
+    "adjoint": "AdjointOperator((x*u)*b,u,y)+AdjointOperator((u|y)*x,u,x)+AdjointOperator(x*u-u/b,u,y)",
+    "adjoint_row": "AdjointOperator(Sum(u*x)*b,u,b)+AdjointOperator(u*y+SumT(Sum(u*x),3),u,y)",
+}
+for nm, f in LINOP.items():
+    case("linop_" + nm, "Sum_Reduction(%s,0)" % f, LINOP_ARGS, dtypes=("float64",), aliases=LINOP_ALI, sizes=(23, 31))
+
+
 def flags(formula):
     head = formula.split("(")[0]
     sumlike = head in ("Sum_Reduction", "Max_SumShiftExp_Reduction", "Max_SumShiftExpWeight_Reduction",
@@ -302,7 +318,7 @@ def main():
     for c in CASES:
         if only and not any(o in c["name"] for o in only):
             continue
-        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_", "td_", "sdtw_", "bspline_", "cplx_")):
+        if c["name"].startswith(("fm_", "dop_", "op2_", "op2grad_", "so_", "ssw_", "ties_", "td_", "sdtw_", "bspline_", "cplx_", "linop_")):
             import zlib
             rng = np.random.default_rng(zlib.crc32(c["name"].encode()))
         dt = np.dtype(c["dtype"])

@@ -51,6 +51,7 @@ EXPRS = {
     "cplx_mixed": "z * b + x.real2complex().sum(-1) * c + (b * z) - y.extract(0, 2).imag2complex() + z * (p * b).exp1j()",
     "cplx_parts": "z.real * w.imag + abs(z) + z.angle() + (z.conj() * w).real + z.exp().imag + (z * w).sum(-1).real",
     "cplx_python_scalars": "(2j * b) * z + (b * (1 + 2j)) * z + (-2 * 3.14 * 1j * p * b).exp() * z",
+    "trace_operator": "(x * s + x / (1 + y.sqnorm2())).trace_operator(x)",
     "tensordot": "A.keops_tensordot(x, (3, 3), (3,), (1,), (0,)).sum(-1) + x.keops_tensordot(y, (3,), (3,), (), (), (1, 0)).sum(-1)",
     "kron": "A.keops_kron(x.tensorprod(y), [3, 3], [3, 3]).sum(-1) + x.keops_kron(y, (3,), (3,)).sum(-1)",
     "factorize": "((-x.sqdist(y)).exp() + (-x.sqdist(y)).exp() * b).factorize((-x.sqdist(y)).exp())",

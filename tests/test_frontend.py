@@ -402,3 +402,29 @@ def test_product_regrouping_terminates_with_one_row_side_and_two_streamed_factor
     got = dag_eval.evaluate("Grad_WithSavedForward(Sum_Reduction(Divide(Var(0,3,0),Var(1,3,1)),0),Var(1,3,1),Var(2,3,0),Var(3,3,0))",
                             [], [x, y, e, e], "float64", fast=True)
     np.testing.assert_allclose(got, -(e[:, None, :] * x[:, None, :] / y[None, :, :] ** 2).sum(0), rtol=1e-12)
+
+
+def test_linear_operators_rules():
+    """``TraceOperator`` / ``AdjointOperator`` (keopscore/keopscore/formulas/LinearOperators/): linearity is checked by the
+    reference's structural rules, the placeholder variable disappears, and the results agree with the explicit matrix."""
+    from keops_b200.formulas import autodiff, ir
+    from keops_b200.formulas.parser import parse_formula, FormulaError
+    al = ["A=Vj(0,9)", "x=Vi(1,3)", "u=Vi(2,3)"]
+    t = parse_formula("TraceOperator(MatVecMult(A,u),u)", al)               # (the reference has no rule for MatVecMult here)
+    assert [v.params[0] for v in t.variables()] == [0]
+    rng = np.random.default_rng(5)
+    A, x = rng.standard_normal((6, 9)), rng.standard_normal((4, 3))
+    got = dag_eval.evaluate("Sum_Reduction(TraceOperator(MatVecMult(A,u),u)+Sum(AdjointOperator(MatVecMult(A,u),u,x)),1)", al, [A, x],
+                            "float64")
+    M = A.reshape(6, 3, 3)
+    # Sum over i (4 rows) of tr(M_j) + sum_k (M_j^T x_i)_k, one value per j
+    want = np.trace(M, axis1=1, axis2=2)[:, None] * 4 + np.einsum("jkl,ik->j", M, x)[:, None]
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    for bad in ("TraceOperator(u*u,u)", "TraceOperator(Exp(u),u)", "TraceOperator(u+x,u)", "AdjointOperator(Square(u),u,x)"):
+        with pytest.raises(FormulaError, match="not linear"):
+            parse_formula(bad, al)
+    with pytest.raises(FormulaError):
+        parse_formula("TraceOperator(Concat(u,u),u)", al)                    # output dimension neither 1 nor dim(u)
+    with pytest.raises(FormulaError):
+        parse_formula("AdjointOperator(u*x,u,A)", al)                        # argument of the wrong size
+    assert autodiff.is_linear(parse_formula("u/Sum(x)-SumT(Sum(u*x),3)", al), ir.Var(2, 3, 0))
