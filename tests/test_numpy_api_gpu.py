@@ -170,3 +170,27 @@ def test_non_contiguous_inputs_and_inplace_out(kn):
     ret = K.__matmul__(w, out=a)
     assert ret is a
     assert np.abs(a - np.exp(-((x - y) ** 2).sum(-1)) @ w).max() <= 1e-5
+
+
+def test_kron_tensordot_and_complex_on_numpy_arrays(kn):
+    # test_kron.py / test_complex_numpy.py: the contraction operators and complex LazyTensors through the numpy front-end
+    rng = np.random.default_rng(0)
+    M, N = 11, 150
+    dimfa, dimfb = [2, 3], [2, 2]
+    x, y = rng.random((M, 6)), rng.random((N, 4))
+    ref = np.stack([sum(np.kron(x[i].reshape(dimfa), y[j].reshape(dimfb)).ravel() for j in range(N)) for i in range(M)])
+    out = kn.LazyTensor(x[:, None, :]).keops_kron(kn.LazyTensor(y[None, :, :]), dimfa, dimfb).sum(axis=1)
+    assert isinstance(out, np.ndarray) and out.shape == (M, 24) and np.allclose(out, ref, atol=1e-10)
+    al = ["x=Vi(0,6)", "y=Vj(1,4)"]
+    o2 = kn.Genred("TensorDot(x, y, [2, 3], [2, 2], [], [], [0, 2, 1, 3])", al, reduction_op="Sum", axis=1)(x, y)
+    assert np.allclose(o2, ref, atol=1e-10)
+    a = rng.random((4, 7)); b = rng.random(7)
+    C = kn.LazyTensor(a.reshape(1, 1, 28)).keops_tensordot(kn.LazyTensor(b.reshape(1, 1, 7)), (4, 7), (7,), (1,), (0,)).sum_reduction(axis=1)
+    assert np.allclose(C.ravel(), a @ b)
+    # non-uniform Fourier sum with a complex signal
+    z = (rng.random((1, N, 1)) + 1j * rng.random((1, N, 1))).astype("complex64")
+    p, f = rng.random((1, N, 1)).astype("float32"), rng.random((M, 1, 1)).astype("float32")
+    Z, P, F = kn.LazyTensor(z), kn.LazyTensor(p), kn.LazyTensor(f)
+    got = (Z * (-2 * np.pi * 1j * P * F).exp()).sum(axis=1)
+    want = (z * np.exp(-2 * np.pi * 1j * p * f)).sum(axis=1)
+    assert got.dtype == np.complex64 and np.allclose(got.ravel(), want.ravel(), rtol=1e-4, atol=1e-4)
