@@ -22,8 +22,10 @@ CHILD = r'''
 import json, os, runpy, sys, types
 from unittest import mock
 for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors", "matplotlib.animation", "imageio",
-             "mpl_toolkits", "mpl_toolkits.mplot3d", "mpl_toolkits.axes_grid1", "seaborn", "plotly", "plotly.graph_objs"):
+             "mpl_toolkits", "mpl_toolkits.mplot3d", "mpl_toolkits.axes_grid1", "seaborn", "plotly", "plotly.graph_objs",
+             "si_prefix"):
     sys.modules[name] = mock.MagicMock()
+sys.path.insert(0, os.path.dirname(os.path.abspath(sys.argv[1])))      # sibling helper modules (benchmarks/benchmark_utils.py)
 import torch
 import pykeops
 from pykeops.common import keops_io
@@ -39,8 +41,10 @@ def shim(tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id, formula, alia
             b = kb.LoadKeOpsB200(1, 0, 1, use_ranges, -1, formula, list(aliases), nargs, dtype, lang, dict(flags))
             if os.environ.get("KB200_ACCEPT_COMPILE") and not b.ks.is_zero:
                 plan.get_cubin(b.ks, bool(b.params.use_fast_math) and dtype == "float32")
+            print("ACCEPTED " + formula[:200], flush=True)
         except Exception as e:
             rejected.append([formula[:300], list(aliases), dtype, repr(e)[:300]])
+            print("REJECTED " + json.dumps(rejected[-1]), flush=True)
     return real(tagCPUGPU, tag1D2D, tagHostDevice, use_ranges, device_id, formula, aliases, nargs, dtype, lang, flags)
 shim.reset = getattr(real, "reset", lambda *a, **k: None)
 keops_io.keops_binder["cpp"] = shim
@@ -80,7 +84,9 @@ def main(argv):
                                                            "rejected": []}
         except subprocess.TimeoutExpired as e:
             out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
-            rec = {"status": "timeout after %d s" % timeout, "requests": out.count("Generating code"), "rejected": []}
+            rej = [json.loads(l[9:]) for l in out.splitlines() if l.startswith("REJECTED ")]
+            rec = {"status": "timeout after %d s (requests up to then)" % timeout,
+                   "requests": sum(l.startswith(("ACCEPTED ", "REJECTED ")) for l in out.splitlines()), "rejected": rej}
         rec["script"] = rel
         print(json.dumps(rec), flush=True)
         total["scripts"] += 1
